@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE ONLY.  Generate tests/golden/*.npz from the reference.
+
+Run in the authoring container (where /root/reference is mounted):
+
+    python oracle/make_golden.py
+
+Every vector written here is produced by the *unmodified* reference code
+(imported through oracle/refshim.py) on the reference's own test fixtures
+(test/picard/*.csv, test/formats/*.cnr|cnn) or on seeded synthetic inputs.
+The files are small, committed, and are what pins the oracle restatements in
+oracle/ (tests -m "not gpu") and the CUDA path (tests -m gpu) on the GPU box,
+where /root/reference does not exist.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import refshim  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+NUMERIC = ("start", "end", "log2", "depth", "weight", "gc", "rmask", "spread", "probes")
+
+
+def table_arrays(cna, prefix):
+    """Flatten a reference CopyNumArray into {prefix_col: ndarray}."""
+    out = {}
+    df = cna.data
+    for col in df.columns:
+        v = df[col].to_numpy()
+        if col in ("chromosome", "gene"):
+            v = np.asarray(v, dtype=str)
+        out[f"{prefix}__{col}"] = v
+    out[f"{prefix}__columns"] = np.asarray(list(df.columns), dtype=str)
+    return out
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.0f} KiB, {len(arrays)} arrays)")
+
+
+# ---------------------------------------------------------------------------
+def gen_smoothing(R):
+    """smoothing.rolling_median / rolling_quantile / savgol known answers."""
+    rng = np.random.default_rng(20261019)
+    arrays = {}
+    cases = []
+    for i, (n, width) in enumerate(
+        [(2, 0.5), (5, 0.3), (57, 0.1), (100, 3), (1000, 0.05), (1000, 51), (4097, 0.02),
+         (18759, 0.0073), (18759, 0.1), (30000, 0.01), (30000, 0.5)]
+    ):
+        x = rng.normal(0, 1, n)
+        if i % 3 == 1:  # heavy ties
+            x = np.round(x, 1)
+        y = R.smoothing.rolling_median(x, width)
+        arrays[f"rm{i}_x"] = x
+        arrays[f"rm{i}_y"] = y
+        cases.append((n, float(width)))
+    arrays["rm_cases"] = np.asarray(cases)
+    # NaN-bearing input (pandas skips NaN, min_periods=1, even counts averaged)
+    x = rng.normal(0, 1, 500)
+    x[rng.integers(0, 500, 60)] = np.nan
+    arrays["rm_nan_x"] = x
+    arrays["rm_nan_y"] = R.smoothing.rolling_median(x, 0.05)
+    # rolling_quantile as used by drop_outliers: width 50, q .95
+    for i, n in enumerate((51, 73, 500, 4000)):
+        x = np.abs(rng.normal(0, 1, n))
+        arrays[f"rq{i}_x"] = x
+        arrays[f"rq{i}_y"] = R.smoothing.rolling_quantile(x, 50, 0.95)
+    # savgol trend as used by drop_outliers (total_width=50)
+    for i, n in enumerate((51, 73, 500, 4000)):
+        x = rng.normal(0, 1, n) + np.sin(np.arange(n) / 30.0)
+        arrays[f"sg{i}_x"] = x
+        arrays[f"sg{i}_y"] = R.smoothing.savgol(x, 50)
+        arrays[f"sg{i}_mask"] = np.asarray(R.smoothing.rolling_outlier_quantile(x, 50, 0.95, 3))
+    save("smoothing", **arrays)
+
+
+# ---------------------------------------------------------------------------
+def gen_regression(R):
+    """import-picard -> do_reference -> do_fix -> do_segmentation('haar').
+
+    Mirrors test/test_regression.py:91-126 and also records the intermediate
+    center_by_window / rolling_median / edge-bias calls of do_fix.
+    """
+    picard = os.path.join(R.root, "test", "picard")
+    normals = ("p2-5_5", "p2-9_5", "p2-20_5")
+    sample = "p2-9_2"
+    arrays = {}
+    with tempfile.TemporaryDirectory() as tmp:
+
+        def to_cnn(sid, kind):
+            path = os.path.join(tmp, f"{sid}.{kind}coverage.cnn")
+            garr = R.importers.do_import_picard(os.path.join(picard, f"{sid}.{kind}coverage.csv"))
+            R.tabio.write(garr, path)
+            return path
+
+        tfn = [to_cnn(s, "target") for s in normals]
+        afn = [to_cnn(s, "antitarget") for s in normals]
+        for s, t, a in zip(normals, tfn, afn):
+            arrays.update(table_arrays(R.read_cna(t), f"normal_{s}_target"))
+            arrays.update(table_arrays(R.read_cna(a), f"normal_{s}_antitarget"))
+
+        # capture the matrices that feed summarize_info
+        captured = {}
+        orig_summarize = R.reference.summarize_info
+
+        def spy_summarize(all_logr, all_depths):
+            captured["all_logr"] = np.array(all_logr)
+            captured["all_depths"] = np.array(all_depths)
+            return orig_summarize(all_logr, all_depths)
+
+        R.reference.summarize_info = spy_summarize
+        try:
+            ref = R.reference.do_reference(tfn, afn, is_haploid_x_reference=True)
+        finally:
+            R.reference.summarize_info = orig_summarize
+        arrays["ref_all_logr"] = captured["all_logr"]
+        arrays["ref_all_depths"] = captured["all_depths"]
+        stats = orig_summarize(captured["all_logr"], captured["all_depths"])
+        for k, v in stats.items():
+            arrays[f"ref_summary_{k}"] = np.asarray(v)
+        arrays.update(table_arrays(ref, "reference"))
+        tgt = R.read_cna(to_cnn(sample, "target"))
+        anti = R.read_cna(to_cnn(sample, "antitarget"))
+    arrays.update(table_arrays(tgt, "sample_target"))
+    arrays.update(table_arrays(anti, "sample_antitarget"))
+
+    # spy on center_by_window + edge bias inside do_fix
+    cbw_calls = []
+    orig_cbw = R.fix.center_by_window
+    orig_edge = R.fix.get_edge_bias
+
+    def spy_cbw(cnarr, fraction, sort_key, bias_smoother="median"):
+        before = cnarr["log2"].to_numpy().copy()
+        key = np.asarray(sort_key, dtype=float).copy()
+        out = orig_cbw(cnarr, fraction, sort_key, bias_smoother=bias_smoother)
+        cbw_calls.append((before, key, float(fraction), out["log2"].to_numpy().copy()))
+        return out
+
+    edge_calls = []
+
+    def spy_edge(cnarr, margin):
+        out = orig_edge(cnarr, margin)
+        edge_calls.append(
+            (
+                np.asarray(cnarr.chromosome, dtype=str),
+                cnarr.start.to_numpy().copy(),
+                cnarr.end.to_numpy().copy(),
+                np.asarray(out, dtype=float).copy(),
+            )
+        )
+        return out
+
+    R.fix.center_by_window = spy_cbw
+    R.fix.get_edge_bias = spy_edge
+    try:
+        cnr = R.fix.do_fix(tgt, anti, ref)
+    finally:
+        R.fix.center_by_window = orig_cbw
+        R.fix.get_edge_bias = orig_edge
+    for i, (b, k, f, o) in enumerate(cbw_calls):
+        arrays[f"cbw{i}_before"] = b
+        arrays[f"cbw{i}_key"] = k
+        arrays[f"cbw{i}_fraction"] = np.asarray(f)
+        arrays[f"cbw{i}_after"] = o
+    arrays["cbw_ncalls"] = np.asarray(len(cbw_calls))
+    for i, (c, s, e, o) in enumerate(edge_calls):
+        arrays[f"edge{i}_chromosome"] = c
+        arrays[f"edge{i}_start"] = s
+        arrays[f"edge{i}_end"] = e
+        arrays[f"edge{i}_bias"] = o
+    arrays["edge_ncalls"] = np.asarray(len(edge_calls))
+    arrays.update(table_arrays(cnr, "cnr"))
+    cns = R.segmentation.do_segmentation(cnr, "haar")
+    arrays.update(table_arrays(cns, "cns_haar"))
+    # no-outlier-filter variant isolates haar + transfer_fields from drop_outliers
+    cns2 = R.segmentation.do_segmentation(cnr, "haar", skip_outliers=0)
+    arrays.update(table_arrays(cns2, "cns_haar_nooutlier"))
+    save("regression", **arrays)
+
+
+# ---------------------------------------------------------------------------
+def gen_haar(R):
+    """Per-arm HaarSeg internals on test/formats/p2-20_1.cnr + KATs."""
+    cnr = R.read_cna(os.path.join(R.root, "test", "formats", "p2-20_1.cnr"))
+    arrays = table_arrays(cnr, "cnr")
+    offsets = [0]
+    arm_chrom = []
+    for chrom, arm in cnr.by_arm():
+        offsets.append(offsets[-1] + len(arm))
+        arm_chrom.append(chrom)
+    arrays["arm_offsets"] = np.asarray(offsets)
+    arrays["arm_chrom"] = np.asarray(arm_chrom, dtype=str)
+    H = R.haar
+    log2 = cnr["log2"].to_numpy()
+    wt = cnr["weight"].to_numpy()
+    bp_w, bp_u, n_w, n_u = [], [], [0], [0]
+    mean_w, mean_u = [], []
+    for a in range(len(arm_chrom)):
+        lo, hi = offsets[a], offsets[a + 1]
+        rw = H.haarSeg(log2[lo:hi], 1e-4, weights=wt[lo:hi])
+        ru = H.haarSeg(log2[lo:hi], 1e-4)
+        bp_w.extend(rw["start"].tolist())
+        mean_w.extend(rw["mean"].tolist())
+        n_w.append(len(bp_w))
+        bp_u.extend(ru["start"].tolist())
+        mean_u.extend(ru["mean"].tolist())
+        n_u.append(len(bp_u))
+    arrays["w_seg_start"] = np.asarray(bp_w)
+    arrays["w_seg_mean"] = np.asarray(mean_w)
+    arrays["w_seg_offsets"] = np.asarray(n_w)
+    arrays["u_seg_start"] = np.asarray(bp_u)
+    arrays["u_seg_mean"] = np.asarray(mean_u)
+    arrays["u_seg_offsets"] = np.asarray(n_u)
+    # a looser q so that more breakpoints/levels are exercised
+    bp_q, n_q = [], [0]
+    for a in range(len(arm_chrom)):
+        lo, hi = offsets[a], offsets[a + 1]
+        r = H.haarSeg(log2[lo:hi], 0.05, weights=wt[lo:hi])
+        bp_q.extend(r["start"].tolist())
+        n_q.append(len(bp_q))
+    arrays["q05_seg_start"] = np.asarray(bp_q)
+    arrays["q05_seg_offsets"] = np.asarray(n_q)
+    # conv + peaks of the largest arm, each level
+    sizes = np.diff(offsets)
+    a = int(np.argmax(sizes))
+    lo, hi = offsets[a], offsets[a + 1]
+    arrays["big_arm"] = np.asarray(a)
+    for level in range(1, 6):
+        h = 2**level
+        cw_ = H.HaarConv(log2[lo:hi], wt[lo:hi], h)
+        cu_ = H.HaarConv(log2[lo:hi], None, h)
+        arrays[f"conv_w_L{level}"] = cw_
+        arrays[f"conv_u_L{level}"] = cu_
+        arrays[f"peaks_w_L{level}"] = H.FindLocalPeaks(cw_)
+        arrays[f"peaks_u_L{level}"] = H.FindLocalPeaks(cu_)
+    arrays["conv_u_L0"] = H.HaarConv(log2[lo:hi], None, 1)
+    # full driver outputs
+    arrays.update(table_arrays(R.segmentation.do_segmentation(cnr, "haar"), "cns_haar"))
+    arrays.update(
+        table_arrays(R.segmentation.do_segmentation(cnr, "haar", threshold=0.01, skip_low=True), "cns_haar_t01")
+    )
+    # drop_outliers mask per arm (width 50, factor 10 and a stricter factor 3)
+    masks10, masks3 = [], []
+    for _chrom, arm in cnr.by_arm():
+        for factor, dest in ((10, masks10), (3, masks3)):
+            parts = [
+                np.asarray(R.smoothing.rolling_outlier_quantile(sub["log2"], 50, 0.95, factor))
+                for _c, sub in arm.by_chromosome()
+            ]
+            dest.append(np.concatenate(parts))
+    arrays["outlier_mask_f10"] = np.concatenate(masks10)
+    arrays["outlier_mask_f3"] = np.concatenate(masks3)
+    # KATs of test/test_haar.py:219-230 (planted steps)
+    rng = np.random.default_rng(7)
+    sig = np.concatenate([np.zeros(100), np.full(100, -2.0), np.full(100, -2.3)]) + rng.normal(0, 0.05, 300)
+    r = H.haarSeg(sig, 1e-4)
+    arrays["kat_signal"] = sig
+    arrays["kat_start"] = r["start"]
+    arrays["kat_mean"] = r["mean"]
+    # FDRThres edge cases
+    x = rng.normal(0, 1, 400)
+    x[:10] *= 8
+    arrays["fdr_x"] = x
+    arrays["fdr_T"] = np.asarray([H.FDRThres(x, q, 1.0) for q in (1e-4, 1e-2, 0.2, 0.5)], dtype=float)
+    save("haar", **arrays)
+
+
+# ---------------------------------------------------------------------------
+def gen_fix_units(R):
+    """Unit-level vectors: center_all, mask_bad_bins, apply_weights, biweight."""
+    rng = np.random.default_rng(99)
+    arrays = {}
+    ref = R.read_cna(os.path.join(R.root, "test", "formats", "reference-tr.cnn"))
+    arrays.update(table_arrays(ref, "ref_tr"))
+    arrays["ref_tr_badmask"] = np.asarray(R.fix.mask_bad_bins(ref))
+    # biweight location / midvariance on assorted vectors
+    vecs = [rng.normal(0, 1, n) for n in (2, 3, 4, 7, 8, 9, 33, 257, 1000)]
+    vecs.append(np.r_[rng.normal(0, 1, 50), 40.0, -35.0])
+    vecs.append(np.r_[np.zeros(30), rng.normal(0, 1, 10)])  # MAD == 0
+    vecs.append(np.full(9, 3.25))
+    for i, v in enumerate(vecs):
+        arrays[f"bw{i}_x"] = v
+        arrays[f"bw{i}_loc"] = np.asarray(R.descriptives.biweight_location(v))
+        arrays[f"bw{i}_var"] = np.asarray(R.descriptives.biweight_midvariance(v))
+        arrays[f"bw{i}_var_init0"] = np.asarray(R.descriptives.biweight_midvariance(v, initial=0.1))
+    arrays["bw_n"] = np.asarray(len(vecs))
+    # center_all on a real .cnr, skip_low on/off
+    cnr = R.read_cna(os.path.join(R.root, "test", "formats", "p2-20_2.cnr"))
+    arrays.update(table_arrays(cnr, "cnr2"))
+    for skip in (False, True):
+        c = cnr.copy()
+        c.data["log2"] = c.data["log2"] + 0.37
+        c.center_all(skip_low=skip)
+        arrays[f"cnr2_centered_skip{int(skip)}"] = c["log2"].to_numpy()
+    save("fix_units", **arrays)
+
+
+def main():
+    logging.basicConfig(level=logging.ERROR)
+    os.makedirs(OUT, exist_ok=True)
+    R = refshim.load()
+    which = sys.argv[1:] or ["smoothing", "regression", "haar", "fix_units"]
+    for w in which:
+        globals()["gen_" + w](R)
+
+
+if __name__ == "__main__":
+    main()
