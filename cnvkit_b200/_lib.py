@@ -1,0 +1,93 @@
+"""ctypes binding of libcnvkit_b200.so (the C ABI declared in include/cnvkit_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the
+caller gets an exception.  Build it with ``python -c "import __graft_entry__ as g; g.build()"``
+or ``make -C cnvkit_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint32, c_uint64, c_ulonglong, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcnvkit_b200.so")
+
+_lib = None
+
+c_double_p = POINTER(c_double)
+c_int64_p = POINTER(c_int64)
+c_int32_p = POINTER(c_int32)
+c_uint32_p = POINTER(c_uint32)
+
+# name -> (restype, argtypes); must list every symbol include/cnvkit_b200.h declares.
+SIGNATURES = {
+    "cnvk_last_error": (c_char_p, []),
+    "cnvk_abi_version": (c_int, []),
+    "cnvk_launch_count": (c_ulonglong, []),
+    "cnvk_device_info": (c_int, [c_int, POINTER(c_int), POINTER(c_uint64), POINTER(c_uint64)]),
+    "cnvk_rolling_median_dev": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "cnvk_rolling_median": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
+    "cnvk_rolling_quantile_dev": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p]),
+    "cnvk_rolling_quantile": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p]),
+    "cnvk_argsort_f64_dev": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+}
+
+
+class CnvkError(RuntimeError):
+    """A libcnvkit_b200 call failed (CUDA error or bad arguments)."""
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: the CUDA library is not built. "
+                "Run `make -C cnvkit_b200/csrc` (needs nvcc); there is no CPU fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().cnvk_last_error().decode(errors="replace")
+        raise CnvkError(f"{what} failed (rc={rc}): {msg}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)
+
+
+def launch_count() -> int:
+    return int(load().cnvk_launch_count())
+
+
+def f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def ptr(a: np.ndarray) -> int:
+    """Host pointer of a contiguous numpy array (0 for None)."""
+    return 0 if a is None else a.ctypes.data
+
+
+def stream_ptr(stream=None) -> int:
+    """cudaStream_t of a torch stream (or torch's current stream), as an int."""
+    import torch
+
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return int(stream.cuda_stream)

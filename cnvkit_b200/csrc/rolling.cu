@@ -1,0 +1,283 @@
+// Mirror-padded centred rolling median / quantile, exact order statistics.
+//
+// Replaces cnvlib/smoothing.py:77-87 (rolling_median) and :135-141 (rolling_quantile), i.e.
+// pandas' Series.rolling(2*wing+1, min_periods, center=True).median()/.quantile(q) over the
+// `_pad_array` mirror padding (smoothing.py:72-74).
+//
+// Design (window-size independent, O(n log n), all HBM/L2 traffic coalesced or L2-resident):
+//   1. rank transform: stable radix argsort of the n values -> every element gets a distinct
+//      rank in [0,n); NaN keys sort last, so ranks >= n_valid are the NaNs pandas skips.
+//   2. the padded rank sequence (length M = n + 2*wing, mirrored indices) is indexed by a
+//      wavelet matrix: per bit level one bitvector + per-word cumulative popcount directory.
+//   3. one thread per output walks the ceil(log2 n) levels (two directory reads per level) to
+//      find the k-th smallest rank inside its window, then maps rank -> value through the
+//      sorted value table.  Selecting an *element* keeps the result bit-exact; even valid
+//      counts (only possible when NaNs are present) average the two middle elements as
+//      pandas' roll_median_c does.
+#include "prims.cuh"
+
+namespace cnvk {
+
+static const int WM_BLOCK = 1024;  // elements per build block (32 words)
+
+__global__ void count_valid_kernel(const u64* __restrict__ sorted_keys, long long n, u32* __restrict__ nvalid) {
+    // sorted ascending with NaN == ~0 last: n_valid = first index holding ~0
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const bool me = sorted_keys[i] == ~0ull;
+        const bool prev = (i > 0) && (sorted_keys[i - 1] == ~0ull);
+        if (me && !prev) *nvalid = (u32)i;
+    }
+}
+
+__global__ void rank_tables_kernel(const double* __restrict__ x, const u32* __restrict__ order, long long n,
+                                   double* __restrict__ sorted_vals, u32* __restrict__ rank) {
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) {
+        const u32 src = order[p];
+        sorted_vals[p] = x[src];
+        rank[src] = (u32)p;
+    }
+}
+
+// padded position -> source index, per smoothing._pad_array
+__device__ __forceinline__ long long mirror_index(long long t, long long n, long long wing) {
+    if (t < wing) return wing - 1 - t;
+    if (t < wing + n) return t - wing;
+    return n - 1 - (t - wing - n);
+}
+
+__global__ void padded_ranks_kernel(const u32* __restrict__ rank, long long n, long long wing,
+                                    u32* __restrict__ seq, long long M) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < M) seq[t] = rank[mirror_index(t, n, wing)];
+}
+
+__global__ void __launch_bounds__(WM_BLOCK)
+wm_count_kernel(const u32* __restrict__ seq, long long M, int bit, u32* __restrict__ block_ones) {
+    __shared__ u32 s_cnt[32];
+    const long long t = (long long)blockIdx.x * WM_BLOCK + threadIdx.x;
+    const bool b = (t < M) && ((seq[t] >> bit) & 1u);
+    const u32 word = __ballot_sync(0xffffffffu, b);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_cnt[warp] = __popc(word);
+    __syncthreads();
+    if (warp == 0) {
+        u32 c = warp_sum_u32(s_cnt[lane]);
+        if (lane == 0) block_ones[blockIdx.x] = c;
+    }
+}
+
+__global__ void __launch_bounds__(WM_BLOCK)
+wm_scatter_kernel(const u32* __restrict__ seq, u32* __restrict__ seq_out, long long M, int bit,
+                  const u32* __restrict__ block_prefix, const u32* __restrict__ total_ones,
+                  uint2* __restrict__ dir, u32* __restrict__ zeros_out, long long nwords) {
+    __shared__ u32 s_cnt[32];
+    const long long t = (long long)blockIdx.x * WM_BLOCK + threadIdx.x;
+    const bool in = t < M;
+    const u32 v = in ? seq[t] : 0u;
+    const bool b = in && ((v >> bit) & 1u);
+    const u32 word = __ballot_sync(0xffffffffu, b);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_cnt[warp] = __popc(word);
+    __syncthreads();
+    if (warp == 0) {
+        u32 c = s_cnt[lane];
+        u32 inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        s_cnt[lane] = inc - c;
+    }
+    __syncthreads();
+    const u32 ones_total = *total_ones;
+    const u32 Z = (u32)M - ones_total;
+    const u32 cum = block_prefix[blockIdx.x] + s_cnt[warp];  // ones before this word
+    const long long w = t >> 5;
+    if (lane == 0 && w < nwords) dir[w] = make_uint2(word, cum);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        dir[nwords] = make_uint2(0u, ones_total);
+        *zeros_out = Z;
+    }
+    if (in) {
+        const u32 ones_before = cum + __popc(word & ((1u << lane) - 1u));
+        const u32 pos = b ? (Z + ones_before) : ((u32)t - ones_before);
+        seq_out[pos] = v;
+    }
+}
+
+struct WmView {
+    const uint2* dir;    // [levels][stride]
+    const u32* zeros;    // [levels]
+    long long stride;
+    int levels;
+};
+
+__device__ __forceinline__ u32 wm_rank1(const uint2* __restrict__ d, u32 p) {
+    const uint2 e = d[p >> 5];
+    return e.y + __popc(e.x & ((1u << (p & 31u)) - 1u));
+}
+
+// k-th smallest (0-based) value in seq[l, r)
+__device__ __forceinline__ u32 wm_kth(const WmView& wm, u32 l, u32 r, u32 k) {
+    u32 val = 0;
+    for (int lev = 0; lev < wm.levels; ++lev) {
+        const uint2* d = wm.dir + (size_t)lev * wm.stride;
+        const u32 ol = wm_rank1(d, l), orr = wm_rank1(d, r);
+        const u32 zl = l - ol, zr = r - orr;
+        const u32 c0 = zr - zl;
+        val <<= 1;
+        if (k < c0) {
+            l = zl;
+            r = zr;
+        } else {
+            k -= c0;
+            const u32 Z = wm.zeros[lev];
+            l = Z + ol;
+            r = Z + orr;
+            val |= 1u;
+        }
+    }
+    return val;
+}
+
+// number of values < v in seq[l, r)
+__device__ __forceinline__ u32 wm_count_lt(const WmView& wm, u32 l, u32 r, u32 v) {
+    if (wm.levels < 32 && (v >> wm.levels)) return r - l;
+    u32 cnt = 0;
+    for (int lev = 0; lev < wm.levels; ++lev) {
+        const uint2* d = wm.dir + (size_t)lev * wm.stride;
+        const u32 ol = wm_rank1(d, l), orr = wm_rank1(d, r);
+        const u32 zl = l - ol, zr = r - orr;
+        if ((v >> (wm.levels - 1 - lev)) & 1u) {
+            cnt += zr - zl;
+            const u32 Z = wm.zeros[lev];
+            l = Z + ol;
+            r = Z + orr;
+        } else {
+            l = zl;
+            r = zr;
+        }
+    }
+    return cnt;
+}
+
+// mode 0: median (pandas roll_median_c), mode 1: linear-interpolated quantile (roll_quantile)
+__global__ void __launch_bounds__(256)
+wm_window_query_kernel(WmView wm, const double* __restrict__ sorted_vals, const u32* __restrict__ nvalid_p,
+                       long long n, long long wing, int mode, double q, int min_periods,
+                       double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 l = (u32)i, r = (u32)(i + 2 * wing + 1);
+    const u32 nvalid = *nvalid_p;
+    u32 c = r - l;
+    if (nvalid < (u32)n) c = wm_count_lt(wm, l, r, nvalid);
+    double res;
+    if (c == 0 || (int)c < min_periods) {
+        res = __longlong_as_double(0x7ff8000000000000ll);
+    } else if (mode == 0) {
+        const u32 mid = c >> 1;
+        const double a = sorted_vals[wm_kth(wm, l, r, mid)];
+        if (c & 1u) {
+            res = a;
+        } else {
+            const double b = sorted_vals[wm_kth(wm, l, r, mid - 1)];
+            res = (a + b) / 2.0;
+        }
+    } else {
+        const double idxf = q * (double)(c - 1);
+        const u32 idx = (u32)idxf;
+        const double vlow = sorted_vals[wm_kth(wm, l, r, idx)];
+        if (idxf == (double)idx) {
+            res = vlow;
+        } else {
+            const double vhigh = sorted_vals[wm_kth(wm, l, r, idx + 1)];
+            res = __dadd_rn(vlow, __dmul_rn(__dsub_rn(vhigh, vlow), __dsub_rn(idxf, (double)idx)));
+        }
+    }
+    out[i] = res;
+}
+
+int rolling_window_stat(const double* d_x, long long n, long long wing, int mode, double q, int min_periods,
+                        double* d_out, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    if (n < 2 || wing < 1 || wing > n - 1) {
+        set_last_error("rolling_window_stat: need n >= 2 and 1 <= wing <= n-1 (n=%lld wing=%lld)", n, wing);
+        return -2;
+    }
+    const long long M = n + 2 * wing;
+    if (M >= (1ll << 31)) {
+        set_last_error("rolling_window_stat: padded length %lld too large", M);
+        return -2;
+    }
+    Scratch scratch(stream);
+    // 1. rank transform
+    u64 *k0, *k1;
+    u32 *v0, *v1;
+    CNVK_CHECK(scratch.alloc(&k0, (size_t)n));
+    CNVK_CHECK(scratch.alloc(&k1, (size_t)n));
+    CNVK_CHECK(scratch.alloc(&v0, (size_t)n));
+    CNVK_CHECK(scratch.alloc(&v1, (size_t)n));
+    int rc = make_sort_keys(d_x, n, k0, v0, stream);
+    if (rc) return rc;
+    u64* sk;
+    u32* order;
+    rc = radix_sort_pairs(k0, k1, v0, v1, n, 0, 64, &sk, &order, stream);
+    if (rc) return rc;
+    u32* nvalid;
+    CNVK_CHECK(scratch.alloc(&nvalid, 1));
+    const u32 n32 = (u32)n;
+    CNVK_CHECK(cudaMemcpyAsync(nvalid, &n32, sizeof(u32), cudaMemcpyHostToDevice, stream));
+    count_valid_kernel<<<div_up(n, 256), 256, 0, stream>>>(sk, n, nvalid);
+    CNVK_LAUNCH_CHECK();
+    double* sorted_vals;
+    u32* rank;
+    CNVK_CHECK(scratch.alloc(&sorted_vals, (size_t)n));
+    CNVK_CHECK(scratch.alloc(&rank, (size_t)n));
+    rank_tables_kernel<<<div_up(n, 256), 256, 0, stream>>>(d_x, order, n, sorted_vals, rank);
+    CNVK_LAUNCH_CHECK();
+    // 2. wavelet matrix over the padded rank sequence
+    int levels = 1;
+    while ((1ll << levels) < n) ++levels;
+    const long long nwords = (M + 31) / 32;
+    const long long stride = nwords + 1;
+    const int nblocks = div_up(M, WM_BLOCK);
+    u32 *seq0, *seq1, *block_ones, *total_ones, *zeros;
+    uint2* dir;
+    CNVK_CHECK(scratch.alloc(&seq0, (size_t)M));
+    CNVK_CHECK(scratch.alloc(&seq1, (size_t)M));
+    CNVK_CHECK(scratch.alloc(&block_ones, (size_t)nblocks));
+    CNVK_CHECK(scratch.alloc(&total_ones, 1));
+    CNVK_CHECK(scratch.alloc(&zeros, (size_t)levels));
+    CNVK_CHECK(scratch.alloc(&dir, (size_t)levels * stride));
+    padded_ranks_kernel<<<div_up(M, 256), 256, 0, stream>>>(rank, n, wing, seq0, M);
+    CNVK_LAUNCH_CHECK();
+    u32* sin = seq0;
+    u32* sout = seq1;
+    for (int lev = 0; lev < levels; ++lev) {
+        const int bit = levels - 1 - lev;
+        wm_count_kernel<<<nblocks, WM_BLOCK, 0, stream>>>(sin, M, bit, block_ones);
+        CNVK_LAUNCH_CHECK();
+        rc = exclusive_scan_u32(block_ones, block_ones, nblocks, total_ones, stream);
+        if (rc) return rc;
+        wm_scatter_kernel<<<nblocks, WM_BLOCK, 0, stream>>>(sin, sout, M, bit, block_ones, total_ones,
+                                                             dir + (size_t)lev * stride, zeros + lev, nwords);
+        CNVK_LAUNCH_CHECK();
+        u32* t = sin; sin = sout; sout = t;
+    }
+    // 3. queries
+    WmView wm;
+    wm.dir = dir;
+    wm.zeros = zeros;
+    wm.stride = stride;
+    wm.levels = levels;
+    wm_window_query_kernel<<<div_up(n, 256), 256, 0, stream>>>(wm, sorted_vals, nvalid, n, wing, mode, q,
+                                                               min_periods, d_out);
+    CNVK_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace cnvk
