@@ -33,7 +33,41 @@ SIGNATURES = {
     "cnvk_rolling_quantile_dev": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p]),
     "cnvk_rolling_quantile": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p]),
     "cnvk_argsort_f64_dev": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "cnvk_cbs_segment_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cnvk_cbs_segment": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cnvk_cbs_getbdry": (c_int, [c_double, c_int32, c_int32, c_void_p]),
 }
+
+
+class CbsParams(ctypes.Structure):
+    """cnvk_cbs_params (include/cnvkit_b200.h)."""
+
+    _fields_ = [
+        ("alpha", c_double),
+        ("nperm", c_int32),
+        ("min_width", c_int32),
+        ("kmax", c_int32),
+        ("nmin", c_int32),
+        ("eta", c_double),
+        ("hybrid", c_int32),
+        ("prune", c_int32),
+        ("seed", c_uint64),
+    ]
+
+
+class CbsStats(ctypes.Structure):
+    """cnvk_cbs_stats (include/cnvkit_b200.h)."""
+
+    _fields_ = [
+        (k, c_int64)
+        for k in ("nodes", "levels", "obs_subtiles_total", "obs_subtiles_scanned", "obs_arcs", "perm_arcs",
+                  "perm_nodes", "perms_run", "flank_perm_tests")
+    ]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
 class CnvkError(RuntimeError):

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 
 #include "../../include/cnvkit_b200.h"
+#include <vector>
+
 #include "ops.cuh"
 
 namespace cnvk {
@@ -104,6 +106,62 @@ int cnvk_rolling_quantile(const double* x, int64_t n, int64_t wing, double q, do
 
 int cnvk_argsort_f64_dev(const double* d_x, int64_t n, uint32_t* d_order, void* stream) {
     return argsort_f64(d_x, n, d_order, (cudaStream_t)stream);
+}
+
+static int cbs_common(const double* d_x, const double* d_w, const int64_t* arm_offsets, int32_t n_arms,
+                      const cnvk_cbs_params* p, int64_t capacity, int32_t* seg_arm, int64_t* seg_lo,
+                      int64_t* seg_hi, double* seg_mean, int64_t* n_segs, cnvk_cbs_stats* stats,
+                      cudaStream_t stream) {
+    CbsParams P;
+    P.alpha = p->alpha; P.nperm = p->nperm; P.min_width = p->min_width; P.kmax = p->kmax; P.nmin = p->nmin;
+    P.eta = p->eta; P.hybrid = p->hybrid; P.prune = p->prune; P.seed = p->seed;
+    std::vector<long long> off(arm_offsets, arm_offsets + n_arms + 1);
+    std::vector<CbsSeg> segs;
+    CbsStats st;
+    RC(cbs_segment(d_x, d_w, off.data(), n_arms, P, segs, &st, stream));
+    if ((int64_t)segs.size() > capacity) {
+        set_last_error("cnvk_cbs_segment: %zu segments exceed capacity %lld", segs.size(), (long long)capacity);
+        return -4;
+    }
+    for (size_t s = 0; s < segs.size(); ++s) {
+        seg_arm[s] = segs[s].arm; seg_lo[s] = segs[s].lo; seg_hi[s] = segs[s].hi; seg_mean[s] = segs[s].mean;
+    }
+    *n_segs = (int64_t)segs.size();
+    if (stats) {
+        stats->nodes = st.nodes; stats->levels = st.levels; stats->obs_subtiles_total = st.obs_subtiles_total;
+        stats->obs_subtiles_scanned = st.obs_subtiles_scanned; stats->obs_arcs = st.obs_arcs;
+        stats->perm_arcs = st.perm_arcs; stats->perm_nodes = st.perm_nodes; stats->perms_run = st.perms_run;
+        stats->flank_perm_tests = st.flank_perm_tests;
+    }
+    return 0;
+}
+
+int cnvk_cbs_segment_dev(const double* d_log2, const double* d_weight, const int64_t* arm_offsets, int32_t n_arms,
+                         const cnvk_cbs_params* params, int64_t capacity, int32_t* seg_arm, int64_t* seg_lo,
+                         int64_t* seg_hi, double* seg_mean, int64_t* n_segs, cnvk_cbs_stats* stats, void* stream) {
+    return cbs_common(d_log2, d_weight, arm_offsets, n_arms, params, capacity, seg_arm, seg_lo, seg_hi, seg_mean,
+                      n_segs, stats, (cudaStream_t)stream);
+}
+
+int cnvk_cbs_segment(const double* log2, const double* weight, const int64_t* arm_offsets, int32_t n_arms,
+                     const cnvk_cbs_params* params, int64_t capacity, int32_t* seg_arm, int64_t* seg_lo,
+                     int64_t* seg_hi, double* seg_mean, int64_t* n_segs, cnvk_cbs_stats* stats) {
+    HostCall hc;
+    RC(hc.begin());
+    const size_t N = n_arms > 0 ? (size_t)arm_offsets[n_arms] : 0;
+    double *dx, *dw;
+    RC(hc.upload(log2, N, &dx));
+    RC(hc.upload(weight, N, &dw));
+    RC(cbs_common(dx, dw, arm_offsets, n_arms, params, capacity, seg_arm, seg_lo, seg_hi, seg_mean, n_segs, stats,
+                  hc.stream));
+    return hc.finish();
+}
+
+int cnvk_cbs_getbdry(double eta, int32_t nperm, int32_t max_ones, int32_t* out) {
+    std::vector<int> b;
+    cbs_getbdry(eta, nperm, max_ones, b);
+    for (size_t k = 0; k < b.size(); ++k) out[k] = b[k];
+    return 0;
 }
 
 }  // extern "C"

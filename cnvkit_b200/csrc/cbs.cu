@@ -1,0 +1,1137 @@
+// Weighted circular binary segmentation (CBS) on B200 -- replaces the Rscript/DNAcopy
+// subprocess of cnvlib/segmentation/__init__.py:292-322 (R script cnvlib/segmentation/cbs.py:1-78,
+// i.e. DNAcopy::segment(CNA(log2,...), weights=w, alpha=threshold) with DNAcopy defaults).
+//
+// Structure (level-synchronous over ALL arms of ALL samples in the batch):
+//   prep   : one CTA per open interval ("node"): weighted centring, tss, and the strictly
+//            sequential FP64 prefix sums S_i = sum w x, cw_i = cumsum(w)/sqrt(sum w) that define
+//            the statistic's bits (one elected thread runs the add chains out of shared-memory
+//            chunks the other threads stage), per-256-point block min/max of S for pruning and a
+//            seed arc (argmin S, argmax S).
+//   scan   : persistent CTAs pull 1024x256 arc tiles from an atomic queue; every thread keeps
+//            4 arc starts in registers and streams 256 arc ends from shared memory;
+//            BSS_ij = (S_j-S_i)^2 / (c (W-c)), c = cw_j-cw_i, is compared division-free against
+//            the running best (exact IEEE division only on the rare update).  256x256 sub-tiles
+//            whose upper bound (block min/max of S, extreme c) cannot reach the node's current
+//            best are skipped -- the GPU form of DNAcopy's block-pruned wtmaxo.  Warp-shuffle
+//            argmax, then one lock-protected update of the node's (q,i,j), ties -> smallest (i,j).
+//   decide : one warp per node: T^2, the 0.1 / 7.0 shortcuts, Siegmund tail approximation
+//            (hybrid, n > nmin), and the number of exceedances tolerated.
+//   perms  : reference distribution for undecided nodes, evaluated in SM-resident tiles with
+//            counter-based permutations (cbs_rng.cuh): hybrid = circular arcs of width <= kmax
+//            (n > nmin), exact = all arcs (n <= nmin); DNAcopy's sequential stopping boundary
+//            is replayed on the exceedance flags chunk by chunk.
+//   flank  : ternary-split confirmation (wtpermp) for arcs interior to the node.
+// Host code only moves a few bytes of per-node decisions per level and builds the next frontier.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "cbs_rng.cuh"
+#include "ops.cuh"
+
+namespace cnvk {
+
+static const int CBS_BLK = 256;           // points per bound block / j-block
+static const int CBS_IW = 4;              // arc starts per thread
+static const int CBS_IBLK = CBS_BLK * CBS_IW;
+static const int PREP_CHUNK = 1024;
+static const int HYB_TP = 2048;           // arc starts per CTA in the hybrid permutation kernel
+static const int HYB_KMAX = 64;           // max supported kmax
+static const int EXACT_NMAX = 256;        // max supported nmin
+
+enum { ST_FINAL = 0, ST_SPLIT = 1, ST_PERM_HYBRID = 2, ST_PERM_EXACT = 3 };
+
+struct Node {
+    int lo, hi, base, flat;
+    double avg, tss, rsw, total;
+    double best_q;
+    int best_i, best_j;
+    int lock, state, nrejc, blk_off;
+    double ostat, ostat1;
+};
+
+struct Decision {
+    int state, nrejc, best_i, best_j;
+    double ostat;
+};
+
+struct FlankTest {
+    int node, off, n1, n2, tid, m1, s0, need_perm;
+    double rm1, xbar, ostat, pvalue;
+};
+
+__device__ __forceinline__ double pt(const double* a, int lo, int i) {
+    return i ? a[lo + i - 1] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------ prep
+__global__ void __launch_bounds__(256)
+cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const double* __restrict__ w,
+                double* __restrict__ xc, double* __restrict__ y, double* __restrict__ S,
+                double* __restrict__ cw, double* __restrict__ wn, double* __restrict__ blk_min,
+                double* __restrict__ blk_max, int al0) {
+    __shared__ double s_a[PREP_CHUNK], s_b[PREP_CHUNK], s_c[PREP_CHUNK];
+    __shared__ double s_red[64];
+    __shared__ int s_redi[64];
+    __shared__ double s_scalar[4];
+    Node nd = nodes[blockIdx.x];
+    const int lo = nd.lo, n = nd.hi - nd.lo;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // range check: isTRUE(all.equal(diff(range(x)), 0)) -> final (changepoints R code)
+    double mn = INFINITY, mx = -INFINITY;
+    for (int k = tid; k < n; k += 256) {
+        const double v = x[lo + k];
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { s_red[warp] = mn; s_red[32 + warp] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < 8; ++k) { mn = fmin(mn, s_red[k]); mx = fmax(mx, s_red[32 + k]); }
+        s_scalar[0] = mx - mn;
+    }
+    __syncthreads();
+    const bool flat = s_scalar[0] <= 1.4901161193847656e-08;
+    if (flat) {
+        if (tid == 0) {
+            nodes[blockIdx.x].flat = 1;
+            nodes[blockIdx.x].best_q = -1.0;
+        }
+        return;
+    }
+
+    // phase 1: sw, swx -- sequential chains (thread 0) over staged chunks
+    double sw = 0.0, swx = 0.0;
+    for (int c0 = 0; c0 < n; c0 += PREP_CHUNK) {
+        const int m = min(PREP_CHUNK, n - c0);
+        for (int k = tid; k < m; k += 256) {
+            const double wv = w[lo + c0 + k];
+            s_a[k] = wv;
+            s_b[k] = __dmul_rn(x[lo + c0 + k], wv);
+        }
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll 8
+            for (int k = 0; k < m; ++k) {
+                sw = __dadd_rn(sw, s_a[k]);
+                swx = __dadd_rn(swx, s_b[k]);
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        s_scalar[0] = sw;
+        s_scalar[1] = __ddiv_rn(swx, sw);
+        s_scalar[2] = sqrt(sw);
+    }
+    __syncthreads();
+    const double avg = s_scalar[1], rsw = s_scalar[2];
+
+    // phase 2: centred data, S / cumsum(w) / tss chains
+    double tss = 0.0, cs = 0.0, Srun = 0.0;
+    for (int c0 = 0; c0 < n; c0 += PREP_CHUNK) {
+        const int m = min(PREP_CHUNK, n - c0);
+        for (int k = tid; k < m; k += 256) {
+            const int g = lo + c0 + k;
+            const double wv = w[g];
+            const double c = __dsub_rn(x[g], avg);
+            const double r = sqrt(wv);
+            xc[g] = c;
+            y[g] = __dmul_rn(c, r);
+            wn[g] = __ddiv_rn(wv, rsw);
+            s_a[k] = wv;
+            s_b[k] = __dmul_rn(c, wv);                 // S term
+            s_c[k] = __dmul_rn(wv, __dmul_rn(c, c));   // tss term
+        }
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll 8
+            for (int k = 0; k < m; ++k) {
+                cs = __dadd_rn(cs, s_a[k]);
+                Srun = __dadd_rn(Srun, s_b[k]);
+                tss = __dadd_rn(tss, s_c[k]);
+                s_a[k] = cs;
+                s_b[k] = Srun;
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < m; k += 256) {
+            const int g = lo + c0 + k;
+            S[g] = s_b[k];
+            cw[g] = __ddiv_rn(s_a[k], rsw);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) s_scalar[3] = tss;
+    __syncthreads();
+    const double total = cw[lo + n - 1];
+
+    // per-block min/max of the prefix points S_0..S_n and the global argmin/argmax (seed arc)
+    const int nb = (n + 1 + CBS_BLK - 1) / CBS_BLK;
+    double gmin = INFINITY, gmax = -INFINITY;
+    int imin = 0, imax = 0;
+    for (int b = warp; b < nb; b += 8) {
+        double bmn = INFINITY, bmx = -INFINITY;
+        int bimn = 0, bimx = 0;
+        for (int k = lane; k < CBS_BLK; k += 32) {
+            const int i = b * CBS_BLK + k;
+            if (i <= n) {
+                const double v = pt(S, lo, i);
+                if (v < bmn) { bmn = v; bimn = i; }
+                if (v > bmx) { bmx = v; bimx = i; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double omn = __shfl_xor_sync(0xffffffffu, bmn, o);
+            const int oimn = __shfl_xor_sync(0xffffffffu, bimn, o);
+            const double omx = __shfl_xor_sync(0xffffffffu, bmx, o);
+            const int oimx = __shfl_xor_sync(0xffffffffu, bimx, o);
+            if (omn < bmn || (omn == bmn && oimn < bimn)) { bmn = omn; bimn = oimn; }
+            if (omx > bmx || (omx == bmx && oimx < bimx)) { bmx = omx; bimx = oimx; }
+        }
+        if (lane == 0) {
+            blk_min[nd.blk_off + b] = bmn;
+            blk_max[nd.blk_off + b] = bmx;
+        }
+        if (bmn < gmin) { gmin = bmn; imin = bimn; }
+        if (bmx > gmax) { gmax = bmx; imax = bimx; }
+    }
+    if (lane == 0) {
+        s_red[warp] = gmin; s_redi[warp] = imin;
+        s_red[32 + warp] = gmax; s_redi[32 + warp] = imax;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < 8; ++k) {
+            if (s_red[k] < gmin) { gmin = s_red[k]; imin = s_redi[k]; }
+            if (s_red[32 + k] > gmax) { gmax = s_red[32 + k]; imax = s_redi[32 + k]; }
+        }
+        Node* out = &nodes[blockIdx.x];
+        out->flat = 0;
+        out->avg = avg;
+        out->tss = s_scalar[3];
+        out->rsw = rsw;
+        out->total = total;
+        out->lock = 0;
+        // seed arc
+        const int i = min(imin, imax), j = max(imin, imax);
+        double q = -1.0;
+        int qi = 0x7fffffff, qj = 0x7fffffff;
+        if (j - i >= al0 && j - i <= n - al0) {
+            const double d = __dsub_rn(pt(S, lo, j), pt(S, lo, i));
+            const double c = __dsub_rn(pt(cw, lo, j), pt(cw, lo, i));
+            const double den = __dmul_rn(c, __dsub_rn(total, c));
+            q = __ddiv_rn(__dmul_rn(d, d), den);
+            qi = i; qj = j;
+        }
+        out->best_q = q;
+        out->best_i = qi;
+        out->best_j = qj;
+    }
+}
+
+// ------------------------------------------------------------------------------------ scan
+struct Cand {
+    double q, qlo;
+    int i, j;
+};
+
+__device__ __forceinline__ bool cand_better(double q, int i, int j, double bq, int bi, int bj) {
+    return q > bq || (q == bq && (i < bi || (i == bi && j < bj)));
+}
+
+__device__ __noinline__ void cand_update(Cand& b, double num, double den, int i, int j) {
+    const double q = __ddiv_rn(num, den);
+    if (cand_better(q, i, j, b.q, b.i, b.j)) {
+        b.q = q;
+        b.i = i;
+        b.j = j;
+        b.qlo = q * (1.0 - 1e-12);
+    }
+}
+
+template <int NA, bool MASKED>
+__device__ __forceinline__ void scan_subtiles(Cand& best, const double2* __restrict__ sj, const double* Si,
+                                              const double* ci, const int* ii, int jbase, int jcount, double total,
+                                              int n, int al0) {
+#pragma unroll 2
+    for (int jj = 0; jj < jcount; ++jj) {
+        const double2 pj = sj[jj];
+        const int j = jbase + jj;
+#pragma unroll
+        for (int r = 0; r < NA; ++r) {
+            const double d = __dsub_rn(pj.x, Si[r]);
+            const double c = __dsub_rn(pj.y, ci[r]);
+            const double den = __dmul_rn(c, __dsub_rn(total, c));
+            const double num = __dmul_rn(d, d);
+            bool hit = num > __dmul_rn(best.qlo, den);
+            if (MASKED) {
+                const int kw = j - ii[r];
+                hit = hit && (kw >= al0) && (kw <= n - al0) && (ii[r] <= n);
+            }
+            if (hit) cand_update(best, num, den, ii[r], j);
+        }
+    }
+}
+
+template <bool PRUNE>
+__global__ void __launch_bounds__(256)
+cbs_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ tile_off, int nnodes, int total_tiles,
+                int* __restrict__ tile_counter, const double* __restrict__ S, const double* __restrict__ cw,
+                const double* __restrict__ blk_min, const double* __restrict__ blk_max, int al0,
+                unsigned long long* __restrict__ stats) {
+    __shared__ double2 sj[CBS_BLK];
+    __shared__ int s_tile;
+    __shared__ double s_q[8];
+    __shared__ int s_i[8], s_j[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long my_subtiles = 0, my_checked = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(tile_counter, 1);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= total_tiles) break;
+        // node lookup
+        int a = 0, b = nnodes;
+        while (b - a > 1) {
+            const int m = (a + b) >> 1;
+            if (tile_off[m] <= tile) a = m; else b = m;
+        }
+        Node* nd = &nodes[a];
+        const int lo = nd->lo, n = nd->hi - nd->lo;
+        const int P = n + 1;
+        const int NJ = (P + CBS_BLK - 1) / CBS_BLK;
+        int t = tile - tile_off[a];
+        int ib = 0;
+        for (;;) {
+            const int cnt = NJ - CBS_IW * ib;
+            if (t < cnt) break;
+            t -= cnt;
+            ++ib;
+        }
+        const int jb = CBS_IW * ib + t;
+        const double total = nd->total;
+        const double gq = *((volatile double*)&nd->best_q);
+        const int jbase = jb * CBS_BLK;
+        const int jcount = min(CBS_BLK, P - jbase);
+        // which 256x256 sub-tiles can matter
+        unsigned act_mask = 0;
+        int na = 0;
+        bool masked = false;
+#pragma unroll
+        for (int r = 0; r < CBS_IW; ++r) {
+            const int bi = CBS_IW * ib + r;
+            const int ibase = bi * CBS_BLK;
+            if (ibase > n || bi > jb) continue;
+            const int iend = min(ibase + CBS_BLK - 1, n);
+            const int jend = jbase + jcount - 1;
+            bool need = true;
+            if (PRUNE && bi < jb && gq >= 0.0) {
+                const double d1 = blk_max[nd->blk_off + jb] - blk_min[nd->blk_off + bi];
+                const double d2 = blk_max[nd->blk_off + bi] - blk_min[nd->blk_off + jb];
+                const double dm = fmax(fabs(d1), fabs(d2));
+                const double cmin = pt(cw, lo, jbase) - pt(cw, lo, iend);
+                const double cmax = pt(cw, lo, jend) - pt(cw, lo, ibase);
+                const double f1 = cmin * (total - cmin), f2 = cmax * (total - cmax);
+                const double fmin_ = fmin(f1, f2);
+                if (fmin_ > 0.0) {
+                    const double ub = (dm * dm) / fmin_ * (1.0 + 1e-9);
+                    need = !(ub < gq);
+                }
+            }
+            if (tid == 0) ++my_checked;
+            if (!need) continue;
+            act_mask |= 1u << r;
+            ++na;
+            if (!(jbase - iend >= al0 && jend - ibase <= n - al0 && ibase + CBS_BLK - 1 <= n)) masked = true;
+        }
+        if (na == 0) continue;
+        if (tid == 0) my_subtiles += na;
+        // stage the j block
+        if (tid < jcount) sj[tid] = make_double2(pt(S, lo, jbase + tid), pt(cw, lo, jbase + tid));
+        double Si[CBS_IW], ci[CBS_IW];
+        int ii[CBS_IW];
+#pragma unroll
+        for (int r = 0; r < CBS_IW; ++r) {
+            const int slot = (int)__fns(act_mask, 0, (r < na) ? r + 1 : 1);
+            const int i = (CBS_IW * ib + slot) * CBS_BLK + tid;
+            ii[r] = i;
+            const bool ok = i <= n;
+            Si[r] = ok ? pt(S, lo, i) : 0.0;
+            ci[r] = ok ? pt(cw, lo, i) : 0.0;
+        }
+        __syncthreads();
+        Cand best;
+        best.q = gq;
+        best.qlo = gq * (1.0 - 1e-12);
+        if (gq < 0.0) best.qlo = -1.0;
+        best.i = 0x7fffffff;
+        best.j = 0x7fffffff;
+        if (masked) {
+            switch (na) {
+                case 1: scan_subtiles<1, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                case 2: scan_subtiles<2, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                case 3: scan_subtiles<3, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                default: scan_subtiles<4, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+            }
+        } else {
+            switch (na) {
+                case 1: scan_subtiles<1, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                case 2: scan_subtiles<2, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                case 3: scan_subtiles<3, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                default: scan_subtiles<4, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+            }
+        }
+        // CTA argmax (ties -> smallest (i,j)); only candidates found in this tile carry i != INT_MAX
+        double q = best.q;
+        int qi = best.i, qj = best.j;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double oq = __shfl_xor_sync(0xffffffffu, q, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, qi, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, qj, o);
+            if (cand_better(oq, oi, oj, q, qi, qj)) { q = oq; qi = oi; qj = oj; }
+        }
+        if (lane == 0) { s_q[warp] = q; s_i[warp] = qi; s_j[warp] = qj; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < 8; ++k)
+                if (cand_better(s_q[k], s_i[k], s_j[k], q, qi, qj)) { q = s_q[k]; qi = s_i[k]; qj = s_j[k]; }
+            if (qi != 0x7fffffff) {
+                while (atomicCAS(&nd->lock, 0, 1) != 0) {}
+                __threadfence();
+                const double cq = *((volatile double*)&nd->best_q);
+                const int cqi = *((volatile int*)&nd->best_i), cqj = *((volatile int*)&nd->best_j);
+                if (cand_better(q, qi, qj, cq, cqi, cqj)) {
+                    *((volatile int*)&nd->best_i) = qi;
+                    *((volatile int*)&nd->best_j) = qj;
+                    *((volatile double*)&nd->best_q) = q;
+                }
+                __threadfence();
+                atomicExch(&nd->lock, 0);
+            }
+        }
+    }
+    if (tid == 0 && stats) {
+        atomicAdd(&stats[0], my_subtiles);
+        atomicAdd(&stats[1], my_checked);
+    }
+}
+
+// ------------------------------------------------------------------------------------ decide
+__device__ __forceinline__ double pnorm_std(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
+
+__device__ double nu_dev(double x, double tol) {
+    double lnu1;
+    if (x > 0.01) {
+        lnu1 = log(2.0) - 2.0 * log(x);
+        double lnu0 = lnu1, dk = 0.0;
+        int k = 2;
+        for (int i = 0; i < k; ++i) {
+            dk += 1.0;
+            lnu1 -= 2.0 * pnorm_std(-x * sqrt(dk) / 2.0) / dk;
+        }
+        while (fabs((lnu1 - lnu0) / lnu1) > tol) {
+            lnu0 = lnu1;
+            for (int i = 0; i < k; ++i) {
+                dk += 1.0;
+                lnu1 -= 2.0 * pnorm_std(-x * sqrt(dk) / 2.0) / dk;
+            }
+            k *= 2;
+        }
+    } else {
+        lnu1 = -0.583 * x;
+    }
+    return exp(lnu1);
+}
+
+__device__ __forceinline__ double it1tsq_dev(double x, double a) {
+    double yy = x + a - 0.5;
+    double r = (8.0 * yy) / (1.0 - 4.0 * yy * yy) + 2.0 * log((1.0 + 2.0 * yy) / (1.0 - 2.0 * yy));
+    yy = x - 0.5;
+    r = r - (8.0 * yy) / (1.0 - 4.0 * yy * yy) - 2.0 * log((1.0 + 2.0 * yy) / (1.0 - 2.0 * yy));
+    return r;
+}
+
+__device__ __forceinline__ double t2_of(double bss, double tss, int n) {
+    if (tss <= bss + 0.0001) tss = bss + 1.0;
+    return bss / ((tss - bss) / ((double)n - 2.0));
+}
+
+// one warp per node
+__global__ void __launch_bounds__(128)
+cbs_decide_kernel(Node* __restrict__ nodes, int nnodes, Decision* __restrict__ dec, double alpha, int nperm,
+                  int kmax, int nmin, int hybrid_method, int ngrid, double tol) {
+    __shared__ double s_terms[4][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * 4 + warp;
+    if (idx >= nnodes) return;
+    Node* nd = &nodes[idx];
+    const int n = nd->hi - nd->lo;
+    int state = ST_FINAL, nrejc = 0;
+    double ostat = 0.0, ostat1 = 0.0;
+    const int bi = nd->best_i, bj = nd->best_j;
+    if (!nd->flat && nd->best_q >= 0.0) {
+        const double t2 = t2_of(nd->best_q, nd->tss, n);
+        ostat1 = sqrt(t2);
+        ostat = t2 * 0.99999;
+        if (ostat1 > 0.1) {
+            const int l = min(bj - bi, n - bj + bi);
+            if (ostat1 >= 7.0 && l >= 10) {
+                state = ST_SPLIT;
+            } else if (hybrid_method && n > nmin) {
+                // tailp: ngrid terms evaluated by the lanes, summed in order by lane 0
+                const double delta = ((double)kmax + 1.0) / (double)n;
+                const double dincr = (0.5 - delta) / (double)ngrid;
+                const double bsqrtm = ostat1 / sqrt((double)n);
+                for (int g = lane; g < ngrid; g += 32) {
+                    double tl = 0.5 - dincr, tt = 0.5 - 0.5 * dincr;
+                    for (int s = 0; s < g; ++s) { tl -= dincr; tt -= dincr; }  // same rounding as the serial loop
+                    const double xx = bsqrtm / sqrt(tt * (1.0 - tt));
+                    const double nux = nu_dev(xx, tol);
+                    s_terms[warp][g] = (nux * nux) * it1tsq_dev(tl, dincr);
+                }
+                __syncwarp();
+                double p = 0.0;
+                if (lane == 0) {
+                    for (int g = 0; g < ngrid; ++g) p += s_terms[warp][g];
+                    p = 9.973557e-2 * (ostat1 * ostat1 * ostat1) * exp(-(ostat1 * ostat1) / 2.0) * p;
+                    p = 2.0 * p;
+                }
+                p = __shfl_sync(0xffffffffu, p, 0);
+                if (p > alpha) {
+                    state = ST_FINAL;
+                } else {
+                    state = ST_PERM_HYBRID;
+                    nrejc = (int)((alpha - p) * (double)nperm);
+                }
+            } else {
+                state = ST_PERM_EXACT;
+                nrejc = (int)(alpha * (double)nperm);
+            }
+        }
+    }
+    if (lane == 0) {
+        nd->state = state;
+        nd->nrejc = nrejc;
+        nd->ostat = ostat;
+        nd->ostat1 = ostat1;
+        Decision d;
+        d.state = state;
+        d.nrejc = nrejc;
+        d.best_i = bi;
+        d.best_j = bj;
+        d.ostat = ostat;
+        dec[idx] = d;
+    }
+}
+
+// ------------------------------------------------------------------------------------ permutations
+// hybrid: circular arcs of width al0..kmax over the permuted terms; grid (pos tile, perm, list idx)
+__global__ void __launch_bounds__(256)
+cbs_perm_hybrid_kernel(const Node* __restrict__ nodes, const int* __restrict__ list, int p0,
+                       const double* __restrict__ y, const double* __restrict__ w_sqrt,
+                       const double* __restrict__ wn, u64 seed, int al0, int kmax,
+                       unsigned long long* __restrict__ pmax, int chunk) {
+    __shared__ double s_t[HYB_TP + HYB_KMAX], s_w[HYB_TP + HYB_KMAX];
+    __shared__ double s_best[8];
+    const Node nd = nodes[list[blockIdx.z]];
+    const int n = nd.hi - nd.lo, lo = nd.lo;
+    const int s0 = blockIdx.x * HYB_TP;
+    if (s0 >= n) return;
+    const int perm = p0 + blockIdx.y;
+    Prp prp;
+    prp.init(seed, (u32)(nd.lo - nd.base), (u32)(nd.hi - nd.base), 0u, (u32)perm, (u32)n);
+    const int count = min(HYB_TP, n - s0);
+    const int need = count + kmax - 1;
+    for (int k = threadIdx.x; k < need; k += 256) {
+        int pos = s0 + k;
+        if (pos >= n) pos -= n;
+        s_t[k] = __dmul_rn(y[lo + prp((u32)pos)], w_sqrt[lo + pos]);
+        s_w[k] = wn[lo + pos];
+    }
+    __syncthreads();
+    const double total = nd.total;
+    double best = 0.0, bestlo = 0.0;
+    for (int s = threadIdx.x; s < count; s += 256) {
+        double acc = 0.0, cacc = 0.0;
+        for (int k = 1; k <= kmax; ++k) {
+            acc = __dadd_rn(acc, s_t[s + k - 1]);
+            cacc = __dadd_rn(cacc, s_w[s + k - 1]);
+            if (k >= al0) {
+                const double num = __dmul_rn(acc, acc);
+                const double den = __dmul_rn(cacc, __dsub_rn(total, cacc));
+                if (num > __dmul_rn(bestlo, den)) {
+                    const double q = __ddiv_rn(num, den);
+                    if (q > best) { best = q; bestlo = q * (1.0 - 1e-12); }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) best = fmax(best, s_best[k]);
+        atomicMax(&pmax[(size_t)blockIdx.z * chunk + blockIdx.y], (unsigned long long)__double_as_longlong(best));
+    }
+}
+
+// exact: all arcs of the permuted node (n <= EXACT_NMAX); one warp per (node, perm)
+__global__ void __launch_bounds__(128)
+cbs_perm_exact_kernel(const Node* __restrict__ nodes, const int* __restrict__ list, int p0,
+                      const double* __restrict__ y, const double* __restrict__ w_sqrt,
+                      const double* __restrict__ cw, u64 seed, int al0, unsigned long long* __restrict__ pmax,
+                      int chunk) {
+    __shared__ double s_S[4][EXACT_NMAX + 1];
+    __shared__ double s_cw[EXACT_NMAX + 1];
+    const Node nd = nodes[list[blockIdx.y]];
+    const int n = nd.hi - nd.lo, lo = nd.lo;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k <= n; k += 128) s_cw[k] = pt(cw, lo, k);
+    const int pidx = blockIdx.x * 4 + warp;
+    const bool live = pidx < chunk;
+    double* Sp = s_S[warp];
+    if (live) {
+        Prp prp;
+        prp.init(seed, (u32)(nd.lo - nd.base), (u32)(nd.hi - nd.base), 0u, (u32)(p0 + pidx), (u32)n);
+        for (int k = lane; k < n; k += 32) Sp[k + 1] = __dmul_rn(y[lo + prp((u32)k)], w_sqrt[lo + k]);
+        __syncwarp();
+        if (lane == 0) {
+            double run = 0.0;
+            Sp[0] = 0.0;
+            for (int k = 1; k <= n; ++k) {
+                run = __dadd_rn(run, Sp[k]);
+                Sp[k] = run;
+            }
+        }
+    }
+    __syncthreads();
+    if (!live) return;
+    const double total = nd.total;
+    double best = 0.0, bestlo = 0.0;
+    for (int i = lane; i <= n - al0; i += 32) {
+        const double Si = Sp[i], ci = s_cw[i];
+        const int jhi = min(n, i + (n - al0));
+        for (int j = i + al0; j <= jhi; ++j) {
+            const double d = __dsub_rn(Sp[j], Si);
+            const double c = __dsub_rn(s_cw[j], ci);
+            const double den = __dmul_rn(c, __dsub_rn(total, c));
+            const double num = __dmul_rn(d, d);
+            if (num > __dmul_rn(bestlo, den)) {
+                const double q = __ddiv_rn(num, den);
+                if (q > best) { best = q; bestlo = q * (1.0 - 1e-12); }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) pmax[(size_t)blockIdx.y * chunk + pidx] = (unsigned long long)__double_as_longlong(best);
+}
+
+// exceedance flags: ostat <= T^2(pmax)
+__global__ void cbs_perm_flags_kernel(const Node* __restrict__ nodes, const int* __restrict__ list, int nlist,
+                                      const unsigned long long* __restrict__ pmax, int chunk,
+                                      unsigned char* __restrict__ flags) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nlist * chunk) return;
+    const Node* nd = &nodes[list[k / chunk]];
+    const double pb = __longlong_as_double((long long)pmax[k]);
+    const double pstat = t2_of(pb, nd->tss, nd->hi - nd->lo);
+    flags[k] = (nd->ostat <= pstat) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------ flank tests
+// wtpermp set-up: one warp per test (sums by warp reduction; thresholds only)
+__global__ void __launch_bounds__(128)
+cbs_flank_prep_kernel(const Node* __restrict__ nodes, FlankTest* __restrict__ tests, int ntests,
+                      const double* __restrict__ xc, const double* __restrict__ w, int nperm) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * 4 + warp;
+    if (idx >= ntests) return;
+    FlankTest ft = tests[idx];
+    const Node* nd = &nodes[ft.node];
+    const int g0 = nd->lo + ft.off;
+    const int n1 = ft.n1, n2 = ft.n2, n = n1 + n2;
+    if (n1 == 1 || n2 == 1) {
+        if (lane == 0) { tests[idx].pvalue = 1.0; tests[idx].need_perm = 0; }
+        return;
+    }
+    double xs1 = 0, xs2 = 0, tss = 0, rn1 = 0, rn2 = 0;
+    for (int k = lane; k < n; k += 32) {
+        const double xv = xc[g0 + k], wv = w[g0 + k];
+        const double wx = wv * xv;
+        tss += wv * (xv * xv);
+        if (k < n1) { xs1 += wx; rn1 += wv; } else { xs2 += wx; rn2 += wv; }
+    }
+    xs1 = warp_sum(xs1); xs2 = warp_sum(xs2); tss = warp_sum(tss); rn1 = warp_sum(rn1); rn2 = warp_sum(rn2);
+    if (lane == 0) {
+        const double rn = rn1 + rn2;
+        const double xbar = (xs1 + xs2) / rn;
+        tss = tss - rn * (xbar * xbar);
+        int m1, s0;
+        double rm1, odiff;
+        if (n1 <= n2) { m1 = n1; s0 = 0; rm1 = rn1; odiff = fabs(xs1 / rn1 - xbar); }
+        else { m1 = n2; s0 = n1; rm1 = rn2; odiff = fabs(xs2 / rn2 - xbar); }
+        double tstat = rn * rm1 * (odiff * odiff) / (rn - rm1);
+        tstat = tstat / ((tss - tstat) / ((double)n - 2.0));
+        FlankTest* o = &tests[idx];
+        o->m1 = m1; o->s0 = s0; o->rm1 = rm1; o->xbar = xbar; o->ostat = 0.99999 * odiff;
+        if (tstat > 25.0 && m1 >= 10) { o->pvalue = 0.0; o->need_perm = 0; }
+        else { o->pvalue = -1.0; o->need_perm = 1; }
+    }
+}
+
+// one warp per (test, perm): pstat = |sum_{short side} y[pi(k)] rw[k] / rm1 - xbar|
+__global__ void __launch_bounds__(128)
+cbs_flank_perm_kernel(const Node* __restrict__ nodes, const FlankTest* __restrict__ tests,
+                      const int* __restrict__ list, int nperm, const double* __restrict__ xc,
+                      const double* __restrict__ w_sqrt, u64 seed, int* __restrict__ nrej) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int perm = blockIdx.x * 4 + warp;
+    if (perm >= nperm) return;
+    const FlankTest ft = tests[list[blockIdx.y]];
+    const Node* nd = &nodes[ft.node];
+    const int g0 = nd->lo + ft.off;
+    const int n = ft.n1 + ft.n2;
+    Prp prp;
+    prp.init(seed, (u32)(nd->lo - nd->base), (u32)(nd->hi - nd->base), (u32)ft.tid, (u32)perm, (u32)n);
+    double xs = 0.0;
+    for (int k = lane; k < ft.m1; k += 32) {
+        const int src = g0 + (int)prp((u32)(ft.s0 + k));
+        xs += (xc[src] * w_sqrt[src]) * w_sqrt[g0 + ft.s0 + k];
+    }
+    xs = warp_sum(xs);
+    if (lane == 0) {
+        const double pstat = fabs(xs / ft.rm1 - ft.xbar);
+        if (ft.ostat <= pstat) atomicAdd(&nrej[blockIdx.y], 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------ misc kernels
+__global__ void sqrt_kernel(const double* __restrict__ w, double* __restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sqrt(w[i]);
+}
+
+// weighted.mean(log2, weight) per segment (cbs.py:70-71); one warp per segment
+__global__ void __launch_bounds__(128)
+seg_mean_kernel(const double* __restrict__ x, const double* __restrict__ w, const long long* __restrict__ lo,
+                const long long* __restrict__ hi, int nseg, double* __restrict__ mean) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * 4 + warp;
+    if (s >= nseg) return;
+    double sw = 0.0, swx = 0.0;
+    for (long long k = lo[s] + lane; k < hi[s]; k += 32) {
+        sw += w[k];
+        swx += x[k] * w[k];
+    }
+    sw = warp_sum(sw);
+    swx = warp_sum(swx);
+    if (lane == 0) mean[s] = swx / sw;
+}
+
+// ------------------------------------------------------------------------------------ host side
+// DNAcopy getbdry (sequential stopping boundary), restated with an exact draw-by-draw
+// hypergeometric recursion instead of phyper()/closed-form pexceed.
+static void etabdry_host(int nperm, double eta0, int j, int* ibdry) {
+    std::vector<double> dist(j + 1, 0.0);
+    dist[0] = 1.0;
+    int k = 0;
+    for (int i = 1; i <= nperm && k < j; ++i) {
+        const double rem = (double)(nperm - i + 1);
+        for (int xx = std::min(i, j); xx >= 0; --xx) {
+            const double stay = dist[xx] * (1.0 - (double)(j - xx) / rem);
+            const double up = xx > 0 ? dist[xx - 1] * ((double)(j - (xx - 1)) / rem) : 0.0;
+            dist[xx] = stay + up;
+        }
+        double cdf = 0.0;
+        for (int xx = 0; xx <= k; ++xx) cdf += dist[xx];
+        if (cdf <= eta0) ibdry[k++] = i;
+    }
+    for (; k < j; ++k) ibdry[k] = nperm;
+}
+
+static double pexceed_host(int nperm, int j, const int* ibdry) {
+    std::vector<double> alive(j + 1, 0.0);
+    alive[0] = 1.0;
+    double crossed = 0.0;
+    int kb = 0;
+    for (int i = 1; i <= nperm; ++i) {
+        const double rem = (double)(nperm - i + 1);
+        for (int xx = std::min(i, j); xx >= 0; --xx) {
+            const double stay = alive[xx] * (1.0 - (double)(j - xx) / rem);
+            const double up = xx > 0 ? alive[xx - 1] * ((double)(j - (xx - 1)) / rem) : 0.0;
+            alive[xx] = stay + up;
+        }
+        while (kb < j && ibdry[kb] == i) {
+            for (int xx = 0; xx <= kb; ++xx) { crossed += alive[xx]; alive[xx] = 0.0; }
+            ++kb;
+        }
+    }
+    return crossed;
+}
+
+void cbs_getbdry(double eta, int nperm, int max_ones, std::vector<int>& out) {
+    out.assign((size_t)max_ones * (max_ones + 1) / 2, 0);
+    out[0] = nperm - (int)((double)nperm * eta);
+    double eta0 = eta;
+    int l = 1;
+    for (int j = 2; j <= max_ones; ++j) {
+        int* b = out.data() + l;
+        double etahi = eta0 * 1.1, etalo = eta0 * 0.25;
+        etabdry_host(nperm, etahi, j, b);
+        double phi = pexceed_host(nperm, j, b);
+        etabdry_host(nperm, etalo, j, b);
+        double plo = pexceed_host(nperm, j, b);
+        while ((etahi - etalo) / etalo > 1e-2) {
+            eta0 = etalo + (etahi - etalo) * (eta - plo) / (phi - plo);
+            etabdry_host(nperm, eta0, j, b);
+            const double pex = pexceed_host(nperm, j, b);
+            if (pex > eta) { etahi = eta0; phi = pex; } else { etalo = eta0; plo = pex; }
+        }
+        l += j;
+    }
+}
+
+struct HostNode {
+    int lo, hi, base, arm;
+};
+
+static int tiles_for(int n) {
+    const int P = n + 1;
+    const int NJ = (P + CBS_BLK - 1) / CBS_BLK, NI = (P + CBS_IBLK - 1) / CBS_IBLK;
+    int t = 0;
+    for (int ib = 0; ib < NI; ++ib) t += std::max(0, NJ - CBS_IW * ib);
+    return t;
+}
+
+int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, const CbsParams& P,
+                std::vector<CbsSeg>& segs, CbsStats* stats, cudaStream_t stream) {
+    segs.clear();
+    CbsStats st;
+    memset(&st, 0, sizeof(st));
+    if (n_arms <= 0) { if (stats) *stats = st; return 0; }
+    const long long N = h_off[n_arms];
+    if (N >= (1ll << 31)) { set_last_error("cbs_segment: too many bins (%lld)", N); return -2; }
+    if (P.kmax > HYB_KMAX || P.nmin > EXACT_NMAX || P.min_width < 2 || P.kmax < P.min_width || P.nperm < 1) {
+        set_last_error("cbs_segment: unsupported parameters (kmax<=%d, nmin<=%d, min_width>=2)", HYB_KMAX, EXACT_NMAX);
+        return -2;
+    }
+    if (P.nmin < 2 * P.kmax) { set_last_error("cbs_segment: need nmin >= 2*kmax"); return -2; }
+    int sm_count = 148;
+    {
+        int dev = 0;
+        CNVK_CHECK(cudaGetDevice(&dev));
+        CNVK_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int max_ones = (int)std::floor((double)P.nperm * P.alpha) + 1;
+    std::vector<int> sbdry;
+    cbs_getbdry(P.eta, P.nperm, max_ones, sbdry);
+
+    Scratch scratch(stream);
+    double *d_rw, *d_xc, *d_y, *d_S, *d_cw, *d_wn, *d_bmin, *d_bmax;
+    const size_t NB = (size_t)(N / CBS_BLK) + 2 * (size_t)n_arms + 2 * (size_t)N / 4 + 16;  // >= sum ceil((n+1)/256)
+    CNVK_CHECK(scratch.alloc(&d_rw, (size_t)N));
+    CNVK_CHECK(scratch.alloc(&d_xc, (size_t)N));
+    CNVK_CHECK(scratch.alloc(&d_y, (size_t)N));
+    CNVK_CHECK(scratch.alloc(&d_S, (size_t)N));
+    CNVK_CHECK(scratch.alloc(&d_cw, (size_t)N));
+    CNVK_CHECK(scratch.alloc(&d_wn, (size_t)N));
+    CNVK_CHECK(scratch.alloc(&d_bmin, NB));
+    CNVK_CHECK(scratch.alloc(&d_bmax, NB));
+    if (N > 0) {
+        sqrt_kernel<<<div_up(N, 256), 256, 0, stream>>>(d_w, d_rw, N);
+        CNVK_LAUNCH_CHECK();
+    }
+    int* d_counter;
+    unsigned long long* d_stats;
+    CNVK_CHECK(scratch.alloc(&d_counter, 1));
+    CNVK_CHECK(scratch.alloc(&d_stats, 2));
+    CNVK_CHECK(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), stream));
+
+    std::vector<HostNode> frontier;
+    std::vector<std::vector<int>> ends(n_arms);
+    for (int a = 0; a < n_arms; ++a) {
+        const int lo = (int)h_off[a], hi = (int)h_off[a + 1];
+        if (hi <= lo) continue;
+        if (hi - lo >= 2 * P.min_width) frontier.push_back({lo, hi, lo, a});
+        else ends[a].push_back(hi);
+    }
+
+    // growable device buffers for per-level arrays
+    size_t cap_nodes = 0;
+    Node* d_nodes = nullptr;
+    Decision* d_dec = nullptr;
+    int* d_tile_off = nullptr;
+    auto free_level = [&]() {
+        if (d_nodes) cudaFreeAsync(d_nodes, stream);
+        if (d_dec) cudaFreeAsync(d_dec, stream);
+        if (d_tile_off) cudaFreeAsync(d_tile_off, stream);
+        d_nodes = nullptr; d_dec = nullptr; d_tile_off = nullptr;
+    };
+    struct Guard { decltype(free_level)& f; ~Guard() { f(); } } guard{free_level};
+
+    std::vector<Node> h_nodes;
+    std::vector<Decision> h_dec;
+    std::vector<int> h_tile_off;
+
+    while (!frontier.empty()) {
+        st.levels++;
+        const int nn = (int)frontier.size();
+        st.nodes += nn;
+        if ((size_t)nn > cap_nodes) {
+            free_level();
+            cap_nodes = (size_t)nn * 2;
+            CNVK_CHECK(cudaMallocAsync((void**)&d_nodes, cap_nodes * sizeof(Node), stream));
+            CNVK_CHECK(cudaMallocAsync((void**)&d_dec, cap_nodes * sizeof(Decision), stream));
+            CNVK_CHECK(cudaMallocAsync((void**)&d_tile_off, (cap_nodes + 1) * sizeof(int), stream));
+        }
+        h_nodes.assign(nn, Node());
+        h_tile_off.assign(nn + 1, 0);
+        long long blk_off = 0, tiles = 0;
+        for (int k = 0; k < nn; ++k) {
+            Node& nd = h_nodes[k];
+            memset(&nd, 0, sizeof(Node));
+            nd.lo = frontier[k].lo; nd.hi = frontier[k].hi; nd.base = frontier[k].base;
+            nd.blk_off = (int)blk_off;
+            nd.best_q = -1.0; nd.best_i = 0x7fffffff; nd.best_j = 0x7fffffff;
+            const int n = nd.hi - nd.lo;
+            blk_off += (n + 1 + CBS_BLK - 1) / CBS_BLK;
+            h_tile_off[k] = (int)tiles;
+            tiles += tiles_for(n);
+            if (tiles >= (1ll << 31)) { set_last_error("cbs_segment: tile count overflow"); return -2; }
+        }
+        h_tile_off[nn] = (int)tiles;
+        if ((size_t)blk_off > NB) { set_last_error("cbs_segment: block buffer too small"); return -3; }
+        CNVK_CHECK(cudaMemcpyAsync(d_nodes, h_nodes.data(), nn * sizeof(Node), cudaMemcpyHostToDevice, stream));
+        CNVK_CHECK(cudaMemcpyAsync(d_tile_off, h_tile_off.data(), (nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+        CNVK_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(int), stream));
+        cbs_prep_kernel<<<nn, 256, 0, stream>>>(d_nodes, d_x, d_w, d_xc, d_y, d_S, d_cw, d_wn, d_bmin, d_bmax, P.min_width);
+        CNVK_LAUNCH_CHECK();
+        {
+            const int grid = (int)std::min<long long>(tiles, (long long)sm_count * 8);
+            if (grid > 0) {
+                if (P.prune)
+                    cbs_scan_kernel<true><<<grid, 256, 0, stream>>>(d_nodes, d_tile_off, nn, (int)tiles, d_counter, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
+                else
+                    cbs_scan_kernel<false><<<grid, 256, 0, stream>>>(d_nodes, d_tile_off, nn, (int)tiles, d_counter, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
+                CNVK_LAUNCH_CHECK();
+            }
+        }
+        cbs_decide_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, nn, d_dec, P.alpha, P.nperm, P.kmax, P.nmin, P.hybrid, 100, 1e-6);
+        CNVK_LAUNCH_CHECK();
+        h_dec.resize(nn);
+        CNVK_CHECK(cudaMemcpyAsync(h_dec.data(), d_dec, nn * sizeof(Decision), cudaMemcpyDeviceToHost, stream));
+        CNVK_CHECK(cudaStreamSynchronize(stream));
+
+        // ---- permutation reference distributions
+        for (int mode = ST_PERM_HYBRID; mode <= ST_PERM_EXACT; ++mode) {
+            std::vector<int> list;
+            for (int k = 0; k < nn; ++k) if (h_dec[k].state == mode) list.push_back(k);
+            if (list.empty()) continue;
+            st.perm_nodes += (long long)list.size();
+            std::vector<int> nrej(list.size(), 0), kk(list.size()), done(list.size(), 0);
+            for (size_t q = 0; q < list.size(); ++q) {
+                const int nrejc = h_dec[list[q]].nrejc;
+                kk[q] = nrejc * (nrejc + 1) / 2 + 1;
+            }
+            int p0 = 0;
+            int chunk = 64;
+            std::vector<int> active(list.begin(), list.end());
+            std::vector<size_t> active_q(list.size());
+            for (size_t q = 0; q < list.size(); ++q) active_q[q] = q;
+            while (!active.empty() && p0 < P.nperm) {
+                chunk = std::min(chunk, P.nperm - p0);
+                const int na = (int)active.size();
+                Scratch ps(stream);
+                int* d_list;
+                unsigned long long* d_pmax;
+                unsigned char* d_flags;
+                CNVK_CHECK(ps.alloc(&d_list, (size_t)na));
+                CNVK_CHECK(ps.alloc(&d_pmax, (size_t)na * chunk));
+                CNVK_CHECK(ps.alloc(&d_flags, (size_t)na * chunk));
+                CNVK_CHECK(cudaMemcpyAsync(d_list, active.data(), na * sizeof(int), cudaMemcpyHostToDevice, stream));
+                CNVK_CHECK(cudaMemsetAsync(d_pmax, 0, (size_t)na * chunk * sizeof(unsigned long long), stream));
+                if (mode == ST_PERM_HYBRID) {
+                    int maxn = 0;
+                    for (int k : active) maxn = std::max(maxn, frontier[k].hi - frontier[k].lo);
+                    // grid.z is limited to 65535 and grid.y too: split the node list if needed
+                    for (int z0 = 0; z0 < na; z0 += 32768) {
+                        const int nz = std::min(32768, na - z0);
+                        dim3 grid(div_up(maxn, HYB_TP), chunk, nz);
+                        cbs_perm_hybrid_kernel<<<grid, 256, 0, stream>>>(d_nodes, d_list + z0, p0, d_y, d_rw, d_wn, P.seed, P.min_width, P.kmax, d_pmax + (size_t)z0 * chunk, chunk);
+                        CNVK_LAUNCH_CHECK();
+                    }
+                    for (int k : active) st.perm_arcs += (long long)(frontier[k].hi - frontier[k].lo) * (P.kmax - P.min_width + 1) * chunk;
+                } else {
+                    for (int z0 = 0; z0 < na; z0 += 32768) {
+                        const int nz = std::min(32768, na - z0);
+                        dim3 grid(div_up(chunk, 4), nz);
+                        cbs_perm_exact_kernel<<<grid, 128, 0, stream>>>(d_nodes, d_list + z0, p0, d_y, d_rw, d_cw, P.seed, P.min_width, d_pmax + (size_t)z0 * chunk, chunk);
+                        CNVK_LAUNCH_CHECK();
+                    }
+                    for (int k : active) { const long long n = frontier[k].hi - frontier[k].lo; st.perm_arcs += n * n / 2 * chunk; }
+                }
+                cbs_perm_flags_kernel<<<div_up((long long)na * chunk, 256), 256, 0, stream>>>(d_nodes, d_list, na, d_pmax, chunk, d_flags);
+                CNVK_LAUNCH_CHECK();
+                std::vector<unsigned char> flags((size_t)na * chunk);
+                CNVK_CHECK(cudaMemcpyAsync(flags.data(), d_flags, flags.size(), cudaMemcpyDeviceToHost, stream));
+                CNVK_CHECK(cudaStreamSynchronize(stream));
+                st.perms_run += (long long)na * chunk;
+                // replay DNAcopy's sequential stopping rule on the flags
+                std::vector<int> next_active;
+                std::vector<size_t> next_q;
+                for (int a = 0; a < na; ++a) {
+                    const size_t q = active_q[a];
+                    const int nrejc = h_dec[list[q]].nrejc;
+                    int decided = 0;
+                    for (int c = 0; c < chunk && !decided; ++c) {
+                        const int np = p0 + c + 1;
+                        if (flags[(size_t)a * chunk + c]) { nrej[q]++; kk[q]++; }
+                        if (nrej[q] > nrejc) decided = -1;
+                        else if (np >= sbdry[kk[q] - 1]) decided = 1;
+                    }
+                    if (decided == 0 && p0 + chunk >= P.nperm) decided = 1;  // survived every permutation
+                    if (decided == 0) { next_active.push_back(active[a]); next_q.push_back(q); }
+                    else h_dec[list[q]].state = decided > 0 ? ST_SPLIT : ST_FINAL;
+                }
+                active.swap(next_active);
+                active_q.swap(next_q);
+                p0 += chunk;
+                chunk = std::min(chunk * 4, 2048);
+            }
+        }
+
+        // ---- ternary-split confirmation
+        std::vector<FlankTest> tests;
+        std::vector<int> test_owner;
+        for (int k = 0; k < nn; ++k) {
+            if (h_dec[k].state != ST_SPLIT) continue;
+            const int n = frontier[k].hi - frontier[k].lo, ai = h_dec[k].best_i, aj = h_dec[k].best_j;
+            if (aj == n || ai == 0) continue;
+            FlankTest f;
+            memset(&f, 0, sizeof(f));
+            f.node = k; f.off = 0; f.n1 = ai; f.n2 = aj - ai; f.tid = 1;
+            tests.push_back(f); test_owner.push_back(k);
+            f.off = ai; f.n1 = aj - ai; f.n2 = n - aj; f.tid = 2;
+            tests.push_back(f); test_owner.push_back(k);
+        }
+        std::vector<double> pvals(tests.size(), 0.0);
+        if (!tests.empty()) {
+            const int nt = (int)tests.size();
+            Scratch fs(stream);
+            FlankTest* d_tests;
+            CNVK_CHECK(fs.alloc(&d_tests, (size_t)nt));
+            CNVK_CHECK(cudaMemcpyAsync(d_tests, tests.data(), nt * sizeof(FlankTest), cudaMemcpyHostToDevice, stream));
+            cbs_flank_prep_kernel<<<div_up(nt, 4), 128, 0, stream>>>(d_nodes, d_tests, nt, d_xc, d_w, P.nperm);
+            CNVK_LAUNCH_CHECK();
+            CNVK_CHECK(cudaMemcpyAsync(tests.data(), d_tests, nt * sizeof(FlankTest), cudaMemcpyDeviceToHost, stream));
+            CNVK_CHECK(cudaStreamSynchronize(stream));
+            std::vector<int> plist;
+            for (int t = 0; t < nt; ++t) if (tests[t].need_perm) plist.push_back(t);
+            if (!plist.empty()) {
+                const int np_ = (int)plist.size();
+                st.flank_perm_tests += np_;
+                int *d_plist, *d_nrej;
+                CNVK_CHECK(fs.alloc(&d_plist, (size_t)np_));
+                CNVK_CHECK(fs.alloc(&d_nrej, (size_t)np_));
+                CNVK_CHECK(cudaMemcpyAsync(d_plist, plist.data(), np_ * sizeof(int), cudaMemcpyHostToDevice, stream));
+                CNVK_CHECK(cudaMemsetAsync(d_nrej, 0, np_ * sizeof(int), stream));
+                for (int z0 = 0; z0 < np_; z0 += 32768) {
+                    const int nz = std::min(32768, np_ - z0);
+                    dim3 grid(div_up(P.nperm, 4), nz);
+                    cbs_flank_perm_kernel<<<grid, 128, 0, stream>>>(d_nodes, d_tests, d_plist + z0, P.nperm, d_xc, d_rw, P.seed, d_nrej + z0);
+                    CNVK_LAUNCH_CHECK();
+                }
+                std::vector<int> h_nrej(np_);
+                CNVK_CHECK(cudaMemcpyAsync(h_nrej.data(), d_nrej, np_ * sizeof(int), cudaMemcpyDeviceToHost, stream));
+                CNVK_CHECK(cudaStreamSynchronize(stream));
+                for (int q = 0; q < np_; ++q) tests[plist[q]].pvalue = (double)h_nrej[q] / (double)P.nperm;
+            }
+            for (int t = 0; t < nt; ++t) pvals[t] = tests[t].pvalue;
+        }
+
+        // ---- next frontier
+        std::vector<HostNode> next;
+        size_t tcur = 0;
+        for (int k = 0; k < nn; ++k) {
+            const HostNode& hn = frontier[k];
+            const int n = hn.hi - hn.lo;
+            int ncpt = 0, icpt[2] = {0, 0};
+            if (h_dec[k].state == ST_SPLIT) {
+                const int ai = h_dec[k].best_i, aj = h_dec[k].best_j;
+                if (aj == n) { ncpt = 1; icpt[0] = ai; }
+                else if (ai == 0) { ncpt = 1; icpt[0] = aj; }
+                else {
+                    if (pvals[tcur] <= P.alpha) { ncpt = 1; icpt[0] = ai; }
+                    if (pvals[tcur + 1] <= P.alpha) { icpt[ncpt] = aj; ++ncpt; }
+                    if (ncpt == 0) { ncpt = 2; icpt[0] = ai; icpt[1] = aj; }
+                    tcur += 2;
+                }
+            }
+            if (ncpt == 0) { ends[hn.arm].push_back(hn.hi); continue; }
+            int cuts[4] = {hn.lo, hn.lo + icpt[0], ncpt == 2 ? hn.lo + icpt[1] : hn.hi, hn.hi};
+            const int npieces = ncpt + 1;
+            for (int c = 0; c < npieces; ++c) {
+                const int a0 = cuts[c], a1 = (c == npieces - 1) ? hn.hi : cuts[c + 1];
+                if (a1 - a0 >= 2 * P.min_width) next.push_back({a0, a1, hn.base, hn.arm});
+                else ends[hn.arm].push_back(a1);
+            }
+        }
+        frontier.swap(next);
+    }
+
+    // ---- segment table + weighted means
+    std::vector<long long> slo, shi;
+    for (int a = 0; a < n_arms; ++a) {
+        std::sort(ends[a].begin(), ends[a].end());
+        long long prev = h_off[a];
+        for (int e : ends[a]) {
+            CbsSeg s;
+            s.arm = a; s.lo = prev; s.hi = e; s.mean = 0.0;
+            segs.push_back(s);
+            slo.push_back(prev); shi.push_back(e);
+            prev = e;
+        }
+    }
+    if (!segs.empty()) {
+        const int ns = (int)segs.size();
+        Scratch ms(stream);
+        long long *d_lo, *d_hi;
+        double* d_mean;
+        CNVK_CHECK(ms.alloc(&d_lo, (size_t)ns));
+        CNVK_CHECK(ms.alloc(&d_hi, (size_t)ns));
+        CNVK_CHECK(ms.alloc(&d_mean, (size_t)ns));
+        CNVK_CHECK(cudaMemcpyAsync(d_lo, slo.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, stream));
+        CNVK_CHECK(cudaMemcpyAsync(d_hi, shi.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, stream));
+        seg_mean_kernel<<<div_up(ns, 4), 128, 0, stream>>>(d_x, d_w, d_lo, d_hi, ns, d_mean);
+        CNVK_LAUNCH_CHECK();
+        std::vector<double> means(ns);
+        CNVK_CHECK(cudaMemcpyAsync(means.data(), d_mean, ns * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CNVK_CHECK(cudaStreamSynchronize(stream));
+        for (int s = 0; s < ns; ++s) segs[s].mean = means[s];
+    }
+    {
+        unsigned long long h_stats[2];
+        CNVK_CHECK(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
+        CNVK_CHECK(cudaStreamSynchronize(stream));
+        st.obs_subtiles_scanned = (long long)h_stats[0];
+        st.obs_subtiles_total = (long long)h_stats[1];
+        st.obs_arcs = st.obs_subtiles_scanned * (long long)CBS_BLK * CBS_BLK;
+    }
+    if (stats) *stats = st;
+    return 0;
+}
+
+}  // namespace cnvk

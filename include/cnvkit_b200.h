@@ -53,6 +53,43 @@ int cnvk_rolling_quantile(const double* x, int64_t n, int64_t wing, double q, do
 /* np.argsort(x, kind="mergesort") as used by cnvlib/fix.py:414 -- stable, NaN last. */
 int cnvk_argsort_f64_dev(const double* d_x, int64_t n, uint32_t* d_order, void* stream);
 
+/* ---- circular binary segmentation ------------------------------------------------------ */
+/* Replaces the Rscript + DNAcopy::segment(cna, weights, alpha) subprocess of
+ * cnvlib/segmentation/__init__.py:292-322 (R script cnvlib/segmentation/cbs.py:1-78).  Field
+ * defaults are DNAcopy's (cbs.py:60 passes only weights and alpha): nperm 10000, min_width 2,
+ * kmax 25, nmin 200, eta 0.05, hybrid 1; seed is cbs.py:49's 0xA5EED. */
+typedef struct cnvk_cbs_params {
+    double alpha;
+    int32_t nperm, min_width, kmax, nmin;
+    double eta;
+    int32_t hybrid; /* p.method == "hybrid" */
+    int32_t prune;  /* 1: skip arc tiles whose upper bound cannot reach the current best (same result) */
+    uint64_t seed;
+} cnvk_cbs_params;
+
+typedef struct cnvk_cbs_stats {
+    int64_t nodes, levels, obs_subtiles_total, obs_subtiles_scanned, obs_arcs, perm_arcs, perm_nodes,
+        perms_run, flank_perm_tests;
+} cnvk_cbs_stats;
+
+/* One call segments every arm of a batch: bins of arm a are [arm_offsets[a], arm_offsets[a+1])
+ * of the (already filtered, %.6g-quantised) log2/weight columns; weights must be > 0
+ * (cbs.py:22-35).  Segments come back in arm order as half-open bin ranges [seg_lo, seg_hi)
+ * with seg_mean = weighted.mean(log2, weight) (cbs.py:70-71).  arm_offsets and all outputs are
+ * HOST arrays (the table is tiny); *n_segs receives the count, which must be <= capacity
+ * (capacity = number of bins is always enough). */
+int cnvk_cbs_segment_dev(const double* d_log2, const double* d_weight, const int64_t* arm_offsets,
+                         int32_t n_arms, const cnvk_cbs_params* params, int64_t capacity,
+                         int32_t* seg_arm, int64_t* seg_lo, int64_t* seg_hi, double* seg_mean,
+                         int64_t* n_segs, cnvk_cbs_stats* stats, void* stream);
+int cnvk_cbs_segment(const double* log2, const double* weight, const int64_t* arm_offsets,
+                     int32_t n_arms, const cnvk_cbs_params* params, int64_t capacity, int32_t* seg_arm,
+                     int64_t* seg_lo, int64_t* seg_hi, double* seg_mean, int64_t* n_segs,
+                     cnvk_cbs_stats* stats);
+/* DNAcopy getbdry(eta, nperm, max.ones): sequential stopping boundary,
+ * out[max_ones*(max_ones+1)/2]. Host-only. */
+int cnvk_cbs_getbdry(double eta, int32_t nperm, int32_t max_ones, int32_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,551 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement of DNAcopy's weighted circular binary
+ * segmentation as CNVkit invokes it.  Never linked into or called by the product.
+ *
+ * ======================= PARITY UNPINNED ==========================================
+ * The arithmetic lives in a third-party dependency that is NOT in /root/reference:
+ * Bioconductor `DNAcopy` (version unpinned by the reference: conda-env.yml:15,
+ * environment-dev.yml:20, devtools/conda-recipe/meta.yaml:20), reached through an Rscript
+ * subprocess (cnvlib/segmentation/__init__.py:292-322, script cnvlib/segmentation/cbs.py:1-78).
+ * Neither R nor DNAcopy (nor their sources) exist in this container, and the reference's own
+ * tests hold no CBS golden vectors (test/test_r.py asserts structure only).  This file
+ * therefore restates the *published* algorithm -- Olshen et al. 2004, Venkatraman & Olshen
+ * 2007, and DNAcopy's R/Fortran control flow (segment -> changepoints -> wfindcpt ->
+ * wtmaxo / hwtmaxp / wtmaxp / tailp / wtpermp / getbdry) -- anchored on the reference's call
+ * site: segment(CNA(log2, chrom, start, "logratio", presorted=T), weights=w, alpha=threshold)
+ * with every other argument at DNAcopy's default (nperm=10000, p.method="hybrid",
+ * min.width=2, kmax=25, nmin=200, eta=0.05, undo.splits="none").
+ *
+ * Deliberate, documented deviations from a bit-faithful DNAcopy:
+ *  (1) RNG.  R's Mersenne-Twister stream cannot be reproduced; the north star only asks that
+ *      permutation p-values agree within Monte-Carlo error.  Permutations here are
+ *      counter-based: permutation p of the test `tid` on node [lo,hi) is the bijection
+ *      PRP(seed, lo, hi, tid, p) on [0,n) (Philox4x32-10 round keys driving a 4-round
+ *      alternating Feistel network with cycle walking).  Results are therefore independent
+ *      of the order in which nodes are visited -- which is what lets the GPU process the
+ *      recursion level-synchronously and still agree with this file exactly.
+ *  (2) R computes sum()/cumsum() in 80-bit extended precision; here every sum is a plain
+ *      left-to-right IEEE double accumulation (as DNAcopy's Fortran partial sums are).
+ *  (3) wtmaxo's block-pruned search is restated as an exhaustive scan over all arcs; the
+ *      maximum is the same, ties resolve to the smallest (i, j).
+ *  (4) hwtmaxp (hybrid permutation statistic) is restated as windowed sums over circular
+ *      arcs of width min.width..kmax, accumulated element by element from the arc start.
+ *
+ * Build: make -C oracle   (gcc -O2 -ffp-contract=off -fopenmp -shared)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+    double alpha;
+    int nperm;
+    int min_width;
+    int kmax;
+    int nmin;
+    double eta;
+    int hybrid; /* p.method == "hybrid" */
+    int ngrid;
+    double tol;
+    uint64_t seed;
+} cbso_params;
+
+typedef struct {
+    long long nodes;          /* intervals tested */
+    long long obs_arcs;       /* arcs evaluated for observed statistics */
+    long long perm_arcs;      /* arcs evaluated inside permutation statistics */
+    long long perm_tests;     /* nodes that needed the permutation reference distribution */
+    long long perms_run;      /* permutations actually generated (early stopping) */
+    long long tperm_tests;    /* ternary-split flank tests that ran permutations */
+} cbso_stats;
+
+/* ------------------------------------------------------------------ RNG / permutation */
+static inline void philox_round(uint32_t c[4], const uint32_t k[2]) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    uint32_t k[2] = {key[0], key[1]};
+    for (int r = 0; r < 10; ++r) {
+        if (r) { k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }
+        philox_round(c, k);
+    }
+    memcpy(out, c, sizeof(c));
+}
+
+static inline uint32_t mix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+
+typedef struct { uint32_t k[4]; int bits_a, bits_b; uint32_t n; } prp_t;
+
+static void prp_init(prp_t* P, uint64_t seed, uint32_t lo, uint32_t hi, uint32_t tid, uint32_t perm, uint32_t n) {
+    const uint32_t ctr[4] = {perm, tid, lo, hi};
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    philox4x32_10(ctr, key, P->k);
+    int bits = 8;
+    while (bits < 32 && (1ull << bits) < n) ++bits;
+    P->bits_a = bits / 2;          /* left half  */
+    P->bits_b = bits - bits / 2;   /* right half */
+    P->n = n;
+}
+
+/* 4-round alternating Feistel on bits_a+bits_b bits, cycle-walked into [0, n). */
+static inline uint32_t prp_eval(const prp_t* P, uint32_t v) {
+    const int a = P->bits_a, b = P->bits_b;
+    const uint32_t ma = (1u << a) - 1u, mb = (1u << b) - 1u;
+    do {
+        uint32_t L = v >> b, R = v & mb;           /* L: a bits, R: b bits */
+        /* round 0: (L:a, R:b) -> (R:b, L ^ F(R):a) */
+        uint32_t t = (L ^ mix32(R ^ P->k[0])) & ma; L = R; R = t;   /* L:b R:a */
+        t = (L ^ mix32(R ^ P->k[1])) & mb; L = R; R = t;            /* L:a R:b */
+        t = (L ^ mix32(R ^ P->k[2])) & ma; L = R; R = t;            /* L:b R:a */
+        t = (L ^ mix32(R ^ P->k[3])) & mb; L = R; R = t;            /* L:a R:b */
+        v = (L << b) | R;
+    } while (v >= P->n);
+    return v;
+}
+
+uint32_t cbso_prp(uint64_t seed, uint32_t lo, uint32_t hi, uint32_t tid, uint32_t perm, uint32_t n, uint32_t t) {
+    prp_t P;
+    prp_init(&P, seed, lo, hi, tid, perm, n);
+    return prp_eval(&P, t);
+}
+
+/* ------------------------------------------------------------------ tail probability */
+static double pnorm_std(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
+
+/* Siegmund's nu(x): DNAcopy tailprobs.f `nu` */
+static double nu_fn(double x, double tol) {
+    double lnu1;
+    if (x > 0.01) {
+        lnu1 = log(2.0) - 2.0 * log(x);
+        double lnu0 = lnu1, dk = 0.0;
+        int k = 2;
+        for (int i = 0; i < k; ++i) {
+            dk += 1.0;
+            lnu1 -= 2.0 * pnorm_std(-x * sqrt(dk) / 2.0) / dk;
+        }
+        while (fabs((lnu1 - lnu0) / lnu1) > tol) {
+            lnu0 = lnu1;
+            for (int i = 0; i < k; ++i) {
+                dk += 1.0;
+                lnu1 -= 2.0 * pnorm_std(-x * sqrt(dk) / 2.0) / dk;
+            }
+            k *= 2;
+        }
+    } else {
+        lnu1 = -0.583 * x;
+    }
+    return exp(lnu1);
+}
+
+/* integral of 1/(t(1-t))^2 from x to x+a: DNAcopy tailprobs.f `it1tsq` */
+static double it1tsq(double x, double a) {
+    double y = x + a - 0.5;
+    double r = (8.0 * y) / (1.0 - 4.0 * y * y) + 2.0 * log((1.0 + 2.0 * y) / (1.0 - 2.0 * y));
+    y = x - 0.5;
+    r = r - (8.0 * y) / (1.0 - 4.0 * y * y) - 2.0 * log((1.0 + 2.0 * y) / (1.0 - 2.0 * y));
+    return r;
+}
+
+/* DNAcopy tailprobs.f `tailp`: P(max over arcs with fraction in [delta, 1/2] > b), two-sided */
+double cbso_tailp(double b, double delta, int m, int ngrid, double tol) {
+    const double dincr = (0.5 - delta) / (double)ngrid;
+    const double bsqrtm = b / sqrt((double)m);
+    double tl = 0.5 - dincr, t = 0.5 - 0.5 * dincr, p = 0.0;
+    for (int i = 0; i < ngrid; ++i) {
+        const double x = bsqrtm / sqrt(t * (1.0 - t));
+        const double nux = nu_fn(x, tol);
+        p += (nux * nux) * it1tsq(tl, dincr);
+        tl -= dincr;
+        t -= dincr;
+    }
+    p = 9.973557e-2 * (b * b * b) * exp(-(b * b) / 2.0) * p;
+    return 2.0 * p;
+}
+
+/* ------------------------------------------------------------------ sequential boundary */
+/* DNAcopy getbdry.f `etabdry`: for k = 0..j-1 the first i with P(X_i <= k) <= eta0, where X_i is
+ * the number of the j "ones" that fall among the first i of nperm permutations (hypergeometric;
+ * the distribution is advanced draw by draw instead of calling phyper at every i). */
+static void etabdry(int nperm, double eta0, int j, int* ibdry) {
+    double* dist = (double*)calloc((size_t)j + 1, sizeof(double));
+    dist[0] = 1.0;
+    int k = 0;
+    for (int i = 1; i <= nperm && k < j; ++i) {
+        for (int x = (i < j ? i : j); x >= 0; --x) {
+            const double stay = dist[x] * (1.0 - (double)(j - x) / (double)(nperm - i + 1));
+            const double up = (x > 0) ? dist[x - 1] * ((double)(j - (x - 1)) / (double)(nperm - i + 1)) : 0.0;
+            dist[x] = stay + up;
+        }
+        double cdf = 0.0;
+        for (int x = 0; x <= k; ++x) cdf += dist[x];
+        if (cdf <= eta0) {
+            ibdry[k] = i;
+            ++k;
+        }
+    }
+    for (; k < j; ++k) ibdry[k] = nperm; /* unreachable for sane eta0 */
+    free(dist);
+}
+
+/* P(the count path touches the boundary) when exactly j ones are placed uniformly among
+ * nperm permutations: first-crossing DP (equals getbdry.f `pexceed`'s closed forms). */
+static double pexceed(int nperm, int j, const int* ibdry) {
+    double* alive = (double*)calloc((size_t)j + 1, sizeof(double));
+    alive[0] = 1.0;
+    double crossed = 0.0;
+    int kb = 0; /* next boundary index to check */
+    for (int i = 1; i <= nperm; ++i) {
+        /* draw i: is it a one?  P = (j - x)/(nperm - i + 1) given x ones so far */
+        for (int x = (i < j ? i : j); x >= 0; --x) {
+            const double stay = alive[x] * (1.0 - (double)(j - x) / (double)(nperm - i + 1));
+            const double up = (x > 0) ? alive[x - 1] * ((double)(j - (x - 1)) / (double)(nperm - i + 1)) : 0.0;
+            alive[x] = stay + up;
+        }
+        while (kb < j && ibdry[kb] == i) {
+            for (int x = 0; x <= kb; ++x) { crossed += alive[x]; alive[x] = 0.0; }
+            ++kb;
+        }
+    }
+    free(alive);
+    return crossed;
+}
+
+/* DNAcopy getbdry: out has max_ones*(max_ones+1)/2 entries */
+int cbso_getbdry(double eta, int nperm, int max_ones, int* out) {
+    const double tol = 1e-2;
+    int l = 0;
+    out[0] = nperm - (int)((double)nperm * eta);
+    double eta0 = eta;
+    l = 1;
+    for (int j = 2; j <= max_ones; ++j) {
+        int* b = out + l;
+        double etahi = eta0 * 1.1, etalo = eta0 * 0.25, phi, plo;
+        etabdry(nperm, etahi, j, b);
+        phi = pexceed(nperm, j, b);
+        etabdry(nperm, etalo, j, b);
+        plo = pexceed(nperm, j, b);
+        while ((etahi - etalo) / etalo > tol) {
+            eta0 = etalo + (etahi - etalo) * (eta - plo) / (phi - plo);
+            etabdry(nperm, eta0, j, b);
+            const double pex = pexceed(nperm, j, b);
+            if (pex > eta) { etahi = eta0; phi = pex; } else { etalo = eta0; plo = pex; }
+        }
+        l += j;
+    }
+    return l;
+}
+
+/* ------------------------------------------------------------------ node statistics */
+typedef struct {
+    int n;
+    double* xc;   /* centred data            */
+    double* w;    /* weights                 */
+    double* rw;   /* sqrt(w)                 */
+    double* y;    /* xc * rw (exchangeable)  */
+    double* cw;   /* cumsum(w)/sqrt(sum w), cw[0..n-1]; cwp(i)= i? cw[i-1] : 0 */
+    double* S;    /* prefix sums, S[0..n]    */
+    double* t;    /* scratch terms           */
+    double tss;
+    double total; /* cw[n-1] */
+} node_t;
+
+static void node_alloc(node_t* N, int n) {
+    N->n = n;
+    N->xc = (double*)malloc(sizeof(double) * n);
+    N->w = (double*)malloc(sizeof(double) * n);
+    N->rw = (double*)malloc(sizeof(double) * n);
+    N->y = (double*)malloc(sizeof(double) * n);
+    N->cw = (double*)malloc(sizeof(double) * n);
+    N->S = (double*)malloc(sizeof(double) * (n + 1));
+    N->t = (double*)malloc(sizeof(double) * n);
+}
+static void node_free(node_t* N) {
+    free(N->xc); free(N->w); free(N->rw); free(N->y); free(N->cw); free(N->S); free(N->t);
+}
+
+static inline double cwp(const node_t* N, int i) { return i ? N->cw[i - 1] : 0.0; }
+
+/* max over linear arcs (i<j), al0 <= j-i <= n-al0, of (S_j-S_i)^2 / (c (total-c)), c = cwp_j-cwp_i.
+ * First maximum in (i, j) lexicographic order. */
+static double max_arc_full(const node_t* N, const double* S, int al0, int* bi, int* bj, long long* arcs) {
+    const int n = N->n;
+    double best = -1.0, bestlo = -1.0;
+    int ai = 0, aj = 0;
+    for (int i = 0; i <= n - al0; ++i) {
+        const double Si = S[i], ci = cwp(N, i);
+        int jhi = i + (n - al0);
+        if (jhi > n) jhi = n;
+        for (int j = i + al0; j <= jhi; ++j) {
+            const double d = S[j] - Si;
+            const double c = cwp(N, j) - ci;
+            const double den = c * (N->total - c);
+            const double num = d * d;
+            if (num > bestlo * den) { /* conservative prefilter; exact test below */
+                const double q = num / den;
+                if (q > best) { best = q; bestlo = q * (1.0 - 1e-12); ai = i; aj = j; }
+            }
+        }
+        if (arcs) *arcs += (jhi >= i + al0) ? (jhi - (i + al0) + 1) : 0;
+    }
+    *bi = ai; *bj = aj;
+    return best < 0.0 ? 0.0 : best;
+}
+
+static double t2_of(double bss, double tss, int n) {
+    if (tss <= bss + 0.0001) tss = bss + 1.0;
+    return bss / ((tss - bss) / ((double)n - 2.0));
+}
+
+/* hybrid permutation statistic: circular arcs of width al0..kmax over terms t[] */
+static double perm_stat_hybrid(const node_t* N, const double* wn, const double* t, int al0, int kmax, long long* arcs) {
+    const int n = N->n;
+    double best = 0.0;
+    for (int s = 0; s < n; ++s) {
+        double acc = 0.0, cacc = 0.0;
+        int pos = s;
+        for (int k = 1; k <= kmax; ++k) {
+            acc += t[pos];
+            cacc += wn[pos];
+            if (++pos == n) pos = 0;
+            if (k >= al0) {
+                const double q = (acc * acc) / (cacc * (N->total - cacc));
+                if (q > best) best = q;
+            }
+        }
+    }
+    if (arcs) *arcs += (long long)n * (kmax - al0 + 1);
+    return best;
+}
+
+/* ------------------------------------------------------------------ ternary-split flank test */
+static double wtpermp(const double* x, const double* w, const double* rw, int n1, int n2, const cbso_params* P,
+                      uint32_t lo, uint32_t hi, uint32_t tid, cbso_stats* st) {
+    const int n = n1 + n2;
+    if (n1 == 1 || n2 == 1) return 1.0;
+    double xsum1 = 0, xsum2 = 0, tss = 0, rn1 = 0, rn2 = 0;
+    for (int i = 0; i < n1; ++i) { xsum1 += w[i] * x[i]; tss += w[i] * (x[i] * x[i]); rn1 += w[i]; }
+    for (int i = n1; i < n; ++i) { xsum2 += w[i] * x[i]; tss += w[i] * (x[i] * x[i]); rn2 += w[i]; }
+    const double rn = rn1 + rn2;
+    const double xbar = (xsum1 + xsum2) / rn;
+    tss = tss - rn * (xbar * xbar);
+    int m1, s0;
+    double rm1, odiff;
+    if (n1 <= n2) { m1 = n1; s0 = 0; rm1 = rn1; odiff = fabs(xsum1 / rn1 - xbar); }
+    else { m1 = n2; s0 = n1; rm1 = rn2; odiff = fabs(xsum2 / rn2 - xbar); }
+    const double ostat = 0.99999 * odiff;
+    double tstat = rn * rm1 * (odiff * odiff) / (rn - rm1);
+    tstat = tstat / ((tss - tstat) / ((double)n - 2.0));
+    if (tstat > 25.0 && m1 >= 10) return 0.0;
+    if (st) st->tperm_tests++;
+    double* y = (double*)malloc(sizeof(double) * n);
+    for (int i = 0; i < n; ++i) y[i] = x[i] * rw[i];
+    int nrej = 0;
+    for (int p = 0; p < P->nperm; ++p) {
+        prp_t prp;
+        prp_init(&prp, P->seed, lo, hi, tid, (uint32_t)p, (uint32_t)n);
+        double xs = 0.0;
+        for (int k = 0; k < m1; ++k) xs += y[prp_eval(&prp, (uint32_t)(s0 + k))] * rw[s0 + k];
+        const double pstat = fabs(xs / rm1 - xbar);
+        if (ostat <= pstat) ++nrej;
+    }
+    free(y);
+    return (double)nrej / (double)P->nperm;
+}
+
+/* ------------------------------------------------------------------ wfindcpt */
+/* Tests the interval [lo,hi) of the arm; returns ncpt (0,1,2) and icpt relative to lo. */
+static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, const cbso_params* P,
+                    const int* sbdry, int icpt[2], cbso_stats* st, double* out_ostat1) {
+    const int n = hi - lo;
+    const double* x = x_arm + lo;
+    const double* w = w_arm + lo;
+    if (out_ostat1) *out_ostat1 = 0.0;
+    if (st) st->nodes++;
+    /* isTRUE(all.equal(diff(range(x)), 0)) -> no change point */
+    double mn = x[0], mx = x[0];
+    for (int i = 1; i < n; ++i) { if (x[i] < mn) mn = x[i]; if (x[i] > mx) mx = x[i]; }
+    if (mx - mn <= 1.4901161193847656e-08) return 0;
+
+    node_t N;
+    node_alloc(&N, n);
+    double sw = 0.0, swx = 0.0;
+    for (int i = 0; i < n; ++i) { sw += w[i]; swx += x[i] * w[i]; }
+    const double avg = swx / sw;
+    const double rsw = sqrt(sw);
+    double tss = 0.0, cs = 0.0, S = 0.0;
+    N.S[0] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        N.w[i] = w[i];
+        N.xc[i] = x[i] - avg;
+        N.rw[i] = sqrt(w[i]);
+        N.y[i] = N.xc[i] * N.rw[i];
+        tss += w[i] * (N.xc[i] * N.xc[i]);
+        cs += w[i];
+        N.cw[i] = cs / rsw;
+        S += N.xc[i] * w[i];
+        N.S[i + 1] = S;
+    }
+    N.tss = tss;
+    N.total = N.cw[n - 1];
+
+    int ncpt = 0, ai, aj;
+    const int al0 = P->min_width;
+    const double bss = max_arc_full(&N, N.S, al0, &ai, &aj, st ? &st->obs_arcs : NULL);
+    const double t2 = t2_of(bss, tss, n);
+    const double ostat1 = sqrt(t2);
+    const double ostat = t2 * 0.99999;
+    if (out_ostat1) *out_ostat1 = ostat1;
+    int split = 0;
+    if (ostat1 <= 0.1) goto done;
+    {
+        const int l = (aj - ai < n - aj + ai) ? (aj - ai) : (n - aj + ai);
+        if (ostat1 >= 7.0 && l >= 10) { split = 1; }
+    }
+    if (!split) {
+        const int hybrid = P->hybrid && (n > P->nmin);
+        int nrejc, nrej = 0, k;
+        double* wn = NULL;
+        if (hybrid) {
+            const double delta = ((double)P->kmax + 1.0) / (double)n;
+            const double pval1 = cbso_tailp(ostat1, delta, n, P->ngrid, P->tol);
+            if (pval1 > P->alpha) goto done;
+            nrejc = (int)((P->alpha - pval1) * (double)P->nperm);
+            wn = (double*)malloc(sizeof(double) * n);
+            for (int i = 0; i < n; ++i) wn[i] = w[i] / rsw;
+        } else {
+            nrejc = (int)(P->alpha * (double)P->nperm);
+        }
+        k = nrejc * (nrejc + 1) / 2 + 1;
+        if (st) st->perm_tests++;
+        split = 1; /* surviving all permutations accepts the split */
+        for (int np = 1; np <= P->nperm; ++np) {
+            prp_t prp;
+            prp_init(&prp, P->seed, (uint32_t)lo, (uint32_t)hi, 0u, (uint32_t)(np - 1), (uint32_t)n);
+            for (int i = 0; i < n; ++i) N.t[i] = N.y[prp_eval(&prp, (uint32_t)i)] * N.rw[i];
+            double pbss;
+            if (hybrid) {
+                pbss = perm_stat_hybrid(&N, wn, N.t, al0, P->kmax, st ? &st->perm_arcs : NULL);
+            } else {
+                double* Sp = (double*)malloc(sizeof(double) * (n + 1));
+                Sp[0] = 0.0;
+                for (int i = 0; i < n; ++i) Sp[i + 1] = Sp[i] + N.t[i];
+                int pi, pj;
+                pbss = max_arc_full(&N, Sp, al0, &pi, &pj, st ? &st->perm_arcs : NULL);
+                free(Sp);
+            }
+            if (st) st->perms_run++;
+            const double pstat = t2_of(pbss, tss, n);
+            if (ostat <= pstat) { ++nrej; ++k; }
+            if (nrej > nrejc) { split = 0; break; }
+            if (np >= sbdry[k - 1]) { split = 1; break; }
+        }
+        free(wn);
+        if (!split) goto done;
+    }
+    /* ternary split bookkeeping (changepoints.f label 200) */
+    if (aj == n) { ncpt = 1; icpt[0] = ai; }
+    else if (ai == 0) { ncpt = 1; icpt[0] = aj; }
+    else {
+        double tp = wtpermp(N.xc, N.w, N.rw, ai, aj - ai, P, (uint32_t)lo, (uint32_t)hi, 1u, st);
+        if (tp <= P->alpha) { ncpt = 1; icpt[0] = ai; }
+        tp = wtpermp(N.xc + ai, N.w + ai, N.rw + ai, aj - ai, n - aj, P, (uint32_t)lo, (uint32_t)hi, 2u, st);
+        if (tp <= P->alpha) { icpt[ncpt] = aj; ++ncpt; }
+        if (ncpt == 0) { ncpt = 2; icpt[0] = ai; icpt[1] = aj; }
+    }
+done:
+    node_free(&N);
+    return ncpt;
+}
+
+/* One node, for unit tests: returns ncpt, fills icpt and the observed sqrt(T^2). */
+int cbso_find_cpt(const double* x, const double* w, int lo, int hi, const cbso_params* P, const int* sbdry,
+                  int* icpt, double* ostat1, cbso_stats* st) {
+    return find_cpt(x, w, lo, hi, P, sbdry, icpt, st, ostat1);
+}
+
+/* DNAcopy changepoints(): returns number of segments; seg_end[k] = exclusive end of segment k.
+ * seg_mean[k] = weighted.mean(log2, weight) as cbs.py:70-71 recomputes it. */
+int cbso_segment_arm(const double* x, const double* w, int n, const cbso_params* P, const int* sbdry,
+                     int* seg_end, double* seg_mean, cbso_stats* st) {
+    if (n <= 0) return 0;
+    int* stack = (int*)malloc(sizeof(int) * (size_t)(n + 2));
+    int* ends = (int*)malloc(sizeof(int) * (size_t)(n + 1));
+    int k = 2, nend = 0;
+    stack[0] = 0; stack[1] = n;
+    while (k > 1) {
+        const int lo = stack[k - 2], hi = stack[k - 1];
+        int icpt[2] = {0, 0}, ncpt = 0;
+        if (hi - lo >= 2 * P->min_width) ncpt = find_cpt(x, w, lo, hi, P, sbdry, icpt, st, NULL);
+        if (ncpt == 0) { ends[nend++] = hi; --k; }
+        else if (ncpt == 1) { stack[k - 1] = lo + icpt[0]; stack[k] = hi; ++k; }
+        else { stack[k - 1] = lo + icpt[0]; stack[k] = lo + icpt[1]; stack[k + 1] = hi; k += 2; }
+    }
+    /* ends were produced right-to-left */
+    for (int s = 0; s < nend; ++s) seg_end[s] = ends[nend - 1 - s];
+    int a = 0;
+    for (int s = 0; s < nend; ++s) {
+        double sw = 0.0, swx = 0.0;
+        for (int i = a; i < seg_end[s]; ++i) { swx += x[i] * w[i]; sw += w[i]; }
+        seg_mean[s] = swx / sw;
+        a = seg_end[s];
+    }
+    free(stack); free(ends);
+    return nend;
+}
+
+/* All arms of a sample (OpenMP over arms).  Outputs are per-arm slabs: segment s of arm a is at
+ * index arm_offsets[a] + s (an arm of n bins has at most n segments).  nseg[a] = count. */
+int cbso_segment(const double* x, const double* w, const int64_t* arm_offsets, int n_arms, const cbso_params* P,
+                 int64_t* seg_end, double* seg_mean, int* nseg, cbso_stats* st_out, int nthreads) {
+    const int max_ones = (int)floor((double)P->nperm * P->alpha) + 1;
+    const int sbn = max_ones * (max_ones + 1) / 2;
+    int* sbdry = (int*)malloc(sizeof(int) * (size_t)sbn);
+    cbso_getbdry(P->eta, P->nperm, max_ones, sbdry);
+    cbso_stats total;
+    memset(&total, 0, sizeof(total));
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int a = 0; a < n_arms; ++a) {
+        const int64_t lo = arm_offsets[a], hi = arm_offsets[a + 1];
+        const int n = (int)(hi - lo);
+        cbso_stats st;
+        memset(&st, 0, sizeof(st));
+        int* ends = (int*)malloc(sizeof(int) * (size_t)(n + 1));
+        nseg[a] = cbso_segment_arm(x + lo, w + lo, n, P, sbdry, ends, seg_mean + lo, &st);
+        for (int s = 0; s < nseg[a]; ++s) seg_end[lo + s] = lo + ends[s];
+        free(ends);
+#pragma omp critical
+        {
+            total.nodes += st.nodes; total.obs_arcs += st.obs_arcs; total.perm_arcs += st.perm_arcs;
+            total.perm_tests += st.perm_tests; total.perms_run += st.perms_run; total.tperm_tests += st.tperm_tests;
+        }
+    }
+    if (st_out) *st_out = total;
+    free(sbdry);
+    return 0;
+}
+
+/* exposed pieces for unit tests */
+double cbso_perm_pvalue_flank(const double* xc, const double* w, int n1, int n2, const cbso_params* P,
+                              uint32_t lo, uint32_t hi, uint32_t tid) {
+    double* rw = (double*)malloc(sizeof(double) * (size_t)(n1 + n2));
+    for (int i = 0; i < n1 + n2; ++i) rw[i] = sqrt(w[i]);
+    const double p = wtpermp(xc, w, rw, n1, n2, P, lo, hi, tid, NULL);
+    free(rw);
+    return p;
+}

@@ -1,0 +1,44 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/cnvkit_b200.h declares
+(no compute calls -- there is no GPU here), and the ctypes table covers the header."""
+import os
+import re
+
+from cnvkit_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "cnvkit_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cnvk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 10
+    for name in syms:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+
+
+def test_ctypes_table_matches_header():
+    assert sorted(_lib.SIGNATURES) == header_symbols()
+
+
+def test_abi_version_and_host_only_calls():
+    lib = _lib.load()
+    assert lib.cnvk_abi_version() == 1
+    from cnvkit_b200.segmentation import cbs
+
+    b = cbs.getbdry(0.05, 10000, 2)  # host-only entry point
+    assert b[0] == 9500 and len(b) == 3
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    import pytest
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError):
+        _lib.load()

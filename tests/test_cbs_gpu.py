@@ -1,0 +1,148 @@
+"""GPU parity: csrc/cbs.cu through the C ABI vs the CPU oracle (oracle/cbs_oracle.c).
+
+The oracle is a *restatement* of DNAcopy (parity unpinned -- see its header); what is asserted
+here is that the CUDA path reproduces it exactly: identical breakpoints, segment means within
+1e-9 relative, on the reference's own .cnr fixture and on synthetic data with planted
+change-points, through every decision path (shortcut split, tail approximation, hybrid and
+exact permutation tests, ternary-split flank tests)."""
+import numpy as np
+import pytest
+
+from oracle import cbs as OC
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    from cnvkit_b200.segmentation import cbs
+
+    return cbs
+
+
+def q6(a):
+    """%.6g quantisation applied at the DNAcopy boundary (segmentation/__init__.py:299-301)."""
+    return np.array([float("%.6g" % v) for v in a])
+
+
+def planted(rng, n, nseg, sigma=0.2):
+    x = rng.normal(0, sigma, n)
+    cuts = np.sort(rng.choice(np.arange(5, n - 5), size=min(nseg, max(0, (n - 10) // 12)), replace=False))
+    for a, b in zip(cuts[::2], cuts[1::2]):
+        x[a:b] += rng.choice([-1.0, -0.4, 0.3, 0.58, 1.0])
+    return x
+
+
+def compare(G, x, w, off, alpha, **kw):
+    P = OC.make_params(alpha=alpha, **kw)
+    o_arm, o_lo, o_hi, o_mean, o_st = OC.segment(x, w, off, P, nthreads=8)
+    g_arm, g_lo, g_hi, g_mean, g_st = G.segment_arms(x, w, off, alpha=alpha, **kw)
+    np.testing.assert_array_equal(g_arm, o_arm)
+    np.testing.assert_array_equal(g_lo, o_lo)
+    np.testing.assert_array_equal(g_hi, o_hi)
+    np.testing.assert_allclose(g_mean, o_mean, rtol=1e-9, atol=0)
+    return o_st, g_st
+
+
+def test_getbdry_matches_oracle(G):
+    for max_ones in (1, 2, 3, 11):
+        np.testing.assert_array_equal(G.getbdry(0.05, 10000, max_ones), OC.getbdry(0.05, 10000, max_ones))
+
+
+def test_planted_changepoints_mixed_arm_sizes(G):
+    rng = np.random.default_rng(11)
+    sizes = [1, 2, 3, 4, 5, 7, 40, 150, 199, 200, 201, 257, 600, 1023, 1024, 1025, 2500, 5000]
+    xs, ws = [], []
+    for n in sizes:
+        xs.append(planted(rng, n, 6) if n > 30 else rng.normal(0, 0.2, n))
+        ws.append(rng.uniform(0.5, 1.0, n))
+    x, w = q6(np.concatenate(xs)), q6(np.concatenate(ws))
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    o_st, g_st = compare(G, x, w, off, 1e-4)
+    assert g_st["nodes"] == o_st["nodes"]
+    # prune on/off give the same table
+    a = G.segment_arms(x, w, off, alpha=1e-4, prune=True)
+    b = G.segment_arms(x, w, off, alpha=1e-4, prune=False)
+    for u, v in zip(a[:4], b[:4]):
+        np.testing.assert_array_equal(u, v)
+    assert a[4]["obs_subtiles_scanned"] <= b[4]["obs_subtiles_scanned"]
+
+
+@pytest.mark.parametrize("alpha", [0.05, 0.01])
+def test_null_and_weak_signals_exercise_permutation_paths(G, alpha):
+    """Loose alpha + weak steps: many nodes land in the hybrid / exact permutation tests and
+    in the ternary-split flank tests; decisions must still agree one for one."""
+    rng = np.random.default_rng(int(alpha * 1000))
+    sizes = [60, 120, 180, 199, 230, 400, 800, 1500] * 3
+    xs, ws = [], []
+    for n in sizes:
+        x = rng.normal(0, 1.0, n)
+        if n % 3 == 0:
+            a = n // 3
+            x[a : a + max(6, n // 10)] += rng.choice([0.8, 1.2, -1.0])
+        xs.append(x)
+        ws.append(rng.uniform(0.2, 1.0, n))
+    x, w = q6(np.concatenate(xs)), q6(np.concatenate(ws))
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    o_st, g_st = compare(G, x, w, off, alpha)
+    assert o_st["perm_tests"] > 0 and g_st["perm_nodes"] == o_st["perm_tests"]
+
+
+def test_reference_fixture_p2_20_1(G, golden):
+    """C1: the reference's own exome .cnr (test/formats/p2-20_1.cnr), arms from by_arm()."""
+    g = golden("haar")
+    x, w = g["cnr__log2"], g["cnr__weight"]
+    keep = w > 0
+    assert keep.all()
+    compare(G, x, w, g["arm_offsets"], 1e-4)
+
+
+def test_unit_weights_and_flat_arms(G):
+    rng = np.random.default_rng(5)
+    x = np.concatenate([np.full(300, 0.25), planted(rng, 700, 4), np.zeros(50)])
+    w = np.ones_like(x)
+    off = np.array([0, 300, 1000, 1050])
+    compare(G, q6(x), w, off, 1e-4)
+    arm, lo, hi, mean, _ = G.segment_arms(q6(x), w, off, alpha=1e-4)
+    assert (arm == 0).sum() == 1 and (arm == 2).sum() == 1
+
+
+def test_empty_and_single_bin(G):
+    arm, lo, hi, mean, st = G.segment_arms(np.zeros(0), np.zeros(0), np.array([0]), alpha=1e-4)
+    assert len(arm) == 0
+    arm, lo, hi, mean, st = G.segment_arms(np.array([0.7]), np.array([0.5]), np.array([0, 1]), alpha=1e-4)
+    assert list(lo) == [0] and list(hi) == [1] and mean[0] == pytest.approx(0.7)  # test_r.py:215-231
+
+
+def test_planted_step_two_segments(G):
+    """test/test_r.py:234-291: step at bin 60 of 120, sigma 0.02 -> exactly 2 segments."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.normal(0.0, 0.02, 60), rng.normal(-1.0, 0.02, 60)])
+    arm, lo, hi, mean, _ = G.segment_arms(q6(x), np.ones(120), np.array([0, 120]), alpha=1e-4)
+    assert list(lo) == [0, 60] and list(hi) == [60, 120]
+
+
+def test_c3_scale_properties(G):
+    """One long WGS-like arm (125k bins): planted breakpoints are recovered, every segment mean
+    equals the weighted mean of its bins, the table tiles the arm, prune on/off agree."""
+    rng = np.random.default_rng(33)
+    n = 125_000
+    x = rng.normal(0, 0.25, n)
+    truth = [20_000, 20_400, 61_000, 90_000, 90_050]
+    lvl = [0.0, 0.58, 0.0, -1.0, 0.0, 1.0]
+    edges = [0] + truth + [n]
+    for k in range(len(edges) - 1):
+        x[edges[k] : edges[k + 1]] += lvl[k]
+    w = rng.uniform(0.5, 1.0, n)
+    x, w = np.round(x, 5), np.round(w, 5)
+    off = np.array([0, n])
+    arm, lo, hi, mean, st = G.segment_arms(x, w, off, alpha=1e-4)
+    assert lo[0] == 0 and hi[-1] == n and (lo[1:] == hi[:-1]).all()
+    for t in truth:
+        assert np.min(np.abs(hi - t)) <= 3, (t, hi)
+    for a, b, m in zip(lo, hi, mean):
+        assert m == pytest.approx(np.average(x[a:b], weights=w[a:b]), rel=1e-9)
+    arm2, lo2, hi2, mean2, st2 = G.segment_arms(x, w, off, alpha=1e-4, prune=False)
+    np.testing.assert_array_equal(lo, lo2)
+    np.testing.assert_array_equal(hi, hi2)
+    assert st["obs_subtiles_scanned"] < st2["obs_subtiles_scanned"]
