@@ -28,6 +28,12 @@ SIGNATURES = {
     "cnvk_abi_version": (c_int, []),
     "cnvk_launch_count": (c_ulonglong, []),
     "cnvk_device_info": (c_int, [c_int, POINTER(c_int), POINTER(c_uint64), POINTER(c_uint64)]),
+    "cnvk_fp64_peak": (c_int, [c_int, c_int, c_void_p]),
+    "cnvk_prof_enable": (None, [c_int]),
+    "cnvk_prof_reset": (None, []),
+    "cnvk_prof_count": (c_int, []),
+    "cnvk_prof_name": (c_char_p, [c_int]),
+    "cnvk_prof_get": (c_int, [c_void_p, c_void_p, c_int]),
     "cnvk_rolling_median_dev": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "cnvk_rolling_median": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
     "cnvk_rolling_quantile_dev": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p]),
@@ -103,6 +109,24 @@ def call(name: str, *args) -> None:
 
 def launch_count() -> int:
     return int(load().cnvk_launch_count())
+
+
+def prof_enable(on: bool = True) -> None:
+    load().cnvk_prof_enable(int(on))
+
+
+def prof_reset() -> None:
+    load().cnvk_prof_reset()
+
+
+def prof_get() -> dict:
+    """{class name: (milliseconds, timed scopes)} accumulated since the last reset."""
+    lib = load()
+    n = lib.cnvk_prof_count()
+    ms = np.zeros(n, dtype=np.float64)
+    cnt = np.zeros(n, dtype=np.uint64)
+    lib.cnvk_prof_get(ms.ctypes.data, cnt.ctypes.data, n)
+    return {lib.cnvk_prof_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n)}
 
 
 def f64(a) -> np.ndarray:

@@ -5,9 +5,40 @@
 #include <vector>
 
 #include "ops.cuh"
+#include "prof.cuh"
 
 namespace cnvk {
 unsigned long long g_launch_count = 0;
+int g_prof_enabled = 0;
+struct ProfPending { int cls; cudaEvent_t a, b; };
+static std::vector<ProfPending> g_prof_pending;
+static double g_prof_ms[PC_COUNT];
+static unsigned long long g_prof_n[PC_COUNT];
+void prof_begin(int cls, cudaStream_t stream, cudaEvent_t* start) {
+    if (cudaEventCreate(start) != cudaSuccess) { *start = nullptr; return; }
+    cudaEventRecord(*start, stream);
+}
+void prof_end(int cls, cudaStream_t stream, cudaEvent_t start) {
+    cudaEvent_t stop;
+    if (cudaEventCreate(&stop) != cudaSuccess) { cudaEventDestroy(start); return; }
+    cudaEventRecord(stop, stream);
+    g_prof_pending.push_back({cls, start, stop});
+}
+static void prof_collect() {
+    for (auto& p : g_prof_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            g_prof_ms[p.cls] += ms;
+            g_prof_n[p.cls] += 1;
+        }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    g_prof_pending.clear();
+}
+static const char* const kProfNames[PC_COUNT] = {
+    "radix_sort", "wavelet_build", "window_query", "cbs_prep", "cbs_scan", "cbs_decide", "cbs_perm_hybrid",
+    "cbs_perm_exact", "cbs_flank", "fix", "haar", "biweight", "other"};
 static thread_local char g_err[1024] = "";
 void set_last_error(const char* fmt, ...) {
     va_list ap;
@@ -64,6 +95,21 @@ extern "C" {
 const char* cnvk_last_error(void) { return g_err; }
 int cnvk_abi_version(void) { return 1; }
 unsigned long long cnvk_launch_count(void) { return g_launch_count; }
+
+void cnvk_prof_enable(int on) { g_prof_enabled = on; }
+void cnvk_prof_reset(void) {
+    prof_collect();
+    for (int k = 0; k < PC_COUNT; ++k) { g_prof_ms[k] = 0.0; g_prof_n[k] = 0; }
+}
+int cnvk_prof_count(void) { return PC_COUNT; }
+const char* cnvk_prof_name(int cls) { return (cls >= 0 && cls < PC_COUNT) ? kProfNames[cls] : ""; }
+int cnvk_prof_get(double* ms, unsigned long long* scopes, int n) {
+    prof_collect();
+    for (int k = 0; k < n && k < PC_COUNT; ++k) { ms[k] = g_prof_ms[k]; scopes[k] = g_prof_n[k]; }
+    return 0;
+}
+
+int cnvk_fp64_peak(int iters, int reps, double* tflops) { return fp64_peak(iters, reps, tflops, nullptr); }
 
 int cnvk_device_info(int device, int* sm_count, uint64_t* free_bytes, uint64_t* total_bytes) {
     cudaDeviceProp prop;

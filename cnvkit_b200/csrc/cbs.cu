@@ -29,6 +29,7 @@
 
 #include "cbs_rng.cuh"
 #include "ops.cuh"
+#include "prof.cuh"
 
 namespace cnvk {
 
@@ -917,9 +918,13 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         CNVK_CHECK(cudaMemcpyAsync(d_nodes, h_nodes.data(), nn * sizeof(Node), cudaMemcpyHostToDevice, stream));
         CNVK_CHECK(cudaMemcpyAsync(d_tile_off, h_tile_off.data(), (nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
         CNVK_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(int), stream));
-        cbs_prep_kernel<<<nn, 256, 0, stream>>>(d_nodes, d_x, d_w, d_xc, d_y, d_S, d_cw, d_wn, d_bmin, d_bmax, P.min_width);
-        CNVK_LAUNCH_CHECK();
         {
+            ProfScope ps(PC_CBS_PREP, stream);
+            cbs_prep_kernel<<<nn, 256, 0, stream>>>(d_nodes, d_x, d_w, d_xc, d_y, d_S, d_cw, d_wn, d_bmin, d_bmax, P.min_width);
+            CNVK_LAUNCH_CHECK();
+        }
+        {
+            ProfScope ps(PC_CBS_SCAN, stream);
             const int grid = (int)std::min<long long>(tiles, (long long)sm_count * 8);
             if (grid > 0) {
                 if (P.prune)
@@ -929,8 +934,11 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 CNVK_LAUNCH_CHECK();
             }
         }
-        cbs_decide_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, nn, d_dec, P.alpha, P.nperm, P.kmax, P.nmin, P.hybrid, 100, 1e-6);
-        CNVK_LAUNCH_CHECK();
+        {
+            ProfScope ps(PC_CBS_DECIDE, stream);
+            cbs_decide_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, nn, d_dec, P.alpha, P.nperm, P.kmax, P.nmin, P.hybrid, 100, 1e-6);
+            CNVK_LAUNCH_CHECK();
+        }
         h_dec.resize(nn);
         CNVK_CHECK(cudaMemcpyAsync(h_dec.data(), d_dec, nn * sizeof(Decision), cudaMemcpyDeviceToHost, stream));
         CNVK_CHECK(cudaStreamSynchronize(stream));
@@ -963,6 +971,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 CNVK_CHECK(ps.alloc(&d_flags, (size_t)na * chunk));
                 CNVK_CHECK(cudaMemcpyAsync(d_list, active.data(), na * sizeof(int), cudaMemcpyHostToDevice, stream));
                 CNVK_CHECK(cudaMemsetAsync(d_pmax, 0, (size_t)na * chunk * sizeof(unsigned long long), stream));
+                ProfScope pscope(mode == ST_PERM_HYBRID ? PC_CBS_PERM_HYBRID : PC_CBS_PERM_EXACT, stream);
                 if (mode == ST_PERM_HYBRID) {
                     int maxn = 0;
                     for (int k : active) maxn = std::max(maxn, frontier[k].hi - frontier[k].lo);
@@ -1034,6 +1043,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             FlankTest* d_tests;
             CNVK_CHECK(fs.alloc(&d_tests, (size_t)nt));
             CNVK_CHECK(cudaMemcpyAsync(d_tests, tests.data(), nt * sizeof(FlankTest), cudaMemcpyHostToDevice, stream));
+            ProfScope fscope(PC_CBS_FLANK, stream);
             cbs_flank_prep_kernel<<<div_up(nt, 4), 128, 0, stream>>>(d_nodes, d_tests, nt, d_xc, d_w, P.nperm);
             CNVK_LAUNCH_CHECK();
             CNVK_CHECK(cudaMemcpyAsync(tests.data(), d_tests, nt * sizeof(FlankTest), cudaMemcpyDeviceToHost, stream));

@@ -8,6 +8,9 @@ namespace cnvk {
 int rolling_window_stat(const double* d_x, long long n, long long wing, int mode, double q, int min_periods,
                         double* d_out, cudaStream_t stream);
 
+// peak.cu
+int fp64_peak(int iters, int reps, double* tflops, cudaStream_t stream);
+
 // cbs.cu
 struct CbsParams {
     double alpha;

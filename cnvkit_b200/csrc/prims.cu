@@ -7,6 +7,7 @@
 //                    per-warp digit counters + a cross-warp scan give the in-tile stable rank.
 // HBM traffic per pass: keys+vals read twice (hist + scatter) and written once.
 #include "prims.cuh"
+#include "prof.cuh"
 
 namespace cnvk {
 
@@ -199,6 +200,7 @@ int radix_sort_pairs(u64* keys, u64* keys_alt, u32* vals, u32* vals_alt, long lo
         set_last_error("radix_sort_pairs: n=%lld exceeds 2^32", n);
         return -1;
     }
+    ProfScope pscope(PC_SORT, stream);
     Scratch scratch(stream);
     const int ntiles = div_up(n, SORT_TILE);
     u32* counts = nullptr;

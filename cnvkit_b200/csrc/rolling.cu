@@ -15,6 +15,7 @@
 //      counts (only possible when NaNs are present) average the two middle elements as
 //      pandas' roll_median_c does.
 #include "prims.cuh"
+#include "prof.cuh"
 
 namespace cnvk {
 
@@ -257,6 +258,7 @@ int rolling_window_stat(const double* d_x, long long n, long long wing, int mode
     CNVK_LAUNCH_CHECK();
     u32* sin = seq0;
     u32* sout = seq1;
+    ProfScope* wscope = new ProfScope(PC_WAVELET_BUILD, stream);
     for (int lev = 0; lev < levels; ++lev) {
         const int bit = levels - 1 - lev;
         wm_count_kernel<<<nblocks, WM_BLOCK, 0, stream>>>(sin, M, bit, block_ones);
@@ -268,7 +270,9 @@ int rolling_window_stat(const double* d_x, long long n, long long wing, int mode
         CNVK_LAUNCH_CHECK();
         u32* t = sin; sin = sout; sout = t;
     }
+    delete wscope;
     // 3. queries
+    ProfScope qscope(PC_WINDOW_QUERY, stream);
     WmView wm;
     wm.dir = dir;
     wm.zeros = zeros;

@@ -34,6 +34,19 @@ unsigned long long cnvk_launch_count(void);
 /* Device properties the host layer wants without importing torch: SM count, free/total bytes. */
 int cnvk_device_info(int device, int* sm_count, uint64_t* free_bytes, uint64_t* total_bytes);
 
+/* Measured FP64 FMA throughput of the device (TFLOP/s, best of `reps` runs of a register-only DFMA
+ * stream): the roofline denominator bench.py uses for the CBS arc scan. */
+int cnvk_fp64_peak(int iters, int reps, double* tflops);
+
+/* Per-kernel-class device timing (CUDA events on the launching stream), off by default.
+ * cnvk_prof_get synchronises on the recorded events and returns accumulated milliseconds and the
+ * number of timed scopes per class; class names come from cnvk_prof_name(0..cnvk_prof_count()-1). */
+void cnvk_prof_enable(int on);
+void cnvk_prof_reset(void);
+int cnvk_prof_count(void);
+const char* cnvk_prof_name(int cls);
+int cnvk_prof_get(double* ms, unsigned long long* scopes, int n);
+
 /* ---- smoothing --------------------------------------------------------------------- */
 /* cnvlib/smoothing.py:77-87 rolling_median  (pandas rolling(2*wing+1, 1, center=True).median()
  * over the mirror padding of smoothing.py:72-74).  `wing` is the integer half-window the host
