@@ -50,12 +50,35 @@ void set_last_error(const char* fmt, ...) {
 
 using namespace cnvk;
 
+// Keep freed scratch in the stream-ordered pool across synchronisations (the default release
+// threshold of 0 hands it back to the driver at every sync, which costs milliseconds per level).
+static int ensure_init() {
+    static thread_local int done_for = -1;
+    int dev = 0;
+    CNVK_CHECK(cudaGetDevice(&dev));
+    if (done_for != dev) {
+        cudaMemPool_t pool;
+        CNVK_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long thr = ~0ull;
+        CNVK_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        done_for = dev;
+    }
+    return 0;
+}
+
+#define RC0(expr)              \
+    do {                       \
+        int _rc = (expr);      \
+        if (_rc) return _rc;   \
+    } while (0)
+
 // Host-buffer helper: stage inputs, run, fetch outputs on a private stream.
 struct HostCall {
     cudaStream_t stream;
     Scratch* scratch;
     HostCall() : stream(nullptr), scratch(nullptr) {}
     int begin() {
+        RC0(ensure_init());
         CNVK_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         scratch = new Scratch(stream);
         return 0;
@@ -124,10 +147,12 @@ int cnvk_device_info(int device, int* sm_count, uint64_t* free_bytes, uint64_t* 
 }
 
 int cnvk_rolling_median_dev(const double* d_x, int64_t n, int64_t wing, double* d_out, void* stream) {
+    RC(ensure_init());
     return rolling_window_stat(d_x, n, wing, 0, 0.5, 1, d_out, (cudaStream_t)stream);
 }
 
 int cnvk_rolling_quantile_dev(const double* d_x, int64_t n, int64_t wing, double q, double* d_out, void* stream) {
+    RC(ensure_init());
     return rolling_window_stat(d_x, n, wing, 1, q, 2, d_out, (cudaStream_t)stream);
 }
 
@@ -151,6 +176,7 @@ int cnvk_rolling_quantile(const double* x, int64_t n, int64_t wing, double q, do
 }
 
 int cnvk_argsort_f64_dev(const double* d_x, int64_t n, uint32_t* d_order, void* stream) {
+    RC(ensure_init());
     return argsort_f64(d_x, n, d_order, (cudaStream_t)stream);
 }
 
@@ -185,6 +211,7 @@ static int cbs_common(const double* d_x, const double* d_w, const int64_t* arm_o
 int cnvk_cbs_segment_dev(const double* d_log2, const double* d_weight, const int64_t* arm_offsets, int32_t n_arms,
                          const cnvk_cbs_params* params, int64_t capacity, int32_t* seg_arm, int64_t* seg_lo,
                          int64_t* seg_hi, double* seg_mean, int64_t* n_segs, cnvk_cbs_stats* stats, void* stream) {
+    RC(ensure_init());
     return cbs_common(d_log2, d_weight, arm_offsets, n_arms, params, capacity, seg_arm, seg_lo, seg_hi, seg_mean,
                       n_segs, stats, (cudaStream_t)stream);
 }

@@ -283,116 +283,168 @@ __device__ __forceinline__ void scan_subtiles(Cand& best, const double2* __restr
     }
 }
 
+// Work item ("task") = (node, 1024-point start block ib, chunk of up to 256 consecutive 256-point
+// end blocks).  The 256 threads first test the pruning bound of one end block each (4 sub-tiles),
+// the survivors are compacted into shared memory and then scanned one after the other.
+struct Survivor {
+    int jb;
+    unsigned mask;
+};
+
 template <bool PRUNE>
 __global__ void __launch_bounds__(256)
-cbs_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ tile_off, int nnodes, int total_tiles,
-                int* __restrict__ tile_counter, const double* __restrict__ S, const double* __restrict__ cw,
+cbs_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ task_off, int nnodes, int total_tasks,
+                int* __restrict__ task_counter, const double* __restrict__ S, const double* __restrict__ cw,
                 const double* __restrict__ blk_min, const double* __restrict__ blk_max, int al0,
                 unsigned long long* __restrict__ stats) {
     __shared__ double2 sj[CBS_BLK];
-    __shared__ int s_tile;
+    __shared__ Survivor s_list[256];
+    __shared__ int s_task, s_nsurv;
+    __shared__ int s_warp_cnt[8];
     __shared__ double s_q[8];
     __shared__ int s_i[8], s_j[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned long long my_subtiles = 0, my_checked = 0;
+    unsigned long long my_scanned = 0, my_checked = 0;
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(tile_counter, 1);
+        if (tid == 0) s_task = atomicAdd(task_counter, 1);
         __syncthreads();
-        const int tile = s_tile;
-        if (tile >= total_tiles) break;
-        // node lookup
+        const int task = s_task;
+        if (task >= total_tasks) break;
         int a = 0, b = nnodes;
         while (b - a > 1) {
             const int m = (a + b) >> 1;
-            if (tile_off[m] <= tile) a = m; else b = m;
+            if (task_off[m] <= task) a = m; else b = m;
         }
         Node* nd = &nodes[a];
         const int lo = nd->lo, n = nd->hi - nd->lo;
         const int P = n + 1;
         const int NJ = (P + CBS_BLK - 1) / CBS_BLK;
-        int t = tile - tile_off[a];
+        int t = task - task_off[a];
         int ib = 0;
         for (;;) {
-            const int cnt = NJ - CBS_IW * ib;
+            const int cnt = (max(0, NJ - CBS_IW * ib) + 255) / 256;
             if (t < cnt) break;
             t -= cnt;
             ++ib;
         }
-        const int jb = CBS_IW * ib + t;
+        const int jb0 = CBS_IW * ib + 256 * t;
         const double total = nd->total;
-        const double gq = *((volatile double*)&nd->best_q);
-        const int jbase = jb * CBS_BLK;
-        const int jcount = min(CBS_BLK, P - jbase);
-        // which 256x256 sub-tiles can matter
-        unsigned act_mask = 0;
-        int na = 0;
-        bool masked = false;
+        const int boff = nd->blk_off;
+        double gq = *((volatile double*)&nd->best_q);
+
+        // ---- bound test: thread <-> one end block
+        unsigned mask = 0;
+        bool any_masked = false;
+        {
+            const int jb = jb0 + tid;
+            if (jb < NJ) {
+                const int jbase = jb * CBS_BLK;
+                const int jend = min(jbase + CBS_BLK - 1, n);
+                double jmx = 0, jmn = 0, cj0 = 0, cj1 = 0;
+                if (PRUNE) {
+                    jmx = blk_max[boff + jb]; jmn = blk_min[boff + jb];
+                    cj0 = pt(cw, lo, jbase); cj1 = pt(cw, lo, jend);
+                }
 #pragma unroll
-        for (int r = 0; r < CBS_IW; ++r) {
-            const int bi = CBS_IW * ib + r;
-            const int ibase = bi * CBS_BLK;
-            if (ibase > n || bi > jb) continue;
-            const int iend = min(ibase + CBS_BLK - 1, n);
-            const int jend = jbase + jcount - 1;
-            bool need = true;
-            if (PRUNE && bi < jb && gq >= 0.0) {
-                const double d1 = blk_max[nd->blk_off + jb] - blk_min[nd->blk_off + bi];
-                const double d2 = blk_max[nd->blk_off + bi] - blk_min[nd->blk_off + jb];
-                const double dm = fmax(fabs(d1), fabs(d2));
-                const double cmin = pt(cw, lo, jbase) - pt(cw, lo, iend);
-                const double cmax = pt(cw, lo, jend) - pt(cw, lo, ibase);
-                const double f1 = cmin * (total - cmin), f2 = cmax * (total - cmax);
-                const double fmin_ = fmin(f1, f2);
-                if (fmin_ > 0.0) {
-                    const double ub = (dm * dm) / fmin_ * (1.0 + 1e-9);
-                    need = !(ub < gq);
+                for (int r = 0; r < CBS_IW; ++r) {
+                    const int bi = CBS_IW * ib + r;
+                    const int ibase = bi * CBS_BLK;
+                    if (ibase > n || bi > jb) continue;
+                    const int iend = min(ibase + CBS_BLK - 1, n);
+                    bool need = true;
+                    if (PRUNE && bi < jb && gq >= 0.0) {
+                        const double d1 = jmx - blk_min[boff + bi];
+                        const double d2 = blk_max[boff + bi] - jmn;
+                        const double dm = fmax(fabs(d1), fabs(d2));
+                        const double cmin = cj0 - pt(cw, lo, iend);
+                        const double cmax = cj1 - pt(cw, lo, ibase);
+                        const double fmin_ = fmin(cmin * (total - cmin), cmax * (total - cmax));
+                        if (fmin_ > 0.0) need = !((dm * dm) / fmin_ * (1.0 + 1e-9) < gq);
+                    }
+                    ++my_checked;
+                    if (need) mask |= 1u << r;
                 }
             }
-            if (tid == 0) ++my_checked;
-            if (!need) continue;
-            act_mask |= 1u << r;
-            ++na;
-            if (!(jbase - iend >= al0 && jend - ibase <= n - al0 && ibase + CBS_BLK - 1 <= n)) masked = true;
         }
-        if (na == 0) continue;
-        if (tid == 0) my_subtiles += na;
-        // stage the j block
-        if (tid < jcount) sj[tid] = make_double2(pt(S, lo, jbase + tid), pt(cw, lo, jbase + tid));
-        double Si[CBS_IW], ci[CBS_IW];
-        int ii[CBS_IW];
-#pragma unroll
-        for (int r = 0; r < CBS_IW; ++r) {
-            const int slot = (int)__fns(act_mask, 0, (r < na) ? r + 1 : 1);
-            const int i = (CBS_IW * ib + slot) * CBS_BLK + tid;
-            ii[r] = i;
-            const bool ok = i <= n;
-            Si[r] = ok ? pt(S, lo, i) : 0.0;
-            ci[r] = ok ? pt(cw, lo, i) : 0.0;
+        // ---- compact survivors
+        {
+            const unsigned bal = __ballot_sync(0xffffffffu, mask != 0);
+            if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int base = 0;
+            for (int k = 0; k < warp; ++k) base += s_warp_cnt[k];
+            if (mask) {
+                Survivor sv;
+                sv.jb = jb0 + tid;
+                sv.mask = mask;
+                s_list[base + __popc(bal & ((1u << lane) - 1u))] = sv;
+            }
+            if (tid == 0) {
+                int tot = 0;
+                for (int k = 0; k < 8; ++k) tot += s_warp_cnt[k];
+                s_nsurv = tot;
+            }
+            __syncthreads();
         }
-        __syncthreads();
+        const int nsurv = s_nsurv;
+        if (nsurv == 0) continue;
+
         Cand best;
         best.q = gq;
-        best.qlo = gq * (1.0 - 1e-12);
-        if (gq < 0.0) best.qlo = -1.0;
+        best.qlo = (gq < 0.0) ? -1.0 : gq * (1.0 - 1e-12);
         best.i = 0x7fffffff;
         best.j = 0x7fffffff;
-        if (masked) {
-            switch (na) {
-                case 1: scan_subtiles<1, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                case 2: scan_subtiles<2, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                case 3: scan_subtiles<3, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                default: scan_subtiles<4, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+        for (int sidx = 0; sidx < nsurv; ++sidx) {
+            const Survivor sv = s_list[sidx];
+            const int jb = sv.jb;
+            const int jbase = jb * CBS_BLK;
+            const int jcount = min(CBS_BLK, P - jbase);
+            const int jend = jbase + jcount - 1;
+            const int na = __popc(sv.mask);
+            bool masked = false;
+#pragma unroll
+            for (int r = 0; r < CBS_IW; ++r) {
+                if (!(sv.mask & (1u << r))) continue;
+                const int ibase = (CBS_IW * ib + r) * CBS_BLK;
+                const int iend = min(ibase + CBS_BLK - 1, n);
+                if (!(jbase - iend >= al0 && jend - ibase <= n - al0 && ibase + CBS_BLK - 1 <= n)) masked = true;
             }
-        } else {
-            switch (na) {
-                case 1: scan_subtiles<1, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                case 2: scan_subtiles<2, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                case 3: scan_subtiles<3, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                default: scan_subtiles<4, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+            my_scanned += (tid == 0) ? na : 0;
+            __syncthreads();  // previous sj consumers are done
+            if (tid < jcount) sj[tid] = make_double2(pt(S, lo, jbase + tid), pt(cw, lo, jbase + tid));
+            double Si[CBS_IW], ci[CBS_IW];
+            int ii[CBS_IW];
+#pragma unroll
+            for (int r = 0; r < CBS_IW; ++r) {
+                const int slot = (int)__fns(sv.mask, 0, (r < na) ? r + 1 : 1);
+                const int i = (CBS_IW * ib + slot) * CBS_BLK + tid;
+                ii[r] = i;
+                const bool ok = i <= n;
+                Si[r] = ok ? pt(S, lo, i) : 0.0;
+                ci[r] = ok ? pt(cw, lo, i) : 0.0;
+            }
+            // tighten the filter with whatever other CTAs have found meanwhile
+            const double gnow = *((volatile double*)&nd->best_q);
+            if (gnow > best.q) { best.q = gnow; best.qlo = gnow * (1.0 - 1e-12); best.i = 0x7fffffff; best.j = 0x7fffffff; }
+            __syncthreads();
+            if (masked) {
+                switch (na) {
+                    case 1: scan_subtiles<1, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                    case 2: scan_subtiles<2, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                    case 3: scan_subtiles<3, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                    default: scan_subtiles<4, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                }
+            } else {
+                switch (na) {
+                    case 1: scan_subtiles<1, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                    case 2: scan_subtiles<2, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                    case 3: scan_subtiles<3, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                    default: scan_subtiles<4, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                }
             }
         }
-        // CTA argmax (ties -> smallest (i,j)); only candidates found in this tile carry i != INT_MAX
+        // ---- CTA argmax (ties -> smallest (i,j)); only candidates found here carry i != INT_MAX
         double q = best.q;
         int qi = best.i, qj = best.j;
 #pragma unroll
@@ -422,9 +474,10 @@ cbs_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ tile_off, int 
             }
         }
     }
-    if (tid == 0 && stats) {
-        atomicAdd(&stats[0], my_subtiles);
-        atomicAdd(&stats[1], my_checked);
+    if (stats) {
+        my_checked = warp_sum_u32((u32)my_checked);
+        if (lane == 0) atomicAdd(&stats[1], my_checked);
+        if (tid == 0) atomicAdd(&stats[0], my_scanned);
     }
 }
 
@@ -468,72 +521,114 @@ __device__ __forceinline__ double t2_of(double bss, double tss, int n) {
     return bss / ((tss - bss) / ((double)n - 2.0));
 }
 
-// one warp per node
-__global__ void __launch_bounds__(128)
-cbs_decide_kernel(Node* __restrict__ nodes, int nnodes, Decision* __restrict__ dec, double alpha, int nperm,
-                  int kmax, int nmin, int hybrid_method, int ngrid, double tol) {
-    __shared__ double s_terms[4][128];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * 4 + warp;
+enum { ST_NEED_TAILP = 4 };
+
+// thread per node: observed T^2 and the decisions that need no p-value
+__global__ void cbs_stat_kernel(Node* __restrict__ nodes, int nnodes, double alpha, int nperm, int nmin,
+                                int hybrid_method) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nnodes) return;
     Node* nd = &nodes[idx];
     const int n = nd->hi - nd->lo;
     int state = ST_FINAL, nrejc = 0;
     double ostat = 0.0, ostat1 = 0.0;
-    const int bi = nd->best_i, bj = nd->best_j;
     if (!nd->flat && nd->best_q >= 0.0) {
         const double t2 = t2_of(nd->best_q, nd->tss, n);
         ostat1 = sqrt(t2);
         ostat = t2 * 0.99999;
         if (ostat1 > 0.1) {
+            const int bi = nd->best_i, bj = nd->best_j;
             const int l = min(bj - bi, n - bj + bi);
-            if (ostat1 >= 7.0 && l >= 10) {
-                state = ST_SPLIT;
-            } else if (hybrid_method && n > nmin) {
-                // tailp: ngrid terms evaluated by the lanes, summed in order by lane 0
-                const double delta = ((double)kmax + 1.0) / (double)n;
-                const double dincr = (0.5 - delta) / (double)ngrid;
-                const double bsqrtm = ostat1 / sqrt((double)n);
-                for (int g = lane; g < ngrid; g += 32) {
-                    double tl = 0.5 - dincr, tt = 0.5 - 0.5 * dincr;
-                    for (int s = 0; s < g; ++s) { tl -= dincr; tt -= dincr; }  // same rounding as the serial loop
-                    const double xx = bsqrtm / sqrt(tt * (1.0 - tt));
-                    const double nux = nu_dev(xx, tol);
-                    s_terms[warp][g] = (nux * nux) * it1tsq_dev(tl, dincr);
-                }
-                __syncwarp();
-                double p = 0.0;
-                if (lane == 0) {
-                    for (int g = 0; g < ngrid; ++g) p += s_terms[warp][g];
-                    p = 9.973557e-2 * (ostat1 * ostat1 * ostat1) * exp(-(ostat1 * ostat1) / 2.0) * p;
-                    p = 2.0 * p;
-                }
-                p = __shfl_sync(0xffffffffu, p, 0);
-                if (p > alpha) {
-                    state = ST_FINAL;
-                } else {
-                    state = ST_PERM_HYBRID;
-                    nrejc = (int)((alpha - p) * (double)nperm);
-                }
-            } else {
-                state = ST_PERM_EXACT;
-                nrejc = (int)(alpha * (double)nperm);
-            }
+            if (ostat1 >= 7.0 && l >= 10) state = ST_SPLIT;
+            else if (hybrid_method && n > nmin) state = ST_NEED_TAILP;
+            else { state = ST_PERM_EXACT; nrejc = (int)(alpha * (double)nperm); }
         }
     }
-    if (lane == 0) {
+    nd->state = state;
+    nd->nrejc = nrejc;
+    nd->ostat = ostat;
+    nd->ostat1 = ostat1;
+}
+
+// DNAcopy tailp: one CTA per (grid point, node).  nu(x)'s series is summed in the reference's
+// doubling blocks (2,2,4,8,...), each block split over the 128 threads and tree-reduced; the
+// relative-change stopping rule is evaluated between blocks exactly as in the serial code.
+__global__ void __launch_bounds__(128)
+cbs_tailp_terms_kernel(const Node* __restrict__ nodes, double* __restrict__ terms, int kmax, int ngrid, double tol) {
+    __shared__ double s_part[4];
+    __shared__ double s_sum;
+    const Node* nd = &nodes[blockIdx.y];
+    if (nd->state != ST_NEED_TAILP) return;
+    const int n = nd->hi - nd->lo;
+    const int g = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double b = nd->ostat1;
+    const double delta = ((double)kmax + 1.0) / (double)n;
+    const double dincr = (0.5 - delta) / (double)ngrid;
+    const double bsqrtm = b / sqrt((double)n);
+    double tl = 0.5 - dincr, tt = 0.5 - 0.5 * dincr;
+    for (int s = 0; s < g; ++s) { tl -= dincr; tt -= dincr; }  // same roundings as the serial loop
+    const double x = bsqrtm / sqrt(tt * (1.0 - tt));
+    double lnu1;
+    if (x > 0.01) {
+        lnu1 = log(2.0) - 2.0 * log(x);
+        double lnu0 = lnu1;
+        long long done = 0;
+        int k = 2;
+        bool first = true;
+        for (;;) {
+            double part = 0.0;
+            for (long long i = done + 1 + tid; i <= done + k; i += 128) {
+                const double dk = (double)i;
+                part += 2.0 * pnorm_std(-x * sqrt(dk) / 2.0) / dk;
+            }
+            part = warp_sum(part);
+            if (lane == 0) s_part[warp] = part;
+            __syncthreads();
+            if (tid == 0) s_sum = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+            __syncthreads();
+            lnu1 -= s_sum;
+            done += k;
+            if (!first) k *= 2;
+            first = false;
+            if (!(fabs((lnu1 - lnu0) / lnu1) > tol)) break;
+            lnu0 = lnu1;
+            __syncthreads();
+        }
+    } else {
+        lnu1 = -0.583 * x;
+    }
+    if (tid == 0) {
+        const double nux = exp(lnu1);
+        terms[(size_t)blockIdx.y * ngrid + g] = (nux * nux) * it1tsq_dev(tl, dincr);
+    }
+}
+
+// thread per node: finish the tail probability and the hybrid decision
+__global__ void cbs_decide_kernel(Node* __restrict__ nodes, int nnodes, Decision* __restrict__ dec,
+                                  const double* __restrict__ terms, double alpha, int nperm, int ngrid) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nnodes) return;
+    Node* nd = &nodes[idx];
+    int state = nd->state, nrejc = nd->nrejc;
+    if (state == ST_NEED_TAILP) {
+        const double b = nd->ostat1;
+        double p = 0.0;
+        for (int g = 0; g < ngrid; ++g) p += terms[(size_t)idx * ngrid + g];
+        p = 9.973557e-2 * (b * b * b) * exp(-(b * b) / 2.0) * p;
+        p = 2.0 * p;
+        if (p > alpha) state = ST_FINAL;
+        else { state = ST_PERM_HYBRID; nrejc = (int)((alpha - p) * (double)nperm); }
         nd->state = state;
         nd->nrejc = nrejc;
-        nd->ostat = ostat;
-        nd->ostat1 = ostat1;
-        Decision d;
-        d.state = state;
-        d.nrejc = nrejc;
-        d.best_i = bi;
-        d.best_j = bj;
-        d.ostat = ostat;
-        dec[idx] = d;
     }
+    Decision d;
+    d.state = state;
+    d.nrejc = nrejc;
+    d.best_i = nd->best_i;
+    d.best_j = nd->best_j;
+    d.ostat = nd->ostat;
+    dec[idx] = d;
 }
 
 // ------------------------------------------------------------------------------------ permutations
@@ -813,7 +908,7 @@ static int tiles_for(int n) {
     const int P = n + 1;
     const int NJ = (P + CBS_BLK - 1) / CBS_BLK, NI = (P + CBS_IBLK - 1) / CBS_IBLK;
     int t = 0;
-    for (int ib = 0; ib < NI; ++ib) t += std::max(0, NJ - CBS_IW * ib);
+    for (int ib = 0; ib < NI; ++ib) t += (std::max(0, NJ - CBS_IW * ib) + 255) / 256;
     return t;
 }
 
@@ -875,7 +970,10 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
     Node* d_nodes = nullptr;
     Decision* d_dec = nullptr;
     int* d_tile_off = nullptr;
+    double* d_terms = nullptr;
     auto free_level = [&]() {
+        if (d_terms) cudaFreeAsync(d_terms, stream);
+        d_terms = nullptr;
         if (d_nodes) cudaFreeAsync(d_nodes, stream);
         if (d_dec) cudaFreeAsync(d_dec, stream);
         if (d_tile_off) cudaFreeAsync(d_tile_off, stream);
@@ -897,6 +995,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             CNVK_CHECK(cudaMallocAsync((void**)&d_nodes, cap_nodes * sizeof(Node), stream));
             CNVK_CHECK(cudaMallocAsync((void**)&d_dec, cap_nodes * sizeof(Decision), stream));
             CNVK_CHECK(cudaMallocAsync((void**)&d_tile_off, (cap_nodes + 1) * sizeof(int), stream));
+            CNVK_CHECK(cudaMallocAsync((void**)&d_terms, cap_nodes * 100 * sizeof(double), stream));
         }
         h_nodes.assign(nn, Node());
         h_tile_off.assign(nn + 1, 0);
@@ -936,7 +1035,17 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         }
         {
             ProfScope ps(PC_CBS_DECIDE, stream);
-            cbs_decide_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, nn, d_dec, P.alpha, P.nperm, P.kmax, P.nmin, P.hybrid, 100, 1e-6);
+            const int ngrid = 100;
+            cbs_stat_kernel<<<div_up(nn, 128), 128, 0, stream>>>(d_nodes, nn, P.alpha, P.nperm, P.nmin, P.hybrid);
+            CNVK_LAUNCH_CHECK();
+            if (P.hybrid) {
+                for (int y0 = 0; y0 < nn; y0 += 32768) {
+                    const int ny = std::min(32768, nn - y0);
+                    cbs_tailp_terms_kernel<<<dim3(ngrid, ny), 128, 0, stream>>>(d_nodes + y0, d_terms + (size_t)y0 * ngrid, P.kmax, ngrid, 1e-6);
+                    CNVK_LAUNCH_CHECK();
+                }
+            }
+            cbs_decide_kernel<<<div_up(nn, 128), 128, 0, stream>>>(d_nodes, nn, d_dec, d_terms, P.alpha, P.nperm, ngrid);
             CNVK_LAUNCH_CHECK();
         }
         h_dec.resize(nn);
