@@ -39,6 +39,20 @@ SIGNATURES = {
     "cnvk_rolling_quantile_dev": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p]),
     "cnvk_rolling_quantile": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p]),
     "cnvk_argsort_f64_dev": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "cnvk_fix_mask_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "cnvk_center_all_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p,
+                                    c_void_p]),
+    "cnvk_center_by_window_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "cnvk_center_by_window": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64]),
+    "cnvk_edge_bias_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "cnvk_fix_group_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64,
+                                   c_void_p, c_int64, c_char_p, c_void_p, c_void_p]),
+    "cnvk_fix_finish_dev": (c_int, [c_void_p] * 9 + [c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "cnvk_segmented_median_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "cnvk_biweight": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "cnvk_biweight_columns_dev": (c_int, [c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "cnvk_biweight_columns": (c_int, [c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
     "cnvk_cbs_segment_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cnvk_cbs_segment": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p,

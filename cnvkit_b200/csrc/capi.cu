@@ -180,6 +180,118 @@ int cnvk_argsort_f64_dev(const double* d_x, int64_t n, uint32_t* d_order, void* 
     return argsort_f64(d_x, n, d_order, (cudaStream_t)stream);
 }
 
+int cnvk_fix_mask_dev(const double* d_sample_log2, const double* d_ref_log2, const double* d_ref_spread,
+                      const double* d_ref_depth, const double* d_ref_gc, int64_t n, uint8_t* d_keep, void* stream) {
+    RC(ensure_init());
+    return fix_mask(d_sample_log2, d_ref_log2, d_ref_spread, d_ref_depth, d_ref_gc, n, d_keep, (cudaStream_t)stream);
+}
+
+int cnvk_center_all_dev(double* d_log2, const double* d_depth, const uint8_t* d_sel, int64_t n,
+                        const int64_t* d_chrom_offsets, int32_t nchrom, int32_t skip_low, double* d_shift_out,
+                        void* stream) {
+    RC(ensure_init());
+    return center_all(d_log2, d_depth, d_sel, n, (const long long*)d_chrom_offsets, nchrom, skip_low, d_shift_out,
+                      (cudaStream_t)stream);
+}
+
+int cnvk_center_by_window_dev(double* d_log2, const double* d_key, const uint32_t* d_perm, int64_t n, int64_t wing,
+                              void* stream) {
+    RC(ensure_init());
+    return center_by_window(d_log2, d_key, d_perm, n, wing, (cudaStream_t)stream);
+}
+
+int cnvk_center_by_window(double* log2, const double* key, const uint32_t* perm, int64_t n, int64_t wing) {
+    HostCall hc;
+    RC(hc.begin());
+    double *dl, *dk;
+    uint32_t* dp;
+    RC(hc.upload(log2, (size_t)n, &dl));
+    RC(hc.upload(key, (size_t)n, &dk));
+    RC(hc.upload(perm, (size_t)n, &dp));
+    RC(center_by_window(dl, dk, dp, n, wing, hc.stream));
+    RC(hc.download(log2, dl, (size_t)n));
+    return hc.finish();
+}
+
+int cnvk_edge_bias_dev(const int64_t* d_start, const int64_t* d_end, const int32_t* d_chrom_id, int64_t n,
+                       int64_t margin, double* d_out, void* stream) {
+    RC(ensure_init());
+    return edge_bias((const long long*)d_start, (const long long*)d_end, d_chrom_id, n, margin, d_out,
+                     (cudaStream_t)stream);
+}
+
+int cnvk_fix_group_dev(double* d_log2, const double* d_depth, const uint8_t* d_auto_sel, int64_t n,
+                       const int64_t* d_chrom_offsets, int32_t nchrom, const int32_t* d_chrom_id,
+                       const int64_t* d_start, const int64_t* d_end, const double* d_gc, const double* d_rmask,
+                       const double* d_edge_key, int32_t do_edge, int32_t skip_low, int32_t do_center, int64_t wing,
+                       const uint32_t* d_perm, int64_t margin, const char* order, int32_t* skipped, void* stream) {
+    RC(ensure_init());
+    int sk = 0;
+    int rc = fix_group(d_log2, d_depth, d_auto_sel, n, (const long long*)d_chrom_offsets, nchrom, d_chrom_id,
+                       (const long long*)d_start, (const long long*)d_end, d_gc, d_rmask, d_edge_key, do_edge,
+                       skip_low, do_center, wing, d_perm, margin, order ? order : "ger", &sk, (cudaStream_t)stream);
+    if (skipped) *skipped = sk;
+    return rc;
+}
+
+int cnvk_fix_finish_dev(double* d_log2, const double* d_depth, const double* d_ref_log2, const double* d_ref_spread,
+                        const int64_t* d_start, const int64_t* d_end, const int32_t* d_chrom_id,
+                        const uint8_t* d_is_anti, const uint8_t* d_auto_sel, int64_t n,
+                        const int64_t* d_chrom_offsets, int32_t nchrom, double* d_weight, double* d_info,
+                        void* stream) {
+    RC(ensure_init());
+    return fix_finish(d_log2, d_depth, d_ref_log2, d_ref_spread, (const long long*)d_start, (const long long*)d_end,
+                      d_chrom_id, d_is_anti, d_auto_sel, n, (const long long*)d_chrom_offsets, nchrom, d_weight,
+                      d_info, (cudaStream_t)stream);
+}
+
+int cnvk_segmented_median_dev(const double* d_x, const uint8_t* d_use, const int64_t* d_seg_offsets, int32_t nseg,
+                              double* d_med, int32_t* d_cnt, void* stream) {
+    RC(ensure_init());
+    return segmented_median(d_x, d_use, (const long long*)d_seg_offsets, nseg, d_med, d_cnt, (cudaStream_t)stream);
+}
+
+int cnvk_biweight(const double* x, int64_t n, const double* initial, double* out) {
+    HostCall hc;
+    RC(hc.begin());
+    double *dx, *dsorted, *dout, *dinit = nullptr;
+    u64 *k0, *k1;
+    u32 *v0, *v1, *nvalid;
+    const size_t m = (size_t)(n > 0 ? n : 1);
+    RC(hc.upload(x, (size_t)n, &dx));
+    CNVK_CHECK(hc.scratch->alloc(&dsorted, m));
+    CNVK_CHECK(hc.scratch->alloc(&dout, 2));
+    CNVK_CHECK(hc.scratch->alloc(&k0, m));
+    CNVK_CHECK(hc.scratch->alloc(&k1, m));
+    CNVK_CHECK(hc.scratch->alloc(&v0, m));
+    CNVK_CHECK(hc.scratch->alloc(&v1, m));
+    CNVK_CHECK(hc.scratch->alloc(&nvalid, 1));
+    if (initial) RC(hc.upload(initial, 1, &dinit));
+    RC(sort_values_f64(dx, n, k0, k1, v0, v1, dsorted, nvalid, hc.stream));
+    RC(biweight_of_sorted(dsorted, nvalid, 0, dinit, dout, hc.stream));
+    RC(hc.download(out, dout, 2));
+    return hc.finish();
+}
+
+int cnvk_biweight_columns_dev(const double* d_mat, int32_t rows, int64_t ncols, int32_t mode, double* d_loc,
+                              double* d_var, void* stream) {
+    RC(ensure_init());
+    return biweight_columns(d_mat, rows, ncols, mode, d_loc, d_var, (cudaStream_t)stream);
+}
+
+int cnvk_biweight_columns(const double* mat, int32_t rows, int64_t ncols, int32_t mode, double* loc, double* var) {
+    HostCall hc;
+    RC(hc.begin());
+    double *dm, *dl, *dv;
+    RC(hc.upload(mat, (size_t)rows * (size_t)ncols, &dm));
+    CNVK_CHECK(hc.scratch->alloc(&dl, (size_t)ncols));
+    CNVK_CHECK(hc.scratch->alloc(&dv, (size_t)ncols));
+    RC(biweight_columns(dm, rows, ncols, mode, dl, dv, hc.stream));
+    if (mode & 1) RC(hc.download(loc, dl, (size_t)ncols));
+    if (mode & 2) RC(hc.download(var, dv, (size_t)ncols));
+    return hc.finish();
+}
+
 static int cbs_common(const double* d_x, const double* d_w, const int64_t* arm_offsets, int32_t n_arms,
                       const cnvk_cbs_params* p, int64_t capacity, int32_t* seg_arm, int64_t* seg_lo,
                       int64_t* seg_hi, double* seg_mean, int64_t* n_segs, cnvk_cbs_stats* stats,

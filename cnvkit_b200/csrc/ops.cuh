@@ -8,6 +8,38 @@ namespace cnvk {
 int rolling_window_stat(const double* d_x, long long n, long long wing, int mode, double q, int min_periods,
                         double* d_out, cudaStream_t stream);
 
+// select.cu
+int segmented_median(const double* d_x, const unsigned char* d_use, const long long* d_seg_off, int nseg,
+                     double* d_med, int* d_cnt, cudaStream_t stream);
+int median_of_medians(const double* d_med, const int* d_cnt, int nseg, double* d_out, double sign,
+                      cudaStream_t stream);
+
+// biweight.cu
+int biweight_of_sorted(const double* d_sorted, const u32* d_nvalid, int n, const double* d_initial, double* d_out,
+                       cudaStream_t stream);
+int biweight_columns(const double* d_mat, int rows, long long ncols, int mode, double* d_loc, double* d_var,
+                     cudaStream_t stream);
+
+// fix.cu
+int fix_mask(const double* d_sample_log2, const double* d_ref_log2, const double* d_ref_spread,
+             const double* d_ref_depth, const double* d_ref_gc, long long n, unsigned char* d_keep,
+             cudaStream_t stream);
+int center_all(double* d_log2, const double* d_depth, const unsigned char* d_sel, long long n,
+               const long long* d_chrom_off, int nchrom, int skip_low, double* d_shift_out, cudaStream_t stream);
+int center_by_window(double* d_log2, const double* d_key, const u32* d_perm, long long n, long long wing,
+                     cudaStream_t stream);
+int edge_bias(const long long* d_start, const long long* d_end, const int* d_chrom_id, long long n, long long margin,
+              double* d_out, cudaStream_t stream);
+int fix_group(double* d_log2, const double* d_depth, const unsigned char* d_auto_sel, long long n,
+              const long long* d_chrom_off, int nchrom, const int* d_chrom_id, const long long* d_start,
+              const long long* d_end, const double* d_gc, const double* d_rmask, const double* d_edge_in,
+              int do_edge, int skip_low, int do_center, long long wing, const u32* d_perm, long long margin,
+              const char* order, int* h_skipped, cudaStream_t stream);
+int fix_finish(double* d_log2, const double* d_depth, const double* d_ref_log2, const double* d_ref_spread,
+               const long long* d_start, const long long* d_end, const int* d_chrom_id,
+               const unsigned char* d_is_anti, const unsigned char* d_auto_sel, long long n,
+               const long long* d_chrom_off, int nchrom, double* d_weight, double* d_info, cudaStream_t stream);
+
 // peak.cu
 int fp64_peak(int iters, int reps, double* tflops, cudaStream_t stream);
 

@@ -240,6 +240,37 @@ int make_sort_keys(const double* d_x, long long n, u64* d_keys, u32* d_idx, cuda
     return 0;
 }
 
+__global__ void keys_to_values_kernel(const u64* __restrict__ keys, long long n, double* __restrict__ out,
+                                      u32* __restrict__ nvalid) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 k = keys[i];
+    const bool isnan_ = (k == ~0ull);
+    const u64 b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    out[i] = isnan_ ? __longlong_as_double(0x7ff8000000000000ll) : __longlong_as_double((long long)b);
+    const bool prev_nan = (i > 0) && (keys[i - 1] == ~0ull);
+    if (isnan_ && !prev_nan) *nvalid = (u32)i;
+}
+
+__global__ void set_u32_kernel(u32* p, u32 v) { *p = v; }
+
+// ascending values with NaNs last; *d_nvalid = number of non-NaN values
+int sort_values_f64(const double* d_x, long long n, u64* k0, u64* k1, u32* v0, u32* v1, double* d_sorted,
+                    u32* d_nvalid, cudaStream_t stream) {
+    set_u32_kernel<<<1, 1, 0, stream>>>(d_nvalid, (u32)(n > 0 ? n : 0));
+    CNVK_LAUNCH_CHECK();
+    if (n <= 0) return 0;
+    int rc = make_sort_keys(d_x, n, k0, v0, stream);
+    if (rc) return rc;
+    u64* ok;
+    u32* ov;
+    rc = radix_sort_pairs(k0, k1, v0, v1, n, 0, 64, &ok, &ov, stream);
+    if (rc) return rc;
+    keys_to_values_kernel<<<div_up(n, 256), 256, 0, stream>>>(ok, n, d_sorted, d_nvalid);
+    CNVK_LAUNCH_CHECK();
+    return 0;
+}
+
 int argsort_f64(const double* d_x, long long n, u32* d_order, cudaStream_t stream) {
     if (n <= 0) return 0;
     Scratch scratch(stream);

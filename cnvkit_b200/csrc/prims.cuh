@@ -19,6 +19,10 @@ int argsort_f64(const double* d_x, long long n, u32* d_order, cudaStream_t strea
 // keys[i] = orderable(x[i]), idx[i] = i
 int make_sort_keys(const double* d_x, long long n, u64* d_keys, u32* d_idx, cudaStream_t stream);
 
+// ascending copy of d_x with NaNs last (scratch k0,k1,v0,v1 of n elements each)
+int sort_values_f64(const double* d_x, long long n, u64* k0, u64* k1, u32* v0, u32* v1, double* d_sorted,
+                    u32* d_nvalid, cudaStream_t stream);
+
 // out[i] = sum_{j<i} in[j]; total written to *d_total if non-null. In-place allowed.
 int exclusive_scan_u32(const u32* d_in, u32* d_out, long long n, u32* d_total, cudaStream_t stream);
 

@@ -1,0 +1,152 @@
+"""Host-side chromosome-name logic (strings never go to the GPU).
+
+Restates the behaviour of skgenome/chromnames.py (autosome / sex / mitochondrial / alt-contig
+classification), skgenome/chromsort.py:43-66 (sort key) and skgenome/genomebuild.py (PAR
+coordinates) that the hot path depends on; their *outputs* -- row masks, chromosome ids, sort
+permutations -- are what the kernels consume.
+"""
+from __future__ import annotations
+
+import re
+
+import numpy as np
+
+_ARABIC = re.compile(r"^(?:chr|Chr)?\d{1,3}$")
+_ALT = re.compile(r"^chrEBV$|^NC[_\-]|_random$|Un_|^HLA[\-_]|_alt$|hap\d+$|_decoy$")
+_MITO = re.compile(r"^(?:chr|Chr)?(?:M|MT|Mito)$", re.IGNORECASE)
+
+
+def _roman(n: int) -> str:
+    out = []
+    for v, sym in ((100, "C"), (90, "XC"), (50, "L"), (40, "XL"), (10, "X"), (9, "IX"), (5, "V"), (4, "IV"),
+                   (1, "I")):
+        while n >= v:
+            out.append(sym)
+            n -= v
+    return "".join(out)
+
+
+_ROMANS = frozenset(_roman(i) for i in range(1, 50))
+
+# skgenome/genomebuild.py: half-open PAR coordinates
+PAR_REGIONS = {
+    "grch37": {"PAR1X": (60000, 2699520), "PAR2X": (154931043, 155260560),
+               "PAR1Y": (10000, 2649520), "PAR2Y": (59034049, 59363566)},
+    "grch38": {"PAR1X": (10000, 2781479), "PAR2X": (155701382, 156030895),
+               "PAR1Y": (10000, 2781479), "PAR2Y": (56887902, 57217415)},
+}
+
+
+def _strip_chr(name: str) -> str:
+    return name.removeprefix("chr").removeprefix("Chr")
+
+
+def is_roman(name: str) -> bool:
+    return _strip_chr(name) in _ROMANS
+
+
+def is_mitochondrial(name: str) -> bool:
+    return bool(_MITO.match(name))
+
+
+def is_alternative_contig(name: str) -> bool:
+    return bool(_ALT.search(name))
+
+
+def infer_sex_chrom_labels(names):
+    """(x_label, y_label) used by a chromosome set; (None, None) for Roman-numeral genomes."""
+    name_set = {str(n) for n in names}
+    if not name_set:
+        return None, None
+    romans = [n for n in name_set if is_roman(n)]
+    if len(romans) >= 3 and any(len(_strip_chr(n)) > 1 for n in romans):
+        return None, None
+    x = next((c for c in ("chrX", "X") if c in name_set), None)
+    y = next((c for c in ("chrY", "Y") if c in name_set), None)
+    return x, y
+
+
+def is_autosome(name: str, x_label=None, y_label=None) -> bool:
+    if not name or name == x_label or name == y_label:
+        return False
+    return bool(_ARABIC.match(name)) or is_roman(name)
+
+
+def chrom_sort_key(label: str):
+    """Integers first, then X/Y, then single letters, then longer strings (chromsort.py:43-66)."""
+    chrom = label[3:] if label.lower().startswith("chr") else label
+    if chrom in ("X", "Y"):
+        return (1000, chrom)
+    i = 0
+    while i < len(chrom) and chrom[i].isdigit():
+        i += 1
+    num = int(chrom[:i]) if i else 0
+    rest = chrom[i:]
+    if not rest:
+        return (num, "")
+    return ((2000 if len(rest) == 1 else 3000) + num, rest)
+
+
+def chrom_runs(chromosomes: np.ndarray):
+    """Run-length encode a chromosome column.
+
+    Returns (names, offsets int64[k+1], chrom_id int32[n]).  Rows of one chromosome must be
+    contiguous (true for any genomically sorted table); raises ValueError otherwise.
+    """
+    chrom = np.asarray(chromosomes, dtype=object)
+    n = len(chrom)
+    if n == 0:
+        return [], np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32)
+    change = np.flatnonzero(chrom[1:] != chrom[:-1]) + 1
+    starts = np.concatenate([[0], change])
+    names = [str(chrom[s]) for s in starts]
+    if len(set(names)) != len(names):
+        raise ValueError("chromosome rows are not contiguous; sort the table first")
+    offsets = np.concatenate([starts, [n]]).astype(np.int64)
+    ids = np.repeat(np.arange(len(names), dtype=np.int32), np.diff(offsets))
+    return names, offsets, ids
+
+
+def autosome_row_mask(chromosomes: np.ndarray, start=None, end=None, diploid_parx_genome=None) -> np.ndarray:
+    """Row mask of CopyNumArray.autosomes(diploid_parx_genome) (cnary.py:155-166, gary.py:268-307).
+
+    Autosomes exclude the inferred sex chromosomes, mitochondria and alternative contigs; PAR1/2
+    on X are added when a genome build is named.  If nothing looks like an autosome the whole
+    table is used (the reference warns and returns itself).
+    """
+    chrom = np.asarray(chromosomes, dtype=object)
+    uniq = list(dict.fromkeys(chrom.tolist()))
+    x_label, y_label = infer_sex_chrom_labels(uniq)
+    ok = {u: (is_autosome(str(u), x_label, y_label) and not is_mitochondrial(str(u))
+              and not is_alternative_contig(str(u))) for u in uniq}
+    mask = np.fromiter((ok[c] for c in chrom.tolist()), dtype=bool, count=len(chrom))
+    if not mask.any():
+        return np.ones(len(chrom), dtype=bool)
+    if diploid_parx_genome is not None and x_label is not None:
+        key = diploid_parx_genome.lower()
+        if key not in PAR_REGIONS:
+            raise KeyError(f"Unknown genome build {diploid_parx_genome!r}; supported: {sorted(PAR_REGIONS)}")
+        p1, p2 = PAR_REGIONS[key]["PAR1X"], PAR_REGIONS[key]["PAR2X"]
+        s, e = np.asarray(start), np.asarray(end)
+        mask |= (chrom == x_label) & (((s >= p1[0]) & (e <= p1[1])) | ((s >= p2[0]) & (e <= p2[1])))
+    return mask
+
+
+def genomic_order(chromosomes, start, end) -> np.ndarray:
+    """Stable permutation that sorts rows by (chromosome key, start, end) -- GenomicArray.sort
+    (gary.py:731-739, mergesort)."""
+    chrom = np.asarray(chromosomes, dtype=object)
+    uniq = list(dict.fromkeys(chrom.tolist()))
+    ranked = sorted(uniq, key=lambda c: chrom_sort_key(str(c)))
+    # equal keys keep their first-appearance order (stable), distinct names with equal keys share a rank
+    rank = {}
+    r = -1
+    prev = None
+    for c in ranked:
+        k = chrom_sort_key(str(c))
+        if k != prev:
+            r += 1
+            prev = k
+        rank[c] = r
+    ck = np.fromiter((rank[c] for c in chrom.tolist()), dtype=np.int64, count=len(chrom))
+    return np.lexsort((np.asarray(end), np.asarray(start), ck))

@@ -66,6 +66,77 @@ int cnvk_rolling_quantile(const double* x, int64_t n, int64_t wing, double q, do
 /* np.argsort(x, kind="mergesort") as used by cnvlib/fix.py:414 -- stable, NaN last. */
 int cnvk_argsort_f64_dev(const double* d_x, int64_t n, uint32_t* d_order, void* stream);
 
+/* ---- fix: bin-level normalisation (device-pointer primitives) ---------------------------- */
+/* cnvlib/fix.py:295-321 mask_bad_bins OR'ed with the sample-NaN test of fix.py:244; keep[i]=1 for
+ * bins that survive.  d_sample_log2, d_ref_depth, d_ref_gc may be NULL (column absent). */
+int cnvk_fix_mask_dev(const double* d_sample_log2, const double* d_ref_log2, const double* d_ref_spread,
+                      const double* d_ref_depth, const double* d_ref_gc, int64_t n, uint8_t* d_keep,
+                      void* stream);
+
+/* cnvlib/cnary.py:253-313 CopyNumArray.center_all(estimator=median, by_chrom=True, skip_low):
+ * log2 += -(median over chromosomes of the per-chromosome median of the selected bins).
+ * d_sel (nullable) is the host-derived autosome(+PAR) row mask, d_chrom_offsets[nchrom+1] the
+ * device CSR of chromosome runs; with skip_low the drop_low_coverage test (cnary.py:315-335) is
+ * applied on the fly.  *d_shift_out (nullable, device) receives the applied shift. */
+int cnvk_center_all_dev(double* d_log2, const double* d_depth, const uint8_t* d_sel, int64_t n,
+                        const int64_t* d_chrom_offsets, int32_t nchrom, int32_t skip_low,
+                        double* d_shift_out, void* stream);
+
+/* cnvlib/fix.py:373-427 center_by_window with bias_smoother="median": d_perm is
+ * np.random.default_rng(0xA5EED).permutation(n) (fix.py:404-405, a pure function of n, generated
+ * on the host), wing = smoothing._width2wing(fraction, n).  In place on d_log2, genomic order
+ * is preserved (the reference re-sorts at fix.py:426). */
+int cnvk_center_by_window_dev(double* d_log2, const double* d_key, const uint32_t* d_perm, int64_t n,
+                              int64_t wing, void* stream);
+int cnvk_center_by_window(double* log2, const double* key, const uint32_t* perm, int64_t n, int64_t wing);
+
+/* cnvlib/fix.py:430-512 get_edge_bias(cnarr, margin): gains - losses per bin; d_chrom_id marks
+ * chromosome runs so neighbours never cross a chromosome boundary. */
+int cnvk_edge_bias_dev(const int64_t* d_start, const int64_t* d_end, const int32_t* d_chrom_id, int64_t n,
+                       int64_t margin, double* d_out, void* stream);
+
+/* One bin set (targets or antitargets) of cnvlib/fix.py:249-291 load_adjust_coverages after row
+ * filtering -- and of cnvlib/reference.py:641-666 bias_correct_logr: [center_all(skip_low)] ->
+ * "mostly empty" guard (fix.py:252-258; *skipped = 1 and nothing else is done) -> centring by
+ * window on the traits named in `order` ('g' = d_gc, 'e' = edge bias, 'r' = d_rmask; fix uses
+ * "ger", reference "gre"); NULL trait columns / do_edge = 0 are skipped.  d_edge_key (nullable)
+ * supplies a precomputed edge-bias column (reference.py:563), otherwise it is computed from
+ * start/end/chrom_id with `margin` (params.INSERT_SIZE).  Synchronises the stream once. */
+int cnvk_fix_group_dev(double* d_log2, const double* d_depth, const uint8_t* d_auto_sel, int64_t n,
+                       const int64_t* d_chrom_offsets, int32_t nchrom, const int32_t* d_chrom_id,
+                       const int64_t* d_start, const int64_t* d_end, const double* d_gc, const double* d_rmask,
+                       const double* d_edge_key, int32_t do_edge, int32_t skip_low, int32_t do_center,
+                       int64_t wing, const uint32_t* d_perm, int64_t margin, const char* order,
+                       int32_t* skipped, void* stream);
+
+/* cnvlib/fix.py:212-214: log2 -= ref_log2; weight = apply_weights(...) (fix.py:515-617, epsilon
+ * 1e-4); center_all(skip_low=True).  d_is_anti = gene in ANTITARGET_ALIASES (host string test).
+ * d_info (nullable, device, 8 doubles) receives [tgt_loc, tgt_sd, anti_loc, anti_sd,
+ * anti_sum_sqrt_size, n_anti, n_anti_ok, 0] for the log messages of fix.py:571-595. */
+int cnvk_fix_finish_dev(double* d_log2, const double* d_depth, const double* d_ref_log2,
+                        const double* d_ref_spread, const int64_t* d_start, const int64_t* d_end,
+                        const int32_t* d_chrom_id, const uint8_t* d_is_anti, const uint8_t* d_auto_sel,
+                        int64_t n, const int64_t* d_chrom_offsets, int32_t nchrom, double* d_weight,
+                        double* d_info, void* stream);
+
+/* ---- robust statistics ------------------------------------------------------------------- */
+/* Exact per-segment medians (pandas Series.median: NaN skipped, even counts averaged) of the
+ * rows with d_use != 0 (nullable = all rows); d_cnt receives the contributing counts. */
+int cnvk_segmented_median_dev(const double* d_x, const uint8_t* d_use, const int64_t* d_seg_offsets,
+                              int32_t nseg, double* d_med, int32_t* d_cnt, void* stream);
+
+/* cnvlib/descriptives.py:96-142 biweight_location and :188-222 biweight_midvariance of one array
+ * (host buffers).  out[0] = location (or *initial if given), out[1] = midvariance about out[0]. */
+int cnvk_biweight(const double* x, int64_t n, const double* initial, double* out);
+
+/* cnvlib/reference.py:717-741 summarize_info building block: per column of the row-major
+ * [rows, ncols] matrix (rows = samples): mode&1 -> biweight location, mode&2 -> midvariance about
+ * that location. */
+int cnvk_biweight_columns_dev(const double* d_mat, int32_t rows, int64_t ncols, int32_t mode, double* d_loc,
+                              double* d_var, void* stream);
+int cnvk_biweight_columns(const double* mat, int32_t rows, int64_t ncols, int32_t mode, double* loc,
+                          double* var);
+
 /* ---- circular binary segmentation ------------------------------------------------------ */
 /* Replaces the Rscript + DNAcopy::segment(cna, weights, alpha) subprocess of
  * cnvlib/segmentation/__init__.py:292-322 (R script cnvlib/segmentation/cbs.py:1-78).  Field

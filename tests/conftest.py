@@ -33,3 +33,17 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+def golden_table(g, prefix):
+    """Rebuild a CopyNumArray from the 'prefix__column' arrays written by oracle/make_golden.py."""
+    import pandas as pd
+
+    from cnvkit_b200.cnary import CopyNumArray
+
+    cols = [str(c) for c in g[f"{prefix}__columns"]]
+    data = {}
+    for c in cols:
+        v = g[f"{prefix}__{c}"]
+        data[c] = v.astype(object) if v.dtype.kind == "U" else v
+    return CopyNumArray(pd.DataFrame(data), {"sample_id": prefix})
