@@ -342,6 +342,44 @@ int cnvk_cbs_segment(const double* log2, const double* weight, const int64_t* ar
     return hc.finish();
 }
 
+static int haar_common(const double* d_x, const double* d_w, const int64_t* arm_offsets, int32_t n_arms, double q,
+                       int64_t capacity, int32_t* seg_arm, int64_t* seg_lo, int64_t* seg_hi, double* seg_mean,
+                       int64_t* n_segs, cudaStream_t stream) {
+    std::vector<long long> off(arm_offsets, arm_offsets + n_arms + 1);
+    std::vector<CbsSeg> segs;
+    RC(haar_segment(d_x, d_w, off.data(), n_arms, q, segs, stream));
+    if ((int64_t)segs.size() > capacity) {
+        set_last_error("cnvk_haar_segment: %zu segments exceed capacity %lld", segs.size(), (long long)capacity);
+        return -4;
+    }
+    for (size_t s = 0; s < segs.size(); ++s) {
+        seg_arm[s] = segs[s].arm; seg_lo[s] = segs[s].lo; seg_hi[s] = segs[s].hi; seg_mean[s] = segs[s].mean;
+    }
+    *n_segs = (int64_t)segs.size();
+    return 0;
+}
+
+int cnvk_haar_segment_dev(const double* d_log2, const double* d_weight, const int64_t* arm_offsets, int32_t n_arms,
+                          double fdr_q, int64_t capacity, int32_t* seg_arm, int64_t* seg_lo, int64_t* seg_hi,
+                          double* seg_mean, int64_t* n_segs, void* stream) {
+    RC(ensure_init());
+    return haar_common(d_log2, d_weight, arm_offsets, n_arms, fdr_q, capacity, seg_arm, seg_lo, seg_hi, seg_mean,
+                       n_segs, (cudaStream_t)stream);
+}
+
+int cnvk_haar_segment(const double* log2, const double* weight, const int64_t* arm_offsets, int32_t n_arms,
+                      double fdr_q, int64_t capacity, int32_t* seg_arm, int64_t* seg_lo, int64_t* seg_hi,
+                      double* seg_mean, int64_t* n_segs) {
+    HostCall hc;
+    RC(hc.begin());
+    const size_t N = n_arms > 0 ? (size_t)arm_offsets[n_arms] : 0;
+    double *dx, *dw = nullptr;
+    RC(hc.upload(log2, N, &dx));
+    if (weight) RC(hc.upload(weight, N, &dw));
+    RC(haar_common(dx, dw, arm_offsets, n_arms, fdr_q, capacity, seg_arm, seg_lo, seg_hi, seg_mean, n_segs, hc.stream));
+    return hc.finish();
+}
+
 int cnvk_cbs_getbdry(double eta, int32_t nperm, int32_t max_ones, int32_t* out) {
     std::vector<int> b;
     cbs_getbdry(eta, nperm, max_ones, b);

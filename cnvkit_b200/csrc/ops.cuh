@@ -66,6 +66,9 @@ struct CbsStats {
 namespace cnvk {
 int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, const CbsParams& P,
                 std::vector<CbsSeg>& segs, CbsStats* stats, cudaStream_t stream);
+// haar.cu (segments reuse CbsSeg)
+int haar_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, double q,
+                 std::vector<CbsSeg>& segs, cudaStream_t stream);
 void cbs_getbdry(double eta, int nperm, int max_ones, std::vector<int>& out);
 
 }  // namespace cnvk

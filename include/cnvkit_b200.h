@@ -174,6 +174,18 @@ int cnvk_cbs_segment(const double* log2, const double* weight, const int64_t* ar
  * out[max_ones*(max_ones+1)/2]. Host-only. */
 int cnvk_cbs_getbdry(double eta, int32_t nperm, int32_t max_ones, int32_t* out);
 
+/* ---- HaarSeg ------------------------------------------------------------------------------ */
+/* cnvlib/segmentation/haar.py:257-371 haarSeg(signal, breaksFdrQ, weights) for every arm of a batch
+ * (haarStartLevel 1, haarEndLevel 5; the arms are those of segment_haar's by_arm(), haar.py:80-82).
+ * d_weight may be NULL (no weight column).  Same batching and output convention as
+ * cnvk_cbs_segment; seg_mean is SegmentByPeaks' (weighted) mean (haar.py:405-451). */
+int cnvk_haar_segment_dev(const double* d_log2, const double* d_weight, const int64_t* arm_offsets,
+                          int32_t n_arms, double fdr_q, int64_t capacity, int32_t* seg_arm, int64_t* seg_lo,
+                          int64_t* seg_hi, double* seg_mean, int64_t* n_segs, void* stream);
+int cnvk_haar_segment(const double* log2, const double* weight, const int64_t* arm_offsets, int32_t n_arms,
+                      double fdr_q, int64_t capacity, int32_t* seg_arm, int64_t* seg_lo, int64_t* seg_hi,
+                      double* seg_mean, int64_t* n_segs);
+
 #ifdef __cplusplus
 }
 #endif
