@@ -53,6 +53,10 @@ SIGNATURES = {
     "cnvk_biweight": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "cnvk_biweight_columns_dev": (c_int, [c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "cnvk_biweight_columns": (c_int, [c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
+    "cnvk_outlier_mask_dev": (c_int, [c_void_p, c_void_p, c_int32, c_double, c_double, c_void_p, c_void_p]),
+    "cnvk_round_sig_dev": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "cnvk_segment_bin_sums_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                          c_void_p]),
     "cnvk_cbs_segment_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cnvk_cbs_segment": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p,

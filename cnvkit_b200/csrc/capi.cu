@@ -342,6 +342,28 @@ int cnvk_cbs_segment(const double* log2, const double* weight, const int64_t* ar
     return hc.finish();
 }
 
+int cnvk_outlier_mask_dev(const double* d_log2, const int64_t* arm_offsets, int32_t n_arms, double q, double factor,
+                          uint8_t* d_mask, void* stream) {
+    RC(ensure_init());
+    std::vector<long long> off(arm_offsets, arm_offsets + n_arms + 1);
+    return outlier_mask(d_log2, off.data(), n_arms, q, factor, d_mask, (cudaStream_t)stream);
+}
+
+int cnvk_round_sig_dev(const double* d_x, int64_t n, int32_t digits, double* d_out, uint64_t* unhandled, void* stream) {
+    RC(ensure_init());
+    unsigned long long u = 0;
+    int rc = round_sig(d_x, n, digits, d_out, &u, (cudaStream_t)stream);
+    if (unhandled) *unhandled = u;
+    return rc;
+}
+
+int cnvk_segment_bin_sums_dev(const double* d_depth, const double* d_weight, const int64_t* d_lo, const int64_t* d_hi,
+                              int32_t nseg, double* d_seg_weight, double* d_seg_depth, void* stream) {
+    RC(ensure_init());
+    return segment_bin_sums(d_depth, d_weight, (const long long*)d_lo, (const long long*)d_hi, nseg, d_seg_weight,
+                            d_seg_depth, (cudaStream_t)stream);
+}
+
 static int haar_common(const double* d_x, const double* d_w, const int64_t* arm_offsets, int32_t n_arms, double q,
                        int64_t capacity, int32_t* seg_arm, int64_t* seg_lo, int64_t* seg_hi, double* seg_mean,
                        int64_t* n_segs, cudaStream_t stream) {

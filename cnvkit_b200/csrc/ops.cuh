@@ -40,6 +40,14 @@ int fix_finish(double* d_log2, const double* d_depth, const double* d_ref_log2, 
                const unsigned char* d_is_anti, const unsigned char* d_auto_sel, long long n,
                const long long* d_chrom_off, int nchrom, double* d_weight, double* d_info, cudaStream_t stream);
 
+// segutil.cu
+int outlier_mask(const double* d_x, const long long* h_off, int n_arms, double q, double factor,
+                 unsigned char* d_mask, cudaStream_t stream);
+int round_sig(const double* d_x, long long n, int digits, double* d_out, unsigned long long* h_unhandled,
+              cudaStream_t stream);
+int segment_bin_sums(const double* d_depth, const double* d_weight, const long long* d_lo, const long long* d_hi,
+                     int nseg, double* d_seg_weight, double* d_seg_depth, cudaStream_t stream);
+
 // peak.cu
 int fp64_peak(int iters, int reps, double* tflops, cudaStream_t stream);
 

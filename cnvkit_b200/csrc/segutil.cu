@@ -1,0 +1,265 @@
+// Per-arm pre-filters and post-processing of cnvlib.segmentation.do_segmentation:
+//
+//   outlier_mask     segmentation/__init__.py:372-398 drop_outliers -> smoothing.rolling_outlier_quantile
+//                    (smoothing.py:439-463): trend = savgol(x, 50) (seven passes of scipy's 7-tap
+//                    order-3 Savitzky-Golay FIR over the 25-mirror-padded arm, smoothing.py:236-331),
+//                    q = rolling 0.95-quantile (window 51) of |x - trend|, outlier = |x-trend| > q*factor.
+//   round_sig        the "%.6g" quantisation applied to every float column of the TSV handed to
+//                    DNAcopy (segmentation/__init__.py:299-301), exact round-half-even in decimal.
+//   segment_bin_sums transfer_fields' numeric part (segmentation/__init__.py:489-501): per segment
+//                    nansum of bin weights and the weighted mean of bin depths.
+#include "ops.cuh"
+#include "prof.cuh"
+#include <vector>
+
+namespace cnvk {
+
+typedef unsigned char u8;
+
+static const int OL_WING = 25;      // _width2wing(50, x) for len(x) > 50
+static const int OL_PASSES = 7;     // total_width 51 // window_width 7
+static const int OL_TILE = 512;
+static const int OL_HALO = 3 * OL_PASSES;   // 21 points each side feed the 7 passes
+
+// scipy.signal.savgol_coeffs(7, 3) as produced by this image's scipy/LAPACK, in the order
+// scipy.ndimage.correlate1d's symmetric branch consumes them (centre, then pairs at +-3, +-2, +-1).
+__device__ __constant__ double SG_C0 = 0x1.555555555555ap-2;
+__device__ __constant__ double SG_C3 = -0x1.861861861861bp-4;
+__device__ __constant__ double SG_C2 = 0x1.2492492492495p-3;
+__device__ __constant__ double SG_C1 = 0x1.2492492492496p-2;
+
+__device__ __forceinline__ int mirror_pad(int t, int n, int wing) {   // padded index -> arm-local index
+    if (t < wing) return wing - 1 - t;
+    if (t < wing + n) return t - wing;
+    return n - 1 - (t - wing - n);
+}
+
+// dists[i] = |x[i] - savgol_trend[i]| for arms longer than 50 bins
+__global__ void __launch_bounds__(256)
+savgol_dists_kernel(const double* __restrict__ x, const long long* __restrict__ off, const int* __restrict__ tile_off,
+                    const int* __restrict__ ex_arm, int n_ex, double* __restrict__ dists) {
+    __shared__ double s_a[OL_TILE + 2 * OL_HALO], s_b[OL_TILE + 2 * OL_HALO];
+    int a = 0, b = n_ex;
+    while (b - a > 1) { const int m = (a + b) >> 1; if (tile_off[m] <= (int)blockIdx.x) a = m; else b = m; }
+    const long long lo = off[ex_arm[a]];
+    const int n = (int)(off[ex_arm[a] + 1] - lo);
+    const int i0 = ((int)blockIdx.x - tile_off[a]) * OL_TILE;
+    const int cnt = min(OL_TILE, n - i0);
+    const int L = n + 2 * OL_WING;
+    // padded positions [p0, p0 + cnt + 2*HALO), p0 = i0 + WING - HALO
+    const int p0 = i0 + OL_WING - OL_HALO;
+    const int span = cnt + 2 * OL_HALO;
+    for (int t = threadIdx.x; t < span; t += 256) {
+        const int p = p0 + t;
+        s_a[t] = (p >= 0 && p < L) ? x[lo + mirror_pad(p, n, OL_WING)] : 0.0;
+    }
+    __syncthreads();
+    double* in = s_a;
+    double* out = s_b;
+    for (int pass = 0; pass < OL_PASSES; ++pass) {
+        const int margin = 3 * (pass + 1);
+        for (int t = threadIdx.x; t < span; t += 256) {
+            double v = in[t];
+            if (t >= margin && t < span - margin) {
+                double acc = __dmul_rn(in[t], SG_C0);
+                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(in[t - 3], in[t + 3]), SG_C3));
+                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(in[t - 2], in[t + 2]), SG_C2));
+                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(in[t - 1], in[t + 1]), SG_C1));
+                v = acc;
+            }
+            out[t] = v;
+        }
+        __syncthreads();
+        double* tmp = in; in = out; out = tmp;
+    }
+    for (int t = threadIdx.x; t < cnt; t += 256) {
+        const int i = i0 + t;
+        dists[lo + i] = fabs(__dsub_rn(x[lo + i], in[t + OL_HALO]));
+    }
+}
+
+// mask[i] = dists[i] > quantile_q(window 2*wing+1 of mirror-padded dists) * factor
+__global__ void __launch_bounds__(256)
+quantile_mask_kernel(const double* __restrict__ dists, const long long* __restrict__ off,
+                     const int* __restrict__ tile_off, const int* __restrict__ ex_arm, int n_ex, double q,
+                     double factor, u8* __restrict__ mask) {
+    __shared__ double s_v[OL_TILE + 2 * OL_WING];
+    int a = 0, b = n_ex;
+    while (b - a > 1) { const int m = (a + b) >> 1; if (tile_off[m] <= (int)blockIdx.x) a = m; else b = m; }
+    const long long lo = off[ex_arm[a]];
+    const int n = (int)(off[ex_arm[a] + 1] - lo);
+    const int i0 = ((int)blockIdx.x - tile_off[a]) * OL_TILE;
+    const int cnt = min(OL_TILE, n - i0);
+    const int W = 2 * OL_WING + 1;
+    for (int t = threadIdx.x; t < cnt + 2 * OL_WING; t += 256)
+        s_v[t] = dists[lo + mirror_pad(i0 + t, n, OL_WING)];
+    __syncthreads();
+    const double idxf = q * (double)(W - 1);
+    const int idx = (int)idxf;
+    const double frac = idxf - (double)idx;
+    for (int t = threadIdx.x; t < cnt; t += 256) {
+        double vlow = 0.0, vhigh = 0.0;
+        for (int j = 0; j < W; ++j) {
+            const double v = s_v[t + j];
+            int rank = 0;
+            for (int k = 0; k < W; ++k) {
+                const double u = s_v[t + k];
+                rank += (u < v || (u == v && k < j)) ? 1 : 0;
+            }
+            if (rank == idx) vlow = v;
+            if (rank == idx + 1) vhigh = v;
+        }
+        const double quant = (frac == 0.0) ? vlow : __dadd_rn(vlow, __dmul_rn(__dsub_rn(vhigh, vlow), frac));
+        mask[lo + i0 + t] = (dists[lo + i0 + t] > __dmul_rn(quant, factor)) ? 1 : 0;
+    }
+}
+
+int outlier_mask(const double* d_x, const long long* h_off, int n_arms, double q, double factor, u8* d_mask,
+                 cudaStream_t stream) {
+    if (n_arms <= 0) return 0;
+    const long long N = h_off[n_arms];
+    if (N <= 0) return 0;
+    ProfScope ps(PC_OTHER, stream);
+    CNVK_CHECK(cudaMemsetAsync(d_mask, 0, (size_t)N, stream));
+    // only arms with more than 50 bins are examined (smoothing.py:458-459)
+    std::vector<int> ex_arm, tile_off;
+    int tiles = 0;
+    for (int a = 0; a < n_arms; ++a) {
+        const long long n = h_off[a + 1] - h_off[a];
+        if (n > 50) {
+            ex_arm.push_back(a);
+            tile_off.push_back(tiles);
+            tiles += div_up(n, OL_TILE);
+        }
+    }
+    tile_off.push_back(tiles);
+    const int n_ex = (int)ex_arm.size();
+    if (n_ex == 0) return 0;
+    Scratch scratch(stream);
+    long long* d_off;
+    int *d_tile_off, *d_ex;
+    double* d_dists;
+    CNVK_CHECK(scratch.alloc(&d_off, (size_t)n_arms + 1));
+    CNVK_CHECK(scratch.alloc(&d_tile_off, tile_off.size()));
+    CNVK_CHECK(scratch.alloc(&d_ex, ex_arm.size()));
+    CNVK_CHECK(scratch.alloc(&d_dists, (size_t)N));
+    CNVK_CHECK(cudaMemcpyAsync(d_off, h_off, ((size_t)n_arms + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    CNVK_CHECK(cudaMemcpyAsync(d_tile_off, tile_off.data(), tile_off.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CNVK_CHECK(cudaMemcpyAsync(d_ex, ex_arm.data(), ex_arm.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    savgol_dists_kernel<<<tiles, 256, 0, stream>>>(d_x, d_off, d_tile_off, d_ex, n_ex, d_dists);
+    CNVK_LAUNCH_CHECK();
+    quantile_mask_kernel<<<tiles, 256, 0, stream>>>(d_dists, d_off, d_tile_off, d_ex, n_ex, q, factor, d_mask);
+    CNVK_LAUNCH_CHECK();
+    CNVK_CHECK(cudaStreamSynchronize(stream));  // the host vectors above back the async copies
+    return 0;
+}
+
+// ------------------------------------------------------------------ "%.{digits}g" quantisation
+__device__ __forceinline__ double pow10_exact(int k) {   // 10^k, exact for 0 <= k <= 22
+    const double t[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                          1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    return t[k];
+}
+
+// nearest integer to the exact value hi+lo (|lo| <= ulp(hi)/2), ties to even
+__device__ __forceinline__ double round_exact_sum(double hi, double lo) {
+    double f = floor(hi);
+    const double d = (hi - f) - 0.5;          // exact
+    if (d > 0.0 || (d == 0.0 && lo > 0.0)) return f + 1.0;
+    if (d < 0.0 || (d == 0.0 && lo < 0.0)) return f;
+    // exact tie
+    return (fmod(f, 2.0) == 0.0) ? f : f + 1.0;
+}
+
+__global__ void round_sig_kernel(const double* __restrict__ x, long long n, int digits, double* __restrict__ out,
+                                 unsigned long long* __restrict__ unhandled) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    if (v == 0.0 || !(fabs(v) < INFINITY)) { out[i] = v; return; }   // 0, inf, NaN print as themselves
+    const double a = fabs(v);
+    int e = (int)floor(log10(a));
+    double m = 0.0;
+    bool ok = false;
+    for (int attempt = 0; attempt < 3 && !ok; ++attempt) {
+        const int k = digits - 1 - e;          // scale by 10^k
+        double hi, lo;
+        if (k >= 0 && k <= 22) {
+            const double s = pow10_exact(k);
+            hi = a * s;
+            lo = fma(a, s, -hi);
+        } else if (k < 0 && k >= -22) {
+            const double s = pow10_exact(-k);
+            hi = a / s;
+            lo = -fma(hi, s, -a) / s;           // residual of the division (sign/magnitude only matter at ties)
+        } else {
+            break;
+        }
+        m = round_exact_sum(hi, lo);
+        const double top = pow10_exact(digits), bot = pow10_exact(digits - 1);
+        if (m >= top) { if (m == top) { m = bot; ++e; ok = true; } else { ++e; } }
+        else if (m < bot) { --e; }
+        else ok = true;
+    }
+    if (!ok) { out[i] = v; atomicAdd(unhandled, 1ull); return; }
+    // value of the decimal m * 10^(e-digits+1), correctly rounded (Clinger's fast path)
+    const int p = e - digits + 1;
+    double r;
+    if (p >= 0 && p <= 22) r = m * pow10_exact(p);
+    else if (p < 0 && p >= -22) r = m / pow10_exact(-p);
+    else { out[i] = v; atomicAdd(unhandled, 1ull); return; }
+    out[i] = copysign(r, v);
+}
+
+int round_sig(const double* d_x, long long n, int digits, double* d_out, unsigned long long* h_unhandled,
+              cudaStream_t stream) {
+    if (h_unhandled) *h_unhandled = 0;
+    if (n <= 0) return 0;
+    if (digits < 1 || digits > 15) { set_last_error("round_sig: digits=%d unsupported", digits); return -2; }
+    ProfScope ps(PC_OTHER, stream);
+    Scratch scratch(stream);
+    unsigned long long* d_cnt;
+    CNVK_CHECK(scratch.alloc(&d_cnt, 1));
+    CNVK_CHECK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), stream));
+    round_sig_kernel<<<div_up(n, 256), 256, 0, stream>>>(d_x, n, digits, d_out, d_cnt);
+    CNVK_LAUNCH_CHECK();
+    if (h_unhandled) {
+        CNVK_CHECK(cudaMemcpyAsync(h_unhandled, d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CNVK_CHECK(cudaStreamSynchronize(stream));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ transfer_fields sums
+// one warp per segment over its bin range [lo, hi): weight = nansum(w); depth = sum(d*w)/sum(w)
+// over non-NaN weights, or 0 when the segment carries no weight
+__global__ void __launch_bounds__(128)
+segment_bin_sums_kernel(const double* __restrict__ depth, const double* __restrict__ weight,
+                        const long long* __restrict__ lo, const long long* __restrict__ hi, int nseg,
+                        double* __restrict__ seg_weight, double* __restrict__ seg_depth) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * 4 + warp;
+    if (s >= nseg) return;
+    double sw = 0.0, sdw = 0.0;
+    for (long long k = lo[s] + lane; k < hi[s]; k += 32) {
+        const double w = weight ? weight[k] : 1.0;
+        if (w == w) { sw += w; sdw += depth[k] * w; }
+    }
+    sw = warp_sum(sw);
+    sdw = warp_sum(sdw);
+    if (lane == 0) {
+        seg_weight[s] = sw;
+        seg_depth[s] = (sw > 0.0) ? sdw / sw : 0.0;
+    }
+}
+
+int segment_bin_sums(const double* d_depth, const double* d_weight, const long long* d_lo, const long long* d_hi,
+                     int nseg, double* d_seg_weight, double* d_seg_depth, cudaStream_t stream) {
+    if (nseg <= 0) return 0;
+    ProfScope ps(PC_OTHER, stream);
+    segment_bin_sums_kernel<<<div_up(nseg, 4), 128, 0, stream>>>(d_depth, d_weight, d_lo, d_hi, nseg, d_seg_weight, d_seg_depth);
+    CNVK_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace cnvk

@@ -1,0 +1,293 @@
+"""Segmentation driver on the GPU -- host mirror of cnvlib/segmentation/__init__.py.
+
+``do_segmentation(cnarr, method)`` keeps the reference's signature, defaults, log lines, error
+behaviour and output table, but instead of mapping ``_do_segmentation`` over chromosome arms in a
+process pool (and, for CBS, spawning one Rscript per arm) it filters every arm, uploads the
+log2/weight columns once and segments all arms in a single device call.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .. import _dev, _lib, params
+from ..cnary import arm_ranges
+from . import cbs as _cbs
+from . import haar as _haar
+
+SEGMENT_METHODS = ("cbs", "haar", "none", "hmm", "hmm-tumor", "hmm-germline")
+_GPU_METHODS = ("cbs", "haar")
+
+
+def do_segmentation(
+    cnarr,
+    method,
+    diploid_parx_genome=None,
+    threshold=None,
+    variants=None,
+    skip_low=False,
+    skip_outliers=10,
+    min_weight=0,
+    save_dataframe=False,
+    rscript_path="Rscript",
+    processes=1,
+    smooth_cbs=False,
+):
+    """Infer copy number segments (cnvlib/segmentation/__init__.py:31-193).
+
+    ``rscript_path`` and ``processes`` are accepted for signature compatibility and ignored (no R,
+    no process pool: all arms are segmented in one batched GPU call).
+    """
+    if method not in SEGMENT_METHODS:
+        raise ValueError("'method' must be one of: " + ", ".join(SEGMENT_METHODS) + "; got: " + repr(method))
+    if not len(cnarr):
+        return (cnarr, "") if save_dataframe else cnarr
+    if method not in _GPU_METHODS:
+        raise NotImplementedError(f"method {method!r} is outside the GPU hot path (cbs and haar are implemented)")
+    if variants is not None and len(variants):
+        raise NotImplementedError("BAF-aware segmentation (variants=...) is outside the GPU hot path")
+    if smooth_cbs:
+        raise NotImplementedError("smooth_cbs (DNAcopy smooth.CNA) is not implemented on the GPU path")
+    if cnarr.sample_id is None:
+        logging.warning(
+            "Input has no sample_id set; the segmented output will be "
+            "unlabeled (CLI usage derives sample_id from the input filename).")
+    if threshold is None:
+        threshold = 0.0001
+    logging.info("Segmenting with method %r, significance threshold %s, in %s processes", method, threshold,
+                 processes)
+
+    data = cnarr.data.reset_index(drop=True)
+    arms = arm_ranges(data)  # GenomicArray.by_arm of the unfiltered table
+    log2 = data["log2"].to_numpy(dtype=np.float64)
+    has_weight = "weight" in data.columns
+    weight = data["weight"].to_numpy(dtype=np.float64) if has_weight else None
+    depth = data["depth"].to_numpy(dtype=np.float64) if "depth" in data.columns else None
+    start = data["start"].to_numpy(dtype=np.int64)
+    end = data["end"].to_numpy(dtype=np.int64)
+    chrom = data["chromosome"].to_numpy()
+    n = len(data)
+    arm_off = np.array([a[1] for a in arms] + [arms[-1][2]], dtype=np.int64)
+    arm_id = np.repeat(np.arange(len(arms)), np.diff(arm_off))
+
+    # ---- per-arm filters of _do_segmentation (:239-282), vectorised over the whole table
+    keep = np.isfinite(log2)
+    n_bad = int((~keep).sum())
+    if n_bad:
+        logging.info("Dropped %d bins with non-finite log2 values", n_bad)
+    if skip_low:
+        low = (log2 < params.NULL_LOG2_COVERAGE - params.MIN_REF_COVERAGE) | np.isnan(log2)
+        if depth is not None:
+            low |= (depth == 0) | np.isnan(depth)
+        keep &= ~low
+    if skip_outliers:
+        idx = np.flatnonzero(keep)
+        if len(idx):
+            sub_off = np.concatenate([[0], np.cumsum(np.bincount(arm_id[idx], minlength=len(arms)))]).astype(np.int64)
+            d_x = _dev.up(log2[idx])
+            d_mask = _dev.empty(len(idx), torch.uint8)
+            _lib.call("cnvk_outlier_mask_dev", _dev.ptr(d_x), _lib.ptr(sub_off), len(arms), 0.95,
+                      float(skip_outliers), _dev.ptr(d_mask), _dev.stream())
+            out = d_mask.cpu().numpy().astype(bool)
+            if out.any():
+                logging.info("Dropped %d outlier bins:\n%s%s", int(out.sum()), data.iloc[idx[out]].head(20),
+                             "\n..." if out.sum() > 20 else "")
+                keep[idx[out]] = False
+    if has_weight:
+        # NaN weights compare False and therefore survive this gate, as in the reference (:262-265)
+        w_bad = (weight < min_weight) if min_weight else (weight == 0)
+        n_wbad = int((w_bad & keep).sum())
+        if n_wbad:
+            keep &= ~w_bad
+            if min_weight:
+                logging.debug("Dropped %d bins with weight below %s", n_wbad, min_weight)
+            else:
+                logging.debug("Dropped %d bins with zero weight", n_wbad)
+    for a, (cname, lo, hi) in enumerate(arms):
+        kept = int(keep[lo:hi].sum())
+        if kept != hi - lo:
+            logging.info("Dropped %d / %d bins on chromosome %s", hi - lo - kept, hi - lo, cname)
+
+    fidx = np.flatnonzero(keep)
+    if not len(fidx):
+        empty = cnarr.as_dataframe(data.iloc[:0])
+        return (empty, "") if save_dataframe else empty
+    f_arm = arm_id[fidx]
+    f_log2, f_start, f_end = log2[fidx], start[fidx], end[fidx]
+    f_weight = weight[fidx] if has_weight else None
+
+    if method == "cbs":
+        seg = _segment_cbs(f_log2, f_weight, f_arm, len(arms), threshold)
+    else:
+        seg = _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, chrom[fidx], len(arms), threshold)
+    s_unit, s_lo, s_hi, s_mean, unit_arm, sub_fidx = seg
+    # rows of the per-arm segment tables (cbs.py:64-73 / haar.py:244-254)
+    src = fidx if sub_fidx is None else fidx[sub_fidx]
+    seg_arm = unit_arm[s_unit]
+    seg_chrom = chrom[src[s_lo]]
+    seg_start = start[src[s_lo]].copy()
+    seg_end = end[src[s_hi - 1]].copy()
+    probes = (s_hi - s_lo).astype(np.int64)
+
+    segtab = _transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, s_mean, probes, arms, data, log2, weight,
+                              depth, start, end)
+    result = cnarr.as_dataframe(segtab)
+    result.sort()
+    result.sort_columns()
+    if save_dataframe:
+        return result, _seg_text(result, cnarr.sample_id)
+    return result
+
+
+def _arm_offsets(arm_of_bin, n_arms):
+    return np.concatenate([[0], np.cumsum(np.bincount(arm_of_bin, minlength=n_arms))]).astype(np.int64)
+
+
+def _segment_cbs(f_log2, f_weight, f_arm, n_arms, threshold):
+    """The `case "cbs"` block (:292-322): %.6g TSV -> R filters (cbs.py:22-35) -> segment()."""
+    d_x = _dev.up(f_log2)
+    d_xq = _dev.empty(len(f_log2), torch.float64)
+    unhandled = np.zeros(1, dtype=np.uint64)
+    _lib.call("cnvk_round_sig_dev", _dev.ptr(d_x), len(f_log2), 6, _dev.ptr(d_xq), _lib.ptr(unhandled), _dev.stream())
+    xq = d_xq.cpu().numpy()
+    if unhandled[0]:
+        bad = (np.abs(f_log2) < 1e-16) | (np.abs(f_log2) > 1e21)
+        xq[bad] = [float("%.6g" % v) for v in f_log2[bad]]
+    if f_weight is not None and np.isfinite(f_weight).any():
+        d_w = _dev.up(f_weight)
+        d_wq = _dev.empty(len(f_weight), torch.float64)
+        _lib.call("cnvk_round_sig_dev", _dev.ptr(d_w), len(f_weight), 6, _dev.ptr(d_wq), _lib.ptr(unhandled),
+                  _dev.stream())
+        wq = d_wq.cpu().numpy()
+        if unhandled[0]:
+            bad = (np.abs(f_weight) < 1e-16) | (np.abs(f_weight) > 1e21)
+            wq[bad] = [float("%.6g" % v) for v in f_weight[bad]]
+        ok = ~np.isnan(wq) & (wq > 0)       # cbs.py:22-24
+    else:
+        wq = np.ones(len(f_log2))           # cbs.py:25-28
+        ok = np.ones(len(f_log2), dtype=bool)
+    ok &= ~np.isnan(xq)
+    sub = None
+    if not ok.all():
+        sub = np.flatnonzero(ok)
+        xq, wq, f_arm = xq[sub], wq[sub], f_arm[sub]
+    off = _arm_offsets(f_arm, n_arms)
+    arm, lo, hi, mean, _stats = _cbs.segment_arms(xq, wq, off, alpha=float(threshold))
+    # R prints seg.mean with 15 significant digits (write.table) before the SEG parser reads it back
+    mean = np.array([float("%.15g" % m) for m in mean]) if len(mean) else mean
+    return arm, lo, hi, mean, np.arange(n_arms), sub
+
+
+def _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, f_chrom, n_arms, threshold):
+    """`case "haar"` (:286-289): segment_haar re-splits every filtered arm with by_arm() again
+    (haar.py:80-82), so the segmentation units are the arms of the *filtered* arm tables."""
+    units_off = [0]
+    unit_arm = []
+    off = _arm_offsets(f_arm, n_arms)
+    for a in range(n_arms):
+        lo, hi = int(off[a]), int(off[a + 1])
+        if hi <= lo:
+            continue
+        sub = pd.DataFrame({"chromosome": f_chrom[lo:hi], "start": f_start[lo:hi], "end": f_end[lo:hi]})
+        for _c, slo, shi in arm_ranges(sub):
+            units_off.append(lo + shi)
+            unit_arm.append(a)
+    arm, lo, hi, mean = _haar.segment_arms(f_log2, f_weight, np.asarray(units_off, dtype=np.int64), float(threshold))
+    return arm, lo, hi, mean, np.asarray(unit_arm, dtype=np.int64), None
+
+
+def _transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, seg_log2, probes, arms, data, log2, weight, depth,
+                     start, end):
+    """transfer_fields(segarr, cnarr) per arm (:401-506), all arms at once.
+
+    Each arm's first/last segment is stretched to the arm's first bin start / last bin end; then
+    every segment aggregates the *unfiltered* bins it spans ('outer' mode of iter_slices): gene
+    names joined on the host, weight and depth reduced on the device."""
+    nseg = len(seg_arm)
+    seg_start = seg_start.copy()
+    seg_end = seg_end.copy()
+    first = np.ones(nseg, dtype=bool)
+    first[1:] = seg_arm[1:] != seg_arm[:-1]
+    last = np.ones(nseg, dtype=bool)
+    last[:-1] = seg_arm[1:] != seg_arm[:-1]
+    arm_lo = np.array([a[1] for a in arms])
+    arm_hi = np.array([a[2] for a in arms])
+    seg_start[first] = start[arm_lo[seg_arm[first]]]
+    seg_end[last] = end[arm_hi[seg_arm[last]] - 1]
+    # bin row ranges per segment: intersect.py:323-346 _irange_simple, mode "outer", within the arm
+    bin_lo = np.empty(nseg, dtype=np.int64)
+    bin_hi = np.empty(nseg, dtype=np.int64)
+    for a in np.unique(seg_arm):
+        lo, hi = int(arm_lo[a]), int(arm_hi[a])
+        sel = np.flatnonzero(seg_arm == a)
+        a_start, a_end = start[lo:hi], end[lo:hi]
+        if np.all(a_end[1:] >= a_end[:-1]):
+            bin_lo[sel] = lo + np.searchsorted(a_end, seg_start[sel], "right")
+            bin_hi[sel] = lo + np.searchsorted(a_start, seg_end[sel], "left")
+        else:
+            raise NotImplementedError("nested bins (non-monotonic end coordinates) are not supported")
+    bin_hi = np.maximum(bin_hi, bin_lo)
+    dep = depth if depth is not None else np.exp2(log2)
+    d_dep, d_lo, d_hi = _dev.up(dep), _dev.up(bin_lo), _dev.up(bin_hi)
+    d_w = _dev.up(weight) if weight is not None else None
+    d_sw, d_sd = _dev.empty(nseg, torch.float64), _dev.empty(nseg, torch.float64)
+    _lib.call("cnvk_segment_bin_sums_dev", _dev.ptr(d_dep), _dev.ptr(d_w), _dev.ptr(d_lo), _dev.ptr(d_hi), nseg,
+              _dev.ptr(d_sw), _dev.ptr(d_sd), _dev.stream())
+    seg_weight, seg_depth = d_sw.cpu().numpy(), d_sd.cpu().numpy()
+    genes = _join_genes(data["gene"].to_numpy(), bin_lo, bin_hi)
+    return pd.DataFrame({
+        "chromosome": seg_chrom, "start": seg_start, "end": seg_end, "gene": genes, "log2": seg_log2,
+        "probes": probes, "weight": seg_weight, "depth": seg_depth,
+    })
+
+
+def _join_genes(bin_genes, bin_lo, bin_hi):
+    """skgenome/combiners.py:58-94 join_strings per segment: ordered-unique gene names of the
+    bins, split on ',', minus the ignored placeholder / antitarget names; '-' if none remain."""
+    ignore = set(params.IGNORE_GENE_NAMES + params.ANTITARGET_ALIASES)
+    codes, uniques = pd.factorize(pd.Series(bin_genes, dtype=object), sort=False)
+    parts = []
+    for u in uniques:
+        parts.append([p for p in u.split(",")] if isinstance(u, str) else None)
+    out = []
+    for lo, hi in zip(bin_lo, bin_hi):
+        c = codes[lo:hi]
+        if len(c) == 0:
+            out.append("-")
+            continue
+        _, first_idx = np.unique(c, return_index=True)
+        seen = {}
+        for ci in c[np.sort(first_idx)]:
+            if ci < 0 or parts[ci] is None:
+                continue
+            for name in parts[ci]:
+                if name not in ignore:
+                    seen.setdefault(name, None)
+        out.append(",".join(seen) or "-")
+    return out
+
+
+def _seg_text(segarr, sample_id):
+    """SEG text in the shape DNAcopy's write.table prints (test/formats/warning.seg); the reference
+    returns R's stdout when save_dataframe=True."""
+    lines = ['"ID"\t"chrom"\t"loc.start"\t"loc.end"\t"num.mark"\t"seg.mean"']
+    d = segarr.data
+    for c, s, e, p, m in zip(d["chromosome"], d["start"], d["end"], d["probes"], d["log2"]):
+        lines.append(f'"{sample_id}"\t"{c}"\t{int(s) + 1}\t{int(e)}\t{int(p)}\t{m:.15g}')
+    return "\n".join(lines) + "\n"
+
+
+def drop_outliers_mask(log2, arm_offsets, width=50, factor=10):
+    """Outlier mask of drop_outliers (:372-398) for pre-split arms, numpy in / numpy out."""
+    if width != 50:
+        raise NotImplementedError("only the reference's width=50 is implemented")
+    x = _lib.f64(log2)
+    off = _lib.i64(arm_offsets)
+    d_x = _dev.up(x)
+    d_mask = _dev.empty(len(x), torch.uint8)
+    _lib.call("cnvk_outlier_mask_dev", _dev.ptr(d_x), _lib.ptr(off), len(off) - 1, 0.95, float(factor),
+              _dev.ptr(d_mask), _dev.stream())
+    return d_mask.cpu().numpy().astype(bool)

@@ -137,6 +137,28 @@ int cnvk_biweight_columns_dev(const double* d_mat, int32_t rows, int64_t ncols, 
 int cnvk_biweight_columns(const double* mat, int32_t rows, int64_t ncols, int32_t mode, double* loc,
                           double* var);
 
+/* ---- segmentation pre-filters / post-processing -------------------------------------------- */
+/* cnvlib/segmentation/__init__.py:372-398 drop_outliers(cnarr, 50, factor) via
+ * smoothing.rolling_outlier_quantile(x, 50, q, factor) (smoothing.py:439-463) for every arm of a
+ * batch: d_mask[i] = 1 for outlier bins; arms of <= 50 bins are never flagged.  arm_offsets is a
+ * HOST array.  Synchronises the stream. */
+int cnvk_outlier_mask_dev(const double* d_log2, const int64_t* arm_offsets, int32_t n_arms, double q,
+                          double factor, uint8_t* d_mask, void* stream);
+
+/* float("%.{digits}g" % x) element-wise (exact decimal round-half-even): the quantisation every
+ * float column undergoes on its way to DNAcopy (segmentation/__init__.py:299-301, float_format
+ * "%.6g").  *unhandled counts elements outside the exactly-handled range (|x| < 1e-16 or > 1e21),
+ * which are copied through for the host to finish.  Synchronises when unhandled != NULL. */
+int cnvk_round_sig_dev(const double* d_x, int64_t n, int32_t digits, double* d_out, uint64_t* unhandled,
+                       void* stream);
+
+/* Numeric part of transfer_fields (segmentation/__init__.py:489-501): per segment over its bin
+ * rows [d_lo, d_hi): seg_weight = nansum(weight) (weight NULL = 1 per bin), seg_depth = weighted
+ * mean of depth over non-NaN weights, 0 when seg_weight == 0. */
+int cnvk_segment_bin_sums_dev(const double* d_depth, const double* d_weight, const int64_t* d_lo,
+                              const int64_t* d_hi, int32_t nseg, double* d_seg_weight, double* d_seg_depth,
+                              void* stream);
+
 /* ---- circular binary segmentation ------------------------------------------------------ */
 /* Replaces the Rscript + DNAcopy::segment(cna, weights, alpha) subprocess of
  * cnvlib/segmentation/__init__.py:292-322 (R script cnvlib/segmentation/cbs.py:1-78).  Field
