@@ -229,7 +229,22 @@ int cnvk_fix_group_dev(double* d_log2, const double* d_depth, const uint8_t* d_a
     int sk = 0;
     int rc = fix_group(d_log2, d_depth, d_auto_sel, n, (const long long*)d_chrom_offsets, nchrom, d_chrom_id,
                        (const long long*)d_start, (const long long*)d_end, d_gc, d_rmask, d_edge_key, do_edge,
-                       skip_low, do_center, wing, d_perm, margin, order ? order : "ger", &sk, (cudaStream_t)stream);
+                       skip_low, do_center, wing, d_perm, margin, order ? order : "ger", nullptr, nullptr, 0, &sk,
+                       (cudaStream_t)stream);
+    if (skipped) *skipped = sk;
+    return rc;
+}
+
+int cnvk_bias_correct_logr_dev(double* d_log2, const double* d_depth, const uint8_t* d_auto_sel, int64_t n,
+                               const int64_t* d_chrom_offsets, int32_t nchrom, const double* d_gc,
+                               const double* d_rmask, const double* d_edge_key, int32_t skip_low, int64_t wing,
+                               const uint32_t* d_perm, const double* d_flat_logr, const uint8_t* d_sex_chrom,
+                               int32_t is_xx, int32_t* skipped, void* stream) {
+    RC(ensure_init());
+    int sk = 0;
+    int rc = fix_group(d_log2, d_depth, d_auto_sel, n, (const long long*)d_chrom_offsets, nchrom, nullptr, nullptr,
+                       nullptr, d_gc, d_rmask, d_edge_key, d_edge_key != nullptr, skip_low, 1, wing, d_perm, 0, "gre",
+                       d_flat_logr, d_sex_chrom, is_xx, &sk, (cudaStream_t)stream);
     if (skipped) *skipped = sk;
     return rc;
 }

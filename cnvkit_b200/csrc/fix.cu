@@ -216,17 +216,35 @@ count_gt_kernel(const double* __restrict__ x, long long n, double thr, unsigned 
 // fix.py:249-291 (and reference.py:641-666 with shifts applied by the caller in between):
 // center_all, the "mostly empty" guard, then GC / edge / RepeatMasker centring by window in the
 // order given by `order` (fix: gc,edge,rmask = "ger"; reference: gc,rmask,edge = "gre").
+// reference.py:670-714 shift_sex_chroms: log2 += flat; XX sample: chrY = -1; XY sample: X,Y += 1
+__global__ void shift_sex_kernel(double* __restrict__ log2, const double* __restrict__ flat,
+                                 const u8* __restrict__ xy, long long n, int is_xx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = __dadd_rn(log2[i], flat[i]);
+    const u8 s = xy[i];   // bit0: chrX (PAR-aware), bit1: chrY
+    if (is_xx) { if (s & 2) v = -1.0; }
+    else if (s & 3) v = __dadd_rn(v, 1.0);
+    log2[i] = v;
+}
+
 int fix_group(double* d_log2, const double* d_depth, const u8* d_auto_sel, long long n,
               const long long* d_chrom_off, int nchrom, const int* d_chrom_id, const long long* d_start,
               const long long* d_end, const double* d_gc, const double* d_rmask, const double* d_edge_in,
               int do_edge, int skip_low, int do_center, long long wing, const u32* d_perm, long long margin,
-              const char* order, int* h_skipped, cudaStream_t stream) {
+              const char* order, const double* d_flat, const u8* d_xy, int is_xx, int* h_skipped,
+              cudaStream_t stream) {
     if (h_skipped) *h_skipped = 0;
     if (n <= 0) return 0;
     int rc;
     if (do_center) {
         rc = center_all(d_log2, d_depth, d_auto_sel, n, d_chrom_off, nchrom, skip_low, nullptr, stream);
         if (rc) return rc;
+    }
+    if (d_flat && d_xy) {
+        ProfScope ps(PC_FIX, stream);
+        shift_sex_kernel<<<div_up(n, 256), 256, 0, stream>>>(d_log2, d_flat, d_xy, n, is_xx);
+        CNVK_LAUNCH_CHECK();
     }
     Scratch scratch(stream);
     unsigned long long* d_cnt;

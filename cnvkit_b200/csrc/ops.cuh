@@ -34,7 +34,8 @@ int fix_group(double* d_log2, const double* d_depth, const unsigned char* d_auto
               const long long* d_chrom_off, int nchrom, const int* d_chrom_id, const long long* d_start,
               const long long* d_end, const double* d_gc, const double* d_rmask, const double* d_edge_in,
               int do_edge, int skip_low, int do_center, long long wing, const u32* d_perm, long long margin,
-              const char* order, int* h_skipped, cudaStream_t stream);
+              const char* order, const double* d_flat, const unsigned char* d_xy, int is_xx, int* h_skipped,
+              cudaStream_t stream);
 int fix_finish(double* d_log2, const double* d_depth, const double* d_ref_log2, const double* d_ref_spread,
                const long long* d_start, const long long* d_end, const int* d_chrom_id,
                const unsigned char* d_is_anti, const unsigned char* d_auto_sel, long long n,

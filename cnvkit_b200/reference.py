@@ -1,0 +1,222 @@
+"""Pooled reference build on the GPU -- host mirror of cnvlib/reference.py (numeric core).
+
+``combine_probes`` / ``do_reference`` keep the reference's contract: they take ``.cnn`` *file
+paths*, return the reference table (chromosome, start, end, gene, log2, depth, [gc], spread) and
+raise the same errors.  On the device: per-normal ``bias_correct_logr`` (centre, sex-chromosome
+shift, GC / RepeatMasker / edge centring by window at fraction 0.1) and ``summarize_info`` (Tukey
+biweight location and midvariance of every bin across the S+1 samples, one warp per bin).
+
+Outside the hot path and therefore *not* reimplemented: FASTA GC/RepeatMasker
+extraction (``fa_fname``), sex inference from coverage (pass ``female_samples`` or ``sexes``) and
+sample clustering (``do_cluster``).
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+import os
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _dev, _lib, cnary, genome, params, smoothing
+
+
+def fbase(fname: str) -> str:
+    """Strip directory and extensions (cnvlib/core.py:118-140)."""
+    base = os.path.basename(fname)
+    if base.endswith(".gz"):
+        base = base[:-3]
+    for ext in (".antitargetcoverage.cnn", ".targetcoverage.cnn", ".antitargetcoverage.csv", ".targetcoverage.csv",
+                ".recal.bam", ".deduplicated.realign.bam"):
+        if base.endswith(ext):
+            return base[: -len(ext)]
+    return base.rsplit(".", 1)[0]
+
+
+def _read(fname):
+    arr = cnary.read(fname, sample_id=fbase(fname))
+    return arr
+
+
+def do_reference(
+    target_fnames,
+    antitarget_fnames=None,
+    fa_fname=None,
+    is_haploid_x_reference=False,
+    diploid_parx_genome=None,
+    female_samples=None,
+    do_gc=True,
+    do_edge=True,
+    do_rmask=True,
+    do_cluster=False,
+    min_cluster_size=4,
+    cluster_method="hierarchical",
+    bias_smoother="median",
+    sexes=None,
+):
+    """Compile a pooled coverage reference from normal samples (cnvlib/reference.py:88-281).
+
+    ``sexes`` ({sample_id: is_female}) is this package's hook for callers that ran the reference's
+    own sex inference; with ``female_samples`` given it is derived exactly as the reference does.
+    """
+    if antitarget_fnames and len(target_fnames) != len(antitarget_fnames):
+        raise ValueError(
+            f"Unequal number of target and antitarget files given: targets = {len(target_fnames)!r}, "
+            f"antitargets = {len(antitarget_fnames)!r}")
+    if fa_fname:
+        raise NotImplementedError("FASTA GC/RepeatMasker extraction (fa_fname) is outside the GPU hot path")
+    if do_cluster:
+        raise NotImplementedError("do_cluster=True is outside the GPU hot path")
+    if bias_smoother != "median":
+        raise NotImplementedError("only bias_smoother='median' runs on the GPU path")
+    logging.info("No FASTA reference genome provided; skipping GC, RM calculations")
+    if sexes is None:
+        if female_samples is None:
+            raise NotImplementedError(
+                "sex inference from coverage stays with the reference (cnvlib/reference.py:284-382); pass "
+                "female_samples=True/False or sexes={sample_id: is_female}")
+        logging.info(f"Provided sample sex is {'female' if female_samples else 'male'}. ")
+        sexes = {fbase(f): female_samples for f in target_fnames}
+    ref = combine_probes(target_fnames, antitarget_fnames, fa_fname, is_haploid_x_reference, diploid_parx_genome,
+                         sexes, do_gc, do_edge, do_rmask, do_cluster, min_cluster_size)
+    return ref
+
+
+def combine_probes(filenames, antitarget_fnames, fa_fname, is_haploid_x, diploid_parx_genome, sexes, fix_gc,
+                   fix_edge, fix_rmask, do_cluster=False, min_cluster_size=4):
+    """cnvlib/reference.py:385-494."""
+    ref_df, d_logr, d_depths = load_sample_block(filenames, fa_fname, is_haploid_x, diploid_parx_genome, sexes, True,
+                                                 fix_gc, fix_edge, False)
+    if antitarget_fnames:
+        anti_df, a_logr, a_depths = load_sample_block(antitarget_fnames, fa_fname, is_haploid_x, diploid_parx_genome,
+                                                      sexes, False, fix_gc, False, fix_rmask)
+        if not anti_df.empty:
+            ref_df = pd.concat([ref_df, anti_df], ignore_index=True)
+        d_logr = torch.cat([d_logr, a_logr], dim=1).contiguous()
+        d_depths = torch.cat([d_depths, a_depths], dim=1).contiguous()
+    stats = summarize_info_device(d_logr, d_depths)
+    ref_df = ref_df.assign(**stats)
+    ref = cnary.CopyNumArray(ref_df, {"sample_id": "reference"})
+    ref.sort()
+    ref.sort_columns()
+    return ref
+
+
+def _sex_chrom_rows(chrom, start, end, diploid_parx_genome):
+    """chr_x_filter / chr_y_filter (cnvlib/cnary.py:89-153): X and Y rows, minus PAR when a build is named."""
+    x_label, y_label = genome.infer_sex_chrom_labels(list(dict.fromkeys(chrom.tolist())))
+    is_x = (chrom == x_label) if x_label is not None else np.zeros(len(chrom), dtype=bool)
+    is_y = (chrom == y_label) if y_label is not None else np.zeros(len(chrom), dtype=bool)
+    is_y_all = is_y.copy()
+    if diploid_parx_genome is not None:
+        regs = genome.PAR_REGIONS[diploid_parx_genome.lower()]
+        for label, mask, keys in ((x_label, is_x, ("PAR1X", "PAR2X")), (y_label, is_y, ("PAR1Y", "PAR2Y"))):
+            if label is None:
+                continue
+            (a1, b1), (a2, b2) = regs[keys[0]], regs[keys[1]]
+            par = (chrom == label) & (((start >= a1) & (end <= b1)) | ((start >= a2) & (end <= b2)))
+            mask &= ~par
+    return is_x, is_y, is_y_all
+
+
+def load_sample_block(filenames, fa_fname, is_haploid_x, diploid_parx_genome, sexes, skip_low, fix_gc, fix_edge,
+                      fix_rmask):
+    """cnvlib/reference.py:497-622; the matrices stay on the device:
+    returns (ref_df, logr[S+1, n] CUDA float64 with row 0 = flat pseudo-sample, depths[S, n])."""
+    filenames = sorted(filenames, key=fbase)
+    logging.info("Loading %s", filenames[0])
+    cnarr1 = _read(filenames[0])
+    if len(cnarr1) == 0:
+        cols = ["chromosome", "start", "end", "gene", "log2", "depth"]
+        if "gc" in cnarr1:
+            cols.append("gc")
+        cols.append("spread")
+        dev = _dev.device()
+        return (pd.DataFrame.from_records([], columns=cols),
+                torch.zeros((len(filenames) + 1, 0), dtype=torch.float64, device=dev),
+                torch.zeros((len(filenames), 0), dtype=torch.float64, device=dev))
+    d1 = cnarr1.data
+    n = len(d1)
+    chrom = d1["chromosome"].to_numpy()
+    start = d1["start"].to_numpy(dtype=np.int64)
+    end = d1["end"].to_numpy(dtype=np.int64)
+    ref_columns = {"chromosome": d1["chromosome"], "start": d1["start"], "end": d1["end"], "gene": d1["gene"]}
+    have_gc = "gc" in cnarr1 and fix_gc
+    if have_gc:
+        ref_columns["gc"] = d1["gc"]
+    names, offsets, chrom_id = genome.chrom_runs(chrom)
+    is_x, is_y, is_y_all = _sex_chrom_rows(chrom, start, end, diploid_parx_genome)
+    # expect_flat_log2 (cnary.py:635-664)
+    flat = np.zeros(n)
+    flat[(is_x | is_y) if is_haploid_x else is_y_all] = -1.0
+    auto = genome.autosome_row_mask(chrom, start, end, diploid_parx_genome)
+
+    d_off, d_cid = _dev.up(offsets), _dev.up(chrom_id)
+    d_start, d_end = _dev.up(start), _dev.up(end)
+    d_auto = _dev.up(auto.astype(np.uint8))
+    d_flat = _dev.up(flat)
+    d_xy = _dev.up((is_x.astype(np.uint8) | (is_y.astype(np.uint8) << 1)))
+    d_gc = _dev.up(d1["gc"].to_numpy(dtype=np.float64)) if have_gc else None
+    d_edge = None
+    if fix_edge:
+        d_edge = _dev.empty(n, torch.float64)
+        _lib.call("cnvk_edge_bias_dev", _dev.ptr(d_start), _dev.ptr(d_end), _dev.ptr(d_cid), n, params.INSERT_SIZE,
+                  _dev.ptr(d_edge), _dev.stream())
+    wing = smoothing._width2wing(0.1, n) if n >= 2 else 1
+    d_perm = _dev.shuffle_permutation(n)
+
+    key_cols = d1.loc[:, ("chromosome", "start", "end", "gene")].values
+    rows_logr = [d_flat.clone()]
+    rows_depth = []
+    for i, fname in enumerate(filenames):
+        if i == 0:
+            cn = cnarr1
+        else:
+            logging.info("Loading %s", fname)
+            cn = _read(fname)
+            if not np.array_equal(key_cols, cn.data.loc[:, ("chromosome", "start", "end", "gene")].values):
+                raise RuntimeError(f"{fname} bins do not match those in {filenames[0]}")
+        log2 = cn.data["log2"].to_numpy(dtype=np.float64)
+        depth = cn.data["depth"].to_numpy(dtype=np.float64) if "depth" in cn else None
+        d_log2 = _dev.up(log2)
+        d_depth = _dev.up(depth) if depth is not None else None
+        rows_depth.append(d_depth if d_depth is not None else torch.exp2(d_log2))
+        known = sexes.get(cn.sample_id)
+        if known is None:
+            logging.warning("Cannot determine sex for sample %s; treating chrX as diploid (female)",
+                            cn.sample_id or "")
+        is_xx = True if known is None else bool(known)
+        skipped = ctypes.c_int32(0)
+        _lib.call("cnvk_bias_correct_logr_dev", _dev.ptr(d_log2), _dev.ptr(d_depth), _dev.ptr(d_auto), n,
+                  _dev.ptr(d_off), len(names), _dev.ptr(d_gc), 0, _dev.ptr(d_edge), int(bool(skip_low)), wing,
+                  _dev.ptr(d_perm), _dev.ptr(d_flat), _dev.ptr(d_xy), int(is_xx), ctypes.addressof(skipped),
+                  _dev.stream())
+        if skipped.value:
+            logging.warning("WARNING: most bins have no or very low coverage; check that the right BED file was used")
+        rows_logr.append(d_log2)
+    ref_df = pd.DataFrame.from_dict(ref_columns)
+    return ref_df, torch.stack(rows_logr).contiguous(), torch.stack(rows_depth).contiguous()
+
+
+def summarize_info_device(d_logr, d_depths):
+    """cnvlib/reference.py:717-741 on device matrices [samples, bins]."""
+    ncols = d_logr.shape[1]
+    logging.info("Calculating average bin coverages")
+    d_loc, d_var, d_dloc = (_dev.empty(max(ncols, 1), torch.float64) for _ in range(3))
+    if ncols:
+        _lib.call("cnvk_biweight_columns_dev", _dev.ptr(d_logr), d_logr.shape[0], ncols, 3, _dev.ptr(d_loc),
+                  _dev.ptr(d_var), _dev.stream())
+        _lib.call("cnvk_biweight_columns_dev", _dev.ptr(d_depths), d_depths.shape[0], ncols, 1, _dev.ptr(d_dloc), 0,
+                  _dev.stream())
+    logging.info("Calculating bin spreads")
+    return {"log2": d_loc[:ncols].cpu().numpy(), "depth": d_dloc[:ncols].cpu().numpy(),
+            "spread": d_var[:ncols].cpu().numpy()}
+
+
+def summarize_info(all_logr, all_depths):
+    """numpy in / numpy out seam of cnvlib/reference.py:717-741."""
+    d_logr = _dev.up(np.ascontiguousarray(all_logr, dtype=np.float64))
+    d_dep = _dev.up(np.ascontiguousarray(all_depths, dtype=np.float64))
+    return summarize_info_device(d_logr, d_dep)

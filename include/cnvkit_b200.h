@@ -109,6 +109,17 @@ int cnvk_fix_group_dev(double* d_log2, const double* d_depth, const uint8_t* d_a
                        int64_t wing, const uint32_t* d_perm, int64_t margin, const char* order,
                        int32_t* skipped, void* stream);
 
+/* cnvlib/reference.py:625-667 bias_correct_logr for one normal sample: center_all(skip_low) ->
+ * shift_sex_chroms (reference.py:670-714: log2 += flat_logr; XX sample: chrY bins = -1, XY
+ * sample: chrX/chrY bins += 1; d_sex_chrom bit0 = chrX row, bit1 = chrY row) -> "mostly empty"
+ * guard -> centring by window (fraction 0.1 => wing from the host) on GC, RepeatMasker, then the
+ * precomputed edge-bias column (reference.py:563); NULL columns are skipped. */
+int cnvk_bias_correct_logr_dev(double* d_log2, const double* d_depth, const uint8_t* d_auto_sel, int64_t n,
+                               const int64_t* d_chrom_offsets, int32_t nchrom, const double* d_gc,
+                               const double* d_rmask, const double* d_edge_key, int32_t skip_low, int64_t wing,
+                               const uint32_t* d_perm, const double* d_flat_logr, const uint8_t* d_sex_chrom,
+                               int32_t is_xx, int32_t* skipped, void* stream);
+
 /* cnvlib/fix.py:212-214: log2 -= ref_log2; weight = apply_weights(...) (fix.py:515-617, epsilon
  * 1e-4); center_all(skip_low=True).  d_is_anti = gene in ANTITARGET_ALIASES (host string test).
  * d_info (nullable, device, 8 doubles) receives [tgt_loc, tgt_sd, anti_loc, anti_sd,

@@ -119,11 +119,22 @@ def gen_regression(R):
             captured["all_depths"] = np.array(all_depths)
             return orig_summarize(all_logr, all_depths)
 
+        orig_combine = R.reference.combine_probes
+
+        def spy_combine(filenames, antitarget_fnames, fa_fname, is_haploid_x, diploid_parx_genome, sexes, *a, **k):
+            captured["sexes"] = dict(sexes)
+            return orig_combine(filenames, antitarget_fnames, fa_fname, is_haploid_x, diploid_parx_genome, sexes,
+                                *a, **k)
+
         R.reference.summarize_info = spy_summarize
+        R.reference.combine_probes = spy_combine
         try:
             ref = R.reference.do_reference(tfn, afn, is_haploid_x_reference=True)
         finally:
             R.reference.summarize_info = orig_summarize
+            R.reference.combine_probes = orig_combine
+        arrays["ref_sex_ids"] = np.asarray(list(captured["sexes"].keys()), dtype=str)
+        arrays["ref_sex_is_female"] = np.asarray([bool(v) for v in captured["sexes"].values()])
         arrays["ref_all_logr"] = captured["all_logr"]
         arrays["ref_all_depths"] = captured["all_depths"]
         stats = orig_summarize(captured["all_logr"], captured["all_depths"])
