@@ -37,6 +37,7 @@ static const int CBS_BLK = 256;           // points per bound block / j-block
 static const int CBS_IW = 4;              // arc starts per thread
 static const int CBS_IBLK = CBS_BLK * CBS_IW;
 static const int PREP_CHUNK = 1024;
+static const size_t PREP_SMEM = (size_t)2 * 3 * PREP_CHUNK * sizeof(double);
 static const int HYB_TP = 2048;           // arc starts per CTA in the hybrid permutation kernel
 static const int HYB_KMAX = 64;           // max supported kmax
 static const int EXACT_NMAX = 256;        // max supported nmin
@@ -67,22 +68,59 @@ __device__ __forceinline__ double pt(const double* a, int lo, int i) {
 }
 
 // ------------------------------------------------------------------------------------ prep
-__global__ void __launch_bounds__(256)
+// Sequential FP64 add chains are the critical path of this kernel (they define the bits of S, cw
+// and tss).  Each chain gets its own warp (lane 0 runs it out of shared memory, 8 elements per
+// iteration with 128-bit loads/stores), while the remaining warps stage the next chunk and write
+// the previous one back to HBM -- double-buffered, one __syncthreads per chunk.
+static const int PREP_THREADS = 256;
+static const int PREP_CHAIN_WARPS = 3;
+static const int PREP_STAGE_T0 = PREP_CHAIN_WARPS * 32;           // first staging thread
+static const int PREP_STAGE_N = PREP_THREADS - PREP_STAGE_T0;     // staging threads
+
+// in-place inclusive running sum over m (multiple of 8) doubles in shared memory
+__device__ __forceinline__ double chain_inplace(double* s, int m, double run) {
+    double2* p = reinterpret_cast<double2*>(s);
+    for (int t = 0; t < m / 2; t += 4) {
+        double2 v0 = p[t], v1 = p[t + 1], v2 = p[t + 2], v3 = p[t + 3];
+        run = __dadd_rn(run, v0.x); v0.x = run; run = __dadd_rn(run, v0.y); v0.y = run;
+        run = __dadd_rn(run, v1.x); v1.x = run; run = __dadd_rn(run, v1.y); v1.y = run;
+        run = __dadd_rn(run, v2.x); v2.x = run; run = __dadd_rn(run, v2.y); v2.y = run;
+        run = __dadd_rn(run, v3.x); v3.x = run; run = __dadd_rn(run, v3.y); v3.y = run;
+        p[t] = v0; p[t + 1] = v1; p[t + 2] = v2; p[t + 3] = v3;
+    }
+    return run;
+}
+
+// running sum without write-back (totals only)
+__device__ __forceinline__ double chain_total(const double* s, int m, double run) {
+    const double2* p = reinterpret_cast<const double2*>(s);
+    for (int t = 0; t < m / 2; t += 4) {
+        const double2 v0 = p[t], v1 = p[t + 1], v2 = p[t + 2], v3 = p[t + 3];
+        run = __dadd_rn(run, v0.x); run = __dadd_rn(run, v0.y);
+        run = __dadd_rn(run, v1.x); run = __dadd_rn(run, v1.y);
+        run = __dadd_rn(run, v2.x); run = __dadd_rn(run, v2.y);
+        run = __dadd_rn(run, v3.x); run = __dadd_rn(run, v3.y);
+    }
+    return run;
+}
+
+__global__ void __launch_bounds__(PREP_THREADS)
 cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const double* __restrict__ w,
                 double* __restrict__ xc, double* __restrict__ y, double* __restrict__ S,
                 double* __restrict__ cw, double* __restrict__ wn, double* __restrict__ blk_min,
                 double* __restrict__ blk_max, int al0) {
-    __shared__ double s_a[PREP_CHUNK], s_b[PREP_CHUNK], s_c[PREP_CHUNK];
+    extern __shared__ __align__(16) double s_dyn[];      // [2 buffers][3 arrays][PREP_CHUNK]
     __shared__ double s_red[64];
     __shared__ int s_redi[64];
-    __shared__ double s_scalar[4];
+    __shared__ double s_scalar[8];
     Node nd = nodes[blockIdx.x];
     const int lo = nd.lo, n = nd.hi - nd.lo;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto buf = [&](int b, int arr) { return s_dyn + ((size_t)b * 3 + arr) * PREP_CHUNK; };
 
     // range check: isTRUE(all.equal(diff(range(x)), 0)) -> final (changepoints R code)
     double mn = INFINITY, mx = -INFINITY;
-    for (int k = tid; k < n; k += 256) {
+    for (int k = tid; k < n; k += PREP_THREADS) {
         const double v = x[lo + k];
         mn = fmin(mn, v);
         mx = fmax(mx, v);
@@ -95,90 +133,112 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
     if (lane == 0) { s_red[warp] = mn; s_red[32 + warp] = mx; }
     __syncthreads();
     if (tid == 0) {
-        for (int k = 1; k < 8; ++k) { mn = fmin(mn, s_red[k]); mx = fmax(mx, s_red[32 + k]); }
+        for (int k = 1; k < PREP_THREADS / 32; ++k) { mn = fmin(mn, s_red[k]); mx = fmax(mx, s_red[32 + k]); }
         s_scalar[0] = mx - mn;
     }
     __syncthreads();
-    const bool flat = s_scalar[0] <= 1.4901161193847656e-08;
-    if (flat) {
+    if (s_scalar[0] <= 1.4901161193847656e-08) {
         if (tid == 0) {
             nodes[blockIdx.x].flat = 1;
             nodes[blockIdx.x].best_q = -1.0;
         }
         return;
     }
+    const int nchunks = (n + PREP_CHUNK - 1) / PREP_CHUNK;
 
-    // phase 1: sw, swx -- sequential chains (thread 0) over staged chunks
-    double sw = 0.0, swx = 0.0;
-    for (int c0 = 0; c0 < n; c0 += PREP_CHUNK) {
-        const int m = min(PREP_CHUNK, n - c0);
-        for (int k = tid; k < m; k += 256) {
-            const double wv = w[lo + c0 + k];
-            s_a[k] = wv;
-            s_b[k] = __dmul_rn(x[lo + c0 + k], wv);
-        }
-        __syncthreads();
-        if (tid == 0) {
-#pragma unroll 8
-            for (int k = 0; k < m; ++k) {
-                sw = __dadd_rn(sw, s_a[k]);
-                swx = __dadd_rn(swx, s_b[k]);
+    // ---- phase 1: sw = sum w, swx = sum x*w  (two chains)
+    {
+        auto stage1 = [&](int c, int b) {
+            const int c0 = c * PREP_CHUNK;
+            const int m = min(PREP_CHUNK, n - c0);
+            const int mp = (m + 7) & ~7;
+            double *A = buf(b, 0), *B = buf(b, 1);
+            for (int k = tid - PREP_STAGE_T0; k < mp; k += PREP_STAGE_N) {
+                double wv = 0.0, pv = 0.0;
+                if (k < m) { wv = w[lo + c0 + k]; pv = __dmul_rn(x[lo + c0 + k], wv); }
+                A[k] = wv;
+                B[k] = pv;
             }
+        };
+        double run = 0.0;
+        if (tid >= PREP_STAGE_T0) stage1(0, 0);
+        __syncthreads();
+        for (int c = 0; c < nchunks; ++c) {
+            const int b = c & 1;
+            const int m = min(PREP_CHUNK, n - c * PREP_CHUNK);
+            const int mp = (m + 7) & ~7;
+            if (tid >= PREP_STAGE_T0) {
+                if (c + 1 < nchunks) stage1(c + 1, b ^ 1);
+            } else if (lane == 0 && warp < 2) {
+                run = chain_total(buf(b, warp), mp, run);
+            }
+            __syncthreads();
         }
+        if (lane == 0 && warp < 2) s_scalar[1 + warp] = run;
         __syncthreads();
     }
-    if (tid == 0) {
-        s_scalar[0] = sw;
-        s_scalar[1] = __ddiv_rn(swx, sw);
-        s_scalar[2] = sqrt(sw);
-    }
-    __syncthreads();
-    const double avg = s_scalar[1], rsw = s_scalar[2];
+    const double sw = s_scalar[1], swx = s_scalar[2];
+    const double avg = __ddiv_rn(swx, sw), rsw = sqrt(sw);
 
-    // phase 2: centred data, S / cumsum(w) / tss chains
-    double tss = 0.0, cs = 0.0, Srun = 0.0;
-    for (int c0 = 0; c0 < n; c0 += PREP_CHUNK) {
-        const int m = min(PREP_CHUNK, n - c0);
-        for (int k = tid; k < m; k += 256) {
-            const int g = lo + c0 + k;
-            const double wv = w[g];
-            const double c = __dsub_rn(x[g], avg);
-            const double r = sqrt(wv);
-            xc[g] = c;
-            y[g] = __dmul_rn(c, r);
-            wn[g] = __ddiv_rn(wv, rsw);
-            s_a[k] = wv;
-            s_b[k] = __dmul_rn(c, wv);                 // S term
-            s_c[k] = __dmul_rn(wv, __dmul_rn(c, c));   // tss term
-        }
-        __syncthreads();
-        if (tid == 0) {
-#pragma unroll 8
-            for (int k = 0; k < m; ++k) {
-                cs = __dadd_rn(cs, s_a[k]);
-                Srun = __dadd_rn(Srun, s_b[k]);
-                tss = __dadd_rn(tss, s_c[k]);
-                s_a[k] = cs;
-                s_b[k] = Srun;
+    // ---- phase 2: centred data; chains cs = cumsum(w), S = cumsum(xc*w), tss = sum w*xc^2
+    {
+        auto stage2 = [&](int c, int b) {
+            const int c0 = c * PREP_CHUNK;
+            const int m = min(PREP_CHUNK, n - c0);
+            const int mp = (m + 7) & ~7;
+            double *A = buf(b, 0), *B = buf(b, 1), *C = buf(b, 2);
+            for (int k = tid - PREP_STAGE_T0; k < mp; k += PREP_STAGE_N) {
+                double wv = 0.0, sv = 0.0, tv = 0.0;
+                if (k < m) {
+                    const int g = lo + c0 + k;
+                    wv = w[g];
+                    const double cc = __dsub_rn(x[g], avg);
+                    xc[g] = cc;
+                    y[g] = __dmul_rn(cc, sqrt(wv));
+                    wn[g] = __ddiv_rn(wv, rsw);
+                    sv = __dmul_rn(cc, wv);
+                    tv = __dmul_rn(wv, __dmul_rn(cc, cc));
+                }
+                A[k] = wv; B[k] = sv; C[k] = tv;
             }
-        }
+        };
+        auto flush2 = [&](int c, int b) {
+            const int c0 = c * PREP_CHUNK;
+            const int m = min(PREP_CHUNK, n - c0);
+            const double *A = buf(b, 0), *B = buf(b, 1);
+            for (int k = tid - PREP_STAGE_T0; k < m; k += PREP_STAGE_N) {
+                const int g = lo + c0 + k;
+                cw[g] = __ddiv_rn(A[k], rsw);
+                S[g] = B[k];
+            }
+        };
+        double run = 0.0;
+        if (tid >= PREP_STAGE_T0) stage2(0, 0);
         __syncthreads();
-        for (int k = tid; k < m; k += 256) {
-            const int g = lo + c0 + k;
-            S[g] = s_b[k];
-            cw[g] = __ddiv_rn(s_a[k], rsw);
+        for (int c = 0; c < nchunks; ++c) {
+            const int b = c & 1;
+            const int m = min(PREP_CHUNK, n - c * PREP_CHUNK);
+            const int mp = (m + 7) & ~7;
+            if (tid >= PREP_STAGE_T0) {
+                if (c >= 1) flush2(c - 1, b ^ 1);          // results of the previous chunk
+                if (c + 1 < nchunks) stage2(c + 1, b ^ 1);  // then reuse that buffer
+            } else if (lane == 0) {
+                if (warp == 2) run = chain_total(buf(b, 2), mp, run);
+                else run = chain_inplace(buf(b, warp), mp, run);
+            }
+            __syncthreads();
         }
+        if (tid >= PREP_STAGE_T0) flush2(nchunks - 1, (nchunks - 1) & 1);
+        if (lane == 0 && warp == 2) s_scalar[3] = run;
         __syncthreads();
     }
-    if (tid == 0) s_scalar[3] = tss;
-    __syncthreads();
     const double total = cw[lo + n - 1];
 
     // per-block min/max of the prefix points S_0..S_n and the global argmin/argmax (seed arc)
     const int nb = (n + 1 + CBS_BLK - 1) / CBS_BLK;
     double gmin = INFINITY, gmax = -INFINITY;
     int imin = 0, imax = 0;
-    for (int b = warp; b < nb; b += 8) {
+    for (int b = warp; b < nb; b += PREP_THREADS / 32) {
         double bmn = INFINITY, bmx = -INFINITY;
         int bimn = 0, bimx = 0;
         for (int k = lane; k < CBS_BLK; k += 32) {
@@ -211,7 +271,7 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
     }
     __syncthreads();
     if (tid == 0) {
-        for (int k = 1; k < 8; ++k) {
+        for (int k = 1; k < PREP_THREADS / 32; ++k) {
             if (s_red[k] < gmin) { gmin = s_red[k]; imin = s_redi[k]; }
             if (s_red[32 + k] > gmax) { gmax = s_red[32 + k]; imax = s_redi[32 + k]; }
         }
@@ -931,6 +991,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         CNVK_CHECK(cudaGetDevice(&dev));
         CNVK_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
+    CNVK_CHECK(cudaFuncSetAttribute(cbs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM));
     const int max_ones = (int)std::floor((double)P.nperm * P.alpha) + 1;
     std::vector<int> sbdry;
     cbs_getbdry(P.eta, P.nperm, max_ones, sbdry);
@@ -1019,7 +1080,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         CNVK_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(int), stream));
         {
             ProfScope ps(PC_CBS_PREP, stream);
-            cbs_prep_kernel<<<nn, 256, 0, stream>>>(d_nodes, d_x, d_w, d_xc, d_y, d_S, d_cw, d_wn, d_bmin, d_bmax, P.min_width);
+            cbs_prep_kernel<<<nn, PREP_THREADS, PREP_SMEM, stream>>>(d_nodes, d_x, d_w, d_xc, d_y, d_S, d_cw, d_wn, d_bmin, d_bmax, P.min_width);
             CNVK_LAUNCH_CHECK();
         }
         {
