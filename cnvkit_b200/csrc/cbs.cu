@@ -51,6 +51,7 @@ struct Node {
     int best_i, best_j;
     int lock, state, nrejc, blk_off;
     double ostat, ostat1;
+    double delta;  // getmncwt: lightest circular arc of kmax+1 probes / total weight (n > nmin only)
 };
 
 struct Decision {
@@ -108,7 +109,8 @@ __global__ void __launch_bounds__(PREP_THREADS)
 cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const double* __restrict__ w,
                 double* __restrict__ xc, double* __restrict__ y, double* __restrict__ S,
                 double* __restrict__ cw, double* __restrict__ wn, double* __restrict__ blk_min,
-                double* __restrict__ blk_max, int al0) {
+                double* __restrict__ blk_max, int* __restrict__ blk_imin, int* __restrict__ blk_imax, int al0,
+                int hk, int nmin) {
     extern __shared__ __align__(16) double s_dyn[];      // [2 buffers][3 arrays][PREP_CHUNK]
     __shared__ double s_red[64];
     __shared__ int s_redi[64];
@@ -234,6 +236,27 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
     }
     const double total = cw[lo + n - 1];
 
+    // DNAcopy getmncwt: the tail approximation's delta for weighted data is the lightest circular
+    // arc of hk+1 consecutive probes over the total weight (min is order-free, hence exact)
+    if (hk > 0 && n > nmin) {
+        const int jw = hk + 1;
+        double dmin = INFINITY;
+        for (int i = tid; i <= n - jw; i += PREP_THREADS)
+            dmin = fmin(dmin, __dsub_rn(pt(cw, lo, i + jw), pt(cw, lo, i)));
+        for (int i = 1 + tid; i <= jw; i += PREP_THREADS)
+            dmin = fmin(dmin, __dadd_rn(__dsub_rn(total, pt(cw, lo, n - jw + i)), pt(cw, lo, i)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        __syncthreads();
+        if (lane == 0) s_red[warp] = dmin;
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < PREP_THREADS / 32; ++k) dmin = fmin(dmin, s_red[k]);
+            s_scalar[4] = __ddiv_rn(dmin, total);
+        }
+        __syncthreads();
+    }
+
     // per-block min/max of the prefix points S_0..S_n and the global argmin/argmax (seed arc)
     const int nb = (n + 1 + CBS_BLK - 1) / CBS_BLK;
     double gmin = INFINITY, gmax = -INFINITY;
@@ -261,6 +284,8 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
         if (lane == 0) {
             blk_min[nd.blk_off + b] = bmn;
             blk_max[nd.blk_off + b] = bmx;
+            blk_imin[nd.blk_off + b] = bimn;
+            blk_imax[nd.blk_off + b] = bimx;
         }
         if (bmn < gmin) { gmin = bmn; imin = bimn; }
         if (bmx > gmax) { gmax = bmx; imax = bimx; }
@@ -281,6 +306,7 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
         out->tss = s_scalar[3];
         out->rsw = rsw;
         out->total = total;
+        out->delta = (hk > 0 && n > nmin) ? s_scalar[4] : 0.0;
         out->lock = 0;
         // seed arc
         const int i = min(imin, imax), j = max(imin, imax);
@@ -343,202 +369,273 @@ __device__ __forceinline__ void scan_subtiles(Cand& best, const double2* __restr
     }
 }
 
-// Work item ("task") = (node, 1024-point start block ib, chunk of up to 256 consecutive 256-point
-// end blocks).  The 256 threads first test the pruning bound of one end block each (4 sub-tiles),
-// the survivors are compacted into shared memory and then scanned one after the other.
-struct Survivor {
-    int jb;
+// The arc scan of one recursion level runs as three kernels over the same tile geometry
+// (node, 1024-point start block ib = 4 bound blocks, 256-point end block jb):
+//   seed  : every pair of bound blocks proposes the arcs between its extreme prefix points
+//           (argmin S of one block, argmax S of the other) -- real arcs, scored exactly, so the
+//           node's running best starts within a few percent of the maximum;
+//   bound : the pruning test of every (start block, end block) pair against that best; survivors
+//           are appended to a device-wide queue of 1024x256 tiles;
+//   scan  : persistent CTAs pop tiles from the queue (each re-tests its bound against the best
+//           found meanwhile) -- equal-sized work items, so no CTA is left walking a long list.
+struct TileRef {
+    int node, ib, jb;
     unsigned mask;
 };
 
+// task -> (node a, start block ib, first end block jb0); task_off[a] = first task of node a
+__device__ __forceinline__ void decode_task(const Node* __restrict__ nodes, const int* __restrict__ task_off,
+                                            int nnodes, int task, int& a, int& ib, int& jb0, int& NJ) {
+    int lo_ = 0, hi_ = nnodes;
+    while (hi_ - lo_ > 1) {
+        const int m = (lo_ + hi_) >> 1;
+        if (task_off[m] <= task) lo_ = m; else hi_ = m;
+    }
+    a = lo_;
+    const int n = nodes[a].hi - nodes[a].lo;
+    NJ = (n + 1 + CBS_BLK - 1) / CBS_BLK;
+    int t = task - task_off[a];
+    ib = 0;
+    for (;;) {
+        const int cnt = (max(0, NJ - CBS_IW * ib) + 255) / 256;
+        if (t < cnt) break;
+        t -= cnt;
+        ++ib;
+    }
+    jb0 = CBS_IW * ib + 256 * t;
+}
+
+// CTA-wide argmax of the threads' candidates (ties -> smallest (i,j)) and one lock-protected
+// update of the node; only candidates found by this CTA carry i != INT_MAX.
+__device__ __forceinline__ void cta_commit(Node* nd, double q, int qi, int qj, double* s_q, int* s_i, int* s_j) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!__syncthreads_or(qi != 0x7fffffff)) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oq = __shfl_xor_sync(0xffffffffu, q, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, qi, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, qj, o);
+        if (cand_better(oq, oi, oj, q, qi, qj)) { q = oq; qi = oi; qj = oj; }
+    }
+    if (lane == 0) { s_q[warp] = q; s_i[warp] = qi; s_j[warp] = qj; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < 8; ++k)
+            if (cand_better(s_q[k], s_i[k], s_j[k], q, qi, qj)) { q = s_q[k]; qi = s_i[k]; qj = s_j[k]; }
+        if (qi != 0x7fffffff) {
+            while (atomicCAS(&nd->lock, 0, 1) != 0) {}
+            __threadfence();
+            const double cq = *((volatile double*)&nd->best_q);
+            const int cqi = *((volatile int*)&nd->best_i), cqj = *((volatile int*)&nd->best_j);
+            if (cand_better(q, qi, qj, cq, cqi, cqj)) {
+                *((volatile int*)&nd->best_i) = qi;
+                *((volatile int*)&nd->best_j) = qj;
+                *((volatile double*)&nd->best_q) = q;
+            }
+            __threadfence();
+            atomicExch(&nd->lock, 0);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+cbs_seed_kernel(Node* __restrict__ nodes, const int* __restrict__ task_off, int nnodes,
+                const double* __restrict__ S, const double* __restrict__ cw, const int* __restrict__ blk_imin,
+                const int* __restrict__ blk_imax, int al0) {
+    __shared__ double s_q[8];
+    __shared__ int s_i[8], s_j[8];
+    int a, ib, jb0, NJ;
+    decode_task(nodes, task_off, nnodes, blockIdx.x, a, ib, jb0, NJ);
+    Node* nd = &nodes[a];
+    if (nd->flat) return;
+    const int lo = nd->lo, n = nd->hi - nd->lo, boff = nd->blk_off;
+    const double total = nd->total;
+    double bq = -1.0;
+    int bi_ = 0x7fffffff, bj_ = 0x7fffffff;
+    const int jb = jb0 + threadIdx.x;
+    if (jb < NJ && threadIdx.x < 256) {
+        const int jmn = blk_imin[boff + jb], jmx = blk_imax[boff + jb];
+#pragma unroll
+        for (int r = 0; r < CBS_IW; ++r) {
+            const int bi = CBS_IW * ib + r;
+            if (bi > jb || bi >= NJ) continue;
+            const int imn = blk_imin[boff + bi], imx = blk_imax[boff + bi];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                int i = c ? imx : imn, j = c ? jmn : jmx;
+                if (i > j) { const int t_ = i; i = j; j = t_; }
+                const int kw = j - i;
+                if (kw < al0 || kw > n - al0) continue;
+                const double d = __dsub_rn(pt(S, lo, j), pt(S, lo, i));
+                const double cc = __dsub_rn(pt(cw, lo, j), pt(cw, lo, i));
+                const double den = __dmul_rn(cc, __dsub_rn(total, cc));
+                const double q = __ddiv_rn(__dmul_rn(d, d), den);
+                if (cand_better(q, i, j, bq, bi_, bj_)) { bq = q; bi_ = i; bj_ = j; }
+            }
+        }
+    }
+    cta_commit(nd, bq, bi_, bj_, s_q, s_i, s_j);
+}
+
+// upper bound test of one (start block bi, end block jb) pair, bi < jb
+__device__ __forceinline__ bool tile_needed(const double* __restrict__ cw, const double* __restrict__ blk_min,
+                                            const double* __restrict__ blk_max, int lo, int n, int boff, int bi,
+                                            int jb, double total, double gq) {
+    const int jbase = jb * CBS_BLK, jend = min(jbase + CBS_BLK - 1, n);
+    const int ibase = bi * CBS_BLK, iend = min(ibase + CBS_BLK - 1, n);
+    const double d1 = blk_max[boff + jb] - blk_min[boff + bi];
+    const double d2 = blk_max[boff + bi] - blk_min[boff + jb];
+    const double dm = fmax(fabs(d1), fabs(d2));
+    const double cmin = pt(cw, lo, jbase) - pt(cw, lo, iend);
+    const double cmax = pt(cw, lo, jend) - pt(cw, lo, ibase);
+    const double fmin_ = fmin(cmin * (total - cmin), cmax * (total - cmax));
+    if (fmin_ > 0.0) return !((dm * dm) / fmin_ * (1.0 + 1e-9) < gq);
+    return true;
+}
+
 template <bool PRUNE>
 __global__ void __launch_bounds__(256)
-cbs_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ task_off, int nnodes, int total_tasks,
-                int* __restrict__ task_counter, const double* __restrict__ S, const double* __restrict__ cw,
+cbs_bound_kernel(const Node* __restrict__ nodes, const int* __restrict__ task_off, int nnodes,
+                 const double* __restrict__ cw, const double* __restrict__ blk_min,
+                 const double* __restrict__ blk_max, TileRef* __restrict__ queue, int* __restrict__ qcount,
+                 unsigned long long* __restrict__ stats) {
+    __shared__ int s_warp_cnt[8];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int a, ib, jb0, NJ;
+    decode_task(nodes, task_off, nnodes, blockIdx.x, a, ib, jb0, NJ);
+    const Node* nd = &nodes[a];
+    if (nd->flat) return;
+    const int lo = nd->lo, n = nd->hi - nd->lo, boff = nd->blk_off;
+    const double total = nd->total, gq = nd->best_q;
+    unsigned mask = 0;
+    u32 checked = 0;
+    const int jb = jb0 + tid;
+    if (jb < NJ) {
+#pragma unroll
+        for (int r = 0; r < CBS_IW; ++r) {
+            const int bi = CBS_IW * ib + r;
+            if (bi * CBS_BLK > n || bi > jb) continue;
+            bool need = true;
+            if (PRUNE && bi < jb && gq >= 0.0) need = tile_needed(cw, blk_min, blk_max, lo, n, boff, bi, jb, total, gq);
+            ++checked;
+            if (need) mask |= 1u << r;
+        }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, mask != 0);
+    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int k = 0; k < 8; ++k) tot += s_warp_cnt[k];
+        s_base = tot ? atomicAdd(qcount, tot) : 0;
+    }
+    __syncthreads();
+    if (mask) {
+        int base = s_base;
+        for (int k = 0; k < warp; ++k) base += s_warp_cnt[k];
+        TileRef e;
+        e.node = a; e.ib = ib; e.jb = jb; e.mask = mask;
+        queue[base + __popc(bal & ((1u << lane) - 1u))] = e;
+    }
+    if (stats) {
+        checked = warp_sum_u32(checked);
+        if (lane == 0 && checked) atomicAdd(&stats[1], (unsigned long long)checked);
+    }
+}
+
+template <bool PRUNE>
+__global__ void __launch_bounds__(256)
+cbs_scan_kernel(Node* __restrict__ nodes, const TileRef* __restrict__ queue, const int* __restrict__ qcount,
+                int* __restrict__ pop_counter, const double* __restrict__ S, const double* __restrict__ cw,
                 const double* __restrict__ blk_min, const double* __restrict__ blk_max, int al0,
                 unsigned long long* __restrict__ stats) {
     __shared__ double2 sj[CBS_BLK];
-    __shared__ Survivor s_list[256];
-    __shared__ int s_task, s_nsurv;
-    __shared__ int s_warp_cnt[8];
+    __shared__ int s_idx;
+    __shared__ unsigned s_mask;
     __shared__ double s_q[8];
     __shared__ int s_i[8], s_j[8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned long long my_scanned = 0, my_checked = 0;
+    const int tid = threadIdx.x;
+    const int nq = *qcount;
+    unsigned long long my_scanned = 0;
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_task = atomicAdd(task_counter, 1);
+        if (tid == 0) s_idx = atomicAdd(pop_counter, 1);
         __syncthreads();
-        const int task = s_task;
-        if (task >= total_tasks) break;
-        int a = 0, b = nnodes;
-        while (b - a > 1) {
-            const int m = (a + b) >> 1;
-            if (task_off[m] <= task) a = m; else b = m;
-        }
-        Node* nd = &nodes[a];
-        const int lo = nd->lo, n = nd->hi - nd->lo;
+        const int idx = s_idx;
+        if (idx >= nq) break;
+        const TileRef e = queue[idx];
+        Node* nd = &nodes[e.node];
+        const int lo = nd->lo, n = nd->hi - nd->lo, boff = nd->blk_off;
         const int P = n + 1;
-        const int NJ = (P + CBS_BLK - 1) / CBS_BLK;
-        int t = task - task_off[a];
-        int ib = 0;
-        for (;;) {
-            const int cnt = (max(0, NJ - CBS_IW * ib) + 255) / 256;
-            if (t < cnt) break;
-            t -= cnt;
-            ++ib;
-        }
-        const int jb0 = CBS_IW * ib + 256 * t;
+        const int ib = e.ib, jb = e.jb;
         const double total = nd->total;
-        const int boff = nd->blk_off;
-        double gq = *((volatile double*)&nd->best_q);
-
-        // ---- bound test: thread <-> one end block
-        unsigned mask = 0;
-        bool any_masked = false;
-        {
-            const int jb = jb0 + tid;
-            if (jb < NJ) {
-                const int jbase = jb * CBS_BLK;
-                const int jend = min(jbase + CBS_BLK - 1, n);
-                double jmx = 0, jmn = 0, cj0 = 0, cj1 = 0;
-                if (PRUNE) {
-                    jmx = blk_max[boff + jb]; jmn = blk_min[boff + jb];
-                    cj0 = pt(cw, lo, jbase); cj1 = pt(cw, lo, jend);
+        const double gq = *((volatile double*)&nd->best_q);
+        unsigned mask = e.mask;
+        if (PRUNE) {
+            // the best may have risen since the bound kernel ran: re-test (warp 0, one lane per start block)
+            if (tid < 32) {
+                bool keep = false;
+                if (tid < CBS_IW && (mask & (1u << tid))) {
+                    const int bi = CBS_IW * ib + tid;
+                    keep = !(bi < jb && gq >= 0.0) || tile_needed(cw, blk_min, blk_max, lo, n, boff, bi, jb, total, gq);
                 }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (tid == 0) s_mask = m;
+            }
+            __syncthreads();
+            mask = s_mask;
+            if (mask == 0) continue;
+        }
+        const int jbase = jb * CBS_BLK;
+        const int jcount = min(CBS_BLK, P - jbase);
+        const int jend = jbase + jcount - 1;
+        const int na = __popc(mask);
+        bool masked = false;
 #pragma unroll
-                for (int r = 0; r < CBS_IW; ++r) {
-                    const int bi = CBS_IW * ib + r;
-                    const int ibase = bi * CBS_BLK;
-                    if (ibase > n || bi > jb) continue;
-                    const int iend = min(ibase + CBS_BLK - 1, n);
-                    bool need = true;
-                    if (PRUNE && bi < jb && gq >= 0.0) {
-                        const double d1 = jmx - blk_min[boff + bi];
-                        const double d2 = blk_max[boff + bi] - jmn;
-                        const double dm = fmax(fabs(d1), fabs(d2));
-                        const double cmin = cj0 - pt(cw, lo, iend);
-                        const double cmax = cj1 - pt(cw, lo, ibase);
-                        const double fmin_ = fmin(cmin * (total - cmin), cmax * (total - cmax));
-                        if (fmin_ > 0.0) need = !((dm * dm) / fmin_ * (1.0 + 1e-9) < gq);
-                    }
-                    ++my_checked;
-                    if (need) mask |= 1u << r;
-                }
-            }
+        for (int r = 0; r < CBS_IW; ++r) {
+            if (!(mask & (1u << r))) continue;
+            const int ibase = (CBS_IW * ib + r) * CBS_BLK;
+            const int iend = min(ibase + CBS_BLK - 1, n);
+            if (!(jbase - iend >= al0 && jend - ibase <= n - al0 && ibase + CBS_BLK - 1 <= n)) masked = true;
         }
-        // ---- compact survivors
-        {
-            const unsigned bal = __ballot_sync(0xffffffffu, mask != 0);
-            if (lane == 0) s_warp_cnt[warp] = __popc(bal);
-            __syncthreads();
-            int base = 0;
-            for (int k = 0; k < warp; ++k) base += s_warp_cnt[k];
-            if (mask) {
-                Survivor sv;
-                sv.jb = jb0 + tid;
-                sv.mask = mask;
-                s_list[base + __popc(bal & ((1u << lane) - 1u))] = sv;
-            }
-            if (tid == 0) {
-                int tot = 0;
-                for (int k = 0; k < 8; ++k) tot += s_warp_cnt[k];
-                s_nsurv = tot;
-            }
-            __syncthreads();
+        my_scanned += (tid == 0) ? na : 0;
+        if (tid < jcount) sj[tid] = make_double2(pt(S, lo, jbase + tid), pt(cw, lo, jbase + tid));
+        double Si[CBS_IW], ci[CBS_IW];
+        int ii[CBS_IW];
+#pragma unroll
+        for (int r = 0; r < CBS_IW; ++r) {
+            const int slot = (int)__fns(mask, 0, (r < na) ? r + 1 : 1);
+            const int i = (CBS_IW * ib + slot) * CBS_BLK + tid;
+            ii[r] = i;
+            const bool ok = i <= n;
+            Si[r] = ok ? pt(S, lo, i) : 0.0;
+            ci[r] = ok ? pt(cw, lo, i) : 0.0;
         }
-        const int nsurv = s_nsurv;
-        if (nsurv == 0) continue;
-
         Cand best;
         best.q = gq;
         best.qlo = (gq < 0.0) ? -1.0 : gq * (1.0 - 1e-12);
         best.i = 0x7fffffff;
         best.j = 0x7fffffff;
-        for (int sidx = 0; sidx < nsurv; ++sidx) {
-            const Survivor sv = s_list[sidx];
-            const int jb = sv.jb;
-            const int jbase = jb * CBS_BLK;
-            const int jcount = min(CBS_BLK, P - jbase);
-            const int jend = jbase + jcount - 1;
-            const int na = __popc(sv.mask);
-            bool masked = false;
-#pragma unroll
-            for (int r = 0; r < CBS_IW; ++r) {
-                if (!(sv.mask & (1u << r))) continue;
-                const int ibase = (CBS_IW * ib + r) * CBS_BLK;
-                const int iend = min(ibase + CBS_BLK - 1, n);
-                if (!(jbase - iend >= al0 && jend - ibase <= n - al0 && ibase + CBS_BLK - 1 <= n)) masked = true;
-            }
-            my_scanned += (tid == 0) ? na : 0;
-            __syncthreads();  // previous sj consumers are done
-            if (tid < jcount) sj[tid] = make_double2(pt(S, lo, jbase + tid), pt(cw, lo, jbase + tid));
-            double Si[CBS_IW], ci[CBS_IW];
-            int ii[CBS_IW];
-#pragma unroll
-            for (int r = 0; r < CBS_IW; ++r) {
-                const int slot = (int)__fns(sv.mask, 0, (r < na) ? r + 1 : 1);
-                const int i = (CBS_IW * ib + slot) * CBS_BLK + tid;
-                ii[r] = i;
-                const bool ok = i <= n;
-                Si[r] = ok ? pt(S, lo, i) : 0.0;
-                ci[r] = ok ? pt(cw, lo, i) : 0.0;
-            }
-            // tighten the filter with whatever other CTAs have found meanwhile
-            const double gnow = *((volatile double*)&nd->best_q);
-            if (gnow > best.q) { best.q = gnow; best.qlo = gnow * (1.0 - 1e-12); best.i = 0x7fffffff; best.j = 0x7fffffff; }
-            __syncthreads();
-            if (masked) {
-                switch (na) {
-                    case 1: scan_subtiles<1, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                    case 2: scan_subtiles<2, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                    case 3: scan_subtiles<3, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                    default: scan_subtiles<4, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                }
-            } else {
-                switch (na) {
-                    case 1: scan_subtiles<1, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                    case 2: scan_subtiles<2, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                    case 3: scan_subtiles<3, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                    default: scan_subtiles<4, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                }
-            }
-        }
-        // ---- CTA argmax (ties -> smallest (i,j)); only candidates found here carry i != INT_MAX
-        double q = best.q;
-        int qi = best.i, qj = best.j;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double oq = __shfl_xor_sync(0xffffffffu, q, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, qi, o);
-            const int oj = __shfl_xor_sync(0xffffffffu, qj, o);
-            if (cand_better(oq, oi, oj, q, qi, qj)) { q = oq; qi = oi; qj = oj; }
-        }
-        if (lane == 0) { s_q[warp] = q; s_i[warp] = qi; s_j[warp] = qj; }
         __syncthreads();
-        if (tid == 0) {
-            for (int k = 1; k < 8; ++k)
-                if (cand_better(s_q[k], s_i[k], s_j[k], q, qi, qj)) { q = s_q[k]; qi = s_i[k]; qj = s_j[k]; }
-            if (qi != 0x7fffffff) {
-                while (atomicCAS(&nd->lock, 0, 1) != 0) {}
-                __threadfence();
-                const double cq = *((volatile double*)&nd->best_q);
-                const int cqi = *((volatile int*)&nd->best_i), cqj = *((volatile int*)&nd->best_j);
-                if (cand_better(q, qi, qj, cq, cqi, cqj)) {
-                    *((volatile int*)&nd->best_i) = qi;
-                    *((volatile int*)&nd->best_j) = qj;
-                    *((volatile double*)&nd->best_q) = q;
-                }
-                __threadfence();
-                atomicExch(&nd->lock, 0);
+        if (masked) {
+            switch (na) {
+                case 1: scan_subtiles<1, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                case 2: scan_subtiles<2, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                case 3: scan_subtiles<3, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                default: scan_subtiles<4, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+            }
+        } else {
+            switch (na) {
+                case 1: scan_subtiles<1, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                case 2: scan_subtiles<2, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                case 3: scan_subtiles<3, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
+                default: scan_subtiles<4, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
             }
         }
+        cta_commit(nd, best.q, best.i, best.j, s_q, s_i, s_j);
     }
-    if (stats) {
-        my_checked = warp_sum_u32((u32)my_checked);
-        if (lane == 0) atomicAdd(&stats[1], my_checked);
-        if (tid == 0) atomicAdd(&stats[0], my_scanned);
-    }
+    if (stats && tid == 0 && my_scanned) atomicAdd(&stats[0], my_scanned);
 }
 
 // ------------------------------------------------------------------------------------ decide
@@ -610,6 +707,51 @@ __global__ void cbs_stat_kernel(Node* __restrict__ nodes, int nnodes, double alp
     nd->ostat1 = ostat1;
 }
 
+// Cheap two-sided bracket of DNAcopy's tailp that settles almost every node without the series.
+// The Siegmund-Yakir closed form  nu_sy(x) = (2/x)(Phi(x/2)-1/2) / ((x/2)Phi(x/2)+phi(x/2))  lies
+// below the reference's truncated series value by at most 2.2 % for every x > 0.01 (it is exact to
+// 1e-15 for x > 12; tests/test_oracle_pins.py sweeps the bracket), so with p_sy = tailp computed
+// from nu_sy:  p_sy (1-1e-6) <= p_reference <= 1.05 p_sy.  One warp per node.  A node whose bracket
+// straddles alpha (or an nrejc step alpha - m/nperm) keeps ST_NEED_TAILP and gets the exact series.
+__global__ void __launch_bounds__(128)
+cbs_tailp_bounds_kernel(Node* __restrict__ nodes, int nnodes, double alpha, int nperm, int ngrid) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * 4 + warp;
+    if (idx >= nnodes) return;
+    Node* nd = &nodes[idx];
+    if (nd->state != ST_NEED_TAILP) return;
+    const int n = nd->hi - nd->lo;
+    const double b = nd->ostat1, delta = nd->delta;
+    const double dincr = (0.5 - delta) / (double)ngrid;
+    const double bsqrtm = b / sqrt((double)n);
+    double p = 0.0;
+    for (int g = lane; g < ngrid; g += 32) {
+        const double tl = 0.5 - dincr * (double)(g + 1), tt = 0.5 - dincr * ((double)g + 0.5);
+        const double x = bsqrtm / sqrt(tt * (1.0 - tt));
+        double nux;
+        if (x > 0.01) {
+            const double h = 0.5 * x;
+            const double Pc = 0.5 * erf(h * 0.70710678118654752440);  // Phi(h) - 1/2
+            const double ph = 0.3989422804014327 * exp(-0.5 * h * h);
+            nux = ((2.0 / x) * Pc) / (h * (0.5 + Pc) + ph);
+        } else {
+            nux = exp(-0.583 * x);
+        }
+        p += (nux * nux) * it1tsq_dev(tl, dincr);
+    }
+    p = warp_sum(p);
+    if (lane == 0) {
+        p = 2.0 * (9.973557e-2 * (b * b * b) * exp(-(b * b) / 2.0) * p);
+        const double plo = p * (1.0 - 1e-6), phi = p * 1.05;
+        if (plo > alpha) {
+            nd->state = ST_FINAL;
+        } else if (phi <= alpha) {
+            const int r_hi = (int)((alpha - plo) * (double)nperm), r_lo = (int)((alpha - phi) * (double)nperm);
+            if (r_hi == r_lo) { nd->state = ST_PERM_HYBRID; nd->nrejc = r_lo; }
+        }
+    }
+}
+
 // DNAcopy tailp: one CTA per (grid point, node).  nu(x)'s series is summed in the reference's
 // doubling blocks (2,2,4,8,...), each block split over the 128 threads and tree-reduced; the
 // relative-change stopping rule is evaluated between blocks exactly as in the serial code.
@@ -623,7 +765,7 @@ cbs_tailp_terms_kernel(const Node* __restrict__ nodes, double* __restrict__ term
     const int g = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double b = nd->ostat1;
-    const double delta = ((double)kmax + 1.0) / (double)n;
+    const double delta = nd->delta;
     const double dincr = (0.5 - delta) / (double)ngrid;
     const double bsqrtm = b / sqrt((double)n);
     double tl = 0.5 - dincr, tt = 0.5 - 0.5 * dincr;
@@ -808,30 +950,34 @@ __global__ void cbs_perm_flags_kernel(const Node* __restrict__ nodes, const int*
 }
 
 // ------------------------------------------------------------------------------------ flank tests
-// wtpermp set-up: one warp per test (sums by warp reduction; thresholds only)
-__global__ void __launch_bounds__(128)
+// wtpermp set-up: one CTA per test (sums by block reduction; thresholds only)
+__global__ void __launch_bounds__(256)
 cbs_flank_prep_kernel(const Node* __restrict__ nodes, FlankTest* __restrict__ tests, int ntests,
                       const double* __restrict__ xc, const double* __restrict__ w, int nperm) {
+    __shared__ double s_part[5][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * 4 + warp;
-    if (idx >= ntests) return;
+    const int idx = blockIdx.x;
     FlankTest ft = tests[idx];
     const Node* nd = &nodes[ft.node];
     const int g0 = nd->lo + ft.off;
     const int n1 = ft.n1, n2 = ft.n2, n = n1 + n2;
     if (n1 == 1 || n2 == 1) {
-        if (lane == 0) { tests[idx].pvalue = 1.0; tests[idx].need_perm = 0; }
+        if (threadIdx.x == 0) { tests[idx].pvalue = 1.0; tests[idx].need_perm = 0; }
         return;
     }
     double xs1 = 0, xs2 = 0, tss = 0, rn1 = 0, rn2 = 0;
-    for (int k = lane; k < n; k += 32) {
+    for (int k = threadIdx.x; k < n; k += 256) {
         const double xv = xc[g0 + k], wv = w[g0 + k];
         const double wx = wv * xv;
         tss += wv * (xv * xv);
         if (k < n1) { xs1 += wx; rn1 += wv; } else { xs2 += wx; rn2 += wv; }
     }
     xs1 = warp_sum(xs1); xs2 = warp_sum(xs2); tss = warp_sum(tss); rn1 = warp_sum(rn1); rn2 = warp_sum(rn2);
-    if (lane == 0) {
+    if (lane == 0) { s_part[0][warp] = xs1; s_part[1][warp] = xs2; s_part[2][warp] = tss; s_part[3][warp] = rn1; s_part[4][warp] = rn2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        xs1 = xs2 = tss = rn1 = rn2 = 0.0;
+        for (int k = 0; k < 8; ++k) { xs1 += s_part[0][k]; xs2 += s_part[1][k]; tss += s_part[2][k]; rn1 += s_part[3][k]; rn2 += s_part[4][k]; }
         const double rn = rn1 + rn2;
         const double xbar = (xs1 + xs2) / rn;
         tss = tss - rn * (xbar * xbar);
@@ -964,12 +1110,18 @@ struct HostNode {
     int lo, hi, base, arm;
 };
 
-static int tiles_for(int n) {
+// tasks (CTAs of the seed / bound kernels) and 1024x256 tiles of a node of n bins
+static void tiles_for(int n, long long* tasks, long long* tiles) {
     const int P = n + 1;
     const int NJ = (P + CBS_BLK - 1) / CBS_BLK, NI = (P + CBS_IBLK - 1) / CBS_IBLK;
-    int t = 0;
-    for (int ib = 0; ib < NI; ++ib) t += (std::max(0, NJ - CBS_IW * ib) + 255) / 256;
-    return t;
+    long long t = 0, q = 0;
+    for (int ib = 0; ib < NI; ++ib) {
+        const int m = std::max(0, NJ - CBS_IW * ib);
+        t += (m + 255) / 256;
+        q += m;
+    }
+    *tasks = t;
+    *tiles = q;
 }
 
 int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, const CbsParams& P,
@@ -1007,13 +1159,16 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
     CNVK_CHECK(scratch.alloc(&d_wn, (size_t)N));
     CNVK_CHECK(scratch.alloc(&d_bmin, NB));
     CNVK_CHECK(scratch.alloc(&d_bmax, NB));
+    int *d_bimin, *d_bimax;
+    CNVK_CHECK(scratch.alloc(&d_bimin, NB));
+    CNVK_CHECK(scratch.alloc(&d_bimax, NB));
     if (N > 0) {
         sqrt_kernel<<<div_up(N, 256), 256, 0, stream>>>(d_w, d_rw, N);
         CNVK_LAUNCH_CHECK();
     }
-    int* d_counter;
+    int* d_counter;  // [0] tiles queued, [1] tiles popped
     unsigned long long* d_stats;
-    CNVK_CHECK(scratch.alloc(&d_counter, 1));
+    CNVK_CHECK(scratch.alloc(&d_counter, 2));
     CNVK_CHECK(scratch.alloc(&d_stats, 2));
     CNVK_CHECK(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), stream));
 
@@ -1027,11 +1182,13 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
     }
 
     // growable device buffers for per-level arrays
-    size_t cap_nodes = 0;
+    size_t cap_nodes = 0, cap_queue = 0;
+    TileRef* d_queue = nullptr;
     Node* d_nodes = nullptr;
     Decision* d_dec = nullptr;
     int* d_tile_off = nullptr;
     double* d_terms = nullptr;
+    struct QueueGuard { TileRef*& q; cudaStream_t s; ~QueueGuard() { if (q) cudaFreeAsync(q, s); } } qguard{d_queue, stream};
     auto free_level = [&]() {
         if (d_terms) cudaFreeAsync(d_terms, stream);
         d_terms = nullptr;
@@ -1060,7 +1217,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         }
         h_nodes.assign(nn, Node());
         h_tile_off.assign(nn + 1, 0);
-        long long blk_off = 0, tiles = 0;
+        long long blk_off = 0, tiles = 0, qtiles = 0;
         for (int k = 0; k < nn; ++k) {
             Node& nd = h_nodes[k];
             memset(&nd, 0, sizeof(Node));
@@ -1070,27 +1227,43 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             const int n = nd.hi - nd.lo;
             blk_off += (n + 1 + CBS_BLK - 1) / CBS_BLK;
             h_tile_off[k] = (int)tiles;
-            tiles += tiles_for(n);
-            if (tiles >= (1ll << 31)) { set_last_error("cbs_segment: tile count overflow"); return -2; }
+            long long nt_, nq_;
+            tiles_for(n, &nt_, &nq_);
+            tiles += nt_;
+            qtiles += nq_;
+            if (tiles >= (1ll << 31) || qtiles >= (1ll << 31)) { set_last_error("cbs_segment: tile count overflow"); return -2; }
         }
         h_tile_off[nn] = (int)tiles;
         if ((size_t)blk_off > NB) { set_last_error("cbs_segment: block buffer too small"); return -3; }
         CNVK_CHECK(cudaMemcpyAsync(d_nodes, h_nodes.data(), nn * sizeof(Node), cudaMemcpyHostToDevice, stream));
         CNVK_CHECK(cudaMemcpyAsync(d_tile_off, h_tile_off.data(), (nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-        CNVK_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(int), stream));
+        CNVK_CHECK(cudaMemsetAsync(d_counter, 0, 2 * sizeof(int), stream));
+        if ((size_t)qtiles > cap_queue) {
+            if (d_queue) cudaFreeAsync(d_queue, stream);
+            d_queue = nullptr;
+            cap_queue = (size_t)qtiles;
+            CNVK_CHECK(cudaMallocAsync((void**)&d_queue, cap_queue * sizeof(TileRef), stream));
+        }
         {
             ProfScope ps(PC_CBS_PREP, stream);
-            cbs_prep_kernel<<<nn, PREP_THREADS, PREP_SMEM, stream>>>(d_nodes, d_x, d_w, d_xc, d_y, d_S, d_cw, d_wn, d_bmin, d_bmax, P.min_width);
+            cbs_prep_kernel<<<nn, PREP_THREADS, PREP_SMEM, stream>>>(d_nodes, d_x, d_w, d_xc, d_y, d_S, d_cw, d_wn, d_bmin, d_bmax, d_bimin, d_bimax, P.min_width, P.hybrid ? P.kmax : 0, P.nmin);
             CNVK_LAUNCH_CHECK();
         }
         {
             ProfScope ps(PC_CBS_SCAN, stream);
-            const int grid = (int)std::min<long long>(tiles, (long long)sm_count * 8);
-            if (grid > 0) {
-                if (P.prune)
-                    cbs_scan_kernel<true><<<grid, 256, 0, stream>>>(d_nodes, d_tile_off, nn, (int)tiles, d_counter, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
-                else
-                    cbs_scan_kernel<false><<<grid, 256, 0, stream>>>(d_nodes, d_tile_off, nn, (int)tiles, d_counter, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
+            if (tiles > 0) {
+                const int grid = sm_count * 4;
+                if (P.prune & 1) {
+                    cbs_seed_kernel<<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_S, d_cw, d_bimin, d_bimax, P.min_width);
+                    CNVK_LAUNCH_CHECK();
+                    cbs_bound_kernel<true><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
+                    CNVK_LAUNCH_CHECK();
+                    cbs_scan_kernel<true><<<grid, 256, 0, stream>>>(d_nodes, d_queue, d_counter, d_counter + 1, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
+                } else {
+                    cbs_bound_kernel<false><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
+                    CNVK_LAUNCH_CHECK();
+                    cbs_scan_kernel<false><<<grid, 256, 0, stream>>>(d_nodes, d_queue, d_counter, d_counter + 1, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
+                }
                 CNVK_LAUNCH_CHECK();
             }
         }
@@ -1099,6 +1272,10 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             const int ngrid = 100;
             cbs_stat_kernel<<<div_up(nn, 128), 128, 0, stream>>>(d_nodes, nn, P.alpha, P.nperm, P.nmin, P.hybrid);
             CNVK_LAUNCH_CHECK();
+            if (P.hybrid && !(P.prune & 2)) {
+                cbs_tailp_bounds_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, nn, P.alpha, P.nperm, ngrid);
+                CNVK_LAUNCH_CHECK();
+            }
             if (P.hybrid) {
                 for (int y0 = 0; y0 < nn; y0 += 32768) {
                     const int ny = std::min(32768, nn - y0);
@@ -1214,7 +1391,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             CNVK_CHECK(fs.alloc(&d_tests, (size_t)nt));
             CNVK_CHECK(cudaMemcpyAsync(d_tests, tests.data(), nt * sizeof(FlankTest), cudaMemcpyHostToDevice, stream));
             ProfScope fscope(PC_CBS_FLANK, stream);
-            cbs_flank_prep_kernel<<<div_up(nt, 4), 128, 0, stream>>>(d_nodes, d_tests, nt, d_xc, d_w, P.nperm);
+            cbs_flank_prep_kernel<<<nt, 256, 0, stream>>>(d_nodes, d_tests, nt, d_xc, d_w, P.nperm);
             CNVK_LAUNCH_CHECK();
             CNVK_CHECK(cudaMemcpyAsync(tests.data(), d_tests, nt * sizeof(FlankTest), cudaMemcpyDeviceToHost, stream));
             CNVK_CHECK(cudaStreamSynchronize(stream));

@@ -12,12 +12,13 @@ from .. import _lib
 DEFAULTS = dict(nperm=10000, min_width=2, kmax=25, nmin=200, eta=0.05, hybrid=True, seed=0xA5EED)
 
 
-def make_params(alpha, prune=True, **overrides) -> _lib.CbsParams:
+def make_params(alpha, prune=True, tailp_bracket=True, **overrides) -> _lib.CbsParams:
     kw = dict(DEFAULTS)
     kw.update(overrides)
+    prune = int(bool(prune)) | (0 if tailp_bracket else 2)
     return _lib.CbsParams(
         float(alpha), int(kw["nperm"]), int(kw["min_width"]), int(kw["kmax"]), int(kw["nmin"]), float(kw["eta"]),
-        int(bool(kw["hybrid"])), int(bool(prune)), int(kw["seed"]),
+        int(bool(kw["hybrid"])), int(prune), int(kw["seed"]),
     )
 
 
@@ -27,7 +28,8 @@ def getbdry(eta: float, nperm: int, max_ones: int) -> np.ndarray:
     return out
 
 
-def segment_arms(log2, weight, arm_offsets, alpha=1e-4, prune=True, device_ptrs=None, stream=0, **overrides):
+def segment_arms(log2, weight, arm_offsets, alpha=1e-4, prune=True, device_ptrs=None, stream=0, tailp_bracket=True,
+                 **overrides):
     """Segment every arm of a batch in one call.
 
     Parameters are numpy arrays (host path) unless ``device_ptrs=(d_log2, d_weight)`` gives raw
@@ -43,7 +45,7 @@ def segment_arms(log2, weight, arm_offsets, alpha=1e-4, prune=True, device_ptrs=
     seg_hi = np.empty(cap, dtype=np.int64)
     seg_mean = np.empty(cap, dtype=np.float64)
     nseg = ctypes.c_int64(0)
-    params = make_params(alpha, prune=prune, **overrides)
+    params = make_params(alpha, prune=prune, tailp_bracket=tailp_bracket, **overrides)
     stats = _lib.CbsStats()
     if device_ptrs is None:
         x = _lib.f64(log2)

@@ -180,7 +180,9 @@ typedef struct cnvk_cbs_params {
     int32_t nperm, min_width, kmax, nmin;
     double eta;
     int32_t hybrid; /* p.method == "hybrid" */
-    int32_t prune;  /* 1: skip arc tiles whose upper bound cannot reach the current best (same result) */
+    int32_t prune;  /* bit 0: skip arc tiles whose upper bound cannot reach the current best;
+                     * bit 1: always sum the tail-probability series (no closed-form bracket).
+                     * Results are identical for every value; 1 is the fast setting. */
     uint64_t seed;
 } cnvk_cbs_params;
 

@@ -10,7 +10,7 @@
  * tests hold no CBS golden vectors (test/test_r.py asserts structure only).  This file
  * therefore restates the *published* algorithm -- Olshen et al. 2004, Venkatraman & Olshen
  * 2007, and DNAcopy's R/Fortran control flow (segment -> changepoints -> wfindcpt ->
- * wtmaxo / hwtmaxp / wtmaxp / tailp / wtpermp / getbdry) -- anchored on the reference's call
+ * wtmaxo / getmncwt / hwtmaxp / wtmaxp / tailp / wtpermp / getbdry) -- anchored on the reference's call
  * site: segment(CNA(log2, chrom, start, "logratio", presorted=T), weights=w, alpha=threshold)
  * with every other argument at DNAcopy's default (nperm=10000, p.method="hybrid",
  * min.width=2, kmax=25, nmin=200, eta=0.05, undo.splits="none").
@@ -368,7 +368,7 @@ static double wtpermp(const double* x, const double* w, const double* rw, int n1
 /* ------------------------------------------------------------------ wfindcpt */
 /* Tests the interval [lo,hi) of the arm; returns ncpt (0,1,2) and icpt relative to lo. */
 static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, const cbso_params* P,
-                    const int* sbdry, int icpt[2], cbso_stats* st, double* out_ostat1) {
+                    const int* sbdry, int icpt[2], cbso_stats* st, double* out_ostat1, double* out_delta) {
     const int n = hi - lo;
     const double* x = x_arm + lo;
     const double* w = w_arm + lo;
@@ -419,7 +419,14 @@ static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, co
         int nrejc, nrej = 0, k;
         double* wn = NULL;
         if (hybrid) {
-            const double delta = ((double)P->kmax + 1.0) / (double)n;
+            /* DNAcopy getmncwt (weighted data): delta = lightest circular arc of kmax+1 consecutive
+             * probes as a fraction of the total weight (R's (kmax+1)/n is overwritten by it) */
+            const int jw = P->kmax + 1;
+            double delta = N.cw[jw - 1];
+            for (int i = 1; i <= n - jw; ++i) { const double a = N.cw[i + jw - 1] - N.cw[i - 1]; if (a < delta) delta = a; }
+            for (int i = 1; i <= jw; ++i) { const double a = N.total - N.cw[n - jw + i - 1] + N.cw[i - 1]; if (a < delta) delta = a; }
+            delta = delta / N.total;
+            if (out_delta) *out_delta = delta;
             const double pval1 = cbso_tailp(ostat1, delta, n, P->ngrid, P->tol);
             if (pval1 > P->alpha) goto done;
             nrejc = (int)((P->alpha - pval1) * (double)P->nperm);
@@ -473,7 +480,7 @@ done:
 /* One node, for unit tests: returns ncpt, fills icpt and the observed sqrt(T^2). */
 int cbso_find_cpt(const double* x, const double* w, int lo, int hi, const cbso_params* P, const int* sbdry,
                   int* icpt, double* ostat1, cbso_stats* st) {
-    return find_cpt(x, w, lo, hi, P, sbdry, icpt, st, ostat1);
+    return find_cpt(x, w, lo, hi, P, sbdry, icpt, st, ostat1, NULL);
 }
 
 /* DNAcopy changepoints(): returns number of segments; seg_end[k] = exclusive end of segment k.
@@ -488,7 +495,7 @@ int cbso_segment_arm(const double* x, const double* w, int n, const cbso_params*
     while (k > 1) {
         const int lo = stack[k - 2], hi = stack[k - 1];
         int icpt[2] = {0, 0}, ncpt = 0;
-        if (hi - lo >= 2 * P->min_width) ncpt = find_cpt(x, w, lo, hi, P, sbdry, icpt, st, NULL);
+        if (hi - lo >= 2 * P->min_width) ncpt = find_cpt(x, w, lo, hi, P, sbdry, icpt, st, NULL, NULL);
         if (ncpt == 0) { ends[nend++] = hi; --k; }
         else if (ncpt == 1) { stack[k - 1] = lo + icpt[0]; stack[k] = hi; ++k; }
         else { stack[k - 1] = lo + icpt[0]; stack[k] = lo + icpt[1]; stack[k + 1] = hi; k += 2; }

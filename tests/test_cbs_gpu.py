@@ -146,3 +146,27 @@ def test_c3_scale_properties(G):
     np.testing.assert_array_equal(lo, lo2)
     np.testing.assert_array_equal(hi, hi2)
     assert st["obs_subtiles_scanned"] < st2["obs_subtiles_scanned"]
+
+
+def test_tailp_bracket_gives_the_series_decisions(G):
+    """The closed-form bracket of tailp (cbs_tailp_bounds_kernel) must never change a decision:
+    same tables with the bracket on (default) and off (always sum the nu series), on weak signals
+    chosen so that many nodes reach the tail approximation, for several alpha (nrejc steps)."""
+    rng = np.random.default_rng(2024)
+    sizes = [260, 400, 900, 1500, 3000, 8000, 20000]
+    for alpha in (1e-4, 1e-3, 1e-2, 0.05):
+        xs, ws = [], []
+        for n in sizes:
+            x = rng.normal(0, 0.2, n)
+            for _ in range(4):
+                a = int(rng.integers(10, n - 40))
+                x[a:a + int(rng.integers(8, 30))] += rng.choice([-1, 1]) * rng.uniform(0.1, 0.35)
+            xs.append(x)
+            ws.append(rng.uniform(0.5, 1.0, n))
+        x, w = q6(np.concatenate(xs)), q6(np.concatenate(ws))
+        off = np.concatenate([[0], np.cumsum(sizes)])
+        a = G.segment_arms(x, w, off, alpha=alpha)
+        b = G.segment_arms(x, w, off, alpha=alpha, tailp_bracket=False)
+        for u, v in zip(a[:4], b[:4]):
+            np.testing.assert_array_equal(u, v)
+        compare(G, x, w, off, alpha)
