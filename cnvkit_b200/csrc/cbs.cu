@@ -3,18 +3,22 @@
 // i.e. DNAcopy::segment(CNA(log2,...), weights=w, alpha=threshold) with DNAcopy defaults).
 //
 // Structure (level-synchronous over ALL arms of ALL samples in the batch):
-//   prep   : one CTA per open interval ("node"): weighted centring, tss, and the strictly
-//            sequential FP64 prefix sums S_i = sum w x, cw_i = cumsum(w)/sqrt(sum w) that define
-//            the statistic's bits (one elected thread runs the add chains out of shared-memory
-//            chunks the other threads stage), per-256-point block min/max of S for pruning and a
-//            seed arc (argmin S, argmax S).
-//   scan   : persistent CTAs pull 1024x256 arc tiles from an atomic queue; every thread keeps
-//            4 arc starts in registers and streams 256 arc ends from shared memory;
-//            BSS_ij = (S_j-S_i)^2 / (c (W-c)), c = cw_j-cw_i, is compared division-free against
-//            the running best (exact IEEE division only on the rare update).  256x256 sub-tiles
-//            whose upper bound (block min/max of S, extreme c) cannot reach the node's current
-//            best are skipped -- the GPU form of DNAcopy's block-pruned wtmaxo.  Warp-shuffle
-//            argmax, then one lock-protected update of the node's (q,i,j), ties -> smallest (i,j).
+//   prep   : one CTA per open interval ("node"): sum w, sum x*w, sum w*xc^2 as double-double
+//            reductions (R-level sum() calls), weighted centring, and the strictly sequential FP64
+//            prefix sums S_i = sum w xc, cw_i = cumsum(w)/sqrt(sum w) that define the statistic's
+//            bits (one warp per chain runs it out of shared-memory chunks the other warps stage),
+//            per-256-point block min/max (+ arg) of S for pruning, getmncwt's delta.
+//   seed   : every pair of 256-point blocks proposes the arcs between its extreme prefix points.
+//   band   : arcs whose end points lie in the same or adjacent 256-point blocks, pruned on 32x32
+//            sub-blocks out of shared memory (they cannot be pruned at 256-point granularity).
+//   bound  : upper bound (block min/max of S, extreme c) of every remaining 256x256 sub-tile
+//            against the node's running best; survivors go to a device-wide tile queue -- the
+//            GPU form of DNAcopy's block-pruned wtmaxo.
+//   scan   : persistent CTAs pop 1024x256 tiles; every thread keeps 4 arc starts in registers and
+//            streams 256 arc ends from shared memory; BSS_ij = (S_j-S_i)^2 / (c (W-c)),
+//            c = cw_j-cw_i, is compared division-free against the running best (exact IEEE
+//            division only on the rare update).  Warp-shuffle argmax, then one lock-protected
+//            update of the node's (q,i,j), ties -> smallest (i,j).
 //   decide : one warp per node: T^2, the 0.1 / 7.0 shortcuts, Siegmund tail approximation
 //            (hybrid, n > nmin), and the number of exceedances tolerated.
 //   perms  : reference distribution for undecided nodes, evaluated in SM-resident tiles with
@@ -37,7 +41,7 @@ static const int CBS_BLK = 256;           // points per bound block / j-block
 static const int CBS_IW = 4;              // arc starts per thread
 static const int CBS_IBLK = CBS_BLK * CBS_IW;
 static const int PREP_CHUNK = 1024;
-static const size_t PREP_SMEM = (size_t)2 * 3 * PREP_CHUNK * sizeof(double);
+static const size_t PREP_SMEM = (size_t)2 * 2 * PREP_CHUNK * sizeof(double);
 static const int HYB_TP = 2048;           // arc starts per CTA in the hybrid permutation kernel
 static const int HYB_KMAX = 64;           // max supported kmax
 static const int EXACT_NMAX = 256;        // max supported nmin
@@ -69,12 +73,18 @@ __device__ __forceinline__ double pt(const double* a, int lo, int i) {
 }
 
 // ------------------------------------------------------------------------------------ prep
-// Sequential FP64 add chains are the critical path of this kernel (they define the bits of S, cw
-// and tss).  Each chain gets its own warp (lane 0 runs it out of shared memory, 8 elements per
-// iteration with 128-bit loads/stores), while the remaining warps stage the next chunk and write
-// the previous one back to HBM -- double-buffered, one __syncthreads per chunk.
+// Which sums are order-defined and which are not (R's changepoints() for weighted data):
+//   * sum(w), sum(x*w), sum(w*xc^2) are R-level sum() calls -- R accumulates them in 80-bit long
+//     double, i.e. they are (to within an ulp) the correctly rounded exact sums.  They are
+//     evaluated here as double-double (compensated) reductions over all threads: parallel, and the
+//     rounded result does not depend on the order of accumulation.
+//   * S_i = sum_{l<=i} xc_l w_l is DNAcopy's Fortran partial-sum loop: a strictly sequential FP64 add
+//     chain that defines the bits of the statistic; cumsum(w) is kept as the same kind of chain.
+//     Each chain gets its own warp (lane 0 runs it out of shared memory, 8 elements per iteration
+//     with 128-bit loads/stores) while the other warps stage the next chunk and write the previous
+//     one back to HBM -- double-buffered, one __syncthreads per chunk.
 static const int PREP_THREADS = 256;
-static const int PREP_CHAIN_WARPS = 3;
+static const int PREP_CHAIN_WARPS = 2;
 static const int PREP_STAGE_T0 = PREP_CHAIN_WARPS * 32;           // first staging thread
 static const int PREP_STAGE_N = PREP_THREADS - PREP_STAGE_T0;     // staging threads
 
@@ -92,17 +102,44 @@ __device__ __forceinline__ double chain_inplace(double* s, int m, double run) {
     return run;
 }
 
-// running sum without write-back (totals only)
-__device__ __forceinline__ double chain_total(const double* s, int m, double run) {
-    const double2* p = reinterpret_cast<const double2*>(s);
-    for (int t = 0; t < m / 2; t += 4) {
-        const double2 v0 = p[t], v1 = p[t + 1], v2 = p[t + 2], v3 = p[t + 3];
-        run = __dadd_rn(run, v0.x); run = __dadd_rn(run, v0.y);
-        run = __dadd_rn(run, v1.x); run = __dadd_rn(run, v1.y);
-        run = __dadd_rn(run, v2.x); run = __dadd_rn(run, v2.y);
-        run = __dadd_rn(run, v3.x); run = __dadd_rn(run, v3.y);
+// double-double accumulator: hi + lo carries the running sum to ~2^-104 relative
+struct DD {
+    double hi, lo;
+};
+__device__ __forceinline__ void dd_add(DD& a, double p) {          // a += p  (Knuth two-sum)
+    const double s = __dadd_rn(a.hi, p);
+    const double bb = __dsub_rn(s, a.hi);
+    const double e = __dadd_rn(__dsub_rn(a.hi, __dsub_rn(s, bb)), __dsub_rn(p, bb));
+    a.hi = s;
+    a.lo = __dadd_rn(a.lo, e);
+}
+__device__ __forceinline__ void dd_merge(DD& a, double bhi, double blo) {  // a += (bhi, blo)
+    dd_add(a, bhi);
+    a.lo = __dadd_rn(a.lo, blo);
+}
+__device__ __forceinline__ DD dd_warp_sum(DD a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double h = __shfl_xor_sync(0xffffffffu, a.hi, o);
+        const double l = __shfl_xor_sync(0xffffffffu, a.lo, o);
+        dd_merge(a, h, l);
     }
-    return run;
+    return a;
+}
+// CTA-wide sum of per-thread double-doubles, rounded to double once; result valid in thread 0
+__device__ __forceinline__ double dd_block_sum(DD a, double* s_hi, double* s_lo) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = dd_warp_sum(a);
+    if (lane == 0) { s_hi[warp] = a.hi; s_lo[warp] = a.lo; }
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0) {
+        DD t = {s_hi[0], s_lo[0]};
+        for (int k = 1; k < PREP_THREADS / 32; ++k) dd_merge(t, s_hi[k], s_lo[k]);
+        r = __dadd_rn(t.hi, t.lo);
+    }
+    __syncthreads();
+    return r;
 }
 
 __global__ void __launch_bounds__(PREP_THREADS)
@@ -111,21 +148,25 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
                 double* __restrict__ cw, double* __restrict__ wn, double* __restrict__ blk_min,
                 double* __restrict__ blk_max, int* __restrict__ blk_imin, int* __restrict__ blk_imax, int al0,
                 int hk, int nmin) {
-    extern __shared__ __align__(16) double s_dyn[];      // [2 buffers][3 arrays][PREP_CHUNK]
+    extern __shared__ __align__(16) double s_dyn[];      // [2 buffers][2 arrays][PREP_CHUNK]
     __shared__ double s_red[64];
     __shared__ int s_redi[64];
     __shared__ double s_scalar[8];
     Node nd = nodes[blockIdx.x];
     const int lo = nd.lo, n = nd.hi - nd.lo;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    auto buf = [&](int b, int arr) { return s_dyn + ((size_t)b * 3 + arr) * PREP_CHUNK; };
+    auto buf = [&](int b, int arr) { return s_dyn + ((size_t)b * 2 + arr) * PREP_CHUNK; };
 
-    // range check: isTRUE(all.equal(diff(range(x)), 0)) -> final (changepoints R code)
+    // range check: isTRUE(all.equal(diff(range(x)), 0)) -> final (changepoints R code);
+    // the same pass accumulates sum(w) and sum(x*w)
     double mn = INFINITY, mx = -INFINITY;
+    DD a_w = {0.0, 0.0}, a_wx = {0.0, 0.0};
     for (int k = tid; k < n; k += PREP_THREADS) {
-        const double v = x[lo + k];
+        const double v = x[lo + k], wv = w[lo + k];
         mn = fmin(mn, v);
         mx = fmax(mx, v);
+        dd_add(a_w, wv);
+        dd_add(a_wx, __dmul_rn(v, wv));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -147,50 +188,25 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
         return;
     }
     const int nchunks = (n + PREP_CHUNK - 1) / PREP_CHUNK;
-
-    // ---- phase 1: sw = sum w, swx = sum x*w  (two chains)
     {
-        auto stage1 = [&](int c, int b) {
-            const int c0 = c * PREP_CHUNK;
-            const int m = min(PREP_CHUNK, n - c0);
-            const int mp = (m + 7) & ~7;
-            double *A = buf(b, 0), *B = buf(b, 1);
-            for (int k = tid - PREP_STAGE_T0; k < mp; k += PREP_STAGE_N) {
-                double wv = 0.0, pv = 0.0;
-                if (k < m) { wv = w[lo + c0 + k]; pv = __dmul_rn(x[lo + c0 + k], wv); }
-                A[k] = wv;
-                B[k] = pv;
-            }
-        };
-        double run = 0.0;
-        if (tid >= PREP_STAGE_T0) stage1(0, 0);
-        __syncthreads();
-        for (int c = 0; c < nchunks; ++c) {
-            const int b = c & 1;
-            const int m = min(PREP_CHUNK, n - c * PREP_CHUNK);
-            const int mp = (m + 7) & ~7;
-            if (tid >= PREP_STAGE_T0) {
-                if (c + 1 < nchunks) stage1(c + 1, b ^ 1);
-            } else if (lane == 0 && warp < 2) {
-                run = chain_total(buf(b, warp), mp, run);
-            }
-            __syncthreads();
-        }
-        if (lane == 0 && warp < 2) s_scalar[1 + warp] = run;
+        const double sw_ = dd_block_sum(a_w, s_red, s_red + 32);
+        const double swx_ = dd_block_sum(a_wx, s_red, s_red + 32);
+        if (tid == 0) { s_scalar[1] = sw_; s_scalar[2] = swx_; }
         __syncthreads();
     }
     const double sw = s_scalar[1], swx = s_scalar[2];
     const double avg = __ddiv_rn(swx, sw), rsw = sqrt(sw);
 
-    // ---- phase 2: centred data; chains cs = cumsum(w), S = cumsum(xc*w), tss = sum w*xc^2
+    // ---- centred data; chains cs = cumsum(w), S = cumsum(xc*w); tss = sum w*xc^2 (double-double)
+    DD a_tss = {0.0, 0.0};
     {
         auto stage2 = [&](int c, int b) {
             const int c0 = c * PREP_CHUNK;
             const int m = min(PREP_CHUNK, n - c0);
             const int mp = (m + 7) & ~7;
-            double *A = buf(b, 0), *B = buf(b, 1), *C = buf(b, 2);
+            double *A = buf(b, 0), *B = buf(b, 1);
             for (int k = tid - PREP_STAGE_T0; k < mp; k += PREP_STAGE_N) {
-                double wv = 0.0, sv = 0.0, tv = 0.0;
+                double wv = 0.0, sv = 0.0;
                 if (k < m) {
                     const int g = lo + c0 + k;
                     wv = w[g];
@@ -199,9 +215,9 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
                     y[g] = __dmul_rn(cc, sqrt(wv));
                     wn[g] = __ddiv_rn(wv, rsw);
                     sv = __dmul_rn(cc, wv);
-                    tv = __dmul_rn(wv, __dmul_rn(cc, cc));
+                    dd_add(a_tss, __dmul_rn(wv, __dmul_rn(cc, cc)));
                 }
-                A[k] = wv; B[k] = sv; C[k] = tv;
+                A[k] = wv; B[k] = sv;
             }
         };
         auto flush2 = [&](int c, int b) {
@@ -225,13 +241,13 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
                 if (c >= 1) flush2(c - 1, b ^ 1);          // results of the previous chunk
                 if (c + 1 < nchunks) stage2(c + 1, b ^ 1);  // then reuse that buffer
             } else if (lane == 0) {
-                if (warp == 2) run = chain_total(buf(b, 2), mp, run);
-                else run = chain_inplace(buf(b, warp), mp, run);
+                run = chain_inplace(buf(b, warp), mp, run);
             }
             __syncthreads();
         }
         if (tid >= PREP_STAGE_T0) flush2(nchunks - 1, (nchunks - 1) & 1);
-        if (lane == 0 && warp == 2) s_scalar[3] = run;
+        const double tss_ = dd_block_sum(a_tss, s_red, s_red + 32);
+        if (tid == 0) s_scalar[3] = tss_;
         __syncthreads();
     }
     const double total = cw[lo + n - 1];
@@ -422,7 +438,8 @@ __device__ __forceinline__ void cta_commit(Node* nd, double q, int qi, int qj, d
     if (tid == 0) {
         for (int k = 1; k < 8; ++k)
             if (cand_better(s_q[k], s_i[k], s_j[k], q, qi, qj)) { q = s_q[k]; qi = s_i[k]; qj = s_j[k]; }
-        if (qi != 0x7fffffff) {
+        // best_q only rises, so a candidate strictly below it can never win: skip the lock
+        if (qi != 0x7fffffff && !(q < *((volatile double*)&nd->best_q))) {
             while (atomicCAS(&nd->lock, 0, 1) != 0) {}
             __threadfence();
             const double cq = *((volatile double*)&nd->best_q);
@@ -493,6 +510,89 @@ __device__ __forceinline__ bool tile_needed(const double* __restrict__ cw, const
     return true;
 }
 
+// Narrow arcs: every (i, j) whose 256-point blocks are equal or adjacent.  At 256-point granularity
+// these tiles can never be pruned (the lightest arc of the pair is a single bin), and they used to
+// be most of the scan; here one CTA owns one start block, keeps its 512 candidate end points in
+// shared memory and repeats the bound test on 32x32 sub-blocks, warp-uniformly (warp <-> 32 starts).
+static const int BAND_SUB = 32;
+static const int BAND_PTS = 2 * CBS_BLK;
+
+template <bool PRUNE>
+__global__ void __launch_bounds__(256)
+cbs_band_kernel(Node* __restrict__ nodes, int nnodes,
+                const double* __restrict__ S, const double* __restrict__ cw, int al0,
+                unsigned long long* __restrict__ stats) {
+    __shared__ double2 sp[BAND_PTS];
+    __shared__ double s_mn[BAND_PTS / BAND_SUB], s_mx[BAND_PTS / BAND_SUB];
+    __shared__ double s_q[8];
+    __shared__ int s_i[8], s_j[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int a = 0, hi_ = nnodes;
+    while (hi_ - a > 1) {
+        const int m = (a + hi_) >> 1;
+        if (nodes[m].blk_off <= (int)blockIdx.x) a = m; else hi_ = m;
+    }
+    Node* nd = &nodes[a];
+    if (nd->flat) return;
+    const int lo = nd->lo, n = nd->hi - nd->lo;
+    const int bi = blockIdx.x - nd->blk_off;
+    const int ibase = bi * CBS_BLK;
+    const int npts = min(BAND_PTS, n + 1 - ibase);   // points ibase .. ibase+npts-1 (<= n)
+    const double total = nd->total;
+    for (int k = tid; k < BAND_PTS; k += 256)
+        sp[k] = (k < npts) ? make_double2(pt(S, lo, ibase + k), pt(cw, lo, ibase + k)) : make_double2(0.0, 0.0);
+    __syncthreads();
+    const int nsub = (npts + BAND_SUB - 1) / BAND_SUB;
+    for (int sb = warp; sb < nsub; sb += 8) {       // min/max of S per 32-point sub-block
+        const int k = sb * BAND_SUB + lane;
+        double vmn = (k < npts) ? sp[k].x : INFINITY, vmx = (k < npts) ? sp[k].x : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vmn = fmin(vmn, __shfl_xor_sync(0xffffffffu, vmn, o));
+            vmx = fmax(vmx, __shfl_xor_sync(0xffffffffu, vmx, o));
+        }
+        if (lane == 0) { s_mn[sb] = vmn; s_mx[sb] = vmx; }
+    }
+    __syncthreads();
+    const double gq = *((volatile double*)&nd->best_q);
+    Cand best;
+    best.q = gq;
+    best.qlo = (gq < 0.0) ? -1.0 : gq * (1.0 - 1e-12);
+    best.i = 0x7fffffff;
+    best.j = 0x7fffffff;
+    unsigned my_pairs = 0;
+    const int il = warp * BAND_SUB + lane;          // this lane's start point (local)
+    if (warp * BAND_SUB < npts && warp * BAND_SUB < CBS_BLK) {
+        const int i = ibase + il;
+        const bool iok = il < npts;
+        const double Si = iok ? sp[il].x : 0.0, ci = iok ? sp[il].y : 0.0;
+        const int wend = min(warp * BAND_SUB + BAND_SUB - 1, npts - 1);
+        for (int sb = warp; sb < nsub; ++sb) {
+            const int j0 = sb * BAND_SUB, j1 = min(j0 + BAND_SUB - 1, npts - 1);
+            if (PRUNE && sb > warp + 1 && gq >= 0.0) {
+                const double d1 = s_mx[sb] - s_mn[warp], d2 = s_mx[warp] - s_mn[sb];
+                const double dm = fmax(fabs(d1), fabs(d2));
+                const double cmin = sp[j0].y - sp[wend].y, cmax = sp[j1].y - sp[warp * BAND_SUB].y;
+                const double fmin_ = fmin(cmin * (total - cmin), cmax * (total - cmax));
+                if (fmin_ > 0.0 && (dm * dm) / fmin_ * (1.0 + 1e-9) < gq) continue;
+            }
+            ++my_pairs;
+            for (int jl = j0; jl <= j1; ++jl) {
+                const double2 pj = sp[jl];
+                const int kw = jl - il;
+                const double d = __dsub_rn(pj.x, Si);
+                const double c = __dsub_rn(pj.y, ci);
+                const double den = __dmul_rn(c, __dsub_rn(total, c));
+                const double num = __dmul_rn(d, d);
+                if (iok && kw >= al0 && kw <= n - al0 && num > __dmul_rn(best.qlo, den))
+                    cand_update(best, num, den, i, ibase + jl);
+            }
+        }
+    }
+    if (stats && lane == 0 && my_pairs) atomicAdd(&stats[2], (unsigned long long)my_pairs);
+    cta_commit(nd, best.q, best.i, best.j, s_q, s_i, s_j);
+}
+
 template <bool PRUNE>
 __global__ void __launch_bounds__(256)
 cbs_bound_kernel(const Node* __restrict__ nodes, const int* __restrict__ task_off, int nnodes,
@@ -515,9 +615,9 @@ cbs_bound_kernel(const Node* __restrict__ nodes, const int* __restrict__ task_of
 #pragma unroll
         for (int r = 0; r < CBS_IW; ++r) {
             const int bi = CBS_IW * ib + r;
-            if (bi * CBS_BLK > n || bi > jb) continue;
+            if (bi * CBS_BLK > n || bi + 1 >= jb) continue;  // bi >= jb-1: the band kernel's arcs
             bool need = true;
-            if (PRUNE && bi < jb && gq >= 0.0) need = tile_needed(cw, blk_min, blk_max, lo, n, boff, bi, jb, total, gq);
+            if (PRUNE && gq >= 0.0) need = tile_needed(cw, blk_min, blk_max, lo, n, boff, bi, jb, total, gq);
             ++checked;
             if (need) mask |= 1u << r;
         }
@@ -1026,21 +1126,26 @@ __global__ void sqrt_kernel(const double* __restrict__ w, double* __restrict__ o
     if (i < n) out[i] = sqrt(w[i]);
 }
 
-// weighted.mean(log2, weight) per segment (cbs.py:70-71); one warp per segment
-__global__ void __launch_bounds__(128)
+// weighted.mean(log2, weight) per segment (cbs.py:70-71); one CTA per segment
+__global__ void __launch_bounds__(256)
 seg_mean_kernel(const double* __restrict__ x, const double* __restrict__ w, const long long* __restrict__ lo,
                 const long long* __restrict__ hi, int nseg, double* __restrict__ mean) {
+    __shared__ double s_a[8], s_b[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x * 4 + warp;
-    if (s >= nseg) return;
+    const int s = blockIdx.x;
     double sw = 0.0, swx = 0.0;
-    for (long long k = lo[s] + lane; k < hi[s]; k += 32) {
+    for (long long k = lo[s] + threadIdx.x; k < hi[s]; k += 256) {
         sw += w[k];
         swx += x[k] * w[k];
     }
     sw = warp_sum(sw);
     swx = warp_sum(swx);
-    if (lane == 0) mean[s] = swx / sw;
+    if (lane == 0) { s_a[warp] = sw; s_b[warp] = swx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) { sw += s_a[k]; swx += s_b[k]; }
+        mean[s] = swx / sw;
+    }
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -1169,8 +1274,8 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
     int* d_counter;  // [0] tiles queued, [1] tiles popped
     unsigned long long* d_stats;
     CNVK_CHECK(scratch.alloc(&d_counter, 2));
-    CNVK_CHECK(scratch.alloc(&d_stats, 2));
-    CNVK_CHECK(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), stream));
+    CNVK_CHECK(scratch.alloc(&d_stats, 3));  // [0] 256x256 sub-tiles scanned, [1] tested, [2] 32x32 band pairs scanned
+    CNVK_CHECK(cudaMemsetAsync(d_stats, 0, 3 * sizeof(unsigned long long), stream));
 
     std::vector<HostNode> frontier;
     std::vector<std::vector<int>> ends(n_arms);
@@ -1256,10 +1361,14 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 if (P.prune & 1) {
                     cbs_seed_kernel<<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_S, d_cw, d_bimin, d_bimax, P.min_width);
                     CNVK_LAUNCH_CHECK();
+                    cbs_band_kernel<true><<<(int)blk_off, 256, 0, stream>>>(d_nodes, nn, d_S, d_cw, P.min_width, d_stats);
+                    CNVK_LAUNCH_CHECK();
                     cbs_bound_kernel<true><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
                     CNVK_LAUNCH_CHECK();
                     cbs_scan_kernel<true><<<grid, 256, 0, stream>>>(d_nodes, d_queue, d_counter, d_counter + 1, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
                 } else {
+                    cbs_band_kernel<false><<<(int)blk_off, 256, 0, stream>>>(d_nodes, nn, d_S, d_cw, P.min_width, d_stats);
+                    CNVK_LAUNCH_CHECK();
                     cbs_bound_kernel<false><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
                     CNVK_LAUNCH_CHECK();
                     cbs_scan_kernel<false><<<grid, 256, 0, stream>>>(d_nodes, d_queue, d_counter, d_counter + 1, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
@@ -1472,7 +1581,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         CNVK_CHECK(ms.alloc(&d_mean, (size_t)ns));
         CNVK_CHECK(cudaMemcpyAsync(d_lo, slo.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, stream));
         CNVK_CHECK(cudaMemcpyAsync(d_hi, shi.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, stream));
-        seg_mean_kernel<<<div_up(ns, 4), 128, 0, stream>>>(d_x, d_w, d_lo, d_hi, ns, d_mean);
+        seg_mean_kernel<<<ns, 256, 0, stream>>>(d_x, d_w, d_lo, d_hi, ns, d_mean);
         CNVK_LAUNCH_CHECK();
         std::vector<double> means(ns);
         CNVK_CHECK(cudaMemcpyAsync(means.data(), d_mean, ns * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -1480,12 +1589,12 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         for (int s = 0; s < ns; ++s) segs[s].mean = means[s];
     }
     {
-        unsigned long long h_stats[2];
+        unsigned long long h_stats[3];
         CNVK_CHECK(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
         CNVK_CHECK(cudaStreamSynchronize(stream));
         st.obs_subtiles_scanned = (long long)h_stats[0];
         st.obs_subtiles_total = (long long)h_stats[1];
-        st.obs_arcs = st.obs_subtiles_scanned * (long long)CBS_BLK * CBS_BLK;
+        st.obs_arcs = st.obs_subtiles_scanned * (long long)CBS_BLK * CBS_BLK + (long long)h_stats[2] * BAND_SUB * BAND_SUB;
     }
     if (stats) *stats = st;
     return 0;

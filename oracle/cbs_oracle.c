@@ -23,8 +23,11 @@
  *      alternating Feistel network with cycle walking).  Results are therefore independent
  *      of the order in which nodes are visited -- which is what lets the GPU process the
  *      recursion level-synchronously and still agree with this file exactly.
- *  (2) R computes sum()/cumsum() in 80-bit extended precision; here every sum is a plain
- *      left-to-right IEEE double accumulation (as DNAcopy's Fortran partial sums are).
+ *  (2) R computes sum()/cumsum() in 80-bit extended precision.  Here the three R-level totals
+ *      (sum w, sum x*w, sum w*xc^2) are compensated double-double sums rounded once -- the
+ *      correctly rounded exact sum, which is what R's long-double accumulation yields to within an
+ *      ulp -- while cumsum(w) and DNAcopy's Fortran partial sums S_i are plain left-to-right IEEE
+ *      double accumulations.
  *  (3) wtmaxo's block-pruned search is restated as an exhaustive scan over all arcs; the
  *      maximum is the same, ties resolve to the smallest (i, j).
  *  (4) hwtmaxp (hybrid permutation statistic) is restated as windowed sums over circular
@@ -248,6 +251,16 @@ int cbso_getbdry(double eta, int nperm, int max_ones, int* out) {
     return l;
 }
 
+/* ------------------------------------------------------------------ exact-ish sums */
+typedef struct { double hi, lo; } dd_t;
+static inline void dd_add(dd_t* a, double p) { /* Knuth two-sum; lo collects the rounding errors */
+    const double s = a->hi + p;
+    const double bb = s - a->hi;
+    const double e = (a->hi - (s - bb)) + (p - bb);
+    a->hi = s;
+    a->lo += e;
+}
+
 /* ------------------------------------------------------------------ node statistics */
 typedef struct {
     int n;
@@ -381,8 +394,11 @@ static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, co
 
     node_t N;
     node_alloc(&N, n);
-    double sw = 0.0, swx = 0.0;
-    for (int i = 0; i < n; ++i) { sw += w[i]; swx += x[i] * w[i]; }
+    /* sum(w), sum(x*w), sum(w*xc^2) are R-level sum() calls (80-bit accumulators in R): evaluated as
+     * compensated double-double sums, i.e. the correctly rounded exact sum, independent of order */
+    dd_t a_w = {0.0, 0.0}, a_wx = {0.0, 0.0}, a_tss = {0.0, 0.0};
+    for (int i = 0; i < n; ++i) { dd_add(&a_w, w[i]); dd_add(&a_wx, x[i] * w[i]); }
+    const double sw = a_w.hi + a_w.lo, swx = a_wx.hi + a_wx.lo;
     const double avg = swx / sw;
     const double rsw = sqrt(sw);
     double tss = 0.0, cs = 0.0, S = 0.0;
@@ -392,12 +408,13 @@ static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, co
         N.xc[i] = x[i] - avg;
         N.rw[i] = sqrt(w[i]);
         N.y[i] = N.xc[i] * N.rw[i];
-        tss += w[i] * (N.xc[i] * N.xc[i]);
+        dd_add(&a_tss, w[i] * (N.xc[i] * N.xc[i]));
         cs += w[i];
         N.cw[i] = cs / rsw;
         S += N.xc[i] * w[i];
         N.S[i + 1] = S;
     }
+    tss = a_tss.hi + a_tss.lo;
     N.tss = tss;
     N.total = N.cw[n - 1];
 
