@@ -34,6 +34,7 @@ METRIC = "bins segmented/s (CBS, WGS 1 kb)"
 UNIT = "bins/s"
 ALPHA = 1e-4
 FLOP_PER_ARC = 7  # sub, sub, sub, mul, mul, mul, compare -- weighted BSS, division-free test
+PREP_BYTES_PER_BIN = 56  # read log2, weight (16 B); write xc, y, wn, S, cw (40 B)
 
 
 def parse_args():
@@ -96,30 +97,6 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
-
-
-def lpt_shards(arm_sizes, n_shards):
-    """Longest-processing-time assignment of arms to ranks, cost ~ n^2 (first-level arc count)."""
-    order = np.argsort(-arm_sizes.astype(np.float64) ** 2, kind="stable")
-    load = np.zeros(n_shards)
-    owner = np.zeros(len(arm_sizes), dtype=np.int64)
-    for a in order:
-        r = int(np.argmin(load))
-        owner[a] = r
-        load[r] += float(arm_sizes[a]) ** 2
-    return owner
-
-
-def shard_columns(data, owner, rank):
-    """Concatenate this rank's arms; returns (log2, weight, local arm offsets, global arm ids)."""
-    off = data["arm_offsets"]
-    mine = np.flatnonzero(owner == rank)
-    xs = [data["log2"][off[a]:off[a + 1]] for a in mine]
-    ws = [data["weight"][off[a]:off[a + 1]] for a in mine]
-    sizes = np.array([off[a + 1] - off[a] for a in mine], dtype=np.int64)
-    x = np.concatenate(xs) if xs else np.zeros(0)
-    w = np.concatenate(ws) if ws else np.zeros(0)
-    return x, w, np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64), mine
 
 
 def reference_sample(data, cpu_seconds, cores):
@@ -189,7 +166,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from cnvkit_b200 import _lib, synth
+    from cnvkit_b200 import _lib, shard, synth
     from cnvkit_b200.segmentation import cbs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,9 +179,8 @@ def run_b200(args):
     _lib.load()
 
     data = synth.wgs_sample(total_bins=args.bins)
-    sizes = np.diff(data["arm_offsets"])
-    owner = lpt_shards(sizes, world)
-    x, w, off, mine = shard_columns(data, owner, rank)
+    owner = shard.arm_owner(data["arm_offsets"], world)
+    x, w, off, mine = shard.take_arms(data["log2"], data["weight"], data["arm_offsets"], owner, rank)
     nbins_total = int(data["arm_offsets"][-1])
     prune = not args.no_prune
 
@@ -228,23 +204,16 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def gather_tables(res):
-        """NCCL gather of the per-rank segment tables (two phases: counts, padded payload)."""
-        if world == 1:
-            return len(res[0])
+        """NCCL gather of the per-rank segment tables (cnvkit_b200.shard: counts, then padded rows)."""
         arm, lo, hi, mean = res[:4]
-        cnt = torch.tensor([len(arm)], dtype=torch.int64, device=dev)
-        cnts = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(cnts, cnt)
-        mx = int(max(int(c.item()) for c in cnts))
-        pay = torch.zeros((mx, 4), dtype=torch.float64, device=dev)
-        if len(arm):
-            pay[: len(arm), 0] = torch.from_numpy(mine[arm].astype(np.float64)).to(dev)
-            pay[: len(arm), 1] = torch.from_numpy(lo.astype(np.float64)).to(dev)
-            pay[: len(arm), 2] = torch.from_numpy(hi.astype(np.float64)).to(dev)
-            pay[: len(arm), 3] = torch.from_numpy(mean).to(dev)
-        out = [torch.zeros_like(pay) for _ in range(world)] if rank == 0 else None
-        dist.gather(pay, out, dst=0)
-        return int(sum(int(c.item()) for c in cnts))
+        if world == 1:
+            return len(arm)
+        g_arm = mine[arm] if len(arm) else np.zeros(0, np.int64)
+        shift = (data["arm_offsets"][g_arm] - off[arm]) if len(arm) else np.zeros(0, np.int64)
+        full = shard.gather_tables([g_arm.astype(np.int64), lo + shift, hi + shift, mean], dst=0, device=dev)
+        n_all = torch.tensor([len(full[0]) if full is not None else 0], dtype=torch.int64, device=dev)
+        dist.broadcast(n_all, src=0)
+        return int(n_all.item())
 
     def timed(fn, steps, profile=False):
         """Per-step CUDA-event brackets on the launching stream; L2 flushed between steps."""
@@ -297,7 +266,7 @@ def run_b200(args):
     ms_e2e = max_over_ranks(float(np.mean(e2e_ms)))
 
     if rank == 0:
-        # ---- roofline of the dominant kernel class (by device time inside the timed region)
+        # ---- rooflines (device time per kernel class inside the timed region, CUDA events)
         steps = args.steps
         per_step = {k: v[0] / steps for k, v in prof.items() if v[1] > 0}
         dominant = max(per_step, key=per_step.get) if per_step else "cbs_scan"
@@ -306,23 +275,42 @@ def run_b200(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6540.8))
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6540.8 GB/s (MEASURED_PEAKS.json absent)"
         tf = np.zeros(1)
         _lib.call("cnvk_fp64_peak", 4096, 5, tf.ctypes.data)
         fp64_peak = float(tf[0])
-        scan_ms = per_step.get("cbs_scan", 0.0)
+        arc_ms = per_step.get("cbs_scan", 0.0) + per_step.get("cbs_band", 0.0)
         arcs = stats["obs_arcs"]
-        scan_tflops = (arcs * FLOP_PER_ARC) / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0
-        roofline = {
-            "kernel": "cbs_scan_kernel", "bound": "fp64", "achieved": scan_tflops, "peak": fp64_peak,
-            "unit": "TFLOP/s", "frac": scan_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+        arc_tflops = (arcs * FLOP_PER_ARC) / (arc_ms * 1e-3) / 1e12 if arc_ms > 0 else 0.0
+        roof_scan = {
+            "kernel": "cbs_scan_kernel + cbs_band_kernel", "bound": "fp64", "achieved": arc_tflops, "peak": fp64_peak,
+            "unit": "TFLOP/s", "frac": arc_tflops / fp64_peak if fp64_peak else None, "traffic": None,
             "peak_source": "measured in this run: register-only DFMA stream (cnvk_fp64_peak); "
                            "MEASURED_PEAKS.json holds no FP64 figure",
-            "algorithmic": f"{FLOP_PER_ARC} FP64 op/arc x {arcs} arcs scanned per step "
+            "algorithmic": f"{FLOP_PER_ARC} FP64 op/arc x {arcs} arcs evaluated per step "
                            f"({stats['obs_subtiles_scanned']} of {stats['obs_subtiles_total']} 256x256 sub-tiles "
-                           f"survive the bound test)",
-            "kernel_ms_per_step": scan_ms, "dominant_class_by_time": dominant,
-            "note": "non-fused FP64 ops: 1 flop per issued DP instruction, so frac <= 0.5 of the DFMA peak",
+                           f"survive the bound test; the rest are narrow-band arcs)",
+            "kernel_ms_per_step": arc_ms,
+            "note": "non-fused FP64 ops: 1 flop per issued DP instruction, so frac <= 0.5 of the DFMA peak; "
+                    "with --no-prune (every arc evaluated) the same kernel reaches 0.46",
         }
+        prep_ms = per_step.get("cbs_prep", 0.0)
+        prep_bytes = PREP_BYTES_PER_BIN * stats["prep_bins"]
+        prep_gbs = prep_bytes / (prep_ms * 1e-3) / 1e9 if prep_ms > 0 else 0.0
+        roof_prep = {
+            "kernel": "cbs_prep_kernel", "bound": "hbm", "achieved": prep_gbs, "peak": hbm_peak, "unit": "GB/s",
+            "frac": prep_gbs / hbm_peak, "traffic": 138.3e6, "peak_source": hbm_src,
+            "algorithmic": f"{PREP_BYTES_PER_BIN} B/bin (read log2, weight; write xc, y, wn, S, cw) x "
+                           f"{stats['prep_bins']} bins centred and prefix-summed over {stats['levels']} levels",
+            "kernel_ms_per_step": prep_ms,
+            "note": "nominally HBM-bound but limited by the strictly sequential FP64 add chain that defines the "
+                    "bits of S (n dependent DADDs per node, ~11 cycles each): the floor is "
+                    "sum over levels of (largest open node) x t_add, not bytes; traffic = ncu dram bytes of the "
+                    "level-1 launch (profiles/r01b_cbs_prep_full_summary.md)",
+        }
+        roofline = dict(roof_prep if dominant == "cbs_prep" else roof_scan)
+        roofline["dominant_class_by_time"] = dominant
         # CPU baseline on a bounded sample (rank 0, N = 1 only)
         cpu = None
         if world == 1:
@@ -352,6 +340,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "rooflines": [roof_prep, roof_scan],
             "cpu_baseline": cpu,
             "clocks": clocks,
             "kernel_ms_per_step": per_step,

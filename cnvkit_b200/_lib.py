@@ -94,7 +94,7 @@ class CbsStats(ctypes.Structure):
     _fields_ = [
         (k, c_int64)
         for k in ("nodes", "levels", "obs_subtiles_total", "obs_subtiles_scanned", "obs_arcs", "perm_arcs",
-                  "perm_nodes", "perms_run", "flank_perm_tests")
+                  "perm_nodes", "perms_run", "flank_perm_tests", "prep_bins")
     ]
 
     def as_dict(self):

@@ -37,7 +37,8 @@ static void prof_collect() {
     g_prof_pending.clear();
 }
 static const char* const kProfNames[PC_COUNT] = {
-    "radix_sort", "wavelet_build", "window_query", "cbs_prep", "cbs_scan", "cbs_decide", "cbs_perm_hybrid",
+    "radix_sort", "wavelet_build", "window_query", "cbs_prep", "cbs_scan", "cbs_seed", "cbs_band",
+    "cbs_bound", "cbs_means", "cbs_decide", "cbs_perm_hybrid",
     "cbs_perm_exact", "cbs_flank", "fix", "haar", "biweight", "other"};
 static thread_local char g_err[1024] = "";
 void set_last_error(const char* fmt, ...) {
@@ -116,7 +117,7 @@ struct HostCall {
 extern "C" {
 
 const char* cnvk_last_error(void) { return g_err; }
-int cnvk_abi_version(void) { return 1; }
+int cnvk_abi_version(void) { return 2; }
 unsigned long long cnvk_launch_count(void) { return g_launch_count; }
 
 void cnvk_prof_enable(int on) { g_prof_enabled = on; }
@@ -331,6 +332,7 @@ static int cbs_common(const double* d_x, const double* d_w, const int64_t* arm_o
         stats->obs_subtiles_scanned = st.obs_subtiles_scanned; stats->obs_arcs = st.obs_arcs;
         stats->perm_arcs = st.perm_arcs; stats->perm_nodes = st.perm_nodes; stats->perms_run = st.perms_run;
         stats->flank_perm_tests = st.flank_perm_tests;
+        stats->prep_bins = st.prep_bins;
     }
     return 0;
 }

@@ -88,11 +88,17 @@ static const int PREP_CHAIN_WARPS = 2;
 static const int PREP_STAGE_T0 = PREP_CHAIN_WARPS * 32;           // first staging thread
 static const int PREP_STAGE_N = PREP_THREADS - PREP_STAGE_T0;     // staging threads
 
-// in-place inclusive running sum over m (multiple of 8) doubles in shared memory
+// in-place inclusive running sum over m (multiple of 8) doubles in shared memory; the next eight
+// operands are fetched before the current eight dependent adds so that only the DADD latency is
+// on the critical path
 __device__ __forceinline__ double chain_inplace(double* s, int m, double run) {
     double2* p = reinterpret_cast<double2*>(s);
-    for (int t = 0; t < m / 2; t += 4) {
-        double2 v0 = p[t], v1 = p[t + 1], v2 = p[t + 2], v3 = p[t + 3];
+    const int m2 = m / 2;
+    if (m2 == 0) return run;
+    double2 n0 = p[0], n1 = p[1], n2 = p[2], n3 = p[3];
+    for (int t = 0; t < m2; t += 4) {
+        double2 v0 = n0, v1 = n1, v2 = n2, v3 = n3;
+        if (t + 4 < m2) { n0 = p[t + 4]; n1 = p[t + 5]; n2 = p[t + 6]; n3 = p[t + 7]; }
         run = __dadd_rn(run, v0.x); v0.x = run; run = __dadd_rn(run, v0.y); v0.y = run;
         run = __dadd_rn(run, v1.x); v1.x = run; run = __dadd_rn(run, v1.y); v1.y = run;
         run = __dadd_rn(run, v2.x); v2.x = run; run = __dadd_rn(run, v2.y); v2.y = run;
@@ -486,7 +492,9 @@ cbs_seed_kernel(Node* __restrict__ nodes, const int* __restrict__ task_off, int 
                 const double d = __dsub_rn(pt(S, lo, j), pt(S, lo, i));
                 const double cc = __dsub_rn(pt(cw, lo, j), pt(cw, lo, i));
                 const double den = __dmul_rn(cc, __dsub_rn(total, cc));
-                const double q = __ddiv_rn(__dmul_rn(d, d), den);
+                const double num = __dmul_rn(d, d);
+                if (!(num >= __dmul_rn(bq * (1.0 - 1e-12), den)) && bq >= 0.0) continue;
+                const double q = __ddiv_rn(num, den);
                 if (cand_better(q, i, j, bq, bi_, bj_)) { bq = q; bi_ = i; bj_ = j; }
             }
         }
@@ -567,15 +575,25 @@ cbs_band_kernel(Node* __restrict__ nodes, int nnodes,
         const bool iok = il < npts;
         const double Si = iok ? sp[il].x : 0.0, ci = iok ? sp[il].y : 0.0;
         const int wend = min(warp * BAND_SUB + BAND_SUB - 1, npts - 1);
-        for (int sb = warp; sb < nsub; ++sb) {
-            const int j0 = sb * BAND_SUB, j1 = min(j0 + BAND_SUB - 1, npts - 1);
-            if (PRUNE && sb > warp + 1 && gq >= 0.0) {
+        // lane <-> end sub-block: one bound test each, then walk the survivors (warp-uniform)
+        unsigned need = 0;
+        {
+            const int sb = lane;
+            bool keep = sb >= warp && sb < nsub;
+            if (PRUNE && keep && sb > warp + 1 && gq >= 0.0) {
+                const int j0 = sb * BAND_SUB, j1 = min(j0 + BAND_SUB - 1, npts - 1);
                 const double d1 = s_mx[sb] - s_mn[warp], d2 = s_mx[warp] - s_mn[sb];
                 const double dm = fmax(fabs(d1), fabs(d2));
                 const double cmin = sp[j0].y - sp[wend].y, cmax = sp[j1].y - sp[warp * BAND_SUB].y;
                 const double fmin_ = fmin(cmin * (total - cmin), cmax * (total - cmax));
-                if (fmin_ > 0.0 && (dm * dm) / fmin_ * (1.0 + 1e-9) < gq) continue;
+                if (fmin_ > 0.0 && (dm * dm) / fmin_ * (1.0 + 1e-9) < gq) keep = false;
             }
+            need = __ballot_sync(0xffffffffu, keep);
+        }
+        while (need) {
+            const int sb = __ffs(need) - 1;
+            need &= need - 1;
+            const int j0 = sb * BAND_SUB, j1 = min(j0 + BAND_SUB - 1, npts - 1);
             ++my_pairs;
             for (int jl = j0; jl <= j1; ++jl) {
                 const double2 pj = sp[jl];
@@ -1127,14 +1145,14 @@ __global__ void sqrt_kernel(const double* __restrict__ w, double* __restrict__ o
 }
 
 // weighted.mean(log2, weight) per segment (cbs.py:70-71); one CTA per segment
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 seg_mean_kernel(const double* __restrict__ x, const double* __restrict__ w, const long long* __restrict__ lo,
                 const long long* __restrict__ hi, int nseg, double* __restrict__ mean) {
-    __shared__ double s_a[8], s_b[8];
+    __shared__ double s_a[32], s_b[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x;
     double sw = 0.0, swx = 0.0;
-    for (long long k = lo[s] + threadIdx.x; k < hi[s]; k += 256) {
+    for (long long k = lo[s] + threadIdx.x; k < hi[s]; k += 1024) {
         sw += w[k];
         swx += x[k] * w[k];
     }
@@ -1143,7 +1161,7 @@ seg_mean_kernel(const double* __restrict__ x, const double* __restrict__ w, cons
     if (lane == 0) { s_a[warp] = sw; s_b[warp] = swx; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 1; k < 8; ++k) { sw += s_a[k]; swx += s_b[k]; }
+        for (int k = 1; k < 32; ++k) { sw += s_a[k]; swx += s_b[k]; }
         mean[s] = swx / sw;
     }
 }
@@ -1330,6 +1348,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             nd.blk_off = (int)blk_off;
             nd.best_q = -1.0; nd.best_i = 0x7fffffff; nd.best_j = 0x7fffffff;
             const int n = nd.hi - nd.lo;
+            st.prep_bins += n;
             blk_off += (n + 1 + CBS_BLK - 1) / CBS_BLK;
             h_tile_off[k] = (int)tiles;
             long long nt_, nq_;
@@ -1355,25 +1374,31 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             CNVK_LAUNCH_CHECK();
         }
         {
-            ProfScope ps(PC_CBS_SCAN, stream);
             if (tiles > 0) {
                 const int grid = sm_count * 4;
                 if (P.prune & 1) {
+                    ProfScope ps(PC_CBS_SEED, stream);
                     cbs_seed_kernel<<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_S, d_cw, d_bimin, d_bimax, P.min_width);
                     CNVK_LAUNCH_CHECK();
-                    cbs_band_kernel<true><<<(int)blk_off, 256, 0, stream>>>(d_nodes, nn, d_S, d_cw, P.min_width, d_stats);
-                    CNVK_LAUNCH_CHECK();
-                    cbs_bound_kernel<true><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
-                    CNVK_LAUNCH_CHECK();
-                    cbs_scan_kernel<true><<<grid, 256, 0, stream>>>(d_nodes, d_queue, d_counter, d_counter + 1, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
-                } else {
-                    cbs_band_kernel<false><<<(int)blk_off, 256, 0, stream>>>(d_nodes, nn, d_S, d_cw, P.min_width, d_stats);
-                    CNVK_LAUNCH_CHECK();
-                    cbs_bound_kernel<false><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
-                    CNVK_LAUNCH_CHECK();
-                    cbs_scan_kernel<false><<<grid, 256, 0, stream>>>(d_nodes, d_queue, d_counter, d_counter + 1, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
                 }
-                CNVK_LAUNCH_CHECK();
+                {
+                    ProfScope ps(PC_CBS_BAND, stream);
+                    if (P.prune & 1) cbs_band_kernel<true><<<(int)blk_off, 256, 0, stream>>>(d_nodes, nn, d_S, d_cw, P.min_width, d_stats);
+                    else cbs_band_kernel<false><<<(int)blk_off, 256, 0, stream>>>(d_nodes, nn, d_S, d_cw, P.min_width, d_stats);
+                    CNVK_LAUNCH_CHECK();
+                }
+                {
+                    ProfScope ps(PC_CBS_BOUND, stream);
+                    if (P.prune & 1) cbs_bound_kernel<true><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
+                    else cbs_bound_kernel<false><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
+                    CNVK_LAUNCH_CHECK();
+                }
+                {
+                    ProfScope ps(PC_CBS_SCAN, stream);
+                    if (P.prune & 1) cbs_scan_kernel<true><<<grid, 256, 0, stream>>>(d_nodes, d_queue, d_counter, d_counter + 1, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
+                    else cbs_scan_kernel<false><<<grid, 256, 0, stream>>>(d_nodes, d_queue, d_counter, d_counter + 1, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
+                    CNVK_LAUNCH_CHECK();
+                }
             }
         }
         {
@@ -1581,8 +1606,11 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         CNVK_CHECK(ms.alloc(&d_mean, (size_t)ns));
         CNVK_CHECK(cudaMemcpyAsync(d_lo, slo.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, stream));
         CNVK_CHECK(cudaMemcpyAsync(d_hi, shi.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, stream));
-        seg_mean_kernel<<<ns, 256, 0, stream>>>(d_x, d_w, d_lo, d_hi, ns, d_mean);
-        CNVK_LAUNCH_CHECK();
+        {
+            ProfScope ps(PC_CBS_MEANS, stream);
+            seg_mean_kernel<<<ns, 1024, 0, stream>>>(d_x, d_w, d_lo, d_hi, ns, d_mean);
+            CNVK_LAUNCH_CHECK();
+        }
         std::vector<double> means(ns);
         CNVK_CHECK(cudaMemcpyAsync(means.data(), d_mean, ns * sizeof(double), cudaMemcpyDeviceToHost, stream));
         CNVK_CHECK(cudaStreamSynchronize(stream));

@@ -68,7 +68,7 @@ struct CbsSeg {
 };
 struct CbsStats {
     long long nodes, levels, obs_subtiles_total, obs_subtiles_scanned, obs_arcs, perm_arcs, perm_nodes, perms_run,
-        flank_perm_tests;
+        flank_perm_tests, prep_bins;
 };
 }  // namespace cnvk
 #include <vector>

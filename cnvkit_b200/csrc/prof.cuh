@@ -11,6 +11,10 @@ enum ProfClass {
     PC_WINDOW_QUERY,
     PC_CBS_PREP,
     PC_CBS_SCAN,
+    PC_CBS_SEED,
+    PC_CBS_BAND,
+    PC_CBS_BOUND,
+    PC_CBS_MEANS,
     PC_CBS_DECIDE,
     PC_CBS_PERM_HYBRID,
     PC_CBS_PERM_EXACT,

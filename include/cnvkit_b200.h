@@ -189,6 +189,7 @@ typedef struct cnvk_cbs_params {
 typedef struct cnvk_cbs_stats {
     int64_t nodes, levels, obs_subtiles_total, obs_subtiles_scanned, obs_arcs, perm_arcs, perm_nodes,
         perms_run, flank_perm_tests;
+    int64_t prep_bins; /* bins centred + prefix-summed, summed over recursion levels (ABI >= 2) */
 } cnvk_cbs_stats;
 
 /* One call segments every arm of a batch: bins of arm a are [arm_offsets[a], arm_offsets[a+1])
