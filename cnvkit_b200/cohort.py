@@ -1,0 +1,380 @@
+"""Cohort fix + segment on one GPU -- the numeric core of cnvlib/batch.py:524-555 (batch_run_sample:
+do_fix followed by do_segmentation) for many samples that share one bin set and one pooled
+reference.
+
+Everything do_fix / do_segmentation derive from the *bins and the reference alone* -- reference
+rows matched to the sample's bins (fix.py:324-370), mask_bad_bins (fix.py:295-321), chromosome
+runs, autosome mask, edge-bias column, shuffle permutation, the target/antitarget merge order
+(fix.py:171-174), arm boundaries (gary.py:309-355), gene codes for transfer_fields -- is computed once
+per `Panel` and kept in HBM.  A sample then costs two host->device column copies, the device calls
+of csrc/fix.cu and csrc/segutil.cu, and one share of a CBS / Haar call that segments the arms of
+many samples together (the recursion is level-synchronous over the whole batch, so the small arms
+of an exome panel fill the GPU only when samples are batched).
+
+Results are identical to calling cnvkit_b200.fix.do_fix and
+cnvkit_b200.segmentation.do_segmentation sample by sample (tests/test_cohort_gpu.py).  Samples the
+shared plan does not cover (NaN log2 in a coverage table, non-finite ratios) take that general path.
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _dev, _lib, fix, genome, params, segmentation, smoothing
+from .cnary import arm_ranges
+from .segmentation import cbs as _cbs
+from .segmentation import haar as _haar
+
+
+class _Group:
+    """One bin set (targets or antitargets) of load_adjust_coverages after reference masking."""
+
+    def __init__(self, table, ref_matched, skip_low, do_gc, do_edge, do_rmask, diploid_parx_genome):
+        self.n0 = len(table)
+        self.skip_low = skip_low
+        self.do_edge = do_edge
+        rd = ref_matched.data
+        self.table = table
+        self.ref_matched = ref_matched
+        if self.n0 == 0:
+            self.n = 0
+            self.keep = np.zeros(0, dtype=bool)
+            return
+        cols = {c: _dev.up(rd[c].to_numpy(dtype=np.float64)) for c in ("log2", "spread", "depth", "gc", "rmask")
+                if c in rd.columns}
+        d_keep = _dev.empty(self.n0, torch.uint8)
+        # sample-independent part of the mask (the sample-NaN test is checked per sample)
+        _lib.call("cnvk_fix_mask_dev", 0, _dev.ptr(cols["log2"]), _dev.ptr(cols["spread"]), _dev.ptr(cols.get("depth")),
+                  _dev.ptr(cols.get("gc")), self.n0, _dev.ptr(d_keep), _dev.stream())
+        self.keep = d_keep.cpu().numpy().astype(bool)
+        self.d_keep_idx = torch.from_numpy(np.flatnonzero(self.keep)).to(_dev.device())
+        kept = table.data[self.keep]
+        self.kept_table = kept.reset_index(drop=True)
+        self.kept_ref = rd[self.keep].reset_index(drop=True)
+        self.n = n = len(kept)
+        if n == 0:
+            return
+        chrom = kept["chromosome"].to_numpy()
+        names, offsets, chrom_id = genome.chrom_runs(chrom)
+        start = kept["start"].to_numpy(dtype=np.int64)
+        end = kept["end"].to_numpy(dtype=np.int64)
+        auto = genome.autosome_row_mask(chrom, start, end, diploid_parx_genome)
+        self.nchrom = len(names)
+        self.d_off, self.d_cid = _dev.up(offsets), _dev.up(chrom_id)
+        self.d_start, self.d_end = _dev.up(start), _dev.up(end)
+        self.d_auto = _dev.up(auto.astype(np.uint8))
+        self.d_gc = cols["gc"].index_select(0, self.d_keep_idx).contiguous() if (do_gc and "gc" in cols) else None
+        self.d_rmask = (cols["rmask"].index_select(0, self.d_keep_idx).contiguous()
+                        if (do_rmask and "rmask" in cols) else None)
+        self.wing = smoothing._width2wing(max(0.01, n ** -0.5), n) if n >= 2 else 1
+        self.d_perm = _dev.shuffle_permutation(n)
+        self.d_edge = None
+        if do_edge:
+            self.d_edge = _dev.empty(n, torch.float64)
+            _lib.call("cnvk_edge_bias_dev", _dev.ptr(self.d_start), _dev.ptr(self.d_end), _dev.ptr(self.d_cid), n,
+                      params.INSERT_SIZE, _dev.ptr(self.d_edge), _dev.stream())
+
+    def adjust(self, log2, depth):
+        """Bias-corrected log2 of the kept rows (device tensor), or None if the sample needs the
+        general path (NaN log2 would change the kept set, fix.py:244)."""
+        if self.n0 == 0 or self.n == 0:
+            return _dev.empty(0, torch.float64)
+        if torch.is_tensor(log2):                 # columns already resident in HBM
+            if bool(torch.isnan(log2).any()):
+                return None
+            d_all, d_dall = log2, depth
+        else:
+            x = np.ascontiguousarray(log2, dtype=np.float64)
+            if np.isnan(x).any():
+                return None
+            d_all, d_dall = _dev.up(x), _dev.up(np.ascontiguousarray(depth, dtype=np.float64))
+        d_log2 = d_all.index_select(0, self.d_keep_idx).contiguous()
+        d_depth = d_dall.index_select(0, self.d_keep_idx).contiguous()
+        skipped = ctypes.c_int32(0)
+        _lib.call("cnvk_fix_group_dev", _dev.ptr(d_log2), _dev.ptr(d_depth), _dev.ptr(self.d_auto), self.n,
+                  _dev.ptr(self.d_off), self.nchrom, _dev.ptr(self.d_cid), _dev.ptr(self.d_start), _dev.ptr(self.d_end),
+                  _dev.ptr(self.d_gc), _dev.ptr(self.d_rmask), _dev.ptr(self.d_edge), int(bool(self.do_edge)),
+                  int(bool(self.skip_low)), 1, self.wing, _dev.ptr(self.d_perm), params.INSERT_SIZE, b"ger",
+                  ctypes.addressof(skipped), _dev.stream())
+        if skipped.value:
+            logging.warning("WARNING: most bins have no or very low coverage; check that the right BED file was used")
+        self._depth_kept = d_depth
+        return d_log2
+
+
+class Panel:
+    """Sample-independent plan for fix + segment over a shared bin set.
+
+    Parameters mirror do_fix (cnvlib/fix.py:20-31): `target_bins` / `antitarget_bins` are any
+    coverage tables of the panel (only their coordinates and gene names are used), `reference` the
+    pooled reference.
+    """
+
+    def __init__(self, target_bins, antitarget_bins, reference, diploid_parx_genome=None, do_gc=True, do_edge=True,
+                 do_rmask=True):
+        self.diploid_parx_genome = diploid_parx_genome
+        self.opts = (do_gc, do_edge, do_rmask)
+        self.meta_cls = target_bins.__class__
+        keepc = ("chromosome", "start", "end", "gene", "log2", "depth")
+        tb = target_bins.keep_columns(keepc) if "gc" in target_bins else target_bins
+        ab = antitarget_bins.keep_columns(keepc) if "gc" in antitarget_bins else antitarget_bins
+        self._proto_t, self._proto_a = tb, ab
+        self.t = _Group(tb, fix.match_ref_to_sample(reference, tb) if len(tb) else reference[:0], True, do_gc, do_edge,
+                        False, diploid_parx_genome)
+        self.a = _Group(ab, fix.match_ref_to_sample(reference, ab) if len(ab) else reference[:0], False, do_gc, False,
+                        do_rmask, diploid_parx_genome)
+        # fix.py:171-174: concat + genomic sort of the two kept tables (and of the matched reference rows)
+        parts = [g.kept_table for g in (self.t, self.a) if g.n0 and g.n]
+        rparts = [g.kept_ref for g in (self.t, self.a) if g.n0 and g.n]
+        cdf = pd.concat(parts, ignore_index=True)
+        rdf = pd.concat(rparts, ignore_index=True)
+        if self.a.n0 and self.a.n:
+            order = genome.genomic_order(cdf["chromosome"].to_numpy(), cdf["start"].to_numpy(), cdf["end"].to_numpy())
+        else:
+            order = np.arange(len(cdf))
+        self.order = order
+        self.d_order = torch.from_numpy(order.astype(np.int64)).to(_dev.device())
+        self.bins = cdf.iloc[order].reset_index(drop=True)            # chromosome,start,end,gene (+ log2/depth unused)
+        rdf = rdf.iloc[order].reset_index(drop=True)
+        self.n = n = len(self.bins)
+        chrom = self.bins["chromosome"].to_numpy()
+        self.chrom = chrom
+        names, offsets, chrom_id = genome.chrom_runs(chrom)
+        self.start = self.bins["start"].to_numpy(dtype=np.int64)
+        self.end = self.bins["end"].to_numpy(dtype=np.int64)
+        auto = genome.autosome_row_mask(chrom, self.start, self.end, diploid_parx_genome)
+        self.is_anti = self.bins["gene"].isin(params.ANTITARGET_ALIASES).to_numpy()
+        self.nchrom = len(names)
+        self.d_rl = _dev.up(rdf["log2"].to_numpy(dtype=np.float64))
+        self.d_rs = _dev.up(rdf["spread"].to_numpy(dtype=np.float64))
+        self.d_start, self.d_end, self.d_cid = _dev.up(self.start), _dev.up(self.end), _dev.up(chrom_id)
+        self.d_anti, self.d_auto, self.d_off = (_dev.up(self.is_anti.astype(np.uint8)), _dev.up(auto.astype(np.uint8)),
+                                                _dev.up(offsets))
+        # segmentation: arms of the .cnr table, gene codes for transfer_fields
+        self.arms = arm_ranges(self.bins)
+        self.arm_off = np.array([a[1] for a in self.arms] + [self.arms[-1][2]], dtype=np.int64)
+        self.arm_id = np.repeat(np.arange(len(self.arms)), np.diff(self.arm_off))
+        self.d_arm_id = torch.from_numpy(self.arm_id).to(_dev.device())
+        self.gene_codes = segmentation.factorize_genes(self.bins["gene"].to_numpy())
+
+    # ------------------------------------------------------------------ fix
+    def fix(self, target, antitarget):
+        """do_fix for one sample given its two coverage tables (CopyNumArray or dict with
+        'log2'/'depth' columns in the panel's bin order).  Returns (d_log2, d_weight, d_depth) device
+        columns over the panel's .cnr rows, or None when the sample needs the general path."""
+        tl, td = _cols(target)
+        al, ad = _cols(antitarget)
+        if len(tl) != self.t.n0 or len(al) != self.a.n0:
+            raise ValueError("sample tables do not match the panel's bin set")
+        xt = self.t.adjust(tl, td)
+        xa = self.a.adjust(al, ad)
+        if xt is None or xa is None:
+            return None
+        parts = [p for p in (xt, xa) if len(p)]
+        dparts = [g._depth_kept for g in (self.t, self.a) if g.n0 and g.n]
+        d_log2 = torch.cat(parts).index_select(0, self.d_order).contiguous()
+        d_depth = torch.cat(dparts).index_select(0, self.d_order).contiguous()
+        d_w = _dev.empty(self.n, torch.float64)
+        _lib.call("cnvk_fix_finish_dev", _dev.ptr(d_log2), _dev.ptr(d_depth), _dev.ptr(self.d_rl), _dev.ptr(self.d_rs),
+                  _dev.ptr(self.d_start), _dev.ptr(self.d_end), _dev.ptr(self.d_cid), _dev.ptr(self.d_anti),
+                  _dev.ptr(self.d_auto), self.n, _dev.ptr(self.d_off), self.nchrom, _dev.ptr(d_w), 0, _dev.stream())
+        return d_log2, d_w, d_depth
+
+    def cnr_table(self, d_log2, d_w, d_depth, sample_id=None):
+        """The .cnr CopyNumArray do_fix returns (host copy of the three device columns)."""
+        df = self.bins[["chromosome", "start", "end", "gene"]].assign(
+            log2=d_log2.cpu().numpy(), depth=d_depth.cpu().numpy(), weight=d_w.cpu().numpy())
+        return self.meta_cls(df, {"sample_id": sample_id})
+
+    # ------------------------------------------------------------------ segment
+    def segment(self, samples, method="cbs", threshold=None, skip_outliers=10, sample_ids=None):
+        """do_segmentation(method) for a list of (d_log2, d_weight, d_depth) device triples over the
+        panel's .cnr rows; all samples are segmented in one batched device call.  Returns one .cns
+        CopyNumArray per sample."""
+        if method not in ("cbs", "haar"):
+            raise ValueError("cohort segmentation implements 'cbs' and 'haar'")
+        if threshold is None:
+            threshold = 0.0001
+        n_arms = len(self.arms)
+        per = []
+        xs, ws, offs = [], [], [0]
+        unit_arm_all = []
+        for d_log2, d_w, d_depth in samples:
+            if not bool(torch.isfinite(d_log2).all()):
+                per.append(None)
+                continue
+            keep = torch.ones(self.n, dtype=torch.bool, device=d_log2.device)
+            if skip_outliers:
+                d_mask = _dev.empty(self.n, torch.uint8)
+                _lib.call("cnvk_outlier_mask_dev", _dev.ptr(d_log2), _lib.ptr(self.arm_off), n_arms, 0.95,
+                          float(skip_outliers), _dev.ptr(d_mask), _dev.stream())
+                keep &= d_mask == 0
+            keep &= d_w != 0                      # NaN weights compare True and survive, as in the reference
+            d_fidx = torch.nonzero(keep).flatten()
+            fidx = d_fidx.cpu().numpy()
+            f_arm = self.arm_id[fidx]
+            x = d_log2.index_select(0, d_fidx)
+            w = d_w.index_select(0, d_fidx)
+            if method == "cbs":
+                x, w, sub = self._quantise(x, w)
+                if sub is not None:
+                    fidx, f_arm = fidx[sub], f_arm[sub]
+                units = segmentation._arm_offsets(f_arm, n_arms)
+                unit_arm = np.arange(n_arms)
+            else:
+                units, unit_arm = self._haar_units(fidx, f_arm, n_arms)
+            per.append(dict(fidx=fidx, units=units, unit_arm=unit_arm, base=offs[-1], unit0=len(unit_arm_all)))
+            unit_arm_all.extend(unit_arm.tolist())
+            xs.append(x)
+            ws.append(w)
+            offs.extend((units[1:] + offs[-1]).tolist() if len(units) > 1 else [])
+        results = [None] * len(samples)
+        if xs:
+            X = torch.cat(xs).contiguous()
+            W = torch.cat(ws).contiguous()
+            off = np.asarray(offs, dtype=np.int64)
+            if method == "cbs":
+                u, lo, hi, mean, _st = _cbs.segment_arms(None, None, off, alpha=float(threshold),
+                                                         device_ptrs=(X.data_ptr(), W.data_ptr()), stream=_dev.stream())
+                mean = np.array([float("%.15g" % m) for m in mean]) if len(mean) else mean
+            else:
+                u, lo, hi, mean = _haar.segment_arms(None, None, off, float(threshold),
+                                                     device_ptrs=(X.data_ptr(), W.data_ptr()), stream=_dev.stream())
+            for k, info in enumerate(per):
+                if info is None:
+                    continue
+                nu = len(info["unit_arm"])
+                sel = (u >= info["unit0"]) & (u < info["unit0"] + nu)
+                s_unit = u[sel] - info["unit0"]
+                s_lo, s_hi = lo[sel] - info["base"], hi[sel] - info["base"]
+                results[k] = self._segments_table(samples[k], info, s_unit, s_lo, s_hi, mean[sel],
+                                                  None if sample_ids is None else sample_ids[k])
+        for k, info in enumerate(per):
+            if info is None:  # non-finite ratios: the general path handles the per-arm drops
+                cnr = self.cnr_table(*samples[k], sample_id=None if sample_ids is None else sample_ids[k])
+                results[k] = segmentation.do_segmentation(cnr, method, self.diploid_parx_genome, threshold=threshold,
+                                                          skip_outliers=skip_outliers)
+        return results
+
+    def _quantise(self, x, w):
+        """%.6g of both columns (segmentation/__init__.py:299-301) and the R row filters (cbs.py:22-35)."""
+        n = len(x)
+        xq, wq = _dev.empty(n, torch.float64), _dev.empty(n, torch.float64)
+        unhandled = np.zeros(1, dtype=np.uint64)
+        cols = [(x.contiguous(), xq)]
+        if bool(torch.isfinite(w).any()):
+            cols.append((w.contiguous(), wq))
+        else:
+            wq.fill_(1.0)                         # cbs.py:25-28: no usable weights -> weight 1 per bin
+        for src, dst in cols:
+            _lib.call("cnvk_round_sig_dev", _dev.ptr(src), n, 6, _dev.ptr(dst), _lib.ptr(unhandled), _dev.stream())
+            if unhandled[0]:
+                h = src.cpu().numpy()
+                bad = (np.abs(h) < 1e-16) | (np.abs(h) > 1e21)
+                fixed = dst.cpu().numpy()
+                fixed[bad] = [float("%.6g" % v) for v in h[bad]]
+                dst.copy_(torch.from_numpy(fixed))
+        ok = ~torch.isnan(wq) & (wq > 0) & ~torch.isnan(xq)
+        if bool(ok.all()):
+            return xq, wq, None
+        d_sub = torch.nonzero(ok).flatten()
+        return xq.index_select(0, d_sub), wq.index_select(0, d_sub), d_sub.cpu().numpy()
+
+    def _haar_units(self, fidx, f_arm, n_arms):
+        """segment_haar re-splits every filtered arm with by_arm() again (haar.py:80-82)."""
+        off = segmentation._arm_offsets(f_arm, n_arms)
+        units, unit_arm = [0], []
+        if len(fidx) == self.n:        # nothing filtered: the re-split is a property of the panel
+            if not hasattr(self, "_haar_full"):
+                self._haar_full = self._haar_units_general(fidx, off, n_arms)
+            return self._haar_full
+        return self._haar_units_general(fidx, off, n_arms)
+
+    def _haar_units_general(self, fidx, off, n_arms):
+        units, unit_arm = [0], []
+        for a in range(n_arms):
+            lo, hi = int(off[a]), int(off[a + 1])
+            if hi <= lo:
+                continue
+            rows = fidx[lo:hi]
+            sub = pd.DataFrame({"chromosome": self.chrom[rows], "start": self.start[rows], "end": self.end[rows]})
+            for _c, _slo, shi in arm_ranges(sub):
+                units.append(lo + shi)
+                unit_arm.append(a)
+        return np.asarray(units, dtype=np.int64), np.asarray(unit_arm, dtype=np.int64)
+
+    def _segments_table(self, sample, info, s_unit, s_lo, s_hi, s_mean, sample_id):
+        d_log2, d_w, d_depth = sample
+        src = info["fidx"]
+        seg_arm = info["unit_arm"][s_unit]
+        seg_chrom = self.chrom[src[s_lo]]
+        seg_start = self.start[src[s_lo]].copy()
+        seg_end = self.end[src[s_hi - 1]].copy()
+        probes = (s_hi - s_lo).astype(np.int64)
+        segtab = segmentation._transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, s_mean, probes, self.arms,
+                                               self.bins, None, d_w, d_depth, self.start, self.end,
+                                               gene_codes=self.gene_codes)
+        out = self.meta_cls(segtab, {"sample_id": sample_id})
+        out.sort()
+        out.sort_columns()
+        return out
+
+    # ------------------------------------------------------------------ driver
+    def run(self, samples, method="cbs", threshold=None, batch=16, sample_ids=None, keep_cnr=False):
+        """fix + segment for an iterable of (target, antitarget) coverage tables.  Returns a list of
+        (.cnr or None, .cns) per sample; `batch` samples share one segmentation call."""
+        out = []
+        pend, pend_ids = [], []
+
+        def flush():
+            if not pend:
+                return
+            cns = self.segment(pend, method, threshold, sample_ids=pend_ids)
+            for trip, sid, seg in zip(pend, pend_ids, cns):
+                out.append((self.cnr_table(*trip, sample_id=sid) if keep_cnr else None, seg))
+            pend.clear()
+            pend_ids.clear()
+
+        for k, (tgt, anti) in enumerate(samples):
+            sid = sample_ids[k] if sample_ids is not None else getattr(tgt, "sample_id", None)
+            trip = self.fix(tgt, anti)
+            if trip is None:  # general path for this sample
+                flush()
+                t_tab, a_tab = self._as_tables(tgt, anti, sid)
+                cnr = fix.do_fix(t_tab, a_tab, self._reference_table(), self.diploid_parx_genome, *self.opts)
+                out.append((cnr if keep_cnr else None,
+                            segmentation.do_segmentation(cnr, method, self.diploid_parx_genome, threshold=threshold)))
+                continue
+            pend.append(trip)
+            pend_ids.append(sid)
+            if len(pend) >= batch:
+                flush()
+        flush()
+        return out
+
+    def _as_tables(self, tgt, anti, sid):
+        def one(proto, s):
+            if hasattr(s, "data"):
+                return s
+            return proto.as_dataframe(proto.data.assign(log2=np.asarray(s["log2"], dtype=float),
+                                                        depth=np.asarray(s["depth"], dtype=float)))
+        return one(self._proto_t, tgt), one(self._proto_a, anti)
+
+    def _reference_table(self):
+        rt = pd.concat([g.ref_matched.data for g in (self.t, self.a) if g.n0], ignore_index=True)
+        ref = self.t.ref_matched.as_dataframe(rt)
+        ref.sort()
+        return ref
+
+
+def _cols(s):
+    if hasattr(s, "data"):
+        d = s.data
+        return d["log2"].to_numpy(dtype=np.float64), d["depth"].to_numpy(dtype=np.float64)
+    if torch.is_tensor(s["log2"]):
+        return s["log2"], s["depth"]
+    return np.asarray(s["log2"], dtype=np.float64), np.asarray(s["depth"], dtype=np.float64)

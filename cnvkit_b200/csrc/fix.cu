@@ -306,12 +306,15 @@ __global__ void residual_kernel(const double* __restrict__ log2, const u8* __res
     resid[i] = use[i] ? __dsub_rn(log2[i], med[chrom_id[i]]) : __longlong_as_double(0x7ff8000000000000ll);
 }
 
-// sum of sqrt(end-start) and count over a group; also counts used (non-low) bins
-__global__ void __launch_bounds__(256)
+// sum of sqrt(end-start) and count over a group; also counts used (non-low) bins.  One CTA with a
+// fixed accumulation order (strided per thread, shuffle tree, warps in order): run-to-run
+// deterministic, unlike floating-point atomics.
+__global__ void __launch_bounds__(1024)
 group_size_kernel(const long long* __restrict__ start, const long long* __restrict__ end, const u8* __restrict__ sel,
                   const u8* __restrict__ use, long long n, double* __restrict__ acc /*[3]: sum sqrt, count, used*/) {
+    __shared__ double s_s[32], s_c[32], s_u[32];
     double s = 0.0, c = 0.0, u = 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    for (long long i = threadIdx.x; i < n; i += 1024) {
         if (sel[i]) {
             s += sqrt((double)(end[i] - start[i]));
             c += 1.0;
@@ -319,7 +322,12 @@ group_size_kernel(const long long* __restrict__ start, const long long* __restri
         }
     }
     s = warp_sum(s); c = warp_sum(c); u = warp_sum(u);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], s); atomicAdd(&acc[1], c); atomicAdd(&acc[2], u); }
+    if ((threadIdx.x & 31) == 0) { s_s[threadIdx.x >> 5] = s; s_c[threadIdx.x >> 5] = c; s_u[threadIdx.x >> 5] = u; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 32; ++k) { s += s_s[k]; c += s_c[k]; u += s_u[k]; }
+        acc[0] = s; acc[1] = c; acc[2] = u;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -406,7 +414,7 @@ int fix_finish(double* d_log2, const double* d_depth, const double* d_ref_log2, 
             CNVK_LAUNCH_CHECK();
             use_mask_kernel<<<g256, 256, 0, stream>>>(d_log2, d_depth, sel, n, 1, use);   // drop_low_coverage
             CNVK_LAUNCH_CHECK();
-            group_size_kernel<<<std::min(g256, 1184), 256, 0, stream>>>(d_start, d_end, sel, use, n, acc + 3 * g);
+            group_size_kernel<<<1, 1024, 0, stream>>>(d_start, d_end, sel, use, n, acc + 3 * g);
             CNVK_LAUNCH_CHECK();
         }
         int rc = segmented_median(d_log2, use, d_chrom_off, nchrom, med, cnt, stream);

@@ -200,7 +200,7 @@ def _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, f_chrom, n_arms, thre
 
 
 def _transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, seg_log2, probes, arms, data, log2, weight, depth,
-                     start, end):
+                     start, end, gene_codes=None):
     """transfer_fields(segarr, cnarr) per arm (:401-506), all arms at once.
 
     Each arm's first/last segment is stretched to the arm's first bin start / last bin end; then
@@ -231,40 +231,43 @@ def _transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, seg_log2, probes, a
             raise NotImplementedError("nested bins (non-monotonic end coordinates) are not supported")
     bin_hi = np.maximum(bin_hi, bin_lo)
     dep = depth if depth is not None else np.exp2(log2)
-    d_dep, d_lo, d_hi = _dev.up(dep), _dev.up(bin_lo), _dev.up(bin_hi)
-    d_w = _dev.up(weight) if weight is not None else None
+    d_dep = dep if torch.is_tensor(dep) else _dev.up(dep)
+    d_lo, d_hi = _dev.up(bin_lo), _dev.up(bin_hi)
+    d_w = weight if (weight is None or torch.is_tensor(weight)) else _dev.up(weight)
     d_sw, d_sd = _dev.empty(nseg, torch.float64), _dev.empty(nseg, torch.float64)
     _lib.call("cnvk_segment_bin_sums_dev", _dev.ptr(d_dep), _dev.ptr(d_w), _dev.ptr(d_lo), _dev.ptr(d_hi), nseg,
               _dev.ptr(d_sw), _dev.ptr(d_sd), _dev.stream())
     seg_weight, seg_depth = d_sw.cpu().numpy(), d_sd.cpu().numpy()
-    genes = _join_genes(data["gene"].to_numpy(), bin_lo, bin_hi)
+    genes = _join_genes(data["gene"].to_numpy(), bin_lo, bin_hi, gene_codes)
     return pd.DataFrame({
         "chromosome": seg_chrom, "start": seg_start, "end": seg_end, "gene": genes, "log2": seg_log2,
         "probes": probes, "weight": seg_weight, "depth": seg_depth,
     })
 
 
-def _join_genes(bin_genes, bin_lo, bin_hi):
-    """skgenome/combiners.py:58-94 join_strings per segment: ordered-unique gene names of the
-    bins, split on ',', minus the ignored placeholder / antitarget names; '-' if none remain."""
+def factorize_genes(bin_genes):
+    """(codes per bin, kept name parts per code) -- depends on the bin set only, so cohorts cache it.
+    A gene field may hold several comma-separated names; placeholder / antitarget names are dropped
+    here once (skgenome/combiners.py:58-94 with params.IGNORE_GENE_NAMES + ANTITARGET_ALIASES)."""
     ignore = set(params.IGNORE_GENE_NAMES + params.ANTITARGET_ALIASES)
     codes, uniques = pd.factorize(pd.Series(bin_genes, dtype=object), sort=False)
-    parts = []
-    for u in uniques:
-        parts.append([p for p in u.split(",")] if isinstance(u, str) else None)
+    parts = [tuple(p for p in u.split(",") if p not in ignore) if isinstance(u, str) else () for u in uniques]
+    return codes, parts
+
+
+def _join_genes(bin_genes, bin_lo, bin_hi, gene_codes=None):
+    """skgenome/combiners.py:58-94 join_strings per segment: ordered-unique gene names of the
+    bins, split on ',', minus the ignored placeholder / antitarget names; '-' if none remain."""
+    codes, parts = gene_codes if gene_codes is not None else factorize_genes(bin_genes)
     out = []
     for lo, hi in zip(bin_lo, bin_hi):
-        c = codes[lo:hi]
-        if len(c) == 0:
+        if hi <= lo:
             out.append("-")
             continue
-        _, first_idx = np.unique(c, return_index=True)
         seen = {}
-        for ci in c[np.sort(first_idx)]:
-            if ci < 0 or parts[ci] is None:
-                continue
-            for name in parts[ci]:
-                if name not in ignore:
+        for ci in pd.unique(codes[lo:hi]):       # hash-based, keeps first-appearance order
+            if ci >= 0:
+                for name in parts[ci]:
                     seen.setdefault(name, None)
         out.append(",".join(seen) or "-")
     return out

@@ -1,0 +1,109 @@
+"""GPU: the cohort plan (cnvkit_b200.cohort.Panel) gives exactly the tables of the per-sample public
+API (do_fix + do_segmentation), for CBS and Haar, including a sample that needs the general path."""
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def world():
+    from cnvkit_b200 import synth
+
+    bins = synth.exome_bins(n_targets=9000, n_antitargets=3000, seed=7)
+    ref = synth.exome_reference(bins, seed=8)
+    samples = [synth.exome_sample(bins, ref, seed=k, n_events=4) for k in range(4)]
+    tabs = [synth.exome_tables(bins, ref, s, sample_id=f"S{k}") for k, s in enumerate(samples)]
+    return bins, ref, tabs
+
+
+def assert_same(a, b):
+    pd.testing.assert_frame_equal(a.data.reset_index(drop=True), b.data.reset_index(drop=True), check_exact=True)
+
+
+@pytest.mark.parametrize("method", ["cbs", "haar"])
+def test_cohort_equals_per_sample_api(world, method):
+    from cnvkit_b200 import cohort, fix, segmentation
+
+    bins, ref, tabs = world
+    T0, A0, R = tabs[0]
+    panel = cohort.Panel(T0, A0, R)
+    got = panel.run([(T, A) for T, A, _ in tabs], method=method, batch=3, keep_cnr=True,
+                    sample_ids=[f"S{k}" for k in range(len(tabs))])
+    assert len(got) == len(tabs)
+    for (T, A, _), (cnr, cns) in zip(tabs, got):
+        want_cnr = fix.do_fix(T, A, R)
+        assert_same(cnr, want_cnr)
+        want_cns = segmentation.do_segmentation(want_cnr, method)
+        assert_same(cns, want_cns)
+        assert cns.meta.get("sample_id") == T.sample_id
+        assert len(cns) >= 2
+
+
+def test_cohort_columns_input_and_general_path(world):
+    from cnvkit_b200 import cohort, fix, segmentation
+
+    bins, ref, tabs = world
+    T0, A0, R = tabs[0]
+    panel = cohort.Panel(T0, A0, R)
+    T1, A1, _ = tabs[1]
+    # plain column dicts instead of tables
+    cols = ({"log2": T1.data["log2"].to_numpy(), "depth": T1.data["depth"].to_numpy()},
+            {"log2": A1.data["log2"].to_numpy(), "depth": A1.data["depth"].to_numpy()})
+    # a sample with NaN coverage in one target bin changes the kept set -> general path
+    T2, A2, _ = tabs[2]
+    t2 = T2.data.copy()
+    t2.loc[17, "log2"] = np.nan
+    T2n = T2.as_dataframe(t2)
+    got = panel.run([cols, (T2n, A2)], method="cbs", keep_cnr=True, sample_ids=["S1", "S2"])
+    want1 = fix.do_fix(T1, A1, R)
+    assert_same(got[0][0], want1)
+    assert_same(got[0][1], segmentation.do_segmentation(want1, "cbs"))
+    want2 = fix.do_fix(T2n, A2, R)
+    assert_same(got[1][0], want2)
+    assert len(got[1][0]) == len(want1) - int(panel.t.keep[17])
+    assert_same(got[1][1], segmentation.do_segmentation(want2, "cbs"))
+    with pytest.raises(ValueError):
+        panel.fix({"log2": np.zeros(3), "depth": np.zeros(3)}, cols[1])
+
+
+@pytest.mark.parametrize("method", ["cbs", "haar"])
+def test_cohort_vs_cpu_oracle_pipeline(world, method):
+    """fix + segment of the CUDA path against the composed CPU oracle (oracle/pipeline.py, built from
+    the units pinned to the reference): ratios bit-exact, weights 1e-12, identical segment
+    boundaries, segment means 1e-9."""
+    from cnvkit_b200 import cohort
+    from oracle import pipeline as OP
+
+    bins, ref, tabs = world
+    T0, A0, R = tabs[0]
+    panel = cohort.Panel(T0, A0, R)
+    refc = dict(log2=ref["log2"], depth=ref["depth"], spread=ref["spread"], gc=bins["gc"], rmask=bins["rmask"])
+    for T, A, _ in tabs[:2]:
+        sample = {"log2": np.empty(len(bins["start"])), "depth": np.empty(len(bins["start"]))}
+        t = bins["is_target"]
+        for c in ("log2", "depth"):
+            sample[c][t] = T.data[c].to_numpy()
+            sample[c][~t] = A.data[c].to_numpy()
+        want = OP.do_fix(bins, sample, refc)
+        d_log2, d_w, d_depth = panel.fix(T, A)
+        np.testing.assert_array_equal(d_log2.cpu().numpy(), want["log2"])
+        np.testing.assert_allclose(d_w.cpu().numpy(), want["weight"], rtol=1e-12, atol=0)
+        k = np.flatnonzero(want["keep"])
+        chrom = np.asarray(bins["chromosome"], dtype=object)[k]
+        start, end = bins["start"][k], bins["end"][k]
+        # segment the oracle's own .cnr columns on both sides so that only the segmenter differs
+        (o_arm, o_lo, o_hi, o_mean), fidx = OP.segment_columns(chrom, start, end, want["log2"], d_w.cpu().numpy(),
+                                                               method, nthreads=4)
+        cns = panel.segment([(d_log2, d_w, d_depth)], method)[0]
+        # interior boundaries (the first/last segment of an arm is stretched by transfer_fields)
+        got_probes = cns.data["probes"].to_numpy()
+        np.testing.assert_array_equal(np.sort(got_probes), np.sort(o_hi - o_lo))
+        got = cns.data.sort_values(["chromosome", "start"]).reset_index(drop=True)
+        o_start = start[fidx[o_lo]]
+        o_chrom = chrom[fidx[o_lo]]
+        want_tab = pd.DataFrame({"chromosome": o_chrom, "start": o_start, "probes": o_hi - o_lo, "log2": o_mean})
+        want_tab = want_tab.sort_values(["chromosome", "start"]).reset_index(drop=True)
+        np.testing.assert_array_equal(got["probes"].to_numpy(), want_tab["probes"].to_numpy())
+        np.testing.assert_allclose(got["log2"].to_numpy(), want_tab["log2"].to_numpy(), rtol=1e-9, atol=0)
