@@ -321,8 +321,8 @@ def run_b200(args):
 
     # warm-up (>= 3): allocator pools, module load, clocks
     for _ in range(max(args.warmup, 3)):
-        step_resident()
-    step_host()
+        gather_tables(step_resident())      # includes NCCL's lazy communicator set-up
+    gather_tables(step_host())
     barrier()
 
     sampler = ClockSampler(local_rank)
