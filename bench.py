@@ -50,6 +50,9 @@ def parse_args():
                     help="wgs: C3 (headline, default); cohort: C5 exome cohort fix + CBS sharded by sample")
     ap.add_argument("--samples", type=int, default=1024, help="cohort size for --workload cohort")
     ap.add_argument("--no-exome-leg", action="store_true", help="skip the C2 exome leg of the default run")
+    ap.add_argument("--sharding", default="samples", choices=["samples", "arms"],
+                    help="N > 1: 'samples' = one WGS sample per rank (weak scaling, default); "
+                         "'arms' = the arms of ONE sample over the ranks (strong scaling, BASELINE configs[2])")
     return ap.parse_args()
 
 
@@ -239,7 +242,7 @@ def run_reference(args):
     sample = f"{len(picked)} shortest arms of the {args.bins}-bin sample ({len(x)} bins), full CBS incl. permutations"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.sharding == "arms" else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"C3 synthetic WGS, {args.bins} 1-kb bins, 48 arms, CBS alpha={ALPHA} nperm=10000",
                    "sample": sample, "segments": nseg},
@@ -266,10 +269,16 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
-    data = synth.wgs_sample(total_bins=args.bins)
-    owner = shard.arm_owner(data["arm_offsets"], world)
+    by_arms = args.sharding == "arms" and world > 1
+    if by_arms:
+        data = synth.wgs_sample(total_bins=args.bins)
+        owner = shard.arm_owner(data["arm_offsets"], world)
+        nbins_total = int(data["arm_offsets"][-1])
+    else:  # cohort mode: every rank owns one whole sample (its own seed), nothing is shared
+        data = synth.wgs_sample(total_bins=args.bins, seed=0xC3 + rank)
+        owner = np.full(len(data["arm_offsets"]) - 1, rank)
+        nbins_total = int(data["arm_offsets"][-1]) * world
     x, w, off, mine = shard.take_arms(data["log2"], data["weight"], data["arm_offsets"], owner, rank)
-    nbins_total = int(data["arm_offsets"][-1])
     prune = not args.no_prune
 
     hx = torch.from_numpy(x).pin_memory()
@@ -298,7 +307,9 @@ def run_b200(args):
             return len(arm)
         g_arm = mine[arm] if len(arm) else np.zeros(0, np.int64)
         shift = (data["arm_offsets"][g_arm] - off[arm]) if len(arm) else np.zeros(0, np.int64)
-        full = shard.gather_tables([g_arm.astype(np.int64), lo + shift, hi + shift, mean], dst=0, device=dev)
+        sample_col = np.full(len(arm), 0 if by_arms else rank, dtype=np.int64)
+        full = shard.gather_tables([sample_col, g_arm.astype(np.int64), lo + shift, hi + shift, mean], dst=0,
+                                   device=dev)
         n_all = torch.tensor([len(full[0]) if full is not None else 0], dtype=torch.int64, device=dev)
         dist.broadcast(n_all, src=0)
         return int(n_all.item())
@@ -425,10 +436,13 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": nbins_total / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C3 synthetic WGS, {args.bins} 1-kb bins, 48 arms, CBS alpha={ALPHA} nperm=10000",
-                       "sharding": f"arms over {world} rank(s) by LPT on n^2; NCCL gather of tables" if world > 1
-                       else "single GPU", "l2": "256 MB flush write between timed steps", "prune": prune,
+            "scaling": "strong" if by_arms else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3 synthetic WGS, {args.bins} 1-kb bins, 48 arms, CBS alpha={ALPHA} nperm=10000"
+                                   + ("" if by_arms or world == 1 else f", one such sample per GPU ({world} samples)"),
+                       "sharding": "single GPU" if world == 1 else
+                       (f"arms of one sample over {world} ranks by LPT on n^2; NCCL gather of tables" if by_arms else
+                        f"samples over {world} ranks (cohort mode), no data-path collective; NCCL gather of tables"),
+                       "l2": "256 MB flush write between timed steps", "prune": prune,
                        "segments": nseg_total},
             "e2e": {"value": nbins_total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -69,6 +69,16 @@ SIGNATURES = {
     "cnvk_haar_segment": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_double, c_int64, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
     "cnvk_cbs_getbdry": (c_int, [c_double, c_int32, c_int32, c_void_p]),
+    "cnvk_tsv_open": (c_int, [c_char_p, c_void_p]),
+    "cnvk_tsv_close": (None, [c_void_p]),
+    "cnvk_tsv_shape": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "cnvk_tsv_colname": (c_char_p, [c_void_p, c_int32]),
+    "cnvk_tsv_col_kind": (c_int, [c_void_p, c_int32]),
+    "cnvk_tsv_read_f64": (c_int, [c_void_p, c_int32, c_void_p]),
+    "cnvk_tsv_read_i64": (c_int, [c_void_p, c_int32, c_void_p]),
+    "cnvk_tsv_read_str": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
+    "cnvk_tsv_hash_cols": (c_uint64, [c_void_p, c_void_p, c_int32]),
+    "cnvk_tsv_write": (c_int, [c_char_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
 }
 
 

@@ -1,0 +1,315 @@
+// Host-side reader / writer of CNVkit's tab-separated tables (.cnn / .cnr / .cns): the boundary of
+// the hot path.  Restates what skgenome/tabio/tab.py:18-33 (pandas.read_csv
+// with sep="\t") and skgenome/tabio/__init__.py:175-195 (DataFrame.to_csv(sep="\t",
+// float_format="%.6g", index=False)) do for these files, without pandas: one pass to index the
+// fields, then per-column conversion with std::from_chars (correctly rounded, like pandas' parser on
+// the <= 15-digit decimals these files hold) and printf-exact "%.6g" on the way out.
+//
+// No CUDA here: the columns land in caller-provided host buffers (pinned, if the caller wants to
+// DMA them straight to HBM).
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/cnvkit_b200.h"
+namespace cnvk {
+void set_last_error(const char* fmt, ...);  // capi.cu
+}
+
+namespace {
+
+struct Field {
+    uint64_t off;
+    uint32_t len;
+    uint32_t quoted;  // field was written as "..." (inner "" are unescaped lazily)
+};
+
+struct Table {
+    std::string data;
+    std::vector<std::string> names;
+    std::vector<Field> fields;  // row-major [nrows][ncols]
+    int64_t nrows = 0;
+    int ncols = 0;
+};
+
+// pandas' default na_values for read_csv
+const char* const kNa[] = {"",     "#N/A", "#N/A N/A", "#NA",  "-1.#IND", "-1.#QNAN", "-NaN", "-nan", "1.#IND",
+                           "1.#QNAN", "<NA>", "N/A",   "NA",   "NULL",    "NaN",      "None", "n/a",  "nan", "null"};
+
+bool is_na(const char* p, size_t n) {
+    if (n == 0) return true;
+    if (n > 8) return false;
+    for (const char* s : kNa)
+        if (strlen(s) == n && memcmp(s, p, n) == 0) return true;
+    return false;
+}
+
+// Splits one line into fields; returns the offset of the next line.  Minimal RFC-4180 quoting, as
+// pandas' C tokenizer applies to sep="\t".
+size_t split_line(const std::string& d, size_t pos, std::vector<Field>& out) {
+    const size_t n = d.size();
+    for (;;) {
+        Field f{pos, 0, 0};
+        if (pos < n && d[pos] == '"') {
+            f.quoted = 1;
+            size_t q = pos + 1;
+            f.off = q;
+            while (q < n) {
+                if (d[q] == '"') {
+                    if (q + 1 < n && d[q + 1] == '"') { q += 2; continue; }
+                    break;
+                }
+                ++q;
+            }
+            f.len = (uint32_t)(q - f.off);
+            pos = q < n ? q + 1 : q;
+        } else {
+            size_t q = pos;
+            while (q < n && d[q] != '\t' && d[q] != '\n' && d[q] != '\r') ++q;
+            f.len = (uint32_t)(q - pos);
+            pos = q;
+        }
+        out.push_back(f);
+        if (pos < n && d[pos] == '\t') { ++pos; continue; }
+        if (pos < n && d[pos] == '\r') ++pos;
+        if (pos < n && d[pos] == '\n') ++pos;
+        return pos;
+    }
+}
+
+std::string field_text(const Table& t, const Field& f) {
+    std::string s(t.data.data() + f.off, f.len);
+    if (f.quoted) {
+        size_t k;
+        size_t from = 0;
+        while ((k = s.find("\"\"", from)) != std::string::npos) { s.erase(k, 1); from = k + 1; }
+    }
+    return s;
+}
+
+bool parse_i64(const char* p, size_t n, int64_t* v) {
+    while (n && (*p == ' ')) { ++p; --n; }
+    while (n && (p[n - 1] == ' ')) --n;
+    if (n && *p == '+') { ++p; --n; }
+    if (!n) return false;
+    auto r = std::from_chars(p, p + n, *v);
+    return r.ec == std::errc() && r.ptr == p + n;
+}
+
+bool parse_f64(const char* p, size_t n, double* v) {
+    while (n && (*p == ' ')) { ++p; --n; }
+    while (n && (p[n - 1] == ' ')) --n;
+    if (n && *p == '+') { ++p; --n; }
+    if (!n) return false;
+    auto r = std::from_chars(p, p + n, *v);
+    if (r.ec == std::errc() && r.ptr == p + n) return true;
+    // "inf", "-inf", "Infinity" spellings pandas also accepts
+    std::string s(p, n);
+    for (auto& c : s) c = (char)tolower(c);
+    if (s == "inf" || s == "infinity") { *v = INFINITY; return true; }
+    if (s == "-inf" || s == "-infinity") { *v = -INFINITY; return true; }
+    return false;
+}
+
+int fail(const char* fmt, const char* a) {
+    cnvk::set_last_error(fmt, a);
+    return -1;
+}
+
+}  // namespace
+
+struct cnvk_tsv {
+    Table t;
+};
+
+extern "C" {
+
+int cnvk_tsv_open(const char* path, cnvk_tsv** out) {
+    *out = nullptr;
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail("cnvk_tsv_open: cannot open %s", path);
+    auto* h = new cnvk_tsv();
+    Table& t = h->t;
+    char buf[1 << 16];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof(buf), fp)) > 0) t.data.append(buf, got);
+    fclose(fp);
+    if (t.data.size() >= 3 && memcmp(t.data.data(), "\xEF\xBB\xBF", 3) == 0) t.data.erase(0, 3);
+    size_t pos = 0;
+    std::vector<Field> row;
+    if (t.data.empty()) { *out = h; return 0; }  // blank file: zero columns (pandas EmptyDataError)
+    pos = split_line(t.data, 0, row);
+    t.ncols = (int)row.size();
+    for (const Field& f : row) t.names.push_back(field_text(t, f));
+    t.fields.reserve((size_t)(t.data.size() / 24) * (size_t)std::max(t.ncols, 1) / 2);
+    while (pos < t.data.size()) {
+        // skip blank lines (pandas skip_blank_lines=True)
+        if (t.data[pos] == '\n') { ++pos; continue; }
+        if (t.data[pos] == '\r' && pos + 1 < t.data.size() && t.data[pos + 1] == '\n') { pos += 2; continue; }
+        row.clear();
+        pos = split_line(t.data, pos, row);
+        // short rows are padded with missing fields, as pandas' tokenizer does; long rows are an error
+        while ((int)row.size() < t.ncols) row.push_back(Field{0, 0, 0});
+        if ((int)row.size() != t.ncols) {
+            char msg[160];
+            snprintf(msg, sizeof(msg), "row %lld has %d fields, header has %d", (long long)t.nrows + 2, (int)row.size(),
+                     t.ncols);
+            delete h;
+            return fail("cnvk_tsv_open: %s", msg);
+        }
+        t.fields.insert(t.fields.end(), row.begin(), row.end());
+        ++t.nrows;
+    }
+    *out = h;
+    return 0;
+}
+
+void cnvk_tsv_close(cnvk_tsv* h) { delete h; }
+
+int cnvk_tsv_shape(const cnvk_tsv* h, int64_t* nrows, int32_t* ncols) {
+    *nrows = h->t.nrows;
+    *ncols = h->t.ncols;
+    return 0;
+}
+
+const char* cnvk_tsv_colname(const cnvk_tsv* h, int32_t col) {
+    return (col >= 0 && col < h->t.ncols) ? h->t.names[col].c_str() : nullptr;
+}
+
+// pandas' dtype inference for one column: 1 = int64 (every field an integer, none missing),
+// 2 = float64 (numbers and missing values), 0 = object/str.
+int cnvk_tsv_col_kind(const cnvk_tsv* h, int32_t col) {
+    const Table& t = h->t;
+    if (col < 0 || col >= t.ncols) return -1;
+    bool all_int = true;
+    for (int64_t r = 0; r < t.nrows; ++r) {
+        const Field& f = t.fields[(size_t)r * t.ncols + col];
+        const char* p = t.data.data() + f.off;
+        if (f.quoted) return 0;
+        int64_t iv;
+        if (all_int && f.len && parse_i64(p, f.len, &iv)) continue;
+        all_int = false;
+        double dv;
+        if (f.len && parse_f64(p, f.len, &dv)) continue;
+        if (!is_na(p, f.len)) return 0;
+    }
+    return all_int ? 1 : 2;
+}
+
+int cnvk_tsv_read_f64(const cnvk_tsv* h, int32_t col, double* out) {
+    const Table& t = h->t;
+    if (col < 0 || col >= t.ncols) return fail("cnvk_tsv_read_f64: %s", "bad column");
+    for (int64_t r = 0; r < t.nrows; ++r) {
+        const Field& f = t.fields[(size_t)r * t.ncols + col];
+        const char* p = t.data.data() + f.off;
+        double v;
+        if (f.len && parse_f64(p, f.len, &v)) { out[r] = v; continue; }   // a number, the common case
+        if (!is_na(p, f.len)) return fail("cnvk_tsv_read_f64: not a number in column %s", t.names[col].c_str());
+        out[r] = std::numeric_limits<double>::quiet_NaN();
+    }
+    return 0;
+}
+
+int cnvk_tsv_read_i64(const cnvk_tsv* h, int32_t col, int64_t* out) {
+    const Table& t = h->t;
+    if (col < 0 || col >= t.ncols) return fail("cnvk_tsv_read_i64: %s", "bad column");
+    for (int64_t r = 0; r < t.nrows; ++r) {
+        const Field& f = t.fields[(size_t)r * t.ncols + col];
+        if (!parse_i64(t.data.data() + f.off, f.len, &out[r]))
+            return fail("cnvk_tsv_read_i64: not an integer in column %s", t.names[col].c_str());
+    }
+    return 0;
+}
+
+// String column as one byte buffer + offsets[nrows+1].  With buf == NULL only *nbytes is filled.
+int cnvk_tsv_read_str(const cnvk_tsv* h, int32_t col, int64_t* offsets, char* buf, int64_t cap, int64_t* nbytes) {
+    const Table& t = h->t;
+    if (col < 0 || col >= t.ncols) return fail("cnvk_tsv_read_str: %s", "bad column");
+    int64_t tot = 0;
+    for (int64_t r = 0; r < t.nrows; ++r) {
+        const Field& f = t.fields[(size_t)r * t.ncols + col];
+        if (buf) {
+            if (f.quoted) {
+                const std::string s = field_text(t, f);
+                if (tot + (int64_t)s.size() > cap) return fail("cnvk_tsv_read_str: %s", "buffer too small");
+                memcpy(buf + tot, s.data(), s.size());
+                offsets[r] = tot;
+                tot += (int64_t)s.size();
+                continue;
+            }
+            if (tot + f.len > cap) return fail("cnvk_tsv_read_str: %s", "buffer too small");
+            memcpy(buf + tot, t.data.data() + f.off, f.len);
+            offsets[r] = tot;
+        }
+        tot += f.len;
+    }
+    if (buf) offsets[t.nrows] = tot;
+    *nbytes = tot;
+    return 0;
+}
+
+// FNV-1a over the raw bytes of the given columns, row by row: lets a cohort reader check that a
+// sample's bin columns equal the panel's without materialising any string.
+uint64_t cnvk_tsv_hash_cols(const cnvk_tsv* h, const int32_t* cols, int32_t n) {
+    const Table& t = h->t;
+    uint64_t x = 1469598103934665603ull;
+    for (int64_t r = 0; r < t.nrows; ++r)
+        for (int k = 0; k < n; ++k) {
+            const Field& f = t.fields[(size_t)r * t.ncols + cols[k]];
+            const unsigned char* p = (const unsigned char*)t.data.data() + f.off;
+            for (uint32_t b = 0; b < f.len; ++b) { x ^= p[b]; x *= 1099511628211ull; }
+            x ^= 0x1f; x *= 1099511628211ull;
+        }
+    return x;
+}
+
+// DataFrame.to_csv(path, sep="\t", index=False, float_format="%.6g"): kinds[c] = 0 str
+// (ptrs[c] = int64 offsets[nrows+1], ptrs2[c] = bytes), 1 int64, 2 float64 (NaN -> empty field).
+int cnvk_tsv_write(const char* path, int32_t ncols, const char* const* names, const int32_t* kinds,
+                   const void* const* ptrs, const void* const* ptrs2, int64_t nrows) {
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail("cnvk_tsv_write: cannot open %s", path);
+    std::string out;
+    out.reserve((size_t)nrows * ncols * 10 + 256);
+    for (int c = 0; c < ncols; ++c) { if (c) out += '\t'; out += names[c]; }
+    out += '\n';
+    char num[64];
+    for (int64_t r = 0; r < nrows; ++r) {
+        for (int c = 0; c < ncols; ++c) {
+            if (c) out += '\t';
+            if (kinds[c] == 1) {
+                auto res = std::to_chars(num, num + sizeof(num), ((const int64_t*)ptrs[c])[r]);
+                out.append(num, res.ptr - num);
+            } else if (kinds[c] == 2) {
+                const double v = ((const double*)ptrs[c])[r];
+                if (v == v) out.append(num, (size_t)snprintf(num, sizeof(num), "%.6g", v));
+            } else {
+                const int64_t* off = (const int64_t*)ptrs[c];
+                const char* s = (const char*)ptrs2[c] + off[r];
+                const size_t len = (size_t)(off[r + 1] - off[r]);
+                bool q = false;
+                for (size_t k = 0; k < len; ++k)
+                    if (s[k] == '\t' || s[k] == '"' || s[k] == '\n' || s[k] == '\r') { q = true; break; }
+                if (!q) out.append(s, len);
+                else {
+                    out += '"';
+                    for (size_t k = 0; k < len; ++k) { if (s[k] == '"') out += '"'; out += s[k]; }
+                    out += '"';
+                }
+            }
+        }
+        out += '\n';
+        if (out.size() > (1u << 22)) { fwrite(out.data(), 1, out.size(), fp); out.clear(); }
+    }
+    fwrite(out.data(), 1, out.size(), fp);
+    if (fclose(fp) != 0) return fail("cnvk_tsv_write: write failed for %s", path);
+    return 0;
+}
+
+}  // extern "C"

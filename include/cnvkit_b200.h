@@ -222,6 +222,30 @@ int cnvk_haar_segment(const double* log2, const double* weight, const int64_t* a
                       double fdr_q, int64_t capacity, int32_t* seg_arm, int64_t* seg_lo, int64_t* seg_hi,
                       double* seg_mean, int64_t* n_segs);
 
+/* ---- table I/O (host only) ------------------------------------------------------------------ */
+/* Reader for the tab-separated .cnn/.cnr/.cns tables: skgenome/tabio/tab.py:18-33 read_tab
+ * (pandas.read_csv(sep="\t", dtype={"chromosome": str})).  cnvk_tsv_open indexes the file (header +
+ * rows, blank lines skipped, minimal quoting); columns are then converted on demand.  Missing values
+ * follow pandas' default na_values; cnvk_tsv_col_kind is pandas' dtype inference (1 int64, 2 float64,
+ * 0 str).  The caller applies read_tab's "drop rows without log2" rule on the columns. */
+typedef struct cnvk_tsv cnvk_tsv;
+int cnvk_tsv_open(const char* path, cnvk_tsv** out);
+void cnvk_tsv_close(cnvk_tsv* h);
+int cnvk_tsv_shape(const cnvk_tsv* h, int64_t* nrows, int32_t* ncols);
+const char* cnvk_tsv_colname(const cnvk_tsv* h, int32_t col);
+int cnvk_tsv_col_kind(const cnvk_tsv* h, int32_t col);
+int cnvk_tsv_read_f64(const cnvk_tsv* h, int32_t col, double* out);
+int cnvk_tsv_read_i64(const cnvk_tsv* h, int32_t col, int64_t* out);
+/* String column as bytes + offsets[nrows+1]; buf == NULL only reports *nbytes. */
+int cnvk_tsv_read_str(const cnvk_tsv* h, int32_t col, int64_t* offsets, char* buf, int64_t cap, int64_t* nbytes);
+/* FNV-1a of the raw field bytes of the given columns: equality test of bin sets without strings. */
+uint64_t cnvk_tsv_hash_cols(const cnvk_tsv* h, const int32_t* cols, int32_t n);
+/* Writer: skgenome/tabio/__init__.py:175-195 write (DataFrame.to_csv(sep="\t", index=False,
+ * float_format="%.6g")).  kinds[c]: 0 str (ptrs[c] = int64 offsets[nrows+1], ptrs2[c] = bytes),
+ * 1 int64, 2 float64 (NaN -> empty field). */
+int cnvk_tsv_write(const char* path, int32_t ncols, const char* const* names, const int32_t* kinds,
+                   const void* const* ptrs, const void* const* ptrs2, int64_t nrows);
+
 #ifdef __cplusplus
 }
 #endif
