@@ -3,11 +3,12 @@
 // i.e. DNAcopy::segment(CNA(log2,...), weights=w, alpha=threshold) with DNAcopy defaults).
 //
 // Structure (level-synchronous over ALL arms of ALL samples in the batch):
-//   prep   : one CTA per open interval ("node"): sum w, sum x*w, sum w*xc^2 as double-double
-//            reductions (R-level sum() calls), weighted centring, and the strictly sequential FP64
-//            prefix sums S_i = sum w xc, cw_i = cumsum(w)/sqrt(sum w) that define the statistic's
-//            bits (one warp per chain runs it out of shared-memory chunks the other warps stage),
-//            per-256-point block min/max (+ arg) of S for pruning, getmncwt's delta.
+//   prep   : one CTA (1024 threads) per open interval ("node"): sum w, sum x*w, sum w*xc^2 as
+//            double-double reductions (R-level sum() calls), weighted centring, and the prefix sums
+//            S_i = sum w xc, cw_i = cumsum(w)/sqrt(sum w) as a blocked FP64 scan with one fixed
+//            association (thread-sequential x8, Kogge-Stone per warp, warp totals and tile carry
+//            left to right) that the CPU oracle replays bit for bit; per-256-point block min/max
+//            (+ arg) of S for pruning, getmncwt's delta.
 //   seed   : every pair of 256-point blocks proposes the arcs between its extreme prefix points.
 //   band   : arcs whose end points lie in the same or adjacent 256-point blocks, pruned on 32x32
 //            sub-blocks out of shared memory (they cannot be pruned at 256-point granularity).
@@ -40,8 +41,7 @@ namespace cnvk {
 static const int CBS_BLK = 256;           // points per bound block / j-block
 static const int CBS_IW = 4;              // arc starts per thread
 static const int CBS_IBLK = CBS_BLK * CBS_IW;
-static const int PREP_CHUNK = 1024;
-static const size_t PREP_SMEM = (size_t)2 * 2 * PREP_CHUNK * sizeof(double);
+static const size_t PREP_SMEM = (size_t)2 * (8192 + 1024) * sizeof(double);   // two padded 8192-term tiles
 static const int HYB_TP = 2048;           // arc starts per CTA in the hybrid permutation kernel
 static const int HYB_KMAX = 64;           // max supported kmax
 static const int EXACT_NMAX = 256;        // max supported nmin
@@ -73,40 +73,25 @@ __device__ __forceinline__ double pt(const double* a, int lo, int i) {
 }
 
 // ------------------------------------------------------------------------------------ prep
-// Which sums are order-defined and which are not (R's changepoints() for weighted data):
+// Sums of R's changepoints() for weighted data, and how they are evaluated here:
 //   * sum(w), sum(x*w), sum(w*xc^2) are R-level sum() calls -- R accumulates them in 80-bit long
 //     double, i.e. they are (to within an ulp) the correctly rounded exact sums.  They are
-//     evaluated here as double-double (compensated) reductions over all threads: parallel, and the
-//     rounded result does not depend on the order of accumulation.
-//   * S_i = sum_{l<=i} xc_l w_l is DNAcopy's Fortran partial-sum loop: a strictly sequential FP64 add
-//     chain that defines the bits of the statistic; cumsum(w) is kept as the same kind of chain.
-//     Each chain gets its own warp (lane 0 runs it out of shared memory, 8 elements per iteration
-//     with 128-bit loads/stores) while the other warps stage the next chunk and write the previous
-//     one back to HBM -- double-buffered, one __syncthreads per chunk.
-static const int PREP_THREADS = 256;
-static const int PREP_CHAIN_WARPS = 2;
-static const int PREP_STAGE_T0 = PREP_CHAIN_WARPS * 32;           // first staging thread
-static const int PREP_STAGE_N = PREP_THREADS - PREP_STAGE_T0;     // staging threads
-
-// in-place inclusive running sum over m (multiple of 8) doubles in shared memory; the next eight
-// operands are fetched before the current eight dependent adds so that only the DADD latency is
-// on the critical path
-__device__ __forceinline__ double chain_inplace(double* s, int m, double run) {
-    double2* p = reinterpret_cast<double2*>(s);
-    const int m2 = m / 2;
-    if (m2 == 0) return run;
-    double2 n0 = p[0], n1 = p[1], n2 = p[2], n3 = p[3];
-    for (int t = 0; t < m2; t += 4) {
-        double2 v0 = n0, v1 = n1, v2 = n2, v3 = n3;
-        if (t + 4 < m2) { n0 = p[t + 4]; n1 = p[t + 5]; n2 = p[t + 6]; n3 = p[t + 7]; }
-        run = __dadd_rn(run, v0.x); v0.x = run; run = __dadd_rn(run, v0.y); v0.y = run;
-        run = __dadd_rn(run, v1.x); v1.x = run; run = __dadd_rn(run, v1.y); v1.y = run;
-        run = __dadd_rn(run, v2.x); v2.x = run; run = __dadd_rn(run, v2.y); v2.y = run;
-        run = __dadd_rn(run, v3.x); v3.x = run; run = __dadd_rn(run, v3.y); v3.y = run;
-        p[t] = v0; p[t + 1] = v1; p[t + 2] = v2; p[t + 3] = v3;
-    }
-    return run;
-}
+//     double-double (compensated) reductions over all threads: the rounded result does not depend
+//     on the order of accumulation.
+//   * the prefix sums S_i = sum_{l<=i} xc_l w_l (DNAcopy's partial sums) and cumsum(w) are a
+//     BLOCKED FP64 prefix sum with one fixed, documented association (oracle/cbs_oracle.c
+//     `blocked_prefix` replays it operation by operation, so GPU and oracle agree bit for bit):
+//       tile   = 8192 consecutive terms; thread j of 1024 owns terms 8j..8j+7
+//       p[j,e] = left-to-right running sum of the thread's terms          (8 dependent adds)
+//       A[j]   = Kogge-Stone inclusive scan of the thread totals p[j,7] inside each warp
+//                (steps 1,2,4,8,16: A[l] += A[l-o] for lanes l >= o), E[j] = A[j-1] (0 for lane 0)
+//       X[w]   = W[0] + W[1] + ... + W[w-1] left to right over the warp totals W[w] = A[32w+31]
+//       out    = ((carry + X[w]) + E[j]) + p[j,e];   carry = out of the tile's last term
+//     It differs from a plain left-to-right sum by rounding only (its error growth is smaller).
+static const int PREP_THREADS = 1024;
+static const int PREP_E = 8;                            // terms per thread
+static const int PREP_TILE = PREP_THREADS * PREP_E;     // 8192 terms per tile
+__host__ __device__ __forceinline__ int prep_pad(int k) { return k + (k >> 3); }  // bank-conflict padding
 
 // double-double accumulator: hi + lo carries the running sum to ~2^-104 relative
 struct DD {
@@ -154,14 +139,16 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
                 double* __restrict__ cw, double* __restrict__ wn, double* __restrict__ blk_min,
                 double* __restrict__ blk_max, int* __restrict__ blk_imin, int* __restrict__ blk_imax, int al0,
                 int hk, int nmin) {
-    extern __shared__ __align__(16) double s_dyn[];      // [2 buffers][2 arrays][PREP_CHUNK]
+    extern __shared__ __align__(16) double s_dyn[];      // [2 arrays][padded tile]
     __shared__ double s_red[64];
     __shared__ int s_redi[64];
     __shared__ double s_scalar[8];
+    __shared__ double s_wtot[2][PREP_THREADS / 32];
     Node nd = nodes[blockIdx.x];
     const int lo = nd.lo, n = nd.hi - nd.lo;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    auto buf = [&](int b, int arr) { return s_dyn + ((size_t)b * 2 + arr) * PREP_CHUNK; };
+    double* s_w = s_dyn;
+    double* s_s = s_dyn + (PREP_TILE + PREP_TILE / 8);
 
     // range check: isTRUE(all.equal(diff(range(x)), 0)) -> final (changepoints R code);
     // the same pass accumulates sum(w) and sum(x*w)
@@ -193,7 +180,6 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
         }
         return;
     }
-    const int nchunks = (n + PREP_CHUNK - 1) / PREP_CHUNK;
     {
         const double sw_ = dd_block_sum(a_w, s_red, s_red + 32);
         const double swx_ = dd_block_sum(a_wx, s_red, s_red + 32);
@@ -203,55 +189,75 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
     const double sw = s_scalar[1], swx = s_scalar[2];
     const double avg = __ddiv_rn(swx, sw), rsw = sqrt(sw);
 
-    // ---- centred data; chains cs = cumsum(w), S = cumsum(xc*w); tss = sum w*xc^2 (double-double)
+    // ---- centred data; blocked prefix sums cs = cumsum(w), S = cumsum(xc*w); tss = sum w*xc^2
     DD a_tss = {0.0, 0.0};
-    {
-        auto stage2 = [&](int c, int b) {
-            const int c0 = c * PREP_CHUNK;
-            const int m = min(PREP_CHUNK, n - c0);
-            const int mp = (m + 7) & ~7;
-            double *A = buf(b, 0), *B = buf(b, 1);
-            for (int k = tid - PREP_STAGE_T0; k < mp; k += PREP_STAGE_N) {
-                double wv = 0.0, sv = 0.0;
-                if (k < m) {
-                    const int g = lo + c0 + k;
-                    wv = w[g];
-                    const double cc = __dsub_rn(x[g], avg);
-                    xc[g] = cc;
-                    y[g] = __dmul_rn(cc, sqrt(wv));
-                    wn[g] = __ddiv_rn(wv, rsw);
-                    sv = __dmul_rn(cc, wv);
-                    dd_add(a_tss, __dmul_rn(wv, __dmul_rn(cc, cc)));
-                }
-                A[k] = wv; B[k] = sv;
+    double carry_w = 0.0, carry_s = 0.0;
+    for (int t0 = 0; t0 < n; t0 += PREP_TILE) {
+        const int m = min(PREP_TILE, n - t0);
+        for (int k = tid; k < PREP_TILE; k += PREP_THREADS) {          // coalesced staging
+            double wv = 0.0, sv = 0.0;
+            if (k < m) {
+                const int g = lo + t0 + k;
+                wv = w[g];
+                const double cc = __dsub_rn(x[g], avg);
+                xc[g] = cc;
+                y[g] = __dmul_rn(cc, sqrt(wv));
+                wn[g] = __ddiv_rn(wv, rsw);
+                sv = __dmul_rn(cc, wv);
+                dd_add(a_tss, __dmul_rn(wv, __dmul_rn(cc, cc)));
             }
-        };
-        auto flush2 = [&](int c, int b) {
-            const int c0 = c * PREP_CHUNK;
-            const int m = min(PREP_CHUNK, n - c0);
-            const double *A = buf(b, 0), *B = buf(b, 1);
-            for (int k = tid - PREP_STAGE_T0; k < m; k += PREP_STAGE_N) {
-                const int g = lo + c0 + k;
-                cw[g] = __ddiv_rn(A[k], rsw);
-                S[g] = B[k];
-            }
-        };
-        double run = 0.0;
-        if (tid >= PREP_STAGE_T0) stage2(0, 0);
-        __syncthreads();
-        for (int c = 0; c < nchunks; ++c) {
-            const int b = c & 1;
-            const int m = min(PREP_CHUNK, n - c * PREP_CHUNK);
-            const int mp = (m + 7) & ~7;
-            if (tid >= PREP_STAGE_T0) {
-                if (c >= 1) flush2(c - 1, b ^ 1);          // results of the previous chunk
-                if (c + 1 < nchunks) stage2(c + 1, b ^ 1);  // then reuse that buffer
-            } else if (lane == 0) {
-                run = chain_inplace(buf(b, warp), mp, run);
-            }
-            __syncthreads();
+            s_w[prep_pad(k)] = wv;
+            s_s[prep_pad(k)] = sv;
         }
-        if (tid >= PREP_STAGE_T0) flush2(nchunks - 1, (nchunks - 1) & 1);
+        __syncthreads();
+        double pw[PREP_E], ps[PREP_E];
+        {
+            double rw = 0.0, rs = 0.0;
+            const int b0 = prep_pad(PREP_E * tid);                     // 8 consecutive padded slots
+#pragma unroll
+            for (int e = 0; e < PREP_E; ++e) {
+                const double vw = s_w[b0 + e], vs = s_s[b0 + e];
+                rw = e ? __dadd_rn(rw, vw) : vw;
+                rs = e ? __dadd_rn(rs, vs) : vs;
+                pw[e] = rw;
+                ps[e] = rs;
+            }
+        }
+        double Aw = pw[PREP_E - 1], As = ps[PREP_E - 1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {                              // Kogge-Stone inclusive warp scan
+            const double tw = __shfl_up_sync(0xffffffffu, Aw, o), ts = __shfl_up_sync(0xffffffffu, As, o);
+            if (lane >= o) { Aw = __dadd_rn(Aw, tw); As = __dadd_rn(As, ts); }
+        }
+        double Ew = __shfl_up_sync(0xffffffffu, Aw, 1), Es = __shfl_up_sync(0xffffffffu, As, 1);
+        if (lane == 0) { Ew = 0.0; Es = 0.0; }
+        if (lane == 31) { s_wtot[0][warp] = Aw; s_wtot[1][warp] = As; }
+        __syncthreads();
+        double Xw = 0.0, Xs = 0.0;
+        for (int k = 0; k < warp; ++k) {
+            Xw = k ? __dadd_rn(Xw, s_wtot[0][k]) : s_wtot[0][0];
+            Xs = k ? __dadd_rn(Xs, s_wtot[1][k]) : s_wtot[1][0];
+        }
+        const double bw_ = __dadd_rn(__dadd_rn(carry_w, Xw), Ew), bs_ = __dadd_rn(__dadd_rn(carry_s, Xs), Es);
+        {
+            const int b0 = prep_pad(PREP_E * tid);
+#pragma unroll
+            for (int e = 0; e < PREP_E; ++e) {
+                s_w[b0 + e] = __dadd_rn(bw_, pw[e]);
+                s_s[b0 + e] = __dadd_rn(bs_, ps[e]);
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < m; k += PREP_THREADS) {                   // coalesced write-back
+            const int g = lo + t0 + k;
+            cw[g] = __ddiv_rn(s_w[prep_pad(k)], rsw);
+            S[g] = s_s[prep_pad(k)];
+        }
+        carry_w = s_w[prep_pad(PREP_TILE - 1)];
+        carry_s = s_s[prep_pad(PREP_TILE - 1)];
+        __syncthreads();
+    }
+    {
         const double tss_ = dd_block_sum(a_tss, s_red, s_red + 32);
         if (tid == 0) s_scalar[3] = tss_;
         __syncthreads();

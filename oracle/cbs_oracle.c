@@ -26,8 +26,9 @@
  *  (2) R computes sum()/cumsum() in 80-bit extended precision.  Here the three R-level totals
  *      (sum w, sum x*w, sum w*xc^2) are compensated double-double sums rounded once -- the
  *      correctly rounded exact sum, which is what R's long-double accumulation yields to within an
- *      ulp -- while cumsum(w) and DNAcopy's Fortran partial sums S_i are plain left-to-right IEEE
- *      double accumulations.
+ *      ulp -- while cumsum(w) and DNAcopy's partial sums S_i are a blocked FP64 prefix sum with one
+ *      fixed association (`blocked_prefix` below, replayed operation by operation by the CUDA prep
+ *      kernel); it equals the left-to-right Fortran loop up to rounding.
  *  (3) wtmaxo's block-pruned search is restated as an exhaustive scan over all arcs; the
  *      maximum is the same, ties resolve to the smallest (i, j).
  *  (4) hwtmaxp (hybrid permutation statistic) is restated as windowed sums over circular
@@ -261,6 +262,54 @@ static inline void dd_add(dd_t* a, double p) { /* Knuth two-sum; lo collects the
     a->lo += e;
 }
 
+/* Blocked FP64 prefix sum with the fixed association the CUDA prep kernel uses (csrc/cbs.cu):
+ * tiles of 8192 terms; "thread" j of 1024 owns terms 8j..8j+7 and sums them left to right; the 1024
+ * thread totals are scanned per "warp" of 32 with the Kogge-Stone steps 1,2,4,8,16; warp totals are
+ * accumulated left to right; out = ((carry + X[warp]) + E[thread]) + p[thread, e]; the carry into the
+ * next tile is the tile's last output (missing terms of a short tile count as 0.0).  Same value as a
+ * left-to-right sum up to rounding (smaller error growth); what matters is that both sides do
+ * exactly these operations. */
+static void blocked_prefix(const double* t, int n, double* out) {
+    enum { PE = 8, NT = 1024, TILE = PE * NT };
+    static _Thread_local double p[TILE], A[NT], tmp[32];
+    double carry = 0.0;
+    for (int t0 = 0; t0 < n; t0 += TILE) {
+        const int m = (n - t0 < TILE) ? n - t0 : TILE;
+        for (int j = 0; j < NT; ++j) {
+            double r = 0.0;
+            for (int e = 0; e < PE; ++e) {
+                const int k = PE * j + e;
+                const double v = (k < m) ? t[t0 + k] : 0.0;
+                r = e ? r + v : v;
+                p[k] = r;
+            }
+            A[j] = r;
+        }
+        for (int w = 0; w < NT / 32; ++w)
+            for (int o = 1; o < 32; o <<= 1) {
+                for (int l = 0; l < 32; ++l) tmp[l] = A[32 * w + l];
+                for (int l = o; l < 32; ++l) A[32 * w + l] = tmp[l] + tmp[l - o];
+            }
+        double last = carry;
+        for (int w = 0; w < NT / 32; ++w) {
+            double X = 0.0;
+            for (int k = 0; k < w; ++k) X = k ? X + A[32 * k + 31] : A[31];
+            for (int l = 0; l < 32; ++l) {
+                const int j = 32 * w + l;
+                const double E = l ? A[j - 1] : 0.0;
+                const double base = (carry + X) + E;
+                for (int e = 0; e < PE; ++e) {
+                    const int k = PE * j + e;
+                    const double v = base + p[k];
+                    if (k < m) out[t0 + k] = v;
+                    if (k == TILE - 1) last = v;
+                }
+            }
+        }
+        carry = last;
+    }
+}
+
 /* ------------------------------------------------------------------ node statistics */
 typedef struct {
     int n;
@@ -401,7 +450,7 @@ static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, co
     const double sw = a_w.hi + a_w.lo, swx = a_wx.hi + a_wx.lo;
     const double avg = swx / sw;
     const double rsw = sqrt(sw);
-    double tss = 0.0, cs = 0.0, S = 0.0;
+    double tss = 0.0;
     N.S[0] = 0.0;
     for (int i = 0; i < n; ++i) {
         N.w[i] = w[i];
@@ -409,11 +458,11 @@ static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, co
         N.rw[i] = sqrt(w[i]);
         N.y[i] = N.xc[i] * N.rw[i];
         dd_add(&a_tss, w[i] * (N.xc[i] * N.xc[i]));
-        cs += w[i];
-        N.cw[i] = cs / rsw;
-        S += N.xc[i] * w[i];
-        N.S[i + 1] = S;
+        N.t[i] = N.xc[i] * w[i];
     }
+    blocked_prefix(N.w, n, N.cw);              /* cumsum(w) ... */
+    for (int i = 0; i < n; ++i) N.cw[i] = N.cw[i] / rsw;   /* ... / sqrt(sum w) */
+    blocked_prefix(N.t, n, N.S + 1);           /* partial sums S_1..S_n of xc*w */
     tss = a_tss.hi + a_tss.lo;
     N.tss = tss;
     N.total = N.cw[n - 1];
