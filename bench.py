@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--workload", default="wgs", choices=["wgs", "cohort"],
                     help="wgs: C3 (headline, default); cohort: C5 exome cohort fix + CBS sharded by sample")
     ap.add_argument("--samples", type=int, default=1024, help="cohort size for --workload cohort")
+    ap.add_argument("--workers", type=int, default=4, help="host threads (one CUDA stream each) per rank, cohort workload")
     ap.add_argument("--no-exome-leg", action="store_true", help="skip the C2 exome leg of the default run")
     ap.add_argument("--sharding", default="samples", choices=["samples", "arms"],
                     help="N > 1: 'samples' = one WGS sample per rank (weak scaling, default); "
@@ -515,7 +516,7 @@ def run_cohort(args):
         work = [source[i % n_distinct] for i in mine]
         if source is pinned:
             work = [tuple({k: v.numpy() for k, v in part.items()} for part in c) for c in work]
-        res = panel.run(work, method="cbs", batch=16, sample_ids=[f"S{i}" for i in mine])
+        res = panel.run(work, method="cbs", batch=8, workers=args.workers, sample_ids=[f"S{i}" for i in mine])
         rows = [np.concatenate([np.full(len(cns), i, dtype=np.int64) for i, (_c, cns) in zip(mine, res)])
                 if len(res) else np.zeros(0, np.int64)]
         for col in ("start", "end", "log2", "probes", "weight", "depth"):
@@ -566,7 +567,7 @@ def run_cohort(args):
             "steps": args.steps, "warmup": max(args.warmup, 3) if args.samples <= 256 else 1, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C5 cohort of {args.samples} C2 exome tumours ({n_distinct} distinct synthetic samples "
-                                   f"cycled), fix + CBS, 16 samples per segmentation call",
+                                   f"cycled), fix + CBS, 8 samples per segmentation call, {args.workers} host threads / streams per rank",
                        "sharding": f"samples over {world} rank(s) in blocks; NCCL gather of .cns rows",
                        "l2": "inputs of one step (>= 400 MB of columns per rank) exceed the 126 MB L2",
                        "segment_rows": n_rows},

@@ -82,7 +82,7 @@ class _Group:
         """Bias-corrected log2 of the kept rows (device tensor), or None if the sample needs the
         general path (NaN log2 would change the kept set, fix.py:244)."""
         if self.n0 == 0 or self.n == 0:
-            return _dev.empty(0, torch.float64)
+            return _dev.empty(0, torch.float64), _dev.empty(0, torch.float64)
         if torch.is_tensor(log2):                 # columns already resident in HBM
             if bool(torch.isnan(log2).any()):
                 return None
@@ -102,8 +102,7 @@ class _Group:
                   ctypes.addressof(skipped), _dev.stream())
         if skipped.value:
             logging.warning("WARNING: most bins have no or very low coverage; check that the right BED file was used")
-        self._depth_kept = d_depth
-        return d_log2
+        return d_log2, d_depth
 
 
 class Panel:
@@ -170,12 +169,12 @@ class Panel:
         al, ad = _cols(antitarget)
         if len(tl) != self.t.n0 or len(al) != self.a.n0:
             raise ValueError("sample tables do not match the panel's bin set")
-        xt = self.t.adjust(tl, td)
-        xa = self.a.adjust(al, ad)
-        if xt is None or xa is None:
+        rt = self.t.adjust(tl, td)
+        ra = self.a.adjust(al, ad)
+        if rt is None or ra is None:
             return None
-        parts = [p for p in (xt, xa) if len(p)]
-        dparts = [g._depth_kept for g in (self.t, self.a) if g.n0 and g.n]
+        parts = [r[0] for r in (rt, ra) if len(r[0])]
+        dparts = [r[1] for r in (rt, ra) if len(r[1])]
         d_log2 = torch.cat(parts).index_select(0, self.d_order).contiguous()
         d_depth = torch.cat(dparts).index_select(0, self.d_order).contiguous()
         d_w = _dev.empty(self.n, torch.float64)
@@ -324,37 +323,77 @@ class Panel:
         return out
 
     # ------------------------------------------------------------------ driver
-    def run(self, samples, method="cbs", threshold=None, batch=16, sample_ids=None, keep_cnr=False):
+    def run(self, samples, method="cbs", threshold=None, batch=16, sample_ids=None, keep_cnr=False, workers=1):
         """fix + segment for an iterable of (target, antitarget) coverage tables.  Returns a list of
-        (.cnr or None, .cns) per sample; `batch` samples share one segmentation call."""
-        out = []
-        pend, pend_ids = [], []
+        (.cnr or None, .cns) per sample, in input order; `batch` consecutive samples share one
+        segmentation call.  With `workers` > 1 the batches are processed by that many host threads,
+        each on its own CUDA stream, so that the host side of one batch (table assembly, gene names)
+        overlaps the device side of another."""
+        samples = list(samples)
+        n = len(samples)
+        ids = [sample_ids[k] if sample_ids is not None else getattr(samples[k][0], "sample_id", None)
+               for k in range(n)]
+        chunks = [list(range(i, min(i + max(int(batch), 1), n))) for i in range(0, n, max(int(batch), 1))]
 
-        def flush():
-            if not pend:
-                return
-            cns = self.segment(pend, method, threshold, sample_ids=pend_ids)
-            for trip, sid, seg in zip(pend, pend_ids, cns):
-                out.append((self.cnr_table(*trip, sample_id=sid) if keep_cnr else None, seg))
-            pend.clear()
-            pend_ids.clear()
+        def do_chunk(idx):
+            out, pend, pend_k = {}, [], []
+            for k in idx:
+                tgt, anti = samples[k]
+                trip = self.fix(tgt, anti)
+                if trip is None:  # general path for this sample
+                    t_tab, a_tab = self._as_tables(tgt, anti, ids[k])
+                    cnr = fix.do_fix(t_tab, a_tab, self._reference_table(), self.diploid_parx_genome, *self.opts)
+                    out[k] = (cnr if keep_cnr else None,
+                              segmentation.do_segmentation(cnr, method, self.diploid_parx_genome, threshold=threshold))
+                    continue
+                pend.append(trip)
+                pend_k.append(k)
+            if pend:
+                cns = self.segment(pend, method, threshold, sample_ids=[ids[k] for k in pend_k])
+                for trip, k, seg in zip(pend, pend_k, cns):
+                    out[k] = (self.cnr_table(*trip, sample_id=ids[k]) if keep_cnr else None, seg)
+            return out
 
-        for k, (tgt, anti) in enumerate(samples):
-            sid = sample_ids[k] if sample_ids is not None else getattr(tgt, "sample_id", None)
-            trip = self.fix(tgt, anti)
-            if trip is None:  # general path for this sample
-                flush()
-                t_tab, a_tab = self._as_tables(tgt, anti, sid)
-                cnr = fix.do_fix(t_tab, a_tab, self._reference_table(), self.diploid_parx_genome, *self.opts)
-                out.append((cnr if keep_cnr else None,
-                            segmentation.do_segmentation(cnr, method, self.diploid_parx_genome, threshold=threshold)))
-                continue
-            pend.append(trip)
-            pend_ids.append(sid)
-            if len(pend) >= batch:
-                flush()
-        flush()
-        return out
+        results = {}
+        if workers <= 1 or len(chunks) <= 1:
+            for idx in chunks:
+                results.update(do_chunk(idx))
+        else:
+            import queue
+            import threading
+
+            dev = _dev.device()
+            todo = queue.Queue()
+            for idx in chunks:
+                todo.put(idx)
+            errors = []
+
+            def worker():
+                torch.cuda.set_device(dev)
+                stream = torch.cuda.Stream(device=dev)
+                with torch.cuda.stream(stream):
+                    while True:
+                        try:
+                            idx = todo.get_nowait()
+                        except queue.Empty:
+                            break
+                        try:
+                            part = do_chunk(idx)
+                            stream.synchronize()
+                            results.update(part)
+                        except Exception as exc:  # surface in the caller
+                            errors.append(exc)
+                            break
+
+            torch.cuda.current_stream().synchronize()
+            threads = [threading.Thread(target=worker) for _ in range(min(int(workers), len(chunks)))]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            if errors:
+                raise errors[0]
+        return [results[k] for k in range(n)]
 
     def _as_tables(self, tgt, anti, sid):
         def one(proto, s):

@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(PREP_THREADS)
 cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const double* __restrict__ w,
                 double* __restrict__ xc, double* __restrict__ y, double* __restrict__ S,
                 double* __restrict__ cw, double* __restrict__ wn, double* __restrict__ blk_min,
-                double* __restrict__ blk_max, int* __restrict__ blk_imin, int* __restrict__ blk_imax, int al0,
-                int hk, int nmin) {
+                double* __restrict__ blk_max, int* __restrict__ blk_imin, int* __restrict__ blk_imax,
+                double* __restrict__ blk_cmin, double* __restrict__ blk_cmax, int al0, int hk, int nmin) {
     extern __shared__ __align__(16) double s_dyn[];      // [2 arrays][padded tile]
     __shared__ double s_red[64];
     __shared__ int s_redi[64];
@@ -314,6 +314,8 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
             blk_max[nd.blk_off + b] = bmx;
             blk_imin[nd.blk_off + b] = bimn;
             blk_imax[nd.blk_off + b] = bimx;
+            blk_cmin[nd.blk_off + b] = pt(cw, lo, bimn);   // cw at the extreme points: the seed kernel
+            blk_cmax[nd.blk_off + b] = pt(cw, lo, bimx);   // then needs no scattered load
         }
         if (bmn < gmin) { gmin = bmn; imin = bimn; }
         if (bmx > gmax) { gmax = bmx; imax = bimx; }
@@ -469,34 +471,46 @@ __device__ __forceinline__ void cta_commit(Node* nd, double q, int qi, int qj, d
 
 __global__ void __launch_bounds__(256)
 cbs_seed_kernel(Node* __restrict__ nodes, const int* __restrict__ task_off, int nnodes,
-                const double* __restrict__ S, const double* __restrict__ cw, const int* __restrict__ blk_imin,
-                const int* __restrict__ blk_imax, int al0) {
+                const double* __restrict__ blk_min, const double* __restrict__ blk_max,
+                const int* __restrict__ blk_imin, const int* __restrict__ blk_imax,
+                const double* __restrict__ blk_cmin, const double* __restrict__ blk_cmax, int al0) {
     __shared__ double s_q[8];
     __shared__ int s_i[8], s_j[8];
     int a, ib, jb0, NJ;
     decode_task(nodes, task_off, nnodes, blockIdx.x, a, ib, jb0, NJ);
     Node* nd = &nodes[a];
     if (nd->flat) return;
-    const int lo = nd->lo, n = nd->hi - nd->lo, boff = nd->blk_off;
+    const int n = nd->hi - nd->lo, boff = nd->blk_off;
     const double total = nd->total;
     double bq = -1.0;
     int bi_ = 0x7fffffff, bj_ = 0x7fffffff;
     const int jb = jb0 + threadIdx.x;
-    if (jb < NJ && threadIdx.x < 256) {
-        const int jmn = blk_imin[boff + jb], jmx = blk_imax[boff + jb];
+    if (jb < NJ) {
+        // per block: (S, cw, index) at the argmin and at the argmax of S -- all coalesced loads
+        const double jSmn = blk_min[boff + jb], jSmx = blk_max[boff + jb];
+        const double jCmn = blk_cmin[boff + jb], jCmx = blk_cmax[boff + jb];
+        const int jImn = blk_imin[boff + jb], jImx = blk_imax[boff + jb];
 #pragma unroll
         for (int r = 0; r < CBS_IW; ++r) {
             const int bi = CBS_IW * ib + r;
             if (bi > jb || bi >= NJ) continue;
-            const int imn = blk_imin[boff + bi], imx = blk_imax[boff + bi];
+            const double iSmn = blk_min[boff + bi], iSmx = blk_max[boff + bi];
+            const double iCmn = blk_cmin[boff + bi], iCmx = blk_cmax[boff + bi];
+            const int iImn = blk_imin[boff + bi], iImx = blk_imax[boff + bi];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                int i = c ? imx : imn, j = c ? jmn : jmx;
-                if (i > j) { const int t_ = i; i = j; j = t_; }
+                // c = 0: from the start block's minimum to the end block's maximum; c = 1: max -> min
+                int i = c ? iImx : iImn, j = c ? jImn : jImx;
+                double Si = c ? iSmx : iSmn, Sj = c ? jSmn : jSmx, ci = c ? iCmx : iCmn, cj = c ? jCmn : jCmx;
+                if (i > j) {                         // same block: order the two points
+                    const int t_ = i; i = j; j = t_;
+                    const double ts = Si; Si = Sj; Sj = ts;
+                    const double tc = ci; ci = cj; cj = tc;
+                }
                 const int kw = j - i;
                 if (kw < al0 || kw > n - al0) continue;
-                const double d = __dsub_rn(pt(S, lo, j), pt(S, lo, i));
-                const double cc = __dsub_rn(pt(cw, lo, j), pt(cw, lo, i));
+                const double d = __dsub_rn(Sj, Si);
+                const double cc = __dsub_rn(cj, ci);
                 const double den = __dmul_rn(cc, __dsub_rn(total, cc));
                 const double num = __dmul_rn(d, d);
                 if (!(num >= __dmul_rn(bq * (1.0 - 1e-12), den)) && bq >= 0.0) continue;
@@ -579,7 +593,9 @@ cbs_band_kernel(Node* __restrict__ nodes, int nnodes,
     if (warp * BAND_SUB < npts && warp * BAND_SUB < CBS_BLK) {
         const int i = ibase + il;
         const bool iok = il < npts;
-        const double Si = iok ? sp[il].x : 0.0, ci = iok ? sp[il].y : 0.0;
+        // lanes without a start point carry NaN so that their comparisons are all false
+        const double Si = iok ? sp[il].x : __longlong_as_double(0x7ff8000000000000ll), ci = iok ? sp[il].y : 0.0;
+        const unsigned kw_span = (unsigned)(n - 2 * al0);   // al0 <= kw <= n - al0  <=>  kw - al0 <= n - 2 al0
         const int wend = min(warp * BAND_SUB + BAND_SUB - 1, npts - 1);
         // lane <-> end sub-block: one bound test each, then walk the survivors (warp-uniform)
         unsigned need = 0;
@@ -608,7 +624,7 @@ cbs_band_kernel(Node* __restrict__ nodes, int nnodes,
                 const double c = __dsub_rn(pj.y, ci);
                 const double den = __dmul_rn(c, __dsub_rn(total, c));
                 const double num = __dmul_rn(d, d);
-                if (iok && kw >= al0 && kw <= n - al0 && num > __dmul_rn(best.qlo, den))
+                if ((unsigned)(kw - al0) <= kw_span && num > __dmul_rn(best.qlo, den))
                     cand_update(best, num, den, i, ibase + jl);
             }
         }
@@ -1074,23 +1090,24 @@ __global__ void cbs_perm_flags_kernel(const Node* __restrict__ nodes, const int*
 }
 
 // ------------------------------------------------------------------------------------ flank tests
-// wtpermp set-up: one CTA per test (sums by block reduction; thresholds only)
+// wtpermp set-up: every test's rows are split over FLANK_SPLIT CTAs (partial sums in a fixed order),
+// then one thread per test combines the partials left to right -- deterministic, thresholds only
+static const int FLANK_SPLIT = 16;
+
 __global__ void __launch_bounds__(256)
-cbs_flank_prep_kernel(const Node* __restrict__ nodes, FlankTest* __restrict__ tests, int ntests,
-                      const double* __restrict__ xc, const double* __restrict__ w, int nperm) {
+cbs_flank_part_kernel(const Node* __restrict__ nodes, const FlankTest* __restrict__ tests,
+                      const double* __restrict__ xc, const double* __restrict__ w, double* __restrict__ part) {
     __shared__ double s_part[5][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x;
-    FlankTest ft = tests[idx];
+    const int idx = blockIdx.x, sp = blockIdx.y;
+    const FlankTest ft = tests[idx];
     const Node* nd = &nodes[ft.node];
     const int g0 = nd->lo + ft.off;
-    const int n1 = ft.n1, n2 = ft.n2, n = n1 + n2;
-    if (n1 == 1 || n2 == 1) {
-        if (threadIdx.x == 0) { tests[idx].pvalue = 1.0; tests[idx].need_perm = 0; }
-        return;
-    }
+    const int n1 = ft.n1, n = ft.n1 + ft.n2;
+    const int chunk = (n + FLANK_SPLIT - 1) / FLANK_SPLIT;
+    const int k0 = sp * chunk, k1 = min(n, k0 + chunk);
     double xs1 = 0, xs2 = 0, tss = 0, rn1 = 0, rn2 = 0;
-    for (int k = threadIdx.x; k < n; k += 256) {
+    for (int k = k0 + threadIdx.x; k < k1; k += 256) {
         const double xv = xc[g0 + k], wv = w[g0 + k];
         const double wx = wv * xv;
         tss += wv * (xv * xv);
@@ -1099,23 +1116,36 @@ cbs_flank_prep_kernel(const Node* __restrict__ nodes, FlankTest* __restrict__ te
     xs1 = warp_sum(xs1); xs2 = warp_sum(xs2); tss = warp_sum(tss); rn1 = warp_sum(rn1); rn2 = warp_sum(rn2);
     if (lane == 0) { s_part[0][warp] = xs1; s_part[1][warp] = xs2; s_part[2][warp] = tss; s_part[3][warp] = rn1; s_part[4][warp] = rn2; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        xs1 = xs2 = tss = rn1 = rn2 = 0.0;
-        for (int k = 0; k < 8; ++k) { xs1 += s_part[0][k]; xs2 += s_part[1][k]; tss += s_part[2][k]; rn1 += s_part[3][k]; rn2 += s_part[4][k]; }
-        const double rn = rn1 + rn2;
-        const double xbar = (xs1 + xs2) / rn;
-        tss = tss - rn * (xbar * xbar);
-        int m1, s0;
-        double rm1, odiff;
-        if (n1 <= n2) { m1 = n1; s0 = 0; rm1 = rn1; odiff = fabs(xs1 / rn1 - xbar); }
-        else { m1 = n2; s0 = n1; rm1 = rn2; odiff = fabs(xs2 / rn2 - xbar); }
-        double tstat = rn * rm1 * (odiff * odiff) / (rn - rm1);
-        tstat = tstat / ((tss - tstat) / ((double)n - 2.0));
-        FlankTest* o = &tests[idx];
-        o->m1 = m1; o->s0 = s0; o->rm1 = rm1; o->xbar = xbar; o->ostat = 0.99999 * odiff;
-        if (tstat > 25.0 && m1 >= 10) { o->pvalue = 0.0; o->need_perm = 0; }
-        else { o->pvalue = -1.0; o->need_perm = 1; }
+    if (threadIdx.x < 5) {
+        double v = 0.0;
+        for (int k = 0; k < 8; ++k) v += s_part[threadIdx.x][k];
+        part[((size_t)idx * FLANK_SPLIT + sp) * 5 + threadIdx.x] = v;
     }
+}
+
+__global__ void cbs_flank_prep_kernel(FlankTest* __restrict__ tests, int ntests, const double* __restrict__ part) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ntests) return;
+    FlankTest* o = &tests[idx];
+    const int n1 = o->n1, n2 = o->n2, n = n1 + n2;
+    if (n1 == 1 || n2 == 1) { o->pvalue = 1.0; o->need_perm = 0; return; }
+    double xs1 = 0, xs2 = 0, tss = 0, rn1 = 0, rn2 = 0;
+    for (int sp = 0; sp < FLANK_SPLIT; ++sp) {
+        const double* q = part + ((size_t)idx * FLANK_SPLIT + sp) * 5;
+        xs1 += q[0]; xs2 += q[1]; tss += q[2]; rn1 += q[3]; rn2 += q[4];
+    }
+    const double rn = rn1 + rn2;
+    const double xbar = (xs1 + xs2) / rn;
+    tss = tss - rn * (xbar * xbar);
+    int m1, s0;
+    double rm1, odiff;
+    if (n1 <= n2) { m1 = n1; s0 = 0; rm1 = rn1; odiff = fabs(xs1 / rn1 - xbar); }
+    else { m1 = n2; s0 = n1; rm1 = rn2; odiff = fabs(xs2 / rn2 - xbar); }
+    double tstat = rn * rm1 * (odiff * odiff) / (rn - rm1);
+    tstat = tstat / ((tss - tstat) / ((double)n - 2.0));
+    o->m1 = m1; o->s0 = s0; o->rm1 = rm1; o->xbar = xbar; o->ostat = 0.99999 * odiff;
+    if (tstat > 25.0 && m1 >= 10) { o->pvalue = 0.0; o->need_perm = 0; }
+    else { o->pvalue = -1.0; o->need_perm = 1; }
 }
 
 // one warp per (test, perm): pstat = |sum_{short side} y[pi(k)] rw[k] / rm1 - xbar|
@@ -1289,8 +1319,11 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
     CNVK_CHECK(scratch.alloc(&d_bmin, NB));
     CNVK_CHECK(scratch.alloc(&d_bmax, NB));
     int *d_bimin, *d_bimax;
+    double *d_bcmin, *d_bcmax;
     CNVK_CHECK(scratch.alloc(&d_bimin, NB));
     CNVK_CHECK(scratch.alloc(&d_bimax, NB));
+    CNVK_CHECK(scratch.alloc(&d_bcmin, NB));
+    CNVK_CHECK(scratch.alloc(&d_bcmax, NB));
     if (N > 0) {
         sqrt_kernel<<<div_up(N, 256), 256, 0, stream>>>(d_w, d_rw, N);
         CNVK_LAUNCH_CHECK();
@@ -1376,7 +1409,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         }
         {
             ProfScope ps(PC_CBS_PREP, stream);
-            cbs_prep_kernel<<<nn, PREP_THREADS, PREP_SMEM, stream>>>(d_nodes, d_x, d_w, d_xc, d_y, d_S, d_cw, d_wn, d_bmin, d_bmax, d_bimin, d_bimax, P.min_width, P.hybrid ? P.kmax : 0, P.nmin);
+            cbs_prep_kernel<<<nn, PREP_THREADS, PREP_SMEM, stream>>>(d_nodes, d_x, d_w, d_xc, d_y, d_S, d_cw, d_wn, d_bmin, d_bmax, d_bimin, d_bimax, d_bcmin, d_bcmax, P.min_width, P.hybrid ? P.kmax : 0, P.nmin);
             CNVK_LAUNCH_CHECK();
         }
         {
@@ -1384,7 +1417,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 const int grid = sm_count * 4;
                 if (P.prune & 1) {
                     ProfScope ps(PC_CBS_SEED, stream);
-                    cbs_seed_kernel<<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_S, d_cw, d_bimin, d_bimax, P.min_width);
+                    cbs_seed_kernel<<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_bmin, d_bmax, d_bimin, d_bimax, d_bcmin, d_bcmax, P.min_width);
                     CNVK_LAUNCH_CHECK();
                 }
                 {
@@ -1531,7 +1564,14 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             CNVK_CHECK(fs.alloc(&d_tests, (size_t)nt));
             CNVK_CHECK(cudaMemcpyAsync(d_tests, tests.data(), nt * sizeof(FlankTest), cudaMemcpyHostToDevice, stream));
             ProfScope fscope(PC_CBS_FLANK, stream);
-            cbs_flank_prep_kernel<<<nt, 256, 0, stream>>>(d_nodes, d_tests, nt, d_xc, d_w, P.nperm);
+            double* d_part;
+            CNVK_CHECK(fs.alloc(&d_part, (size_t)nt * FLANK_SPLIT * 5));
+            for (int z0 = 0; z0 < nt; z0 += 32768) {   // grid.x is the test index
+                const int nz = std::min(32768, nt - z0);
+                cbs_flank_part_kernel<<<dim3(nz, FLANK_SPLIT), 256, 0, stream>>>(d_nodes, d_tests + z0, d_xc, d_w, d_part + (size_t)z0 * FLANK_SPLIT * 5);
+                CNVK_LAUNCH_CHECK();
+            }
+            cbs_flank_prep_kernel<<<div_up(nt, 128), 128, 0, stream>>>(d_tests, nt, d_part);
             CNVK_LAUNCH_CHECK();
             CNVK_CHECK(cudaMemcpyAsync(tests.data(), d_tests, nt * sizeof(FlankTest), cudaMemcpyDeviceToHost, stream));
             CNVK_CHECK(cudaStreamSynchronize(stream));

@@ -21,4 +21,4 @@ for method in ("cbs", "haar"):
 import cProfile, pstats, io
 pr = cProfile.Profile(); pr.enable()
 trips = [panel.fix(*c) for c in cols]; cns = panel.segment(trips, "cbs")
-pr.disable(); st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats("cumulative").print_stats(35); print(st.getvalue()[:7000])
+pr.disable(); st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats("tottime").print_stats(45); print(st.getvalue()[:7000])

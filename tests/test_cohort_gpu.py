@@ -107,3 +107,18 @@ def test_cohort_vs_cpu_oracle_pipeline(world, method):
         want_tab = want_tab.sort_values(["chromosome", "start"]).reset_index(drop=True)
         np.testing.assert_array_equal(got["probes"].to_numpy(), want_tab["probes"].to_numpy())
         np.testing.assert_allclose(got["log2"].to_numpy(), want_tab["log2"].to_numpy(), rtol=1e-9, atol=0)
+
+
+def test_cohort_threaded_workers_give_the_same_tables(world):
+    from cnvkit_b200 import cohort
+
+    bins, ref, tabs = world
+    T0, A0, R = tabs[0]
+    panel = cohort.Panel(T0, A0, R)
+    work = [(T, A) for T, A, _ in tabs] * 3
+    one = panel.run(work, method="cbs", batch=2, keep_cnr=True)
+    many = panel.run(work, method="cbs", batch=2, keep_cnr=True, workers=3)
+    assert len(one) == len(many) == len(work)
+    for (c1, s1), (c2, s2) in zip(one, many):
+        assert_same(c1, c2)
+        assert_same(s1, s2)
