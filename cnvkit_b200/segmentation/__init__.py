@@ -238,36 +238,53 @@ def _transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, seg_log2, probes, a
     _lib.call("cnvk_segment_bin_sums_dev", _dev.ptr(d_dep), _dev.ptr(d_w), _dev.ptr(d_lo), _dev.ptr(d_hi), nseg,
               _dev.ptr(d_sw), _dev.ptr(d_sd), _dev.stream())
     seg_weight, seg_depth = d_sw.cpu().numpy(), d_sd.cpu().numpy()
-    genes = _join_genes(data["gene"].to_numpy(), bin_lo, bin_hi, gene_codes)
+    genes = _join_genes(None if gene_codes is not None else data["gene"].to_numpy(), bin_lo, bin_hi, gene_codes)
     return pd.DataFrame({
         "chromosome": seg_chrom, "start": seg_start, "end": seg_end, "gene": genes, "log2": seg_log2,
         "probes": probes, "weight": seg_weight, "depth": seg_depth,
     })
 
 
+class GeneCodes:
+    """Gene column of a bin set, factorised once: codes per bin, kept name parts per code, and -- when
+    every code holds at most one kept name and no name is shared between codes -- a name table that
+    lets a segment's gene list be assembled without per-name Python work."""
+
+    def __init__(self, bin_genes):
+        ignore = set(params.IGNORE_GENE_NAMES + params.ANTITARGET_ALIASES)
+        codes, uniques = pd.factorize(pd.Series(bin_genes, dtype=object), sort=False)
+        self.codes = codes
+        self.parts = [tuple(p for p in u.split(",") if p not in ignore) if isinstance(u, str) else ()
+                      for u in uniques]
+        flat = [p for ps in self.parts for p in ps]
+        self.simple = all(len(ps) <= 1 for ps in self.parts) and len(set(flat)) == len(flat)
+        self.names = np.array([ps[0] if ps else "" for ps in self.parts] + [""], dtype=object)  # [-1] -> ""
+        self.has_name = np.array([bool(ps) for ps in self.parts] + [False])
+
+
 def factorize_genes(bin_genes):
-    """(codes per bin, kept name parts per code) -- depends on the bin set only, so cohorts cache it.
-    A gene field may hold several comma-separated names; placeholder / antitarget names are dropped
-    here once (skgenome/combiners.py:58-94 with params.IGNORE_GENE_NAMES + ANTITARGET_ALIASES)."""
-    ignore = set(params.IGNORE_GENE_NAMES + params.ANTITARGET_ALIASES)
-    codes, uniques = pd.factorize(pd.Series(bin_genes, dtype=object), sort=False)
-    parts = [tuple(p for p in u.split(",") if p not in ignore) if isinstance(u, str) else () for u in uniques]
-    return codes, parts
+    """Gene codes of a bin set (depends on the bins only, so cohorts cache it)."""
+    return GeneCodes(bin_genes)
 
 
 def _join_genes(bin_genes, bin_lo, bin_hi, gene_codes=None):
     """skgenome/combiners.py:58-94 join_strings per segment: ordered-unique gene names of the
     bins, split on ',', minus the ignored placeholder / antitarget names; '-' if none remain."""
-    codes, parts = gene_codes if gene_codes is not None else factorize_genes(bin_genes)
+    gc = gene_codes if gene_codes is not None else GeneCodes(bin_genes)
+    codes = gc.codes
     out = []
     for lo, hi in zip(bin_lo, bin_hi):
         if hi <= lo:
             out.append("-")
             continue
+        u = pd.unique(codes[lo:hi])               # hash-based, keeps first-appearance order
+        if gc.simple:
+            out.append(",".join(gc.names[u[gc.has_name[u]]].tolist()) or "-")
+            continue
         seen = {}
-        for ci in pd.unique(codes[lo:hi]):       # hash-based, keeps first-appearance order
+        for ci in u:
             if ci >= 0:
-                for name in parts[ci]:
+                for name in gc.parts[ci]:
                     seen.setdefault(name, None)
         out.append(",".join(seen) or "-")
     return out
