@@ -25,6 +25,7 @@ class Params(Structure):
         ("ngrid", c_int),
         ("tol", c_double),
         ("seed", c_uint64),
+        ("prune", c_int),
     ]
 
 
@@ -38,8 +39,11 @@ class Stats(Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
-def make_params(alpha=1e-4, nperm=10000, min_width=2, kmax=25, nmin=200, eta=0.05, hybrid=True, seed=0xA5EED):
-    return Params(alpha, nperm, min_width, kmax, nmin, eta, int(hybrid), 100, 1e-6, seed)
+def make_params(alpha=1e-4, nperm=10000, min_width=2, kmax=25, nmin=200, eta=0.05, hybrid=True, seed=0xA5EED,
+                prune=False):
+    """prune=True: block-pruned search for the observed maximum (what DNAcopy's wtmaxo does); same
+    result as the exhaustive default, used for the CPU baseline timings."""
+    return Params(alpha, nperm, min_width, kmax, nmin, eta, int(hybrid), 100, 1e-6, seed, int(prune))
 
 
 _lib = None

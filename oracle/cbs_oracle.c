@@ -55,6 +55,7 @@ typedef struct {
     int ngrid;
     double tol;
     uint64_t seed;
+    int prune; /* 1: block-pruned search for the observed maximum (same result as the exhaustive scan) */
 } cbso_params;
 
 typedef struct {
@@ -366,6 +367,76 @@ static double max_arc_full(const node_t* N, const double* S, int al0, int* bi, i
     return best < 0.0 ? 0.0 : best;
 }
 
+/* Same maximum (and the same (i, j) on ties) as max_arc_full, found the way DNAcopy's wtmaxo does
+ * it: prefix points are grouped in blocks, the statistic of a block pair is bounded from the block
+ * minima / maxima of S and the extreme arc weights, and pairs that cannot reach the current best
+ * are skipped.  Used for the CPU baseline timing; tests check it against the exhaustive scan. */
+static double max_arc_pruned(const node_t* N, const double* S, int al0, int* bi, int* bj, long long* arcs) {
+    enum { B = 32 };
+    const int n = N->n, P = n + 1, nb = (P + B - 1) / B;
+    double* mn = (double*)malloc(sizeof(double) * nb);
+    double* mx = (double*)malloc(sizeof(double) * nb);
+    int* imn = (int*)malloc(sizeof(int) * nb);
+    int* imx = (int*)malloc(sizeof(int) * nb);
+    for (int b = 0; b < nb; ++b) {
+        const int p0 = b * B, p1 = (p0 + B - 1 < n) ? p0 + B - 1 : n;
+        mn[b] = mx[b] = S[p0]; imn[b] = imx[b] = p0;
+        for (int p = p0 + 1; p <= p1; ++p) {
+            if (S[p] < mn[b]) { mn[b] = S[p]; imn[b] = p; }
+            if (S[p] > mx[b]) { mx[b] = S[p]; imx[b] = p; }
+        }
+    }
+    double best = -1.0;
+    int ai = 0x7fffffff, aj = 0x7fffffff;
+#define CBSO_TRY(I, J)                                                                         \
+    do {                                                                                       \
+        const int i_ = (I), j_ = (J);                                                          \
+        const int kw_ = j_ - i_;                                                               \
+        if (kw_ >= al0 && kw_ <= n - al0) {                                                    \
+            const double d_ = S[j_] - S[i_];                                                   \
+            const double c_ = cwp(N, j_) - cwp(N, i_);                                         \
+            const double q_ = (d_ * d_) / (c_ * (N->total - c_));                              \
+            if (q_ > best || (q_ == best && (i_ < ai || (i_ == ai && j_ < aj)))) {            \
+                best = q_; ai = i_; aj = j_;                                                   \
+            }                                                                                  \
+        }                                                                                      \
+    } while (0)
+    /* seed: arcs between block extremes */
+    for (int a = 0; a < nb; ++a)
+        for (int b = a; b < nb; ++b) {
+            int i = imn[a], j = imx[b];
+            if (i > j) { const int t = i; i = j; j = t; }
+            CBSO_TRY(i, j);
+            i = imx[a]; j = imn[b];
+            if (i > j) { const int t = i; i = j; j = t; }
+            CBSO_TRY(i, j);
+        }
+    long long scanned = 0;
+    for (int a = 0; a < nb; ++a) {
+        const int i0 = a * B, i1 = (i0 + B - 1 < n) ? i0 + B - 1 : n;
+        for (int b = a; b < nb; ++b) {
+            const int j0 = b * B, j1 = (j0 + B - 1 < n) ? j0 + B - 1 : n;
+            if (b > a + 1 && best >= 0.0) {
+                const double d1 = fabs(mx[b] - mn[a]), d2 = fabs(mx[a] - mn[b]);
+                const double dm = d1 > d2 ? d1 : d2;
+                const double cmin = cwp(N, j0) - cwp(N, i1), cmax = cwp(N, j1) - cwp(N, i0);
+                const double f1 = cmin * (N->total - cmin), f2 = cmax * (N->total - cmax);
+                const double fm = f1 < f2 ? f1 : f2;
+                if (fm > 0.0 && (dm * dm) / fm * (1.0 + 1e-9) < best) continue;
+            }
+            for (int i = i0; i <= i1; ++i)
+                for (int j = (j0 > i + al0 ? j0 : i + al0); j <= j1; ++j) CBSO_TRY(i, j);
+            scanned += (long long)(i1 - i0 + 1) * (j1 - j0 + 1);
+        }
+    }
+#undef CBSO_TRY
+    if (arcs) *arcs += scanned;
+    free(mn); free(mx); free(imn); free(imx);
+    if (best < 0.0) { *bi = 0; *bj = 0; return 0.0; }
+    *bi = ai; *bj = aj;
+    return best;
+}
+
 static double t2_of(double bss, double tss, int n) {
     if (tss <= bss + 0.0001) tss = bss + 1.0;
     return bss / ((tss - bss) / ((double)n - 2.0));
@@ -469,7 +540,8 @@ static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, co
 
     int ncpt = 0, ai, aj;
     const int al0 = P->min_width;
-    const double bss = max_arc_full(&N, N.S, al0, &ai, &aj, st ? &st->obs_arcs : NULL);
+    const double bss = P->prune ? max_arc_pruned(&N, N.S, al0, &ai, &aj, st ? &st->obs_arcs : NULL)
+                                : max_arc_full(&N, N.S, al0, &ai, &aj, st ? &st->obs_arcs : NULL);
     const double t2 = t2_of(bss, tss, n);
     const double ostat1 = sqrt(t2);
     const double ostat = t2 * 0.99999;

@@ -114,7 +114,8 @@ def arm_offsets(chrom, start, end, min_gap_size=1e5, min_arm_bins=50):
     return np.asarray(cuts, dtype=np.int64)
 
 
-def segment_columns(chrom, start, end, log2, weight, method, threshold=1e-4, skip_outliers=10, nthreads=0):
+def segment_columns(chrom, start, end, log2, weight, method, threshold=1e-4, skip_outliers=10, nthreads=0,
+                    prune=False):
     """Numeric core of do_segmentation: per-arm filters, %.6g quantisation (cbs), the segmenter.
     Returns (seg_arm, seg_lo, seg_hi, seg_mean) with bin ranges into the *filtered* rows, plus the
     filtered row indices."""
@@ -135,7 +136,7 @@ def segment_columns(chrom, start, end, log2, weight, method, threshold=1e-4, ski
 
         xq = np.char.mod("%.6g", x).astype(float)
         wq = np.char.mod("%.6g", w).astype(float)
-        res = OC.segment(xq, wq, foff, OC.make_params(alpha=threshold), nthreads=nthreads)[:4]
+        res = OC.segment(xq, wq, foff, OC.make_params(alpha=threshold, prune=prune), nthreads=nthreads)[:4]
     else:
         from . import haar as OH
 

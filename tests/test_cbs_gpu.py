@@ -170,3 +170,23 @@ def test_tailp_bracket_gives_the_series_decisions(G):
         for u, v in zip(a[:4], b[:4]):
             np.testing.assert_array_equal(u, v)
         compare(G, x, w, off, alpha)
+
+
+def test_full_c3_sample_equals_oracle(G):
+    """BASELINE's full size: the 3 M-bin synthetic WGS sample (48 arms) segmented on the GPU gives the
+    table of the CPU oracle (block-pruned search; equal to its exhaustive scan by
+    tests/test_oracle_pins.py) -- identical breakpoints, means to 1e-9 -- and recovers the planted
+    change-points."""
+    from cnvkit_b200 import synth
+
+    d = synth.wgs_sample()
+    g = G.segment_arms(d["log2"], d["weight"], d["arm_offsets"], alpha=1e-4)
+    o = OC.segment(d["log2"], d["weight"], d["arm_offsets"], OC.make_params(alpha=1e-4, prune=True), nthreads=16)
+    for a, b in zip(g[:3], o[:3]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_allclose(g[3], o[3], rtol=1e-9, atol=0)
+    cuts = set(g[1].tolist()) | set(g[2].tolist())
+    found = sum(1 for lo, hi, step in d["truth"] if (hi - lo) >= 50 and abs(step) >= 0.5
+                and min(abs(c - lo) for c in cuts) <= 5 and min(abs(c - hi) for c in cuts) <= 5)
+    big = sum(1 for lo, hi, step in d["truth"] if (hi - lo) >= 50 and abs(step) >= 0.5)
+    assert found >= 0.95 * big, (found, big)
