@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--bins", type=int, default=3_000_000)
     ap.add_argument("--no-prune", action="store_true", help="exhaustive arc scan (roofline study)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time per reference step")
-    ap.add_argument("--workload", default="wgs", choices=["wgs", "cohort"],
+    ap.add_argument("--workload", default="wgs", choices=["wgs", "cohort", "reference"],
                     help="wgs: C3 (headline, default); cohort: C5 exome cohort fix + CBS sharded by sample")
     ap.add_argument("--samples", type=int, default=1024, help="cohort size for --workload cohort")
     ap.add_argument("--workers", type=int, default=4, help="host threads (one CUDA stream each) per rank, cohort workload")
@@ -459,6 +459,117 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_reference_build(args):
+    """C4: pooled reference from S synthetic normals on the C2 bin set -- .cnn files in, reference table
+    out (do_reference: TSV parse, per-normal bias correction at window fraction 0.1, per-bin Tukey
+    biweight across samples).  Single GPU."""
+    import tempfile
+
+    import pandas as pd
+    import torch
+
+    from cnvkit_b200 import _lib, reference, synth, tabio
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    S = args.samples if args.samples != 1024 else 32
+    bins = synth.exome_bins()
+    rng = np.random.default_rng(0xC4)
+    n = len(bins["start"])
+    effect = rng.normal(0, 0.4, n)
+    t = bins["is_target"]
+    base = pd.DataFrame({"chromosome": bins["chromosome"], "start": bins["start"], "end": bins["end"],
+                         "gene": bins["gene"]})
+    tmp = tempfile.mkdtemp(prefix="cnvk_c4_")
+    tfn, afn, sexes = [], [], {}
+    cols = []
+    for k in range(S):
+        smp = synth.exome_normal(bins, effect, k, male=bool(k % 2))
+        cols.append(smp)
+        df = base.assign(log2=smp["log2"], depth=smp["depth"], gc=bins["gc"], rmask=bins["rmask"])
+        sid = f"N{k:03d}"
+        sexes[sid] = not bool(k % 2)
+        for sel, kind, dest in ((t, "targetcoverage", tfn), (~t, "antitargetcoverage", afn)):
+            path = os.path.join(tmp, f"{sid}.{kind}.cnn")
+            tabio.write(df[sel].reset_index(drop=True), path)
+            dest.append(path)
+    file_bytes = sum(os.path.getsize(f) for f in tfn + afn)
+    if args.impl == "reference":
+        from oracle import np_oracle as O
+        from oracle import pipeline as OP
+
+        cores = len(os.sched_getaffinity(0))
+        idx = np.flatnonzero(t)
+        c0 = time.perf_counter()
+        x = cols[0]["log2"][idx].astype(float)
+        for key in (bins["gc"][idx], bins["rmask"][idx]):
+            x = OP.center_by_window(x, key, 0.1)
+        per_normal = (time.perf_counter() - c0) * (n / len(idx))
+        m = 4000
+        mat = np.stack([c["log2"][:m] for c in cols])
+        c0 = time.perf_counter()
+        for c in range(m):
+            loc = O.biweight_location(mat[:, c])
+            O.biweight_midvariance(mat[:, c], initial=loc)
+        per_bin = (time.perf_counter() - c0) / m
+        total = S * per_normal + 1.5 * n * per_bin      # log2 location+spread, depth location
+        sample = (f"1 normal's window corrections + {m} bins of summarize_info, extrapolated to {S} normals x {n} bins; "
+                  "oracle/np_oracle.py + pandas rolling median, 1 core")
+        print(json.dumps({"impl": "reference", "metric": "normals/s (reference build)", "value": S / total,
+                          "unit": "normals/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": 1e3 * total,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": {"workload": f"C4 reference build, {S} normals x {n} bins"},
+                          "cpu_baseline": {"value": S / total, "unit": "normals/s", "cores": 1, "kind": "port",
+                                           "sample": sample},
+                          "e2e": {"value": S / total, "unit": "normals/s", "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}))
+        return
+    torch.cuda.set_device(0)
+    _lib.load()
+    for _ in range(max(1, min(args.warmup, 2))):
+        reference.do_reference(tfn[:4], afn[:4], sexes=sexes)
+    launches0 = _lib.launch_count()
+    times = []
+    _lib.prof_enable(True)
+    _lib.prof_reset()
+    for _ in range(args.steps):
+        torch.cuda.synchronize()
+        c0 = time.perf_counter()
+        ref = reference.do_reference(tfn, afn, sexes=sexes)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - c0)
+    prof = _lib.prof_get()
+    _lib.prof_enable(False)
+    ms = 1e3 * float(np.mean(times))
+    per_step = {k: v[0] / args.steps for k, v in prof.items() if v[1] > 0}
+    bw_ms = per_step.get("biweight", 0.0)
+    bw_bytes = n * (2 * (S + 1) * 8 + S * 8 + 24)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6540.8))
+    print(json.dumps({
+        "metric": "normals/s (reference build)", "value": S / (ms * 1e-3), "unit": "normals/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C4 reference build: {S} normals x {n} bins ({2 * S} .cnn files, {file_bytes / 1e6:.0f} MB "
+                               f"of TSV), do_reference with GC/RepeatMasker/edge centring at fraction 0.1",
+                   "l2": "every normal's columns are fresh host data; the [S+1, n] matrices exceed L2"},
+        "e2e": {"value": S / (ms * 1e-3), "unit": "normals/s", "h2d_bytes_per_step": int(S * n * 16),
+                "d2h_bytes_per_step": int(n * 24)},
+        "gpu_launches": int((_lib.launch_count() - launches0) / args.steps),
+        "roofline": {"kernel": "biweight_columns_kernel (summarize_info)", "bound": "hbm",
+                     "achieved": bw_bytes / (bw_ms * 1e-3) / 1e9 if bw_ms else None, "peak": hbm, "unit": "GB/s",
+                     "frac": (bw_bytes / (bw_ms * 1e-3) / 1e9 / hbm) if bw_ms else None, "traffic": None,
+                     "algorithmic": "read 2(S+1)+S doubles per bin (log2 twice: location, midvariance; depth once), "
+                                    "write 24 B per bin"},
+        "kernel_ms_per_step": per_step, "rows": int(len(ref)),
+        "note": "e2e includes TSV parsing (native reader) of every file; value == e2e (no resident variant)"}))
+
+
 def run_cohort(args):
     """C5: a cohort of exome tumours fixed against one pooled reference and CBS-segmented, sharded by
     sample over the ranks (strong scaling: the cohort is fixed), .cns rows gathered on rank 0 with NCCL."""
@@ -582,6 +693,8 @@ def main():
     args = parse_args()
     if args.workload == "cohort":
         run_cohort(args)
+    elif args.workload == "reference":
+        run_reference_build(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

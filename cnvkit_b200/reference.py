@@ -20,7 +20,7 @@ import numpy as np
 import pandas as pd
 import torch
 
-from . import _dev, _lib, cnary, genome, params, smoothing
+from . import _dev, _lib, cnary, genome, params, smoothing, tabio
 
 
 def fbase(fname: str) -> str:
@@ -168,25 +168,51 @@ def load_sample_block(filenames, fa_fname, is_haploid_x, diploid_parx_genome, se
     d_perm = _dev.shuffle_permutation(n)
 
     key_cols = d1.loc[:, ("chromosome", "start", "end", "gene")].values
+    # Fast path for files 2..S: when the first file is already in sorted order with no dropped rows,
+    # the other files need only their numeric columns -- the native reader returns them together with
+    # a hash of the coordinate/gene fields, which replaces the row-by-row key comparison
+    # (reference.py:594-598) without building a table.
+    fast_hash = None
+    num_cols = ("log2", "depth") if "depth" in cnarr1 else ("log2",)
+    if len(filenames) > 1:
+        try:
+            raw, h0 = tabio.read_columns(filenames[0], columns=num_cols + ("start", "end"))
+            if (len(raw["log2"]) == n and np.array_equal(raw["log2"], d1["log2"].to_numpy(dtype=np.float64))
+                    and np.array_equal(raw["start"], start.astype(np.float64))
+                    and np.array_equal(raw["end"], end.astype(np.float64))):
+                fast_hash = h0
+        except (KeyError, _lib.CnvkError):
+            fast_hash = None
     rows_logr = [d_flat.clone()]
     rows_depth = []
     for i, fname in enumerate(filenames):
+        sample_id = fbase(fname)
         if i == 0:
-            cn = cnarr1
+            log2 = d1["log2"].to_numpy(dtype=np.float64)
+            depth = d1["depth"].to_numpy(dtype=np.float64) if "depth" in cnarr1 else None
+        elif fast_hash is not None:
+            logging.info("Loading %s", fname)
+            try:
+                raw, h = tabio.read_columns(fname, columns=num_cols)
+            except KeyError:
+                raw, h = None, None
+            if raw is None or h != fast_hash or len(raw["log2"]) != n or np.isnan(raw["log2"]).any():
+                raise RuntimeError(f"{fname} bins do not match those in {filenames[0]}")
+            log2, depth = raw["log2"], raw.get("depth")
         else:
             logging.info("Loading %s", fname)
             cn = _read(fname)
             if not np.array_equal(key_cols, cn.data.loc[:, ("chromosome", "start", "end", "gene")].values):
                 raise RuntimeError(f"{fname} bins do not match those in {filenames[0]}")
-        log2 = cn.data["log2"].to_numpy(dtype=np.float64)
-        depth = cn.data["depth"].to_numpy(dtype=np.float64) if "depth" in cn else None
+            log2 = cn.data["log2"].to_numpy(dtype=np.float64)
+            depth = cn.data["depth"].to_numpy(dtype=np.float64) if "depth" in cn else None
         d_log2 = _dev.up(log2)
         d_depth = _dev.up(depth) if depth is not None else None
         rows_depth.append(d_depth if d_depth is not None else torch.exp2(d_log2))
-        known = sexes.get(cn.sample_id)
+        known = sexes.get(sample_id)
         if known is None:
             logging.warning("Cannot determine sex for sample %s; treating chrX as diploid (female)",
-                            cn.sample_id or "")
+                            sample_id or "")
         is_xx = True if known is None else bool(known)
         skipped = ctypes.c_int32(0)
         _lib.call("cnvk_bias_correct_logr_dev", _dev.ptr(d_log2), _dev.ptr(d_depth), _dev.ptr(d_auto), n,

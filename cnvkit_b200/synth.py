@@ -159,3 +159,21 @@ def exome_tables(bins, ref, sample, sample_id="tumor"):
     reference = CopyNumArray(base.assign(log2=ref["log2"], depth=ref["depth"], gc=bins["gc"], rmask=bins["rmask"],
                                          spread=ref["spread"]), {"sample_id": "reference"})
     return target, anti, reference
+
+
+def exome_normal(bins, bin_effect, seed: int, male: bool = False):
+    """One normal sample on `bins` for the reference build (C4): log2 = bin effect + per-sample GC /
+    RepeatMasker biases of random amplitude + N(0, 0.15); chrX at -1 and chrY present for males."""
+    rng = np.random.default_rng([0xC4, seed])
+    n = len(bins["start"])
+    gc_b = rng.uniform(0.1, 0.4) * (1.0 - ((bins["gc"] - 0.5) / 0.3) ** 2)
+    rm_b = rng.uniform(-0.2, 0.2) * bins["rmask"]
+    log2 = bin_effect + gc_b + rm_b + rng.normal(0, 0.15, n)
+    chrom = bins["chromosome"]
+    if male:
+        log2[chrom == "chrX"] -= 1.0
+        log2[chrom == "chrY"] -= 1.0
+    else:
+        log2[chrom == "chrY"] = -18.0
+    log2 = round_sig6(log2)
+    return dict(log2=log2, depth=round_sig6(100.0 * np.exp2(log2)))
