@@ -41,7 +41,7 @@ namespace cnvk {
 static const int CBS_BLK = 256;           // points per bound block / j-block
 static const int CBS_IW = 4;              // arc starts per thread
 static const int CBS_IBLK = CBS_BLK * CBS_IW;
-static const size_t PREP_SMEM = (size_t)2 * (8192 + 1024) * sizeof(double);   // two padded 8192-term tiles
+static const size_t PREP_SMEM = (size_t)2 * (2048 + 256) * sizeof(double);   // two padded 2048-term tiles
 static const int HYB_TP = 2048;           // arc starts per CTA in the hybrid permutation kernel
 static const int HYB_KMAX = 64;           // max supported kmax
 static const int EXACT_NMAX = 256;        // max supported nmin
@@ -76,21 +76,31 @@ __device__ __forceinline__ double pt(const double* a, int lo, int i) {
 // Sums of R's changepoints() for weighted data, and how they are evaluated here:
 //   * sum(w), sum(x*w), sum(w*xc^2) are R-level sum() calls -- R accumulates them in 80-bit long
 //     double, i.e. they are (to within an ulp) the correctly rounded exact sums.  They are
-//     double-double (compensated) reductions over all threads: the rounded result does not depend
-//     on the order of accumulation.
+//     double-double (compensated) reductions: the rounded result does not depend on the order.
 //   * the prefix sums S_i = sum_{l<=i} xc_l w_l (DNAcopy's partial sums) and cumsum(w) are a
 //     BLOCKED FP64 prefix sum with one fixed, documented association (oracle/cbs_oracle.c
 //     `blocked_prefix` replays it operation by operation, so GPU and oracle agree bit for bit):
-//       tile   = 8192 consecutive terms; thread j of 1024 owns terms 8j..8j+7
+//       tile   = 2048 consecutive terms; thread j of 256 owns terms 8j..8j+7
 //       p[j,e] = left-to-right running sum of the thread's terms          (8 dependent adds)
 //       A[j]   = Kogge-Stone inclusive scan of the thread totals p[j,7] inside each warp
 //                (steps 1,2,4,8,16: A[l] += A[l-o] for lanes l >= o), E[j] = A[j-1] (0 for lane 0)
 //       X[w]   = W[0] + W[1] + ... + W[w-1] left to right over the warp totals W[w] = A[32w+31]
-//       out    = ((carry + X[w]) + E[j]) + p[j,e];   carry = out of the tile's last term
+//       local  = (X[w] + E[j]) + p[j,e];   T = local of the tile's last slot (missing terms are 0.0)
+//       C[k]   = T[0] + T[1] + ... + T[k-1] left to right over the node's tiles (C[0] = 0)
+//       out    = C[k] + local
 //     It differs from a plain left-to-right sum by rounding only (its error growth is smaller).
-static const int PREP_THREADS = 1024;
+// A node is cut into tiles of 2048 prefix POINTS (point i = S_i, i = 0..n; point i > 0 is term i-1)
+// and every tile is one CTA, so the largest arm no longer sits on a single SM:
+//   sums   (tile)  : min / max of x, double-double partials of sum w and sum x*w
+//   scan   (tile)  : node totals from the partials -> avg; centred data, tile-local prefix scan, tile
+//                    totals, double-double partial of sum w*xc^2
+//   finish (tile)  : carry C[k] from the tile totals, final S and cw, per-256-point block min / max
+//                    (+ arg, + cw at the arg), partial minimum for getmncwt
+//   node   (node)  : tss, total, delta, reset of the running best
+static const int PREP_THREADS = 256;
 static const int PREP_E = 8;                            // terms per thread
-static const int PREP_TILE = PREP_THREADS * PREP_E;     // 8192 terms per tile
+static const int PREP_TILE = PREP_THREADS * PREP_E;     // 2048 terms / points per tile
+static const int PREP_HALO = HYB_KMAX + 2;              // getmncwt looks kmax+1 points ahead
 __host__ __device__ __forceinline__ int prep_pad(int k) { return k + (k >> 3); }  // bank-conflict padding
 
 // double-double accumulator: hi + lo carries the running sum to ~2^-104 relative
@@ -117,45 +127,52 @@ __device__ __forceinline__ DD dd_warp_sum(DD a) {
     }
     return a;
 }
-// CTA-wide sum of per-thread double-doubles, rounded to double once; result valid in thread 0
-__device__ __forceinline__ double dd_block_sum(DD a, double* s_hi, double* s_lo) {
+// CTA-wide double-double sum (not rounded); result valid in thread 0
+__device__ __forceinline__ DD dd_block_sum(DD a, double* s_hi, double* s_lo) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     a = dd_warp_sum(a);
     if (lane == 0) { s_hi[warp] = a.hi; s_lo[warp] = a.lo; }
     __syncthreads();
-    double r = 0.0;
+    DD t = {0.0, 0.0};
     if (threadIdx.x == 0) {
-        DD t = {s_hi[0], s_lo[0]};
+        t.hi = s_hi[0]; t.lo = s_lo[0];
         for (int k = 1; k < PREP_THREADS / 32; ++k) dd_merge(t, s_hi[k], s_lo[k]);
-        r = __dadd_rn(t.hi, t.lo);
     }
     __syncthreads();
-    return r;
+    return t;
+}
+
+struct TileSums {      // per tile, written by the sums kernel
+    double mn, mx, sw_hi, sw_lo, swx_hi, swx_lo;
+};
+struct TileScan {      // per tile, written by the scan kernel
+    double Tw, Ts, tss_hi, tss_lo, dmin, pad;
+};
+
+// tile -> (node, tile index inside the node); ptile_off[a] = first tile of node a
+__device__ __forceinline__ void decode_ptile(const int* __restrict__ ptile_off, int nnodes, int tile, int& a, int& k) {
+    int lo_ = 0, hi_ = nnodes;
+    while (hi_ - lo_ > 1) {
+        const int m = (lo_ + hi_) >> 1;
+        if (ptile_off[m] <= tile) lo_ = m; else hi_ = m;
+    }
+    a = lo_;
+    k = tile - ptile_off[a];
 }
 
 __global__ void __launch_bounds__(PREP_THREADS)
-cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const double* __restrict__ w,
-                double* __restrict__ xc, double* __restrict__ y, double* __restrict__ S,
-                double* __restrict__ cw, double* __restrict__ wn, double* __restrict__ blk_min,
-                double* __restrict__ blk_max, int* __restrict__ blk_imin, int* __restrict__ blk_imax,
-                double* __restrict__ blk_cmin, double* __restrict__ blk_cmax, int al0, int hk, int nmin) {
-    extern __shared__ __align__(16) double s_dyn[];      // [2 arrays][padded tile]
-    __shared__ double s_red[64];
-    __shared__ int s_redi[64];
-    __shared__ double s_scalar[8];
-    __shared__ double s_wtot[2][PREP_THREADS / 32];
-    Node nd = nodes[blockIdx.x];
-    const int lo = nd.lo, n = nd.hi - nd.lo;
+cbs_prep_sums_kernel(const Node* __restrict__ nodes, const int* __restrict__ ptile_off, int nnodes,
+                     const double* __restrict__ x, const double* __restrict__ w, TileSums* __restrict__ part) {
+    __shared__ double s_a[32], s_b[32];
+    int a, k;
+    decode_ptile(ptile_off, nnodes, blockIdx.x, a, k);
+    const int lo = nodes[a].lo, n = nodes[a].hi - nodes[a].lo;
+    const int t0 = k * PREP_TILE, m = max(0, min(PREP_TILE, n - t0));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* s_w = s_dyn;
-    double* s_s = s_dyn + (PREP_TILE + PREP_TILE / 8);
-
-    // range check: isTRUE(all.equal(diff(range(x)), 0)) -> final (changepoints R code);
-    // the same pass accumulates sum(w) and sum(x*w)
     double mn = INFINITY, mx = -INFINITY;
     DD a_w = {0.0, 0.0}, a_wx = {0.0, 0.0};
-    for (int k = tid; k < n; k += PREP_THREADS) {
-        const double v = x[lo + k], wv = w[lo + k];
+    for (int r = tid; r < m; r += PREP_THREADS) {
+        const double v = x[lo + t0 + r], wv = w[lo + t0 + r];
         mn = fmin(mn, v);
         mx = fmax(mx, v);
         dd_add(a_w, wv);
@@ -166,138 +183,206 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
         mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    if (lane == 0) { s_red[warp] = mn; s_red[32 + warp] = mx; }
+    if (lane == 0) { s_a[warp] = mn; s_b[warp] = mx; }
     __syncthreads();
+    if (tid == 0)
+        for (int q = 1; q < PREP_THREADS / 32; ++q) { mn = fmin(mn, s_a[q]); mx = fmax(mx, s_b[q]); }
+    __syncthreads();
+    const DD sw = dd_block_sum(a_w, s_a, s_b);
+    const DD swx = dd_block_sum(a_wx, s_a, s_b);
     if (tid == 0) {
-        for (int k = 1; k < PREP_THREADS / 32; ++k) { mn = fmin(mn, s_red[k]); mx = fmax(mx, s_red[32 + k]); }
-        s_scalar[0] = mx - mn;
+        TileSums o;
+        o.mn = mn; o.mx = mx; o.sw_hi = sw.hi; o.sw_lo = sw.lo; o.swx_hi = swx.hi; o.swx_lo = swx.lo;
+        part[blockIdx.x] = o;
+    }
+}
+
+// node totals from the tile partials, in tile order (every CTA of the node computes the same values)
+__device__ __forceinline__ void node_totals(const TileSums* __restrict__ part, int ntiles, double& range,
+                                            double& sw, double& swx) {
+    double mn = INFINITY, mx = -INFINITY;
+    DD a = {0.0, 0.0}, b = {0.0, 0.0};
+    for (int t = 0; t < ntiles; ++t) {
+        const TileSums p = part[t];
+        mn = fmin(mn, p.mn);
+        mx = fmax(mx, p.mx);
+        if (t == 0) { a.hi = p.sw_hi; a.lo = p.sw_lo; b.hi = p.swx_hi; b.lo = p.swx_lo; }
+        else { dd_merge(a, p.sw_hi, p.sw_lo); dd_merge(b, p.swx_hi, p.swx_lo); }
+    }
+    range = mx - mn;
+    sw = __dadd_rn(a.hi, a.lo);
+    swx = __dadd_rn(b.hi, b.lo);
+}
+
+__global__ void __launch_bounds__(PREP_THREADS)
+cbs_prep_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_off, int nnodes,
+                     const double* __restrict__ x, const double* __restrict__ w, const TileSums* __restrict__ part1,
+                     double* __restrict__ xc, double* __restrict__ y, double* __restrict__ wn,
+                     double* __restrict__ Sl, double* __restrict__ cwl, TileScan* __restrict__ part3) {
+    extern __shared__ __align__(16) double s_dyn[];      // [2 arrays][padded tile]
+    __shared__ double s_a[32], s_b[32];
+    __shared__ double s_scalar[4];
+    __shared__ double s_wtot[2][PREP_THREADS / 32];
+    int a, k;
+    decode_ptile(ptile_off, nnodes, blockIdx.x, a, k);
+    const int lo = nodes[a].lo, n = nodes[a].hi - nodes[a].lo;
+    const int ntiles = ptile_off[a + 1] - ptile_off[a];
+    const int t0 = k * PREP_TILE, m = max(0, min(PREP_TILE, n - t0));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* s_w = s_dyn;
+    double* s_s = s_dyn + (PREP_TILE + PREP_TILE / 8);
+    if (tid == 0) {
+        double range, sw, swx;
+        node_totals(part1 + ptile_off[a], ntiles, range, sw, swx);
+        s_scalar[0] = range; s_scalar[1] = sw; s_scalar[2] = swx;
     }
     __syncthreads();
+    // range check: isTRUE(all.equal(diff(range(x)), 0)) -> final (changepoints R code)
     if (s_scalar[0] <= 1.4901161193847656e-08) {
-        if (tid == 0) {
-            nodes[blockIdx.x].flat = 1;
-            nodes[blockIdx.x].best_q = -1.0;
-        }
+        if (tid == 0 && k == 0) { nodes[a].flat = 1; nodes[a].best_q = -1.0; }
         return;
-    }
-    {
-        const double sw_ = dd_block_sum(a_w, s_red, s_red + 32);
-        const double swx_ = dd_block_sum(a_wx, s_red, s_red + 32);
-        if (tid == 0) { s_scalar[1] = sw_; s_scalar[2] = swx_; }
-        __syncthreads();
     }
     const double sw = s_scalar[1], swx = s_scalar[2];
     const double avg = __ddiv_rn(swx, sw), rsw = sqrt(sw);
+    if (tid == 0 && k == 0) { nodes[a].flat = 0; nodes[a].avg = avg; nodes[a].rsw = rsw; }
 
-    // ---- centred data; blocked prefix sums cs = cumsum(w), S = cumsum(xc*w); tss = sum w*xc^2
     DD a_tss = {0.0, 0.0};
-    double carry_w = 0.0, carry_s = 0.0;
-    for (int t0 = 0; t0 < n; t0 += PREP_TILE) {
-        const int m = min(PREP_TILE, n - t0);
-        for (int k = tid; k < PREP_TILE; k += PREP_THREADS) {          // coalesced staging
-            double wv = 0.0, sv = 0.0;
-            if (k < m) {
-                const int g = lo + t0 + k;
-                wv = w[g];
-                const double cc = __dsub_rn(x[g], avg);
-                xc[g] = cc;
-                y[g] = __dmul_rn(cc, sqrt(wv));
-                wn[g] = __ddiv_rn(wv, rsw);
-                sv = __dmul_rn(cc, wv);
-                dd_add(a_tss, __dmul_rn(wv, __dmul_rn(cc, cc)));
-            }
-            s_w[prep_pad(k)] = wv;
-            s_s[prep_pad(k)] = sv;
+    for (int r = tid; r < PREP_TILE; r += PREP_THREADS) {              // coalesced staging
+        double wv = 0.0, sv = 0.0;
+        if (r < m) {
+            const int g = lo + t0 + r;
+            wv = w[g];
+            const double cc = __dsub_rn(x[g], avg);
+            xc[g] = cc;
+            y[g] = __dmul_rn(cc, sqrt(wv));
+            wn[g] = __ddiv_rn(wv, rsw);
+            sv = __dmul_rn(cc, wv);
+            dd_add(a_tss, __dmul_rn(wv, __dmul_rn(cc, cc)));
         }
-        __syncthreads();
-        double pw[PREP_E], ps[PREP_E];
-        {
-            double rw = 0.0, rs = 0.0;
-            const int b0 = prep_pad(PREP_E * tid);                     // 8 consecutive padded slots
-#pragma unroll
-            for (int e = 0; e < PREP_E; ++e) {
-                const double vw = s_w[b0 + e], vs = s_s[b0 + e];
-                rw = e ? __dadd_rn(rw, vw) : vw;
-                rs = e ? __dadd_rn(rs, vs) : vs;
-                pw[e] = rw;
-                ps[e] = rs;
-            }
-        }
-        double Aw = pw[PREP_E - 1], As = ps[PREP_E - 1];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {                              // Kogge-Stone inclusive warp scan
-            const double tw = __shfl_up_sync(0xffffffffu, Aw, o), ts = __shfl_up_sync(0xffffffffu, As, o);
-            if (lane >= o) { Aw = __dadd_rn(Aw, tw); As = __dadd_rn(As, ts); }
-        }
-        double Ew = __shfl_up_sync(0xffffffffu, Aw, 1), Es = __shfl_up_sync(0xffffffffu, As, 1);
-        if (lane == 0) { Ew = 0.0; Es = 0.0; }
-        if (lane == 31) { s_wtot[0][warp] = Aw; s_wtot[1][warp] = As; }
-        __syncthreads();
-        double Xw = 0.0, Xs = 0.0;
-        for (int k = 0; k < warp; ++k) {
-            Xw = k ? __dadd_rn(Xw, s_wtot[0][k]) : s_wtot[0][0];
-            Xs = k ? __dadd_rn(Xs, s_wtot[1][k]) : s_wtot[1][0];
-        }
-        const double bw_ = __dadd_rn(__dadd_rn(carry_w, Xw), Ew), bs_ = __dadd_rn(__dadd_rn(carry_s, Xs), Es);
-        {
-            const int b0 = prep_pad(PREP_E * tid);
-#pragma unroll
-            for (int e = 0; e < PREP_E; ++e) {
-                s_w[b0 + e] = __dadd_rn(bw_, pw[e]);
-                s_s[b0 + e] = __dadd_rn(bs_, ps[e]);
-            }
-        }
-        __syncthreads();
-        for (int k = tid; k < m; k += PREP_THREADS) {                   // coalesced write-back
-            const int g = lo + t0 + k;
-            cw[g] = __ddiv_rn(s_w[prep_pad(k)], rsw);
-            S[g] = s_s[prep_pad(k)];
-        }
-        carry_w = s_w[prep_pad(PREP_TILE - 1)];
-        carry_s = s_s[prep_pad(PREP_TILE - 1)];
-        __syncthreads();
+        s_w[prep_pad(r)] = wv;
+        s_s[prep_pad(r)] = sv;
     }
+    __syncthreads();
+    double pw[PREP_E], ps[PREP_E];
     {
-        const double tss_ = dd_block_sum(a_tss, s_red, s_red + 32);
-        if (tid == 0) s_scalar[3] = tss_;
-        __syncthreads();
-    }
-    const double total = cw[lo + n - 1];
-
-    // DNAcopy getmncwt: the tail approximation's delta for weighted data is the lightest circular
-    // arc of hk+1 consecutive probes over the total weight (min is order-free, hence exact)
-    if (hk > 0 && n > nmin) {
-        const int jw = hk + 1;
-        double dmin = INFINITY;
-        for (int i = tid; i <= n - jw; i += PREP_THREADS)
-            dmin = fmin(dmin, __dsub_rn(pt(cw, lo, i + jw), pt(cw, lo, i)));
-        for (int i = 1 + tid; i <= jw; i += PREP_THREADS)
-            dmin = fmin(dmin, __dadd_rn(__dsub_rn(total, pt(cw, lo, n - jw + i)), pt(cw, lo, i)));
+        double rw = 0.0, rs = 0.0;
+        const int b0 = prep_pad(PREP_E * tid);                         // 8 consecutive padded slots
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-        __syncthreads();
-        if (lane == 0) s_red[warp] = dmin;
-        __syncthreads();
-        if (tid == 0) {
-            for (int k = 1; k < PREP_THREADS / 32; ++k) dmin = fmin(dmin, s_red[k]);
-            s_scalar[4] = __ddiv_rn(dmin, total);
+        for (int e = 0; e < PREP_E; ++e) {
+            const double vw = s_w[b0 + e], vs = s_s[b0 + e];
+            rw = e ? __dadd_rn(rw, vw) : vw;
+            rs = e ? __dadd_rn(rs, vs) : vs;
+            pw[e] = rw;
+            ps[e] = rs;
         }
-        __syncthreads();
     }
+    double Aw = pw[PREP_E - 1], As = ps[PREP_E - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {                                  // Kogge-Stone inclusive warp scan
+        const double tw = __shfl_up_sync(0xffffffffu, Aw, o), ts = __shfl_up_sync(0xffffffffu, As, o);
+        if (lane >= o) { Aw = __dadd_rn(Aw, tw); As = __dadd_rn(As, ts); }
+    }
+    double Ew = __shfl_up_sync(0xffffffffu, Aw, 1), Es = __shfl_up_sync(0xffffffffu, As, 1);
+    if (lane == 0) { Ew = 0.0; Es = 0.0; }
+    if (lane == 31) { s_wtot[0][warp] = Aw; s_wtot[1][warp] = As; }
+    __syncthreads();
+    double Xw = 0.0, Xs = 0.0;
+    for (int q = 0; q < warp; ++q) {
+        Xw = q ? __dadd_rn(Xw, s_wtot[0][q]) : s_wtot[0][0];
+        Xs = q ? __dadd_rn(Xs, s_wtot[1][q]) : s_wtot[1][0];
+    }
+    const double bw_ = __dadd_rn(Xw, Ew), bs_ = __dadd_rn(Xs, Es);
+    {
+        const int b0 = prep_pad(PREP_E * tid);
+#pragma unroll
+        for (int e = 0; e < PREP_E; ++e) {
+            s_w[b0 + e] = __dadd_rn(bw_, pw[e]);
+            s_s[b0 + e] = __dadd_rn(bs_, ps[e]);
+        }
+    }
+    __syncthreads();
+    for (int r = tid; r < m; r += PREP_THREADS) {                       // coalesced write-back of the locals
+        const int g = lo + t0 + r;
+        cwl[g] = s_w[prep_pad(r)];
+        Sl[g] = s_s[prep_pad(r)];
+    }
+    const double Tw = s_w[prep_pad(PREP_TILE - 1)], Ts = s_s[prep_pad(PREP_TILE - 1)];
+    const DD tss = dd_block_sum(a_tss, s_a, s_b);
+    if (tid == 0) {
+        TileScan o;
+        o.Tw = Tw; o.Ts = Ts; o.tss_hi = tss.hi; o.tss_lo = tss.lo; o.dmin = INFINITY; o.pad = 0.0;
+        part3[blockIdx.x] = o;
+    }
+}
 
-    // per-block min/max of the prefix points S_0..S_n and the global argmin/argmax (seed arc)
-    const int nb = (n + 1 + CBS_BLK - 1) / CBS_BLK;
-    double gmin = INFINITY, gmax = -INFINITY;
-    int imin = 0, imax = 0;
-    for (int b = warp; b < nb; b += PREP_THREADS / 32) {
+__global__ void __launch_bounds__(PREP_THREADS)
+cbs_prep_finish_kernel(const Node* __restrict__ nodes, const int* __restrict__ ptile_off, int nnodes,
+                       const double* __restrict__ Sl, const double* __restrict__ cwl, TileScan* __restrict__ part3,
+                       double* __restrict__ S, double* __restrict__ cw, double* __restrict__ blk_min,
+                       double* __restrict__ blk_max, int* __restrict__ blk_imin, int* __restrict__ blk_imax,
+                       double* __restrict__ blk_cmin, double* __restrict__ blk_cmax, int hk, int nmin) {
+    __shared__ double pS[PREP_TILE];
+    __shared__ double pC[PREP_TILE + PREP_HALO];
+    __shared__ double s_carry[4];
+    __shared__ double s_red[8];
+    int a, k;
+    decode_ptile(ptile_off, nnodes, blockIdx.x, a, k);
+    const Node* nd = &nodes[a];
+    if (nd->flat) return;
+    const int lo = nd->lo, n = nd->hi - nd->lo, boff = nd->blk_off;
+    const int ntiles = ptile_off[a + 1] - ptile_off[a];
+    const double rsw = nd->rsw;
+    const int t0 = k * PREP_TILE, m = max(0, min(PREP_TILE, n - t0));
+    const int npts = min(PREP_TILE, n + 1 - t0);                         // points t0 .. t0+npts-1 (<= n)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        // C[k] = T[0] + ... + T[k-1], left to right; C[k+1] for the halo
+        const TileScan* ts = part3 + ptile_off[a];
+        double Cw = 0.0, Cs = 0.0;
+        for (int t = 0; t < k; ++t) {
+            Cw = t ? __dadd_rn(Cw, ts[t].Tw) : ts[0].Tw;
+            Cs = t ? __dadd_rn(Cs, ts[t].Ts) : ts[0].Ts;
+        }
+        s_carry[0] = Cw; s_carry[1] = Cs;
+        s_carry[2] = k ? __dadd_rn(Cw, ts[k].Tw) : ts[0].Tw;           // C[k+1]
+    }
+    __syncthreads();
+    const double Cw = s_carry[0], Cs = s_carry[1], Cw1 = s_carry[2];
+    if (tid == 0) {                                                      // the tile's first point is the carry
+        pS[0] = k ? Cs : 0.0;
+        pC[0] = k ? __ddiv_rn(Cw, rsw) : 0.0;
+    }
+    for (int r = tid; r < m; r += PREP_THREADS) {
+        const int g = lo + t0 + r;
+        // tile 0 has C = 0: 0 + local = local exactly, as the oracle computes it
+        const double vS = k ? __dadd_rn(Cs, Sl[g]) : Sl[g];
+        const double vC = __ddiv_rn(k ? __dadd_rn(Cw, cwl[g]) : cwl[g], rsw);
+        S[g] = vS;
+        cw[g] = vC;
+        if (r + 1 < PREP_TILE) pS[r + 1] = vS;
+        pC[r + 1] = vC;                                                  // slot PREP_TILE = first halo point
+    }
+    // halo for getmncwt: cw at points t0+PREP_TILE+1 .. (terms of the next tile, carried by C[k+1])
+    const bool want_delta = hk > 0 && n > nmin;
+    const int jw = hk + 1;
+    if (want_delta) {
+        for (int h = tid; h < jw; h += PREP_THREADS) {
+            const int p = t0 + PREP_TILE + 1 + h;                        // point index; its term is p-1
+            if (p <= n) pC[PREP_TILE + 1 + h] = __ddiv_rn(__dadd_rn(Cw1, cwl[lo + p - 1]), rsw);
+        }
+    }
+    __syncthreads();
+    // per-256-point block min / max of S with arg (ties -> smallest index) and cw at the arg
+    if (warp * CBS_BLK < npts) {
+        const int b = (t0 / CBS_BLK) + warp;
         double bmn = INFINITY, bmx = -INFINITY;
         int bimn = 0, bimx = 0;
-        for (int k = lane; k < CBS_BLK; k += 32) {
-            const int i = b * CBS_BLK + k;
-            if (i <= n) {
-                const double v = pt(S, lo, i);
-                if (v < bmn) { bmn = v; bimn = i; }
-                if (v > bmx) { bmx = v; bimx = i; }
+        for (int q = lane; q < CBS_BLK; q += 32) {
+            const int lp = warp * CBS_BLK + q;
+            if (lp < npts) {
+                const double v = pS[lp];
+                if (v < bmn) { bmn = v; bimn = lp; }
+                if (v > bmx) { bmx = v; bimx = lp; }
             }
         }
 #pragma unroll
@@ -310,48 +395,100 @@ cbs_prep_kernel(Node* __restrict__ nodes, const double* __restrict__ x, const do
             if (omx > bmx || (omx == bmx && oimx < bimx)) { bmx = omx; bimx = oimx; }
         }
         if (lane == 0) {
-            blk_min[nd.blk_off + b] = bmn;
-            blk_max[nd.blk_off + b] = bmx;
-            blk_imin[nd.blk_off + b] = bimn;
-            blk_imax[nd.blk_off + b] = bimx;
-            blk_cmin[nd.blk_off + b] = pt(cw, lo, bimn);   // cw at the extreme points: the seed kernel
-            blk_cmax[nd.blk_off + b] = pt(cw, lo, bimx);   // then needs no scattered load
+            blk_min[boff + b] = bmn;
+            blk_max[boff + b] = bmx;
+            blk_imin[boff + b] = t0 + bimn;
+            blk_imax[boff + b] = t0 + bimx;
+            blk_cmin[boff + b] = pC[bimn];     // cw at the extreme points: the seed kernel then needs
+            blk_cmax[boff + b] = pC[bimx];     // no scattered load
         }
-        if (bmn < gmin) { gmin = bmn; imin = bimn; }
-        if (bmx > gmax) { gmax = bmx; imax = bimx; }
+    }
+    // DNAcopy getmncwt, linear arcs starting in this tile: min over i of cw(i+jw) - cw(i)
+    if (want_delta) {
+        double dmin = INFINITY;
+        for (int q = tid; q < npts; q += PREP_THREADS) {
+            const int i = t0 + q;
+            if (i + jw <= n) dmin = fmin(dmin, __dsub_rn(pC[q + jw], pC[q]));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        if (lane == 0) s_red[warp] = dmin;
+        __syncthreads();
+        if (tid == 0) {
+            for (int q = 1; q < PREP_THREADS / 32; ++q) dmin = fmin(dmin, s_red[q]);
+            part3[blockIdx.x].dmin = dmin;
+        }
+    }
+    (void)ntiles;
+}
+
+// one warp per node: tss, total, delta (linear partials + the wrap-around arcs), reset of the best
+__global__ void __launch_bounds__(128)
+cbs_prep_node_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_off, int nnodes,
+                     const TileScan* __restrict__ part3, const double* __restrict__ cw,
+                     const double* __restrict__ blk_min, const double* __restrict__ blk_max,
+                     const int* __restrict__ blk_imin, const int* __restrict__ blk_imax,
+                     const double* __restrict__ blk_cmin, const double* __restrict__ blk_cmax, int al0, int hk,
+                     int nmin) {
+    const int a = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (a >= nnodes) return;
+    Node* nd = &nodes[a];
+    if (nd->flat) return;
+    const int lo = nd->lo, n = nd->hi - nd->lo;
+    const int ntiles = ptile_off[a + 1] - ptile_off[a];
+    const TileScan* ts = part3 + ptile_off[a];
+    const double total = cw[lo + n - 1];
+    double delta = 0.0;
+    if (hk > 0 && n > nmin) {
+        const int jw = hk + 1;
+        double dmin = INFINITY;
+        for (int t = lane; t < ntiles; t += 32) dmin = fmin(dmin, ts[t].dmin);
+        for (int i = 1 + lane; i <= jw; i += 32)
+            dmin = fmin(dmin, __dadd_rn(__dsub_rn(total, pt(cw, lo, n - jw + i)), pt(cw, lo, i)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        delta = __ddiv_rn(dmin, total);
+    }
+    // seed arc: from the global argmin of S to its global argmax (a real arc, scored exactly) -- gives
+    // the seed kernel's CTAs a running best to filter against before they take the node's lock
+    const int nb = (n + 1 + CBS_BLK - 1) / CBS_BLK, boff = nd->blk_off;
+    double gmn = INFINITY, gmx = -INFINITY, cmn = 0.0, cmx = 0.0;
+    int imn = 0x7fffffff, imx = 0x7fffffff;
+    for (int b = lane; b < nb; b += 32) {
+        const double vmn = blk_min[boff + b], vmx = blk_max[boff + b];
+        if (vmn < gmn) { gmn = vmn; imn = blk_imin[boff + b]; cmn = blk_cmin[boff + b]; }
+        if (vmx > gmx) { gmx = vmx; imx = blk_imax[boff + b]; cmx = blk_cmax[boff + b]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double omn = __shfl_xor_sync(0xffffffffu, gmn, o), ocmn = __shfl_xor_sync(0xffffffffu, cmn, o);
+        const int oimn = __shfl_xor_sync(0xffffffffu, imn, o);
+        const double omx = __shfl_xor_sync(0xffffffffu, gmx, o), ocmx = __shfl_xor_sync(0xffffffffu, cmx, o);
+        const int oimx = __shfl_xor_sync(0xffffffffu, imx, o);
+        if (omn < gmn || (omn == gmn && oimn < imn)) { gmn = omn; imn = oimn; cmn = ocmn; }
+        if (omx > gmx || (omx == gmx && oimx < imx)) { gmx = omx; imx = oimx; cmx = ocmx; }
     }
     if (lane == 0) {
-        s_red[warp] = gmin; s_redi[warp] = imin;
-        s_red[32 + warp] = gmax; s_redi[32 + warp] = imax;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int k = 1; k < PREP_THREADS / 32; ++k) {
-            if (s_red[k] < gmin) { gmin = s_red[k]; imin = s_redi[k]; }
-            if (s_red[32 + k] > gmax) { gmax = s_red[32 + k]; imax = s_redi[32 + k]; }
-        }
-        Node* out = &nodes[blockIdx.x];
-        out->flat = 0;
-        out->avg = avg;
-        out->tss = s_scalar[3];
-        out->rsw = rsw;
-        out->total = total;
-        out->delta = (hk > 0 && n > nmin) ? s_scalar[4] : 0.0;
-        out->lock = 0;
-        // seed arc
-        const int i = min(imin, imax), j = max(imin, imax);
+        DD t = {ts[0].tss_hi, ts[0].tss_lo};
+        for (int q = 1; q < ntiles; ++q) dd_merge(t, ts[q].tss_hi, ts[q].tss_lo);
+        nd->tss = __dadd_rn(t.hi, t.lo);
+        nd->total = total;
+        nd->delta = delta;
+        nd->lock = 0;
         double q = -1.0;
         int qi = 0x7fffffff, qj = 0x7fffffff;
+        const bool fwd = imn < imx;
+        const int i = fwd ? imn : imx, j = fwd ? imx : imn;
         if (j - i >= al0 && j - i <= n - al0) {
-            const double d = __dsub_rn(pt(S, lo, j), pt(S, lo, i));
-            const double c = __dsub_rn(pt(cw, lo, j), pt(cw, lo, i));
+            const double d = fwd ? __dsub_rn(gmx, gmn) : __dsub_rn(gmn, gmx);          // S_j - S_i
+            const double c = fwd ? __dsub_rn(cmx, cmn) : __dsub_rn(cmn, cmx);          // cw_j - cw_i
             const double den = __dmul_rn(c, __dsub_rn(total, c));
             q = __ddiv_rn(__dmul_rn(d, d), den);
             qi = i; qj = j;
         }
-        out->best_q = q;
-        out->best_i = qi;
-        out->best_j = qj;
+        nd->best_q = q;
+        nd->best_i = qi;
+        nd->best_j = qj;
     }
 }
 
@@ -1302,13 +1439,12 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         CNVK_CHECK(cudaGetDevice(&dev));
         CNVK_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    CNVK_CHECK(cudaFuncSetAttribute(cbs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM));
     const int max_ones = (int)std::floor((double)P.nperm * P.alpha) + 1;
     std::vector<int> sbdry;
     cbs_getbdry(P.eta, P.nperm, max_ones, sbdry);
 
     Scratch scratch(stream);
-    double *d_rw, *d_xc, *d_y, *d_S, *d_cw, *d_wn, *d_bmin, *d_bmax;
+    double *d_rw, *d_xc, *d_y, *d_S, *d_cw, *d_wn, *d_bmin, *d_bmax, *d_Sl, *d_cwl;
     const size_t NB = (size_t)(N / CBS_BLK) + 2 * (size_t)n_arms + 2 * (size_t)N / 4 + 16;  // >= sum ceil((n+1)/256)
     CNVK_CHECK(scratch.alloc(&d_rw, (size_t)N));
     CNVK_CHECK(scratch.alloc(&d_xc, (size_t)N));
@@ -1316,6 +1452,8 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
     CNVK_CHECK(scratch.alloc(&d_S, (size_t)N));
     CNVK_CHECK(scratch.alloc(&d_cw, (size_t)N));
     CNVK_CHECK(scratch.alloc(&d_wn, (size_t)N));
+    CNVK_CHECK(scratch.alloc(&d_Sl, (size_t)N));    // tile-local prefix sums (before the carries)
+    CNVK_CHECK(scratch.alloc(&d_cwl, (size_t)N));
     CNVK_CHECK(scratch.alloc(&d_bmin, NB));
     CNVK_CHECK(scratch.alloc(&d_bmax, NB));
     int *d_bimin, *d_bimax;
@@ -1344,8 +1482,13 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
     }
 
     // growable device buffers for per-level arrays
-    size_t cap_nodes = 0, cap_queue = 0;
+    size_t cap_nodes = 0, cap_queue = 0, cap_ptiles = 0;
     TileRef* d_queue = nullptr;
+    TileSums* d_part1 = nullptr;
+    TileScan* d_part3 = nullptr;
+    int* d_ptile_off = nullptr;
+    std::vector<int> h_ptile_off;
+    struct PartGuard { TileSums*& a; TileScan*& b; cudaStream_t s; ~PartGuard() { if (a) cudaFreeAsync(a, s); if (b) cudaFreeAsync(b, s); } } pguard{d_part1, d_part3, stream};
     Node* d_nodes = nullptr;
     Decision* d_dec = nullptr;
     int* d_tile_off = nullptr;
@@ -1357,7 +1500,8 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         if (d_nodes) cudaFreeAsync(d_nodes, stream);
         if (d_dec) cudaFreeAsync(d_dec, stream);
         if (d_tile_off) cudaFreeAsync(d_tile_off, stream);
-        d_nodes = nullptr; d_dec = nullptr; d_tile_off = nullptr;
+        if (d_ptile_off) cudaFreeAsync(d_ptile_off, stream);
+        d_nodes = nullptr; d_dec = nullptr; d_tile_off = nullptr; d_ptile_off = nullptr;
     };
     struct Guard { decltype(free_level)& f; ~Guard() { f(); } } guard{free_level};
 
@@ -1375,11 +1519,13 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             CNVK_CHECK(cudaMallocAsync((void**)&d_nodes, cap_nodes * sizeof(Node), stream));
             CNVK_CHECK(cudaMallocAsync((void**)&d_dec, cap_nodes * sizeof(Decision), stream));
             CNVK_CHECK(cudaMallocAsync((void**)&d_tile_off, (cap_nodes + 1) * sizeof(int), stream));
+            CNVK_CHECK(cudaMallocAsync((void**)&d_ptile_off, (cap_nodes + 1) * sizeof(int), stream));
             CNVK_CHECK(cudaMallocAsync((void**)&d_terms, cap_nodes * 100 * sizeof(double), stream));
         }
         h_nodes.assign(nn, Node());
         h_tile_off.assign(nn + 1, 0);
-        long long blk_off = 0, tiles = 0, qtiles = 0;
+        h_ptile_off.assign(nn + 1, 0);
+        long long blk_off = 0, tiles = 0, qtiles = 0, ptiles = 0;
         for (int k = 0; k < nn; ++k) {
             Node& nd = h_nodes[k];
             memset(&nd, 0, sizeof(Node));
@@ -1388,6 +1534,8 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             nd.best_q = -1.0; nd.best_i = 0x7fffffff; nd.best_j = 0x7fffffff;
             const int n = nd.hi - nd.lo;
             st.prep_bins += n;
+            h_ptile_off[k] = (int)ptiles;
+            ptiles += (n + 1 + PREP_TILE - 1) / PREP_TILE;     // tiles of 2048 prefix points
             blk_off += (n + 1 + CBS_BLK - 1) / CBS_BLK;
             h_tile_off[k] = (int)tiles;
             long long nt_, nq_;
@@ -1397,9 +1545,19 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             if (tiles >= (1ll << 31) || qtiles >= (1ll << 31)) { set_last_error("cbs_segment: tile count overflow"); return -2; }
         }
         h_tile_off[nn] = (int)tiles;
+        h_ptile_off[nn] = (int)ptiles;
+        if ((size_t)ptiles > cap_ptiles) {
+            if (d_part1) cudaFreeAsync(d_part1, stream);
+            if (d_part3) cudaFreeAsync(d_part3, stream);
+            d_part1 = nullptr; d_part3 = nullptr;
+            cap_ptiles = (size_t)ptiles * 2;
+            CNVK_CHECK(cudaMallocAsync((void**)&d_part1, cap_ptiles * sizeof(TileSums), stream));
+            CNVK_CHECK(cudaMallocAsync((void**)&d_part3, cap_ptiles * sizeof(TileScan), stream));
+        }
         if ((size_t)blk_off > NB) { set_last_error("cbs_segment: block buffer too small"); return -3; }
         CNVK_CHECK(cudaMemcpyAsync(d_nodes, h_nodes.data(), nn * sizeof(Node), cudaMemcpyHostToDevice, stream));
         CNVK_CHECK(cudaMemcpyAsync(d_tile_off, h_tile_off.data(), (nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+        CNVK_CHECK(cudaMemcpyAsync(d_ptile_off, h_ptile_off.data(), (nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
         CNVK_CHECK(cudaMemsetAsync(d_counter, 0, 2 * sizeof(int), stream));
         if ((size_t)qtiles > cap_queue) {
             if (d_queue) cudaFreeAsync(d_queue, stream);
@@ -1409,7 +1567,14 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         }
         {
             ProfScope ps(PC_CBS_PREP, stream);
-            cbs_prep_kernel<<<nn, PREP_THREADS, PREP_SMEM, stream>>>(d_nodes, d_x, d_w, d_xc, d_y, d_S, d_cw, d_wn, d_bmin, d_bmax, d_bimin, d_bimax, d_bcmin, d_bcmax, P.min_width, P.hybrid ? P.kmax : 0, P.nmin);
+            const int hk = P.hybrid ? P.kmax : 0;
+            cbs_prep_sums_kernel<<<(int)ptiles, PREP_THREADS, 0, stream>>>(d_nodes, d_ptile_off, nn, d_x, d_w, d_part1);
+            CNVK_LAUNCH_CHECK();
+            cbs_prep_scan_kernel<<<(int)ptiles, PREP_THREADS, PREP_SMEM, stream>>>(d_nodes, d_ptile_off, nn, d_x, d_w, d_part1, d_xc, d_y, d_wn, d_Sl, d_cwl, d_part3);
+            CNVK_LAUNCH_CHECK();
+            cbs_prep_finish_kernel<<<(int)ptiles, PREP_THREADS, 0, stream>>>(d_nodes, d_ptile_off, nn, d_Sl, d_cwl, d_part3, d_S, d_cw, d_bmin, d_bmax, d_bimin, d_bimax, d_bcmin, d_bcmax, hk, P.nmin);
+            CNVK_LAUNCH_CHECK();
+            cbs_prep_node_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, d_ptile_off, nn, d_part3, d_cw, d_bmin, d_bmax, d_bimin, d_bimax, d_bcmin, d_bcmax, P.min_width, hk, P.nmin);
             CNVK_LAUNCH_CHECK();
         }
         {

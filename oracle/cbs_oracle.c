@@ -263,18 +263,19 @@ static inline void dd_add(dd_t* a, double p) { /* Knuth two-sum; lo collects the
     a->lo += e;
 }
 
-/* Blocked FP64 prefix sum with the fixed association the CUDA prep kernel uses (csrc/cbs.cu):
- * tiles of 8192 terms; "thread" j of 1024 owns terms 8j..8j+7 and sums them left to right; the 1024
- * thread totals are scanned per "warp" of 32 with the Kogge-Stone steps 1,2,4,8,16; warp totals are
- * accumulated left to right; out = ((carry + X[warp]) + E[thread]) + p[thread, e]; the carry into the
- * next tile is the tile's last output (missing terms of a short tile count as 0.0).  Same value as a
- * left-to-right sum up to rounding (smaller error growth); what matters is that both sides do
- * exactly these operations. */
+/* Blocked FP64 prefix sum with the fixed association the CUDA prep kernels use (csrc/cbs.cu):
+ * tiles of 2048 terms; "thread" j of 256 owns terms 8j..8j+7 and sums them left to right (p); the 256
+ * thread totals are scanned per "warp" of 32 with the Kogge-Stone steps 1,2,4,8,16 (A; E = exclusive);
+ * warp totals are accumulated left to right (X); local = (X[warp] + E[thread]) + p[thread, e]; the tile
+ * total T is the local value of the tile's last slot (missing terms of a short tile count as 0.0); the
+ * carry of tile k is C[k] = T[0] + ... + T[k-1] left to right; out = C[k] + local (tile 0: out = local).
+ * Same value as a left-to-right sum up to rounding (smaller error growth); what matters is that both
+ * sides do exactly these operations. */
 static void blocked_prefix(const double* t, int n, double* out) {
-    enum { PE = 8, NT = 1024, TILE = PE * NT };
+    enum { PE = 8, NT = 256, TILE = PE * NT };
     static _Thread_local double p[TILE], A[NT], tmp[32];
     double carry = 0.0;
-    for (int t0 = 0; t0 < n; t0 += TILE) {
+    for (int t0 = 0, tile = 0; t0 < n; t0 += TILE, ++tile) {
         const int m = (n - t0 < TILE) ? n - t0 : TILE;
         for (int j = 0; j < NT; ++j) {
             double r = 0.0;
@@ -291,23 +292,23 @@ static void blocked_prefix(const double* t, int n, double* out) {
                 for (int l = 0; l < 32; ++l) tmp[l] = A[32 * w + l];
                 for (int l = o; l < 32; ++l) A[32 * w + l] = tmp[l] + tmp[l - o];
             }
-        double last = carry;
+        double T = 0.0;
         for (int w = 0; w < NT / 32; ++w) {
             double X = 0.0;
             for (int k = 0; k < w; ++k) X = k ? X + A[32 * k + 31] : A[31];
             for (int l = 0; l < 32; ++l) {
                 const int j = 32 * w + l;
                 const double E = l ? A[j - 1] : 0.0;
-                const double base = (carry + X) + E;
+                const double base = X + E;
                 for (int e = 0; e < PE; ++e) {
                     const int k = PE * j + e;
-                    const double v = base + p[k];
-                    if (k < m) out[t0 + k] = v;
-                    if (k == TILE - 1) last = v;
+                    const double loc = base + p[k];
+                    if (k < m) out[t0 + k] = tile ? carry + loc : loc;
+                    if (k == TILE - 1) T = loc;
                 }
             }
         }
-        carry = last;
+        carry = tile ? carry + T : T;
     }
 }
 
