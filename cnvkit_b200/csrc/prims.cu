@@ -6,6 +6,10 @@
 //   scatter        : warp-striped tile walk; __match_any_sync gives the in-warp stable rank,
 //                    per-warp digit counters + a cross-warp scan give the in-tile stable rank.
 // HBM traffic per pass: keys+vals read twice (hist + scatter) and written once.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 #include "prims.cuh"
 #include "prof.cuh"
 
@@ -191,6 +195,124 @@ digit_scatter_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals,
     }
 }
 
+// Whole sort in ONE cooperative launch for arrays of up to SORT_COOP_MAX_TILES tiles (the sizes of the
+// exome path: 50 k - 1 M keys, where eight passes x five launches were pure launch latency).  Per pass:
+// every CTA histograms its tiles, grid.sync, every CTA derives the global base of its (digit, tile)
+// pairs straight from the counter table (digit totals + the counts of the tiles before it -- no
+// separate scan kernel) and scatters, grid.sync.  Same stable ranking as the multi-launch path.
+static const int SORT_COOP_MAX_TILES = 256;
+
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_sort_coop_kernel(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, long long n, int begin_bit, int end_bit,
+                       u32* __restrict__ counts, int ntiles) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ u32 s_warp_hist[SORT_WARPS][256];
+    __shared__ u32 s_base[256];
+    __shared__ u32 s_scan[32];
+    __shared__ u32 s_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lt_mask = (1u << lane) - 1u;
+    u64* kin = keys_a;
+    u64* kout = keys_b;
+    u32* vin = vals_a;
+    u32* vout = vals_b;
+    for (int shift = begin_bit; shift < end_bit; shift += 8) {
+        // ---- histogram of every tile this CTA owns
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            s_base[threadIdx.x] = 0;
+            __syncthreads();
+            const long long base = (long long)tile * SORT_TILE;
+#pragma unroll 4
+            for (int k = threadIdx.x; k < SORT_TILE; k += SORT_THREADS) {
+                const long long i = base + k;
+                if (i < n) atomicAdd(&s_base[(u32)(kin[i] >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            counts[(size_t)threadIdx.x * ntiles + tile] = s_base[threadIdx.x];
+            __syncthreads();
+        }
+        grid.sync();
+        // ---- scatter
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int d = lane; d < 256; d += 32) s_warp_hist[warp][d] = 0;
+            {
+                // thread d: total of digit d over all tiles and the part that lies in earlier tiles
+                const u32* row = counts + (size_t)threadIdx.x * ntiles;
+                u32 before = 0, total = 0;
+                for (int t = 0; t < ntiles; ++t) {
+                    const u32 c = row[t];
+                    if (t < tile) before += c;
+                    total += c;
+                }
+                const u32 ex = block_exclusive_scan(total, s_scan, &s_total);   // digits before d
+                s_base[threadIdx.x] = ex + before;
+            }
+            __syncthreads();
+            const long long wbase = (long long)tile * SORT_TILE + (long long)warp * (SORT_ITEMS * 32);
+            u64 k[SORT_ITEMS];
+            u32 local[SORT_ITEMS];
+#pragma unroll
+            for (int r = 0; r < SORT_ITEMS; ++r) {
+                const long long i = wbase + r * 32 + lane;
+                const bool ok = i < n;
+                k[r] = ok ? kin[i] : 0ull;
+                const u32 d = ok ? ((u32)(k[r] >> shift) & 255u) : 0xffffffffu;
+                const u32 peers = __match_any_sync(0xffffffffu, d);
+                const int leader = __ffs(peers) - 1;
+                u32 old = 0;
+                if (ok && lane == leader) {
+                    old = s_warp_hist[warp][d];
+                    s_warp_hist[warp][d] = old + __popc(peers);
+                }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                local[r] = old + __popc(peers & lt_mask);
+                __syncwarp();
+            }
+            __syncthreads();
+            {
+                const int d = threadIdx.x;
+                u32 run = s_base[d];
+#pragma unroll
+                for (int w = 0; w < SORT_WARPS; ++w) {
+                    const u32 c = s_warp_hist[w][d];
+                    s_warp_hist[w][d] = run;
+                    run += c;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < SORT_ITEMS; ++r) {
+                const long long i = wbase + r * 32 + lane;
+                if (i < n) {
+                    const u32 d = (u32)(k[r] >> shift) & 255u;
+                    const u32 pos = s_warp_hist[warp][d] + local[r];
+                    kout[pos] = k[r];
+                    vout[pos] = vin[i];
+                }
+            }
+            __syncthreads();
+        }
+        grid.sync();
+        u64* tk = kin; kin = kout; kout = tk;
+        u32* tv = vin; vin = vout; vout = tv;
+    }
+}
+
+static int coop_grid_limit() {
+    static thread_local int cached = -1;
+    if (cached < 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_sort_coop_kernel, SORT_THREADS, 0);
+        cached = coop ? sms * per_sm : 0;
+    }
+    return cached;
+}
+
 int radix_sort_pairs(u64* keys, u64* keys_alt, u32* vals, u32* vals_alt, long long n, int begin_bit,
                      int end_bit, u64** out_keys, u32** out_vals, cudaStream_t stream) {
     *out_keys = keys;
@@ -209,6 +331,19 @@ int radix_sort_pairs(u64* keys, u64* keys_alt, u32* vals, u32* vals_alt, long lo
     u64* kout = keys_alt;
     u32* vin = vals;
     u32* vout = vals_alt;
+    const int coop_limit = ntiles <= SORT_COOP_MAX_TILES ? coop_grid_limit() : 0;
+    if (coop_limit > 0) {
+        int grid = std::min(ntiles, coop_limit);
+        long long n_ = n;
+        int bb = begin_bit, eb = end_bit, nt = ntiles;
+        void* args[] = {&kin, &kout, &vin, &vout, &n_, &bb, &eb, &counts, &nt};
+        CNVK_CHECK(cudaLaunchCooperativeKernel((const void*)radix_sort_coop_kernel, dim3(grid), dim3(SORT_THREADS), args,
+                                               0, stream));
+        CNVK_LAUNCH_CHECK();
+        const int passes = (end_bit - begin_bit + 7) / 8;
+        if (passes & 1) { *out_keys = kout; *out_vals = vout; } else { *out_keys = kin; *out_vals = vin; }
+        return 0;
+    }
     for (int shift = begin_bit; shift < end_bit; shift += 8) {
         digit_hist_kernel<<<ntiles, SORT_THREADS, 0, stream>>>(kin, n, shift, counts, ntiles);
         CNVK_LAUNCH_CHECK();

@@ -17,6 +17,10 @@
 #include "prims.cuh"
 #include "prof.cuh"
 
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 namespace cnvk {
 
 static const int WM_BLOCK = 1024;  // elements per build block (32 words)
@@ -107,6 +111,109 @@ wm_scatter_kernel(const u32* __restrict__ seq, u32* __restrict__ seq_out, long l
         const u32 pos = b ? (Z + ones_before) : ((u32)t - ones_before);
         seq_out[pos] = v;
     }
+}
+
+// All levels of the wavelet matrix in ONE cooperative launch (the exome-sized sequences used to pay
+// ~6 launches per level for a few microseconds of work each).  Per level: every CTA counts the ones of
+// its blocks, grid.sync, every CTA sums the counts of the blocks before its own (and the total) straight
+// from the table and scatters, grid.sync.  Same bitvectors, directories and order as the per-level path.
+static const int WM_COOP_MAX_BLOCKS = 2048;
+
+__global__ void __launch_bounds__(WM_BLOCK)
+wm_build_coop_kernel(u32* seq_a, u32* seq_b, long long M, int levels, u32* __restrict__ block_ones,
+                     uint2* __restrict__ dir, u32* __restrict__ zeros_out, long long stride, long long nwords,
+                     int nblocks) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ u32 s_cnt[32];
+    __shared__ u32 s_a[32], s_b[32];
+    __shared__ u32 s_pre[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32* sin = seq_a;
+    u32* sout = seq_b;
+    for (int lev = 0; lev < levels; ++lev) {
+        const int bit = levels - 1 - lev;
+        for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+            const long long t = (long long)blk * WM_BLOCK + threadIdx.x;
+            const bool b = (t < M) && ((sin[t] >> bit) & 1u);
+            const u32 word = __ballot_sync(0xffffffffu, b);
+            if (lane == 0) s_cnt[warp] = __popc(word);
+            __syncthreads();
+            if (warp == 0) {
+                const u32 c = warp_sum_u32(s_cnt[lane]);
+                if (lane == 0) block_ones[blk] = c;
+            }
+            __syncthreads();
+        }
+        grid.sync();
+        uint2* ldir = dir + (size_t)lev * stride;
+        for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+            // ones in the blocks before this one, and in all blocks
+            u32 before = 0, total = 0;
+            for (int q = threadIdx.x; q < nblocks; q += WM_BLOCK) {
+                const u32 c = block_ones[q];
+                total += c;
+                if (q < blk) before += c;
+            }
+            before = warp_sum_u32(before);
+            total = warp_sum_u32(total);
+            if (lane == 0) { s_a[warp] = before; s_b[warp] = total; }
+            __syncthreads();
+            if (warp == 0) {
+                const u32 x = warp_sum_u32(s_a[lane]), y = warp_sum_u32(s_b[lane]);
+                if (lane == 0) { s_pre[0] = x; s_pre[1] = y; }
+            }
+            __syncthreads();
+            const u32 block_prefix = s_pre[0], ones_total = s_pre[1];
+            const long long t = (long long)blk * WM_BLOCK + threadIdx.x;
+            const bool in = t < M;
+            const u32 v = in ? sin[t] : 0u;
+            const bool b = in && ((v >> bit) & 1u);
+            const u32 word = __ballot_sync(0xffffffffu, b);
+            if (lane == 0) s_cnt[warp] = __popc(word);
+            __syncthreads();
+            if (warp == 0) {
+                const u32 c = s_cnt[lane];
+                u32 inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 y = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += y;
+                }
+                s_cnt[lane] = inc - c;
+            }
+            __syncthreads();
+            const u32 Z = (u32)M - ones_total;
+            const u32 cum = block_prefix + s_cnt[warp];  // ones before this word
+            const long long w = t >> 5;
+            if (lane == 0 && w < nwords) ldir[w] = make_uint2(word, cum);
+            if (blk == 0 && threadIdx.x == 0) {
+                ldir[nwords] = make_uint2(0u, ones_total);
+                zeros_out[lev] = Z;
+            }
+            if (in) {
+                const u32 ones_before = cum + __popc(word & ((1u << lane) - 1u));
+                const u32 pos = b ? (Z + ones_before) : ((u32)t - ones_before);
+                sout[pos] = v;
+            }
+            __syncthreads();
+        }
+        grid.sync();
+        u32* tmp = sin; sin = sout; sout = tmp;
+    }
+}
+
+static int wm_coop_grid_limit() {
+    static thread_local int cached = -1;
+    if (cached < 0) {
+        int dev = 0, sms = 0, per_sm = 0, coop = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wm_build_coop_kernel, WM_BLOCK, 0);
+        cached = coop ? sms * per_sm : 0;
+    }
+    return cached;
 }
 
 struct WmView {
@@ -259,6 +366,16 @@ int rolling_window_stat(const double* d_x, long long n, long long wing, int mode
     u32* sin = seq0;
     u32* sout = seq1;
     ProfScope* wscope = new ProfScope(PC_WAVELET_BUILD, stream);
+    const int coop_limit = nblocks <= WM_COOP_MAX_BLOCKS ? wm_coop_grid_limit() : 0;
+    if (coop_limit > 0) {
+        int grid = std::min(nblocks, coop_limit);
+        long long M_ = M, stride_ = stride, nwords_ = nwords;
+        int levels_ = levels, nblocks_ = nblocks;
+        void* args[] = {&sin, &sout, &M_, &levels_, &block_ones, &dir, &zeros, &stride_, &nwords_, &nblocks_};
+        CNVK_CHECK(cudaLaunchCooperativeKernel((const void*)wm_build_coop_kernel, dim3(grid), dim3(WM_BLOCK), args, 0,
+                                               stream));
+        CNVK_LAUNCH_CHECK();
+    } else
     for (int lev = 0; lev < levels; ++lev) {
         const int bit = levels - 1 - lev;
         wm_count_kernel<<<nblocks, WM_BLOCK, 0, stream>>>(sin, M, bit, block_ones);
