@@ -512,6 +512,17 @@ __device__ __noinline__ void cand_update(Cand& b, double num, double den, int i,
     }
 }
 
+// inlined form for kernels that scan one arc per iteration: the candidate stays in registers
+__device__ __forceinline__ void cand_update_inl(Cand& b, double num, double den, int i, int j) {
+    const double q = __ddiv_rn(num, den);
+    if (cand_better(q, i, j, b.q, b.i, b.j)) {
+        b.q = q;
+        b.i = i;
+        b.j = j;
+        b.qlo = q * (1.0 - 1e-12);
+    }
+}
+
 template <int NA, bool MASKED>
 __device__ __forceinline__ void scan_subtiles(Cand& best, const double2* __restrict__ sj, const double* Si,
                                               const double* ci, const int* ii, int jbase, int jcount, double total,
@@ -762,7 +773,7 @@ cbs_band_kernel(Node* __restrict__ nodes, int nnodes,
                 const double den = __dmul_rn(c, __dsub_rn(total, c));
                 const double num = __dmul_rn(d, d);
                 if ((unsigned)(kw - al0) <= kw_span && num > __dmul_rn(best.qlo, den))
-                    cand_update(best, num, den, i, ibase + jl);
+                    cand_update_inl(best, num, den, i, ibase + jl);
             }
         }
     }
@@ -1402,6 +1413,42 @@ void cbs_getbdry(double eta, int nperm, int max_ones, std::vector<int>& out) {
     }
 }
 
+// Pinned staging memory for the small per-level host<->device copies (node tables, decisions, flags):
+// copies from pageable std::vector storage go through the driver's own staging buffer and cost ~10 us
+// each, which adds up over ~10 copies per recursion level.  Chunks persist per thread across calls.
+struct PinnedArena {
+    struct Chunk { char* p; size_t cap; };
+    std::vector<Chunk> chunks;
+    size_t cur = 0, used = 0;
+    void rewind() { cur = 0; used = 0; }
+    void* get(size_t bytes) {
+        bytes = (bytes + 63) & ~(size_t)63;
+        while (cur < chunks.size() && used + bytes > chunks[cur].cap) { ++cur; used = 0; }
+        if (cur == chunks.size()) {
+            Chunk c;
+            c.cap = std::max(bytes, (size_t)1 << 20);
+            if (cudaHostAlloc((void**)&c.p, c.cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+            chunks.push_back(c);
+            used = 0;
+        }
+        void* r = chunks[cur].p + used;
+        used += bytes;
+        return r;
+    }
+    template <typename T>
+    T* put(const T* src, size_t count) {          // copy into pinned memory, return the pinned pointer
+        T* d = (T*)get(count * sizeof(T));
+        if (d && count) memcpy(d, src, count * sizeof(T));
+        return d;
+    }
+};
+static thread_local PinnedArena g_pinned;
+
+#define CNVK_PIN_CHECK(ptr)                                                     \
+    do {                                                                        \
+        if (!(ptr)) { set_last_error("cbs_segment: pinned staging allocation failed"); return (int)cudaErrorMemoryAllocation; } \
+    } while (0)
+
 struct HostNode {
     int lo, hi, base, arm;
 };
@@ -1555,9 +1602,16 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             CNVK_CHECK(cudaMallocAsync((void**)&d_part3, cap_ptiles * sizeof(TileScan), stream));
         }
         if ((size_t)blk_off > NB) { set_last_error("cbs_segment: block buffer too small"); return -3; }
-        CNVK_CHECK(cudaMemcpyAsync(d_nodes, h_nodes.data(), nn * sizeof(Node), cudaMemcpyHostToDevice, stream));
-        CNVK_CHECK(cudaMemcpyAsync(d_tile_off, h_tile_off.data(), (nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-        CNVK_CHECK(cudaMemcpyAsync(d_ptile_off, h_ptile_off.data(), (nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+        g_pinned.rewind();   // every copy of the previous level has completed (the level ends with a sync)
+        {
+            Node* p_nodes = g_pinned.put(h_nodes.data(), (size_t)nn);
+            int* p_to = g_pinned.put(h_tile_off.data(), (size_t)nn + 1);
+            int* p_pto = g_pinned.put(h_ptile_off.data(), (size_t)nn + 1);
+            CNVK_PIN_CHECK(p_nodes && p_to && p_pto);
+            CNVK_CHECK(cudaMemcpyAsync(d_nodes, p_nodes, nn * sizeof(Node), cudaMemcpyHostToDevice, stream));
+            CNVK_CHECK(cudaMemcpyAsync(d_tile_off, p_to, (nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+            CNVK_CHECK(cudaMemcpyAsync(d_ptile_off, p_pto, (nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+        }
         CNVK_CHECK(cudaMemsetAsync(d_counter, 0, 2 * sizeof(int), stream));
         if ((size_t)qtiles > cap_queue) {
             if (d_queue) cudaFreeAsync(d_queue, stream);
@@ -1625,8 +1679,13 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             CNVK_LAUNCH_CHECK();
         }
         h_dec.resize(nn);
-        CNVK_CHECK(cudaMemcpyAsync(h_dec.data(), d_dec, nn * sizeof(Decision), cudaMemcpyDeviceToHost, stream));
-        CNVK_CHECK(cudaStreamSynchronize(stream));
+        {
+            Decision* p_dec = (Decision*)g_pinned.get((size_t)nn * sizeof(Decision));
+            CNVK_PIN_CHECK(p_dec);
+            CNVK_CHECK(cudaMemcpyAsync(p_dec, d_dec, nn * sizeof(Decision), cudaMemcpyDeviceToHost, stream));
+            CNVK_CHECK(cudaStreamSynchronize(stream));
+            memcpy(h_dec.data(), p_dec, (size_t)nn * sizeof(Decision));
+        }
 
         // ---- permutation reference distributions
         for (int mode = ST_PERM_HYBRID; mode <= ST_PERM_EXACT; ++mode) {
@@ -1654,7 +1713,11 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 CNVK_CHECK(ps.alloc(&d_list, (size_t)na));
                 CNVK_CHECK(ps.alloc(&d_pmax, (size_t)na * chunk));
                 CNVK_CHECK(ps.alloc(&d_flags, (size_t)na * chunk));
-                CNVK_CHECK(cudaMemcpyAsync(d_list, active.data(), na * sizeof(int), cudaMemcpyHostToDevice, stream));
+                {
+                    int* p_list = g_pinned.put(active.data(), (size_t)na);
+                    CNVK_PIN_CHECK(p_list);
+                    CNVK_CHECK(cudaMemcpyAsync(d_list, p_list, na * sizeof(int), cudaMemcpyHostToDevice, stream));
+                }
                 CNVK_CHECK(cudaMemsetAsync(d_pmax, 0, (size_t)na * chunk * sizeof(unsigned long long), stream));
                 ProfScope pscope(mode == ST_PERM_HYBRID ? PC_CBS_PERM_HYBRID : PC_CBS_PERM_EXACT, stream);
                 if (mode == ST_PERM_HYBRID) {
@@ -1679,8 +1742,9 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 }
                 cbs_perm_flags_kernel<<<div_up((long long)na * chunk, 256), 256, 0, stream>>>(d_nodes, d_list, na, d_pmax, chunk, d_flags);
                 CNVK_LAUNCH_CHECK();
-                std::vector<unsigned char> flags((size_t)na * chunk);
-                CNVK_CHECK(cudaMemcpyAsync(flags.data(), d_flags, flags.size(), cudaMemcpyDeviceToHost, stream));
+                unsigned char* flags = (unsigned char*)g_pinned.get((size_t)na * chunk);
+                CNVK_PIN_CHECK(flags);
+                CNVK_CHECK(cudaMemcpyAsync(flags, d_flags, (size_t)na * chunk, cudaMemcpyDeviceToHost, stream));
                 CNVK_CHECK(cudaStreamSynchronize(stream));
                 st.perms_run += (long long)na * chunk;
                 // replay DNAcopy's sequential stopping rule on the flags
@@ -1727,7 +1791,9 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             Scratch fs(stream);
             FlankTest* d_tests;
             CNVK_CHECK(fs.alloc(&d_tests, (size_t)nt));
-            CNVK_CHECK(cudaMemcpyAsync(d_tests, tests.data(), nt * sizeof(FlankTest), cudaMemcpyHostToDevice, stream));
+            FlankTest* p_tests = g_pinned.put(tests.data(), (size_t)nt);
+            CNVK_PIN_CHECK(p_tests);
+            CNVK_CHECK(cudaMemcpyAsync(d_tests, p_tests, nt * sizeof(FlankTest), cudaMemcpyHostToDevice, stream));
             ProfScope fscope(PC_CBS_FLANK, stream);
             double* d_part;
             CNVK_CHECK(fs.alloc(&d_part, (size_t)nt * FLANK_SPLIT * 5));
@@ -1738,8 +1804,9 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             }
             cbs_flank_prep_kernel<<<div_up(nt, 128), 128, 0, stream>>>(d_tests, nt, d_part);
             CNVK_LAUNCH_CHECK();
-            CNVK_CHECK(cudaMemcpyAsync(tests.data(), d_tests, nt * sizeof(FlankTest), cudaMemcpyDeviceToHost, stream));
+            CNVK_CHECK(cudaMemcpyAsync(p_tests, d_tests, nt * sizeof(FlankTest), cudaMemcpyDeviceToHost, stream));
             CNVK_CHECK(cudaStreamSynchronize(stream));
+            memcpy(tests.data(), p_tests, (size_t)nt * sizeof(FlankTest));
             std::vector<int> plist;
             for (int t = 0; t < nt; ++t) if (tests[t].need_perm) plist.push_back(t);
             if (!plist.empty()) {
