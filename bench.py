@@ -29,6 +29,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "bins segmented/s (CBS, WGS 1 kb)"
 UNIT = "bins/s"
@@ -272,8 +274,10 @@ def run_b200(args):
         data = synth.wgs_sample(total_bins=args.bins)
         owner = shard.arm_owner(data["arm_offsets"], world)
         nbins_total = int(data["arm_offsets"][-1])
-    else:  # cohort mode: every rank owns one whole sample (its own seed), nothing is shared
-        data = synth.wgs_sample(total_bins=args.bins, seed=0xC3 + rank)
+    else:  # cohort mode: every rank owns one whole sample; the same synthetic sample on every rank, so that
+        # per-GPU work is exactly fixed (CBS cost is data-dependent: one borderline node that needs all
+        # 9 500 permutations costs several times the rest of the sample)
+        data = synth.wgs_sample(total_bins=args.bins)
         owner = np.full(len(data["arm_offsets"]) - 1, rank)
         nbins_total = int(data["arm_offsets"][-1]) * world
     x, w, off, mine = shard.take_arms(data["log2"], data["weight"], data["arm_offsets"], owner, rank)
@@ -400,15 +404,15 @@ def run_b200(args):
         prep_bytes = PREP_BYTES_PER_BIN * stats["prep_bins"]
         prep_gbs = prep_bytes / (prep_ms * 1e-3) / 1e9 if prep_ms > 0 else 0.0
         roof_prep = {
-            "kernel": "cbs_prep_kernel", "bound": "hbm", "achieved": prep_gbs, "peak": hbm_peak, "unit": "GB/s",
-            "frac": prep_gbs / hbm_peak, "traffic": 138.3e6, "peak_source": hbm_src,
+            "kernel": "cbs_prep_{sums,scan,finish,node}_kernel", "bound": "hbm", "achieved": prep_gbs, "peak": hbm_peak,
+            "unit": "GB/s", "frac": prep_gbs / hbm_peak, "traffic": 217.0e6, "peak_source": hbm_src,
             "algorithmic": f"{PREP_BYTES_PER_BIN} B/bin (read log2, weight; write xc, y, wn, S, cw) x "
                            f"{stats['prep_bins']} bins centred and prefix-summed over {stats['levels']} levels",
             "kernel_ms_per_step": prep_ms,
-            "note": "nominally HBM-bound but limited by the strictly sequential FP64 add chain that defines the "
-                    "bits of S (n dependent DADDs per node, ~11 cycles each): the floor is "
-                    "sum over levels of (largest open node) x t_add, not bytes; traffic = ncu dram bytes of the "
-                    "level-1 launch (profiles/r01b_cbs_prep_full_summary.md)",
+            "note": "blocked FP64 prefix scan cut into 2048-point tiles (one CTA each); the tile kernels move 104 B/bin "
+                    "(the sums pass re-reads the inputs, the tile-local prefixes make one round trip before the "
+                    "carries are added); traffic = ncu dram bytes of the level-1 launches of the three tile kernels "
+                    "(profiles/r01d_cbs_kernels_full_summary.md), the rest of the writes stays in L2",
         }
         roofline = dict(roof_prep if dominant == "cbs_prep" else roof_scan)
         roofline["dominant_class_by_time"] = dominant
@@ -441,7 +445,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if by_arms else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C3 synthetic WGS, {args.bins} 1-kb bins, 48 arms, CBS alpha={ALPHA} nperm=10000"
-                                   + ("" if by_arms or world == 1 else f", one such sample per GPU ({world} samples)"),
+                                   + ("" if by_arms or world == 1 else f", one such sample per GPU ({world} replicas of the same synthetic sample)"),
                        "sharding": "single GPU" if world == 1 else
                        (f"arms of one sample over {world} ranks by LPT on n^2; NCCL gather of tables" if by_arms else
                         f"samples over {world} ranks (cohort mode), no data-path collective; NCCL gather of tables"),
