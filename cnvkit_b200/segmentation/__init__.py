@@ -142,6 +142,59 @@ def do_segmentation(
     return result
 
 
+def transfer_fields(segments, cnarr, ignore=params.IGNORE_GENE_NAMES):
+    """Map gene names, weights and depths from `cnarr` bins to segments, and stretch every
+    chromosome's first / last segment to that chromosome's bins -- the reference's public seam
+    (cnvlib/segmentation/__init__.py:401-506), same arguments, errors and result; the sums run on the
+    device (cnvk_segment_bin_sums_dev).  Segment rows may be in any order; the bins of a chromosome
+    need not be contiguous in `cnarr`."""
+    if not len(cnarr):
+        logging.warning("No bins for:\n%s", segments.data)
+        return segments
+    cdata = cnarr.data.reset_index(drop=True)
+    sdata = segments.data.reset_index(drop=True)
+    b_chrom = cdata["chromosome"].to_numpy().astype(object)
+    s_chrom = sdata["chromosome"].to_numpy().astype(object)
+    chroms = list(dict.fromkeys(b_chrom.tolist()))           # first-appearance order, as by_chromosome()
+    unknown = sorted(set(s_chrom.tolist()) - set(chroms))
+    seg_start = sdata["start"].to_numpy(dtype=np.int64).copy()
+    seg_end = sdata["end"].to_numpy(dtype=np.int64).copy()
+    # group the bins by chromosome (stable), so that every chromosome is one contiguous "arm"
+    code = {c: k for k, c in enumerate(chroms)}
+    b_code = np.fromiter((code[c] for c in b_chrom.tolist()), dtype=np.int64, count=len(b_chrom))
+    order = np.argsort(b_code, kind="stable")
+    g = cdata.iloc[order].reset_index(drop=True)
+    off = np.concatenate([[0], np.cumsum(np.bincount(b_code, minlength=len(chroms)))]).astype(np.int64)
+    arms = [(c, int(off[k]), int(off[k + 1])) for k, c in enumerate(chroms)]
+    g_start = g["start"].to_numpy(dtype=np.int64)
+    g_end = g["end"].to_numpy(dtype=np.int64)
+    known = np.array([c in code for c in s_chrom.tolist()], dtype=bool)
+    seg_arm = np.array([code.get(c, 0) for c in s_chrom.tolist()], dtype=np.int64)
+    # stretch per chromosome by POSITION in the segment table (first / last row of that chromosome)
+    for k, c in enumerate(chroms):
+        pos = np.flatnonzero(known & (seg_arm == k))
+        if len(pos):
+            seg_start[pos[0]] = g_start[off[k]]
+            seg_end[pos[-1]] = g_end[off[k + 1] - 1]
+    if unknown:
+        raise ValueError("Segments on chromosomes absent from the input bins: " + ", ".join(unknown))
+    # aggregate in chromosome-grouped order, then put the rows back where they were
+    sorder = np.argsort(seg_arm, kind="stable")
+    weight = g["weight"].to_numpy(dtype=np.float64) if "weight" in g.columns else None
+    depth = g["depth"].to_numpy(dtype=np.float64) if "depth" in g.columns else None
+    log2 = g["log2"].to_numpy(dtype=np.float64)
+    gc = GeneCodes(g["gene"].to_numpy(), ignore=ignore)
+    tab = _transfer_fields(seg_arm[sorder], s_chrom[sorder], seg_start[sorder], seg_end[sorder],
+                           np.zeros(len(sorder)), np.zeros(len(sorder), dtype=np.int64), arms, g, log2, weight, depth,
+                           g_start, g_end, gene_codes=gc, stretch=False)
+    inv = np.empty_like(sorder)
+    inv[sorder] = np.arange(len(sorder))
+    out = sdata.assign(start=seg_start, end=seg_end, gene=np.asarray(tab["gene"], dtype=object)[inv],
+                       weight=tab["weight"].to_numpy()[inv], depth=tab["depth"].to_numpy()[inv])
+    segments.data = out
+    return segments
+
+
 def _arm_offsets(arm_of_bin, n_arms):
     return np.concatenate([[0], np.cumsum(np.bincount(arm_of_bin, minlength=n_arms))]).astype(np.int64)
 
@@ -200,7 +253,7 @@ def _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, f_chrom, n_arms, thre
 
 
 def _transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, seg_log2, probes, arms, data, log2, weight, depth,
-                     start, end, gene_codes=None):
+                     start, end, gene_codes=None, stretch=True):
     """transfer_fields(segarr, cnarr) per arm (:401-506), all arms at once.
 
     Each arm's first/last segment is stretched to the arm's first bin start / last bin end; then
@@ -215,8 +268,9 @@ def _transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, seg_log2, probes, a
     last[:-1] = seg_arm[1:] != seg_arm[:-1]
     arm_lo = np.array([a[1] for a in arms])
     arm_hi = np.array([a[2] for a in arms])
-    seg_start[first] = start[arm_lo[seg_arm[first]]]
-    seg_end[last] = end[arm_hi[seg_arm[last]] - 1]
+    if stretch:
+        seg_start[first] = start[arm_lo[seg_arm[first]]]
+        seg_end[last] = end[arm_hi[seg_arm[last]] - 1]
     # bin row ranges per segment: intersect.py:323-346 _irange_simple, mode "outer", within the arm
     bin_lo = np.empty(nseg, dtype=np.int64)
     bin_hi = np.empty(nseg, dtype=np.int64)
@@ -250,8 +304,8 @@ class GeneCodes:
     every code holds at most one kept name and no name is shared between codes -- a name table that
     lets a segment's gene list be assembled without per-name Python work."""
 
-    def __init__(self, bin_genes):
-        ignore = set(params.IGNORE_GENE_NAMES + params.ANTITARGET_ALIASES)
+    def __init__(self, bin_genes, ignore=None):
+        ignore = set((params.IGNORE_GENE_NAMES if ignore is None else tuple(ignore)) + params.ANTITARGET_ALIASES)
         codes, uniques = pd.factorize(pd.Series(bin_genes, dtype=object), sort=False)
         self.codes = codes
         self.parts = [tuple(p for p in u.split(",") if p not in ignore) if isinstance(u, str) else ()
