@@ -51,6 +51,10 @@ SIGNATURES = {
     "cnvk_bias_correct_logr_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p,
                                            c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
                                            c_int32, c_void_p, c_void_p]),
+    "cnvk_trait_order_dev": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "cnvk_center_by_order_dev": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "cnvk_fix_group_ordered_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p,
+                                           c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
     "cnvk_fix_finish_dev": (c_int, [c_void_p] * 9 + [c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "cnvk_segmented_median_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "cnvk_biweight": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),

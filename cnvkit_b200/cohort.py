@@ -77,6 +77,16 @@ class _Group:
             self.d_edge = _dev.empty(n, torch.float64)
             _lib.call("cnvk_edge_bias_dev", _dev.ptr(self.d_start), _dev.ptr(self.d_end), _dev.ptr(self.d_cid), n,
                       params.INSERT_SIZE, _dev.ptr(self.d_edge), _dev.stream())
+        # visiting orders of center_by_window for GC, edge, RepeatMasker ("ger", fix.py:265-289): they
+        # depend on the bins only, so the per-sample work is one rolling median per trait, no sort
+        self.d_orders = []
+        for key in (self.d_gc, self.d_edge, self.d_rmask):
+            if key is None:
+                self.d_orders.append(None)
+                continue
+            d_ord = _dev.empty(n, torch.int32)
+            _lib.call("cnvk_trait_order_dev", _dev.ptr(key), _dev.ptr(self.d_perm), n, _dev.ptr(d_ord), _dev.stream())
+            self.d_orders.append(d_ord)
 
     def adjust(self, log2, depth):
         """Bias-corrected log2 of the kept rows (device tensor), or None if the sample needs the
@@ -95,11 +105,10 @@ class _Group:
         d_log2 = d_all.index_select(0, self.d_keep_idx).contiguous()
         d_depth = d_dall.index_select(0, self.d_keep_idx).contiguous()
         skipped = ctypes.c_int32(0)
-        _lib.call("cnvk_fix_group_dev", _dev.ptr(d_log2), _dev.ptr(d_depth), _dev.ptr(self.d_auto), self.n,
-                  _dev.ptr(self.d_off), self.nchrom, _dev.ptr(self.d_cid), _dev.ptr(self.d_start), _dev.ptr(self.d_end),
-                  _dev.ptr(self.d_gc), _dev.ptr(self.d_rmask), _dev.ptr(self.d_edge), int(bool(self.do_edge)),
-                  int(bool(self.skip_low)), 1, self.wing, _dev.ptr(self.d_perm), params.INSERT_SIZE, b"ger",
-                  ctypes.addressof(skipped), _dev.stream())
+        o = self.d_orders
+        _lib.call("cnvk_fix_group_ordered_dev", _dev.ptr(d_log2), _dev.ptr(d_depth), _dev.ptr(self.d_auto), self.n,
+                  _dev.ptr(self.d_off), self.nchrom, _dev.ptr(o[0]), _dev.ptr(o[1]), _dev.ptr(o[2]),
+                  int(bool(self.skip_low)), 1, self.wing, ctypes.addressof(skipped), _dev.stream())
         if skipped.value:
             logging.warning("WARNING: most bins have no or very low coverage; check that the right BED file was used")
         return d_log2, d_depth

@@ -236,6 +236,29 @@ int cnvk_fix_group_dev(double* d_log2, const double* d_depth, const uint8_t* d_a
     return rc;
 }
 
+int cnvk_trait_order_dev(const double* d_key, const uint32_t* d_perm, int64_t n, uint32_t* d_order, void* stream) {
+    RC(ensure_init());
+    return trait_order(d_key, d_perm, n, d_order, (cudaStream_t)stream);
+}
+
+int cnvk_center_by_order_dev(double* d_log2, const uint32_t* d_order, int64_t n, int64_t wing, void* stream) {
+    RC(ensure_init());
+    return center_by_order(d_log2, d_order, n, wing, (cudaStream_t)stream);
+}
+
+int cnvk_fix_group_ordered_dev(double* d_log2, const double* d_depth, const uint8_t* d_auto_sel, int64_t n,
+                               const int64_t* d_chrom_offsets, int32_t nchrom, const uint32_t* d_order0,
+                               const uint32_t* d_order1, const uint32_t* d_order2, int32_t skip_low, int32_t do_center,
+                               int64_t wing, int32_t* skipped, void* stream) {
+    RC(ensure_init());
+    int sk = 0;
+    const uint32_t* orders[3] = {d_order0, d_order1, d_order2};
+    int rc = fix_group_ordered(d_log2, d_depth, d_auto_sel, n, (const long long*)d_chrom_offsets, nchrom, orders, 3,
+                               skip_low, do_center, wing, &sk, (cudaStream_t)stream);
+    if (skipped) *skipped = sk;
+    return rc;
+}
+
 int cnvk_bias_correct_logr_dev(double* d_log2, const double* d_depth, const uint8_t* d_auto_sel, int64_t n,
                                const int64_t* d_chrom_offsets, int32_t nchrom, const double* d_gc,
                                const double* d_rmask, const double* d_edge_key, int32_t skip_low, int64_t wing,

@@ -121,6 +121,59 @@ __global__ void scatter_sub_kernel(double* __restrict__ log2, const u32* __restr
     if (t < n) log2[src_of[t]] = __dsub_rn(xs[t], bias[t]);
 }
 
+__global__ void compose_kernel(const u32* __restrict__ perm, const u32* __restrict__ order, long long n,
+                               u32* __restrict__ src_of) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) src_of[t] = perm[order[t]];
+}
+
+// The order in which center_by_window visits the bins -- shuffle by the fixed permutation, then stable
+// argsort by the trait (fix.py:404-414) -- depends on the bin set only, not on the sample: a cohort
+// computes it once per (trait, bin set) and reuses it for every sample.
+int trait_order(const double* d_key, const u32* d_perm, long long n, u32* d_src_of, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    Scratch scratch(stream);
+    double* kperm;
+    u32* order;
+    CNVK_CHECK(scratch.alloc(&kperm, (size_t)n));
+    CNVK_CHECK(scratch.alloc(&order, (size_t)n));
+    {
+        ProfScope ps(PC_FIX, stream);
+        gather_f64_kernel<<<div_up(n, 256), 256, 0, stream>>>(d_key, d_perm, n, kperm);
+        CNVK_LAUNCH_CHECK();
+    }
+    int rc = argsort_f64(kperm, n, order, stream);
+    if (rc) return rc;
+    ProfScope ps(PC_FIX, stream);
+    compose_kernel<<<div_up(n, 256), 256, 0, stream>>>(d_perm, order, n, d_src_of);
+    CNVK_LAUNCH_CHECK();
+    return 0;
+}
+
+// center_by_window given the visiting order: rolling median of log2 along it, subtracted in place
+int center_by_order(double* d_log2, const u32* d_src_of, long long n, long long wing, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    Scratch scratch(stream);
+    double *xs, *bias;
+    CNVK_CHECK(scratch.alloc(&xs, (size_t)n));
+    CNVK_CHECK(scratch.alloc(&bias, (size_t)n));
+    {
+        ProfScope ps(PC_FIX, stream);
+        gather_f64_kernel<<<div_up(n, 256), 256, 0, stream>>>(d_log2, d_src_of, n, xs);
+        CNVK_LAUNCH_CHECK();
+    }
+    if (n < 2) {
+        CNVK_CHECK(cudaMemcpyAsync(bias, xs, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    } else {
+        int rc = rolling_window_stat(xs, n, wing, 0, 0.5, 1, bias, stream);
+        if (rc) return rc;
+    }
+    ProfScope ps(PC_FIX, stream);
+    scatter_sub_kernel<<<div_up(n, 256), 256, 0, stream>>>(d_log2, d_src_of, xs, bias, n);
+    CNVK_LAUNCH_CHECK();
+    return 0;
+}
+
 int center_by_window(double* d_log2, const double* d_key, const u32* d_perm, long long n, long long wing,
                      cudaStream_t stream) {
     if (n <= 0) return 0;
@@ -226,6 +279,41 @@ __global__ void shift_sex_kernel(double* __restrict__ log2, const double* __rest
     if (is_xx) { if (s & 2) v = -1.0; }
     else if (s & 3) v = __dadd_rn(v, 1.0);
     log2[i] = v;
+}
+
+// the same with the visiting orders precomputed (trait_order): one rolling median per trait, no sort
+int fix_group_ordered(double* d_log2, const double* d_depth, const u8* d_auto_sel, long long n,
+                      const long long* d_chrom_off, int nchrom, const u32* const* d_orders, int n_orders, int skip_low,
+                      int do_center, long long wing, int* h_skipped, cudaStream_t stream) {
+    if (h_skipped) *h_skipped = 0;
+    if (n <= 0) return 0;
+    int rc;
+    if (do_center) {
+        rc = center_all(d_log2, d_depth, d_auto_sel, n, d_chrom_off, nchrom, skip_low, nullptr, stream);
+        if (rc) return rc;
+    }
+    Scratch scratch(stream);
+    unsigned long long* d_cnt;
+    CNVK_CHECK(scratch.alloc(&d_cnt, 1));
+    CNVK_CHECK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), stream));
+    {
+        ProfScope ps(PC_FIX, stream);
+        count_gt_kernel<<<std::min(div_up(n, 256), 1184), 256, 0, stream>>>(d_log2, n, NULL_LOG2_COVERAGE - MIN_REF_COVERAGE, d_cnt);
+        CNVK_LAUNCH_CHECK();
+    }
+    unsigned long long h_cnt = 0;
+    CNVK_CHECK(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, stream));
+    CNVK_CHECK(cudaStreamSynchronize(stream));
+    if ((long long)h_cnt <= n / 2) {
+        if (h_skipped) *h_skipped = 1;   // "most bins have no or very low coverage"
+        return 0;
+    }
+    for (int k = 0; k < n_orders; ++k) {
+        if (!d_orders[k]) continue;
+        rc = center_by_order(d_log2, d_orders[k], n, wing, stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 int fix_group(double* d_log2, const double* d_depth, const u8* d_auto_sel, long long n,

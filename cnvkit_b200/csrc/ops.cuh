@@ -28,6 +28,11 @@ int center_all(double* d_log2, const double* d_depth, const unsigned char* d_sel
                const long long* d_chrom_off, int nchrom, int skip_low, double* d_shift_out, cudaStream_t stream);
 int center_by_window(double* d_log2, const double* d_key, const u32* d_perm, long long n, long long wing,
                      cudaStream_t stream);
+int trait_order(const double* d_key, const u32* d_perm, long long n, u32* d_src_of, cudaStream_t stream);
+int center_by_order(double* d_log2, const u32* d_src_of, long long n, long long wing, cudaStream_t stream);
+int fix_group_ordered(double* d_log2, const double* d_depth, const unsigned char* d_auto_sel, long long n,
+                      const long long* d_chrom_off, int nchrom, const u32* const* d_orders, int n_orders, int skip_low,
+                      int do_center, long long wing, int* h_skipped, cudaStream_t stream);
 int edge_bias(const long long* d_start, const long long* d_end, const int* d_chrom_id, long long n, long long margin,
               double* d_out, cudaStream_t stream);
 int fix_group(double* d_log2, const double* d_depth, const unsigned char* d_auto_sel, long long n,

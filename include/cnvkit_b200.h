@@ -109,6 +109,18 @@ int cnvk_fix_group_dev(double* d_log2, const double* d_depth, const uint8_t* d_a
                        int64_t wing, const uint32_t* d_perm, int64_t margin, const char* order,
                        int32_t* skipped, void* stream);
 
+/* Cohort form of center_by_window: the order in which fix.py:404-414 visits the bins (fixed shuffle,
+ * then stable argsort by the trait) depends on the bin set only.  cnvk_trait_order_dev computes it once
+ * (d_order[t] = row visited t-th); cnvk_center_by_order_dev applies fix.py:417-426 along it (rolling
+ * median of log2, subtracted in place); cnvk_fix_group_ordered_dev is cnvk_fix_group_dev with up to three
+ * precomputed orders (NULL = skip), applied in the order given. */
+int cnvk_trait_order_dev(const double* d_key, const uint32_t* d_perm, int64_t n, uint32_t* d_order, void* stream);
+int cnvk_center_by_order_dev(double* d_log2, const uint32_t* d_order, int64_t n, int64_t wing, void* stream);
+int cnvk_fix_group_ordered_dev(double* d_log2, const double* d_depth, const uint8_t* d_auto_sel, int64_t n,
+                               const int64_t* d_chrom_offsets, int32_t nchrom, const uint32_t* d_order0,
+                               const uint32_t* d_order1, const uint32_t* d_order2, int32_t skip_low, int32_t do_center,
+                               int64_t wing, int32_t* skipped, void* stream);
+
 /* cnvlib/reference.py:625-667 bias_correct_logr for one normal sample: center_all(skip_low) ->
  * shift_sex_chroms (reference.py:670-714: log2 += flat_logr; XX sample: chrY bins = -1, XY
  * sample: chrX/chrY bins += 1; d_sex_chrom bit0 = chrX row, bit1 = chrY row) -> "mostly empty"
