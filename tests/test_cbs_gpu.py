@@ -190,3 +190,28 @@ def test_full_c3_sample_equals_oracle(G):
                 and min(abs(c - lo) for c in cuts) <= 5 and min(abs(c - hi) for c in cuts) <= 5)
     big = sum(1 for lo, hi, step in d["truth"] if (hi - lo) >= 50 and abs(step) >= 0.5)
     assert found >= 0.95 * big, (found, big)
+
+
+def test_many_small_arms_in_one_batch(G):
+    """A cohort-style batch: thousands of arms of 1..600 bins in one call (every kernel's node / tile
+    indexing, empty arms included) against the oracle."""
+    rng = np.random.default_rng(77)
+    sizes = rng.integers(0, 600, size=4000)
+    sizes[rng.integers(0, len(sizes), 200)] = 0
+    xs, ws = [], []
+    for n in sizes:
+        x = rng.normal(0, 0.2, n)
+        if n > 60 and rng.random() < 0.5:
+            a = int(rng.integers(5, n - 30))
+            x[a:a + int(rng.integers(10, 25))] += rng.choice([-0.8, 0.6, 1.0])
+        xs.append(x)
+        ws.append(rng.uniform(0.5, 1.0, n))
+    x, w = q6(np.concatenate(xs)), q6(np.concatenate(ws))
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    P = OC.make_params(alpha=1e-4, prune=True)
+    o = OC.segment(x, w, off, P, nthreads=16)
+    g = G.segment_arms(x, w, off, alpha=1e-4)
+    for a, b in zip(g[:3], o[:3]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_allclose(g[3], o[3], rtol=1e-9, atol=0)
+    assert len(g[0]) > int((sizes > 0).sum())
