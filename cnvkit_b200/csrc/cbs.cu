@@ -1122,15 +1122,77 @@ __global__ void cbs_decide_kernel(Node* __restrict__ nodes, int nnodes, Decision
 }
 
 // ------------------------------------------------------------------------------------ permutations
+// Pruning limits for the hybrid permutation statistic of one node (DNAcopy keeps the same kind of table,
+// mncwt, for hwtmaxp).  A permutation only has to answer "does any short arc reach the observed
+// statistic?", i.e. is  acc^2 / den(s,k) >= q_thr  for some arc, with q_thr the smallest BSS whose T^2
+// reaches ostat.  The weights are not permuted, so den(s,k) = c (W - c), c = sum of the arc's k
+// normalised weights, is the same in every permutation: lim[k] = q_thr * min_s den(s,k) * (1 - 1e-12)
+// lets the permutation kernel drop an arc after one add, one multiply and one compare.
+// One CTA per node; cacc is accumulated exactly as the permutation kernel accumulates it.
+static const int HYB_LIM = HYB_KMAX + 1;
+
+__global__ void __launch_bounds__(256)
+cbs_perm_bounds_kernel(const Node* __restrict__ nodes, const int* __restrict__ list, const double* __restrict__ wn,
+                       int al0, int kmax, unsigned long long* __restrict__ dmin_bits) {
+    // grid (tile of HYB_TP arc starts, list index): min over the tile's starts of den(s, k) for every k,
+    // merged into dmin_bits[node][k] with atomicMin on the bit pattern (den > 0, so the order is numeric)
+    __shared__ double s_w[HYB_TP + HYB_KMAX];
+    __shared__ double s_min[8][HYB_LIM];
+    const int node = list[blockIdx.y];
+    const Node nd = nodes[node];
+    const int n = nd.hi - nd.lo, lo = nd.lo;
+    const int s0 = blockIdx.x * HYB_TP;
+    if (s0 >= n) return;
+    const double total = nd.total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int count = min(HYB_TP, n - s0);
+    const int need = count + kmax - 1;
+    for (int k = threadIdx.x; k < need; k += 256) {
+        int pos = s0 + k;
+        if (pos >= n) pos -= n;
+        s_w[k] = wn[lo + pos];
+    }
+    __syncthreads();
+    double dmin[HYB_LIM];
+#pragma unroll 1
+    for (int k = 0; k <= kmax; ++k) dmin[k] = INFINITY;
+    for (int s = threadIdx.x; s < count; s += 256) {
+        double cacc = 0.0;
+#pragma unroll 1
+        for (int k = 1; k <= kmax; ++k) {
+            cacc = __dadd_rn(cacc, s_w[s + k - 1]);
+            if (k >= al0) dmin[k] = fmin(dmin[k], __dmul_rn(cacc, __dsub_rn(total, cacc)));
+        }
+    }
+#pragma unroll 1
+    for (int k = al0; k <= kmax; ++k) {
+        double v = dmin[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) s_min[warp][k] = v;
+    }
+    __syncthreads();
+    for (int k = al0 + threadIdx.x; k <= kmax; k += 256) {
+        double v = s_min[0][k];
+        for (int w_ = 1; w_ < 8; ++w_) v = fmin(v, s_min[w_][k]);
+        if (v < INFINITY) atomicMin(&dmin_bits[(size_t)node * HYB_LIM + k], (unsigned long long)__double_as_longlong(v));
+    }
+}
+
 // hybrid: circular arcs of width al0..kmax over the permuted terms; grid (pos tile, perm, list idx)
+// KMAX_T / AL0_T > 0: widths fixed at compile time (DNAcopy's defaults kmax = 25, min.width = 2) so that the
+// arc loop unrolls into LDS + DADD + DMUL + DSETP per arc; 0 = run-time widths.
+template <int KMAX_T, int AL0_T>
 __global__ void __launch_bounds__(256)
 cbs_perm_hybrid_kernel(const Node* __restrict__ nodes, const int* __restrict__ list, int p0,
                        const double* __restrict__ y, const double* __restrict__ w_sqrt,
-                       const double* __restrict__ wn, u64 seed, int al0, int kmax,
-                       unsigned long long* __restrict__ pmax, int chunk) {
+                       const double* __restrict__ wn, const unsigned long long* __restrict__ dmin_bits, u64 seed,
+                       int al0, int kmax, unsigned long long* __restrict__ pmax, int chunk) {
     __shared__ double s_t[HYB_TP + HYB_KMAX], s_w[HYB_TP + HYB_KMAX];
+    __shared__ double s_lim[HYB_LIM];
     __shared__ double s_best[8];
-    const Node nd = nodes[list[blockIdx.z]];
+    const int node = list[blockIdx.z];
+    const Node nd = nodes[node];
     const int n = nd.hi - nd.lo, lo = nd.lo;
     const int s0 = blockIdx.x * HYB_TP;
     if (s0 >= n) return;
@@ -1145,20 +1207,48 @@ cbs_perm_hybrid_kernel(const Node* __restrict__ nodes, const int* __restrict__ l
         s_t[k] = __dmul_rn(y[lo + prp((u32)pos)], w_sqrt[lo + pos]);
         s_w[k] = wn[lo + pos];
     }
+    if (threadIdx.x <= kmax) {
+        // smallest BSS whose T^2 reaches ostat: bss (n-2) / (tss - bss) >= ostat (t2_of is increasing there);
+        // no pruning when tss is so small that t2_of's guard (tss <= bss + 1e-4) could come into play
+        const double nm2 = (double)n - 2.0;
+        const double qthr = nd.ostat * nd.tss / (nm2 + nd.ostat) * (1.0 - 1e-9);
+        const bool safe = nd.tss * nm2 / (nm2 + nd.ostat) > 1e-3 && nd.ostat > 0.0 && threadIdx.x >= al0;
+        const double dm = __longlong_as_double((long long)dmin_bits[(size_t)node * HYB_LIM + threadIdx.x]);
+        s_lim[threadIdx.x] = safe ? qthr * dm * (1.0 - 1e-12) : 0.0;
+    }
     __syncthreads();
     const double total = nd.total;
     double best = 0.0, bestlo = 0.0;
-    for (int s = threadIdx.x; s < count; s += 256) {
-        double acc = 0.0, cacc = 0.0;
-        for (int k = 1; k <= kmax; ++k) {
-            acc = __dadd_rn(acc, s_t[s + k - 1]);
-            cacc = __dadd_rn(cacc, s_w[s + k - 1]);
-            if (k >= al0) {
-                const double num = __dmul_rn(acc, acc);
-                const double den = __dmul_rn(cacc, __dsub_rn(total, cacc));
-                if (num > __dmul_rn(bestlo, den)) {
-                    const double q = __ddiv_rn(num, den);
-                    if (q > best) { best = q; bestlo = q * (1.0 - 1e-12); }
+    // rare path: this arc could reach the observed statistic -> score it exactly
+    auto score = [&](int s, int k, double num) {
+        double cacc = 0.0;
+        for (int j = 0; j < k; ++j) cacc = __dadd_rn(cacc, s_w[s + j]);
+        const double den = __dmul_rn(cacc, __dsub_rn(total, cacc));
+        if (num > __dmul_rn(bestlo, den)) {
+            const double q = __ddiv_rn(num, den);
+            if (q > best) { best = q; bestlo = q * (1.0 - 1e-12); }
+        }
+    };
+    if (KMAX_T > 0) {
+        for (int s = threadIdx.x; s < count; s += 256) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 1; k <= KMAX_T; ++k) {
+                acc = __dadd_rn(acc, s_t[s + k - 1]);
+                if (k >= AL0_T) {
+                    const double num = __dmul_rn(acc, acc);
+                    if (num >= s_lim[k]) score(s, k, num);
+                }
+            }
+        }
+    } else {
+        for (int s = threadIdx.x; s < count; s += 256) {
+            double acc = 0.0;
+            for (int k = 1; k <= kmax; ++k) {
+                acc = __dadd_rn(acc, s_t[s + k - 1]);
+                if (k >= al0) {
+                    const double num = __dmul_rn(acc, acc);
+                    if (num >= s_lim[k]) score(s, k, num);
                 }
             }
         }
@@ -1169,7 +1259,8 @@ cbs_perm_hybrid_kernel(const Node* __restrict__ nodes, const int* __restrict__ l
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int k = 1; k < 8; ++k) best = fmax(best, s_best[k]);
-        atomicMax(&pmax[(size_t)blockIdx.z * chunk + blockIdx.y], (unsigned long long)__double_as_longlong(best));
+        if (best > 0.0)
+            atomicMax(&pmax[(size_t)blockIdx.z * chunk + blockIdx.y], (unsigned long long)__double_as_longlong(best));
     }
 }
 
@@ -1703,6 +1794,26 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             std::vector<int> active(list.begin(), list.end());
             std::vector<size_t> active_q(list.size());
             for (size_t q = 0; q < list.size(); ++q) active_q[q] = q;
+            Scratch limscratch(stream);
+            unsigned long long* d_lim = nullptr;
+            if (mode == ST_PERM_HYBRID) {
+                // pruning limits of every node that enters the hybrid permutation test (once per node)
+                int* d_all;
+                CNVK_CHECK(limscratch.alloc(&d_lim, (size_t)nn * HYB_LIM));
+                CNVK_CHECK(limscratch.alloc(&d_all, list.size()));
+                CNVK_CHECK(cudaMemsetAsync(d_lim, 0x7f, (size_t)nn * HYB_LIM * sizeof(unsigned long long), stream));
+                int* p_all = g_pinned.put(list.data(), list.size());
+                CNVK_PIN_CHECK(p_all);
+                CNVK_CHECK(cudaMemcpyAsync(d_all, p_all, list.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+                ProfScope bscope(PC_CBS_PERM_HYBRID, stream);
+                int maxn = 0;
+                for (int k : list) maxn = std::max(maxn, frontier[k].hi - frontier[k].lo);
+                for (size_t z0 = 0; z0 < list.size(); z0 += 32768) {
+                    const int nz = (int)std::min<size_t>(32768, list.size() - z0);
+                    cbs_perm_bounds_kernel<<<dim3(div_up(maxn, HYB_TP), nz), 256, 0, stream>>>(d_nodes, d_all + z0, d_wn, P.min_width, P.kmax, d_lim);
+                    CNVK_LAUNCH_CHECK();
+                }
+            }
             while (!active.empty() && p0 < P.nperm) {
                 chunk = std::min(chunk, P.nperm - p0);
                 const int na = (int)active.size();
@@ -1727,7 +1838,10 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                     for (int z0 = 0; z0 < na; z0 += 32768) {
                         const int nz = std::min(32768, na - z0);
                         dim3 grid(div_up(maxn, HYB_TP), chunk, nz);
-                        cbs_perm_hybrid_kernel<<<grid, 256, 0, stream>>>(d_nodes, d_list + z0, p0, d_y, d_rw, d_wn, P.seed, P.min_width, P.kmax, d_pmax + (size_t)z0 * chunk, chunk);
+                        if (P.kmax == 25 && P.min_width == 2)
+                            cbs_perm_hybrid_kernel<25, 2><<<grid, 256, 0, stream>>>(d_nodes, d_list + z0, p0, d_y, d_rw, d_wn, d_lim, P.seed, P.min_width, P.kmax, d_pmax + (size_t)z0 * chunk, chunk);
+                        else
+                            cbs_perm_hybrid_kernel<0, 0><<<grid, 256, 0, stream>>>(d_nodes, d_list + z0, p0, d_y, d_rw, d_wn, d_lim, P.seed, P.min_width, P.kmax, d_pmax + (size_t)z0 * chunk, chunk);
                         CNVK_LAUNCH_CHECK();
                     }
                     for (int k : active) st.perm_arcs += (long long)(frontier[k].hi - frontier[k].lo) * (P.kmax - P.min_width + 1) * chunk;
