@@ -2,16 +2,18 @@
 #include <stdarg.h>
 
 #include "../../include/cnvkit_b200.h"
+#include <mutex>
 #include <vector>
 
 #include "ops.cuh"
 #include "prof.cuh"
 
 namespace cnvk {
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 int g_prof_enabled = 0;
 struct ProfPending { int cls; cudaEvent_t a, b; };
 static std::vector<ProfPending> g_prof_pending;
+static std::mutex g_prof_mutex;   // host threads of a cohort run share the profiler
 static double g_prof_ms[PC_COUNT];
 static unsigned long long g_prof_n[PC_COUNT];
 void prof_begin(int cls, cudaStream_t stream, cudaEvent_t* start) {
@@ -22,9 +24,11 @@ void prof_end(int cls, cudaStream_t stream, cudaEvent_t start) {
     cudaEvent_t stop;
     if (cudaEventCreate(&stop) != cudaSuccess) { cudaEventDestroy(start); return; }
     cudaEventRecord(stop, stream);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     g_prof_pending.push_back({cls, start, stop});
 }
 static void prof_collect() {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     for (auto& p : g_prof_pending) {
         float ms = 0.f;
         if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
@@ -118,7 +122,7 @@ extern "C" {
 
 const char* cnvk_last_error(void) { return g_err; }
 int cnvk_abi_version(void) { return 2; }
-unsigned long long cnvk_launch_count(void) { return g_launch_count; }
+unsigned long long cnvk_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
 
 void cnvk_prof_enable(int on) { g_prof_enabled = on; }
 void cnvk_prof_reset(void) {

@@ -24,8 +24,10 @@
 //            (hybrid, n > nmin), and the number of exceedances tolerated.
 //   perms  : reference distribution for undecided nodes, evaluated in SM-resident tiles with
 //            counter-based permutations (cbs_rng.cuh): hybrid = circular arcs of width <= kmax
-//            (n > nmin), exact = all arcs (n <= nmin); DNAcopy's sequential stopping boundary
-//            is replayed on the exceedance flags chunk by chunk.
+//            (n > nmin), each arc dropped after add + multiply + compare against a per-node, per-width
+//            limit (the weights are not permuted, so the smallest denominator is a constant of the
+//            node); exact = all arcs (n <= nmin); DNAcopy's sequential stopping boundary is replayed
+//            on the exceedance flags chunk by chunk.
 //   flank  : ternary-split confirmation (wtpermp) for arcs interior to the node.
 // Host code only moves a few bytes of per-node decisions per level and builds the next frontier.
 #include <algorithm>
@@ -330,7 +332,6 @@ cbs_prep_finish_kernel(const Node* __restrict__ nodes, const int* __restrict__ p
     const Node* nd = &nodes[a];
     if (nd->flat) return;
     const int lo = nd->lo, n = nd->hi - nd->lo, boff = nd->blk_off;
-    const int ntiles = ptile_off[a + 1] - ptile_off[a];
     const double rsw = nd->rsw;
     const int t0 = k * PREP_TILE, m = max(0, min(PREP_TILE, n - t0));
     const int npts = min(PREP_TILE, n + 1 - t0);                         // points t0 .. t0+npts-1 (<= n)
@@ -419,7 +420,6 @@ cbs_prep_finish_kernel(const Node* __restrict__ nodes, const int* __restrict__ p
             part3[blockIdx.x].dmin = dmin;
         }
     }
-    (void)ntiles;
 }
 
 // one warp per node: tss, total, delta (linear partials + the wrap-around arcs), reset of the best
@@ -1183,12 +1183,12 @@ cbs_perm_bounds_kernel(const Node* __restrict__ nodes, const int* __restrict__ l
 // KMAX_T / AL0_T > 0: widths fixed at compile time (DNAcopy's defaults kmax = 25, min.width = 2) so that the
 // arc loop unrolls into LDS + DADD + DMUL + DSETP per arc; 0 = run-time widths.
 template <int KMAX_T, int AL0_T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 cbs_perm_hybrid_kernel(const Node* __restrict__ nodes, const int* __restrict__ list, int p0,
                        const double* __restrict__ y, const double* __restrict__ w_sqrt,
                        const double* __restrict__ wn, const unsigned long long* __restrict__ dmin_bits, u64 seed,
                        int al0, int kmax, unsigned long long* __restrict__ pmax, int chunk) {
-    __shared__ double s_t[HYB_TP + HYB_KMAX], s_w[HYB_TP + HYB_KMAX];
+    __shared__ double s_t[HYB_TP + HYB_KMAX];
     __shared__ double s_lim[HYB_LIM];
     __shared__ double s_best[8];
     const int node = list[blockIdx.z];
@@ -1205,7 +1205,6 @@ cbs_perm_hybrid_kernel(const Node* __restrict__ nodes, const int* __restrict__ l
         int pos = s0 + k;
         if (pos >= n) pos -= n;
         s_t[k] = __dmul_rn(y[lo + prp((u32)pos)], w_sqrt[lo + pos]);
-        s_w[k] = wn[lo + pos];
     }
     if (threadIdx.x <= kmax) {
         // smallest BSS whose T^2 reaches ostat: bss (n-2) / (tss - bss) >= ostat (t2_of is increasing there);
@@ -1222,7 +1221,12 @@ cbs_perm_hybrid_kernel(const Node* __restrict__ nodes, const int* __restrict__ l
     // rare path: this arc could reach the observed statistic -> score it exactly
     auto score = [&](int s, int k, double num) {
         double cacc = 0.0;
-        for (int j = 0; j < k; ++j) cacc = __dadd_rn(cacc, s_w[s + j]);
+        int pos = s0 + s;                                  // the weights are read from global memory here only
+        for (int j = 0; j < k; ++j) {
+            if (pos >= n) pos -= n;
+            cacc = __dadd_rn(cacc, wn[lo + pos]);
+            ++pos;
+        }
         const double den = __dmul_rn(cacc, __dsub_rn(total, cacc));
         if (num > __dmul_rn(bestlo, den)) {
             const double q = __ddiv_rn(num, den);

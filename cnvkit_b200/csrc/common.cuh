@@ -1,6 +1,8 @@
 // Shared device/host helpers for the cnvkit_b200 CUDA library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -23,10 +25,10 @@ void set_last_error(const char* fmt, ...);
         }                                                                             \
     } while (0)
 
-extern unsigned long long g_launch_count;  // kernels launched by this library (host-side tally)
+extern std::atomic<unsigned long long> g_launch_count;  // kernels launched by this library (host-side tally)
 #define CNVK_LAUNCH_CHECK()                 \
     do {                                    \
-        ++cnvk::g_launch_count;             \
+        cnvk::g_launch_count.fetch_add(1, std::memory_order_relaxed); \
         CNVK_CHECK(cudaGetLastError());     \
     } while (0)
 

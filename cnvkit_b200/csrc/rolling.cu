@@ -601,8 +601,8 @@ int rolling_window_stat(const double* d_x, long long n, long long wing, int mode
         CNVK_CHECK(cudaLaunchCooperativeKernel((const void*)wm_build_coop_kernel, dim3(grid), dim3(WM_BLOCK), args, 0,
                                                stream));
         CNVK_LAUNCH_CHECK();
-    } else
-    for (int lev = 0; lev < levels; ++lev) {
+    }
+    for (int lev = 0; lev < levels && coop_limit <= 0; ++lev) {
         const int bit = levels - 1 - lev;
         wm_count_kernel<<<nblocks, WM_BLOCK, 0, stream>>>(sin, M, bit, block_ones);
         CNVK_LAUNCH_CHECK();
