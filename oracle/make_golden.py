@@ -317,11 +317,43 @@ def gen_fix_units(R):
     save("fix_units", **arrays)
 
 
+def gen_exome_mini(R):
+    """Synthetic exome panel (cnvkit_b200.synth, 9 000 targets + 3 000 antitargets, C2's construction at
+    1/16 scale) through the UNMODIFIED reference: do_fix, then do_segmentation('haar') -- pins the fix
+    path on a bin set with close-packed targets (edge gains), masked bins and antitargets, which the
+    real-data regression fixture exercises less."""
+    import pandas as pd
+
+    from cnvkit_b200 import synth
+
+    bins = synth.exome_bins(n_targets=9000, n_antitargets=3000, seed=7)
+    ref = synth.exome_reference(bins, seed=8)
+    arrays = {}
+    t = bins["is_target"]
+    base = pd.DataFrame({"chromosome": bins["chromosome"], "start": bins["start"], "end": bins["end"],
+                         "gene": bins["gene"]})
+    reference = R.cnary.CopyNumArray(base.assign(log2=ref["log2"], depth=ref["depth"], gc=bins["gc"],
+                                                 rmask=bins["rmask"], spread=ref["spread"]), {"sample_id": "reference"})
+    for k in range(2):
+        smp = synth.exome_sample(bins, ref, seed=k, n_events=4)
+        cov = base.assign(log2=smp["log2"], depth=smp["depth"])
+        tgt = R.cnary.CopyNumArray(cov[t].reset_index(drop=True), {"sample_id": f"S{k}"})
+        anti = R.cnary.CopyNumArray(cov[~t].reset_index(drop=True), {"sample_id": f"S{k}"})
+        cnr = R.fix.do_fix(tgt, anti, reference)
+        cns = R.segmentation.do_segmentation(cnr, "haar")
+        arrays[f"s{k}_in_log2_checksum"] = np.asarray([float(np.sum(smp["log2"])), float(np.sum(smp["depth"]))])
+        arrays.update(table_arrays(cnr, f"s{k}_cnr"))
+        arrays.update(table_arrays(cns, f"s{k}_cns_haar"))
+    arrays["ref_checksum"] = np.asarray([float(np.sum(ref["log2"])), float(np.sum(ref["spread"])),
+                                         float(np.sum(bins["gc"])), float(np.sum(bins["start"]))])
+    save("exome_mini", **arrays)
+
+
 def main():
     logging.basicConfig(level=logging.ERROR)
     os.makedirs(OUT, exist_ok=True)
     R = refshim.load()
-    which = sys.argv[1:] or ["smoothing", "regression", "haar", "fix_units"]
+    which = sys.argv[1:] or ["smoothing", "regression", "haar", "fix_units", "exome_mini"]
     for w in which:
         globals()["gen_" + w](R)
 
