@@ -561,26 +561,14 @@ struct TileRef {
     unsigned mask;
 };
 
-// task -> (node a, start block ib, first end block jb0); task_off[a] = first task of node a
-__device__ __forceinline__ void decode_task(const Node* __restrict__ nodes, const int* __restrict__ task_off,
-                                            int nnodes, int task, int& a, int& ib, int& jb0, int& NJ) {
-    int lo_ = 0, hi_ = nnodes;
-    while (hi_ - lo_ > 1) {
-        const int m = (lo_ + hi_) >> 1;
-        if (task_off[m] <= task) lo_ = m; else hi_ = m;
-    }
-    a = lo_;
-    const int n = nodes[a].hi - nodes[a].lo;
-    NJ = (n + 1 + CBS_BLK - 1) / CBS_BLK;
-    int t = task - task_off[a];
-    ib = 0;
-    for (;;) {
-        const int cnt = (max(0, NJ - CBS_IW * ib) + 255) / 256;
-        if (t < cnt) break;
-        t -= cnt;
-        ++ib;
-    }
-    jb0 = CBS_IW * ib + 256 * t;
+// task -> (node a, start block ib, first end block jb0): a host-built table, one int4 per task
+__device__ __forceinline__ void decode_task(const Node* __restrict__ nodes, const int4* __restrict__ task_tab,
+                                            int task, int& a, int& ib, int& jb0, int& NJ) {
+    const int4 t = task_tab[task];
+    a = t.x;
+    ib = t.y;
+    jb0 = t.z;
+    NJ = t.w;
 }
 
 // CTA-wide argmax of the threads' candidates (ties -> smallest (i,j)) and one lock-protected
@@ -618,14 +606,14 @@ __device__ __forceinline__ void cta_commit(Node* nd, double q, int qi, int qj, d
 }
 
 __global__ void __launch_bounds__(256)
-cbs_seed_kernel(Node* __restrict__ nodes, const int* __restrict__ task_off, int nnodes,
+cbs_seed_kernel(Node* __restrict__ nodes, const int4* __restrict__ task_tab,
                 const double* __restrict__ blk_min, const double* __restrict__ blk_max,
                 const int* __restrict__ blk_imin, const int* __restrict__ blk_imax,
                 const double* __restrict__ blk_cmin, const double* __restrict__ blk_cmax, int al0) {
     __shared__ double s_q[8];
     __shared__ int s_i[8], s_j[8];
     int a, ib, jb0, NJ;
-    decode_task(nodes, task_off, nnodes, blockIdx.x, a, ib, jb0, NJ);
+    decode_task(nodes, task_tab, blockIdx.x, a, ib, jb0, NJ);
     Node* nd = &nodes[a];
     if (nd->flat) return;
     const int n = nd->hi - nd->lo, boff = nd->blk_off;
@@ -783,7 +771,7 @@ cbs_band_kernel(Node* __restrict__ nodes, int nnodes,
 
 template <bool PRUNE>
 __global__ void __launch_bounds__(256)
-cbs_bound_kernel(const Node* __restrict__ nodes, const int* __restrict__ task_off, int nnodes,
+cbs_bound_kernel(const Node* __restrict__ nodes, const int4* __restrict__ task_tab,
                  const double* __restrict__ cw, const double* __restrict__ blk_min,
                  const double* __restrict__ blk_max, TileRef* __restrict__ queue, int* __restrict__ qcount,
                  unsigned long long* __restrict__ stats) {
@@ -791,7 +779,7 @@ cbs_bound_kernel(const Node* __restrict__ nodes, const int* __restrict__ task_of
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int a, ib, jb0, NJ;
-    decode_task(nodes, task_off, nnodes, blockIdx.x, a, ib, jb0, NJ);
+    decode_task(nodes, task_tab, blockIdx.x, a, ib, jb0, NJ);
     const Node* nd = &nodes[a];
     if (nd->flat) return;
     const int lo = nd->lo, n = nd->hi - nd->lo, boff = nd->blk_off;
@@ -1549,13 +1537,15 @@ struct HostNode {
 };
 
 // tasks (CTAs of the seed / bound kernels) and 1024x256 tiles of a node of n bins
-static void tiles_for(int n, long long* tasks, long long* tiles) {
+static void tiles_for(int n, int node, std::vector<int4>* table, long long* tasks, long long* tiles) {
     const int P = n + 1;
     const int NJ = (P + CBS_BLK - 1) / CBS_BLK, NI = (P + CBS_IBLK - 1) / CBS_IBLK;
     long long t = 0, q = 0;
     for (int ib = 0; ib < NI; ++ib) {
         const int m = std::max(0, NJ - CBS_IW * ib);
-        t += (m + 255) / 256;
+        const int chunks = (m + 255) / 256;
+        for (int c = 0; c < chunks; ++c) table->push_back(make_int4(node, ib, CBS_IW * ib + 256 * c, NJ));
+        t += chunks;
         q += m;
     }
     *tasks = t;
@@ -1630,10 +1620,13 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
     TileScan* d_part3 = nullptr;
     int* d_ptile_off = nullptr;
     std::vector<int> h_ptile_off;
+    std::vector<int4> h_task_tab;
+    int4* d_task_tab = nullptr;
+    size_t cap_tasks = 0;
+    struct TaskGuard { int4*& p; cudaStream_t s; ~TaskGuard() { if (p) cudaFreeAsync(p, s); } } tguard{d_task_tab, stream};
     struct PartGuard { TileSums*& a; TileScan*& b; cudaStream_t s; ~PartGuard() { if (a) cudaFreeAsync(a, s); if (b) cudaFreeAsync(b, s); } } pguard{d_part1, d_part3, stream};
     Node* d_nodes = nullptr;
     Decision* d_dec = nullptr;
-    int* d_tile_off = nullptr;
     double* d_terms = nullptr;
     struct QueueGuard { TileRef*& q; cudaStream_t s; ~QueueGuard() { if (q) cudaFreeAsync(q, s); } } qguard{d_queue, stream};
     auto free_level = [&]() {
@@ -1641,9 +1634,8 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         d_terms = nullptr;
         if (d_nodes) cudaFreeAsync(d_nodes, stream);
         if (d_dec) cudaFreeAsync(d_dec, stream);
-        if (d_tile_off) cudaFreeAsync(d_tile_off, stream);
         if (d_ptile_off) cudaFreeAsync(d_ptile_off, stream);
-        d_nodes = nullptr; d_dec = nullptr; d_tile_off = nullptr; d_ptile_off = nullptr;
+        d_nodes = nullptr; d_dec = nullptr; d_ptile_off = nullptr;
     };
     struct Guard { decltype(free_level)& f; ~Guard() { f(); } } guard{free_level};
 
@@ -1660,13 +1652,13 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             cap_nodes = (size_t)nn * 2;
             CNVK_CHECK(cudaMallocAsync((void**)&d_nodes, cap_nodes * sizeof(Node), stream));
             CNVK_CHECK(cudaMallocAsync((void**)&d_dec, cap_nodes * sizeof(Decision), stream));
-            CNVK_CHECK(cudaMallocAsync((void**)&d_tile_off, (cap_nodes + 1) * sizeof(int), stream));
             CNVK_CHECK(cudaMallocAsync((void**)&d_ptile_off, (cap_nodes + 1) * sizeof(int), stream));
             CNVK_CHECK(cudaMallocAsync((void**)&d_terms, cap_nodes * 100 * sizeof(double), stream));
         }
         h_nodes.assign(nn, Node());
         h_tile_off.assign(nn + 1, 0);
         h_ptile_off.assign(nn + 1, 0);
+        h_task_tab.clear();
         long long blk_off = 0, tiles = 0, qtiles = 0, ptiles = 0;
         for (int k = 0; k < nn; ++k) {
             Node& nd = h_nodes[k];
@@ -1681,7 +1673,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             blk_off += (n + 1 + CBS_BLK - 1) / CBS_BLK;
             h_tile_off[k] = (int)tiles;
             long long nt_, nq_;
-            tiles_for(n, &nt_, &nq_);
+            tiles_for(n, k, &h_task_tab, &nt_, &nq_);
             tiles += nt_;
             qtiles += nq_;
             if (tiles >= (1ll << 31) || qtiles >= (1ll << 31)) { set_last_error("cbs_segment: tile count overflow"); return -2; }
@@ -1698,13 +1690,22 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         }
         if ((size_t)blk_off > NB) { set_last_error("cbs_segment: block buffer too small"); return -3; }
         g_pinned.rewind();   // every copy of the previous level has completed (the level ends with a sync)
+        if (h_task_tab.size() > cap_tasks) {
+            if (d_task_tab) cudaFreeAsync(d_task_tab, stream);
+            d_task_tab = nullptr;
+            cap_tasks = h_task_tab.size() * 2;
+            CNVK_CHECK(cudaMallocAsync((void**)&d_task_tab, cap_tasks * sizeof(int4), stream));
+        }
+        if (!h_task_tab.empty()) {
+            int4* p_tab = g_pinned.put(h_task_tab.data(), h_task_tab.size());
+            CNVK_PIN_CHECK(p_tab);
+            CNVK_CHECK(cudaMemcpyAsync(d_task_tab, p_tab, h_task_tab.size() * sizeof(int4), cudaMemcpyHostToDevice, stream));
+        }
         {
             Node* p_nodes = g_pinned.put(h_nodes.data(), (size_t)nn);
-            int* p_to = g_pinned.put(h_tile_off.data(), (size_t)nn + 1);
             int* p_pto = g_pinned.put(h_ptile_off.data(), (size_t)nn + 1);
-            CNVK_PIN_CHECK(p_nodes && p_to && p_pto);
+            CNVK_PIN_CHECK(p_nodes && p_pto);
             CNVK_CHECK(cudaMemcpyAsync(d_nodes, p_nodes, nn * sizeof(Node), cudaMemcpyHostToDevice, stream));
-            CNVK_CHECK(cudaMemcpyAsync(d_tile_off, p_to, (nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
             CNVK_CHECK(cudaMemcpyAsync(d_ptile_off, p_pto, (nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
         }
         CNVK_CHECK(cudaMemsetAsync(d_counter, 0, 2 * sizeof(int), stream));
@@ -1731,7 +1732,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 const int grid = sm_count * 4;
                 if (P.prune & 1) {
                     ProfScope ps(PC_CBS_SEED, stream);
-                    cbs_seed_kernel<<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_bmin, d_bmax, d_bimin, d_bimax, d_bcmin, d_bcmax, P.min_width);
+                    cbs_seed_kernel<<<(int)tiles, 256, 0, stream>>>(d_nodes, d_task_tab, d_bmin, d_bmax, d_bimin, d_bimax, d_bcmin, d_bcmax, P.min_width);
                     CNVK_LAUNCH_CHECK();
                 }
                 {
@@ -1742,8 +1743,8 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 }
                 {
                     ProfScope ps(PC_CBS_BOUND, stream);
-                    if (P.prune & 1) cbs_bound_kernel<true><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
-                    else cbs_bound_kernel<false><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_tile_off, nn, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
+                    if (P.prune & 1) cbs_bound_kernel<true><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_task_tab, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
+                    else cbs_bound_kernel<false><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_task_tab, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
                     CNVK_LAUNCH_CHECK();
                 }
                 {
