@@ -29,8 +29,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL
+# prints its version banner there), so fd 1 is pointed at stderr for the whole run and the JSON line is
+# written to a duplicate of the original stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 
 METRIC = "bins segmented/s (CBS, WGS 1 kb)"
 UNIT = "bins/s"
@@ -250,7 +258,7 @@ def run_reference(args):
                                             "unavailable), OpenMP over arms"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_b200(args):
@@ -464,7 +472,7 @@ def run_b200(args):
             "cbs_stats": stats,
             "exome": exome,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -526,7 +534,7 @@ def run_reference_build(args):
         total = S * per_normal + 1.5 * n * per_bin      # log2 location+spread, depth location
         sample = (f"1 normal's window corrections + {m} bins of summarize_info, extrapolated to {S} normals x {n} bins; "
                   "oracle/np_oracle.py + pandas rolling median, 1 core")
-        print(json.dumps({"impl": "reference", "metric": "normals/s (reference build)", "value": S / total,
+        emit(({"impl": "reference", "metric": "normals/s (reference build)", "value": S / total,
                           "unit": "normals/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": 1e3 * total,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic", "config": {"workload": f"C4 reference build, {S} normals x {n} bins"},
@@ -561,7 +569,7 @@ def run_reference_build(args):
     except OSError:
         pass
     hbm = float(peaks.get("hbm_gbs", 6540.8))
-    print(json.dumps({
+    emit(({
         "metric": "normals/s (reference build)", "value": S / (ms * 1e-3), "unit": "normals/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -603,7 +611,7 @@ def run_cohort(args):
                 times.append(c["fix_s"] + c["cbs_s"])
         ms = 1e3 * float(np.mean(times))
         sample = "1 sample of the cohort per step, oracle/pipeline.py (pandas rolling median, C CBS with OpenMP over arms)"
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": EXOME_METRIC, "value": 1e3 / ms, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -681,7 +689,7 @@ def run_cohort(args):
     ms_h = max_over_ranks(float(np.mean(ev_h)))
     if rank == 0:
         per_sample_bytes = sum(v.numel() * 8 for part in pinned[0] for v in part.values())
-        print(json.dumps({
+        emit(({
             "metric": EXOME_METRIC, "value": args.samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3) if args.samples <= 256 else 1, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
