@@ -61,12 +61,16 @@ def _world(group=None):
     return dist.get_world_size(group), dist.get_rank(group)
 
 
-def gather_tables(columns, dst: int = 0, group=None, device=None):
+def gather_tables(columns, dst: int = 0, group=None, device=None, capacity=None):
     """Gather per-rank row tables on ``dst``.
 
     ``columns`` is a list of equal-length 1-d numpy arrays (int or float; all are shipped as one
     float64 [rows, ncols] payload -- bin indices are < 2^53).  Returns, on ``dst``, the list of
     concatenated columns in rank order (dtypes restored); ``None`` on the other ranks.
+
+    With ``capacity`` (an upper bound on any rank's row count, known to every rank) the exchange is a
+    single ``gather`` of [capacity + 1, ncols] payloads whose first row carries the row count; without
+    it the counts are all-gathered first and the payload is padded to the largest one.
     """
     import torch
     import torch.distributed as dist
@@ -78,6 +82,22 @@ def gather_tables(columns, dst: int = 0, group=None, device=None):
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
     rows = len(columns[0]) if columns else 0
+    if capacity is not None:
+        if rows > capacity:
+            raise ValueError(f"gather_tables: {rows} rows exceed the agreed capacity {capacity}")
+        pay = torch.zeros((int(capacity) + 1, max(len(columns), 1)), dtype=torch.float64, device=device)
+        pay[0, 0] = float(rows)
+        if rows:
+            host = np.stack([np.asarray(c, dtype=np.float64) for c in columns], axis=1)
+            pay[1:rows + 1, :len(columns)] = torch.from_numpy(host).to(device)
+        out = [torch.zeros_like(pay) for _ in range(world)] if rank == dst else None
+        dist.gather(pay, out, dst=dst, group=group)
+        if rank != dst:
+            return None
+        hosts = [o.cpu().numpy() for o in out]
+        parts = [h[1:int(h[0, 0]) + 1, :len(columns)] for h in hosts]
+        full = np.concatenate(parts, axis=0) if parts else np.zeros((0, len(columns)))
+        return [full[:, k].astype(dt) for k, dt in enumerate(dtypes)]
     cnt = torch.tensor([rows], dtype=torch.int64, device=device)
     cnts = [torch.zeros_like(cnt) for _ in range(world)]
     dist.all_gather(cnts, cnt, group=group)

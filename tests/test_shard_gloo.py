@@ -62,6 +62,12 @@ def _worker(rank, world, port, out_path):
         # a rank with no rows at all must still take part in the gather
         empty = shard.gather_tables([np.zeros(0, np.int64), np.zeros(0)] if rank == 1 else
                                     [np.arange(3, dtype=np.int64), np.ones(3)], dst=0)
+        capped = shard.gather_tables([np.arange(rank + 2, dtype=np.int64), np.full(rank + 2, 0.5 + rank)], dst=0,
+                                     capacity=8)
+        if rank == 0:
+            assert capped[0].tolist() == [0, 1, 0, 1, 2] and capped[1].tolist() == [0.5, 0.5, 1.5, 1.5, 1.5]
+        else:
+            assert capped is None
         if rank == 0:
             ref = OC.segment(x, w, off, P, nthreads=1)
             for a, b in zip(full, ref[:4]):
