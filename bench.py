@@ -320,7 +320,7 @@ def run_b200(args):
         sample_col = np.full(len(arm), 0 if by_arms else rank, dtype=np.int64)
         # one collective: fixed-capacity payloads (a 3 M-bin sample has a few hundred segments)
         full = shard.gather_tables([sample_col, g_arm.astype(np.int64), lo + shift, hi + shift, mean], dst=0,
-                                   device=dev, capacity=16384)
+                                   device=dev, capacity=4096)
         return len(full[0]) if full is not None else 0
 
     def timed(fn, steps, profile=False):
