@@ -397,7 +397,7 @@ def run_b200(args):
         arc_tflops = (arcs * FLOP_PER_ARC) / (arc_ms * 1e-3) / 1e12 if arc_ms > 0 else 0.0
         roof_scan = {
             "kernel": "cbs_scan_kernel + cbs_band_kernel", "bound": "fp64", "achieved": arc_tflops, "peak": fp64_peak,
-            "unit": "TFLOP/s", "frac": arc_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+            "unit": "TFLOP/s", "frac": arc_tflops / fp64_peak if fp64_peak else None, "traffic": 49.8e6,
             "peak_source": "measured in this run: register-only DFMA stream (cnvk_fp64_peak); "
                            "MEASURED_PEAKS.json holds no FP64 figure",
             "algorithmic": f"{FLOP_PER_ARC} FP64 op/arc x {arcs} arcs evaluated per step "
@@ -405,7 +405,9 @@ def run_b200(args):
                            f"survive the bound test; the rest are narrow-band arcs)",
             "kernel_ms_per_step": arc_ms,
             "note": "non-fused FP64 ops: 1 flop per issued DP instruction, so frac <= 0.5 of the DFMA peak; "
-                    "with --no-prune (every arc evaluated) the same kernel reaches 0.46",
+                    "with --no-prune (every arc evaluated) the same kernel reaches 0.46; traffic = ncu dram bytes of "
+                    "the level-1 launches (band 48.0 MB + scan 1.7 MB: one read of S and cw, "
+                    "profiles/r01d_cbs_kernels_full_summary.md) -- DRAM is idle, the pipe is the bound",
         }
         prep_ms = per_step.get("cbs_prep", 0.0)
         prep_bytes = PREP_BYTES_PER_BIN * stats["prep_bins"]
