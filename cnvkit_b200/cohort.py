@@ -24,7 +24,7 @@ import numpy as np
 import pandas as pd
 import torch
 
-from . import _dev, _lib, fix, genome, params, segmentation, smoothing
+from . import _dev, _lib, fix, genome, params, segmentation, smoothing, tabio
 from .cnary import arm_ranges
 from .segmentation import cbs as _cbs
 from .segmentation import haar as _haar
@@ -348,7 +348,10 @@ class Panel:
             out, pend, pend_k = {}, [], []
             for k in idx:
                 tgt, anti = samples[k]
-                trip = self.fix(tgt, anti)
+                if hasattr(tgt, "data") and (len(tgt) != self.t.n0 or len(anti) != self.a.n0):
+                    trip = None   # a table whose rows differ from the panel's (e.g. rows dropped on reading)
+                else:
+                    trip = self.fix(tgt, anti)
                 if trip is None:  # general path for this sample
                     t_tab, a_tab = self._as_tables(tgt, anti, ids[k])
                     cnr = fix.do_fix(t_tab, a_tab, self._reference_table(), self.diploid_parx_genome, *self.opts)
@@ -417,6 +420,86 @@ class Panel:
         ref = self.t.ref_matched.as_dataframe(rt)
         ref.sort()
         return ref
+
+
+def run_files(target_fnames, antitarget_fnames, reference, out_dir, method="cbs", threshold=None, batch=8, workers=4,
+              io_threads=8, diploid_parx_genome=None, do_gc=True, do_edge=True, do_rmask=True, write_cnr=True):
+    """File-to-file cohort run: the fix -> segment core of `cnvkit.py batch` (cnvlib/batch.py:524-555) for
+    samples that share one panel.  Reads every sample's `.targetcoverage.cnn` / `.antitargetcoverage.cnn`
+    with the native columns-only reader (bin sets verified by hash against the first sample), runs the
+    shared-panel plan on the GPU, and writes `<sample>.cnr` / `<sample>.cns` into `out_dir` with the native
+    `%.6g` writer.  Files whose bins differ from the first sample's (or that hold NaN coverage) go through
+    the general per-sample path.  Returns the list of (cnr_path or None, cns_path)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    from .cnary import CopyNumArray
+    from .reference import fbase
+
+    if len(target_fnames) != len(antitarget_fnames):
+        raise ValueError("Unequal number of target and antitarget files given")
+    if isinstance(reference, (str, os.PathLike)):
+        reference = tabio.read(reference)
+    os.makedirs(out_dir, exist_ok=True)
+    n = len(target_fnames)
+    if n == 0:
+        return []
+    t0 = tabio.read(target_fnames[0], sample_id=fbase(target_fnames[0]))
+    a0 = tabio.read(antitarget_fnames[0], sample_id=fbase(antitarget_fnames[0]))
+    panel = Panel(t0, a0, reference, diploid_parx_genome, do_gc, do_edge, do_rmask)
+    _, ht = tabio.read_columns(target_fnames[0])
+    _, ha = tabio.read_columns(antitarget_fnames[0]) if len(a0) else (None, None)
+    # the columns-only reader returns rows in file order: usable when that is the table's sorted order
+    sorted_t = _file_is_sorted(target_fnames[0], t0)
+    sorted_a = _file_is_sorted(antitarget_fnames[0], a0) if len(a0) else True
+
+    def load(k):
+        tf, af = target_fnames[k], antitarget_fnames[k]
+        try:
+            if not (sorted_t and sorted_a):
+                raise KeyError("unsorted panel")
+            tc, h1 = tabio.read_columns(tf)
+            if len(a0):
+                ac, h2 = tabio.read_columns(af)
+            else:
+                ac, h2 = {"log2": np.zeros(0), "depth": np.zeros(0)}, None
+            if h1 != ht or h2 != ha or len(tc["log2"]) != len(t0) or len(ac["log2"]) != len(a0):
+                raise KeyError("different bins")
+            return tc, ac
+        except (KeyError, _lib.CnvkError):
+            return (tabio.read(tf, sample_id=fbase(tf)), tabio.read(af, sample_id=fbase(af)))
+
+    ids = [fbase(f) for f in target_fnames]
+    outputs = [None] * n
+    with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool:
+        loaded = list(pool.map(load, range(n)))
+        results = panel.run(loaded, method=method, threshold=threshold, batch=batch, sample_ids=ids, keep_cnr=write_cnr,
+                            workers=workers)
+
+        def store(k):
+            cnr, cns = results[k]
+            cnr_path = None
+            if write_cnr and cnr is not None:
+                cnr_path = os.path.join(out_dir, ids[k] + ".cnr")
+                tabio.write(cnr, cnr_path)
+            cns_path = os.path.join(out_dir, ids[k] + ".cns")
+            tabio.write(cns, cns_path)
+            return cnr_path, cns_path
+
+        outputs = list(pool.map(store, range(n)))
+    return outputs
+
+
+def _file_is_sorted(path, table):
+    """True when the rows of `path` are already in the order tabio.read gives the table (genomic order,
+    no dropped rows), so that columns read in file order line up with the panel's rows."""
+    try:
+        cols, _ = tabio.read_columns(path, columns=("start", "end"))
+    except (KeyError, _lib.CnvkError):
+        return False
+    return (len(cols["start"]) == len(table)
+            and np.array_equal(cols["start"], table.data["start"].to_numpy(dtype=np.float64))
+            and np.array_equal(cols["end"], table.data["end"].to_numpy(dtype=np.float64)))
 
 
 def _cols(s):

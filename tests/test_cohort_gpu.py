@@ -122,3 +122,43 @@ def test_cohort_threaded_workers_give_the_same_tables(world):
     for (c1, s1), (c2, s2) in zip(one, many):
         assert_same(c1, c2)
         assert_same(s1, s2)
+
+
+def test_run_files_writes_the_tables_of_the_per_sample_path(world, tmp_path):
+    """File-to-file cohort driver: .cnn files in, .cnr/.cns files out, byte-identical to writing the
+    tables of do_fix / do_segmentation sample by sample (one sample has a NaN row -> general path)."""
+    import os
+
+    from cnvkit_b200 import cohort, fix, segmentation, tabio
+
+    bins, ref, tabs = world
+    tdir, odir, wdir = tmp_path / "in", tmp_path / "out", tmp_path / "want"
+    for d in (tdir, odir, wdir):
+        os.makedirs(d)
+    R = tabs[0][2]
+    ref_path = str(tdir / "reference.cnn")
+    tabio.write(R, ref_path)
+    tf, af = [], []
+    for k, (T, A, _) in enumerate(tabs[:3]):
+        t = T.data.copy()
+        if k == 2:
+            t.loc[5, "log2"] = np.nan           # read_tab drops the row; this sample's bins then differ
+        tp, ap = str(tdir / f"S{k}.targetcoverage.cnn"), str(tdir / f"S{k}.antitargetcoverage.cnn")
+        tabio.write(T.as_dataframe(t), tp)
+        tabio.write(A, ap)
+        tf.append(tp)
+        af.append(ap)
+    outs = cohort.run_files(tf, af, ref_path, str(odir), method="cbs", batch=2, workers=2, io_threads=2)
+    assert len(outs) == 3
+    Rr = tabio.read(ref_path)
+    for k, (cnr_path, cns_path) in enumerate(outs):
+        T = tabio.read(tf[k], sample_id=f"S{k}")
+        A = tabio.read(af[k], sample_id=f"S{k}")
+        want_cnr = fix.do_fix(T, A, Rr)
+        want_cns = segmentation.do_segmentation(want_cnr, "cbs")
+        a, b = str(wdir / f"S{k}.cnr"), str(wdir / f"S{k}.cns")
+        tabio.write(want_cnr, a)
+        tabio.write(want_cns, b)
+        assert open(cnr_path, "rb").read() == open(a, "rb").read()
+        assert open(cns_path, "rb").read() == open(b, "rb").read()
+        assert os.path.basename(cns_path) == f"S{k}.cns"
