@@ -216,7 +216,7 @@ __device__ __forceinline__ void node_totals(const TileSums* __restrict__ part, i
     swx = __dadd_rn(b.hi, b.lo);
 }
 
-__global__ void __launch_bounds__(PREP_THREADS)
+__global__ void __launch_bounds__(PREP_THREADS, 4)
 cbs_prep_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_off, int nnodes,
                      const double* __restrict__ x, const double* __restrict__ w, const TileSums* __restrict__ part1,
                      double* __restrict__ xc, double* __restrict__ y, double* __restrict__ wn,
