@@ -133,6 +133,10 @@ def load_adjust_coverages(cnarr, ref_cnarr, skip_low, fix_gc, fix_edge, fix_rmas
 def match_ref_to_sample(ref_cnarr, samp_cnarr):
     """Reference rows re-ordered to the sample's bins by exact (chromosome, start, end)
     (cnvlib/fix.py:324-370), with the reference's error messages."""
+    fast = _match_fast(ref_cnarr, samp_cnarr)
+    if fast is not None:
+        matched = ref_cnarr.data.iloc[fast].set_index(samp_cnarr.data.index)
+        return ref_cnarr.as_dataframe(matched)
     samp_keys = pd.MultiIndex.from_arrays(
         [samp_cnarr.data["chromosome"].to_numpy(), samp_cnarr.data["start"].to_numpy(),
          samp_cnarr.data["end"].to_numpy()])
@@ -160,6 +164,51 @@ def match_ref_to_sample(ref_cnarr, samp_cnarr):
             "reference was likely built for a different target panel.")
     matched = ref_cnarr.data.iloc[pos].set_index(samp_cnarr.data.index)
     return ref_cnarr.as_dataframe(matched)
+
+
+def _match_fast(ref_cnarr, samp_cnarr):
+    """Positions of the sample's bins in the reference by exact (chromosome, start, end), or None when
+    anything is unusual (duplicates, missing bins, coordinates outside 32 bits) -- the caller then takes
+    the MultiIndex path, which also words the errors.  Chromosome names are factorised jointly and
+    (code, start) packed into one int64 that is sorted once and searched."""
+    rs, re_ = ref_cnarr.data["start"].to_numpy(), ref_cnarr.data["end"].to_numpy()
+    ss, se = samp_cnarr.data["start"].to_numpy(), samp_cnarr.data["end"].to_numpy()
+    nr, ns = len(rs), len(ss)
+    if nr == 0 or ns == 0:
+        return None
+    if not (np.issubdtype(rs.dtype, np.integer) and np.issubdtype(ss.dtype, np.integer)):
+        return None
+    if min(rs.min(), ss.min()) < 0 or max(rs.max(), ss.max()) >= (1 << 32):
+        return None
+    both = np.concatenate([ref_cnarr.data["chromosome"].to_numpy().astype(object),
+                           samp_cnarr.data["chromosome"].to_numpy().astype(object)])
+    codes, uniq = pd.factorize(both, sort=False)
+    if len(uniq) >= (1 << 30) or (codes < 0).any():
+        return None
+    kr = (codes[:nr].astype(np.int64) << 32) | rs.astype(np.int64)
+    ks = (codes[nr:].astype(np.int64) << 32) | ss.astype(np.int64)
+    order = np.lexsort((re_, kr))
+    kr_s, re_s = kr[order], np.asarray(re_)[order]
+    if nr > 1 and ((kr_s[1:] == kr_s[:-1]) & (re_s[1:] == re_s[:-1])).any():
+        return None                                   # duplicated reference bins
+    so = np.lexsort((se, ks))
+    if ns > 1 and ((ks[so][1:] == ks[so][:-1]) & (np.asarray(se)[so][1:] == np.asarray(se)[so][:-1])).any():
+        return None                                   # duplicated sample bins
+    lo = np.searchsorted(kr_s, ks, "left")
+    lo_c = np.minimum(lo, nr - 1)
+    hit = (lo < nr) & (kr_s[lo_c] == ks) & (re_s[lo_c] == se)
+    if not hit.all():
+        # several reference bins may share (chromosome, start): look further along the run
+        miss = np.flatnonzero(~hit)
+        for m in miss:
+            j = lo[m]
+            while j < nr and kr_s[j] == ks[m] and re_s[j] != se[m]:
+                j += 1
+            if j < nr and kr_s[j] == ks[m] and re_s[j] == se[m]:
+                lo_c[m] = j
+            else:
+                return None                           # missing bins
+    return order[lo_c]
 
 
 def _finish(cnarr, ref_matched, diploid_parx_genome):

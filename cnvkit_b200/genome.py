@@ -87,6 +87,15 @@ def chrom_sort_key(label: str):
     return ((2000 if len(rest) == 1 else 3000) + num, rest)
 
 
+def _factorize(chrom):
+    """(codes, unique names in first-appearance order) of a chromosome column -- one hash pass instead
+    of a Python loop over the rows."""
+    import pandas as pd
+
+    codes, uniq = pd.factorize(chrom, sort=False)
+    return codes, list(uniq)
+
+
 def chrom_runs(chromosomes: np.ndarray):
     """Run-length encode a chromosome column.
 
@@ -115,11 +124,11 @@ def autosome_row_mask(chromosomes: np.ndarray, start=None, end=None, diploid_par
     table is used (the reference warns and returns itself).
     """
     chrom = np.asarray(chromosomes, dtype=object)
-    uniq = list(dict.fromkeys(chrom.tolist()))
+    codes, uniq = _factorize(chrom)
     x_label, y_label = infer_sex_chrom_labels(uniq)
-    ok = {u: (is_autosome(str(u), x_label, y_label) and not is_mitochondrial(str(u))
-              and not is_alternative_contig(str(u))) for u in uniq}
-    mask = np.fromiter((ok[c] for c in chrom.tolist()), dtype=bool, count=len(chrom))
+    ok = np.array([(is_autosome(str(u), x_label, y_label) and not is_mitochondrial(str(u))
+                    and not is_alternative_contig(str(u))) for u in uniq], dtype=bool)
+    mask = ok[codes] if len(uniq) else np.zeros(0, dtype=bool)
     if not mask.any():
         return np.ones(len(chrom), dtype=bool)
     if diploid_parx_genome is not None and x_label is not None:
@@ -136,7 +145,7 @@ def genomic_order(chromosomes, start, end) -> np.ndarray:
     """Stable permutation that sorts rows by (chromosome key, start, end) -- GenomicArray.sort
     (gary.py:731-739, mergesort)."""
     chrom = np.asarray(chromosomes, dtype=object)
-    uniq = list(dict.fromkeys(chrom.tolist()))
+    codes, uniq = _factorize(chrom)
     ranked = sorted(uniq, key=lambda c: chrom_sort_key(str(c)))
     # equal keys keep their first-appearance order (stable), distinct names with equal keys share a rank
     rank = {}
@@ -148,5 +157,5 @@ def genomic_order(chromosomes, start, end) -> np.ndarray:
             r += 1
             prev = k
         rank[c] = r
-    ck = np.fromiter((rank[c] for c in chrom.tolist()), dtype=np.int64, count=len(chrom))
+    ck = np.array([rank[c] for c in uniq], dtype=np.int64)[codes] if len(uniq) else np.zeros(0, dtype=np.int64)
     return np.lexsort((np.asarray(end), np.asarray(start), ck))

@@ -108,3 +108,26 @@ def test_do_fix_errors_and_empty_antitarget(F, golden):
         F.do_fix(tgt, anti, shifted)
     with pytest.raises(ValueError, match="Unknown bias_smoother"):
         F.do_fix(tgt, anti, ref, bias_smoother="nope")
+
+
+def test_center_by_precomputed_order_equals_center_by_window(F):
+    """Cohort entry points: cnvk_trait_order_dev + cnvk_center_by_order_dev reproduce
+    cnvk_center_by_window_dev bit for bit (the visiting order depends on the trait and the bin count only)."""
+    import torch
+
+    from cnvkit_b200 import _dev, _lib, smoothing
+
+    rng = np.random.default_rng(12)
+    for n, frac in ((1, 0.5), (7, 0.5), (2000, 0.05), (60000, 0.01)):
+        log2 = rng.normal(0, 0.3, n)
+        key = np.round(rng.beta(8, 8, n), 3)          # many ties: the stable order matters
+        want = F.center_by_window(log2, frac, key)
+        d_log2, d_key = _dev.up(log2), _dev.up(key)
+        d_perm = _dev.shuffle_permutation(n)
+        d_ord = _dev.empty(n, torch.int32)
+        _lib.call("cnvk_trait_order_dev", _dev.ptr(d_key), _dev.ptr(d_perm), n, _dev.ptr(d_ord), _dev.stream())
+        wing = smoothing._width2wing(frac, n) if n >= 2 else 1
+        _lib.call("cnvk_center_by_order_dev", _dev.ptr(d_log2), _dev.ptr(d_ord), n, wing, _dev.stream())
+        np.testing.assert_array_equal(d_log2.cpu().numpy(), want)
+        order = d_ord.cpu().numpy().view(np.uint32)
+        assert sorted(order.tolist()) == list(range(n))
