@@ -334,6 +334,69 @@ struct SlideCfg {
                                + (size_t)L * 2;    // local index -> rank
 };
 
+// ---- in-tile bitonic sort of (ordered key, local index), 8 consecutive elements per thread in registers.
+// Partner distance j < 8: inside the thread; 8 <= j < 256: another lane of the warp (shuffles);
+// j >= 256: another warp (one round trip through shared memory).  Only 10 of the 78 stages of a 4096-slot
+// tile (15 of 91 for 8192) touch shared memory and a barrier.
+__device__ __forceinline__ void sort_cx(u64& k, unsigned short& ix, u64 pk, unsigned short pix, bool keep_min) {
+    const bool mine_greater = k > pk || (k == pk && ix > pix);
+    if (mine_greater == keep_min) { k = pk; ix = pix; }
+}
+
+template <int J>
+__device__ __forceinline__ void sort_in_thread(u64 (&key)[8], unsigned short (&idx)[8], bool asc_hi, int kk) {
+    // kk < 8: the direction depends on the register slot; otherwise it is the thread's (asc_hi)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int p = r ^ J;
+        if (p > r) {
+            const bool asc = kk < 8 ? ((r & kk) == 0) : asc_hi;
+            const bool gt = key[r] > key[p] || (key[r] == key[p] && idx[r] > idx[p]);
+            if (gt == asc) {
+                const u64 tk = key[r]; key[r] = key[p]; key[p] = tk;
+                const unsigned short ti = idx[r]; idx[r] = idx[p]; idx[p] = ti;
+            }
+        }
+    }
+}
+
+template <int L>
+__device__ __forceinline__ void tile_bitonic_sort(u64 (&key)[8], unsigned short (&idx)[8], u64* s_key,
+                                                  unsigned short* s_idx) {
+    const int t = threadIdx.x;
+    for (int k = 2; k <= L; k <<= 1) {
+        const bool asc_hi = ((8 * t) & k) == 0;        // direction of this thread's elements when k >= 8
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 256) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) { s_key[8 * t + r] = key[r]; s_idx[8 * t + r] = idx[r]; }
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i = 8 * t + r, p = i ^ j;
+                    sort_cx(key[r], idx[r], s_key[p], s_idx[p], (i < p) == asc_hi);
+                }
+                __syncthreads();
+            } else if (j >= 8) {
+                const int lm = j >> 3;
+                const bool keep_min = ((t & lm) == 0) == asc_hi;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const u64 pk = __shfl_xor_sync(0xffffffffu, key[r], lm);
+                    const unsigned short pix = (unsigned short)__shfl_xor_sync(0xffffffffu, (unsigned)idx[r], lm);
+                    sort_cx(key[r], idx[r], pk, pix, keep_min);
+                }
+            } else if (j == 4) {
+                sort_in_thread<4>(key, idx, asc_hi, k);
+            } else if (j == 2) {
+                sort_in_thread<2>(key, idx, asc_hi, k);
+            } else {
+                sort_in_thread<1>(key, idx, asc_hi, k);
+            }
+        }
+    }
+}
+
 template <int L>
 __global__ void __launch_bounds__(SlideCfg<L>::THREADS)
 rolling_slide_kernel(const double* __restrict__ x, long long n, long long wing, int mode, double q, int min_periods,
@@ -351,43 +414,36 @@ rolling_slide_kernel(const double* __restrict__ x, long long n, long long wing, 
     const long long M = n + 2 * wing;
     const int nload = (int)min((long long)(T + 2 * wing), M - o0);   // padded elements o0 .. o0+nload-1
     const int nout = (int)min((long long)T, n - o0);
-    // ---- load + keys; slots past the end of the sequence sort after everything, NaN included
-    for (int k = tid; k < L; k += C::THREADS) {
+    // ---- load: thread t owns slots 8t..8t+7; slots past the end of the sequence sort after everything
+    u64 key[8];
+    unsigned short idx[8];
+    int myvalid = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int k = 8 * tid + r;
         double v = 0.0;
-        u64 key = ~0ull;
+        u64 kk = ~0ull;
         if (k < nload) {
             v = x[mirror_index(o0 + k, n, wing)];
-            key = f64_to_ordered(v);
+            kk = f64_to_ordered(v);
         }
         s_val[k] = v;
-        s_key[k] = key;
-        s_idx[k] = (unsigned short)k;
+        key[r] = kk;
+        idx[r] = (unsigned short)k;
+        myvalid += kk != ~0ull;
     }
     if (tid == 0) s_nvalid = 0;
     __syncthreads();
-    // ---- bitonic sort of (key, index)
-    for (int k = 2; k <= L; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < L; i += C::THREADS) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const u64 ka = s_key[i], kb = s_key[p];
-                    const unsigned short ia = s_idx[i], ib = s_idx[p];
-                    const bool gt = ka > kb || (ka == kb && ia > ib);
-                    const bool asc = (i & k) == 0;
-                    if (gt == asc) { s_key[i] = kb; s_key[p] = ka; s_idx[i] = ib; s_idx[p] = ia; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    // ---- ranks; number of valid (non-NaN, in-range) elements = first position holding the NaN key
-    for (int p = tid; p < L; p += C::THREADS) {
-        s_rank[s_idx[p]] = (unsigned short)p;
-        const bool isn = s_key[p] == ~0ull;
-        const bool prevn = p > 0 && s_key[p - 1] == ~0ull;
-        if (isn && !prevn) s_nvalid = p;
-        if (p == L - 1 && !isn) s_nvalid = L;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) myvalid += __shfl_xor_sync(0xffffffffu, myvalid, o);
+    if (lane == 0 && myvalid) atomicAdd(&s_nvalid, myvalid);   // NaN keys (and empty slots) sort last
+    tile_bitonic_sort<L>(key, idx, s_key, s_idx);
+    __syncthreads();
+    // ---- sorted position -> local index, local index -> rank
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        s_idx[8 * tid + r] = idx[r];
+        s_rank[idx[r]] = (unsigned short)(8 * tid + r);
     }
     __syncthreads();
     const int nvalid = s_nvalid;
