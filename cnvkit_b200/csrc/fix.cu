@@ -394,15 +394,20 @@ __global__ void residual_kernel(const double* __restrict__ log2, const u8* __res
     resid[i] = use[i] ? __dsub_rn(log2[i], med[chrom_id[i]]) : __longlong_as_double(0x7ff8000000000000ll);
 }
 
-// sum of sqrt(end-start) and count over a group; also counts used (non-low) bins.  One CTA with a
-// fixed accumulation order (strided per thread, shuffle tree, warps in order): run-to-run
-// deterministic, unlike floating-point atomics.
-__global__ void __launch_bounds__(1024)
-group_size_kernel(const long long* __restrict__ start, const long long* __restrict__ end, const u8* __restrict__ sel,
-                  const u8* __restrict__ use, long long n, double* __restrict__ acc /*[3]: sum sqrt, count, used*/) {
-    __shared__ double s_s[32], s_c[32], s_u[32];
+// sum of sqrt(end-start) and count over a group; also counts used (non-low) bins.  Two stages with a
+// fixed accumulation order (per-CTA partials, then one warp adds them left to right): run-to-run
+// deterministic, unlike floating-point atomics, and not limited to one SM's bandwidth.
+static const int GS_CTAS = 128;
+
+__global__ void __launch_bounds__(256)
+group_size_part_kernel(const long long* __restrict__ start, const long long* __restrict__ end,
+                       const u8* __restrict__ sel, const u8* __restrict__ use, long long n, double* __restrict__ part) {
+    __shared__ double s_s[8], s_c[8], s_u[8];
     double s = 0.0, c = 0.0, u = 0.0;
-    for (long long i = threadIdx.x; i < n; i += 1024) {
+    // contiguous slice per CTA, strided inside it: the order of every partial sum is fixed
+    const long long per = (n + GS_CTAS - 1) / GS_CTAS;
+    const long long i0 = (long long)blockIdx.x * per, i1 = min(n, i0 + per);
+    for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
         if (sel[i]) {
             s += sqrt((double)(end[i] - start[i]));
             c += 1.0;
@@ -413,8 +418,16 @@ group_size_kernel(const long long* __restrict__ start, const long long* __restri
     if ((threadIdx.x & 31) == 0) { s_s[threadIdx.x >> 5] = s; s_c[threadIdx.x >> 5] = c; s_u[threadIdx.x >> 5] = u; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 1; k < 32; ++k) { s += s_s[k]; c += s_c[k]; u += s_u[k]; }
-        acc[0] = s; acc[1] = c; acc[2] = u;
+        for (int k = 1; k < 8; ++k) { s += s_s[k]; c += s_c[k]; u += s_u[k]; }
+        part[3 * blockIdx.x + 0] = s; part[3 * blockIdx.x + 1] = c; part[3 * blockIdx.x + 2] = u;
+    }
+}
+
+__global__ void group_size_final_kernel(const double* __restrict__ part, double* __restrict__ acc) {
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int k = 0; k < GS_CTAS; ++k) v += part[3 * k + threadIdx.x];
+        acc[threadIdx.x] = v;
     }
 }
 
@@ -474,6 +487,8 @@ int fix_finish(double* d_log2, const double* d_depth, const double* d_ref_log2, 
     CNVK_CHECK(scratch.alloc(&resid, (size_t)n));
     CNVK_CHECK(scratch.alloc(&bw, 4));
     CNVK_CHECK(scratch.alloc(&acc, 6));
+    double* gs_part;
+    CNVK_CHECK(scratch.alloc(&gs_part, (size_t)3 * GS_CTAS));
     CNVK_CHECK(scratch.alloc(&flags, 2));
     CNVK_CHECK(cudaMemsetAsync(acc, 0, 6 * sizeof(double), stream));
     CNVK_CHECK(cudaMemsetAsync(flags, 0, 2 * sizeof(int), stream));
@@ -502,7 +517,9 @@ int fix_finish(double* d_log2, const double* d_depth, const double* d_ref_log2, 
             CNVK_LAUNCH_CHECK();
             use_mask_kernel<<<g256, 256, 0, stream>>>(d_log2, d_depth, sel, n, 1, use);   // drop_low_coverage
             CNVK_LAUNCH_CHECK();
-            group_size_kernel<<<1, 1024, 0, stream>>>(d_start, d_end, sel, use, n, acc + 3 * g);
+            group_size_part_kernel<<<GS_CTAS, 256, 0, stream>>>(d_start, d_end, sel, use, n, gs_part);
+            CNVK_LAUNCH_CHECK();
+            group_size_final_kernel<<<1, 32, 0, stream>>>(gs_part, acc + 3 * g);
             CNVK_LAUNCH_CHECK();
         }
         int rc = segmented_median(d_log2, use, d_chrom_off, nchrom, med, cnt, stream);

@@ -26,18 +26,40 @@ __device__ u64 cta_radix_select(const double* __restrict__ x, const unsigned cha
             if (use && !use[i]) continue;
             const u64 key = f64_to_ordered(x[i]);
             if (key == ~0ull) continue;  // NaN
-            if ((key & pmask) == prefix) atomicAdd(&s_hist[(u32)(key >> shift) & 255u], 1u);
+            if ((key & pmask) == prefix) {
+                // warp-aggregated: in the leading passes every key of a segment shares the digit, and
+                // 1024 atomics on one shared-memory word serialise
+                const u32 d = (u32)(key >> shift) & 255u;
+                const u32 active = __activemask();
+                const u32 peers = __match_any_sync(active, d);
+                if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[d], (u32)__popc(peers));
+            }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            long long kk = k;
-            int d = 0;
-            for (; d < 256; ++d) {
-                if (kk < (long long)s_hist[d]) break;
-                kk -= s_hist[d];
+        if (threadIdx.x < 32) {
+            // bucket holding the k-th element: lane l owns buckets 8l..8l+7
+            const int lane = threadIdx.x;
+            u32 c[8], tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { c[q] = s_hist[8 * lane + q]; tot += c[q]; }
+            u32 inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 t_ = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t_;
             }
-            s_state[0] = (u64)d;
-            s_state[1] = (u64)kk;
+            const u32 owners = __ballot_sync(0xffffffffu, (long long)inc > k);
+            const int owner = __ffs(owners) - 1;
+            if (lane == owner) {
+                long long kk = k - (long long)(inc - tot);
+                int q = 0;
+                for (; q < 7; ++q) {
+                    if (kk < (long long)c[q]) break;
+                    kk -= c[q];
+                }
+                s_state[0] = (u64)(8 * lane + q);
+                s_state[1] = (u64)kk;
+            }
         }
         __syncthreads();
         prefix |= s_state[0] << shift;
