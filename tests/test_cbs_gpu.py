@@ -34,8 +34,10 @@ def planted(rng, n, nseg, sigma=0.2):
 
 
 def compare(G, x, w, off, alpha, **kw):
-    P = OC.make_params(alpha=alpha, **kw)
-    o_arm, o_lo, o_hi, o_mean, o_st = OC.segment(x, w, off, P, nthreads=8)
+    # large inputs use the oracle's block-pruned search (equal to its exhaustive scan by
+    # tests/test_oracle_pins.py::test_cbs_oracle_pruned_search_equals_exhaustive); small ones the exhaustive scan
+    P = OC.make_params(alpha=alpha, prune=len(x) > 20000, **kw)
+    o_arm, o_lo, o_hi, o_mean, o_st = OC.segment(x, w, off, P, nthreads=16)
     g_arm, g_lo, g_hi, g_mean, g_st = G.segment_arms(x, w, off, alpha=alpha, **kw)
     np.testing.assert_array_equal(g_arm, o_arm)
     np.testing.assert_array_equal(g_lo, o_lo)
