@@ -1572,8 +1572,15 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         CNVK_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     const int max_ones = (int)std::floor((double)P.nperm * P.alpha) + 1;
-    std::vector<int> sbdry;
-    cbs_getbdry(P.eta, P.nperm, max_ones, sbdry);
+    // the stopping boundary depends on (eta, nperm, max.ones) only and costs ~nperm * max.ones * 20 flops to
+    // build: keep the last one per thread
+    static thread_local std::vector<int> sbdry;
+    static thread_local double sb_eta = -1.0;
+    static thread_local int sb_nperm = -1, sb_ones = -1;
+    if (sb_eta != P.eta || sb_nperm != P.nperm || sb_ones != max_ones) {
+        cbs_getbdry(P.eta, P.nperm, max_ones, sbdry);
+        sb_eta = P.eta; sb_nperm = P.nperm; sb_ones = max_ones;
+    }
 
     Scratch scratch(stream);
     double *d_rw, *d_xc, *d_y, *d_S, *d_cw, *d_wn, *d_bmin, *d_bmax, *d_Sl, *d_cwl;
