@@ -561,6 +561,12 @@ struct TileRef {
     unsigned mask;
 };
 
+struct SeedRes {   // best seed candidate of one task
+    double q;
+    int i, j;
+    long long pad;
+};
+
 // task -> (node a, start block ib, first end block jb0): a host-built table, one int4 per task
 __device__ __forceinline__ void decode_task(const Node* __restrict__ nodes, const int4* __restrict__ task_tab,
                                             int task, int& a, int& ib, int& jb0, int& NJ) {
@@ -606,7 +612,7 @@ __device__ __forceinline__ void cta_commit(Node* nd, double q, int qi, int qj, d
 }
 
 __global__ void __launch_bounds__(256)
-cbs_seed_kernel(Node* __restrict__ nodes, const int4* __restrict__ task_tab,
+cbs_seed_kernel(const Node* __restrict__ nodes, const int4* __restrict__ task_tab, SeedRes* __restrict__ res,
                 const double* __restrict__ blk_min, const double* __restrict__ blk_max,
                 const int* __restrict__ blk_imin, const int* __restrict__ blk_imax,
                 const double* __restrict__ blk_cmin, const double* __restrict__ blk_cmax, int al0) {
@@ -614,8 +620,8 @@ cbs_seed_kernel(Node* __restrict__ nodes, const int4* __restrict__ task_tab,
     __shared__ int s_i[8], s_j[8];
     int a, ib, jb0, NJ;
     decode_task(nodes, task_tab, blockIdx.x, a, ib, jb0, NJ);
-    Node* nd = &nodes[a];
-    if (nd->flat) return;
+    const Node* nd = &nodes[a];
+    if (nd->flat) { if (threadIdx.x == 0) { SeedRes r_; r_.q = -1.0; r_.i = 0x7fffffff; r_.j = 0x7fffffff; r_.pad = 0; res[blockIdx.x] = r_; } return; }
     const int n = nd->hi - nd->lo, boff = nd->blk_off;
     const double total = nd->total;
     double bq = -1.0;
@@ -655,8 +661,55 @@ cbs_seed_kernel(Node* __restrict__ nodes, const int4* __restrict__ task_tab,
             }
         }
     }
-    cta_commit(nd, bq, bi_, bj_, s_q, s_i, s_j);
+    // CTA argmax (ties -> smallest (i,j)); the per-task results are reduced per node by
+    // cbs_seed_reduce_kernel -- no lock, no atomics
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oq = __shfl_xor_sync(0xffffffffu, bq, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi_, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj_, o);
+        if (cand_better(oq, oi, oj, bq, bi_, bj_)) { bq = oq; bi_ = oi; bj_ = oj; }
+    }
+    if (lane == 0) { s_q[warp] = bq; s_i[warp] = bi_; s_j[warp] = bj_; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k)
+            if (cand_better(s_q[k], s_i[k], s_j[k], bq, bi_, bj_)) { bq = s_q[k]; bi_ = s_i[k]; bj_ = s_j[k]; }
+        SeedRes r_;
+        r_.q = bq; r_.i = bi_; r_.j = bj_; r_.pad = 0;
+        res[blockIdx.x] = r_;
+    }
 }
+
+// one warp per node: best of the node's per-task seed candidates and of the arc prep_node left there
+__global__ void __launch_bounds__(128)
+cbs_seed_reduce_kernel(Node* __restrict__ nodes, int nnodes, const int* __restrict__ task_off,
+                       const SeedRes* __restrict__ res) {
+    const int a = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (a >= nnodes) return;
+    Node* nd = &nodes[a];
+    if (nd->flat) return;
+    double q = -1.0;
+    int qi = 0x7fffffff, qj = 0x7fffffff;
+    for (int t = task_off[a] + lane; t < task_off[a + 1]; t += 32) {
+        const SeedRes r_ = res[t];
+        if (cand_better(r_.q, r_.i, r_.j, q, qi, qj)) { q = r_.q; qi = r_.i; qj = r_.j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oq = __shfl_xor_sync(0xffffffffu, q, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, qi, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, qj, o);
+        if (cand_better(oq, oi, oj, q, qi, qj)) { q = oq; qi = oi; qj = oj; }
+    }
+    if (lane == 0 && qi != 0x7fffffff && cand_better(q, qi, qj, nd->best_q, nd->best_i, nd->best_j)) {
+        nd->best_q = q;
+        nd->best_i = qi;
+        nd->best_j = qj;
+    }
+}
+
 
 // upper bound test of one (start block bi, end block jb) pair, bi < jb
 __device__ __forceinline__ bool tile_needed(const double* __restrict__ cw, const double* __restrict__ blk_min,
@@ -1629,8 +1682,10 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
     std::vector<int> h_ptile_off;
     std::vector<int4> h_task_tab;
     int4* d_task_tab = nullptr;
-    size_t cap_tasks = 0;
-    struct TaskGuard { int4*& p; cudaStream_t s; ~TaskGuard() { if (p) cudaFreeAsync(p, s); } } tguard{d_task_tab, stream};
+    SeedRes* d_seedres = nullptr;
+    int* d_task_off = nullptr;
+    size_t cap_tasks = 0, cap_task_off = 0;
+    struct TaskGuard { int4*& p; SeedRes*& r; int*& o; cudaStream_t s; ~TaskGuard() { if (p) cudaFreeAsync(p, s); if (r) cudaFreeAsync(r, s); if (o) cudaFreeAsync(o, s); } } tguard{d_task_tab, d_seedres, d_task_off, stream};
     struct PartGuard { TileSums*& a; TileScan*& b; cudaStream_t s; ~PartGuard() { if (a) cudaFreeAsync(a, s); if (b) cudaFreeAsync(b, s); } } pguard{d_part1, d_part3, stream};
     Node* d_nodes = nullptr;
     Decision* d_dec = nullptr;
@@ -1699,9 +1754,22 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         g_pinned.rewind();   // every copy of the previous level has completed (the level ends with a sync)
         if (h_task_tab.size() > cap_tasks) {
             if (d_task_tab) cudaFreeAsync(d_task_tab, stream);
-            d_task_tab = nullptr;
+            if (d_seedres) cudaFreeAsync(d_seedres, stream);
+            d_task_tab = nullptr; d_seedres = nullptr;
             cap_tasks = h_task_tab.size() * 2;
             CNVK_CHECK(cudaMallocAsync((void**)&d_task_tab, cap_tasks * sizeof(int4), stream));
+            CNVK_CHECK(cudaMallocAsync((void**)&d_seedres, cap_tasks * sizeof(SeedRes), stream));
+        }
+        if ((size_t)nn + 1 > cap_task_off) {
+            if (d_task_off) cudaFreeAsync(d_task_off, stream);
+            d_task_off = nullptr;
+            cap_task_off = ((size_t)nn + 1) * 2;
+            CNVK_CHECK(cudaMallocAsync((void**)&d_task_off, cap_task_off * sizeof(int), stream));
+        }
+        {
+            int* p_to = g_pinned.put(h_tile_off.data(), (size_t)nn + 1);
+            CNVK_PIN_CHECK(p_to);
+            CNVK_CHECK(cudaMemcpyAsync(d_task_off, p_to, ((size_t)nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
         }
         if (!h_task_tab.empty()) {
             int4* p_tab = g_pinned.put(h_task_tab.data(), h_task_tab.size());
@@ -1739,7 +1807,9 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 const int grid = sm_count * 4;
                 if (P.prune & 1) {
                     ProfScope ps(PC_CBS_SEED, stream);
-                    cbs_seed_kernel<<<(int)tiles, 256, 0, stream>>>(d_nodes, d_task_tab, d_bmin, d_bmax, d_bimin, d_bimax, d_bcmin, d_bcmax, P.min_width);
+                    cbs_seed_kernel<<<(int)tiles, 256, 0, stream>>>(d_nodes, d_task_tab, d_seedres, d_bmin, d_bmax, d_bimin, d_bimax, d_bcmin, d_bcmax, P.min_width);
+                    CNVK_LAUNCH_CHECK();
+                    cbs_seed_reduce_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, nn, d_task_off, d_seedres);
                     CNVK_LAUNCH_CHECK();
                 }
                 {
