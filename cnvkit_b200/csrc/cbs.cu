@@ -786,16 +786,25 @@ cbs_band_kernel(Node* __restrict__ nodes, int nnodes,
         const double Si = iok ? sp[il].x : __longlong_as_double(0x7ff8000000000000ll), ci = iok ? sp[il].y : 0.0;
         const unsigned kw_span = (unsigned)(n - 2 * al0);   // al0 <= kw <= n - al0  <=>  kw - al0 <= n - 2 al0
         const int wend = min(warp * BAND_SUB + BAND_SUB - 1, npts - 1);
+        // weight of the lightest al0-wide window that starts in this warp's sub-block
+        double wmin = (il + al0 < npts) ? sp[il + al0].y - ci : INFINITY;
+        if (PRUNE) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+        }
         // lane <-> end sub-block: one bound test each, then walk the survivors (warp-uniform)
         unsigned need = 0;
         {
             const int sb = lane;
             bool keep = sb >= warp && sb < nsub;
-            if (PRUNE && keep && sb > warp + 1 && gq >= 0.0) {
+            if (PRUNE && keep && gq >= 0.0) {
                 const int j0 = sb * BAND_SUB, j1 = min(j0 + BAND_SUB - 1, npts - 1);
                 const double d1 = s_mx[sb] - s_mn[warp], d2 = s_mx[warp] - s_mn[sb];
                 const double dm = fmax(fabs(d1), fabs(d2));
-                const double cmin = sp[j0].y - sp[wend].y, cmax = sp[j1].y - sp[warp * BAND_SUB].y;
+                // lightest arc: for the own and the next sub-block every admissible arc holds an
+                // al0-wide window that starts in this warp's sub-block (the weights are >= 0)
+                const double cmin = (sb > warp + 1) ? sp[j0].y - sp[wend].y : wmin;
+                const double cmax = sp[j1].y - sp[warp * BAND_SUB].y;
                 const double fmin_ = fmin(cmin * (total - cmin), cmax * (total - cmax));
                 if (fmin_ > 0.0 && (dm * dm) / fmin_ * (1.0 + 1e-9) < gq) keep = false;
             }
