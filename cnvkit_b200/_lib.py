@@ -73,6 +73,10 @@ SIGNATURES = {
     "cnvk_haar_segment": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_double, c_int64, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
     "cnvk_cbs_getbdry": (c_int, [c_double, c_int32, c_int32, c_void_p]),
+    "cnvk_bootstrap_ci_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
+    "cnvk_bootstrap_ci": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                  c_void_p]),
     "cnvk_tsv_open": (c_int, [c_char_p, c_void_p]),
     "cnvk_tsv_close": (None, [c_void_p]),
     "cnvk_tsv_shape": (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -113,6 +117,19 @@ class CbsStats(ctypes.Structure):
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class BootParams(ctypes.Structure):
+    """cnvk_boot_params (include/cnvkit_b200.h)."""
+
+    _fields_ = [
+        ("alpha", c_double),
+        ("bootstraps", c_int32),
+        ("smooth_upto", c_int32),
+        ("pcg_state", c_uint64 * 2),
+        ("pcg_inc", c_uint64 * 2),
+        ("noise_seed", c_uint64),
+    ]
 
 
 class CnvkError(RuntimeError):

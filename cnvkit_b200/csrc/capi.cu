@@ -121,7 +121,7 @@ struct HostCall {
 extern "C" {
 
 const char* cnvk_last_error(void) { return g_err; }
-int cnvk_abi_version(void) { return 2; }
+int cnvk_abi_version(void) { return 3; }
 unsigned long long cnvk_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
 
 void cnvk_prof_enable(int on) { g_prof_enabled = on; }
@@ -332,6 +332,51 @@ int cnvk_biweight_columns(const double* mat, int32_t rows, int64_t ncols, int32_
     RC(biweight_columns(dm, rows, ncols, mode, dl, dv, hc.stream));
     if (mode & 1) RC(hc.download(loc, dl, (size_t)ncols));
     if (mode & 2) RC(hc.download(var, dv, (size_t)ncols));
+    return hc.finish();
+}
+
+static void boot_pcg(const cnvk_boot_params* p, u64 pcg[4]) {
+    pcg[0] = p->pcg_state[0]; pcg[1] = p->pcg_state[1]; pcg[2] = p->pcg_inc[0]; pcg[3] = p->pcg_inc[1];
+    if (!(pcg[0] | pcg[1] | pcg[2] | pcg[3])) {   // numpy.random.PCG64(0xA5EED).state
+        pcg[0] = 0x52637b81f59d8cc6ull; pcg[1] = 0x00b11abc6a6a0481ull;
+        pcg[2] = 0x392a8421e3a06208ull; pcg[3] = 0x808513643339beb7ull;
+    }
+}
+
+int cnvk_bootstrap_ci_dev(const double* d_values, const double* d_weights, const int64_t* seg_lo,
+                          const int64_t* seg_hi, int32_t n_segs, const cnvk_boot_params* params,
+                          double* d_ci_lo, double* d_ci_hi, void* stream) {
+    RC(ensure_init());
+    u64 pcg[4];
+    boot_pcg(params, pcg);
+    return bootstrap_ci(d_values, d_weights, (const long long*)seg_lo, (const long long*)seg_hi, n_segs, params->alpha,
+                        params->bootstraps, params->smooth_upto, pcg, params->noise_seed, d_ci_lo, d_ci_hi,
+                        (cudaStream_t)stream);
+}
+
+int cnvk_bootstrap_ci(const double* values, const double* weights, int64_t n, const int64_t* seg_lo,
+                      const int64_t* seg_hi, int32_t n_segs, const cnvk_boot_params* params, double* ci_lo,
+                      double* ci_hi) {
+    for (int32_t s = 0; s < n_segs; ++s) {
+        if (seg_lo[s] < 0 || seg_hi[s] > n || seg_hi[s] < seg_lo[s]) {
+            set_last_error("cnvk_bootstrap_ci: segment %d spans rows [%lld, %lld) of %lld", (int)s,
+                           (long long)seg_lo[s], (long long)seg_hi[s], (long long)n);
+            return -2;
+        }
+    }
+    HostCall hc;
+    RC(hc.begin());
+    double *dv, *dw, *dl, *dh;
+    RC(hc.upload(values, (size_t)n, &dv));
+    RC(hc.upload(weights, (size_t)n, &dw));
+    CNVK_CHECK(hc.scratch->alloc(&dl, (size_t)n_segs));
+    CNVK_CHECK(hc.scratch->alloc(&dh, (size_t)n_segs));
+    u64 pcg[4];
+    boot_pcg(params, pcg);
+    RC(bootstrap_ci(dv, dw, (const long long*)seg_lo, (const long long*)seg_hi, n_segs, params->alpha,
+                    params->bootstraps, params->smooth_upto, pcg, params->noise_seed, dl, dh, hc.stream));
+    RC(hc.download(ci_lo, dl, (size_t)n_segs));
+    RC(hc.download(ci_hi, dh, (size_t)n_segs));
     return hc.finish();
 }
 

@@ -54,6 +54,11 @@ int round_sig(const double* d_x, long long n, int digits, double* d_out, unsigne
 int segment_bin_sums(const double* d_depth, const double* d_weight, const long long* d_lo, const long long* d_hi,
                      int nseg, double* d_seg_weight, double* d_seg_depth, cudaStream_t stream);
 
+// bootstrap.cu
+int bootstrap_ci(const double* d_values, const double* d_weights, const long long* h_lo, const long long* h_hi,
+                 int n_segs, double alpha, int bootstraps, int smooth_upto, const u64 pcg[4], u64 noise_seed,
+                 double* d_ci_lo, double* d_ci_hi, cudaStream_t stream);
+
 // peak.cu
 int fp64_peak(int iters, int reps, double* tflops, cudaStream_t stream);
 

@@ -8,7 +8,8 @@
 The reference calls its seams through module attributes (``fix.do_fix`` at
 cnvlib/commands.py:1177 and cnvlib/batch.py:524, ``reference.do_reference`` at commands.py:1017 and
 batch.py:411, ``segmentation.do_segmentation`` at commands.py:1290 and batch.py:547,
-``smoothing.rolling_median`` at fix.py:417), so rebinding those attributes -- plus the public
+``smoothing.rolling_median`` at fix.py:417, ``segmetrics.do_segmetrics`` at batch.py:559 and
+commands.py's segmetrics command), so rebinding those attributes -- plus the public
 aliases commands.py:979/1128/1277 creates at import time -- is the whole integration.
 Options outside the GPU path (``method='hmm'``, ``bias_smoother='loess'``, ``do_cluster``,
 ``variants``, ``smooth_cbs``) are forwarded to the original callables untouched.
@@ -71,23 +72,62 @@ def _segment_needs_reference(args, kwargs):
     return method not in ("cbs", "haar") or (variants is not None and len(variants) > 0) or bool(smooth)
 
 
+def _segmetrics_seam(ours, theirs):
+    """do_segmetrics(cnarr, segarr, location_stats, spread_stats, interval_stats, alpha, bootstraps,
+    smoothed, skip_low)  cnvlib/segmetrics.py:24-34: the bootstrap 'ci' columns come from the GPU, every
+    other statistic from the reference (called without 'ci'), in the reference's column order."""
+
+    def seam(*args, **kwargs):
+        interval = list(_arg(args, kwargs, 4, "interval_stats", ()))
+        if "ci" not in interval:
+            return theirs(*args, **kwargs)
+        names = ("cnarr", "segarr", "location_stats", "spread_stats", "interval_stats", "alpha", "bootstraps",
+                 "smoothed", "skip_low")
+        kw = dict(zip(names, args))
+        kw.update(kwargs)
+        rest = [s for s in interval if s != "ci"]
+        try:
+            ci = ours(kw["cnarr"], kw["segarr"], interval_stats=["ci"], alpha=kw.get("alpha", 0.05),
+                      bootstraps=kw.get("bootstraps", 100), smoothed=kw.get("smoothed", 10),
+                      skip_low=kw.get("skip_low", False))
+        except NotImplementedError:
+            return theirs(*args, **kwargs)
+        if not (kw.get("location_stats") or kw.get("spread_stats") or rest):
+            return ci
+        out = theirs(**dict(kw, interval_stats=rest))
+        # the reference writes ci_lo/ci_hi before pi_lo/pi_hi (segmetrics.py:111-119)
+        pi = {c: out.data.pop(c) for c in ("pi_lo", "pi_hi") if c in out.data.columns}
+        out["ci_lo"] = ci["ci_lo"].to_numpy()
+        out["ci_hi"] = ci["ci_hi"].to_numpy()
+        for c, v in pi.items():
+            out[c] = v.to_numpy()
+        return out
+
+    seam.__name__ = getattr(theirs, "__name__", "seam")
+    seam.__doc__ = getattr(ours, "__doc__", None)
+    seam.__wrapped__ = theirs
+    return seam
+
+
 def install():
     """Rebind cnvlib's hot-path seams to the B200 implementations.  Idempotent."""
     if _saved:
         return
-    from . import _lib, fix, reference, segmentation, smoothing
+    from . import _lib, fix, reference, segmentation, segmetrics, smoothing
 
     _lib.load()  # fail now, loudly, if the CUDA library is not built
     r_fix = _resolve("cnvlib.fix")
     r_ref = _resolve("cnvlib.reference")
     r_seg = _resolve("cnvlib.segmentation")
     r_smooth = _resolve("cnvlib.smoothing")
+    r_metrics = _resolve("cnvlib.segmetrics")
     plan = [
         (r_fix, "do_fix", _route(fix.do_fix, r_fix.do_fix, _fix_needs_reference)),
         (r_ref, "do_reference", _route(reference.do_reference, r_ref.do_reference, _reference_needs_reference)),
         (r_seg, "do_segmentation", _route(segmentation.do_segmentation, r_seg.do_segmentation,
                                           _segment_needs_reference)),
         (r_smooth, "rolling_median", smoothing.rolling_median),
+        (r_metrics, "do_segmetrics", _segmetrics_seam(segmetrics.do_segmetrics, r_metrics.do_segmetrics)),
     ]
     cmds = sys.modules.get("cnvlib.commands")
     for mod, name, new in plan:

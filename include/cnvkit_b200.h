@@ -222,6 +222,34 @@ int cnvk_cbs_segment(const double* log2, const double* weight, const int64_t* ar
  * out[max_ones*(max_ones+1)/2]. Host-only. */
 int cnvk_cbs_getbdry(double eta, int32_t nperm, int32_t max_ones, int32_t* out);
 
+/* ---- segment metrics ------------------------------------------------------------------------ */
+/* cnvlib/segmetrics.py:176-245 confidence_interval_bootstrap (the 'ci' interval statistic of
+ * do_segmetrics, :24-121, which `cnvkit.py batch` runs after segmentation, batch.py:559-566) for every
+ * segment of a table.  Segment s resamples the bins [seg_lo[s], seg_hi[s]) of values / weights with
+ * numpy's default_rng(0xA5EED).integers(0, k, (bootstraps, k)) -- the PCG64 stream and Lemire's
+ * bounded-integer rejection are reproduced draw for draw -- and takes percentiles of the weighted
+ * means, each summed in np.average's pairwise order.  bootstraps is raised to ceil(2/alpha) like the
+ * reference does.  smooth_upto: -1 never smooth (BCa correction, :292-351), otherwise smooth
+ * segments of <= smooth_upto bins (INT32_MAX = always): N(0, k^-1/4 sqrt(1-w)) noise on every
+ * resampled value (:248-289; the reference's noise generator is unseeded, ours is counter-based
+ * on noise_seed).  pcg_state / pcg_inc = {high, low} words of the generator's initial 128-bit state
+ * and increment; all zero selects numpy's PCG64(0xA5EED).  k == 0 -> NaN, k == 1 -> the bin's value.
+ * seg_lo / seg_hi are HOST arrays. */
+typedef struct cnvk_boot_params {
+    double alpha;
+    int32_t bootstraps;
+    int32_t smooth_upto;
+    uint64_t pcg_state[2];
+    uint64_t pcg_inc[2];
+    uint64_t noise_seed;
+} cnvk_boot_params;
+int cnvk_bootstrap_ci_dev(const double* d_values, const double* d_weights, const int64_t* seg_lo,
+                          const int64_t* seg_hi, int32_t n_segs, const cnvk_boot_params* params,
+                          double* d_ci_lo, double* d_ci_hi, void* stream);
+int cnvk_bootstrap_ci(const double* values, const double* weights, int64_t n, const int64_t* seg_lo,
+                      const int64_t* seg_hi, int32_t n_segs, const cnvk_boot_params* params, double* ci_lo,
+                      double* ci_hi);
+
 /* ---- HaarSeg ------------------------------------------------------------------------------ */
 /* cnvlib/segmentation/haar.py:257-371 haarSeg(signal, breaksFdrQ, weights) for every arm of a batch
  * (haarStartLevel 1, haarEndLevel 5; the arms are those of segment_haar's by_arm(), haar.py:80-82).

@@ -349,11 +349,56 @@ def gen_exome_mini(R):
     save("exome_mini", **arrays)
 
 
+def gen_segmetrics(R):
+    """segmetrics.confidence_interval_bootstrap / do_segmetrics(interval_stats=['ci']) known answers:
+    seeded synthetic segments of many sizes, and test/formats/amplicon.cnr + .cns (the tables of
+    test_analysis.py:270-311)."""
+    from cnvlib import segmetrics  # the unmodified reference
+
+    rng = np.random.default_rng(0x5E6)
+    arrays = {}
+    cases = []
+    sizes = [2, 3, 4, 5, 7, 8, 9, 11, 16, 31, 64, 100, 127, 128, 129, 137, 255, 256, 257, 300, 520, 1000, 2049, 5000]
+    for i, k in enumerate(sizes):
+        level = rng.choice([-1.0, -0.4, 0.0, 0.3, 0.58])
+        v = level + rng.normal(0, 0.25, k)
+        if i % 5 == 0:
+            v[rng.integers(0, k)] += 3.0         # an outlier makes the jackknife skewed
+        w = np.clip(rng.uniform(0.3, 1.0, k), 1e-4, 1)
+        arrays[f"unit{i}_values"] = v
+        arrays[f"unit{i}_weights"] = w
+        for alpha, boots in ((0.05, 100), (0.5, 100), (0.05, 30), (0.01, 100)):
+            ci = segmetrics.confidence_interval_bootstrap(v, w, alpha, boots, False)
+            arrays[f"unit{i}_ci_a{alpha}_b{boots}"] = np.asarray(ci, dtype=float)
+        cases.append(k)
+    arrays["unit_sizes"] = np.asarray(cases)
+    # one smoothed realisation per size (the reference's noise is unseeded: statistical comparison only)
+    for i, k in enumerate(sizes):
+        reps = np.array([segmetrics.confidence_interval_bootstrap(arrays[f"unit{i}_values"], arrays[f"unit{i}_weights"],
+                                                                  0.5, 100, True) for _ in range(8)])
+        arrays[f"unit{i}_ci_smoothed_a0.5_reps"] = reps
+
+    cnr = R.read_cna(os.path.join(R.root, "test", "formats", "amplicon.cnr"))
+    cns = R.read_cna(os.path.join(R.root, "test", "formats", "amplicon.cns"))
+    arrays.update(table_arrays(cnr, "cnr"))
+    arrays.update(table_arrays(cns, "cns"))
+    sel = [ser.index.to_numpy() for ser in cnr.iter_ranges_of(cns, "log2", "outer", True)]
+    arrays["sel_lo"] = np.asarray([s[0] if len(s) else 0 for s in sel])
+    arrays["sel_hi"] = np.asarray([s[-1] + 1 if len(s) else 0 for s in sel])
+    assert all(len(s) == 0 or np.array_equal(s, np.arange(s[0], s[-1] + 1)) for s in sel)
+    for tag, kw in (("default", dict()), ("bca", dict(smoothed=False)), ("bca_a0.5_b50", dict(smoothed=False, alpha=0.5, bootstraps=50)),
+                    ("batch", dict(alpha=0.5, smoothed=True))):
+        sm = segmetrics.do_segmetrics(cnr, cns, interval_stats=["ci"], **kw)
+        arrays[f"amplicon_{tag}_ci_lo"] = sm["ci_lo"].to_numpy()
+        arrays[f"amplicon_{tag}_ci_hi"] = sm["ci_hi"].to_numpy()
+    save("segmetrics", **arrays)
+
+
 def main():
     logging.basicConfig(level=logging.ERROR)
     os.makedirs(OUT, exist_ok=True)
     R = refshim.load()
-    which = sys.argv[1:] or ["smoothing", "regression", "haar", "fix_units", "exome_mini"]
+    which = sys.argv[1:] or ["smoothing", "regression", "haar", "fix_units", "exome_mini", "segmetrics"]
     for w in which:
         globals()["gen_" + w](R)
 

@@ -28,7 +28,7 @@ def test_ctypes_table_matches_header():
 
 def test_abi_version_and_host_only_calls():
     lib = _lib.load()
-    assert lib.cnvk_abi_version() == 2
+    assert lib.cnvk_abi_version() == 3
     from cnvkit_b200.segmentation import cbs
 
     b = cbs.getbdry(0.05, 10000, 2)  # host-only entry point
