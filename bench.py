@@ -194,6 +194,30 @@ def exome_leg(args, torch, dev):
         out[f"ms_per_sample_fix_{m}"] = 1e3 * dt
         out[f"segments_{m}"] = [len(r[1]) for r in res]
     out["value"] = 1.0 / (out["ms_per_sample_fix_cbs"] * 1e-3)
+    # the same with the batch command's bootstrap confidence intervals per segment (batch.py:559-566)
+    panel.run(cols[:2], method="cbs", ci=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res_ci = panel.run(cols, method="cbs", batch=1, ci=True, keep_cnr=True)
+    torch.cuda.synchronize()
+    out["ms_per_sample_fix_cbs_ci_incl_cnr_copy"] = 1e3 * (time.perf_counter() - t0) / len(cols)
+    cnr0, cns0 = res_ci[0]
+    from cnvkit_b200 import segmetrics as _sm
+    b_lo, b_hi = _sm.segment_bin_ranges(cnr0.data, cns0.data)
+    v0, w0 = cnr0["log2"].to_numpy(), cnr0["weight"].to_numpy()
+    _sm.bootstrap_ci(v0, w0, b_lo, b_hi, 0.5, 100, True)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        _sm.bootstrap_ci(v0, w0, b_lo, b_hi, 0.5, 100, True)
+    ci_ms = 1e3 * (time.perf_counter() - t0) / 5
+    from oracle import segmetrics as _OS
+    t0 = time.perf_counter()
+    _OS.ci_table(v0, w0, b_lo, b_hi, 0.5, 100, True)
+    ci_cpu_s = time.perf_counter() - t0
+    out["bootstrap_ci"] = {"segments": int(len(b_lo)), "bins": int(len(v0)), "resampled_values": int(100 * (b_hi - b_lo).sum()),
+                           "ms_host_call": ci_ms, "cpu_port_s": ci_cpu_s,
+                           "note": "cnvk_bootstrap_ci with host columns (H2D + 4 kernels + D2H) vs oracle/segmetrics.py "
+                                   "(numpy, 1 core) on the first sample's segments; alpha 0.5, 100 smoothed replicates"}
     # device time by kernel class for one sample (fix + cbs + haar)
     _lib.prof_enable(True)
     _lib.prof_reset()

@@ -24,7 +24,7 @@ import numpy as np
 import pandas as pd
 import torch
 
-from . import _dev, _lib, fix, genome, params, segmentation, smoothing, tabio
+from . import _dev, _lib, fix, genome, params, segmentation, segmetrics, smoothing, tabio
 from .cnary import arm_ranges
 from .segmentation import cbs as _cbs
 from .segmentation import haar as _haar
@@ -114,6 +114,23 @@ class _Group:
         return d_log2, d_depth
 
 
+BATCH_CI = dict(alpha=0.5, bootstraps=100, smoothed=True)     # cnvlib/batch.py:559-566
+
+
+def _ci_options(ci):
+    """None / False -> no intervals; True -> the batch command's settings; dict -> do_segmetrics keywords."""
+    if not ci:
+        return None
+    opts = dict(BATCH_CI)
+    if isinstance(ci, dict):
+        unknown = set(ci) - {"alpha", "bootstraps", "smoothed"}
+        if unknown:
+            raise ValueError(f"unknown confidence-interval options: {sorted(unknown)}")
+        opts = dict(alpha=0.05, bootstraps=100, smoothed=10)   # do_segmetrics' own defaults
+        opts.update(ci)
+    return opts
+
+
 class Panel:
     """Sample-independent plan for fix + segment over a shared bin set.
 
@@ -199,10 +216,13 @@ class Panel:
         return self.meta_cls(df, {"sample_id": sample_id})
 
     # ------------------------------------------------------------------ segment
-    def segment(self, samples, method="cbs", threshold=None, skip_outliers=10, sample_ids=None):
+    def segment(self, samples, method="cbs", threshold=None, skip_outliers=10, sample_ids=None, ci=None):
         """do_segmentation(method) for a list of (d_log2, d_weight, d_depth) device triples over the
         panel's .cnr rows; all samples are segmented in one batched device call.  Returns one .cns
-        CopyNumArray per sample."""
+        CopyNumArray per sample.  With `ci` (True = the batch command's alpha 0.5 / smoothed bootstrap, or a
+        dict of do_segmetrics keywords) every table also gets the `ci_lo` / `ci_hi` columns of
+        do_segmetrics(cnr, cns, interval_stats=["ci"], ...) (cnvlib/batch.py:559-566)."""
+        ci = _ci_options(ci)
         if method not in ("cbs", "haar"):
             raise ValueError("cohort segmentation implements 'cbs' and 'haar'")
         if threshold is None:
@@ -260,12 +280,14 @@ class Panel:
                 s_unit = u[sel] - info["unit0"]
                 s_lo, s_hi = lo[sel] - info["base"], hi[sel] - info["base"]
                 results[k] = self._segments_table(samples[k], info, s_unit, s_lo, s_hi, mean[sel],
-                                                  None if sample_ids is None else sample_ids[k])
+                                                  None if sample_ids is None else sample_ids[k], ci)
         for k, info in enumerate(per):
             if info is None:  # non-finite ratios: the general path handles the per-arm drops
                 cnr = self.cnr_table(*samples[k], sample_id=None if sample_ids is None else sample_ids[k])
                 results[k] = segmentation.do_segmentation(cnr, method, self.diploid_parx_genome, threshold=threshold,
                                                           skip_outliers=skip_outliers)
+                if ci:
+                    results[k] = segmetrics.do_segmetrics(cnr, results[k], interval_stats=["ci"], **ci)
         return results
 
     def _quantise(self, x, w):
@@ -315,7 +337,7 @@ class Panel:
                 unit_arm.append(a)
         return np.asarray(units, dtype=np.int64), np.asarray(unit_arm, dtype=np.int64)
 
-    def _segments_table(self, sample, info, s_unit, s_lo, s_hi, s_mean, sample_id):
+    def _segments_table(self, sample, info, s_unit, s_lo, s_hi, s_mean, sample_id, ci=None):
         d_log2, d_w, d_depth = sample
         src = info["fidx"]
         seg_arm = info["unit_arm"][s_unit]
@@ -329,15 +351,24 @@ class Panel:
         out = self.meta_cls(segtab, {"sample_id": sample_id})
         out.sort()
         out.sort_columns()
+        if ci:
+            # segmetrics.py:93: the bins each (stretched) segment overlaps, filtered bins included
+            b_lo, b_hi = segmetrics.segment_bin_ranges(self.bins, out.data)
+            c_lo, c_hi = segmetrics.bootstrap_ci(None, None, b_lo, b_hi, device_ptrs=(d_log2.data_ptr(), d_w.data_ptr()),
+                                                 stream=_dev.stream(), **ci)
+            out["ci_lo"] = c_lo.cpu().numpy()
+            out["ci_hi"] = c_hi.cpu().numpy()
         return out
 
     # ------------------------------------------------------------------ driver
-    def run(self, samples, method="cbs", threshold=None, batch=16, sample_ids=None, keep_cnr=False, workers=1):
+    def run(self, samples, method="cbs", threshold=None, batch=16, sample_ids=None, keep_cnr=False, workers=1,
+            ci=None):
         """fix + segment for an iterable of (target, antitarget) coverage tables.  Returns a list of
         (.cnr or None, .cns) per sample, in input order; `batch` consecutive samples share one
         segmentation call.  With `workers` > 1 the batches are processed by that many host threads,
         each on its own CUDA stream, so that the host side of one batch (table assembly, gene names)
-        overlaps the device side of another."""
+        overlaps the device side of another.  `ci`: see `segment`."""
+        ci = _ci_options(ci)
         samples = list(samples)
         n = len(samples)
         ids = [sample_ids[k] if sample_ids is not None else getattr(samples[k][0], "sample_id", None)
@@ -355,13 +386,15 @@ class Panel:
                 if trip is None:  # general path for this sample
                     t_tab, a_tab = self._as_tables(tgt, anti, ids[k])
                     cnr = fix.do_fix(t_tab, a_tab, self._reference_table(), self.diploid_parx_genome, *self.opts)
-                    out[k] = (cnr if keep_cnr else None,
-                              segmentation.do_segmentation(cnr, method, self.diploid_parx_genome, threshold=threshold))
+                    cns = segmentation.do_segmentation(cnr, method, self.diploid_parx_genome, threshold=threshold)
+                    if ci:
+                        cns = segmetrics.do_segmetrics(cnr, cns, interval_stats=["ci"], **ci)
+                    out[k] = (cnr if keep_cnr else None, cns)
                     continue
                 pend.append(trip)
                 pend_k.append(k)
             if pend:
-                cns = self.segment(pend, method, threshold, sample_ids=[ids[k] for k in pend_k])
+                cns = self.segment(pend, method, threshold, sample_ids=[ids[k] for k in pend_k], ci=ci)
                 for trip, k, seg in zip(pend, pend_k, cns):
                     out[k] = (self.cnr_table(*trip, sample_id=ids[k]) if keep_cnr else None, seg)
             return out
@@ -423,13 +456,14 @@ class Panel:
 
 
 def run_files(target_fnames, antitarget_fnames, reference, out_dir, method="cbs", threshold=None, batch=8, workers=4,
-              io_threads=8, diploid_parx_genome=None, do_gc=True, do_edge=True, do_rmask=True, write_cnr=True):
+              io_threads=8, diploid_parx_genome=None, do_gc=True, do_edge=True, do_rmask=True, write_cnr=True, ci=None):
     """File-to-file cohort run: the fix -> segment core of `cnvkit.py batch` (cnvlib/batch.py:524-555) for
     samples that share one panel.  Reads every sample's `.targetcoverage.cnn` / `.antitargetcoverage.cnn`
     with the native columns-only reader (bin sets verified by hash against the first sample), runs the
     shared-panel plan on the GPU, and writes `<sample>.cnr` / `<sample>.cns` into `out_dir` with the native
     `%.6g` writer.  Files whose bins differ from the first sample's (or that hold NaN coverage) go through
-    the general per-sample path.  Returns the list of (cnr_path or None, cns_path)."""
+    the general per-sample path.  `ci=True` adds the batch command's bootstrap `ci_lo` / `ci_hi` columns
+    (batch.py:559-566) to every `.cns`.  Returns the list of (cnr_path or None, cns_path)."""
     import os
     from concurrent.futures import ThreadPoolExecutor
 
@@ -474,7 +508,7 @@ def run_files(target_fnames, antitarget_fnames, reference, out_dir, method="cbs"
     with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool:
         loaded = list(pool.map(load, range(n)))
         results = panel.run(loaded, method=method, threshold=threshold, batch=batch, sample_ids=ids, keep_cnr=write_cnr,
-                            workers=workers)
+                            workers=workers, ci=ci)
 
         def store(k):
             cnr, cns = results[k]

@@ -162,3 +162,42 @@ def test_run_files_writes_the_tables_of_the_per_sample_path(world, tmp_path):
         assert open(cnr_path, "rb").read() == open(a, "rb").read()
         assert open(cns_path, "rb").read() == open(b, "rb").read()
         assert os.path.basename(cns_path) == f"S{k}.cns"
+
+
+def test_cohort_confidence_intervals_equal_do_segmetrics(world, tmp_path):
+    """Panel.run(ci=...) adds exactly the columns of do_segmetrics(cnr, cns, interval_stats=['ci'], ...) --
+    the step `cnvkit.py batch` runs after segmentation (batch.py:559-566) -- and they agree with the CPU
+    oracle on the same bins; run_files writes them into the .cns."""
+    from cnvkit_b200 import cohort, segmetrics, tabio
+    from oracle import segmetrics as OS
+
+    bins, ref, tabs = world
+    T0, A0, R = tabs[0]
+    panel = cohort.Panel(T0, A0, R)
+    pairs = [(T, A) for T, A, _ in tabs[:3]]
+    plain = panel.run(pairs, method="cbs", keep_cnr=True)
+    for ci, kw in ((True, dict(alpha=0.5, bootstraps=100, smoothed=True)),
+                   (dict(alpha=0.05, smoothed=False), dict(alpha=0.05, bootstraps=100, smoothed=False))):
+        got = panel.run(pairs, method="cbs", keep_cnr=True, ci=ci)
+        for (cnr, cns), (_, cns_ci) in zip(plain, got):
+            want = segmetrics.do_segmetrics(cnr, cns, interval_stats=["ci"], **kw)
+            assert_same(cns_ci, want)
+            d, s = cnr.data, cns.data
+            lo, hi = OS.bin_ranges(d["chromosome"], d["start"], d["end"], s["chromosome"], s["start"], s["end"])
+            assert (hi - lo >= s["probes"].to_numpy()).all()          # filtered bins count too
+            olo, ohi = OS.ci_table(d["log2"].to_numpy(), d["weight"].to_numpy(), lo, hi, **kw)
+            np.testing.assert_allclose(cns_ci["ci_lo"].to_numpy(), olo, rtol=0, atol=1e-9)
+            np.testing.assert_allclose(cns_ci["ci_hi"].to_numpy(), ohi, rtol=0, atol=1e-9)
+            assert (cns_ci["ci_lo"].to_numpy() <= cns_ci["ci_hi"].to_numpy()).all()
+    # file-to-file
+    tf, af = [], []
+    for k, (T, A, _) in enumerate(tabs[:2]):
+        tf.append(str(tmp_path / f"S{k}.targetcoverage.cnn"))
+        af.append(str(tmp_path / f"S{k}.antitargetcoverage.cnn"))
+        tabio.write(T, tf[-1])
+        tabio.write(A, af[-1])
+    outs = cohort.run_files(tf, af, R, str(tmp_path / "out"), ci=True, workers=2, batch=1)
+    for _, cns_path in outs:
+        tab = tabio.read(cns_path)
+        assert {"ci_lo", "ci_hi"} <= set(tab.data.columns)
+        assert np.isfinite(tab["ci_lo"].to_numpy()).all() and (tab["ci_lo"].to_numpy() <= tab["ci_hi"].to_numpy()).all()

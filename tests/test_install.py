@@ -57,3 +57,41 @@ def test_out_of_scope_options_reach_the_reference():
     finally:
         I.uninstall()
         R.segmentation.do_segmentation = real
+
+
+@pytest.mark.needs_reference
+def test_segmetrics_seam_merges_reference_columns_with_ours(golden):
+    """Statistics outside the GPU path come from the reference, 'ci' from ours, columns in the
+    reference's order (segmetrics.py:93-119).  The GPU call is replaced by the numpy oracle here."""
+    import numpy as np
+
+    from oracle import refshim
+    from oracle import segmetrics as OS
+
+    R = refshim.load()
+    from cnvlib import segmetrics as ref_sm
+
+    import os
+
+    cnr = R.read_cna(os.path.join(R.root, "test", "formats", "amplicon.cnr"))
+    cns = R.read_cna(os.path.join(R.root, "test", "formats", "amplicon.cns"))
+
+    def ours(cnarr, segarr, interval_stats=(), alpha=0.05, bootstraps=100, smoothed=10, skip_low=False):
+        d, s = cnarr.data, segarr.data
+        lo, hi = OS.bin_ranges(d["chromosome"], d["start"], d["end"], s["chromosome"], s["start"], s["end"])
+        out = segarr.copy()
+        out["ci_lo"], out["ci_hi"] = OS.ci_table(d["log2"].to_numpy(), d["weight"].to_numpy(), lo, hi, alpha,
+                                                 bootstraps, smoothed)
+        return out
+
+    seam = I._segmetrics_seam(ours, ref_sm.do_segmetrics)
+    kw = dict(location_stats=["mean", "median"], spread_stats=["stdev"], interval_stats=["pi", "ci"], smoothed=False)
+    got = seam(cnr, cns, **kw)
+    exp = ref_sm.do_segmetrics(cnr, cns, **kw)
+    assert list(got.data.columns) == list(exp.data.columns)
+    for col in exp.data.columns[len(cns.data.columns):]:
+        np.testing.assert_allclose(got[col].to_numpy(), exp[col].to_numpy(), rtol=0, atol=1e-9, equal_nan=True)
+    only_ci = seam(cnr, cns, interval_stats=["ci"], smoothed=False)
+    assert list(only_ci.data.columns) == list(cns.data.columns) + ["ci_lo", "ci_hi"]
+    no_ci = seam(cnr, cns, location_stats=["mean"])
+    assert "ci_lo" not in no_ci.data.columns and "mean" in no_ci.data.columns
