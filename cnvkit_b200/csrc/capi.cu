@@ -335,6 +335,32 @@ int cnvk_biweight_columns(const double* mat, int32_t rows, int64_t ncols, int32_
     return hc.finish();
 }
 
+int cnvk_fasta_gc_lo_dev(const uint8_t* d_bytes, int64_t nbytes, const int64_t* d_range_lo,
+                         const int64_t* d_range_hi, int64_t n_ranges, double* d_gc, double* d_rmask,
+                         void* stream) {
+    RC(ensure_init());
+    return fasta_gc_lo(d_bytes, nbytes, (const long long*)d_range_lo, (const long long*)d_range_hi, n_ranges, d_gc,
+                       d_rmask, (cudaStream_t)stream);
+}
+
+int cnvk_fasta_gc_lo(const uint8_t* bytes, int64_t nbytes, const int64_t* range_lo, const int64_t* range_hi,
+                     int64_t n_ranges, double* gc, double* rmask) {
+    HostCall hc;
+    RC(hc.begin());
+    unsigned char* db;
+    long long *dl, *dh;
+    double *dg, *dr;
+    RC(hc.upload((const unsigned char*)bytes, (size_t)nbytes, &db));
+    RC(hc.upload((const long long*)range_lo, (size_t)n_ranges, &dl));
+    RC(hc.upload((const long long*)range_hi, (size_t)n_ranges, &dh));
+    CNVK_CHECK(hc.scratch->alloc(&dg, (size_t)n_ranges));
+    CNVK_CHECK(hc.scratch->alloc(&dr, (size_t)n_ranges));
+    RC(fasta_gc_lo(db, nbytes, dl, dh, n_ranges, dg, dr, hc.stream));
+    RC(hc.download(gc, dg, (size_t)n_ranges));
+    RC(hc.download(rmask, dr, (size_t)n_ranges));
+    return hc.finish();
+}
+
 static void boot_pcg(const cnvk_boot_params* p, u64 pcg[4]) {
     pcg[0] = p->pcg_state[0]; pcg[1] = p->pcg_state[1]; pcg[2] = p->pcg_inc[0]; pcg[3] = p->pcg_inc[1];
     if (!(pcg[0] | pcg[1] | pcg[2] | pcg[3])) {   // numpy.random.PCG64(0xA5EED).state

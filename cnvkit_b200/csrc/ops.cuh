@@ -59,6 +59,10 @@ int bootstrap_ci(const double* d_values, const double* d_weights, const long lon
                  int n_segs, double alpha, int bootstraps, int smooth_upto, const u64 pcg[4], u64 noise_seed,
                  double* d_ci_lo, double* d_ci_hi, cudaStream_t stream);
 
+// fasta.cu
+int fasta_gc_lo(const unsigned char* d_bytes, long long nbytes, const long long* d_lo, const long long* d_hi,
+                long long n, double* d_gc, double* d_rm, cudaStream_t stream);
+
 // peak.cu
 int fp64_peak(int iters, int reps, double* tflops, cudaStream_t stream);
 

@@ -6,9 +6,10 @@ raise the same errors.  On the device: per-normal ``bias_correct_logr`` (centre,
 shift, GC / RepeatMasker / edge centring by window at fraction 0.1) and ``summarize_info`` (Tukey
 biweight location and midvariance of every bin across the S+1 samples, one warp per bin).
 
-Outside the hot path and therefore *not* reimplemented: FASTA GC/RepeatMasker
-extraction (``fa_fname``), sex inference from coverage (pass ``female_samples`` or ``sexes``) and
-sample clustering (``do_cluster``).
+``fa_fname`` adds the GC / RepeatMasker columns by counting letters of the FASTA file on the device
+(``cnvkit_b200.fasta``, reference.py:859-895).  Outside the hot path and therefore *not* reimplemented
+(SURVEY.md section 2): sex inference from coverage (pass ``female_samples`` or ``sexes``) and sample
+clustering (``do_cluster``).
 """
 from __future__ import annotations
 
@@ -65,13 +66,12 @@ def do_reference(
         raise ValueError(
             f"Unequal number of target and antitarget files given: targets = {len(target_fnames)!r}, "
             f"antitargets = {len(antitarget_fnames)!r}")
-    if fa_fname:
-        raise NotImplementedError("FASTA GC/RepeatMasker extraction (fa_fname) is outside the GPU hot path")
     if do_cluster:
         raise NotImplementedError("do_cluster=True is outside the GPU hot path")
     if bias_smoother != "median":
         raise NotImplementedError("only bias_smoother='median' runs on the GPU path")
-    logging.info("No FASTA reference genome provided; skipping GC, RM calculations")
+    if not fa_fname:
+        logging.info("No FASTA reference genome provided; skipping GC, RM calculations")
     if sexes is None:
         if female_samples is None:
             raise NotImplementedError(
@@ -130,8 +130,10 @@ def load_sample_block(filenames, fa_fname, is_haploid_x, diploid_parx_genome, se
     cnarr1 = _read(filenames[0])
     if len(cnarr1) == 0:
         cols = ["chromosome", "start", "end", "gene", "log2", "depth"]
-        if "gc" in cnarr1:
+        if "gc" in cnarr1 or fa_fname:
             cols.append("gc")
+        if fa_fname:
+            cols.append("rmask")
         cols.append("spread")
         dev = _dev.device()
         return (pd.DataFrame.from_records([], columns=cols),
@@ -143,9 +145,18 @@ def load_sample_block(filenames, fa_fname, is_haploid_x, diploid_parx_genome, se
     start = d1["start"].to_numpy(dtype=np.int64)
     end = d1["end"].to_numpy(dtype=np.int64)
     ref_columns = {"chromosome": d1["chromosome"], "start": d1["start"], "end": d1["end"], "gene": d1["gene"]}
-    have_gc = "gc" in cnarr1 and fix_gc
-    if have_gc:
+    gc_col = rm_col = None
+    if fa_fname and (fix_rmask or fix_gc):         # reference.py:552-557
+        from . import fasta
+
+        gc_vals, rm_vals = fasta.get_fasta_stats(cnarr1, fa_fname)
+        if fix_gc:
+            gc_col = ref_columns["gc"] = gc_vals
+        if fix_rmask:
+            rm_col = ref_columns["rmask"] = rm_vals
+    elif "gc" in cnarr1 and fix_gc:                # reuse .cnn GC values (import-picard)
         ref_columns["gc"] = d1["gc"]
+        gc_col = d1["gc"].to_numpy(dtype=np.float64)
     names, offsets, chrom_id = genome.chrom_runs(chrom)
     is_x, is_y, is_y_all = _sex_chrom_rows(chrom, start, end, diploid_parx_genome)
     # expect_flat_log2 (cnary.py:635-664)
@@ -158,7 +169,8 @@ def load_sample_block(filenames, fa_fname, is_haploid_x, diploid_parx_genome, se
     d_auto = _dev.up(auto.astype(np.uint8))
     d_flat = _dev.up(flat)
     d_xy = _dev.up((is_x.astype(np.uint8) | (is_y.astype(np.uint8) << 1)))
-    d_gc = _dev.up(d1["gc"].to_numpy(dtype=np.float64)) if have_gc else None
+    d_gc = _dev.up(np.asarray(gc_col, dtype=np.float64)) if gc_col is not None else None
+    d_rm = _dev.up(np.asarray(rm_col, dtype=np.float64)) if rm_col is not None else None
     d_edge = None
     if fix_edge:
         d_edge = _dev.empty(n, torch.float64)
@@ -216,7 +228,7 @@ def load_sample_block(filenames, fa_fname, is_haploid_x, diploid_parx_genome, se
         is_xx = True if known is None else bool(known)
         skipped = ctypes.c_int32(0)
         _lib.call("cnvk_bias_correct_logr_dev", _dev.ptr(d_log2), _dev.ptr(d_depth), _dev.ptr(d_auto), n,
-                  _dev.ptr(d_off), len(names), _dev.ptr(d_gc), 0, _dev.ptr(d_edge), int(bool(skip_low)), wing,
+                  _dev.ptr(d_off), len(names), _dev.ptr(d_gc), _dev.ptr(d_rm), _dev.ptr(d_edge), int(bool(skip_low)), wing,
                   _dev.ptr(d_perm), _dev.ptr(d_flat), _dev.ptr(d_xy), int(is_xx), ctypes.addressof(skipped),
                   _dev.stream())
         if skipped.value:

@@ -222,6 +222,17 @@ int cnvk_cbs_segment(const double* log2, const double* weight, const int64_t* ar
  * out[max_ones*(max_ones+1)/2]. Host-only. */
 int cnvk_cbs_getbdry(double eta, int32_t nperm, int32_t max_ones, int32_t* out);
 
+/* ---- reference build: GC / RepeatMasker content from the genome ------------------------------ */
+/* cnvlib/reference.py:859-880 get_fasta_stats / calculate_gc_lo: for byte range r of a FASTA file
+ * image (the bin's sequence under the .fai line geometry; line breaks and non-ACGT letters do not
+ * count), gc[r] = (#G + #C) / #ACGT and rmask[r] = #lowercase ACGT / #ACGT in either case, 0 when
+ * the range holds no ACGT.  Ranges are clamped to [0, nbytes). */
+int cnvk_fasta_gc_lo_dev(const uint8_t* d_bytes, int64_t nbytes, const int64_t* d_range_lo,
+                         const int64_t* d_range_hi, int64_t n_ranges, double* d_gc, double* d_rmask,
+                         void* stream);
+int cnvk_fasta_gc_lo(const uint8_t* bytes, int64_t nbytes, const int64_t* range_lo, const int64_t* range_hi,
+                     int64_t n_ranges, double* gc, double* rmask);
+
 /* ---- segment metrics ------------------------------------------------------------------------ */
 /* cnvlib/segmetrics.py:176-245 confidence_interval_bootstrap (the 'ci' interval statistic of
  * do_segmetrics, :24-121, which `cnvkit.py batch` runs after segmentation, batch.py:559-566) for every

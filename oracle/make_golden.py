@@ -394,11 +394,90 @@ def gen_segmetrics(R):
     save("segmetrics", **arrays)
 
 
+def synth_fasta(rng, lengths, width=60):
+    """A small soft-masked genome: random ACGT with lowercase repeat runs, N gaps and a few IUPAC codes."""
+    lines = []
+    for name, L in lengths.items():
+        seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=L, p=[0.29, 0.21, 0.21, 0.29])
+        gc_rich = rng.integers(0, max(L - 5000, 1), size=max(L // 20000, 1))
+        for g in gc_rich:
+            seq[g:g + 4000] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=len(seq[g:g + 4000]), p=[0.15, 0.35, 0.35, 0.15])
+        for _ in range(max(L // 3000, 1)):           # repeats -> lowercase
+            a = rng.integers(0, L)
+            b = min(L, a + int(rng.geometric(1 / 400)))
+            seq[a:b] |= 0x20
+        for _ in range(max(L // 40000, 1)):          # assembly gaps
+            a = rng.integers(0, L)
+            seq[a:a + int(rng.integers(10, 3000))] = ord("N")
+        for a in rng.integers(0, L, size=max(L // 5000, 1)):
+            seq[a] = rng.choice(np.frombuffer(b"RYKMSWnry", dtype=np.uint8))
+        text = seq.tobytes().decode()
+        lines.append(f">{name} synthetic")
+        lines.extend(text[i:i + width] for i in range(0, L, width))
+    return "\n".join(lines) + "\n"
+
+
+def gen_fasta(R):
+    """reference.get_fasta_stats / calculate_gc_lo known answers and a do_reference(fa_fname=...) run on a
+    synthetic soft-masked genome (the pyfaidx calls go through oracle/refshim_stubs/pyfaidx.py)."""
+    import pandas as pd
+
+    rng = np.random.default_rng(0xFA57A)
+    arrays = {}
+    seqs = ["", "N" * 50, "ACGT", "acgt", "AAAA", "ggcc", "ACGTNNNNacgtRYKM", "nnnnACGTTGCAacgtnn\n", "GATTACA" * 37]
+    seqs += ["".join(rng.choice(list("ACGTacgtNn"), size=int(k))) for k in (1, 2, 15, 16, 17, 31, 33, 64, 100, 1000, 4097)]
+    arrays["kat_seqs"] = np.asarray(seqs, dtype=str)
+    arrays["kat_gc_lo"] = np.asarray([R.reference.calculate_gc_lo(q) for q in seqs], dtype=float)
+
+    lengths = {"chr1": 150_011, "chr2": 90_000, "chrX": 61_234, "chrY": 20_001}
+    text = synth_fasta(rng, lengths)
+    arrays["fasta_bytes"] = np.frombuffer(text.encode(), dtype=np.uint8)
+    rows = []
+    for name, L in lengths.items():
+        pos = 200
+        while pos < L - 2000:                        # targets
+            size = int(np.clip(rng.normal(267, 60), 80, 1000))
+            rows.append((name, pos, pos + size, f"G{len(rows) // 7}"))
+            pos += size + int(rng.lognormal(6.5, 1.0))
+        rows.append((name, L - 150, L + 500, "Edge"))            # runs past the end of the sequence
+    tgt = pd.DataFrame(rows, columns=["chromosome", "start", "end", "gene"])
+    anti_rows = []
+    for name, L in lengths.items():
+        for a in range(0, L, 15_000):
+            anti_rows.append((name, a, min(a + 14_000, L), "Antitarget"))
+    anti = pd.DataFrame(anti_rows, columns=["chromosome", "start", "end", "gene"])
+    with tempfile.TemporaryDirectory() as tmp:
+        fa = os.path.join(tmp, "genome.fa")
+        with open(fa, "w") as handle:
+            handle.write(text)
+        for tag, bins in (("tgt", tgt), ("anti", anti)):
+            probe = R.cnary.CopyNumArray(bins.assign(log2=0.0, depth=1.0), {"sample_id": "probe"})
+            gc, rm = R.reference.get_fasta_stats(probe, fa)
+            arrays[f"{tag}_gc"], arrays[f"{tag}_rmask"] = gc, rm
+            arrays.update(table_arrays(probe, tag))
+        # three normals through the unmodified do_reference with the FASTA
+        tnames, anames = [], []
+        for k in range(3):
+            for tag, bins, names, sd in (("targetcoverage", tgt, tnames, 0.25), ("antitargetcoverage", anti, anames, 0.12)):
+                gcv = arrays["tgt_gc" if bins is tgt else "anti_gc"]
+                log2 = rng.normal(0, sd, len(bins)) + 1.5 * (gcv - 0.45) * (k - 1) + rng.normal(0, 0.5, 1)
+                log2[bins["chromosome"].to_numpy() == "chrY"] -= 6.0          # female samples
+                cna = R.cnary.CopyNumArray(bins.assign(log2=log2, depth=np.exp2(log2) * 80), {"sample_id": f"N{k}"})
+                path = os.path.join(tmp, f"N{k}.{tag}.cnn")
+                R.tabio.write(cna, path)
+                names.append(path)
+                arrays[f"N{k}_{tag}_log2"] = cna["log2"].to_numpy()
+                arrays[f"N{k}_{tag}_depth"] = cna["depth"].to_numpy()
+        ref = R.reference.do_reference(tnames, anames, fa, female_samples=True)
+        arrays.update(table_arrays(ref, "ref"))
+    save("fasta", **arrays)
+
+
 def main():
     logging.basicConfig(level=logging.ERROR)
     os.makedirs(OUT, exist_ok=True)
     R = refshim.load()
-    which = sys.argv[1:] or ["smoothing", "regression", "haar", "fix_units", "exome_mini", "segmetrics"]
+    which = sys.argv[1:] or ["smoothing", "regression", "haar", "fix_units", "exome_mini", "segmetrics", "fasta"]
     for w in which:
         globals()["gen_" + w](R)
 

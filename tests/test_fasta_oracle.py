@@ -1,0 +1,87 @@
+"""CPU-only: FASTA GC / RepeatMasker content -- the oracle (oracle/np_oracle.py) against vectors of the
+unmodified reference (tests/golden/fasta.npz), and the host logic of cnvkit_b200.fasta (index scan,
+.fai parsing, base -> file-offset ranges) checked by counting the byte ranges with numpy."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+
+
+def count_ranges(data, lo, hi):
+    return np.array([O.calculate_gc_lo(data[a:b].tobytes()) for a, b in zip(lo, hi)])
+
+
+def test_calculate_gc_lo_known_answers(golden):
+    g = golden("fasta")
+    got = np.array([O.calculate_gc_lo(str(q)) for q in g["kat_seqs"]])
+    np.testing.assert_array_equal(got, g["kat_gc_lo"])
+
+
+def test_fasta_stats_oracle_matches_reference(golden):
+    g = golden("fasta")
+    text = g["fasta_bytes"].tobytes().decode()
+    for tag in ("tgt", "anti"):
+        gc, rm = O.fasta_stats(text, g[f"{tag}__chromosome"], g[f"{tag}__start"], g[f"{tag}__end"])
+        np.testing.assert_array_equal(gc, g[f"{tag}_gc"])
+        np.testing.assert_array_equal(rm, g[f"{tag}_rmask"])
+
+
+@pytest.mark.parametrize("variant", ["scan", "fai", "crlf", "no_final_newline"])
+def test_host_index_and_byte_ranges(golden, tmp_path, variant):
+    from cnvkit_b200 import fasta
+
+    g = golden("fasta")
+    text = g["fasta_bytes"].tobytes().decode()
+    if variant == "crlf":
+        text = text.replace("\n", "\r\n")
+    if variant == "no_final_newline":
+        text = text.rstrip("\n")
+    path = str(tmp_path / "genome.fa")
+    with open(path, "wb") as fh:
+        fh.write(text.encode())
+    seqs = O.parse_fasta(text)
+    index = fasta.build_index(path)
+    assert list(index) == list(seqs)
+    for name, seq in seqs.items():
+        assert index[name].length == len(seq), (name, index[name])
+        assert index[name].linebases == 60
+        assert index[name].linewidth == (62 if variant == "crlf" else 61)
+    if variant == "fai":
+        with open(path + ".fai", "w") as fh:
+            for name, e in index.items():
+                fh.write(f"{name}\t{e.length}\t{e.offset}\t{e.linebases}\t{e.linewidth}\n")
+        assert fasta.read_index(path) == index
+    else:
+        assert fasta.read_index(path) == index
+    data = np.frombuffer(text.encode(), dtype=np.uint8)
+    for tag in ("tgt", "anti"):
+        chrom, start, end = g[f"{tag}__chromosome"], g[f"{tag}__start"], g[f"{tag}__end"]
+        gc = np.zeros(len(chrom))
+        rm = np.zeros(len(chrom))
+        for name in dict.fromkeys(chrom.tolist()):
+            rows = np.flatnonzero(chrom == name)
+            lo, hi = fasta.byte_ranges(index[name], start[rows], end[rows])
+            assert (hi >= lo).all() and lo.min() >= index[name].offset
+            vals = count_ranges(data, lo, hi)
+            gc[rows], rm[rows] = vals[:, 0], vals[:, 1]
+        np.testing.assert_array_equal(gc, g[f"{tag}_gc"])
+        np.testing.assert_array_equal(rm, g[f"{tag}_rmask"])
+    # slices outside the sequence are empty, as in Python
+    e = index["chr2"]
+    lo, hi = fasta.byte_ranges(e, [e.length + 5, 0, e.length - 1], [e.length + 50, 0, e.length + 7])
+    assert hi[0] == lo[0] and hi[1] == lo[1] and hi[2] == lo[2] + 1
+
+
+def test_compressed_or_bad_input_is_refused(tmp_path):
+    from cnvkit_b200 import fasta
+
+    gz = tmp_path / "g.fa.gz"
+    gz.write_bytes(b"\x1f\x8b\x08\x00rest")
+    with pytest.raises(NotImplementedError):
+        fasta.build_index(str(gz))
+    bad = tmp_path / "bad.fa"
+    bad.write_bytes(b"not a fasta\nACGT\n")
+    with pytest.raises(ValueError):
+        fasta.build_index(str(bad))
