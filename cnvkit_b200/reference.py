@@ -8,8 +8,8 @@ biweight location and midvariance of every bin across the S+1 samples, one warp 
 
 ``fa_fname`` adds the GC / RepeatMasker columns by counting letters of the FASTA file on the device
 (``cnvkit_b200.fasta``, reference.py:859-895).  Outside the hot path and therefore *not* reimplemented
-(SURVEY.md section 2): sex inference from coverage (pass ``female_samples`` or ``sexes``) and sample
-clustering (``do_cluster``).
+(SURVEY.md section 2): sample clustering (``do_cluster``).  With ``female_samples=None`` each sample's sex
+is inferred from its coverage as the reference does (medians on the device, reference.py:284-382).
 """
 from __future__ import annotations
 
@@ -74,14 +74,121 @@ def do_reference(
         logging.info("No FASTA reference genome provided; skipping GC, RM calculations")
     if sexes is None:
         if female_samples is None:
-            raise NotImplementedError(
-                "sex inference from coverage stays with the reference (cnvlib/reference.py:284-382); pass "
-                "female_samples=True/False or sexes={sample_id: is_female}")
-        logging.info(f"Provided sample sex is {'female' if female_samples else 'male'}. ")
-        sexes = {fbase(f): female_samples for f in target_fnames}
+            # reference.py:226-239: infer from coverage, targets reconciled with antitargets
+            logging.info("Sample sex not provided; inferring from samples. ")
+            t_guesses = _guess_sexes(target_fnames, False, diploid_parx_genome)
+            if antitarget_fnames:
+                a_guesses = _guess_sexes(antitarget_fnames, False, diploid_parx_genome)
+                sexes = _reconcile_sex_guesses(t_guesses, a_guesses)
+            else:
+                sexes = {sid: is_xx for sid, (is_xx, _lr) in t_guesses.items()}
+        else:
+            logging.info(f"Provided sample sex is {'female' if female_samples else 'male'}. ")
+            sexes = {fbase(f): female_samples for f in target_fnames}
     ref = combine_probes(target_fnames, antitarget_fnames, fa_fname, is_haploid_x_reference, diploid_parx_genome,
                          sexes, do_gc, do_edge, do_rmask, do_cluster, min_cluster_size)
     return ref
+
+
+def compare_sex_chromosomes(cnarr, is_haploid_x_reference=False, diploid_parx_genome=None):
+    """CopyNumArray.compare_sex_chromosomes (cnvlib/cnary.py:484-632) for a coverage table without a
+    weight column: medians of log2 over the autosomes, chrX and chrY (exact radix-select medians on the
+    device), "maleness" ratios against the expected positions, AND-gate of the two.  Returns
+    (is_male or None, stats)."""
+    if not len(cnarr):
+        return None, {}
+    d = cnarr.data
+    if "weight" in d.columns:
+        raise NotImplementedError("weighted sex-chromosome medians (a 'weight' column) stay with cnvlib")
+    chrom = d["chromosome"].to_numpy()
+    start = d["start"].to_numpy(dtype=np.int64)
+    end = d["end"].to_numpy(dtype=np.int64)
+    log2 = d["log2"].to_numpy(dtype=np.float64)
+    if np.isnan(log2).any():
+        raise NotImplementedError("NaN log2 values in a coverage table")
+    is_x, is_y, _ = _sex_chrom_rows(chrom, start, end, diploid_parx_genome)
+    if not is_x.any():
+        return None, {}
+    auto = genome.autosome_row_mask(chrom, start, end, diploid_parx_genome)
+    n = len(log2)
+    d_x = _dev.up(log2)
+    d_off = _dev.up(np.array([0, n], dtype=np.int64))
+    meds = []
+    for mask in (auto, is_x, is_y):
+        if not mask.any():
+            meds.append(np.nan)
+            continue
+        d_med, d_cnt = _dev.empty(1, torch.float64), _dev.empty(1, torch.int32)
+        _lib.call("cnvk_segmented_median_dev", _dev.ptr(d_x), _dev.ptr(_dev.up(mask.astype(np.uint8))), _dev.ptr(d_off), 1,
+                  _dev.ptr(d_med), _dev.ptr(d_cnt), _dev.stream())
+        meds.append(float(d_med.cpu()[0]))
+    auto_med, chrx_med, chry_med = meds
+
+    def maleness(observed_med, female_shift, male_shift):
+        ratio = observed_med - auto_med
+        return abs(ratio + female_shift) / max(abs(ratio + male_shift), 1e-6)
+
+    female_x_shift, male_x_shift = (-1, 0) if is_haploid_x_reference else (0, +1)
+    chrx_male_lr = maleness(chrx_med, female_x_shift, male_x_shift)
+    if is_y.any():
+        chry_male_lr = maleness(chry_med, -params.NULL_LOG2_COVERAGE, 0.0)
+        is_male = chrx_male_lr > 1.0 and chry_male_lr > 1.0
+        chry_ratio = chry_med - auto_med
+    else:
+        chry_male_lr = np.nan
+        chry_ratio = np.nan
+        is_male = chrx_male_lr > 1.0
+    return bool(is_male), {"chrx_ratio": chrx_med - auto_med, "chry_ratio": chry_ratio,
+                           "chrx_male_lr": chrx_male_lr, "chry_male_lr": chry_male_lr}
+
+
+def _guess_sexes(cnn_fnames, is_haploid_x, diploid_parx_genome, verbose=True):
+    """cnvlib/reference.py:284-321: {sample_id: (is_xx, chrx_male_lr)} where sex is determinable."""
+    guesses = {}
+    for fname in cnn_fnames:
+        cnarr = _read(fname)
+        if not len(cnarr):
+            continue
+        is_xy, stats = compare_sex_chromosomes(cnarr, is_haploid_x, diploid_parx_genome)
+        if is_xy is None:
+            continue
+        if verbose:
+            x_label, y_label = genome.infer_sex_chrom_labels(list(dict.fromkeys(cnarr.data["chromosome"].tolist())))
+            logging.info("Relative log2 coverage of %s=%.3g, %s=%.3g (maleness chrX=%.3g, chrY=%.3g) --> assuming %s",
+                         x_label or "chrX", stats["chrx_ratio"], y_label or "chrY", stats["chry_ratio"],
+                         stats["chrx_male_lr"], stats["chry_male_lr"], "male" if is_xy else "female")
+        guesses[cnarr.sample_id] = (not is_xy, stats["chrx_male_lr"])
+    return guesses
+
+
+def _chrx_maleness_confidence(chrx_male_lr):
+    """cnvlib/reference.py:324-332."""
+    if not (chrx_male_lr > 0.0 and np.isfinite(chrx_male_lr)):
+        return 0.0
+    return abs(float(np.log(chrx_male_lr)))
+
+
+def _reconcile_sex_guesses(target_guesses, antitarget_guesses):
+    """cnvlib/reference.py:335-382: the target call stands unless the antitargets' chrX signal is strictly
+    more decisive, in which case only their chrX call is adopted."""
+    sexes = {sid: is_xx for sid, (is_xx, _lr) in target_guesses.items()}
+    for sid, (a_is_xx, a_lr) in antitarget_guesses.items():
+        if sid not in target_guesses:
+            sexes[sid] = a_is_xx
+            continue
+        t_is_xx, t_lr = target_guesses[sid]
+        if t_is_xx == a_is_xx:
+            continue
+        if _chrx_maleness_confidence(a_lr) > _chrx_maleness_confidence(t_lr):
+            sexes[sid] = a_lr <= 1.0
+            preferred = "antitargets"
+        else:
+            sexes[sid] = t_is_xx
+            preferred = "targets"
+        logging.warning("Sample %s chromosomal X/Y ploidy looks like %s in targets but %s in antitargets; "
+                        "preferring %s (more decisive chrX coverage)", sid, "female" if t_is_xx else "male",
+                        "female" if a_is_xx else "male", preferred)
+    return sexes
 
 
 def combine_probes(filenames, antitarget_fnames, fa_fname, is_haploid_x, diploid_parx_genome, sexes, fix_gc,

@@ -473,11 +473,62 @@ def gen_fasta(R):
     save("fasta", **arrays)
 
 
+def gen_sex(R):
+    """CopyNumArray.compare_sex_chromosomes (cnary.py:484-632) and reference._reconcile_sex_guesses
+    (reference.py:335-382) known answers on synthetic coverage tables."""
+    import pandas as pd
+
+    rng = np.random.default_rng(0x5E)
+    arrays = {}
+    chroms = ["chr1", "chr2", "chr3", "chrX", "chrY"]
+    sizes = [400, 300, 251, 180, 41]
+    cases = []
+    for i, (x_shift, y_shift, drop_y, haploid, parx) in enumerate([
+            (0.0, -18.0, False, False, None), (-1.0, 0.0, False, False, None), (-0.45, -9.0, False, False, None),
+            (-0.55, -10.5, False, False, None), (0.0, 0.0, True, False, None), (-1.0, 0.0, True, False, None),
+            (1.0, -19.0, False, True, None), (0.0, 0.2, False, True, None), (-1.0, -0.3, False, False, "grch38"),
+            (-0.9, -19.5, False, False, None), (0.1, 0.3, False, False, None)]):
+        rows = []
+        for c, m in zip(chroms, sizes):
+            if c == "chrY" and drop_y:
+                continue
+            pos = np.sort(rng.choice(np.arange(10_000, 150_000_000, 1000), size=m, replace=False))
+            if c in ("chrX", "chrY"):
+                pos[:6] = np.arange(6) * 20_000 + 100_000          # a few bins inside PAR1
+            shift = x_shift if c == "chrX" else y_shift if c == "chrY" else 0.0
+            for p in pos:
+                rows.append((c, int(p), int(p) + 500, "G", shift + rng.normal(0, 0.3)))
+        df = pd.DataFrame(rows, columns=["chromosome", "start", "end", "gene", "log2"])
+        df["depth"] = np.exp2(df["log2"]) * 50
+        cna = R.cnary.CopyNumArray(df, {"sample_id": f"S{i}"})
+        is_xy, stats = cna.compare_sex_chromosomes(haploid, parx)
+        arrays.update(table_arrays(cna, f"case{i}"))
+        arrays[f"case{i}_is_xy"] = np.asarray(-1 if is_xy is None else int(is_xy))
+        arrays[f"case{i}_stats"] = np.asarray([stats.get(k, np.nan) for k in ("chrx_ratio", "chry_ratio", "chrx_male_lr", "chry_male_lr")], dtype=float)
+        arrays[f"case{i}_haploid"] = np.asarray(int(haploid))
+        arrays[f"case{i}_parx"] = np.asarray(parx or "")
+        cases.append(i)
+    arrays["n_cases"] = np.asarray(len(cases))
+    # reconcile: (target guess, antitarget guess) -> final is_xx
+    recon_in = [((True, 0.2), (True, 0.3)), ((True, 0.9), (False, 5.0)), ((False, 4.0), (True, 0.8)), ((False, 1.2), (True, 0.1)),
+                ((True, 0.5), (False, 2.0)), ((True, float("nan")), (False, 3.0)), ((False, 2.0), (True, float("inf"))),
+                ((True, 0.7), None), (None, (False, 2.5))]
+    outs = []
+    for k, (t, a) in enumerate(recon_in):
+        tg = {f"s{k}": (np.bool_(t[0]), t[1])} if t else {}
+        ag = {f"s{k}": (np.bool_(a[0]), a[1])} if a else {}
+        outs.append(int(bool(R.reference._reconcile_sex_guesses(tg, ag)[f"s{k}"])))
+    arrays["recon_t"] = np.asarray([[-1, np.nan] if t is None else [int(t[0]), t[1]] for t, _ in recon_in], dtype=float)
+    arrays["recon_a"] = np.asarray([[-1, np.nan] if a is None else [int(a[0]), a[1]] for _, a in recon_in], dtype=float)
+    arrays["recon_out"] = np.asarray(outs)
+    save("sex", **arrays)
+
+
 def main():
     logging.basicConfig(level=logging.ERROR)
     os.makedirs(OUT, exist_ok=True)
     R = refshim.load()
-    which = sys.argv[1:] or ["smoothing", "regression", "haar", "fix_units", "exome_mini", "segmetrics", "fasta"]
+    which = sys.argv[1:] or ["smoothing", "regression", "haar", "fix_units", "exome_mini", "segmetrics", "fasta", "sex"]
     for w in which:
         globals()["gen_" + w](R)
 
