@@ -17,6 +17,7 @@ Options outside the GPU path (``method='hmm'``, ``bias_smoother='loess'``, ``do_
 from __future__ import annotations
 
 import importlib
+import logging
 import sys
 
 _saved = {}
@@ -35,7 +36,11 @@ def _route(ours, theirs, needs_reference):
     def seam(*args, **kwargs):
         if needs_reference(args, kwargs):
             return theirs(*args, **kwargs)
-        return ours(*args, **kwargs)
+        try:
+            return ours(*args, **kwargs)
+        except NotImplementedError as exc:   # an input shape the GPU path declines (it never guesses)
+            logging.info("cnvkit_b200: %s -- using cnvlib for this call", exc)
+            return theirs(*args, **kwargs)
 
     seam.__name__ = getattr(theirs, "__name__", "seam")
     seam.__doc__ = getattr(ours, "__doc__", None)

@@ -95,3 +95,13 @@ def test_segmetrics_seam_merges_reference_columns_with_ours(golden):
     assert list(only_ci.data.columns) == list(cns.data.columns) + ["ci_lo", "ci_hi"]
     no_ci = seam(cnr, cns, location_stats=["mean"])
     assert "ci_lo" not in no_ci.data.columns and "mean" in no_ci.data.columns
+
+
+def test_declined_inputs_fall_back_to_the_reference():
+    def ours(x):
+        if x == "odd":
+            raise NotImplementedError("nested bins")
+        return "ours"
+
+    seam = I._route(ours, lambda x: "theirs", lambda a, k: False)
+    assert seam("plain") == "ours" and seam("odd") == "theirs"
