@@ -237,7 +237,7 @@ boot_replicate_kernel(const double* __restrict__ values, const double* __restric
     // numpy pairwise recursion over the k terms, leaves filled in order
     int st_n[24];
     unsigned char st_stage[24];
-    double st_a[24], st_unused_[1];
+    double st_a[24];
     int d = 0;
     st_n[0] = (int)k;
     st_stage[0] = 0;
@@ -306,7 +306,6 @@ boot_replicate_kernel(const double* __restrict__ values, const double* __restric
             --d;
         }
     }
-    (void)st_unused_;
     const double svw = __shfl_sync(0xffffffffu, ret, 0), sw = __shfl_sync(0xffffffffu, ret, 8);
     if (lane == 0) {
         if (identity) {
