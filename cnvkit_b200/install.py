@@ -129,6 +129,7 @@ def install():
     plan = [
         (r_fix, "do_fix", _route(fix.do_fix, r_fix.do_fix, _fix_needs_reference)),
         (r_ref, "do_reference", _route(reference.do_reference, r_ref.do_reference, _reference_needs_reference)),
+        (r_ref, "do_reference_flat", _route(reference.do_reference_flat, r_ref.do_reference_flat, lambda a, k: False)),
         (r_seg, "do_segmentation", _route(segmentation.do_segmentation, r_seg.do_segmentation,
                                           _segment_needs_reference)),
         (r_smooth, "rolling_median", smoothing.rolling_median),

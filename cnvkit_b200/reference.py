@@ -41,6 +41,76 @@ def _read(fname):
     return arr
 
 
+def read_bed(bed_fname):
+    """skgenome/tabio/bedio.py:17-57 read_bed: chromosome, start, end, [gene] of a UCSC BED file
+    (0-based), up to the second "track" line; the gene is "-" where the file has no name column."""
+    rows = []
+    with open(bed_fname) as handle:
+        first = True
+        for line in handle:
+            if first:
+                first = False
+                if line.startswith("browser "):
+                    first = True
+                    continue
+                if line.startswith("track"):
+                    continue
+            elif line.startswith("track"):
+                break
+            fields = line.split("\t", 6)
+            if len(fields) < 3:
+                raise ValueError(f"Bad line in {bed_fname}: {line!r}")
+            gene = fields[3].rstrip() if len(fields) >= 4 else "-"
+            rows.append((fields[0], int(fields[1]), int(fields[2]), gene))
+    return pd.DataFrame.from_records(rows, columns=["chromosome", "start", "end", "gene"])
+
+
+def bed2probes(bed_fname):
+    """Create a neutral-coverage CopyNumArray from a file of regions (cnvlib/reference.py:78-86).
+    The reference sniffs the format (tabio.read_auto); here BED files and CNVkit's own tab format are read."""
+    with open(bed_fname) as handle:
+        head = handle.readline()
+    if head.startswith("chromosome\tstart\tend"):
+        table = tabio.read(bed_fname).data.loc[:, ["chromosome", "start", "end", "gene"]]
+    elif str(bed_fname).endswith(".bed") or head.startswith(("track", "browser ")):
+        table = read_bed(bed_fname)
+    else:
+        raise NotImplementedError(f"{bed_fname}: only BED and CNVkit tab region files are read on this path")
+    table = table.assign(log2=0.0, spread=0.0)
+    probes = cnary.CopyNumArray(table, {"sample_id": fbase(bed_fname)})
+    probes.sort()
+    return probes
+
+
+def do_reference_flat(targets, antitargets=None, fa_fname=None, is_haploid_x_reference=False,
+                      diploid_parx_genome=None):
+    """Compile a neutral-coverage reference from the given intervals (cnvlib/reference.py:26-75): flat
+    log2 (-1 on the sex chromosomes a haploid-X reference expects at half coverage), depth = 2^log2, and
+    GC / RepeatMasker content counted from the FASTA on the device."""
+    ref_probes = bed2probes(targets)
+    if antitargets:
+        ref_probes.add(bed2probes(antitargets))
+    d = ref_probes.data
+    chrom = d["chromosome"].to_numpy()
+    start = d["start"].to_numpy(dtype=np.int64)
+    end = d["end"].to_numpy(dtype=np.int64)
+    is_x, is_y, is_y_all = _sex_chrom_rows(chrom, start, end, diploid_parx_genome)
+    flat = np.zeros(len(d))                                  # expect_flat_log2 (cnary.py:635-664)
+    flat[(is_x | is_y) if is_haploid_x_reference else is_y_all] = -1.0
+    ref_probes["log2"] = flat
+    ref_probes["depth"] = np.exp2(flat)
+    if fa_fname:
+        from . import fasta
+
+        gc, rmask = fasta.get_fasta_stats(ref_probes, fa_fname)
+        ref_probes["gc"] = gc
+        ref_probes["rmask"] = rmask
+    else:
+        logging.info("No FASTA reference genome provided; skipping GC, RM calculations")
+    ref_probes.sort_columns()
+    return ref_probes
+
+
 def do_reference(
     target_fnames,
     antitarget_fnames=None,

@@ -470,6 +470,21 @@ def gen_fasta(R):
                 arrays[f"N{k}_{tag}_depth"] = cna["depth"].to_numpy()
         ref = R.reference.do_reference(tnames, anames, fa, female_samples=True)
         arrays.update(table_arrays(ref, "ref"))
+        # flat reference from BED files (do_reference_flat, reference.py:26-75)
+        t_bed, a_bed = os.path.join(tmp, "targets.bed"), os.path.join(tmp, "antitargets.bed")
+        with open(t_bed, "w") as handle:
+            handle.write('track name="panel" description="synthetic"\n')
+            for c, a, b, gname in tgt.itertuples(index=False):
+                handle.write(f"{c}\t{a}\t{b}\t{gname}\t0\t+\n")
+        with open(a_bed, "w") as handle:
+            for c, a, b, _g in anti.itertuples(index=False):
+                handle.write(f"{c}\t{a}\t{b}\n")               # BED3: gene becomes "-"
+        arrays["targets_bed"] = np.frombuffer(open(t_bed, "rb").read(), dtype=np.uint8)
+        arrays["antitargets_bed"] = np.frombuffer(open(a_bed, "rb").read(), dtype=np.uint8)
+        for tag, kw in (("flat_hx", dict(is_haploid_x_reference=True)), ("flat", dict())):
+            flat = R.reference.do_reference_flat(t_bed, a_bed, fa, **kw)
+            arrays.update(table_arrays(flat, tag))
+        arrays.update(table_arrays(R.reference.do_reference_flat(t_bed), "flat_nofa"))
     save("fasta", **arrays)
 
 

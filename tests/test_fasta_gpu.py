@@ -89,3 +89,29 @@ def test_do_reference_with_fasta_matches_reference(golden, tmp_path):
     np.testing.assert_allclose(got.data["log2"].to_numpy(), want.data["log2"].to_numpy(), rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(got.data["depth"].to_numpy(), want.data["depth"].to_numpy(), rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(got.data["spread"].to_numpy(), want.data["spread"].to_numpy(), rtol=1e-11, atol=1e-12)
+
+
+def write_beds(g, tmp_path):
+    t_bed, a_bed = os.path.join(str(tmp_path), "targets.bed"), os.path.join(str(tmp_path), "antitargets.bed")
+    with open(t_bed, "wb") as fh:
+        fh.write(g["targets_bed"].tobytes())
+    with open(a_bed, "wb") as fh:
+        fh.write(g["antitargets_bed"].tobytes())
+    return t_bed, a_bed
+
+
+def assert_tables_equal(got, want):
+    assert list(got.data.columns) == list(want.data.columns)
+    assert len(got) == len(want)
+    for col in want.data.columns:
+        np.testing.assert_array_equal(got.data[col].to_numpy(), want.data[col].to_numpy(), err_msg=col)
+
+
+def test_do_reference_flat_matches_reference(golden, tmp_path):
+    from cnvkit_b200 import reference
+
+    g = golden("fasta")
+    fa = write_genome(g, tmp_path)
+    t_bed, a_bed = write_beds(g, tmp_path)
+    assert_tables_equal(reference.do_reference_flat(t_bed, a_bed, fa, is_haploid_x_reference=True), golden_table(g, "flat_hx"))
+    assert_tables_equal(reference.do_reference_flat(t_bed, a_bed, fa), golden_table(g, "flat"))

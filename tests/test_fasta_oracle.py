@@ -85,3 +85,26 @@ def test_compressed_or_bad_input_is_refused(tmp_path):
     bad.write_bytes(b"not a fasta\nACGT\n")
     with pytest.raises(ValueError):
         fasta.build_index(str(bad))
+
+
+def test_flat_reference_without_fasta_matches_reference(golden, tmp_path):
+    """do_reference_flat(targets.bed) (reference.py:26-75) needs no device work without a FASTA: BED
+    parsing (track line, name column), flat log2 / depth / spread columns, column order."""
+    from conftest import golden_table
+
+    from cnvkit_b200 import reference
+
+    g = golden("fasta")
+    t_bed = str(tmp_path / "targets.bed")
+    with open(t_bed, "wb") as fh:
+        fh.write(g["targets_bed"].tobytes())
+    got = reference.do_reference_flat(t_bed)
+    want = golden_table(g, "flat_nofa")
+    assert list(got.data.columns) == list(want.data.columns)
+    for col in want.data.columns:
+        np.testing.assert_array_equal(got.data[col].to_numpy(), want.data[col].to_numpy(), err_msg=col)
+    assert got.sample_id == "targets"
+    other = tmp_path / "regions.txt"
+    other.write_text("chr1:100-200\n")
+    with pytest.raises(NotImplementedError):
+        reference.bed2probes(str(other))
