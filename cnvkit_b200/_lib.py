@@ -121,6 +121,12 @@ class CbsStats(ctypes.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+class TsvDict(ctypes.Structure):
+    """cnvk_tsv_dict (include/cnvkit_b200.h)."""
+
+    _fields_ = [("offsets", POINTER(c_int64)), ("blob", c_char_p), ("n", c_int64)]
+
+
 class BootParams(ctypes.Structure):
     """cnvk_boot_params (include/cnvkit_b200.h)."""
 

@@ -8,13 +8,16 @@
 // No CUDA here: the columns land in caller-provided host buffers (pinned, if the caller wants to
 // DMA them straight to HBM).
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/cnvkit_b200.h"
@@ -127,6 +130,17 @@ int fail(const char* fmt, const char* a) {
 struct cnvk_tsv {
     Table t;
 };
+
+// one string field, quoted the way csv.QUOTE_MINIMAL does (tab, quote, CR or LF inside)
+static void append_field(std::string& out, const char* s, size_t len) {
+    bool q = false;
+    for (size_t k = 0; k < len; ++k)
+        if (s[k] == '\t' || s[k] == '"' || s[k] == '\n' || s[k] == '\r') { q = true; break; }
+    if (!q) { out.append(s, len); return; }
+    out += '"';
+    for (size_t k = 0; k < len; ++k) { if (s[k] == '"') out += '"'; out += s[k]; }
+    out += '"';
+}
 
 extern "C" {
 
@@ -270,44 +284,89 @@ uint64_t cnvk_tsv_hash_cols(const cnvk_tsv* h, const int32_t* cols, int32_t n) {
 }
 
 // DataFrame.to_csv(path, sep="\t", index=False, float_format="%.6g"): kinds[c] = 0 str
-// (ptrs[c] = int64 offsets[nrows+1], ptrs2[c] = bytes), 1 int64, 2 float64 (NaN -> empty field).
+// (ptrs[c] = int64 offsets[nrows+1], ptrs2[c] = bytes), 1 int64, 2 float64 (NaN -> empty field),
+// 3 dictionary-coded str (ptrs[c] = int32 codes[nrows], -1 = missing; ptrs2[c] = cnvk_tsv_dict*).
+// Rows are formatted in parallel (contiguous row ranges, one buffer each) and written in order.
 int cnvk_tsv_write(const char* path, int32_t ncols, const char* const* names, const int32_t* kinds,
                    const void* const* ptrs, const void* const* ptrs2, int64_t nrows) {
-    FILE* fp = fopen(path, "wb");
-    if (!fp) return fail("cnvk_tsv_write: cannot open %s", path);
-    std::string out;
-    out.reserve((size_t)nrows * ncols * 10 + 256);
-    for (int c = 0; c < ncols; ++c) { if (c) out += '\t'; out += names[c]; }
-    out += '\n';
-    char num[64];
-    for (int64_t r = 0; r < nrows; ++r) {
-        for (int c = 0; c < ncols; ++c) {
-            if (c) out += '\t';
-            if (kinds[c] == 1) {
-                auto res = std::to_chars(num, num + sizeof(num), ((const int64_t*)ptrs[c])[r]);
-                out.append(num, res.ptr - num);
-            } else if (kinds[c] == 2) {
-                const double v = ((const double*)ptrs[c])[r];
-                if (v == v) out.append(num, (size_t)snprintf(num, sizeof(num), "%.6g", v));
-            } else {
-                const int64_t* off = (const int64_t*)ptrs[c];
-                const char* s = (const char*)ptrs2[c] + off[r];
-                const size_t len = (size_t)(off[r + 1] - off[r]);
-                bool q = false;
-                for (size_t k = 0; k < len; ++k)
-                    if (s[k] == '\t' || s[k] == '"' || s[k] == '\n' || s[k] == '\r') { q = true; break; }
-                if (!q) out.append(s, len);
-                else {
-                    out += '"';
-                    for (size_t k = 0; k < len; ++k) { if (s[k] == '"') out += '"'; out += s[k]; }
-                    out += '"';
+    // dictionary columns: render (quote) every distinct value once
+    std::vector<std::vector<std::string>> dict((size_t)ncols);
+    for (int c = 0; c < ncols; ++c) {
+        if (kinds[c] != 3) continue;
+        const cnvk_tsv_dict* d = (const cnvk_tsv_dict*)ptrs2[c];
+        dict[c].resize((size_t)d->n);
+        for (int64_t u = 0; u < d->n; ++u)
+            append_field(dict[c][(size_t)u], d->blob + d->offsets[u], (size_t)(d->offsets[u + 1] - d->offsets[u]));
+    }
+    for (int c = 0; c < ncols; ++c) {
+        if (kinds[c] != 3) continue;
+        const int32_t* codes = (const int32_t*)ptrs[c];
+        const int64_t nu = (int64_t)dict[c].size();
+        for (int64_t r = 0; r < nrows; ++r)
+            if (codes[r] >= nu) return fail("cnvk_tsv_write: dictionary code out of range in column %s", names[c]);
+    }
+    auto format_rows = [&](int64_t r0, int64_t r1, std::string& out) {
+        char num[64];
+        out.reserve((size_t)(r1 - r0) * (size_t)ncols * 9 + 64);
+        for (int64_t r = r0; r < r1; ++r) {
+            for (int c = 0; c < ncols; ++c) {
+                if (c) out += '\t';
+                if (kinds[c] == 1) {
+                    auto res = std::to_chars(num, num + sizeof(num), ((const int64_t*)ptrs[c])[r]);
+                    out.append(num, res.ptr - num);
+                } else if (kinds[c] == 2) {
+                    const double v = ((const double*)ptrs[c])[r];
+                    if (v == v) {
+                        if (std::isinf(v)) out += (v > 0 ? "inf" : "-inf");
+                        else {   // "as if by printf %.6g in the C locale"
+                            auto res = std::to_chars(num, num + sizeof(num), v, std::chars_format::general, 6);
+                            out.append(num, res.ptr - num);
+                        }
+                    }
+                } else if (kinds[c] == 3) {
+                    const int32_t code = ((const int32_t*)ptrs[c])[r];
+                    if (code >= 0) out += dict[c][(size_t)code];
+                } else {
+                    const int64_t* off = (const int64_t*)ptrs[c];
+                    append_field(out, (const char*)ptrs2[c] + off[r], (size_t)(off[r + 1] - off[r]));
                 }
             }
+            out += '\n';
         }
-        out += '\n';
-        if (out.size() > (1u << 22)) { fwrite(out.data(), 1, out.size(), fp); out.clear(); }
+    };
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail("cnvk_tsv_write: cannot open %s", path);
+    std::string head;
+    for (int c = 0; c < ncols; ++c) { if (c) head += '\t'; head += names[c]; }
+    head += '\n';
+    fwrite(head.data(), 1, head.size(), fp);
+    const int64_t chunk = 32768;
+    int nthreads = (int)std::min<int64_t>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 4u),
+                                          (nrows + chunk - 1) / chunk);
+    if (const char* env = getenv("CNVK_TSV_THREADS")) nthreads = std::max(1, std::min(nthreads, atoi(env)));
+    if (nthreads <= 1) {
+        std::string out;
+        for (int64_t r0 = 0; r0 < nrows; r0 += chunk) {
+            out.clear();
+            format_rows(r0, std::min(nrows, r0 + chunk), out);
+            fwrite(out.data(), 1, out.size(), fp);
+        }
+    } else {
+        const int64_t nchunks = (nrows + chunk - 1) / chunk;
+        std::vector<std::string> parts((size_t)nchunks);
+        std::atomic<int64_t> next{0};
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t)
+            pool.emplace_back([&]() {
+                for (;;) {
+                    const int64_t k = next.fetch_add(1);
+                    if (k >= nchunks) break;
+                    format_rows(k * chunk, std::min(nrows, (k + 1) * chunk), parts[(size_t)k]);
+                }
+            });
+        for (auto& th : pool) th.join();
+        for (auto& p : parts) fwrite(p.data(), 1, p.size(), fp);
     }
-    fwrite(out.data(), 1, out.size(), fp);
     if (fclose(fp) != 0) return fail("cnvk_tsv_write: write failed for %s", path);
     return 0;
 }

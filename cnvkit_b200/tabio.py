@@ -168,15 +168,18 @@ def write(cnarr, path):
             a = np.ascontiguousarray(col.to_numpy(dtype=np.float64))
             kinds.append(2); ptrs.append(a.ctypes.data); ptrs2.append(0); keep.append(a)
         else:
-            vals = ["" if (v is None or v is pd.NA or (isinstance(v, float) and v != v)) else str(v)
-                    for v in col.tolist()]
-            enc = [v.encode("utf-8") for v in vals]
-            off = np.zeros(n + 1, dtype=np.int64)
-            if n:
+            # dictionary-code the strings: a table has few distinct chromosomes / gene labels
+            codes, uniques = pd.factorize(col, use_na_sentinel=True)
+            enc = [str(v).encode("utf-8") for v in np.asarray(uniques, dtype=object).tolist()]
+            off = np.zeros(len(enc) + 1, dtype=np.int64)
+            if enc:
                 np.cumsum([len(b) for b in enc], out=off[1:])
             blob = b"".join(enc)
             buf = ctypes.create_string_buffer(blob, max(len(blob), 1))
-            kinds.append(0); ptrs.append(off.ctypes.data); ptrs2.append(ctypes.addressof(buf)); keep.append((off, buf))
+            codes = np.ascontiguousarray(codes, dtype=np.int32)
+            d = _lib.TsvDict(ctypes.cast(off.ctypes.data, ctypes.POINTER(ctypes.c_int64)),
+                             ctypes.cast(buf, ctypes.c_char_p), len(enc))
+            kinds.append(3); ptrs.append(codes.ctypes.data); ptrs2.append(ctypes.addressof(d)); keep.append((codes, off, buf, d))
     k = len(names)
     c_names = (ctypes.c_char_p * k)(*names)
     c_kinds = (ctypes.c_int32 * k)(*kinds)

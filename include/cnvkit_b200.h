@@ -293,7 +293,14 @@ int cnvk_tsv_read_str(const cnvk_tsv* h, int32_t col, int64_t* offsets, char* bu
 uint64_t cnvk_tsv_hash_cols(const cnvk_tsv* h, const int32_t* cols, int32_t n);
 /* Writer: skgenome/tabio/__init__.py:175-195 write (DataFrame.to_csv(sep="\t", index=False,
  * float_format="%.6g")).  kinds[c]: 0 str (ptrs[c] = int64 offsets[nrows+1], ptrs2[c] = bytes),
- * 1 int64, 2 float64 (NaN -> empty field). */
+ * 1 int64, 2 float64 (NaN -> empty field), 3 dictionary-coded str (ptrs[c] = int32 codes[nrows]
+ * into the distinct values of ptrs2[c] = cnvk_tsv_dict*, -1 = missing -> empty field).  Rows are
+ * formatted by several host threads and written in order. */
+typedef struct cnvk_tsv_dict {
+    const int64_t* offsets; /* n + 1 offsets into blob */
+    const char* blob;       /* the distinct values, concatenated (UTF-8) */
+    int64_t n;
+} cnvk_tsv_dict;
 int cnvk_tsv_write(const char* path, int32_t ncols, const char* const* names, const int32_t* kinds,
                    const void* const* ptrs, const void* const* ptrs2, int64_t nrows);
 

@@ -132,3 +132,24 @@ def test_reader_and_writer_on_reference_fixtures(tmp_path):
         want.to_csv(a, sep="\t", index=False, float_format="%.6g")
         tabio.write(got, b)
         assert a.read_bytes() == b.read_bytes(), f
+
+
+def test_writer_dictionary_strings_quoting_and_special_floats(tmp_path):
+    """String columns go through dictionary codes (cnvk_tsv_dict): missing values, fields that need
+    csv quoting, many distinct values, and %.6g of inf / tiny / huge / negative-zero floats."""
+    n = 70_000                                   # more than one formatting chunk
+    rng = np.random.default_rng(3)
+    genes = np.array([f"G{k}" for k in rng.integers(0, 9000, n)], dtype=object)
+    genes[5] = 'has"quote'
+    genes[6] = "has\ttab"
+    genes[7] = None
+    genes[8] = "multi\nline"
+    vals = rng.normal(0, 1, n)
+    vals[:6] = [np.inf, -np.inf, np.nan, 1e-300, 1e21, -0.0]
+    df = pd.DataFrame({"chromosome": [f"chr{1 + k % 22}" for k in range(n)], "start": np.arange(n) * 100,
+                       "end": np.arange(n) * 100 + 50, "gene": genes, "log2": vals,
+                       "depth": rng.uniform(0, 1e6, n)})
+    ours, theirs = tmp_path / "ours.tsv", tmp_path / "pandas.tsv"
+    tabio.write(df, str(ours))
+    df.to_csv(theirs, sep="\t", index=False, float_format="%.6g")
+    assert ours.read_bytes() == theirs.read_bytes()
