@@ -87,6 +87,7 @@ SIGNATURES = {
     "cnvk_tsv_read_f64": (c_int, [c_void_p, c_int32, c_void_p]),
     "cnvk_tsv_read_i64": (c_int, [c_void_p, c_int32, c_void_p]),
     "cnvk_tsv_read_str": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
+    "cnvk_tsv_read_str_dict": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "cnvk_tsv_hash_cols": (c_uint64, [c_void_p, c_void_p, c_int32]),
     "cnvk_tsv_write": (c_int, [c_char_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
 }

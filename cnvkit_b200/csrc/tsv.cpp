@@ -15,9 +15,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <limits>
 #include <string>
+#include <string_view>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/cnvkit_b200.h"
@@ -265,6 +268,65 @@ int cnvk_tsv_read_str(const cnvk_tsv* h, int32_t col, int64_t* offsets, char* bu
     }
     if (buf) offsets[t.nrows] = tot;
     *nbytes = tot;
+    return 0;
+}
+
+// String column dictionary-coded in order of first appearance: codes[nrows] plus the distinct values as
+// offsets[n_unique + 1] into one byte buffer.  With codes == NULL only *n_unique / *nbytes are filled
+// (sizes for the second call).  A table has few distinct chromosomes and gene labels, so the caller
+// builds a handful of Python strings instead of one per row.
+int cnvk_tsv_read_str_dict(const cnvk_tsv* h, int32_t col, int32_t* codes, int64_t* offsets, char* buf, int64_t cap,
+                           int64_t* n_unique, int64_t* nbytes) {
+    const Table& t = h->t;
+    if (col < 0 || col >= t.ncols) return fail("cnvk_tsv_read_str_dict: %s", "bad column");
+    std::unordered_map<std::string_view, int32_t> seen;
+    std::deque<std::string> owned;           // unescaped text of quoted fields (a deque keeps addresses stable)
+    std::vector<std::string_view> uniq;
+    int64_t tot = 0;
+    std::string_view prev;
+    int32_t prev_code = -1;
+    for (int64_t r = 0; r < t.nrows; ++r) {
+        const Field& f = t.fields[(size_t)r * t.ncols + col];
+        std::string_view v(t.data.data() + f.off, f.len);
+        int32_t code;
+        if (!f.quoted && prev_code >= 0 && v == prev) {
+            code = prev_code;                // runs of equal labels (chromosome, gene) skip the hash
+        } else {
+            if (f.quoted) {
+                std::string s = field_text(t, f);
+                auto it0 = seen.find(std::string_view(s));
+                if (it0 == seen.end()) {
+                    owned.push_back(std::move(s));
+                    v = std::string_view(owned.back());
+                } else {
+                    v = it0->first;
+                }
+            }
+            auto it = seen.find(v);
+            if (it == seen.end()) {
+                code = (int32_t)uniq.size();
+                seen.emplace(v, code);
+                uniq.push_back(v);
+                tot += (int64_t)v.size();
+            } else {
+                code = it->second;
+            }
+            if (!f.quoted) { prev = v; prev_code = code; }
+        }
+        if (codes) codes[r] = code;
+    }
+    *n_unique = (int64_t)uniq.size();
+    *nbytes = tot;
+    if (codes) {
+        if (tot > cap) return fail("cnvk_tsv_read_str_dict: %s", "buffer too small");
+        int64_t pos = 0;
+        for (size_t u = 0; u < uniq.size(); ++u) {
+            offsets[u] = pos;
+            memcpy(buf + pos, uniq[u].data(), uniq[u].size());
+            pos += (int64_t)uniq[u].size();
+        }
+        offsets[uniq.size()] = pos;
+    }
     return 0;
 }
 

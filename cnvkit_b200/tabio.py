@@ -54,22 +54,27 @@ class _Handle:
         _lib.check(self.lib.cnvk_tsv_read_i64(self.h, col, out.ctypes.data), "cnvk_tsv_read_i64")
         return out
 
-    def strings(self, col):
-        nbytes = ctypes.c_int64()
-        _lib.check(self.lib.cnvk_tsv_read_str(self.h, col, None, None, 0, ctypes.byref(nbytes)), "cnvk_tsv_read_str")
-        off = np.empty(self.nrows + 1, dtype=np.int64)
+    def strings(self, col, na_values=()):
+        """Column as an object array of str; values listed in `na_values` become NaN.  The native side
+        dictionary-codes the column, so only the distinct values are turned into Python strings."""
+        n_unique, nbytes = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self.lib.cnvk_tsv_read_str_dict(self.h, col, None, None, None, 0, ctypes.byref(n_unique),
+                                                   ctypes.byref(nbytes)), "cnvk_tsv_read_str_dict")
+        if self.nrows == 0:
+            return np.zeros(0, dtype=object)
+        codes = np.empty(self.nrows, dtype=np.int32)
+        off = np.empty(n_unique.value + 1, dtype=np.int64)
         buf = ctypes.create_string_buffer(max(nbytes.value, 1))
-        _lib.check(self.lib.cnvk_tsv_read_str(self.h, col, off.ctypes.data, buf, nbytes.value, ctypes.byref(nbytes)),
-                   "cnvk_tsv_read_str")
+        _lib.check(self.lib.cnvk_tsv_read_str_dict(self.h, col, codes.ctypes.data, off.ctypes.data, buf, nbytes.value,
+                                                   ctypes.byref(n_unique), ctypes.byref(nbytes)),
+                   "cnvk_tsv_read_str_dict")
         raw = buf.raw[: nbytes.value]
-        try:
-            text = raw.decode("ascii")
-            o = off.tolist()
-            vals = [text[a:b] for a, b in zip(o[:-1], o[1:])]
-        except UnicodeDecodeError:
-            o = off.tolist()
-            vals = [raw[a:b].decode("utf-8") for a, b in zip(o[:-1], o[1:])]
-        return np.array(vals, dtype=object) if vals else np.zeros(0, dtype=object)
+        o = off.tolist()
+        uniq = np.empty(len(o) - 1, dtype=object)
+        for k, (a, b) in enumerate(zip(o[:-1], o[1:])):
+            text = raw[a:b].decode("utf-8")
+            uniq[k] = np.nan if text in na_values else text
+        return uniq[codes]
 
     def hash_cols(self, cols):
         arr = (ctypes.c_int32 * len(cols))(*cols)
@@ -90,13 +95,7 @@ def read_frame(path) -> pd.DataFrame:
             elif kind == 2:
                 cols[name] = t.f64(c)
             else:
-                v = t.strings(c)
-                if name != "chromosome" and len(v):
-                    na = np.isin(v, _NA_STRINGS)
-                    if na.any():
-                        v = v.copy()
-                        v[na] = np.nan
-                cols[name] = v
+                cols[name] = t.strings(c, () if name == "chromosome" else _NA_SET)
         df = pd.DataFrame(cols, columns=t.names)
     if "log2" in df.columns:
         keep = df["log2"].notna().to_numpy()
@@ -108,6 +107,7 @@ def read_frame(path) -> pd.DataFrame:
 
 _NA_STRINGS = ("", "#N/A", "#N/A N/A", "#NA", "-1.#IND", "-1.#QNAN", "-NaN", "-nan", "1.#IND", "1.#QNAN", "<NA>",
                "N/A", "NA", "NULL", "NaN", "None", "n/a", "nan", "null")
+_NA_SET = frozenset(_NA_STRINGS)
 
 
 def read(path, sample_id=None, into=None):

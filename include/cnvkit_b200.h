@@ -291,6 +291,11 @@ int cnvk_tsv_read_i64(const cnvk_tsv* h, int32_t col, int64_t* out);
 int cnvk_tsv_read_str(const cnvk_tsv* h, int32_t col, int64_t* offsets, char* buf, int64_t cap, int64_t* nbytes);
 /* FNV-1a of the raw field bytes of the given columns: equality test of bin sets without strings. */
 uint64_t cnvk_tsv_hash_cols(const cnvk_tsv* h, const int32_t* cols, int32_t n);
+/* String column dictionary-coded in order of first appearance: codes[nrows] and the distinct values
+ * (offsets[n_unique + 1] into buf).  Call with codes == NULL for the sizes first. */
+int cnvk_tsv_read_str_dict(const cnvk_tsv* h, int32_t col, int32_t* codes, int64_t* offsets, char* buf,
+                           int64_t cap, int64_t* n_unique, int64_t* nbytes);
+
 /* Writer: skgenome/tabio/__init__.py:175-195 write (DataFrame.to_csv(sep="\t", index=False,
  * float_format="%.6g")).  kinds[c]: 0 str (ptrs[c] = int64 offsets[nrows+1], ptrs2[c] = bytes),
  * 1 int64, 2 float64 (NaN -> empty field), 3 dictionary-coded str (ptrs[c] = int32 codes[nrows]
