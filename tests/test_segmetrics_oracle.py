@@ -110,3 +110,39 @@ def test_out_of_scope_statistics_are_refused(golden):
         SM.do_segmetrics(cnr, cns, interval_stats=["pi"])
     out = SM.do_segmetrics(cnr, cns)        # nothing requested: a copy, no device call
     assert list(out.data.columns) == list(cns.data.columns) and out is not cns
+
+
+@pytest.mark.needs_reference
+def test_host_logic_with_nan_weights_and_skip_low_matches_reference(monkeypatch):
+    """do_segmetrics' host side (bin selection, NaN-weight compaction, skip_low) against the unmodified
+    reference, with the device call replaced by the numpy oracle."""
+    from cnvkit_b200 import cohort
+    from cnvkit_b200 import segmetrics as SM
+    from oracle import refshim
+
+    R = refshim.load()
+    from cnvlib import segmetrics as ref_sm
+
+    cnr = R.read_cna(os.path.join(R.root, "test", "formats", "amplicon.cnr"))
+    cns = R.read_cna(os.path.join(R.root, "test", "formats", "amplicon.cns"))
+    d = cnr.data.copy()
+    rng = np.random.default_rng(2)
+    d.loc[rng.choice(len(d), 40, replace=False), "weight"] = np.nan
+    d.loc[rng.choice(len(d), 25, replace=False), "log2"] = -30.0          # dropped by skip_low
+    cnr = cnr.as_dataframe(d)
+
+    def fake(values, weights, lo, hi, alpha=0.05, bootstraps=100, smoothed=False, **kw):
+        return OS.ci_table(np.asarray(values), np.asarray(weights), lo, hi, alpha, bootstraps, smoothed)
+
+    monkeypatch.setattr(SM, "bootstrap_ci", fake)
+    for kw in (dict(smoothed=False), dict(smoothed=False, skip_low=True), dict(smoothed=False, alpha=0.5, bootstraps=3)):
+        got = SM.do_segmetrics(cnr, cns, interval_stats=["ci"], **kw)
+        want = ref_sm.do_segmetrics(cnr, cns, interval_stats=["ci"], **kw)
+        assert list(got.data.columns) == list(want.data.columns)
+        np.testing.assert_allclose(got["ci_lo"].to_numpy(), want["ci_lo"].to_numpy(), rtol=0, atol=TOL, equal_nan=True)
+        np.testing.assert_allclose(got["ci_hi"].to_numpy(), want["ci_hi"].to_numpy(), rtol=0, atol=TOL, equal_nan=True)
+    assert cohort._ci_options(None) is None and cohort._ci_options(False) is None
+    assert cohort._ci_options(True) == dict(alpha=0.5, bootstraps=100, smoothed=True)
+    assert cohort._ci_options(dict(alpha=0.1)) == dict(alpha=0.1, bootstraps=100, smoothed=10)
+    with pytest.raises(ValueError):
+        cohort._ci_options(dict(alpah=0.1))
