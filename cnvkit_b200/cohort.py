@@ -185,6 +185,7 @@ class Panel:
         self.arm_id = np.repeat(np.arange(len(self.arms)), np.diff(self.arm_off))
         self.d_arm_id = torch.from_numpy(self.arm_id).to(_dev.device())
         self.gene_codes = segmentation.factorize_genes(self.bins["gene"].to_numpy())
+        self._bin_index = None           # segmetrics.BinIndex of the .cnr rows, built on first use
 
     # ------------------------------------------------------------------ fix
     def fix(self, target, antitarget):
@@ -353,7 +354,9 @@ class Panel:
         out.sort_columns()
         if ci:
             # segmetrics.py:93: the bins each (stretched) segment overlaps, filtered bins included
-            b_lo, b_hi = segmetrics.segment_bin_ranges(self.bins, out.data)
+            if self._bin_index is None:
+                self._bin_index = segmetrics.BinIndex(self.bins)
+            b_lo, b_hi = self._bin_index.ranges(out.data)
             c_lo, c_hi = segmetrics.bootstrap_ci(None, None, b_lo, b_hi, device_ptrs=(d_log2.data_ptr(), d_w.data_ptr()),
                                                  stream=_dev.stream(), **ci)
             out["ci_lo"] = c_lo.cpu().numpy()

@@ -83,47 +83,65 @@ def bootstrap_ci(values, weights, seg_lo, seg_hi, alpha=0.05, bootstraps=100, sm
     return d_lo[:ns], d_hi[:ns]
 
 
+class BinIndex:
+    """Per-chromosome row runs and coordinate columns of a bin table, checked once (ascending start and
+    end within each chromosome) so that many segment tables can be matched against it cheaply."""
+
+    def __init__(self, bins):
+        from .genome import chrom_runs
+
+        self.n = len(bins)
+        self.start = bins["start"].to_numpy()
+        self.end = bins["end"].to_numpy()
+        self.runs = {}
+        if not self.n:
+            return
+        try:
+            names, run_off, _ = chrom_runs(bins["chromosome"].to_numpy())
+        except ValueError as exc:
+            raise NotImplementedError("bins of one chromosome must be contiguous rows (sort the .cnr first)") from exc
+        for r, name in enumerate(names):
+            a, b = int(run_off[r]), int(run_off[r + 1])
+            st, en = self.start[a:b], self.end[a:b]
+            if len(st) > 1 and np.any(st[1:] < st[:-1]):
+                row = int(np.flatnonzero(st[1:] < st[:-1])[0]) + 1
+                raise ValueError(
+                    "Genomic intervals must be sorted by start position to be searched: "
+                    f"start={st[row]} follows start={st[row - 1]}, at row {row} of {len(st)}. "
+                    "To fix, sort the rows by start -- GenomicArray.sort, or sort_values.")   # intersect.py:270-310
+            if len(en) > 1 and np.any(en[1:] < en[:-1]):
+                raise NotImplementedError("nested bins (end not ascending) are outside the GPU path")
+            self.runs[name] = (a, b)
+
+    def ranges(self, segs):
+        """(lo, hi) row positions of the bins each segment selects in 'outer' mode."""
+        s_chrom = segs["chromosome"].to_numpy()
+        s_start = segs["start"].to_numpy()
+        s_end = segs["end"].to_numpy()
+        lo = np.zeros(len(segs), dtype=np.int64)
+        hi = np.zeros(len(segs), dtype=np.int64)
+        if not self.n or not len(segs):
+            return lo, hi
+        seg_names, seg_codes = np.unique(s_chrom.astype(object), return_inverse=True)
+        for code, name in enumerate(seg_names):
+            run = self.runs.get(name)
+            if run is None:
+                continue
+            a, b = run
+            sel = np.flatnonzero(seg_codes == code)
+            lo[sel] = a + np.searchsorted(self.end[a:b], s_start[sel], "right")
+            hi[sel] = a + np.searchsorted(self.start[a:b], s_end[sel], "left")
+        return lo, np.maximum(hi, lo)
+
+
 def segment_bin_ranges(bins, segs):
     """Rows of the bin table each segment selects: ``cnarr.iter_ranges_of(segarr, "log2", "outer", True)``
     (skgenome/gary.py:582-630 -> intersect.py:169-342).  Per chromosome, in 'outer' mode, the selection
     is the run [searchsorted(end, seg_start, "right"), searchsorted(start, seg_end)).  Returns (lo, hi)
     as positions into ``bins``; hi == lo where nothing is selected (unknown chromosome included)."""
-    b_chrom = bins["chromosome"].to_numpy()
-    b_start = bins["start"].to_numpy()
-    b_end = bins["end"].to_numpy()
-    s_chrom = segs["chromosome"].to_numpy()
-    s_start = segs["start"].to_numpy()
-    s_end = segs["end"].to_numpy()
-    lo = np.zeros(len(segs), dtype=np.int64)
-    hi = np.zeros(len(segs), dtype=np.int64)
     if not len(bins) or not len(segs):
-        return lo, hi
-    from .genome import chrom_runs
-
-    try:
-        names, run_off, _ = chrom_runs(b_chrom)
-    except ValueError as exc:
-        raise NotImplementedError("bins of one chromosome must be contiguous rows (sort the .cnr first)") from exc
-    first = {name: r for r, name in enumerate(names)}
-    seg_names, seg_codes = np.unique(s_chrom.astype(object), return_inverse=True)
-    for code, name in enumerate(seg_names):
-        r = first.get(name)
-        if r is None:
-            continue
-        a, b = int(run_off[r]), int(run_off[r + 1])
-        st, en = b_start[a:b], b_end[a:b]
-        if len(st) > 1 and np.any(st[1:] < st[:-1]):
-            row = int(np.flatnonzero(st[1:] < st[:-1])[0]) + 1
-            raise ValueError(
-                "Genomic intervals must be sorted by start position to be searched: "
-                f"start={st[row]} follows start={st[row - 1]}, at row {row} of {len(st)}. "
-                "To fix, sort the rows by start -- GenomicArray.sort, or sort_values.")   # intersect.py:270-310
-        if len(en) > 1 and np.any(en[1:] < en[:-1]):
-            raise NotImplementedError("nested bins (end not ascending) are outside the GPU path")
-        sel = np.flatnonzero(seg_codes == code)
-        lo[sel] = a + np.searchsorted(en, s_start[sel], "right")
-        hi[sel] = a + np.searchsorted(st, s_end[sel], "left")
-    return lo, np.maximum(hi, lo)
+        return np.zeros(len(segs), dtype=np.int64), np.zeros(len(segs), dtype=np.int64)
+    return BinIndex(bins).ranges(segs)
 
 
 def do_segmetrics(cnarr, segarr, location_stats=(), spread_stats=(), interval_stats=(), alpha=0.05,
