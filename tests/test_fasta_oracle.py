@@ -108,3 +108,29 @@ def test_flat_reference_without_fasta_matches_reference(golden, tmp_path):
     other.write_text("chr1:100-200\n")
     with pytest.raises(NotImplementedError):
         reference.bed2probes(str(other))
+
+
+def test_index_scan_edge_cases(tmp_path):
+    from cnvkit_b200 import fasta
+
+    text = ">a first record\nACGTAC\nGTACGT\nAC\n\n>b\nGGGG\n>c desc\n" + "T" * 7 + "\n" + "T" * 3 + "\n\n\n"
+    path = tmp_path / "g.fa"
+    path.write_text(text)
+    idx = fasta.build_index(str(path))
+    assert {k: v.length for k, v in idx.items()} == {"a": 14, "b": 4, "c": 10}
+    assert (idx["a"].linebases, idx["a"].linewidth) == (6, 7) and (idx["c"].linebases, idx["c"].linewidth) == (7, 8)
+    data = np.frombuffer(text.encode(), dtype=np.uint8)
+    seqs = O.parse_fasta(text)
+    for name, seq in seqs.items():
+        for s, e in ((0, len(seq)), (1, 5), (5, 9), (len(seq) - 1, len(seq) + 4), (3, 3)):
+            lo, hi = fasta.byte_ranges(idx[name], [s], [e])
+            got = bytes(data[lo[0]:hi[0]]).replace(b"\n", b"").decode()
+            assert got == seq[s:e], (name, s, e, got)
+    # a stale .fai (older than the FASTA) is ignored, a fresh one is used
+    fai = tmp_path / "g.fa.fai"
+    fai.write_text("a\t999\t16\t6\t7\n")
+    os.utime(fai, (1, 1))
+    assert fasta.read_index(str(path))["a"].length == 14
+    os.utime(fai, None)
+    os.utime(path, (2, 2))
+    assert fasta.read_index(str(path))["a"].length == 999
