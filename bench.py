@@ -45,6 +45,11 @@ UNIT = "bins/s"
 ALPHA = 1e-4
 FLOP_PER_ARC = 7  # sub, sub, sub, mul, mul, mul, compare -- weighted BSS, division-free test
 PREP_BYTES_PER_BIN = 56  # read log2, weight (16 B); write xc, y, wn, S, cw (40 B)
+PREP_TRAFFIC = 217.0e6   # ncu dram bytes of the level-1 launches of the prep tile kernels (profiles/)
+PREP_NOTE = ("blocked FP64 prefix scan cut into 2048-point tiles (one CTA each); the tile kernels move 104 B/bin "
+             "(the sums pass re-reads the inputs, the tile-local prefixes make one round trip before the carries "
+             "are added); traffic = ncu dram bytes of the level-1 launches of the three tile kernels "
+             "(profiles/r01d_cbs_kernels_full_summary.md), the rest of the writes stays in L2")
 
 
 def parse_args():
@@ -61,6 +66,9 @@ def parse_args():
     ap.add_argument("--samples", type=int, default=1024, help="cohort size for --workload cohort")
     ap.add_argument("--workers", type=int, default=4, help="host threads (one CUDA stream each) per rank, cohort workload")
     ap.add_argument("--no-exome-leg", action="store_true", help="skip the C2 exome leg of the default run")
+    ap.add_argument("--no-cohort-leg", action="store_true", help="skip the C5 cohort leg of the default run")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the cliff / public-API / C1 legs (N = 1)")
+    ap.add_argument("--cohort-samples", type=int, default=1024, help="cohort size of the C5 leg of the default run")
     ap.add_argument("--sharding", default="samples", choices=["samples", "arms"],
                     help="N > 1: 'samples' = one WGS sample per rank (weak scaling, default); "
                          "'arms' = the arms of ONE sample over the ranks (strong scaling, BASELINE configs[2])")
@@ -131,6 +139,48 @@ def reference_sample(data, cpu_seconds, cores):
     w = np.concatenate([data["weight"][off[a]:off[a + 1]] for a in picked])
     o = np.concatenate([[0], np.cumsum(sizes[picked])]).astype(np.int64)
     return x, w, o, picked
+
+
+def wgs_config(args, world, by_arms):
+    """The `config` object of the headline line -- the same keys and values for both arms (--impl b200 and
+    --impl reference), so that the driver's same_config test compares like with like."""
+    return {
+        "workload": f"C3 synthetic WGS, {args.bins} 1-kb bins, 48 arms, CBS alpha={ALPHA} nperm=10000",
+        "bins_per_sample": int(args.bins), "arms_per_sample": 48, "alpha": ALPHA, "nperm": 10000,
+        "samples_in_flight": 1 if (by_arms or world == 1) else world,
+        "sharding": "single GPU" if world == 1 else
+        (f"arms of one sample over {world} ranks by LPT on n^2; one NCCL gather of the tables" if by_arms else
+         f"one sample per rank ({world} replicas of the same synthetic sample), no data-path collective; "
+         f"one NCCL all-gather of the tables per batch of steps"),
+        "l2": "256 MB flush write between timed steps",
+    }
+
+
+def bind_to_gpu_numa(torch, local_rank):
+    """Pin this rank's host threads to the CPUs of the GPU's NUMA node BEFORE allocating pinned staging
+    buffers (first touch places them on that node), so that N ranks' host->device copies do not all cross
+    one socket.  Best effort; returns a short description for the JSON line."""
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        dom = getattr(props, "pci_domain_id", 0)
+        bus, devid = props.pci_bus_id, props.pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0"
+        node = int(open(path + "/numa_node").read().strip())
+        cpulist = open(path + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return f"node {node}: not bound"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to NUMA node {node} ({len(cpus)} cpus)"
+    except Exception as exc:  # sysfs layout / torch attribute missing: run unbound
+        return f"not bound ({type(exc).__name__})"
 
 
 # ------------------------------------------------------------------------------------------ exome legs
@@ -250,6 +300,7 @@ def run_reference(args):
     from oracle import cbs as OC
 
     cores = len(os.sched_getaffinity(0))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     data = synth.wgs_sample(total_bins=args.bins)
     x, w, off, picked = reference_sample(data, args.cpu_seconds, cores)
     P = OC.make_params(alpha=ALPHA, prune=True)
@@ -271,18 +322,108 @@ def run_reference(args):
     value = len(x) / (ms * 1e-3)
     sample = (f"{len(picked)} of {len(data['arm_offsets']) - 1} arms of the {args.bins}-bin sample ({len(x)} bins), "
               f"full CBS incl. permutations")
+    by_arms = args.sharding == "arms" and world > 1
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.sharding == "arms" else "weak",
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if by_arms else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C3 synthetic WGS, {args.bins} 1-kb bins, 48 arms, CBS alpha={ALPHA} nperm=10000",
-                   "sample": sample, "segments": nseg},
+        "config": wgs_config(args, world, by_arms),
+        "segments": nseg,
+        "note": "CPU throughput of ONE sample on all host cores; it does not grow with --gpus (the GPU arm at N > 1 "
+                "segments N samples at once, so the N-GPU ratio is a throughput ratio)",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample + "; oracle/cbs_oracle.c (restated DNAcopy with block-pruned wtmaxo; R "
                                             "unavailable), OpenMP over arms"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
+
+
+def cliff_sample():
+    """One 120 000-bin arm whose maximal statistic (|t| = 6.81) lies between the reach of the hybrid tail
+    approximation (tailp = 1.9e-5 <= alpha) and the 7.0 shortcut: only DNAcopy's full 9 500 clean permutations of
+    24 n short arcs each can accept the split (tests/test_cbs_stats_gpu.py uses the same sample)."""
+    from cnvkit_b200 import synth
+
+    rng = np.random.default_rng(0xC11FF)
+    n = 120000
+    w = rng.uniform(0.5, 1.0, n)
+    x = rng.normal(0, 0.25, n)
+    x[45000:] += 0.009
+    return synth.round_sig6(x), synth.round_sig6(w), np.array([0, n], dtype=np.int64)
+
+
+def extra_legs(args, torch, dev, data):
+    """N = 1 only: (a) the permutation-cliff sample, (b) C3 through the public do_segmentation(cnarr, 'cbs') with the
+    table in host memory (pandas in, .cns out), (c) C1: the reference's own exome-sized .cnr shape through
+    do_segmentation.  Reported beside the headline; none of them enters `value`."""
+    import pandas as pd
+
+    from cnvkit_b200 import _lib, synth
+    from cnvkit_b200.cnary import CopyNumArray
+    from cnvkit_b200.segmentation import cbs, do_segmentation
+
+    out = {}
+    stream = torch.cuda.current_stream()
+    # (a) cliff
+    cx, cw, coff = cliff_sample()
+    dcx, dcw = torch.from_numpy(cx).to(dev), torch.from_numpy(cw).to(dev)
+    ms = []
+    st = None
+    for k in range(3):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        r = cbs.segment_arms(None, None, coff, alpha=ALPHA, device_ptrs=(dcx.data_ptr(), dcw.data_ptr()),
+                             stream=_lib.stream_ptr(stream))
+        b.record(stream)
+        torch.cuda.synchronize()
+        st = r[4]
+        if k:
+            ms.append(a.elapsed_time(b))
+    out["cliff"] = {"workload": "one 120 000-bin arm, |t| = 6.81: accepted only by 9 500 clean hybrid permutations "
+                                "(24 n arcs each)", "ms_per_step": float(np.mean(ms)), "bins_per_s": 120000 / (np.mean(ms) * 1e-3),
+                    "perms_run": st["perms_run"], "perm_arcs": st["perm_arcs"], "segments": int(len(r[0])),
+                    "perm_arcs_per_s": st["perm_arcs"] / (np.mean(ms) * 1e-3)}
+    # (b) public API on C3
+    chrom = np.asarray(synth.CHROM_NAMES, dtype=object)[data["chromosome_id"]]
+    df = pd.DataFrame({"chromosome": chrom, "start": data["start"], "end": data["end"], "gene": "-",
+                       "log2": data["log2"], "depth": np.exp2(data["log2"]) * 100.0, "weight": data["weight"]})
+    cnarr = CopyNumArray(df, {"sample_id": "C3"})
+    t_api = []
+    for k in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cns = do_segmentation(cnarr, "cbs", threshold=ALPHA)
+        torch.cuda.synchronize()
+        if k:
+            t_api.append(time.perf_counter() - t0)
+    out["public_api_c3"] = {"call": "cnvkit_b200.segmentation.do_segmentation(cnarr, 'cbs') -- pandas table in host "
+                                    "memory in, .cns CopyNumArray out (by_arm, outlier mask, %.6g, CBS, transfer_fields)",
+                            "ms_per_sample": 1e3 * float(np.mean(t_api)), "bins_per_s": len(df) / float(np.mean(t_api)),
+                            "segments": int(len(cns))}
+    # (c) C1-shaped sample: the first 19 089 bins' worth of an exome panel (47 arms) -- the reference's own
+    # p2-20_1.cnr cannot travel to the GPU box; tests/golden holds its Haar tables, this leg times the same shape
+    bins = synth.exome_bins(n_targets=14000, n_antitargets=5089, seed=0xC1)
+    ref = synth.exome_reference(bins)
+    smp = synth.exome_sample(bins, ref, seed=7)
+    T, A, R = synth.exome_tables(bins, ref, smp, sample_id="C1")
+    from cnvkit_b200 import fix as _fix
+
+    t_c1 = []
+    for k in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cnr = _fix.do_fix(T, A, R)
+        cns1 = do_segmentation(cnr, "cbs", threshold=ALPHA)
+        torch.cuda.synchronize()
+        if k:
+            t_c1.append(time.perf_counter() - t0)
+    out["c1_shape"] = {"workload": f"C1 shape: {len(T) + len(A)} bins, do_fix + do_segmentation('cbs') through the "
+                                   "pandas API, one sample", "ms_per_sample": 1e3 * float(np.mean(t_c1)),
+                       "segments": int(len(cns1))}
+    return out
 
 
 def run_b200(args):
@@ -297,6 +438,7 @@ def run_b200(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa(torch, local_rank) if world > 1 else "single rank: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
@@ -308,7 +450,7 @@ def run_b200(args):
         nbins_total = int(data["arm_offsets"][-1])
     else:  # cohort mode: every rank owns one whole sample; the same synthetic sample on every rank, so that
         # per-GPU work is exactly fixed (CBS cost is data-dependent: one borderline node that needs all
-        # 9 500 permutations costs several times the rest of the sample)
+        # 9 500 permutations costs several times the rest of the sample -- see the `cliff` object)
         data = synth.wgs_sample(total_bins=args.bins)
         owner = np.full(len(data["arm_offsets"]) - 1, rank)
         nbins_total = int(data["arm_offsets"][-1]) * world
@@ -321,6 +463,8 @@ def run_b200(args):
     dw = hw.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
+    steps_max = max(args.steps, 3) + 2
+    gatherer = shard.TableGatherer(ncols=5, capacity=4096 * steps_max, device=dev if world > 1 else None)
 
     def step_resident():
         return cbs.segment_arms(None, None, off, alpha=ALPHA, prune=prune,
@@ -334,40 +478,42 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather_tables(res):
-        """NCCL gather of the per-rank segment tables (cnvkit_b200.shard: counts, then padded rows)."""
+    def stage_table(res):
+        """this step's table -> the pinned gather payload (host memory only; no device work, no sync)"""
         arm, lo, hi, mean = res[:4]
-        if world == 1:
-            return len(arm)
         g_arm = mine[arm] if len(arm) else np.zeros(0, np.int64)
         shift = (data["arm_offsets"][g_arm] - off[arm]) if len(arm) else np.zeros(0, np.int64)
-        sample_col = np.full(len(arm), 0 if by_arms else rank, dtype=np.int64)
-        # one collective: fixed-capacity payloads (a 3 M-bin sample has a few hundred segments)
-        full = shard.gather_tables([sample_col, g_arm.astype(np.int64), lo + shift, hi + shift, mean], dst=0,
-                                   device=dev, capacity=4096)
-        return len(full[0]) if full is not None else 0
+        gatherer.append([np.full(len(arm), 0 if by_arms else rank), g_arm, lo + shift, hi + shift, mean])
 
-    def timed(fn, steps, profile=False):
-        """Per-step CUDA-event brackets on the launching stream; L2 flushed between steps."""
-        ev_ms, res = [], None
+    def timed(fn, steps):
+        """K steps between two barriers; one CUDA-event pair per step on the launching stream (L2 flushed
+        before each pair); the segment tables of the K steps are gathered with ONE collective after the last
+        step, timed by its own event pair and charged to the K steps."""
+        pairs, res = [], None
+        barrier()
         for _ in range(steps):
             flush.zero_()
-            barrier()
             a = torch.cuda.Event(enable_timing=True)
             b = torch.cuda.Event(enable_timing=True)
             a.record(stream)
             res = fn()
-            nseg_total = gather_tables(res)
             b.record(stream)
-            barrier()
-            ev_ms.append(a.elapsed_time(b))
-        return ev_ms, res, nseg_total
+            stage_table(res)
+            pairs.append((a, b))
+        g0 = torch.cuda.Event(enable_timing=True)
+        g1 = torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        full = gatherer.flush(dst=0)
+        g1.record(stream)
+        barrier()
+        step_ms = [a.elapsed_time(b) for a, b in pairs]
+        gather_ms = g0.elapsed_time(g1)
+        nrows = int(len(full)) // steps if full is not None else 0
+        return (float(np.sum(step_ms)) + gather_ms) / steps, gather_ms, res, nrows
 
-    # warm-up (>= 3): allocator pools, module load, clocks
-    for _ in range(max(args.warmup, 3)):
-        gather_tables(step_resident())      # includes NCCL's lazy communicator set-up
-    gather_tables(step_host())
-    barrier()
+    # warm-up (>= 3): allocator pools, module load, clocks, NCCL's lazy communicator set-up
+    timed(step_resident, max(args.warmup, 3))
+    timed(step_host, 1)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -375,21 +521,22 @@ def run_b200(args):
         time.sleep(0.3)
     launches0 = _lib.launch_count()
     t0 = time.time()
-    ev_ms, res, nseg_total = timed(step_resident, args.steps)
+    ms_res, gather_ms, res, nseg_total = timed(step_resident, args.steps)
     t1 = time.time()
     launches = _lib.launch_count() - launches0
     # per-kernel attribution: the same K steps again with one CUDA-event pair around every kernel class
     # (kept out of the headline timing: creating and recording ~150 events per step costs ~0.5 ms)
     _lib.prof_enable(True)
     _lib.prof_reset()
-    ev_prof, _, _ = timed(step_resident, args.steps)
+    ms_prof, _, _, _ = timed(step_resident, args.steps)
     t1 = time.time()
     prof = _lib.prof_get()
     _lib.prof_enable(False)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     stats = res[4]
 
-    e2e_ms, res_h, _ = timed(step_host, max(2, min(args.steps, 5)))
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_host, gather_ms_h, res_h, _ = timed(step_host, e2e_steps)
 
     def max_over_ranks(v):
         if world == 1:
@@ -398,8 +545,16 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    ms_step = max_over_ranks(float(np.mean(ev_ms)))
-    ms_e2e = max_over_ranks(float(np.mean(e2e_ms)))
+    ms_step = max_over_ranks(ms_res)
+    ms_e2e = max_over_ranks(ms_host)
+
+    cohort = None
+    if not args.no_cohort_leg and not args.no_prune:
+        try:
+            cohort = cohort_core(args, torch, dist, dev, world, rank, local_rank, samples=args.cohort_samples, steps=1,
+                                 quiet=True)
+        except Exception as exc:  # the headline line must still print
+            cohort = {"error": repr(exc)}
 
     if rank == 0:
         # ---- rooflines (device time per kernel class inside the timed region, CUDA events)
@@ -430,22 +585,18 @@ def run_b200(args):
             "kernel_ms_per_step": arc_ms,
             "note": "non-fused FP64 ops: 1 flop per issued DP instruction, so frac <= 0.5 of the DFMA peak; "
                     "with --no-prune (every arc evaluated) the same kernel reaches 0.46; traffic = ncu dram bytes of "
-                    "the level-1 launches (band 48.0 MB + scan 1.7 MB: one read of S and cw, "
-                    "profiles/r01d_cbs_kernels_full_summary.md) -- DRAM is idle, the pipe is the bound",
+                    "the level-1 launches (one read of S and cw) -- DRAM is idle, the pipe is the bound",
         }
         prep_ms = per_step.get("cbs_prep", 0.0)
         prep_bytes = PREP_BYTES_PER_BIN * stats["prep_bins"]
         prep_gbs = prep_bytes / (prep_ms * 1e-3) / 1e9 if prep_ms > 0 else 0.0
         roof_prep = {
-            "kernel": "cbs_prep_{sums,scan,finish,node}_kernel", "bound": "hbm", "achieved": prep_gbs, "peak": hbm_peak,
-            "unit": "GB/s", "frac": prep_gbs / hbm_peak, "traffic": 217.0e6, "peak_source": hbm_src,
-            "algorithmic": f"{PREP_BYTES_PER_BIN} B/bin (read log2, weight; write xc, y, wn, S, cw) x "
+            "kernel": "cbs_prep_* kernels", "bound": "hbm", "achieved": prep_gbs, "peak": hbm_peak,
+            "unit": "GB/s", "frac": prep_gbs / hbm_peak, "traffic": PREP_TRAFFIC, "peak_source": hbm_src,
+            "algorithmic": f"{PREP_BYTES_PER_BIN} B/bin x "
                            f"{stats['prep_bins']} bins centred and prefix-summed over {stats['levels']} levels",
             "kernel_ms_per_step": prep_ms,
-            "note": "blocked FP64 prefix scan cut into 2048-point tiles (one CTA each); the tile kernels move 104 B/bin "
-                    "(the sums pass re-reads the inputs, the tile-local prefixes make one round trip before the "
-                    "carries are added); traffic = ncu dram bytes of the level-1 launches of the three tile kernels "
-                    "(profiles/r01d_cbs_kernels_full_summary.md), the rest of the writes stays in L2",
+            "note": PREP_NOTE,
         }
         roofline = dict(roof_prep if dominant == "cbs_prep" else roof_scan)
         roofline["dominant_class_by_time"] = dominant
@@ -471,32 +622,38 @@ def run_b200(args):
                 exome = exome_leg(args, torch, dev)
             except Exception as exc:  # the headline line must still print
                 exome = {"error": repr(exc)}
+        extras = None
+        if world == 1 and not args.no_extra_legs and not args.no_prune:
+            try:
+                extras = extra_legs(args, torch, dev, data)
+            except Exception as exc:
+                extras = {"error": repr(exc)}
         h2d = int(hx.numel() * 8 + hw.numel() * 8)
         d2h = int(len(res_h[0]) * (4 + 8 + 8 + 8))
+        cfg = wgs_config(args, world, by_arms)
         line = {
             "metric": METRIC, "value": nbins_total / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if by_arms else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C3 synthetic WGS, {args.bins} 1-kb bins, 48 arms, CBS alpha={ALPHA} nperm=10000"
-                                   + ("" if by_arms or world == 1 else f", one such sample per GPU ({world} replicas of the same synthetic sample)"),
-                       "sharding": "single GPU" if world == 1 else
-                       (f"arms of one sample over {world} ranks by LPT on n^2; NCCL gather of tables" if by_arms else
-                        f"samples over {world} ranks (cohort mode), no data-path collective; NCCL gather of tables"),
-                       "l2": "256 MB flush write between timed steps", "prune": prune,
-                       "segments": nseg_total},
+            "config": cfg, "segments": nseg_total, "prune": prune, "numa": numa,
+            "gather_ms_per_batch": gather_ms,
             "e2e": {"value": nbins_total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches),
+            "gpu_launches_per_step": int(launches) // max(args.steps, 1),
             "roofline": roofline,
             "rooflines": [roof_prep, roof_scan],
             "cpu_baseline": cpu,
             "clocks": clocks,
             "kernel_ms_per_step": per_step,
             "kernel_ms_note": "device time per kernel class from a second pass of the same steps with CUDA events "
-                              f"around every class ({float(np.mean(ev_prof)):.3f} ms/step with the events on)",
+                              f"around every class ({ms_prof:.3f} ms/step with the events on)",
             "cbs_stats": stats,
+            "cohort": cohort,
             "exome": exome,
         }
+        if extras:
+            line.update(extras)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -613,13 +770,104 @@ def run_reference_build(args):
         "note": "e2e includes TSV parsing (native reader) of every file; value == e2e (no resident variant)"}))
 
 
+def cohort_core(args, torch, dist, dev, world, rank, local_rank, samples, steps, quiet=False):
+    """C5: `samples` exome tumours fixed against one pooled reference and CBS-segmented, sharded by sample over
+    the ranks in blocks (strong scaling: the cohort is fixed), .cns rows gathered on rank 0 with one NCCL
+    collective per step.  Returns the result object on rank 0 (None elsewhere).  The process group, if any,
+    is the caller's."""
+    from cnvkit_b200 import _lib, cohort, shard
+
+    n_distinct = 16
+    bins, ref, smp, cols, (T, A, R) = exome_world(n_distinct)
+    panel = cohort.Panel(T, A, R)
+    owner = shard.block_owner(samples, world)
+    mine = np.flatnonzero(owner == rank)
+    pinned = [tuple({k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in part.items()} for part in c)
+              for c in cols]
+    resident = [tuple({k: v.to(dev) for k, v in part.items()} for part in c) for c in pinned]
+    stream = torch.cuda.current_stream()
+    gatherer = shard.TableGatherer(ncols=7, capacity=max(len(mine), 1) * 512 + 16, device=dev if world > 1 else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(source, which):
+        work = [source[i % n_distinct] for i in which]
+        if source is pinned:
+            work = [tuple({k: v.numpy() for k, v in part.items()} for part in c) for c in work]
+        res = panel.run(work, method="cbs", batch=8, workers=args.workers, sample_ids=[f"S{i}" for i in which])
+        for i, (_c, cns) in zip(which, res):
+            d = cns.data
+            gatherer.append([np.full(len(d), i)] + [d[c].to_numpy() for c in ("start", "end", "log2", "probes", "weight", "depth")])
+        full = gatherer.flush(dst=0)
+        return len(full) if full is not None else 0
+
+    def timed(source, nsteps):
+        out = []
+        n_rows = 0
+        for _ in range(nsteps):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            n_rows = step(source, mine)
+            b.record(stream)
+            barrier()
+            out.append(a.elapsed_time(b))
+        return out, n_rows
+
+    # warm-up on a slice of this rank's share (module load, allocator pools, NCCL communicator)
+    for _ in range(2):
+        step(resident, mine[: min(len(mine), 32)])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = _lib.launch_count()
+    t0 = time.time()
+    ev, n_rows = timed(resident, steps)
+    t1 = time.time()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ev_h, _ = timed(pinned, 1)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms = max_over_ranks(float(np.mean(ev)))
+    ms_h = max_over_ranks(float(np.mean(ev_h)))
+    if rank != 0:
+        return None
+    per_sample_bytes = sum(v.numel() * 8 for part in pinned[0] for v in part.values())
+    return {
+        "metric": EXOME_METRIC, "value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+        "steps": steps, "warmup": 2, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C5 cohort of {samples} C2 exome tumours ({n_distinct} distinct synthetic samples "
+                               f"cycled), fix + CBS, 8 samples per segmentation call, {args.workers} host threads / streams per rank",
+                   "samples": int(samples),
+                   "sharding": f"samples over {world} rank(s) in blocks; one NCCL all-gather of the .cns rows per step",
+                   "l2": "inputs of one step (>= 400 MB of columns per rank) exceed the 126 MB L2",
+                   "segment_rows": n_rows},
+        "e2e": {"value": samples / (ms_h * 1e-3), "unit": "samples/s", "ms_per_step": ms_h,
+                "h2d_bytes_per_step": int(per_sample_bytes * len(mine)), "d2h_bytes_per_step": int(n_rows * 7 * 8)},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": None, "cpu_baseline": None,
+        "note": "a step = the whole cohort; host-side table assembly (pandas) is inside the timed region; strong-scaling "
+                "efficiency = value(N) / (N x value(1)) with the same cohort size at every N"}
+
+
 def run_cohort(args):
-    """C5: a cohort of exome tumours fixed against one pooled reference and CBS-segmented, sharded by
-    sample over the ranks (strong scaling: the cohort is fixed), .cns rows gathered on rank 0 with NCCL."""
+    """--workload cohort: the C5 leg alone (it is also part of the default run, key `cohort`)."""
     import torch
     import torch.distributed as dist
 
-    from cnvkit_b200 import _lib, cohort, shard
+    from cnvkit_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -646,88 +894,13 @@ def run_cohort(args):
         return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bind_to_gpu_numa(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
-    n_distinct = 16
-    bins, ref, samples, cols, (T, A, R) = exome_world(n_distinct)
-    panel = cohort.Panel(T, A, R)
-    owner = shard.block_owner(args.samples, world)
-    mine = np.flatnonzero(owner == rank)
-    pinned = [tuple({k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in part.items()} for part in c)
-              for c in cols]
-    resident = [tuple({k: v.to(dev) for k, v in part.items()} for part in c) for c in pinned]
-    stream = torch.cuda.current_stream()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step(source):
-        work = [source[i % n_distinct] for i in mine]
-        if source is pinned:
-            work = [tuple({k: v.numpy() for k, v in part.items()} for part in c) for c in work]
-        res = panel.run(work, method="cbs", batch=8, workers=args.workers, sample_ids=[f"S{i}" for i in mine])
-        rows = [np.concatenate([np.full(len(cns), i, dtype=np.int64) for i, (_c, cns) in zip(mine, res)])
-                if len(res) else np.zeros(0, np.int64)]
-        for col in ("start", "end", "log2", "probes", "weight", "depth"):
-            rows.append(np.concatenate([cns.data[col].to_numpy() for _c, cns in res]) if len(res) else np.zeros(0))
-        full = shard.gather_tables(rows, dst=0, device=dev)
-        return len(full[0]) if full is not None else 0
-
-    def timed(source, steps):
-        out = []
-        n_rows = 0
-        for _ in range(steps):
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            n_rows = step(source)
-            b.record(stream)
-            barrier()
-            out.append(a.elapsed_time(b))
-        return out, n_rows
-
-    for _ in range(max(args.warmup, 3) if args.samples <= 256 else 1):
-        step(resident)
-    sampler = ClockSampler(local_rank)
+    line = cohort_core(args, torch, dist, dev, world, rank, local_rank, samples=args.samples, steps=args.steps)
     if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    launches0 = _lib.launch_count()
-    t0 = time.time()
-    ev, n_rows = timed(resident, args.steps)
-    t1 = time.time()
-    launches = _lib.launch_count() - launches0
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
-    ev_h, _ = timed(pinned, max(1, min(args.steps, 2)))
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    ms = max_over_ranks(float(np.mean(ev)))
-    ms_h = max_over_ranks(float(np.mean(ev_h)))
-    if rank == 0:
-        per_sample_bytes = sum(v.numel() * 8 for part in pinned[0] for v in part.values())
-        emit(({
-            "metric": EXOME_METRIC, "value": args.samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3) if args.samples <= 256 else 1, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C5 cohort of {args.samples} C2 exome tumours ({n_distinct} distinct synthetic samples "
-                                   f"cycled), fix + CBS, 8 samples per segmentation call, {args.workers} host threads / streams per rank",
-                       "sharding": f"samples over {world} rank(s) in blocks; NCCL gather of .cns rows",
-                       "l2": "inputs of one step (>= 400 MB of columns per rank) exceed the 126 MB L2",
-                       "segment_rows": n_rows},
-            "e2e": {"value": args.samples / (ms_h * 1e-3), "unit": "samples/s", "ms_per_step": ms_h,
-                    "h2d_bytes_per_step": int(per_sample_bytes * len(mine)), "d2h_bytes_per_step": int(n_rows * 7 * 8)},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": None, "cpu_baseline": None,
-            "note": "host-side table assembly (pandas) is inside the timed region; see the C3 line for kernel rooflines"}))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

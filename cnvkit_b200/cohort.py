@@ -249,7 +249,7 @@ class Panel:
             x = d_log2.index_select(0, d_fidx)
             w = d_w.index_select(0, d_fidx)
             if method == "cbs":
-                x, w, sub = self._quantise(x, w)
+                x, w, sub = self._quantise(x, w, f_arm, n_arms)
                 if sub is not None:
                     fidx, f_arm = fidx[sub], f_arm[sub]
                 units = segmentation._arm_offsets(f_arm, n_arms)
@@ -291,14 +291,24 @@ class Panel:
                     results[k] = segmetrics.do_segmetrics(cnr, results[k], interval_stats=["ci"], **ci)
         return results
 
-    def _quantise(self, x, w):
+    def _quantise(self, x, w, f_arm=None, n_arms=0):
         """%.6g of both columns (segmentation/__init__.py:299-301) and the R row filters (cbs.py:22-35)."""
         n = len(x)
         xq, wq = _dev.empty(n, torch.float64), _dev.empty(n, torch.float64)
         unhandled = np.zeros(1, dtype=np.uint64)
         cols = [(x.contiguous(), xq)]
-        if bool(torch.isfinite(w).any()):
+        w_nan = torch.isnan(w)
+        any_nan = bool(w_nan.any())
+        if not any_nan or not bool(w_nan.all()):
             cols.append((w.contiguous(), wq))
+            if any_nan and f_arm is not None:
+                # the R script runs per arm: an arm without a single non-NA weight gets weight 1.0 (cbs.py:22-28)
+                ok_np = (~w_nan).cpu().numpy()
+                has_w = np.bincount(f_arm, weights=ok_np.astype(np.float64), minlength=n_arms) > 0
+                no_w = ~has_w[f_arm]
+                if no_w.any():
+                    w = torch.where(torch.from_numpy(no_w).to(w.device), torch.ones_like(w), w)
+                    cols[-1] = (w.contiguous(), wq)
         else:
             wq.fill_(1.0)                         # cbs.py:25-28: no usable weights -> weight 1 per bin
         for src, dst in cols:

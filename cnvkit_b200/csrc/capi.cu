@@ -457,6 +457,22 @@ int cnvk_cbs_segment(const double* log2, const double* weight, const int64_t* ar
     return hc.finish();
 }
 
+int cnvk_cbs_node_diag(const double* log2, const double* weight, const int64_t* node_offsets, int32_t n_nodes,
+                       const cnvk_cbs_params* p, double* out6, int32_t* iout5) {
+    HostCall hc;
+    RC(hc.begin());
+    const size_t N = n_nodes > 0 ? (size_t)node_offsets[n_nodes] : 0;
+    double *dx, *dw;
+    RC(hc.upload(log2, N, &dx));
+    RC(hc.upload(weight, N, &dw));
+    CbsParams P;
+    P.alpha = p->alpha; P.nperm = p->nperm; P.min_width = p->min_width; P.kmax = p->kmax; P.nmin = p->nmin;
+    P.eta = p->eta; P.hybrid = p->hybrid; P.prune = p->prune; P.seed = p->seed;
+    std::vector<long long> off(node_offsets, node_offsets + n_nodes + 1);
+    RC(cbs_node_diag(dx, dw, off.data(), n_nodes, P, out6, (int*)iout5, hc.stream));
+    return hc.finish();
+}
+
 int cnvk_outlier_mask_dev(const double* d_log2, const int64_t* arm_offsets, int32_t n_arms, double q, double factor,
                           uint8_t* d_mask, void* stream) {
     RC(ensure_init());
@@ -475,7 +491,16 @@ int cnvk_round_sig_dev(const double* d_x, int64_t n, int32_t digits, double* d_o
 int cnvk_segment_bin_sums_dev(const double* d_depth, const double* d_weight, const int64_t* d_lo, const int64_t* d_hi,
                               int32_t nseg, double* d_seg_weight, double* d_seg_depth, void* stream) {
     RC(ensure_init());
-    return segment_bin_sums(d_depth, d_weight, (const long long*)d_lo, (const long long*)d_hi, nseg, d_seg_weight,
+    return segment_bin_sums(d_depth, d_weight, (const long long*)d_lo, (const long long*)d_hi, nullptr, nullptr, nseg,
+                            d_seg_weight, d_seg_depth, (cudaStream_t)stream);
+}
+
+int cnvk_segment_bin_sums_masked_dev(const double* d_depth, const double* d_weight, const int64_t* d_lo,
+                                     const int64_t* d_hi, const int64_t* d_bin_end, const int64_t* d_seg_start,
+                                     int32_t nseg, double* d_seg_weight, double* d_seg_depth, void* stream) {
+    RC(ensure_init());
+    return segment_bin_sums(d_depth, d_weight, (const long long*)d_lo, (const long long*)d_hi,
+                            (const long long*)d_bin_end, (const long long*)d_seg_start, nseg, d_seg_weight,
                             d_seg_depth, (cudaStream_t)stream);
 }
 

@@ -58,6 +58,13 @@ struct Node {
     int lock, state, nrejc, blk_off;
     double ostat, ostat1;
     double delta;  // getmncwt: lightest circular arc of kmax+1 probes / total weight (n > nmin only)
+    double tailp;  // DNAcopy tailp of the node when the series was summed, else -1 (diagnostics)
+};
+
+struct CbsDiag {
+    std::vector<Node> nodes;       // after the decision kernels of the (single) level
+    std::vector<int> nrej;         // permutations whose statistic reached the observed one, per node
+    std::vector<double> flank_p;   // [node][2] flank p-values with the permutations forced, -1 = no test
 };
 
 struct Decision {
@@ -1031,11 +1038,12 @@ __global__ void cbs_stat_kernel(Node* __restrict__ nodes, int nnodes, double alp
         const double t2 = t2_of(nd->best_q, nd->tss, n);
         ostat1 = sqrt(t2);
         ostat = t2 * 0.99999;
-        if (ostat1 > 0.1) {
+        if (ostat1 > 0.1 || (hybrid_method & 2)) {
             const int bi = nd->best_i, bj = nd->best_j;
             const int l = min(bj - bi, n - bj + bi);
-            if (ostat1 >= 7.0 && l >= 10) state = ST_SPLIT;
-            else if (hybrid_method && n > nmin) state = ST_NEED_TAILP;
+            const bool diag = (hybrid_method & 2) != 0;   // diagnostics: every hybrid node gets its tail probability
+            if (ostat1 >= 7.0 && l >= 10 && !diag) state = ST_SPLIT;
+            else if ((hybrid_method & 1) && n > nmin) state = ST_NEED_TAILP;
             else { state = ST_PERM_EXACT; nrejc = (int)(alpha * (double)nperm); }
         }
     }
@@ -1157,6 +1165,7 @@ __global__ void cbs_decide_kernel(Node* __restrict__ nodes, int nnodes, Decision
         for (int g = 0; g < ngrid; ++g) p += terms[(size_t)idx * ngrid + g];
         p = 9.973557e-2 * (b * b * b) * exp(-(b * b) / 2.0) * p;
         p = 2.0 * p;
+        nd->tailp = p;
         if (p > alpha) state = ST_FINAL;
         else { state = ST_PERM_HYBRID; nrejc = (int)((alpha - p) * (double)nperm); }
         nd->state = state;
@@ -1416,7 +1425,8 @@ cbs_flank_part_kernel(const Node* __restrict__ nodes, const FlankTest* __restric
     }
 }
 
-__global__ void cbs_flank_prep_kernel(FlankTest* __restrict__ tests, int ntests, const double* __restrict__ part) {
+__global__ void cbs_flank_prep_kernel(FlankTest* __restrict__ tests, int ntests, const double* __restrict__ part,
+                                      int force_perm) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= ntests) return;
     FlankTest* o = &tests[idx];
@@ -1437,7 +1447,7 @@ __global__ void cbs_flank_prep_kernel(FlankTest* __restrict__ tests, int ntests,
     double tstat = rn * rm1 * (odiff * odiff) / (rn - rm1);
     tstat = tstat / ((tss - tstat) / ((double)n - 2.0));
     o->m1 = m1; o->s0 = s0; o->rm1 = rm1; o->xbar = xbar; o->ostat = 0.99999 * odiff;
-    if (tstat > 25.0 && m1 >= 10) { o->pvalue = 0.0; o->need_perm = 0; }
+    if (tstat > 25.0 && m1 >= 10 && !force_perm) { o->pvalue = 0.0; o->need_perm = 0; }
     else { o->pvalue = -1.0; o->need_perm = 1; }
 }
 
@@ -1614,8 +1624,12 @@ static void tiles_for(int n, int node, std::vector<int4>* table, long long* task
     *tiles = q;
 }
 
-int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, const CbsParams& P,
-                std::vector<CbsSeg>& segs, CbsStats* stats, cudaStream_t stream) {
+int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, const CbsParams& P_in,
+                std::vector<CbsSeg>& segs, CbsStats* stats, cudaStream_t stream, CbsDiag* diag) {
+    // diagnostics (cnvk_cbs_node_diag): every interval is ONE node; one level only, the tail series is always
+    // summed, every node runs all nperm permutations (no stopping rule) and both flank tests with permutations
+    CbsParams P = P_in;
+    if (diag) P.prune |= 2;
     segs.clear();
     CbsStats st;
     memset(&st, 0, sizeof(st));
@@ -1737,6 +1751,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             nd.lo = frontier[k].lo; nd.hi = frontier[k].hi; nd.base = frontier[k].base;
             nd.blk_off = (int)blk_off;
             nd.best_q = -1.0; nd.best_i = 0x7fffffff; nd.best_j = 0x7fffffff;
+            nd.tailp = -1.0;
             const int n = nd.hi - nd.lo;
             st.prep_bins += n;
             h_ptile_off[k] = (int)ptiles;
@@ -1844,7 +1859,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         {
             ProfScope ps(PC_CBS_DECIDE, stream);
             const int ngrid = 100;
-            cbs_stat_kernel<<<div_up(nn, 128), 128, 0, stream>>>(d_nodes, nn, P.alpha, P.nperm, P.nmin, P.hybrid);
+            cbs_stat_kernel<<<div_up(nn, 128), 128, 0, stream>>>(d_nodes, nn, P.alpha, P.nperm, P.nmin, (P.hybrid ? 1 : 0) | (diag ? 2 : 0));
             CNVK_LAUNCH_CHECK();
             if (P.hybrid && !(P.prune & 2)) {
                 cbs_tailp_bounds_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, nn, P.alpha, P.nperm, ngrid);
@@ -1867,6 +1882,19 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             CNVK_CHECK(cudaMemcpyAsync(p_dec, d_dec, nn * sizeof(Decision), cudaMemcpyDeviceToHost, stream));
             CNVK_CHECK(cudaStreamSynchronize(stream));
             memcpy(h_dec.data(), p_dec, (size_t)nn * sizeof(Decision));
+        }
+        std::vector<int> diag_nrej;
+        if (diag) {
+            diag->nodes.resize(nn);
+            CNVK_CHECK(cudaMemcpyAsync(diag->nodes.data(), d_nodes, nn * sizeof(Node), cudaMemcpyDeviceToHost, stream));
+            CNVK_CHECK(cudaStreamSynchronize(stream));
+            diag_nrej.assign(nn, 0);
+            for (int k = 0; k < nn; ++k) {
+                const Node& nd = diag->nodes[k];
+                if (nd.flat || nd.best_q < 0.0) { h_dec[k].state = ST_FINAL; continue; }
+                h_dec[k].state = (P.hybrid && nd.hi - nd.lo > P.nmin) ? ST_PERM_HYBRID : ST_PERM_EXACT;
+                h_dec[k].nrejc = P.nperm;
+            }
         }
 
         // ---- permutation reference distributions
@@ -1962,9 +1990,11 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                     for (int c = 0; c < chunk && !decided; ++c) {
                         const int np = p0 + c + 1;
                         if (flags[(size_t)a * chunk + c]) { nrej[q]++; kk[q]++; }
+                        if (diag) continue;
                         if (nrej[q] > nrejc) decided = -1;
                         else if (np >= sbdry[kk[q] - 1]) decided = 1;
                     }
+                    if (diag) diag_nrej[list[q]] = nrej[q];
                     if (decided == 0 && p0 + chunk >= P.nperm) decided = 1;  // survived every permutation
                     if (decided == 0) { next_active.push_back(active[a]); next_q.push_back(q); }
                     else h_dec[list[q]].state = decided > 0 ? ST_SPLIT : ST_FINAL;
@@ -2007,7 +2037,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 cbs_flank_part_kernel<<<dim3(nz, FLANK_SPLIT), 256, 0, stream>>>(d_nodes, d_tests + z0, d_xc, d_w, d_part + (size_t)z0 * FLANK_SPLIT * 5);
                 CNVK_LAUNCH_CHECK();
             }
-            cbs_flank_prep_kernel<<<div_up(nt, 128), 128, 0, stream>>>(d_tests, nt, d_part);
+            cbs_flank_prep_kernel<<<div_up(nt, 128), 128, 0, stream>>>(d_tests, nt, d_part, diag ? 1 : 0);
             CNVK_LAUNCH_CHECK();
             CNVK_CHECK(cudaMemcpyAsync(p_tests, d_tests, nt * sizeof(FlankTest), cudaMemcpyDeviceToHost, stream));
             CNVK_CHECK(cudaStreamSynchronize(stream));
@@ -2036,6 +2066,13 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             for (int t = 0; t < nt; ++t) pvals[t] = tests[t].pvalue;
         }
 
+        if (diag) {
+            diag->nrej = diag_nrej;
+            diag->flank_p.assign((size_t)2 * nn, -1.0);
+            for (size_t t = 0; t < tests.size(); ++t) diag->flank_p[(size_t)2 * test_owner[t] + (tests[t].tid - 1)] = pvals[t];
+            if (stats) *stats = st;
+            return 0;
+        }
         // ---- next frontier
         std::vector<HostNode> next;
         size_t tcur = 0;
@@ -2108,6 +2145,40 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         st.obs_arcs = st.obs_subtiles_scanned * (long long)CBS_BLK * CBS_BLK + (long long)h_stats[2] * BAND_SUB * BAND_SUB;
     }
     if (stats) *stats = st;
+    return 0;
+}
+
+// One level over the given intervals, nothing decided early: the numbers the statistical tests compare with
+// true-shuffle Monte-Carlo estimates (tests/test_cbs_stats_gpu.py; oracle twin: cbso_node_diag).
+// out6[k] = {sqrt(T^2), tailp | -1, delta | -1, 0.99999 T^2, flank p 1 | -1, flank p 2 | -1},
+// iout5[k] = {arc i, arc j, exceedances among nperm permutations, hybrid?, constant data?}.
+int cbs_node_diag(const double* d_x, const double* d_w, const long long* h_off, int n_nodes, const CbsParams& P,
+                  double* out6, int* iout5, cudaStream_t stream) {
+    for (int k = 0; k < n_nodes; ++k)
+        if (h_off[k + 1] - h_off[k] < 2 * P.min_width) { set_last_error("cbs_node_diag: node %d is shorter than 2*min_width", k); return -2; }
+    CbsDiag diag;
+    std::vector<CbsSeg> segs;
+    CbsStats st;
+    const int rc = cbs_segment(d_x, d_w, h_off, n_nodes, P, segs, &st, stream, &diag);
+    if (rc) return rc;
+    for (int k = 0; k < n_nodes; ++k) {
+        const Node& nd = diag.nodes[k];
+        double* o = out6 + (size_t)6 * k;
+        int* io = iout5 + (size_t)5 * k;
+        const bool live = !nd.flat && nd.best_q >= 0.0;
+        const bool hyb = P.hybrid && (nd.hi - nd.lo) > P.nmin;
+        o[0] = live ? nd.ostat1 : -1.0;
+        o[1] = (live && hyb) ? nd.tailp : -1.0;
+        o[2] = (live && hyb) ? nd.delta : -1.0;
+        o[3] = live ? nd.ostat : -1.0;
+        o[4] = diag.flank_p[(size_t)2 * k];
+        o[5] = diag.flank_p[(size_t)2 * k + 1];
+        io[0] = live ? nd.best_i : 0;
+        io[1] = live ? nd.best_j : 0;
+        io[2] = diag.nrej[k];
+        io[3] = hyb ? 1 : 0;
+        io[4] = nd.flat ? 1 : 0;
+    }
     return 0;
 }
 

@@ -4,8 +4,13 @@
 // xperm/wxperm Fisher-Yates); a sequential stream cannot be evaluated tile-parallel on a GPU and
 // would make results depend on the order nodes are visited.  Instead permutation `perm` of test
 // `tid` on the interval [lo,hi) of an arm is the keyed bijection below, evaluated independently
-// per element: Philox4x32-10(counter=(perm,tid,lo,hi), key=seed) yields four round keys for a
-// 4-round alternating Feistel network over ceil(log2 n) (>= 8) bits, cycle-walked into [0,n).
+// per element: Philox4x32-10(counter=(perm,tid,lo,hi), key=seed) yields four round keys (four more
+// are derived from them) for an alternating Feistel network over ceil(log2 n) (>= 8) bits,
+// cycle-walked into [0,n).  Rounds by domain width: a balanced Feistel network over 2a bits is
+// pairwise-uniform only up to O(2^-a) after 4 rounds (positions that share the right half keep their
+// left-half difference with probability 2^-b + 2^-a instead of 2^-a) -- measurable for the narrow
+// domains of the exact test (n <= 256) and gone after two to four more rounds, so domains of
+// <= 10 / <= 14 / more bits get 8 / 6 / 4 rounds (tests/test_cbs_stats.py checks pair statistics).
 #pragma once
 #include "common.cuh"
 
@@ -26,8 +31,8 @@ __host__ __device__ __forceinline__ u32 mix32(u32 h) {
 }
 
 struct Prp {
-    u32 k[4];
-    int bits_a, bits_b;
+    u32 k[8];
+    int bits_a, bits_b, rounds;
     u32 n;
 
     __host__ __device__ __forceinline__ void init(u64 seed, u32 lo, u32 hi, u32 tid, u32 perm, u32 n_) {
@@ -39,10 +44,13 @@ struct Prp {
             philox_round(c, key);
         }
         k[0] = c[0]; k[1] = c[1]; k[2] = c[2]; k[3] = c[3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) k[4 + r] = mix32(k[r] + 0x9E3779B9u * (u32)(r + 1));
         int bits = 8;
         while (bits < 32 && (1ull << bits) < n_) ++bits;
         bits_a = bits / 2;
         bits_b = bits - bits / 2;
+        rounds = bits <= 10 ? 8 : (bits <= 14 ? 6 : 4);
         n = n_;
     }
 
@@ -55,6 +63,14 @@ struct Prp {
             t = (L ^ mix32(R ^ k[1])) & mb; L = R; R = t;
             t = (L ^ mix32(R ^ k[2])) & ma; L = R; R = t;
             t = (L ^ mix32(R ^ k[3])) & mb; L = R; R = t;
+            if (rounds > 4) {
+                t = (L ^ mix32(R ^ k[4])) & ma; L = R; R = t;
+                t = (L ^ mix32(R ^ k[5])) & mb; L = R; R = t;
+                if (rounds > 6) {
+                    t = (L ^ mix32(R ^ k[6])) & ma; L = R; R = t;
+                    t = (L ^ mix32(R ^ k[7])) & mb; L = R; R = t;
+                }
+            }
             v = (L << b) | R;
         } while (v >= n);
         return v;

@@ -46,9 +46,9 @@ struct Scratch {
         void* p = nullptr;
         size_t bytes = count * sizeof(T);
         if (bytes == 0) bytes = 16;
+        if (n >= 64) return cudaErrorMemoryAllocation;
         cudaError_t e = cudaMallocAsync(&p, bytes, stream);
         if (e != cudaSuccess) return e;
-        if (n >= 64) return cudaErrorMemoryAllocation;
         ptrs[n++] = p;
         *out = (T*)p;
         return cudaSuccess;

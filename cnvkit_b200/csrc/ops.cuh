@@ -52,7 +52,8 @@ int outlier_mask(const double* d_x, const long long* h_off, int n_arms, double q
 int round_sig(const double* d_x, long long n, int digits, double* d_out, unsigned long long* h_unhandled,
               cudaStream_t stream);
 int segment_bin_sums(const double* d_depth, const double* d_weight, const long long* d_lo, const long long* d_hi,
-                     int nseg, double* d_seg_weight, double* d_seg_depth, cudaStream_t stream);
+                     const long long* d_bin_end, const long long* d_seg_start, int nseg, double* d_seg_weight,
+                     double* d_seg_depth, cudaStream_t stream);
 
 // bootstrap.cu
 int bootstrap_ci(const double* d_values, const double* d_weights, const long long* h_lo, const long long* h_hi,
@@ -87,8 +88,11 @@ struct CbsStats {
 }  // namespace cnvk
 #include <vector>
 namespace cnvk {
+struct CbsDiag;   // cbs.cu: per-node diagnostics of one level (cnvk_cbs_node_diag)
 int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, const CbsParams& P,
-                std::vector<CbsSeg>& segs, CbsStats* stats, cudaStream_t stream);
+                std::vector<CbsSeg>& segs, CbsStats* stats, cudaStream_t stream, CbsDiag* diag = nullptr);
+int cbs_node_diag(const double* d_x, const double* d_w, const long long* h_off, int n_nodes, const CbsParams& P,
+                  double* out6, int* iout5, cudaStream_t stream);
 // haar.cu (segments reuse CbsSeg)
 int haar_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, double q,
                  std::vector<CbsSeg>& segs, cudaStream_t stream);

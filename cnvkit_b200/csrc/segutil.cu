@@ -235,13 +235,18 @@ int round_sig(const double* d_x, long long n, int digits, double* d_out, unsigne
 // over non-NaN weights, or 0 when the segment carries no weight
 __global__ void __launch_bounds__(128)
 segment_bin_sums_kernel(const double* __restrict__ depth, const double* __restrict__ weight,
-                        const long long* __restrict__ lo, const long long* __restrict__ hi, int nseg,
+                        const long long* __restrict__ lo, const long long* __restrict__ hi,
+                        const long long* __restrict__ bin_end, const long long* __restrict__ seg_start, int nseg,
                         double* __restrict__ seg_weight, double* __restrict__ seg_depth) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x * 4 + warp;
     if (s >= nseg) return;
     double sw = 0.0, sdw = 0.0;
+    // nested bins (intersect.py _irange_nested, mode "outer"): rows [lo, hi) whose end lies beyond the
+    // segment start; without the two optional columns every row of the range counts (_irange_simple)
+    const long long s0 = bin_end ? seg_start[s] : 0;
     for (long long k = lo[s] + lane; k < hi[s]; k += 32) {
+        if (bin_end && !(bin_end[k] > s0)) continue;
         const double w = weight ? weight[k] : 1.0;
         if (w == w) { sw += w; sdw += depth[k] * w; }
     }
@@ -254,10 +259,11 @@ segment_bin_sums_kernel(const double* __restrict__ depth, const double* __restri
 }
 
 int segment_bin_sums(const double* d_depth, const double* d_weight, const long long* d_lo, const long long* d_hi,
-                     int nseg, double* d_seg_weight, double* d_seg_depth, cudaStream_t stream) {
+                     const long long* d_bin_end, const long long* d_seg_start, int nseg, double* d_seg_weight,
+                     double* d_seg_depth, cudaStream_t stream) {
     if (nseg <= 0) return 0;
     ProfScope ps(PC_OTHER, stream);
-    segment_bin_sums_kernel<<<div_up(nseg, 4), 128, 0, stream>>>(d_depth, d_weight, d_lo, d_hi, nseg, d_seg_weight, d_seg_depth);
+    segment_bin_sums_kernel<<<div_up(nseg, 4), 128, 0, stream>>>(d_depth, d_weight, d_lo, d_hi, d_bin_end, d_seg_start, nseg, d_seg_weight, d_seg_depth);
     CNVK_LAUNCH_CHECK();
     return 0;
 }

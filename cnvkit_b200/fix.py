@@ -85,19 +85,21 @@ def load_adjust_coverages(cnarr, ref_cnarr, skip_low, fix_gc, fix_edge, fix_rmas
         return cnarr, ref_matched
     # genomic order is required for the per-chromosome runs (read_cna sorts; do it for API callers)
     chrom = cnarr.data["chromosome"].to_numpy()
+    kept_rows = np.flatnonzero(keep)            # rows of the uploaded (pre-filter) columns, in table order
     try:
         names, offsets, chrom_id = genome.chrom_runs(chrom)
     except ValueError:
         order = genome.genomic_order(chrom, cnarr.data["start"].to_numpy(), cnarr.data["end"].to_numpy())
         cnarr = cnarr.as_dataframe(cnarr.data.iloc[order])
         ref_matched = ref_matched.as_dataframe(ref_matched.data.iloc[order])
+        kept_rows = kept_rows[order]            # the device columns follow the same re-ordering
         chrom = cnarr.data["chromosome"].to_numpy()
         names, offsets, chrom_id = genome.chrom_runs(chrom)
     start = cnarr.data["start"].to_numpy(dtype=np.int64)
     end = cnarr.data["end"].to_numpy(dtype=np.int64)
     auto = genome.autosome_row_mask(chrom, start, end, diploid_parx_genome)
 
-    kidx = torch.from_numpy(np.flatnonzero(keep)).to(d_log2.device)
+    kidx = torch.from_numpy(np.ascontiguousarray(kept_rows)).to(d_log2.device)
     d_log2 = d_log2.index_select(0, kidx).contiguous()
     d_depth = _dev.up(cnarr.data["depth"].to_numpy(dtype=np.float64)) if "depth" in cnarr else None
     d_gc = dev_ref["gc"].index_select(0, kidx).contiguous() if (fix_gc and "gc" in dev_ref) else None

@@ -11,13 +11,13 @@ batch.py:411, ``segmentation.do_segmentation`` at commands.py:1290 and batch.py:
 ``smoothing.rolling_median`` at fix.py:417, ``segmetrics.do_segmetrics`` at batch.py:559 and
 commands.py's segmetrics command), so rebinding those attributes -- plus the public
 aliases commands.py:979/1128/1277 creates at import time -- is the whole integration.
-Options outside the GPU path (``method='hmm'``, ``bias_smoother='loess'``, ``do_cluster``,
-``variants``, ``smooth_cbs``) are forwarded to the original callables untouched.
+Options outside the GPU path (``method='hmm*'/'none'``, ``bias_smoother='loess'``, ``do_cluster``, ``variants`` with
+CBS) are forwarded to the original callables by explicit predicates on the arguments; nothing else falls
+back -- an in-scope call that fails raises.
 """
 from __future__ import annotations
 
 import importlib
-import logging
 import sys
 
 _saved = {}
@@ -34,13 +34,9 @@ def _route(ours, theirs, needs_reference):
     """Call ``ours`` unless the arguments ask for something only the reference implements."""
 
     def seam(*args, **kwargs):
-        if needs_reference(args, kwargs):
+        if needs_reference(args, kwargs):       # an OPTION the GPU path does not cover (explicit predicates below)
             return theirs(*args, **kwargs)
-        try:
-            return ours(*args, **kwargs)
-        except NotImplementedError as exc:   # an input shape the GPU path declines (it never guesses)
-            logging.info("cnvkit_b200: %s -- using cnvlib for this call", exc)
-            return theirs(*args, **kwargs)
+        return ours(*args, **kwargs)            # in-scope inputs never fall back: errors propagate
 
     seam.__name__ = getattr(theirs, "__name__", "seam")
     seam.__doc__ = getattr(ours, "__doc__", None)
@@ -91,12 +87,9 @@ def _segmetrics_seam(ours, theirs):
         kw = dict(zip(names, args))
         kw.update(kwargs)
         rest = [s for s in interval if s != "ci"]
-        try:
-            ci = ours(kw["cnarr"], kw["segarr"], interval_stats=["ci"], alpha=kw.get("alpha", 0.05),
-                      bootstraps=kw.get("bootstraps", 100), smoothed=kw.get("smoothed", 10),
-                      skip_low=kw.get("skip_low", False))
-        except NotImplementedError:
-            return theirs(*args, **kwargs)
+        ci = ours(kw["cnarr"], kw["segarr"], interval_stats=["ci"], alpha=kw.get("alpha", 0.05),
+                  bootstraps=kw.get("bootstraps", 100), smoothed=kw.get("smoothed", 10),
+                  skip_low=kw.get("skip_low", False))
         if not (kw.get("location_stats") or kw.get("spread_stats") or rest):
             return ci
         out = theirs(**dict(kw, interval_stats=rest))

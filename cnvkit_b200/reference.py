@@ -189,7 +189,8 @@ def compare_sex_chromosomes(cnarr, is_haploid_x_reference=False, diploid_parx_ge
             meds.append(np.nan)
             continue
         d_med, d_cnt = _dev.empty(1, torch.float64), _dev.empty(1, torch.int32)
-        _lib.call("cnvk_segmented_median_dev", _dev.ptr(d_x), _dev.ptr(_dev.up(mask.astype(np.uint8))), _dev.ptr(d_off), 1,
+        d_mask = _dev.up(mask.astype(np.uint8))      # bound to a name: must outlive the enqueued kernel
+        _lib.call("cnvk_segmented_median_dev", _dev.ptr(d_x), _dev.ptr(d_mask), _dev.ptr(d_off), 1,
                   _dev.ptr(d_med), _dev.ptr(d_cnt), _dev.stream())
         meds.append(float(d_med.cpu()[0]))
     auto_med, chrx_med, chry_med = meds

@@ -138,7 +138,10 @@ def do_segmentation(
     result.sort()
     result.sort_columns()
     if save_dataframe:
-        return result, _seg_text(result, cnarr.sample_id)
+        # the reference returns R's stdout per arm, i.e. the SEG rows BEFORE transfer_fields stretches the
+        # first / last segment of every arm (:180-188, :314-322); Haar has no R output (seg_out = "")
+        text = _seg_text(cnarr.sample_id, seg_chrom, seg_start, seg_end, probes, s_mean) if method == "cbs" else ""
+        return result, text
     return result
 
 
@@ -209,7 +212,7 @@ def _segment_cbs(f_log2, f_weight, f_arm, n_arms, threshold):
     if unhandled[0]:
         bad = (np.abs(f_log2) < 1e-16) | (np.abs(f_log2) > 1e21)
         xq[bad] = [float("%.6g" % v) for v in f_log2[bad]]
-    if f_weight is not None and np.isfinite(f_weight).any():
+    if f_weight is not None and (~np.isnan(f_weight)).any():
         d_w = _dev.up(f_weight)
         d_wq = _dev.empty(len(f_weight), torch.float64)
         _lib.call("cnvk_round_sig_dev", _dev.ptr(d_w), len(f_weight), 6, _dev.ptr(d_wq), _lib.ptr(unhandled),
@@ -218,6 +221,12 @@ def _segment_cbs(f_log2, f_weight, f_arm, n_arms, threshold):
         if unhandled[0]:
             bad = (np.abs(f_weight) < 1e-16) | (np.abs(f_weight) > 1e21)
             wq[bad] = [float("%.6g" % v) for v in f_weight[bad]]
+        # the R script runs per arm: an arm without a single non-NA weight gets weight 1.0 for every bin
+        # (cbs.py:22-28, `sum(!is.na(tbl$weight)) > 0` is evaluated on that arm's table)
+        has_w = np.bincount(f_arm, weights=(~np.isnan(wq)).astype(np.float64), minlength=n_arms) > 0
+        no_w = ~has_w[f_arm]
+        if no_w.any():
+            wq = np.where(no_w, 1.0, wq)
         ok = ~np.isnan(wq) & (wq > 0)       # cbs.py:22-24
     else:
         wq = np.ones(len(f_log2))           # cbs.py:25-28
@@ -274,25 +283,35 @@ def _transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, seg_log2, probes, a
     # bin row ranges per segment: intersect.py:323-346 _irange_simple, mode "outer", within the arm
     bin_lo = np.empty(nseg, dtype=np.int64)
     bin_hi = np.empty(nseg, dtype=np.int64)
+    nested = False
     for a in np.unique(seg_arm):
         lo, hi = int(arm_lo[a]), int(arm_hi[a])
         sel = np.flatnonzero(seg_arm == a)
         a_start, a_end = start[lo:hi], end[lo:hi]
+        bin_hi[sel] = lo + np.searchsorted(a_start, seg_end[sel], "left")
         if np.all(a_end[1:] >= a_end[:-1]):
             bin_lo[sel] = lo + np.searchsorted(a_end, seg_start[sel], "right")
-            bin_hi[sel] = lo + np.searchsorted(a_start, seg_end[sel], "left")
         else:
-            raise NotImplementedError("nested bins (non-monotonic end coordinates) are not supported")
+            # nested bins (`end` not ascending): _irange_nested keeps, of the rows before the first start >=
+            # seg_end, those whose end lies beyond seg_start -- a mask, evaluated on the device below
+            nested = True
+            bin_lo[sel] = lo
     bin_hi = np.maximum(bin_hi, bin_lo)
     dep = depth if depth is not None else np.exp2(log2)
     d_dep = dep if torch.is_tensor(dep) else _dev.up(dep)
     d_lo, d_hi = _dev.up(bin_lo), _dev.up(bin_hi)
     d_w = weight if (weight is None or torch.is_tensor(weight)) else _dev.up(weight)
     d_sw, d_sd = _dev.empty(nseg, torch.float64), _dev.empty(nseg, torch.float64)
-    _lib.call("cnvk_segment_bin_sums_dev", _dev.ptr(d_dep), _dev.ptr(d_w), _dev.ptr(d_lo), _dev.ptr(d_hi), nseg,
-              _dev.ptr(d_sw), _dev.ptr(d_sd), _dev.stream())
+    if nested:
+        d_bend, d_sstart = _dev.up(np.ascontiguousarray(end, dtype=np.int64)), _dev.up(seg_start.astype(np.int64))
+        _lib.call("cnvk_segment_bin_sums_masked_dev", _dev.ptr(d_dep), _dev.ptr(d_w), _dev.ptr(d_lo), _dev.ptr(d_hi),
+                  _dev.ptr(d_bend), _dev.ptr(d_sstart), nseg, _dev.ptr(d_sw), _dev.ptr(d_sd), _dev.stream())
+    else:
+        _lib.call("cnvk_segment_bin_sums_dev", _dev.ptr(d_dep), _dev.ptr(d_w), _dev.ptr(d_lo), _dev.ptr(d_hi), nseg,
+                  _dev.ptr(d_sw), _dev.ptr(d_sd), _dev.stream())
     seg_weight, seg_depth = d_sw.cpu().numpy(), d_sd.cpu().numpy()
-    genes = _join_genes(None if gene_codes is not None else data["gene"].to_numpy(), bin_lo, bin_hi, gene_codes)
+    genes = _join_genes(None if gene_codes is not None else data["gene"].to_numpy(), bin_lo, bin_hi, gene_codes,
+                        mask_end=end if nested else None, mask_start=seg_start if nested else None)
     return pd.DataFrame({
         "chromosome": seg_chrom, "start": seg_start, "end": seg_end, "gene": genes, "log2": seg_log2,
         "probes": probes, "weight": seg_weight, "depth": seg_depth,
@@ -321,17 +340,20 @@ def factorize_genes(bin_genes):
     return GeneCodes(bin_genes)
 
 
-def _join_genes(bin_genes, bin_lo, bin_hi, gene_codes=None):
+def _join_genes(bin_genes, bin_lo, bin_hi, gene_codes=None, mask_end=None, mask_start=None):
     """skgenome/combiners.py:58-94 join_strings per segment: ordered-unique gene names of the
     bins, split on ',', minus the ignored placeholder / antitarget names; '-' if none remain."""
     gc = gene_codes if gene_codes is not None else GeneCodes(bin_genes)
     codes = gc.codes
     out = []
-    for lo, hi in zip(bin_lo, bin_hi):
+    for k, (lo, hi) in enumerate(zip(bin_lo, bin_hi)):
         if hi <= lo:
             out.append("-")
             continue
-        u = pd.unique(codes[lo:hi])               # hash-based, keeps first-appearance order
+        rows = codes[lo:hi]
+        if mask_end is not None:                  # nested bins: only rows whose end lies beyond the segment start
+            rows = rows[np.asarray(mask_end[lo:hi]) > mask_start[k]]
+        u = pd.unique(rows)                       # hash-based, keeps first-appearance order
         if gc.simple:
             out.append(",".join(gc.names[u[gc.has_name[u]]].tolist()) or "-")
             continue
@@ -344,13 +366,16 @@ def _join_genes(bin_genes, bin_lo, bin_hi, gene_codes=None):
     return out
 
 
-def _seg_text(segarr, sample_id):
-    """SEG text in the shape DNAcopy's write.table prints (test/formats/warning.seg); the reference
-    returns R's stdout when save_dataframe=True."""
+def _seg_text(sample_id, chrom, start, end, probes, mean):
+    """SEG text as DNAcopy's write.table prints it arm by arm (test/formats/warning.seg; header once,
+    :180-188): loc.start is the first bin's start + 1 (the TSV handed to R is 1-based, :296), loc.end the last
+    bin's end, seg.mean the weighted mean at up to 15 significant digits; strings quoted, and a chromosome
+    column that read.delim parsed as integers printed bare."""
     lines = ['"ID"\t"chrom"\t"loc.start"\t"loc.end"\t"num.mark"\t"seg.mean"']
-    d = segarr.data
-    for c, s, e, p, m in zip(d["chromosome"], d["start"], d["end"], d["probes"], d["log2"]):
-        lines.append(f'"{sample_id}"\t"{c}"\t{int(s) + 1}\t{int(e)}\t{int(p)}\t{m:.15g}')
+    for c, s_, e, p, m in zip(chrom, start, end, probes, mean):
+        c = str(c)
+        cq = c if c.lstrip("-").isdigit() else f'"{c}"'
+        lines.append(f'"{sample_id}"\t{cq}\t{int(s_) + 1}\t{int(e)}\t{int(p)}\t{m:.15g}')
     return "\n".join(lines) + "\n"
 
 

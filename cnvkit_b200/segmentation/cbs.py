@@ -61,3 +61,22 @@ def segment_arms(log2, weight, arm_offsets, alpha=1e-4, prune=True, device_ptrs=
                   _lib.ptr(seg_mean), ctypes.addressof(nseg), ctypes.addressof(stats), int(stream))
     k = nseg.value
     return seg_arm[:k].copy(), seg_lo[:k].copy(), seg_hi[:k].copy(), seg_mean[:k].copy(), stats.as_dict()
+
+
+def node_diag(log2, weight, node_offsets, alpha=1e-4, **overrides):
+    """Decision-chain diagnostics of every interval tested once as a node, nothing decided early
+    (cnvk_cbs_node_diag): list of dicts with ``ostat1`` (sqrt T^2), ``ostat`` (0.99999 T^2), ``arc``, ``tailp`` /
+    ``delta`` (hybrid nodes), ``nrej`` (permutations, out of nperm, whose statistic reached ``ostat``),
+    ``flank_p`` (ternary-split p-values with the permutations forced), ``hybrid`` and ``flat``."""
+    off = _lib.i64(node_offsets)
+    n_nodes = len(off) - 1
+    x = _lib.f64(log2)
+    w = _lib.f64(weight)
+    params = make_params(alpha, **overrides)
+    out = np.zeros((n_nodes, 6), dtype=np.float64)
+    iout = np.zeros((n_nodes, 5), dtype=np.int32)
+    _lib.call("cnvk_cbs_node_diag", _lib.ptr(x), _lib.ptr(w), _lib.ptr(off), n_nodes, ctypes.addressof(params),
+              _lib.ptr(out), _lib.ptr(iout))
+    return [dict(ostat1=o[0], tailp=o[1], delta=o[2], ostat=o[3], flank_p=(o[4], o[5]), arc=(int(i[0]), int(i[1])),
+                 nrej=int(i[2]), hybrid=bool(i[3]), flat=bool(i[4]), nperm_run=int(params.nperm))
+            for o, i in zip(out, iout)]

@@ -163,9 +163,11 @@ def do_segmetrics(cnarr, segarr, location_stats=(), spread_stats=(), interval_st
     bins = cnarr.data
     keep = np.ones(len(bins), dtype=bool)
     if skip_low:    # CopyNumArray.drop_low_coverage (cnary.py:315-335)
-        keep &= ~(bins["log2"].to_numpy() < params.NULL_LOG2_COVERAGE - params.MIN_REF_COVERAGE)
+        l2 = bins["log2"].to_numpy(dtype=np.float64)
+        keep &= ~((l2 < params.NULL_LOG2_COVERAGE - params.MIN_REF_COVERAGE) | np.isnan(l2))
         if "depth" in bins.columns:
-            keep &= ~(bins["depth"].to_numpy() == 0)
+            dp = bins["depth"].to_numpy(dtype=np.float64)
+            keep &= ~((dp == 0) | np.isnan(dp))
         bins = bins[keep]
     lo, hi = segment_bin_ranges(bins, segarr.data)
     values = bins["log2"].to_numpy(dtype=np.float64)

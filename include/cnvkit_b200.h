@@ -181,6 +181,12 @@ int cnvk_round_sig_dev(const double* d_x, int64_t n, int32_t digits, double* d_o
 int cnvk_segment_bin_sums_dev(const double* d_depth, const double* d_weight, const int64_t* d_lo,
                               const int64_t* d_hi, int32_t nseg, double* d_seg_weight, double* d_seg_depth,
                               void* stream);
+/* The same for tables whose bins nest (`end` not ascending within a chromosome): skgenome/intersect.py
+ * _irange_nested, mode "outer" -- of the rows [d_lo, d_hi) only those with d_bin_end[row] > d_seg_start[seg]
+ * belong to the segment. */
+int cnvk_segment_bin_sums_masked_dev(const double* d_depth, const double* d_weight, const int64_t* d_lo,
+                                     const int64_t* d_hi, const int64_t* d_bin_end, const int64_t* d_seg_start,
+                                     int32_t nseg, double* d_seg_weight, double* d_seg_depth, void* stream);
 
 /* ---- circular binary segmentation ------------------------------------------------------ */
 /* Replaces the Rscript + DNAcopy::segment(cna, weights, alpha) subprocess of
@@ -218,6 +224,19 @@ int cnvk_cbs_segment(const double* log2, const double* weight, const int64_t* ar
                      int32_t n_arms, const cnvk_cbs_params* params, int64_t capacity, int32_t* seg_arm,
                      int64_t* seg_lo, int64_t* seg_hi, double* seg_mean, int64_t* n_segs,
                      cnvk_cbs_stats* stats);
+/* Diagnostics of the CBS decision chain (DNAcopy wfindcpt; call site
+ * cnvlib/segmentation/cbs.py:49-60): every interval [node_offsets[k], node_offsets[k+1]) is tested ONCE as a
+ * node, nothing is decided early -- all nperm permutations run (no sequential stopping) and both ternary-split
+ * flank tests run their permutations.  Host buffers.  Per node k:
+ *   out6[6k..]  = sqrt(T^2) observed, tailp (hybrid nodes, else -1), getmncwt delta (hybrid, else -1),
+ *                 0.99999 T^2 (what permutation statistics are compared with), flank p-values 1 and 2 (-1 when
+ *                 the maximal arc touches an end of the node)
+ *   iout5[5k..] = arc i, arc j (prefix points relative to the node), permutations whose statistic reached the
+ *                 observed one, 1 = hybrid (n > nmin) / 0 = exact, 1 = constant data (no test).
+ * This is what tests/test_cbs_stats_gpu.py compares with true-shuffle Monte-Carlo estimates (north_star:
+ * "permutation p-values agree within Monte Carlo standard error"). */
+int cnvk_cbs_node_diag(const double* log2, const double* weight, const int64_t* node_offsets,
+                       int32_t n_nodes, const cnvk_cbs_params* params, double* out6, int32_t* iout5);
 /* DNAcopy getbdry(eta, nperm, max.ones): sequential stopping boundary,
  * out[max_ones*(max_ones+1)/2]. Host-only. */
 int cnvk_cbs_getbdry(double eta, int32_t nperm, int32_t max_ones, int32_t* out);

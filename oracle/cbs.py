@@ -73,6 +73,13 @@ def lib():
         L.cbso_perm_pvalue_flank.restype = c_double
         L.cbso_perm_pvalue_flank.argtypes = [c_void_p, c_void_p, c_int, c_int, POINTER(Params), c_uint32, c_uint32,
                                              c_uint32]
+        L.cbso_prp_fill.restype = None
+        L.cbso_prp_fill.argtypes = [c_uint64, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32, c_void_p]
+        L.cbso_prp_at.restype = None
+        L.cbso_prp_at.argtypes = [c_uint64, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32, c_void_p,
+                                  c_uint32, c_void_p]
+        L.cbso_node_diag.restype = c_int
+        L.cbso_node_diag.argtypes = [c_void_p, c_void_p, c_int, c_int, POINTER(Params), c_int, c_void_p, c_void_p]
         _lib = L
     return _lib
 
@@ -95,6 +102,37 @@ def sbdry_for(params):
 def prp(seed, lo, hi, tid, perm, n):
     L = lib()
     return np.array([L.cbso_prp(seed, lo, hi, tid, perm, n, t) for t in range(n)], dtype=np.int64)
+
+
+def prp_fill(seed, lo, hi, tid, perm0, nperms, n):
+    """Permutations perm0..perm0+nperms-1 of the test (lo, hi, tid) as an int64 [nperms, n] matrix."""
+    out = np.zeros((nperms, n), dtype=np.uint32)
+    lib().cbso_prp_fill(seed, lo, hi, tid, perm0, nperms, n, out.ctypes.data)
+    return out.astype(np.int64)
+
+
+def prp_at(seed, lo, hi, tid, perm0, nperms, n, positions):
+    """Values of permutations perm0..perm0+nperms-1 at the given positions: int64 [nperms, len(positions)]."""
+    pos = np.ascontiguousarray(positions, dtype=np.uint32)
+    out = np.zeros((nperms, len(pos)), dtype=np.uint32)
+    lib().cbso_prp_at(seed, lo, hi, tid, perm0, nperms, n, pos.ctypes.data, len(pos), out.ctypes.data)
+    return out.astype(np.int64)
+
+
+def node_diag(x, w, lo, hi, params, nperm_run=None):
+    """One node without early stopping (statistical tests): dict with the observed sqrt(T^2) (`ostat1`), the
+    value permutations are compared with (`ostat`), the arc, `tailp` / `delta` (hybrid nodes), the number of
+    the first `nperm_run` permutations that reach `ostat` (`nrej`) and the two flank p-values with the
+    permutations forced (`flank_p`, -1 when the arc touches an end of the node)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    nrun = params.nperm if nperm_run is None else int(nperm_run)
+    out = np.zeros(6, dtype=np.float64)
+    iout = np.zeros(5, dtype=np.int32)
+    lib().cbso_node_diag(x.ctypes.data, w.ctypes.data, lo, hi, params, nrun, out.ctypes.data, iout.ctypes.data)
+    return dict(ostat1=out[0], tailp=out[1], delta=out[2], ostat=out[3], flank_p=(out[4], out[5]),
+                arc=(int(iout[0]), int(iout[1])), nrej=int(iout[2]), hybrid=bool(iout[3]), flat=bool(iout[4]),
+                nperm_run=nrun)
 
 
 def find_cpt(x, w, lo, hi, params, sbdry=None):

@@ -19,8 +19,8 @@
  *  (1) RNG.  R's Mersenne-Twister stream cannot be reproduced; the north star only asks that
  *      permutation p-values agree within Monte-Carlo error.  Permutations here are
  *      counter-based: permutation p of the test `tid` on node [lo,hi) is the bijection
- *      PRP(seed, lo, hi, tid, p) on [0,n) (Philox4x32-10 round keys driving a 4-round
- *      alternating Feistel network with cycle walking).  Results are therefore independent
+ *      PRP(seed, lo, hi, tid, p) on [0,n) (Philox4x32-10 round keys driving an alternating
+ *      Feistel network -- 8 / 6 / 4 rounds for domains of <= 10 / <= 14 / more bits -- with cycle walking).  Results are therefore independent
  *      of the order in which nodes are visited -- which is what lets the GPU process the
  *      recursion level-synchronously and still agree with this file exactly.
  *  (2) R computes sum()/cumsum() in 80-bit extended precision.  Here the three R-level totals
@@ -92,30 +92,39 @@ static inline uint32_t mix32(uint32_t h) {
     return h;
 }
 
-typedef struct { uint32_t k[4]; int bits_a, bits_b; uint32_t n; } prp_t;
+typedef struct { uint32_t k[8]; int bits_a, bits_b, rounds; uint32_t n; } prp_t;
+
+/* Round count by domain width: a balanced Feistel network over 2a bits is only pairwise-uniform up to
+ * O(2^-a) after 4 rounds (two positions that share the right half land on values whose left halves differ
+ * by their own left-half difference with probability 2^-b + 2^-a instead of 2^-a) -- measurable for the
+ * narrow domains of the exact test (n <= 256: a = b = 4) and gone after two to four more rounds
+ * (tests/test_cbs_stats.py: pair statistics of 4e5 permutations).  Wide domains keep 4 rounds. */
+static inline int prp_rounds(int bits) { return bits <= 10 ? 8 : (bits <= 14 ? 6 : 4); }
 
 static void prp_init(prp_t* P, uint64_t seed, uint32_t lo, uint32_t hi, uint32_t tid, uint32_t perm, uint32_t n) {
     const uint32_t ctr[4] = {perm, tid, lo, hi};
     const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     philox4x32_10(ctr, key, P->k);
+    for (int r = 0; r < 4; ++r) P->k[4 + r] = mix32(P->k[r] + 0x9E3779B9u * (uint32_t)(r + 1));
     int bits = 8;
     while (bits < 32 && (1ull << bits) < n) ++bits;
     P->bits_a = bits / 2;          /* left half  */
     P->bits_b = bits - bits / 2;   /* right half */
+    P->rounds = prp_rounds(bits);
     P->n = n;
 }
 
-/* 4-round alternating Feistel on bits_a+bits_b bits, cycle-walked into [0, n). */
+/* alternating Feistel on bits_a+bits_b bits (4, 6 or 8 rounds), cycle-walked into [0, n). */
 static inline uint32_t prp_eval(const prp_t* P, uint32_t v) {
     const int a = P->bits_a, b = P->bits_b;
     const uint32_t ma = (1u << a) - 1u, mb = (1u << b) - 1u;
     do {
         uint32_t L = v >> b, R = v & mb;           /* L: a bits, R: b bits */
-        /* round 0: (L:a, R:b) -> (R:b, L ^ F(R):a) */
-        uint32_t t = (L ^ mix32(R ^ P->k[0])) & ma; L = R; R = t;   /* L:b R:a */
-        t = (L ^ mix32(R ^ P->k[1])) & mb; L = R; R = t;            /* L:a R:b */
-        t = (L ^ mix32(R ^ P->k[2])) & ma; L = R; R = t;            /* L:b R:a */
-        t = (L ^ mix32(R ^ P->k[3])) & mb; L = R; R = t;            /* L:a R:b */
+        for (int r = 0; r < P->rounds; r += 2) {
+            /* (L:a, R:b) -> (R:b, L ^ F(R):a) -> (L:a, R:b) */
+            uint32_t t = (L ^ mix32(R ^ P->k[r])) & ma; L = R; R = t;
+            t = (L ^ mix32(R ^ P->k[r + 1])) & mb; L = R; R = t;
+        }
         v = (L << b) | R;
     } while (v >= P->n);
     return v;
@@ -125,6 +134,26 @@ uint32_t cbso_prp(uint64_t seed, uint32_t lo, uint32_t hi, uint32_t tid, uint32_
     prp_t P;
     prp_init(&P, seed, lo, hi, tid, perm, n);
     return prp_eval(&P, t);
+}
+
+/* permutations perm0 .. perm0+nperms-1 of the test (lo, hi, tid), row-major out[nperms][n] */
+void cbso_prp_fill(uint64_t seed, uint32_t lo, uint32_t hi, uint32_t tid, uint32_t perm0, uint32_t nperms,
+                   uint32_t n, uint32_t* out) {
+    for (uint32_t p = 0; p < nperms; ++p) {
+        prp_t P;
+        prp_init(&P, seed, lo, hi, tid, perm0 + p, n);
+        for (uint32_t t = 0; t < n; ++t) out[(size_t)p * n + t] = prp_eval(&P, t);
+    }
+}
+
+/* the same for selected positions only: out[nperms][npos] */
+void cbso_prp_at(uint64_t seed, uint32_t lo, uint32_t hi, uint32_t tid, uint32_t perm0, uint32_t nperms,
+                 uint32_t n, const uint32_t* pos, uint32_t npos, uint32_t* out) {
+    for (uint32_t p = 0; p < nperms; ++p) {
+        prp_t P;
+        prp_init(&P, seed, lo, hi, tid, perm0 + p, n);
+        for (uint32_t t = 0; t < npos; ++t) out[(size_t)p * npos + t] = prp_eval(&P, pos[t]);
+    }
 }
 
 /* ------------------------------------------------------------------ tail probability */
@@ -465,8 +494,8 @@ static double perm_stat_hybrid(const node_t* N, const double* wn, const double* 
 }
 
 /* ------------------------------------------------------------------ ternary-split flank test */
-static double wtpermp(const double* x, const double* w, const double* rw, int n1, int n2, const cbso_params* P,
-                      uint32_t lo, uint32_t hi, uint32_t tid, cbso_stats* st) {
+static double wtpermp_impl(const double* x, const double* w, const double* rw, int n1, int n2, const cbso_params* P,
+                           uint32_t lo, uint32_t hi, uint32_t tid, cbso_stats* st, int force) {
     const int n = n1 + n2;
     if (n1 == 1 || n2 == 1) return 1.0;
     double xsum1 = 0, xsum2 = 0, tss = 0, rn1 = 0, rn2 = 0;
@@ -482,7 +511,7 @@ static double wtpermp(const double* x, const double* w, const double* rw, int n1
     const double ostat = 0.99999 * odiff;
     double tstat = rn * rm1 * (odiff * odiff) / (rn - rm1);
     tstat = tstat / ((tss - tstat) / ((double)n - 2.0));
-    if (tstat > 25.0 && m1 >= 10) return 0.0;
+    if (tstat > 25.0 && m1 >= 10 && !force) return 0.0;
     if (st) st->tperm_tests++;
     double* y = (double*)malloc(sizeof(double) * n);
     for (int i = 0; i < n; ++i) y[i] = x[i] * rw[i];
@@ -498,16 +527,19 @@ static double wtpermp(const double* x, const double* w, const double* rw, int n1
     free(y);
     return (double)nrej / (double)P->nperm;
 }
+static double wtpermp(const double* x, const double* w, const double* rw, int n1, int n2, const cbso_params* P,
+                      uint32_t lo, uint32_t hi, uint32_t tid, cbso_stats* st) {
+    return wtpermp_impl(x, w, rw, n1, n2, P, lo, hi, tid, st, 0);
+}
+static double wtpermp_forced(const double* x, const double* w, const double* rw, int n1, int n2, const cbso_params* P,
+                             uint32_t lo, uint32_t hi, uint32_t tid) {
+    return wtpermp_impl(x, w, rw, n1, n2, P, lo, hi, tid, NULL, 1);
+}
 
 /* ------------------------------------------------------------------ wfindcpt */
-/* Tests the interval [lo,hi) of the arm; returns ncpt (0,1,2) and icpt relative to lo. */
-static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, const cbso_params* P,
-                    const int* sbdry, int icpt[2], cbso_stats* st, double* out_ostat1, double* out_delta) {
-    const int n = hi - lo;
-    const double* x = x_arm + lo;
-    const double* w = w_arm + lo;
-    if (out_ostat1) *out_ostat1 = 0.0;
-    if (st) st->nodes++;
+/* Node set-up shared by find_cpt and the diagnostic hook: centring, R-level totals, prefix sums.
+ * Returns 0 when the data are constant (changepoints(): no change point), else 1 with N allocated. */
+static int node_build(const double* x, const double* w, int n, node_t* Nout, double* rsw_out) {
     /* isTRUE(all.equal(diff(range(x)), 0)) -> no change point */
     double mn = x[0], mx = x[0];
     for (int i = 1; i < n; ++i) { if (x[i] < mn) mn = x[i]; if (x[i] > mx) mx = x[i]; }
@@ -522,7 +554,6 @@ static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, co
     const double sw = a_w.hi + a_w.lo, swx = a_wx.hi + a_wx.lo;
     const double avg = swx / sw;
     const double rsw = sqrt(sw);
-    double tss = 0.0;
     N.S[0] = 0.0;
     for (int i = 0; i < n; ++i) {
         N.w[i] = w[i];
@@ -535,9 +566,62 @@ static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, co
     blocked_prefix(N.w, n, N.cw);              /* cumsum(w) ... */
     for (int i = 0; i < n; ++i) N.cw[i] = N.cw[i] / rsw;   /* ... / sqrt(sum w) */
     blocked_prefix(N.t, n, N.S + 1);           /* partial sums S_1..S_n of xc*w */
-    tss = a_tss.hi + a_tss.lo;
-    N.tss = tss;
+    N.tss = a_tss.hi + a_tss.lo;
     N.total = N.cw[n - 1];
+    *Nout = N;
+    *rsw_out = rsw;
+    return 1;
+}
+
+/* DNAcopy getmncwt (weighted data): delta = lightest circular arc of kmax+1 consecutive probes as a
+ * fraction of the total weight (R's (kmax+1)/n is overwritten by it) */
+static double node_delta(const node_t* N, int kmax) {
+    const int n = N->n, jw = kmax + 1;
+    double delta = N->cw[jw - 1];
+    for (int i = 1; i <= n - jw; ++i) { const double a = N->cw[i + jw - 1] - N->cw[i - 1]; if (a < delta) delta = a; }
+    for (int i = 1; i <= jw; ++i) { const double a = N->total - N->cw[n - jw + i - 1] + N->cw[i - 1]; if (a < delta) delta = a; }
+    return delta / N->total;
+}
+
+/* permutation statistic T^2 of permutation `perm` of the node [lo,hi): hybrid (short circular arcs)
+ * or exact (all arcs) */
+static double node_perm_stat_buf(const node_t* N, double* t, const double* wn, const cbso_params* P, int hybrid,
+                                 int lo, int hi, int perm, cbso_stats* st) {
+    const int n = N->n, al0 = P->min_width;
+    prp_t prp;
+    prp_init(&prp, P->seed, (uint32_t)lo, (uint32_t)hi, 0u, (uint32_t)perm, (uint32_t)n);
+    for (int i = 0; i < n; ++i) t[i] = N->y[prp_eval(&prp, (uint32_t)i)] * N->rw[i];
+    double pbss;
+    if (hybrid) {
+        pbss = perm_stat_hybrid(N, wn, t, al0, P->kmax, st ? &st->perm_arcs : NULL);
+    } else {
+        double* Sp = (double*)malloc(sizeof(double) * (n + 1));
+        Sp[0] = 0.0;
+        for (int i = 0; i < n; ++i) Sp[i + 1] = Sp[i] + t[i];
+        int pi, pj;
+        pbss = max_arc_full(N, Sp, al0, &pi, &pj, st ? &st->perm_arcs : NULL);
+        free(Sp);
+    }
+    if (st) st->perms_run++;
+    return t2_of(pbss, N->tss, n);
+}
+static double node_perm_stat(node_t* N, const double* wn, const cbso_params* P, int hybrid, int lo, int hi, int perm,
+                             cbso_stats* st) {
+    return node_perm_stat_buf(N, N->t, wn, P, hybrid, lo, hi, perm, st);
+}
+
+/* Tests the interval [lo,hi) of the arm; returns ncpt (0,1,2) and icpt relative to lo. */
+static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, const cbso_params* P,
+                    const int* sbdry, int icpt[2], cbso_stats* st, double* out_ostat1, double* out_delta) {
+    const int n = hi - lo;
+    const double* x = x_arm + lo;
+    const double* w = w_arm + lo;
+    if (out_ostat1) *out_ostat1 = 0.0;
+    if (st) st->nodes++;
+    node_t N;
+    double rsw;
+    if (!node_build(x, w, n, &N, &rsw)) return 0;
+    const double tss = N.tss;
 
     int ncpt = 0, ai, aj;
     const int al0 = P->min_width;
@@ -558,13 +642,7 @@ static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, co
         int nrejc, nrej = 0, k;
         double* wn = NULL;
         if (hybrid) {
-            /* DNAcopy getmncwt (weighted data): delta = lightest circular arc of kmax+1 consecutive
-             * probes as a fraction of the total weight (R's (kmax+1)/n is overwritten by it) */
-            const int jw = P->kmax + 1;
-            double delta = N.cw[jw - 1];
-            for (int i = 1; i <= n - jw; ++i) { const double a = N.cw[i + jw - 1] - N.cw[i - 1]; if (a < delta) delta = a; }
-            for (int i = 1; i <= jw; ++i) { const double a = N.total - N.cw[n - jw + i - 1] + N.cw[i - 1]; if (a < delta) delta = a; }
-            delta = delta / N.total;
+            const double delta = node_delta(&N, P->kmax);
             if (out_delta) *out_delta = delta;
             const double pval1 = cbso_tailp(ostat1, delta, n, P->ngrid, P->tol);
             if (pval1 > P->alpha) goto done;
@@ -577,26 +655,43 @@ static int find_cpt(const double* x_arm, const double* w_arm, int lo, int hi, co
         k = nrejc * (nrejc + 1) / 2 + 1;
         if (st) st->perm_tests++;
         split = 1; /* surviving all permutations accepts the split */
-        for (int np = 1; np <= P->nperm; ++np) {
-            prp_t prp;
-            prp_init(&prp, P->seed, (uint32_t)lo, (uint32_t)hi, 0u, (uint32_t)(np - 1), (uint32_t)n);
-            for (int i = 0; i < n; ++i) N.t[i] = N.y[prp_eval(&prp, (uint32_t)i)] * N.rw[i];
-            double pbss;
-            if (hybrid) {
-                pbss = perm_stat_hybrid(&N, wn, N.t, al0, P->kmax, st ? &st->perm_arcs : NULL);
+        /* Permutations are counter-based, so a block of them can be scored in any order (in parallel for
+         * large nodes -- the CPU baseline's answer to a node that survives thousands of permutations) and
+         * DNAcopy's sequential stopping rule replayed over the block afterwards: same decisions, and
+         * perms_run counts the permutations up to the stopping point only. */
+        const int par = (long long)n * (hybrid ? 24 : n / 2) >= 200000;
+        int decided = 0;
+        for (int p0 = 0, blk = 16; p0 < P->nperm && !decided; p0 += blk, blk = blk < 1024 ? blk * 4 : blk) {
+            const int cnt = (P->nperm - p0 < blk) ? P->nperm - p0 : blk;
+            double* ps = (double*)malloc(sizeof(double) * (size_t)cnt);
+            long long arcs_blk = 0;
+            if (par && cnt > 1) {
+#pragma omp parallel
+                {
+                    double* tbuf = (double*)malloc(sizeof(double) * (size_t)n);
+                    cbso_stats lst;
+                    memset(&lst, 0, sizeof(lst));
+#pragma omp for schedule(dynamic, 4)
+                    for (int c = 0; c < cnt; ++c) ps[c] = node_perm_stat_buf(&N, tbuf, wn, P, hybrid, lo, hi, p0 + c, &lst);
+#pragma omp atomic
+                    arcs_blk += lst.perm_arcs;
+                    free(tbuf);
+                }
             } else {
-                double* Sp = (double*)malloc(sizeof(double) * (n + 1));
-                Sp[0] = 0.0;
-                for (int i = 0; i < n; ++i) Sp[i + 1] = Sp[i] + N.t[i];
-                int pi, pj;
-                pbss = max_arc_full(&N, Sp, al0, &pi, &pj, st ? &st->perm_arcs : NULL);
-                free(Sp);
+                cbso_stats lst;
+                memset(&lst, 0, sizeof(lst));
+                for (int c = 0; c < cnt; ++c) ps[c] = node_perm_stat_buf(&N, N.t, wn, P, hybrid, lo, hi, p0 + c, &lst);
+                arcs_blk = lst.perm_arcs;
             }
-            if (st) st->perms_run++;
-            const double pstat = t2_of(pbss, tss, n);
-            if (ostat <= pstat) { ++nrej; ++k; }
-            if (nrej > nrejc) { split = 0; break; }
-            if (np >= sbdry[k - 1]) { split = 1; break; }
+            int used = cnt;
+            for (int c = 0; c < cnt; ++c) {
+                const int np = p0 + c + 1;
+                if (ostat <= ps[c]) { ++nrej; ++k; }
+                if (nrej > nrejc) { split = 0; decided = 1; used = c + 1; break; }
+                if (np >= sbdry[k - 1]) { split = 1; decided = 1; used = c + 1; break; }
+            }
+            if (st) { st->perms_run += used; st->perm_arcs += arcs_blk / cnt * used; }
+            free(ps);
         }
         free(wn);
         if (!split) goto done;
@@ -665,7 +760,8 @@ int cbso_segment(const double* x, const double* w, const int64_t* arm_offsets, i
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
-#pragma omp parallel for schedule(dynamic, 1)
+    /* a single arm leaves the threads to the permutation blocks inside find_cpt */
+#pragma omp parallel for schedule(dynamic, 1) if (n_arms > 1)
     for (int a = 0; a < n_arms; ++a) {
         const int64_t lo = arm_offsets[a], hi = arm_offsets[a + 1];
         const int n = (int)(hi - lo);
@@ -683,6 +779,52 @@ int cbso_segment(const double* x, const double* w, const int64_t* arm_offsets, i
     }
     if (st_out) *st_out = total;
     free(sbdry);
+    return 0;
+}
+
+
+/* Diagnostic hook for the statistical tests (tests/test_cbs_stats*.py): ONE node, no early stopping.
+ * out[0] = sqrt(T^2) observed, out[1] = tailp (hybrid nodes; -1 otherwise), out[2] = getmncwt delta (hybrid),
+ * out[3] = 0.99999 T^2 (the value permutations are compared with), out[4], out[5] = flank p-values of the
+ * ternary split with the permutations forced (-1 when the arc touches an end of the node).
+ * iout[0..1] = arc (i, j), iout[2] = permutations whose statistic reached the observed one among the
+ * first nperm_run, iout[3] = 1 hybrid / 0 exact, iout[4] = 1 when the data are constant. */
+int cbso_node_diag(const double* x_arm, const double* w_arm, int lo, int hi, const cbso_params* P, int nperm_run,
+                   double* out, int* iout) {
+    const int n = hi - lo;
+    const double* x = x_arm + lo;
+    const double* w = w_arm + lo;
+    for (int k = 0; k < 6; ++k) out[k] = -1.0;
+    for (int k = 0; k < 5; ++k) iout[k] = 0;
+    node_t N;
+    double rsw;
+    if (!node_build(x, w, n, &N, &rsw)) { iout[4] = 1; return 0; }
+    int ai, aj;
+    const double bss = P->prune ? max_arc_pruned(&N, N.S, P->min_width, &ai, &aj, NULL)
+                                : max_arc_full(&N, N.S, P->min_width, &ai, &aj, NULL);
+    const double t2 = t2_of(bss, N.tss, n);
+    out[0] = sqrt(t2);
+    out[3] = t2 * 0.99999;
+    iout[0] = ai; iout[1] = aj;
+    const int hybrid = P->hybrid && (n > P->nmin);
+    iout[3] = hybrid;
+    double* wn = NULL;
+    if (hybrid) {
+        out[2] = node_delta(&N, P->kmax);
+        out[1] = cbso_tailp(out[0], out[2], n, P->ngrid, P->tol);
+        wn = (double*)malloc(sizeof(double) * n);
+        for (int i = 0; i < n; ++i) wn[i] = w[i] / rsw;
+    }
+    int nrej = 0;
+    for (int np = 0; np < nperm_run; ++np)
+        if (out[3] <= node_perm_stat(&N, wn, P, hybrid, lo, hi, np, NULL)) ++nrej;
+    iout[2] = nrej;
+    free(wn);
+    if (ai != 0 && aj != n) {
+        out[4] = wtpermp_forced(N.xc, N.w, N.rw, ai, aj - ai, P, (uint32_t)lo, (uint32_t)hi, 1u);
+        out[5] = wtpermp_forced(N.xc + ai, N.w + ai, N.rw + ai, aj - ai, n - aj, P, (uint32_t)lo, (uint32_t)hi, 2u);
+    }
+    node_free(&N);
     return 0;
 }
 

@@ -131,3 +131,18 @@ def test_center_by_precomputed_order_equals_center_by_window(F):
         np.testing.assert_array_equal(d_log2.cpu().numpy(), want)
         order = d_ord.cpu().numpy().view(np.uint32)
         assert sorted(order.tolist()) == list(range(n))
+
+
+def test_row_shuffled_sample_gives_the_sorted_result(F, golden):
+    """API callers may pass tables whose chromosomes are not contiguous runs: load_adjust_coverages re-orders
+    them genomically, and the device columns uploaded before that must follow the same order."""
+    g = golden("regression")
+    tgt, anti, ref = (golden_table(g, k) for k in ("sample_target", "sample_antitarget", "reference"))
+    want = F.do_fix(tgt, anti, ref)
+    rng = np.random.default_rng(3)
+    shuf = tgt.as_dataframe(tgt.data.iloc[rng.permutation(len(tgt))].reset_index(drop=True))
+    got = F.do_fix(shuf, anti, ref)
+    for c in ("chromosome", "start", "end"):
+        assert got.data[c].tolist() == want.data[c].tolist()
+    np.testing.assert_array_equal(got.data["log2"].to_numpy(), want.data["log2"].to_numpy())
+    np.testing.assert_allclose(got.data["weight"].to_numpy(), want.data["weight"].to_numpy(), rtol=1e-12)

@@ -142,6 +142,22 @@ def test_api_behaviour(S, golden):
     assert S.do_segmentation(empty, "cbs") is empty           # test_segmentation.py:188-212
     out, text = S.do_segmentation(cnr[:300], "cbs", save_dataframe=True, processes=2)
     assert len(out) > 0 and text.startswith('"ID"\t"chrom"') and text.count("\n") == len(out) + 1
+    # the SEG text is R's per-arm stdout, i.e. the rows BEFORE transfer_fields stretches arm ends
+    # (cnvlib/segmentation/__init__.py:180-188): 1-based first-bin start, last-bin end, filtered bin counts
+    rows = [ln.split("\t") for ln in text.strip().split("\n")[1:]]
+    assert [int(r[4]) for r in rows] == out.data["probes"].tolist()
+    sub = cnr[:300].data
+    starts1 = set((sub["start"] + 1).tolist())
+    assert all(int(r[2]) in starts1 for r in rows) and all(int(r[3]) in set(sub["end"].tolist()) for r in rows)
+    assert all(r[0] == f'"{cnr.sample_id}"' for r in rows)
+    assert S.do_segmentation(cnr[:300], "haar", save_dataframe=True)[1] == ""
+    # an arm whose weights are all NaN is segmented with weight 1.0 (the R script runs per arm, cbs.py:22-28);
+    # the other arms keep their weights and the arm does not vanish
+    part = cnr[:3000].copy()
+    first_chrom = part.data["chromosome"].iat[0]
+    part.data.loc[part.data["chromosome"] == first_chrom, "weight"] = np.nan
+    got = S.do_segmentation(part, "cbs")
+    assert first_chrom in set(got.data["chromosome"])
     # NaN / inf log2 bins are dropped before segmentation (test_segmentation.py:741-806)
     bad = cnr[:2000].copy()
     bad.data.loc[bad.data.index[5], "log2"] = np.nan

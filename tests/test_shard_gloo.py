@@ -64,6 +64,22 @@ def _worker(rank, world, port, out_path):
                                     [np.arange(3, dtype=np.int64), np.ones(3)], dst=0)
         capped = shard.gather_tables([np.arange(rank + 2, dtype=np.int64), np.full(rank + 2, 0.5 + rank)], dst=0,
                                      capacity=8)
+        # batched gather: several small tables appended per rank, ONE collective per flush, reusable
+        tg = shard.TableGatherer(ncols=3, capacity=16)
+        for rnd in range(2):
+            for step in range(2 + rank):
+                k = step + 1
+                tg.append([np.full(k, rank, dtype=np.int64), np.arange(k) + 10 * step, np.full(k, 0.25 * rnd)])
+            tab = tg.flush(dst=0)
+            if rank == 0:
+                assert tab.shape == (3 + 6, 3)
+                assert tab[:, 0].tolist() == [0, 0, 0, 1, 1, 1, 1, 1, 1]
+                assert tab[:, 1].tolist() == [0, 10, 11, 0, 10, 11, 20, 21, 22]
+                assert (tab[:, 2] == 0.25 * rnd).all()
+            else:
+                assert tab is None
+        with pytest.raises(ValueError):
+            tg.append([np.zeros(17), np.zeros(17), np.zeros(17)])
         if rank == 0:
             assert capped[0].tolist() == [0, 1, 0, 1, 2] and capped[1].tolist() == [0.5, 0.5, 1.5, 1.5, 1.5]
         else:

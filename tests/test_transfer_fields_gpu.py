@@ -141,3 +141,23 @@ def test_filtered_bins_gapped_index(S):
     res = S.transfer_fields(seg, kept)
     assert res["gene"].tolist() == ["CCC", "DDD"]
     assert res["depth"].tolist() == [300.0, 400.0] and res["weight"].tolist() == [3.0, 4.0]
+
+
+def test_nested_bins_use_the_mask_of_irange_nested(S):
+    """skgenome/intersect.py _irange_nested, mode 'outer': with a bin nested inside a longer one (`end` not
+    ascending) a segment takes the rows before the first start >= its end whose end lies beyond its start --
+    a mask, not a run of rows.  Checked against a direct numpy statement of that rule."""
+    start = np.array([0, 100, 150, 400, 600, 900])
+    end = np.array([1000, 200, 500, 700, 800, 1200])          # bin 0 spans bins 1-4: nested
+    w = np.array([1.0, 2.0, 4.0, 8.0, 16.0, 32.0])
+    d = np.array([10.0, 20.0, 30.0, 40.0, 50.0, 60.0])
+    cnarr = CNA({"chromosome": ["chr1"] * 6, "start": start, "end": end, "gene": list("ABCDEF"), "log2": np.zeros(6),
+                 "depth": d, "weight": w})
+    seg = CNA({"chromosome": ["chr1"] * 2, "start": [0, 550], "end": [550, 1200], "gene": ["-"] * 2,
+               "log2": [0.0, 0.1], "probes": [3, 3], "weight": [0.0, 0.0]})
+    res = S.transfer_fields(seg, cnarr)
+    for k, (s0, s1) in enumerate([(0, 550), (550, 1200)]):
+        mask = (end > s0) & (np.arange(6) < np.searchsorted(start, s1))
+        assert res["weight"].iat[k] == w[mask].sum()
+        assert res["depth"].iat[k] == pytest.approx((d[mask] * w[mask]).sum() / w[mask].sum(), rel=1e-12)
+        assert res["gene"].iat[k] == ",".join(np.array(list("ABCDEF"))[mask])
