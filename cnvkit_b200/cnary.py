@@ -155,20 +155,29 @@ def arm_ranges(df: pd.DataFrame, min_gap_size=1e5, min_arm_bins=50):
     """(chromosome, lo, hi) row ranges of GenomicArray.by_arm (skgenome/gary.py:309-355): per
     chromosome, the largest inter-bin gap inside the middle 80 % (margin >= min_arm_bins) is the
     centromere if it is at least min_gap_size wide.  Rows of a chromosome must be contiguous."""
-    names, offsets, _ = genome.chrom_runs(df["chromosome"].to_numpy())
-    start = df["start"].to_numpy()
-    end = df["end"].to_numpy()
+    names, offsets, _ = genome.chrom_runs(df["chromosome"])
+    return arm_ranges_from_runs(names, offsets, df["start"].to_numpy(), df["end"].to_numpy(), min_gap_size,
+                                min_arm_bins)
+
+
+def arm_cut(start, end, lo, hi, min_gap_size=1e5, min_arm_bins=50):
+    """Row offset (relative to lo) of the centromere split of the chromosome run [lo, hi), 0 = no split
+    (skgenome/gary.py:309-355)."""
+    n = hi - lo
+    margin = max(min_arm_bins, round(0.1 * n))
+    if n > 2 * margin + 1:
+        gaps = start[lo + margin + 1 : hi - margin] - end[lo + margin : hi - margin - 1]
+        k = int(np.argmax(gaps))
+        if gaps[k] >= min_gap_size:
+            return k + margin + 1
+    return 0
+
+
+def arm_ranges_from_runs(names, offsets, start, end, min_gap_size=1e5, min_arm_bins=50):
     out = []
     for c, name in enumerate(names):
         lo, hi = int(offsets[c]), int(offsets[c + 1])
-        n = hi - lo
-        margin = max(min_arm_bins, round(0.1 * n))
-        cut = 0
-        if n > 2 * margin + 1:
-            gaps = start[lo + margin + 1 : hi - margin] - end[lo + margin : hi - margin - 1]
-            k = int(np.argmax(gaps))
-            if gaps[k] >= min_gap_size:
-                cut = k + margin + 1
+        cut = arm_cut(start, end, lo, hi, min_gap_size, min_arm_bins)
         if cut:
             out.append((name, lo, lo + cut))
             out.append((name, lo + cut, hi))

@@ -2,53 +2,63 @@
 // subprocess of cnvlib/segmentation/__init__.py:292-322 (R script cnvlib/segmentation/cbs.py:1-78,
 // i.e. DNAcopy::segment(CNA(log2,...), weights=w, alpha=threshold) with DNAcopy defaults).
 //
-// Structure (level-synchronous over ALL arms of ALL samples in the batch):
-//   prep   : one CTA (1024 threads) per open interval ("node"): sum w, sum x*w, sum w*xc^2 as
-//            double-double reductions (R-level sum() calls), weighted centring, and the prefix sums
-//            S_i = sum w xc, cw_i = cumsum(w)/sqrt(sum w) as a blocked FP64 scan with one fixed
-//            association (thread-sequential x8, Kogge-Stone per warp, warp totals and tile carry
-//            left to right) that the CPU oracle replays bit for bit; per-256-point block min/max
-//            (+ arg) of S for pruning, getmncwt's delta.
-//   seed   : every pair of 256-point blocks proposes the arcs between its extreme prefix points.
-//   band   : arcs whose end points lie in the same or adjacent 256-point blocks, pruned on 32x32
-//            sub-blocks out of shared memory (they cannot be pruned at 256-point granularity).
-//   bound  : upper bound (block min/max of S, extreme c) of every remaining 256x256 sub-tile
-//            against the node's running best; survivors go to a device-wide tile queue -- the
-//            GPU form of DNAcopy's block-pruned wtmaxo.
-//   scan   : persistent CTAs pop 1024x256 tiles; every thread keeps 4 arc starts in registers and
-//            streams 256 arc ends from shared memory; BSS_ij = (S_j-S_i)^2 / (c (W-c)),
-//            c = cw_j-cw_i, is compared division-free against the running best (exact IEEE
-//            division only on the rare update).  Warp-shuffle argmax, then one lock-protected
-//            update of the node's (q,i,j), ties -> smallest (i,j).
-//   decide : one warp per node: T^2, the 0.1 / 7.0 shortcuts, Siegmund tail approximation
-//            (hybrid, n > nmin), and the number of exceedances tolerated.
-//   perms  : reference distribution for undecided nodes, evaluated in SM-resident tiles with
-//            counter-based permutations (cbs_rng.cuh): hybrid = circular arcs of width <= kmax
-//            (n > nmin), each arc dropped after add + multiply + compare against a per-node, per-width
-//            limit (the weights are not permuted, so the smallest denominator is a constant of the
-//            node); exact = all arcs (n <= nmin); DNAcopy's sequential stopping boundary is replayed
-//            on the exceedance flags chunk by chunk.
-//   flank  : ternary-split confirmation (wtpermp) for arcs interior to the node.
-// Host code only moves a few bytes of per-node decisions per level and builds the next frontier.
+// The recursion is level-synchronous over ALL arms of ALL samples in the batch and DEVICE-RESIDENT:
+// the frontier of open intervals ("nodes"), every decision, the permutation stopping rule, the
+// ternary-split flank tests and the next frontier live in HBM; the host enqueues one fixed sequence of
+// kernels per level and reads back one small record (the next level's sizes + the segments that
+// became final) -- ONE synchronisation per recursion level.
+//
+// Per level:
+//   maps    : tile / block -> node lookup tables of the level (so no kernel binary-searches the node list)
+//   prep    : sums   (tile)  min / max of x, double-double partials of sum w, sum x*w; the node's LAST tile
+//                            folds them into avg, sqrt(sum w) and the constant-data flag
+//             scan   (tile)  weighted centring, tile-local blocked FP64 prefix scan with one fixed
+//                            association (replayed bit for bit by oracle/cbs_oracle.c), carries from the
+//                            preceding tiles by a chained look-back (tile k waits for tiles < k only),
+//                            final S and cw, per-256-point block extrema, lightest al0-window per block,
+//                            getmncwt partials; the node's LAST tile computes tss, total, delta and the
+//                            seed arc.  Reads x, w once more and writes S, cw: 48 B/bin with the sums pass.
+//   seed    : every pair of 256-point blocks proposes the arcs between its extreme prefix points; the
+//             node's last CTA folds the candidates (no lock, no atomics on doubles).
+//   band    : arcs whose end points lie in the same or adjacent 256-point blocks.  One CTA per start
+//             block: CTA-level bound test from the block extrema first (no staging when the whole strip
+//             cannot reach the running best), else the 512-point strip is staged with one TMA bulk copy
+//             per array (cp.async.bulk + mbarrier) and pruned on 32x32 sub-blocks.
+//   bound   : upper bound of every remaining 1024x256 tile against the running best -> device tile queue.
+//   scan    : persistent CTAs pop tiles; 4 arc starts per thread in registers, 256 arc ends from shared
+//             memory, division-free comparison, exact division only on update.
+//   decide  : T^2, the 0.1 / 7.0 shortcuts, closed-form bracket of DNAcopy's tailp, the nu-series only when
+//             the bracket straddles alpha, nrejc; lists of nodes for the permutation tests.
+//   perms   : ONE cooperative persistent kernel per method (hybrid / exact): materialises the exchangeable
+//             terms of the listed nodes, pruning limits, then chunks of 64 -> 2048 counter-based permutations
+//             with DNAcopy's sequential stopping boundary replayed ON THE DEVICE between chunks.
+//   flank   : ternary-split confirmation (wtpermp) for arcs interior to the node.
+//   frontier: children of every split node -> next level's node table; intervals that became final ->
+//             segment records (+ weighted means) in the level's read-back record.
 #include <algorithm>
 #include <cmath>
 #include <vector>
+
+#include <cooperative_groups.h>
 
 #include "cbs_rng.cuh"
 #include "ops.cuh"
 #include "prof.cuh"
 
 namespace cnvk {
+namespace cg = cooperative_groups;
 
 static const int CBS_BLK = 256;           // points per bound block / j-block
 static const int CBS_IW = 4;              // arc starts per thread
 static const int CBS_IBLK = CBS_BLK * CBS_IW;
-static const size_t PREP_SMEM = (size_t)2 * (2048 + 256) * sizeof(double);   // two padded 2048-term tiles
-static const int HYB_TP = 2048;           // arc starts per CTA in the hybrid permutation kernel
+static const int HYB_TP = 2048;           // arc starts per tile in the hybrid permutation kernel
 static const int HYB_KMAX = 64;           // max supported kmax
 static const int EXACT_NMAX = 256;        // max supported nmin
+static const int HYB_LIM = HYB_KMAX + 1;
+static const int PERM_CHUNK_MAX = 2048;   // permutations per chunk (upper end of the 64 -> 2048 schedule)
+static const int SEG_WINDOW = 1024;       // final segments read back with the level record in one copy
 
-enum { ST_FINAL = 0, ST_SPLIT = 1, ST_PERM_HYBRID = 2, ST_PERM_EXACT = 3 };
+enum { ST_FINAL = 0, ST_SPLIT = 1, ST_PERM_HYBRID = 2, ST_PERM_EXACT = 3, ST_NEED_TAILP = 4 };
 
 struct Node {
     int lo, hi, base, flat;
@@ -59,26 +69,72 @@ struct Node {
     double ostat, ostat1;
     double delta;  // getmncwt: lightest circular arc of kmax+1 probes / total weight (n > nmin only)
     double tailp;  // DNAcopy tailp of the node when the series was summed, else -1 (diagnostics)
+    int ptile_off, iblk_off;              // first 2048-point prefix tile / first 1024-point start block
+    int done_sums, done_scan, done_seed;  // "last CTA of the node" counters
+    int nrej, kk;                         // permutation test state (exceedances, boundary index)
+    int flank;                            // index of the node's first flank test, or -1
 };
 
 struct CbsDiag {
-    std::vector<Node> nodes;       // after the decision kernels of the (single) level
-    std::vector<int> nrej;         // permutations whose statistic reached the observed one, per node
+    std::vector<Node> nodes;       // after the (single) level
     std::vector<double> flank_p;   // [node][2] flank p-values with the permutations forced, -1 = no test
-};
-
-struct Decision {
-    int state, nrejc, best_i, best_j;
-    double ostat;
 };
 
 struct FlankTest {
     int node, off, n1, n2, tid, m1, s0, need_perm;
     double rm1, xbar, ostat, pvalue;
+    int nrej, pad;
+};
+
+// level control block (device); the host reads it back once per level together with the new segments
+struct Ctl {
+    // next level (written by the frontier kernel)
+    int nn_next, ptiles_next, nblk_next, niblk_next;
+    long long qtiles_next;
+    int overflow;                  // bit 0: next level exceeds the node capacity, bit 1: segment capacity
+    int nseg_new;                  // intervals that became final at this level
+    // lists of this level
+    int n_need, n_hyb, n_exact, n_flank, n_fperm, n_act;
+    int qcount, qpop;              // tile queue of the arc scan
+    int pad0;
+    long long bins_next;           // bins of the next level's nodes (prep work counter)
+    unsigned long long stats[8];   // [0] sub-tiles scanned [1] tested [2] band pairs [3] perm nodes [4] perms run
+                                   // [5] perm arcs [6] flank perm tests
+};
+
+struct LevelOut {                  // one device->host copy per level
+    Ctl ctl;
+    int seg_lo[SEG_WINDOW], seg_hi[SEG_WINDOW];
+    double seg_mean[SEG_WINDOW];
 };
 
 __device__ __forceinline__ double pt(const double* a, int lo, int i) {
     return i ? a[lo + i - 1] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------ TMA bulk copy
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (TMA, UBLKCP in SASS): 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 // ------------------------------------------------------------------------------------ prep
@@ -99,17 +155,14 @@ __device__ __forceinline__ double pt(const double* a, int lo, int i) {
 //       out    = C[k] + local
 //     It differs from a plain left-to-right sum by rounding only (its error growth is smaller).
 // A node is cut into tiles of 2048 prefix POINTS (point i = S_i, i = 0..n; point i > 0 is term i-1)
-// and every tile is one CTA, so the largest arm no longer sits on a single SM:
-//   sums   (tile)  : min / max of x, double-double partials of sum w and sum x*w
-//   scan   (tile)  : node totals from the partials -> avg; centred data, tile-local prefix scan, tile
-//                    totals, double-double partial of sum w*xc^2
-//   finish (tile)  : carry C[k] from the tile totals, final S and cw, per-256-point block min / max
-//                    (+ arg, + cw at the arg), partial minimum for getmncwt
-//   node   (node)  : tss, total, delta, reset of the running best
+// and every tile is one CTA.
 static const int PREP_THREADS = 256;
 static const int PREP_E = 8;                            // terms per thread
 static const int PREP_TILE = PREP_THREADS * PREP_E;     // 2048 terms / points per tile
 static const int PREP_HALO = HYB_KMAX + 2;              // getmncwt looks kmax+1 points ahead
+static const int PREP_PADDED = PREP_TILE + PREP_TILE / 8;
+// dynamic shared memory of the scan kernel: two padded tiles + final S points + final cw points and halo
+static const size_t PREP_SMEM = (size_t)(2 * PREP_PADDED + PREP_TILE + PREP_TILE + PREP_HALO + 2) * sizeof(double);
 __host__ __device__ __forceinline__ int prep_pad(int k) { return k + (k >> 3); }  // bank-conflict padding
 
 // double-double accumulator: hi + lo carries the running sum to ~2^-104 relative
@@ -155,27 +208,34 @@ struct TileSums {      // per tile, written by the sums kernel
     double mn, mx, sw_hi, sw_lo, swx_hi, swx_lo;
 };
 struct TileScan {      // per tile, written by the scan kernel
-    double Tw, Ts, tss_hi, tss_lo, dmin, pad;
+    double Tw, Ts, tss_hi, tss_lo, dmin;
+    int flag, pad;     // flag == level epoch: Tw / Ts of this level are published
 };
 
-// tile -> (node, tile index inside the node); ptile_off[a] = first tile of node a
-__device__ __forceinline__ void decode_ptile(const int* __restrict__ ptile_off, int nnodes, int tile, int& a, int& k) {
-    int lo_ = 0, hi_ = nnodes;
-    while (hi_ - lo_ > 1) {
-        const int m = (lo_ + hi_) >> 1;
-        if (ptile_off[m] <= tile) lo_ = m; else hi_ = m;
-    }
-    a = lo_;
-    k = tile - ptile_off[a];
+// one warp per node: tile -> node, 256-block -> node, 1024-start-block -> node tables of the level
+__global__ void __launch_bounds__(128)
+cbs_maps_kernel(const Node* __restrict__ nodes, int nnodes, int* __restrict__ ptile_node, int* __restrict__ blk_node,
+                int* __restrict__ iblk_node) {
+    const int a = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (a >= nnodes) return;
+    const Node nd = nodes[a];
+    const int P = nd.hi - nd.lo + 1;
+    const int nt = (P + PREP_TILE - 1) / PREP_TILE, nb = (P + CBS_BLK - 1) / CBS_BLK, ni = (P + CBS_IBLK - 1) / CBS_IBLK;
+    for (int k = lane; k < nt; k += 32) ptile_node[nd.ptile_off + k] = a;
+    for (int k = lane; k < nb; k += 32) blk_node[nd.blk_off + k] = a;
+    for (int k = lane; k < ni; k += 32) iblk_node[nd.iblk_off + k] = a;
 }
 
 __global__ void __launch_bounds__(PREP_THREADS)
-cbs_prep_sums_kernel(const Node* __restrict__ nodes, const int* __restrict__ ptile_off, int nnodes,
-                     const double* __restrict__ x, const double* __restrict__ w, TileSums* __restrict__ part) {
+cbs_prep_sums_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_node, const double* __restrict__ x,
+                     const double* __restrict__ w, TileSums* __restrict__ part) {
     __shared__ double s_a[32], s_b[32];
-    int a, k;
-    decode_ptile(ptile_off, nnodes, blockIdx.x, a, k);
-    const int lo = nodes[a].lo, n = nodes[a].hi - nodes[a].lo;
+    __shared__ int s_last;
+    const int a = ptile_node[blockIdx.x];
+    Node* nd = &nodes[a];
+    const int lo = nd->lo, n = nd->hi - nd->lo, first = nd->ptile_off;
+    const int k = blockIdx.x - first;
+    const int ntiles = (n + 1 + PREP_TILE - 1) / PREP_TILE;
     const int t0 = k * PREP_TILE, m = max(0, min(PREP_TILE, n - t0));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double mn = INFINITY, mx = -INFINITY;
@@ -203,57 +263,130 @@ cbs_prep_sums_kernel(const Node* __restrict__ nodes, const int* __restrict__ pti
         TileSums o;
         o.mn = mn; o.mx = mx; o.sw_hi = sw.hi; o.sw_lo = sw.lo; o.swx_hi = swx.hi; o.swx_lo = swx.lo;
         part[blockIdx.x] = o;
-    }
-}
-
-// node totals from the tile partials, in tile order (every CTA of the node computes the same values)
-__device__ __forceinline__ void node_totals(const TileSums* __restrict__ part, int ntiles, double& range,
-                                            double& sw, double& swx) {
-    double mn = INFINITY, mx = -INFINITY;
-    DD a = {0.0, 0.0}, b = {0.0, 0.0};
-    for (int t = 0; t < ntiles; ++t) {
-        const TileSums p = part[t];
-        mn = fmin(mn, p.mn);
-        mx = fmax(mx, p.mx);
-        if (t == 0) { a.hi = p.sw_hi; a.lo = p.sw_lo; b.hi = p.swx_hi; b.lo = p.swx_lo; }
-        else { dd_merge(a, p.sw_hi, p.sw_lo); dd_merge(b, p.swx_hi, p.swx_lo); }
-    }
-    range = mx - mn;
-    sw = __dadd_rn(a.hi, a.lo);
-    swx = __dadd_rn(b.hi, b.lo);
-}
-
-__global__ void __launch_bounds__(PREP_THREADS, 4)
-cbs_prep_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_off, int nnodes,
-                     const double* __restrict__ x, const double* __restrict__ w, const TileSums* __restrict__ part1,
-                     double* __restrict__ xc, double* __restrict__ y, double* __restrict__ wn,
-                     double* __restrict__ Sl, double* __restrict__ cwl, TileScan* __restrict__ part3) {
-    extern __shared__ __align__(16) double s_dyn[];      // [2 arrays][padded tile]
-    __shared__ double s_a[32], s_b[32];
-    __shared__ double s_scalar[4];
-    __shared__ double s_wtot[2][PREP_THREADS / 32];
-    int a, k;
-    decode_ptile(ptile_off, nnodes, blockIdx.x, a, k);
-    const int lo = nodes[a].lo, n = nodes[a].hi - nodes[a].lo;
-    const int ntiles = ptile_off[a + 1] - ptile_off[a];
-    const int t0 = k * PREP_TILE, m = max(0, min(PREP_TILE, n - t0));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* s_w = s_dyn;
-    double* s_s = s_dyn + (PREP_TILE + PREP_TILE / 8);
-    if (tid == 0) {
-        double range, sw, swx;
-        node_totals(part1 + ptile_off[a], ntiles, range, sw, swx);
-        s_scalar[0] = range; s_scalar[1] = sw; s_scalar[2] = swx;
+        __threadfence();
+        s_last = (atomicAdd(&nd->done_sums, 1) == ntiles - 1);
     }
     __syncthreads();
-    // range check: isTRUE(all.equal(diff(range(x)), 0)) -> final (changepoints R code)
-    if (s_scalar[0] <= 1.4901161193847656e-08) {
-        if (tid == 0 && k == 0) { nodes[a].flat = 1; nodes[a].best_q = -1.0; }
-        return;
+    if (!s_last || tid != 0) return;
+    // the node's last tile: totals from the tile partials, in tile order (order-independent anyway)
+    __threadfence();
+    double gmn = INFINITY, gmx = -INFINITY;
+    DD A = {0.0, 0.0}, B = {0.0, 0.0};
+    const volatile TileSums* ps = part + first;
+    for (int t = 0; t < ntiles; ++t) {
+        gmn = fmin(gmn, ps[t].mn);
+        gmx = fmax(gmx, ps[t].mx);
+        if (t == 0) { A.hi = ps[0].sw_hi; A.lo = ps[0].sw_lo; B.hi = ps[0].swx_hi; B.lo = ps[0].swx_lo; }
+        else { dd_merge(A, ps[t].sw_hi, ps[t].sw_lo); dd_merge(B, ps[t].swx_hi, ps[t].swx_lo); }
     }
-    const double sw = s_scalar[1], swx = s_scalar[2];
-    const double avg = __ddiv_rn(swx, sw), rsw = sqrt(sw);
-    if (tid == 0 && k == 0) { nodes[a].flat = 0; nodes[a].avg = avg; nodes[a].rsw = rsw; }
+    const double tot_w = __dadd_rn(A.hi, A.lo), tot_wx = __dadd_rn(B.hi, B.lo);
+    // range check: isTRUE(all.equal(diff(range(x)), 0)) -> final (changepoints R code)
+    if (gmx - gmn <= 1.4901161193847656e-08) {
+        nd->flat = 1;
+        nd->best_q = -1.0;
+    } else {
+        nd->flat = 0;
+        nd->avg = __ddiv_rn(tot_wx, tot_w);
+        nd->rsw = sqrt(tot_w);
+    }
+}
+
+// one warp of the node's LAST scan tile: tss, total, delta (linear partials + the wrap-around arcs), seed arc
+__device__ __forceinline__ double ptcg(const double* a, int lo, int i) {
+    return i ? __ldcg(&a[lo + i - 1]) : 0.0;
+}
+
+__device__ __forceinline__ void node_finish(Node* nd, const volatile TileScan* ts, int ntiles, const double* __restrict__ cw,
+                                            const double* __restrict__ blk_min, const double* __restrict__ blk_max,
+                                            const int* __restrict__ blk_imin, const int* __restrict__ blk_imax,
+                                            const double* __restrict__ blk_cmin, const double* __restrict__ blk_cmax,
+                                            int al0, int hk, int nmin, int lane) {
+    const int lo = nd->lo, n = nd->hi - nd->lo;
+    // every value below was written by OTHER CTAs of this launch: read through L2 (__ldcg / volatile)
+    const double total = __ldcg(&cw[lo + n - 1]);
+    double delta = 0.0;
+    if (hk > 0 && n > nmin) {
+        const int jw = hk + 1;
+        double dmin = INFINITY;
+        for (int t = lane; t < ntiles; t += 32) dmin = fmin(dmin, ts[t].dmin);
+        for (int i = 1 + lane; i <= jw; i += 32)
+            dmin = fmin(dmin, __dadd_rn(__dsub_rn(total, ptcg(cw, lo, n - jw + i)), ptcg(cw, lo, i)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        delta = __ddiv_rn(dmin, total);
+    }
+    // seed arc: from the global argmin of S to its global argmax (a real arc, scored exactly)
+    const int nb = (n + 1 + CBS_BLK - 1) / CBS_BLK, boff = nd->blk_off;
+    double gmn = INFINITY, gmx = -INFINITY, cmn = 0.0, cmx = 0.0;
+    int imn = 0x7fffffff, imx = 0x7fffffff;
+    for (int b = lane; b < nb; b += 32) {
+        const double vmn = __ldcg(&blk_min[boff + b]), vmx = __ldcg(&blk_max[boff + b]);
+        if (vmn < gmn) { gmn = vmn; imn = __ldcg(&blk_imin[boff + b]); cmn = __ldcg(&blk_cmin[boff + b]); }
+        if (vmx > gmx) { gmx = vmx; imx = __ldcg(&blk_imax[boff + b]); cmx = __ldcg(&blk_cmax[boff + b]); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double omn = __shfl_xor_sync(0xffffffffu, gmn, o), ocmn = __shfl_xor_sync(0xffffffffu, cmn, o);
+        const int oimn = __shfl_xor_sync(0xffffffffu, imn, o);
+        const double omx = __shfl_xor_sync(0xffffffffu, gmx, o), ocmx = __shfl_xor_sync(0xffffffffu, cmx, o);
+        const int oimx = __shfl_xor_sync(0xffffffffu, imx, o);
+        if (omn < gmn || (omn == gmn && oimn < imn)) { gmn = omn; imn = oimn; cmn = ocmn; }
+        if (omx > gmx || (omx == gmx && oimx < imx)) { gmx = omx; imx = oimx; cmx = ocmx; }
+    }
+    if (lane == 0) {
+        DD t = {ts[0].tss_hi, ts[0].tss_lo};
+        for (int q = 1; q < ntiles; ++q) dd_merge(t, ts[q].tss_hi, ts[q].tss_lo);
+        nd->tss = __dadd_rn(t.hi, t.lo);
+        nd->total = total;
+        nd->delta = delta;
+        nd->lock = 0;
+        double q = -1.0;
+        int qi = 0x7fffffff, qj = 0x7fffffff;
+        const bool fwd = imn < imx;
+        const int i = fwd ? imn : imx, j = fwd ? imx : imn;
+        if (j - i >= al0 && j - i <= n - al0) {
+            const double d = fwd ? __dsub_rn(gmx, gmn) : __dsub_rn(gmn, gmx);          // S_j - S_i
+            const double c = fwd ? __dsub_rn(cmx, cmn) : __dsub_rn(cmn, cmx);          // cw_j - cw_i
+            const double den = __dmul_rn(c, __dsub_rn(total, c));
+            q = __ddiv_rn(__dmul_rn(d, d), den);
+            qi = i; qj = j;
+        }
+        nd->best_q = q;
+        nd->best_i = qi;
+        nd->best_j = qj;
+    }
+}
+
+// centring + blocked prefix scan + carries (chained look-back) + block extrema + node finish, one CTA per tile.
+// Deadlock freedom of the look-back: tile k waits for tiles k' < k of the same node only; CTAs are dispatched
+// in blockIdx order and a tile never waits for a later one, so the earliest unfinished tile can always run.
+__global__ void __launch_bounds__(PREP_THREADS, 3)
+cbs_prep_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_node, const double* __restrict__ x,
+                     const double* __restrict__ w, TileScan* __restrict__ part3, double* __restrict__ S,
+                     double* __restrict__ cw, double* __restrict__ blk_min, double* __restrict__ blk_max,
+                     int* __restrict__ blk_imin, int* __restrict__ blk_imax, double* __restrict__ blk_cmin,
+                     double* __restrict__ blk_cmax, double* __restrict__ blk_wmin, int al0, int hk, int nmin, int epoch) {
+    extern __shared__ __align__(16) double s_dyn[];
+    __shared__ double s_a[32], s_b[32];
+    __shared__ double s_wtot[2][PREP_THREADS / 32];
+    __shared__ double s_carry[4];
+    __shared__ double s_halo[PREP_HALO + 8];
+    __shared__ double s_red[8];
+    __shared__ int s_last;
+    double* s_w = s_dyn;                       // padded tile: weights -> local prefix of w
+    double* s_s = s_dyn + PREP_PADDED;         // padded tile: xc*w    -> local prefix
+    double* pS = s_dyn + 2 * PREP_PADDED;      // final S at the tile's points
+    double* pC = pS + PREP_TILE;               // final cw at the tile's points + halo
+    const int a = ptile_node[blockIdx.x];
+    Node* nd = &nodes[a];
+    if (nd->flat) return;
+    const int lo = nd->lo, n = nd->hi - nd->lo, first = nd->ptile_off, boff = nd->blk_off;
+    const int k = blockIdx.x - first;
+    const int ntiles = (n + 1 + PREP_TILE - 1) / PREP_TILE;
+    const int t0 = k * PREP_TILE, m = max(0, min(PREP_TILE, n - t0));
+    const int npts = min(PREP_TILE, n + 1 - t0);                         // points t0 .. t0+npts-1 (<= n)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double avg = nd->avg, rsw = nd->rsw;
 
     DD a_tss = {0.0, 0.0};
     for (int r = tid; r < PREP_TILE; r += PREP_THREADS) {              // coalesced staging
@@ -262,9 +395,6 @@ cbs_prep_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_off
             const int g = lo + t0 + r;
             wv = w[g];
             const double cc = __dsub_rn(x[g], avg);
-            xc[g] = cc;
-            y[g] = __dmul_rn(cc, sqrt(wv));
-            wn[g] = __ddiv_rn(wv, rsw);
             sv = __dmul_rn(cc, wv);
             dd_add(a_tss, __dmul_rn(wv, __dmul_rn(cc, cc)));
         }
@@ -310,49 +440,53 @@ cbs_prep_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_off
         }
     }
     __syncthreads();
-    for (int r = tid; r < m; r += PREP_THREADS) {                       // coalesced write-back of the locals
-        const int g = lo + t0 + r;
-        cwl[g] = s_w[prep_pad(r)];
-        Sl[g] = s_s[prep_pad(r)];
-    }
     const double Tw = s_w[prep_pad(PREP_TILE - 1)], Ts = s_s[prep_pad(PREP_TILE - 1)];
     const DD tss = dd_block_sum(a_tss, s_a, s_b);
+    volatile TileScan* ts_node = part3 + first;
+    const bool want_delta = hk > 0 && n > nmin;
+    const int jw = hk + 1;
     if (tid == 0) {
-        TileScan o;
-        o.Tw = Tw; o.Ts = Ts; o.tss_hi = tss.hi; o.tss_lo = tss.lo; o.dmin = INFINITY; o.pad = 0.0;
-        part3[blockIdx.x] = o;
-    }
-}
-
-__global__ void __launch_bounds__(PREP_THREADS)
-cbs_prep_finish_kernel(const Node* __restrict__ nodes, const int* __restrict__ ptile_off, int nnodes,
-                       const double* __restrict__ Sl, const double* __restrict__ cwl, TileScan* __restrict__ part3,
-                       double* __restrict__ S, double* __restrict__ cw, double* __restrict__ blk_min,
-                       double* __restrict__ blk_max, int* __restrict__ blk_imin, int* __restrict__ blk_imax,
-                       double* __restrict__ blk_cmin, double* __restrict__ blk_cmax, int hk, int nmin) {
-    __shared__ double pS[PREP_TILE];
-    __shared__ double pC[PREP_TILE + PREP_HALO];
-    __shared__ double s_carry[4];
-    __shared__ double s_red[8];
-    int a, k;
-    decode_ptile(ptile_off, nnodes, blockIdx.x, a, k);
-    const Node* nd = &nodes[a];
-    if (nd->flat) return;
-    const int lo = nd->lo, n = nd->hi - nd->lo, boff = nd->blk_off;
-    const double rsw = nd->rsw;
-    const int t0 = k * PREP_TILE, m = max(0, min(PREP_TILE, n - t0));
-    const int npts = min(PREP_TILE, n + 1 - t0);                         // points t0 .. t0+npts-1 (<= n)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        // C[k] = T[0] + ... + T[k-1], left to right; C[k+1] for the halo
-        const TileScan* ts = part3 + ptile_off[a];
+        // publish this tile's totals, then take the carry C[k] = T[0] + ... + T[k-1] left to right
+        TileScan* o = &part3[blockIdx.x];
+        o->Tw = Tw; o->Ts = Ts; o->tss_hi = tss.hi; o->tss_lo = tss.lo; o->dmin = INFINITY;
+        __threadfence();
+        *((volatile int*)&o->flag) = epoch;
         double Cw = 0.0, Cs = 0.0;
         for (int t = 0; t < k; ++t) {
-            Cw = t ? __dadd_rn(Cw, ts[t].Tw) : ts[0].Tw;
-            Cs = t ? __dadd_rn(Cs, ts[t].Ts) : ts[0].Ts;
+            volatile TileScan* p = ts_node + t;
+            while (p->flag != epoch) {}
+            __threadfence();
+            Cw = t ? __dadd_rn(Cw, p->Tw) : p->Tw;
+            Cs = t ? __dadd_rn(Cs, p->Ts) : p->Ts;
         }
         s_carry[0] = Cw; s_carry[1] = Cs;
-        s_carry[2] = k ? __dadd_rn(Cw, ts[k].Tw) : ts[0].Tw;           // C[k+1]
+        s_carry[2] = k ? __dadd_rn(Cw, Tw) : Tw;                       // C[k+1]
+    }
+    // halo for getmncwt: cw at points t0+PREP_TILE+1 .. +jw are terms 0..jw-1 of the NEXT tile.  Their
+    // tile-local prefix values follow from the same fixed association (warp 0 of that tile: X = 0, so
+    // local = E[j] + p[j,e]); thread 1 replays it from the raw weights -- no wait on a later tile.
+    if (want_delta && tid == 32) {
+        const int nthr = (jw + PREP_E - 1) / PREP_E;                     // "threads" of the next tile involved (<= 9)
+        double A[12], p8[12][PREP_E];
+        const int g1 = lo + t0 + PREP_TILE;                              // first term of the next tile
+        const int m1 = max(0, min(PREP_TILE, n - (t0 + PREP_TILE)));
+        for (int j = 0; j < nthr; ++j) {
+            double r = 0.0;
+            for (int e = 0; e < PREP_E; ++e) {
+                const int kk = PREP_E * j + e;
+                const double v = (kk < m1) ? w[g1 + kk] : 0.0;
+                r = e ? __dadd_rn(r, v) : v;
+                p8[j][e] = r;
+            }
+            A[j] = r;
+        }
+        for (int o = 1; o < 32; o <<= 1)
+            for (int l = nthr - 1; l >= o; --l) A[l] = __dadd_rn(A[l], A[l - o]);
+        for (int h = 0; h < jw; ++h) {
+            const int j = h / PREP_E, e = h % PREP_E;
+            const double E = j ? A[j - 1] : 0.0;
+            s_halo[h] = __dadd_rn(__dadd_rn(0.0, E), p8[j][e]);
+        }
     }
     __syncthreads();
     const double Cw = s_carry[0], Cs = s_carry[1], Cw1 = s_carry[2];
@@ -363,27 +497,26 @@ cbs_prep_finish_kernel(const Node* __restrict__ nodes, const int* __restrict__ p
     for (int r = tid; r < m; r += PREP_THREADS) {
         const int g = lo + t0 + r;
         // tile 0 has C = 0: 0 + local = local exactly, as the oracle computes it
-        const double vS = k ? __dadd_rn(Cs, Sl[g]) : Sl[g];
-        const double vC = __ddiv_rn(k ? __dadd_rn(Cw, cwl[g]) : cwl[g], rsw);
+        const double ls = s_s[prep_pad(r)], lw = s_w[prep_pad(r)];
+        const double vS = k ? __dadd_rn(Cs, ls) : ls;
+        const double vC = __ddiv_rn(k ? __dadd_rn(Cw, lw) : lw, rsw);
         S[g] = vS;
         cw[g] = vC;
         if (r + 1 < PREP_TILE) pS[r + 1] = vS;
         pC[r + 1] = vC;                                                  // slot PREP_TILE = first halo point
     }
-    // halo for getmncwt: cw at points t0+PREP_TILE+1 .. (terms of the next tile, carried by C[k+1])
-    const bool want_delta = hk > 0 && n > nmin;
-    const int jw = hk + 1;
     if (want_delta) {
         for (int h = tid; h < jw; h += PREP_THREADS) {
             const int p = t0 + PREP_TILE + 1 + h;                        // point index; its term is p-1
-            if (p <= n) pC[PREP_TILE + 1 + h] = __ddiv_rn(__dadd_rn(Cw1, cwl[lo + p - 1]), rsw);
+            if (p <= n) pC[PREP_TILE + 1 + h] = __ddiv_rn(__dadd_rn(Cw1, s_halo[h]), rsw);
         }
     }
     __syncthreads();
-    // per-256-point block min / max of S with arg (ties -> smallest index) and cw at the arg
+    // per-256-point block min / max of S with arg (ties -> smallest index), cw at the arg, and the
+    // lightest al0-wide window that starts in the block (denominator bound of the band kernel)
     if (warp * CBS_BLK < npts) {
         const int b = (t0 / CBS_BLK) + warp;
-        double bmn = INFINITY, bmx = -INFINITY;
+        double bmn = INFINITY, bmx = -INFINITY, wmin = INFINITY;
         int bimn = 0, bimx = 0;
         for (int q = lane; q < CBS_BLK; q += 32) {
             const int lp = warp * CBS_BLK + q;
@@ -391,6 +524,7 @@ cbs_prep_finish_kernel(const Node* __restrict__ nodes, const int* __restrict__ p
                 const double v = pS[lp];
                 if (v < bmn) { bmn = v; bimn = lp; }
                 if (v > bmx) { bmx = v; bimx = lp; }
+                if (t0 + lp + al0 <= n) wmin = fmin(wmin, __dsub_rn(pC[lp + al0], pC[lp]));
             }
         }
 #pragma unroll
@@ -401,6 +535,7 @@ cbs_prep_finish_kernel(const Node* __restrict__ nodes, const int* __restrict__ p
             const int oimx = __shfl_xor_sync(0xffffffffu, bimx, o);
             if (omn < bmn || (omn == bmn && oimn < bimn)) { bmn = omn; bimn = oimn; }
             if (omx > bmx || (omx == bmx && oimx < bimx)) { bmx = omx; bimx = oimx; }
+            wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
         }
         if (lane == 0) {
             blk_min[boff + b] = bmn;
@@ -409,6 +544,7 @@ cbs_prep_finish_kernel(const Node* __restrict__ nodes, const int* __restrict__ p
             blk_imax[boff + b] = t0 + bimx;
             blk_cmin[boff + b] = pC[bimn];     // cw at the extreme points: the seed kernel then needs
             blk_cmax[boff + b] = pC[bimx];     // no scattered load
+            blk_wmin[boff + b] = wmin;
         }
     }
     // DNAcopy getmncwt, linear arcs starting in this tile: min over i of cw(i+jw) - cw(i)
@@ -427,76 +563,14 @@ cbs_prep_finish_kernel(const Node* __restrict__ nodes, const int* __restrict__ p
             part3[blockIdx.x].dmin = dmin;
         }
     }
-}
-
-// one warp per node: tss, total, delta (linear partials + the wrap-around arcs), reset of the best
-__global__ void __launch_bounds__(128)
-cbs_prep_node_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_off, int nnodes,
-                     const TileScan* __restrict__ part3, const double* __restrict__ cw,
-                     const double* __restrict__ blk_min, const double* __restrict__ blk_max,
-                     const int* __restrict__ blk_imin, const int* __restrict__ blk_imax,
-                     const double* __restrict__ blk_cmin, const double* __restrict__ blk_cmax, int al0, int hk,
-                     int nmin) {
-    const int a = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (a >= nnodes) return;
-    Node* nd = &nodes[a];
-    if (nd->flat) return;
-    const int lo = nd->lo, n = nd->hi - nd->lo;
-    const int ntiles = ptile_off[a + 1] - ptile_off[a];
-    const TileScan* ts = part3 + ptile_off[a];
-    const double total = cw[lo + n - 1];
-    double delta = 0.0;
-    if (hk > 0 && n > nmin) {
-        const int jw = hk + 1;
-        double dmin = INFINITY;
-        for (int t = lane; t < ntiles; t += 32) dmin = fmin(dmin, ts[t].dmin);
-        for (int i = 1 + lane; i <= jw; i += 32)
-            dmin = fmin(dmin, __dadd_rn(__dsub_rn(total, pt(cw, lo, n - jw + i)), pt(cw, lo, i)));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-        delta = __ddiv_rn(dmin, total);
-    }
-    // seed arc: from the global argmin of S to its global argmax (a real arc, scored exactly) -- gives
-    // the seed kernel's CTAs a running best to filter against before they take the node's lock
-    const int nb = (n + 1 + CBS_BLK - 1) / CBS_BLK, boff = nd->blk_off;
-    double gmn = INFINITY, gmx = -INFINITY, cmn = 0.0, cmx = 0.0;
-    int imn = 0x7fffffff, imx = 0x7fffffff;
-    for (int b = lane; b < nb; b += 32) {
-        const double vmn = blk_min[boff + b], vmx = blk_max[boff + b];
-        if (vmn < gmn) { gmn = vmn; imn = blk_imin[boff + b]; cmn = blk_cmin[boff + b]; }
-        if (vmx > gmx) { gmx = vmx; imx = blk_imax[boff + b]; cmx = blk_cmax[boff + b]; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double omn = __shfl_xor_sync(0xffffffffu, gmn, o), ocmn = __shfl_xor_sync(0xffffffffu, cmn, o);
-        const int oimn = __shfl_xor_sync(0xffffffffu, imn, o);
-        const double omx = __shfl_xor_sync(0xffffffffu, gmx, o), ocmx = __shfl_xor_sync(0xffffffffu, cmx, o);
-        const int oimx = __shfl_xor_sync(0xffffffffu, imx, o);
-        if (omn < gmn || (omn == gmn && oimn < imn)) { gmn = omn; imn = oimn; cmn = ocmn; }
-        if (omx > gmx || (omx == gmx && oimx < imx)) { gmx = omx; imx = oimx; cmx = ocmx; }
-    }
-    if (lane == 0) {
-        DD t = {ts[0].tss_hi, ts[0].tss_lo};
-        for (int q = 1; q < ntiles; ++q) dd_merge(t, ts[q].tss_hi, ts[q].tss_lo);
-        nd->tss = __dadd_rn(t.hi, t.lo);
-        nd->total = total;
-        nd->delta = delta;
-        nd->lock = 0;
-        double q = -1.0;
-        int qi = 0x7fffffff, qj = 0x7fffffff;
-        const bool fwd = imn < imx;
-        const int i = fwd ? imn : imx, j = fwd ? imx : imn;
-        if (j - i >= al0 && j - i <= n - al0) {
-            const double d = fwd ? __dsub_rn(gmx, gmn) : __dsub_rn(gmn, gmx);          // S_j - S_i
-            const double c = fwd ? __dsub_rn(cmx, cmn) : __dsub_rn(cmn, cmx);          // cw_j - cw_i
-            const double den = __dmul_rn(c, __dsub_rn(total, c));
-            q = __ddiv_rn(__dmul_rn(d, d), den);
-            qi = i; qj = j;
-        }
-        nd->best_q = q;
-        nd->best_i = qi;
-        nd->best_j = qj;
-    }
+    // the node's last tile finishes the node
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&nd->done_scan, 1) == ntiles - 1);
+    __syncthreads();
+    if (!s_last || warp != 0) return;
+    __threadfence();
+    node_finish(nd, ts_node, ntiles, cw, blk_min, blk_max, blk_imin, blk_imax, blk_cmin, blk_cmax, al0, hk, nmin, lane);
 }
 
 // ------------------------------------------------------------------------------------ scan
@@ -554,11 +628,12 @@ __device__ __forceinline__ void scan_subtiles(Cand& best, const double2* __restr
     }
 }
 
-// The arc scan of one recursion level runs as three kernels over the same tile geometry
+// The arc scan of one recursion level runs as four kernels over the same geometry
 // (node, 1024-point start block ib = 4 bound blocks, 256-point end block jb):
 //   seed  : every pair of bound blocks proposes the arcs between its extreme prefix points
 //           (argmin S of one block, argmax S of the other) -- real arcs, scored exactly, so the
 //           node's running best starts within a few percent of the maximum;
+//   band  : arcs inside the same or adjacent bound blocks;
 //   bound : the pruning test of every (start block, end block) pair against that best; survivors
 //           are appended to a device-wide queue of 1024x256 tiles;
 //   scan  : persistent CTAs pop tiles from the queue (each re-tests its bound against the best
@@ -568,21 +643,11 @@ struct TileRef {
     unsigned mask;
 };
 
-struct SeedRes {   // best seed candidate of one task
+struct SeedRes {   // best seed candidate of one start block
     double q;
     int i, j;
     long long pad;
 };
-
-// task -> (node a, start block ib, first end block jb0): a host-built table, one int4 per task
-__device__ __forceinline__ void decode_task(const Node* __restrict__ nodes, const int4* __restrict__ task_tab,
-                                            int task, int& a, int& ib, int& jb0, int& NJ) {
-    const int4 t = task_tab[task];
-    a = t.x;
-    ib = t.y;
-    jb0 = t.z;
-    NJ = t.w;
-}
 
 // CTA-wide argmax of the threads' candidates (ties -> smallest (i,j)) and one lock-protected
 // update of the node; only candidates found by this CTA carry i != INT_MAX.
@@ -618,23 +683,27 @@ __device__ __forceinline__ void cta_commit(Node* nd, double q, int qi, int qj, d
     }
 }
 
+// one CTA per (node, 1024-point start block): thread <-> end block, looping over the node's end blocks in
+// chunks of 256; the node's last CTA folds the per-CTA candidates into the node (deterministic: the
+// candidate order is total, so the fold does not depend on which CTA finishes last)
 __global__ void __launch_bounds__(256)
-cbs_seed_kernel(const Node* __restrict__ nodes, const int4* __restrict__ task_tab, SeedRes* __restrict__ res,
+cbs_seed_kernel(Node* __restrict__ nodes, const int* __restrict__ iblk_node, SeedRes* __restrict__ res,
                 const double* __restrict__ blk_min, const double* __restrict__ blk_max,
                 const int* __restrict__ blk_imin, const int* __restrict__ blk_imax,
                 const double* __restrict__ blk_cmin, const double* __restrict__ blk_cmax, int al0) {
     __shared__ double s_q[8];
     __shared__ int s_i[8], s_j[8];
-    int a, ib, jb0, NJ;
-    decode_task(nodes, task_tab, blockIdx.x, a, ib, jb0, NJ);
-    const Node* nd = &nodes[a];
-    if (nd->flat) { if (threadIdx.x == 0) { SeedRes r_; r_.q = -1.0; r_.i = 0x7fffffff; r_.j = 0x7fffffff; r_.pad = 0; res[blockIdx.x] = r_; } return; }
+    __shared__ int s_last;
+    const int a = iblk_node[blockIdx.x];
+    Node* nd = &nodes[a];
+    if (nd->flat) return;
+    const int ib = blockIdx.x - nd->iblk_off;
     const int n = nd->hi - nd->lo, boff = nd->blk_off;
+    const int NJ = (n + 1 + CBS_BLK - 1) / CBS_BLK, NI = (n + 1 + CBS_IBLK - 1) / CBS_IBLK;
     const double total = nd->total;
     double bq = -1.0;
     int bi_ = 0x7fffffff, bj_ = 0x7fffffff;
-    const int jb = jb0 + threadIdx.x;
-    if (jb < NJ) {
+    for (int jb = CBS_IW * ib + threadIdx.x; jb < NJ; jb += 256) {
         // per block: (S, cw, index) at the argmin and at the argmax of S -- all coalesced loads
         const double jSmn = blk_min[boff + jb], jSmx = blk_max[boff + jb];
         const double jCmn = blk_cmin[boff + jb], jCmx = blk_cmax[boff + jb];
@@ -668,8 +737,6 @@ cbs_seed_kernel(const Node* __restrict__ nodes, const int4* __restrict__ task_ta
             }
         }
     }
-    // CTA argmax (ties -> smallest (i,j)); the per-task results are reduced per node by
-    // cbs_seed_reduce_kernel -- no lock, no atomics
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -686,22 +753,19 @@ cbs_seed_kernel(const Node* __restrict__ nodes, const int4* __restrict__ task_ta
         SeedRes r_;
         r_.q = bq; r_.i = bi_; r_.j = bj_; r_.pad = 0;
         res[blockIdx.x] = r_;
+        __threadfence();
+        s_last = (atomicAdd(&nd->done_seed, 1) == NI - 1);
     }
-}
-
-// one warp per node: best of the node's per-task seed candidates and of the arc prep_node left there
-__global__ void __launch_bounds__(128)
-cbs_seed_reduce_kernel(Node* __restrict__ nodes, int nnodes, const int* __restrict__ task_off,
-                       const SeedRes* __restrict__ res) {
-    const int a = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (a >= nnodes) return;
-    Node* nd = &nodes[a];
-    if (nd->flat) return;
+    __syncthreads();
+    if (!s_last || warp != 0) return;
+    __threadfence();
     double q = -1.0;
     int qi = 0x7fffffff, qj = 0x7fffffff;
-    for (int t = task_off[a] + lane; t < task_off[a + 1]; t += 32) {
-        const SeedRes r_ = res[t];
-        if (cand_better(r_.q, r_.i, r_.j, q, qi, qj)) { q = r_.q; qi = r_.i; qj = r_.j; }
+    const volatile SeedRes* rs = res + nd->iblk_off;
+    for (int t = lane; t < NI; t += 32) {
+        const double rq = rs[t].q;
+        const int ri = rs[t].i, rj = rs[t].j;
+        if (cand_better(rq, ri, rj, q, qi, qj)) { q = rq; qi = ri; qj = rj; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -716,7 +780,6 @@ cbs_seed_reduce_kernel(Node* __restrict__ nodes, int nnodes, const int* __restri
         nd->best_j = qj;
     }
 }
-
 
 // upper bound test of one (start block bi, end block jb) pair, bi < jb
 __device__ __forceinline__ bool tile_needed(const double* __restrict__ cw, const double* __restrict__ blk_min,
@@ -735,41 +798,79 @@ __device__ __forceinline__ bool tile_needed(const double* __restrict__ cw, const
 }
 
 // Narrow arcs: every (i, j) whose 256-point blocks are equal or adjacent.  At 256-point granularity
-// these tiles can never be pruned (the lightest arc of the pair is a single bin), and they used to
-// be most of the scan; here one CTA owns one start block, keeps its 512 candidate end points in
-// shared memory and repeats the bound test on 32x32 sub-blocks, warp-uniformly (warp <-> 32 starts).
+// these pairs cannot be pruned by the tile bound (the lightest arc of the pair is a single bin), so one
+// CTA owns one start block:
+//   1. CTA-level bound from the block extrema of the two blocks and the lightest al0-window that starts
+//      in the start block (prep): when even that cannot reach the node's running best the CTA exits
+//      without touching S / cw -- the common case in nodes that hold a strong change-point;
+//   2. otherwise the 512-point strip of S and of cw is staged with one TMA bulk copy each
+//      (cp.async.bulk -> UBLKCP, completion on an mbarrier) and the bound test is repeated on 32x32
+//      sub-blocks, warp-uniformly (warp <-> 32 starts).
 static const int BAND_SUB = 32;
 static const int BAND_PTS = 2 * CBS_BLK;
 
 template <bool PRUNE>
 __global__ void __launch_bounds__(256)
-cbs_band_kernel(Node* __restrict__ nodes, int nnodes,
-                const double* __restrict__ S, const double* __restrict__ cw, int al0,
-                unsigned long long* __restrict__ stats) {
-    __shared__ double2 sp[BAND_PTS];
+cbs_band_kernel(Node* __restrict__ nodes, const int* __restrict__ blk_node,
+                const double* __restrict__ S, const double* __restrict__ cw,
+                const double* __restrict__ blk_min, const double* __restrict__ blk_max,
+                const double* __restrict__ blk_wmin, int al0, unsigned long long* __restrict__ stats) {
+    __shared__ __align__(16) double sS[BAND_PTS + 4], sC[BAND_PTS + 4];
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ double s_mn[BAND_PTS / BAND_SUB], s_mx[BAND_PTS / BAND_SUB];
     __shared__ double s_q[8];
     __shared__ int s_i[8], s_j[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int a = 0, hi_ = nnodes;
-    while (hi_ - a > 1) {
-        const int m = (a + hi_) >> 1;
-        if (nodes[m].blk_off <= (int)blockIdx.x) a = m; else hi_ = m;
-    }
+    const int a = blk_node[blockIdx.x];
     Node* nd = &nodes[a];
     if (nd->flat) return;
-    const int lo = nd->lo, n = nd->hi - nd->lo;
-    const int bi = blockIdx.x - nd->blk_off;
+    const int lo = nd->lo, n = nd->hi - nd->lo, boff = nd->blk_off;
+    const int bi = blockIdx.x - boff;
+    const int nb = (n + 1 + CBS_BLK - 1) / CBS_BLK;
     const int ibase = bi * CBS_BLK;
     const int npts = min(BAND_PTS, n + 1 - ibase);   // points ibase .. ibase+npts-1 (<= n)
     const double total = nd->total;
-    for (int k = tid; k < BAND_PTS; k += 256)
-        sp[k] = (k < npts) ? make_double2(pt(S, lo, ibase + k), pt(cw, lo, ibase + k)) : make_double2(0.0, 0.0);
+    __shared__ double s_gq;
+    if (tid == 0) s_gq = *((volatile double*)&nd->best_q);   // one read: the early exit below must be CTA-uniform
     __syncthreads();
+    const double gq = s_gq;
+    if (PRUNE && gq >= 0.0) {
+        // CTA-level bound (uniform: every thread reads the same few words)
+        double mn = blk_min[boff + bi], mx = blk_max[boff + bi];
+        if (bi + 1 < nb) { mn = fmin(mn, blk_min[boff + bi + 1]); mx = fmax(mx, blk_max[boff + bi + 1]); }
+        const double dm = mx - mn;
+        const double cmin = blk_wmin[boff + bi];
+        const double cmax = pt(cw, lo, ibase + npts - 1) - pt(cw, lo, ibase);
+        const double fmin_ = fmin(cmin * (total - cmin), cmax * (total - cmax));
+        if (fmin_ > 0.0 && (dm * dm) / fmin_ * (1.0 + 1e-9) < gq) return;
+    }
+    // stage points ibase .. ibase+npts-1: point p > 0 is array element lo+p-1, point 0 is the constant 0.
+    // The copied range is widened to 16-byte alignment; slot(g) = g - a0 + 2 keeps a free slot for point 0.
+    const int g0 = lo + max(ibase, 1) - 1, g1 = lo + ibase + npts - 1;      // elements [g0, g1)
+    const int a0 = g0 & ~1, a1 = (g1 + 1) & ~1;
+    const int shift = 2 - a0;                                               // slot(g) = g + shift
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const u32 bytes = (u32)(a1 - a0) * 8u;
+        if (bytes) {
+            mbar_expect_tx(&s_bar, 2 * bytes);
+            bulk_g2s(sS + 2, S + a0, bytes, &s_bar);
+            bulk_g2s(sC + 2, cw + a0, bytes, &s_bar);
+        } else {
+            mbar_expect_tx(&s_bar, 0);
+        }
+    }
+    mbar_wait(&s_bar, 0);
+    const int base = lo + ibase - 1 + shift;        // slot of point ibase + k is base + k
+    if (ibase == 0 && tid == 0) { sS[base] = 0.0; sC[base] = 0.0; }
+    __syncthreads();
+    const double* pS = sS + base;
+    const double* pC = sC + base;
     const int nsub = (npts + BAND_SUB - 1) / BAND_SUB;
     for (int sb = warp; sb < nsub; sb += 8) {       // min/max of S per 32-point sub-block
         const int k = sb * BAND_SUB + lane;
-        double vmn = (k < npts) ? sp[k].x : INFINITY, vmx = (k < npts) ? sp[k].x : -INFINITY;
+        double vmn = (k < npts) ? pS[k] : INFINITY, vmx = (k < npts) ? pS[k] : -INFINITY;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             vmn = fmin(vmn, __shfl_xor_sync(0xffffffffu, vmn, o));
@@ -778,7 +879,6 @@ cbs_band_kernel(Node* __restrict__ nodes, int nnodes,
         if (lane == 0) { s_mn[sb] = vmn; s_mx[sb] = vmx; }
     }
     __syncthreads();
-    const double gq = *((volatile double*)&nd->best_q);
     Cand best;
     best.q = gq;
     best.qlo = (gq < 0.0) ? -1.0 : gq * (1.0 - 1e-12);
@@ -790,11 +890,11 @@ cbs_band_kernel(Node* __restrict__ nodes, int nnodes,
         const int i = ibase + il;
         const bool iok = il < npts;
         // lanes without a start point carry NaN so that their comparisons are all false
-        const double Si = iok ? sp[il].x : __longlong_as_double(0x7ff8000000000000ll), ci = iok ? sp[il].y : 0.0;
+        const double Si = iok ? pS[il] : __longlong_as_double(0x7ff8000000000000ll), ci = iok ? pC[il] : 0.0;
         const unsigned kw_span = (unsigned)(n - 2 * al0);   // al0 <= kw <= n - al0  <=>  kw - al0 <= n - 2 al0
         const int wend = min(warp * BAND_SUB + BAND_SUB - 1, npts - 1);
         // weight of the lightest al0-wide window that starts in this warp's sub-block
-        double wmin = (il + al0 < npts) ? sp[il + al0].y - ci : INFINITY;
+        double wmin = (il + al0 < npts) ? pC[il + al0] - ci : INFINITY;
         if (PRUNE) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
@@ -810,8 +910,8 @@ cbs_band_kernel(Node* __restrict__ nodes, int nnodes,
                 const double dm = fmax(fabs(d1), fabs(d2));
                 // lightest arc: for the own and the next sub-block every admissible arc holds an
                 // al0-wide window that starts in this warp's sub-block (the weights are >= 0)
-                const double cmin = (sb > warp + 1) ? sp[j0].y - sp[wend].y : wmin;
-                const double cmax = sp[j1].y - sp[warp * BAND_SUB].y;
+                const double cmin = (sb > warp + 1) ? pC[j0] - pC[wend] : wmin;
+                const double cmax = pC[j1] - pC[warp * BAND_SUB];
                 const double fmin_ = fmin(cmin * (total - cmin), cmax * (total - cmax));
                 if (fmin_ > 0.0 && (dm * dm) / fmin_ * (1.0 + 1e-9) < gq) keep = false;
             }
@@ -823,10 +923,10 @@ cbs_band_kernel(Node* __restrict__ nodes, int nnodes,
             const int j0 = sb * BAND_SUB, j1 = min(j0 + BAND_SUB - 1, npts - 1);
             ++my_pairs;
             for (int jl = j0; jl <= j1; ++jl) {
-                const double2 pj = sp[jl];
+                const double Sj = pS[jl], cj = pC[jl];
                 const int kw = jl - il;
-                const double d = __dsub_rn(pj.x, Si);
-                const double c = __dsub_rn(pj.y, ci);
+                const double d = __dsub_rn(Sj, Si);
+                const double c = __dsub_rn(cj, ci);
                 const double den = __dmul_rn(c, __dsub_rn(total, c));
                 const double num = __dmul_rn(d, d);
                 if ((unsigned)(kw - al0) <= kw_span && num > __dmul_rn(best.qlo, den))
@@ -838,50 +938,55 @@ cbs_band_kernel(Node* __restrict__ nodes, int nnodes,
     cta_commit(nd, best.q, best.i, best.j, s_q, s_i, s_j);
 }
 
+// one CTA per (node, 1024-point start block), thread <-> end block in chunks of 256
 template <bool PRUNE>
 __global__ void __launch_bounds__(256)
-cbs_bound_kernel(const Node* __restrict__ nodes, const int4* __restrict__ task_tab,
+cbs_bound_kernel(const Node* __restrict__ nodes, const int* __restrict__ iblk_node,
                  const double* __restrict__ cw, const double* __restrict__ blk_min,
                  const double* __restrict__ blk_max, TileRef* __restrict__ queue, int* __restrict__ qcount,
                  unsigned long long* __restrict__ stats) {
     __shared__ int s_warp_cnt[8];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int a, ib, jb0, NJ;
-    decode_task(nodes, task_tab, blockIdx.x, a, ib, jb0, NJ);
+    const int a = iblk_node[blockIdx.x];
     const Node* nd = &nodes[a];
     if (nd->flat) return;
+    const int ib = blockIdx.x - nd->iblk_off;
     const int lo = nd->lo, n = nd->hi - nd->lo, boff = nd->blk_off;
+    const int NJ = (n + 1 + CBS_BLK - 1) / CBS_BLK;
     const double total = nd->total, gq = nd->best_q;
-    unsigned mask = 0;
     u32 checked = 0;
-    const int jb = jb0 + tid;
-    if (jb < NJ) {
+    for (int jb0 = CBS_IW * ib; jb0 < NJ; jb0 += 256) {        // uniform trip count across the CTA
+        unsigned mask = 0;
+        const int jb = jb0 + tid;
+        if (jb < NJ) {
 #pragma unroll
-        for (int r = 0; r < CBS_IW; ++r) {
-            const int bi = CBS_IW * ib + r;
-            if (bi * CBS_BLK > n || bi + 1 >= jb) continue;  // bi >= jb-1: the band kernel's arcs
-            bool need = true;
-            if (PRUNE && gq >= 0.0) need = tile_needed(cw, blk_min, blk_max, lo, n, boff, bi, jb, total, gq);
-            ++checked;
-            if (need) mask |= 1u << r;
+            for (int r = 0; r < CBS_IW; ++r) {
+                const int bi = CBS_IW * ib + r;
+                if (bi * CBS_BLK > n || bi + 1 >= jb) continue;  // bi >= jb-1: the band kernel's arcs
+                bool need = true;
+                if (PRUNE && gq >= 0.0) need = tile_needed(cw, blk_min, blk_max, lo, n, boff, bi, jb, total, gq);
+                ++checked;
+                if (need) mask |= 1u << r;
+            }
         }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, mask != 0);
-    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
-    __syncthreads();
-    if (tid == 0) {
-        int tot = 0;
-        for (int k = 0; k < 8; ++k) tot += s_warp_cnt[k];
-        s_base = tot ? atomicAdd(qcount, tot) : 0;
-    }
-    __syncthreads();
-    if (mask) {
-        int base = s_base;
-        for (int k = 0; k < warp; ++k) base += s_warp_cnt[k];
-        TileRef e;
-        e.node = a; e.ib = ib; e.jb = jb; e.mask = mask;
-        queue[base + __popc(bal & ((1u << lane) - 1u))] = e;
+        const unsigned bal = __ballot_sync(0xffffffffu, mask != 0);
+        if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int k = 0; k < 8; ++k) tot += s_warp_cnt[k];
+            s_base = tot ? atomicAdd(qcount, tot) : 0;
+        }
+        __syncthreads();
+        if (mask) {
+            int base = s_base;
+            for (int k = 0; k < warp; ++k) base += s_warp_cnt[k];
+            TileRef e;
+            e.node = a; e.ib = ib; e.jb = jb; e.mask = mask;
+            queue[base + __popc(bal & ((1u << lane) - 1u))] = e;
+        }
+        __syncthreads();
     }
     if (stats) {
         checked = warp_sum_u32(checked);
@@ -986,30 +1091,6 @@ cbs_scan_kernel(Node* __restrict__ nodes, const TileRef* __restrict__ queue, con
 // ------------------------------------------------------------------------------------ decide
 __device__ __forceinline__ double pnorm_std(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
 
-__device__ double nu_dev(double x, double tol) {
-    double lnu1;
-    if (x > 0.01) {
-        lnu1 = log(2.0) - 2.0 * log(x);
-        double lnu0 = lnu1, dk = 0.0;
-        int k = 2;
-        for (int i = 0; i < k; ++i) {
-            dk += 1.0;
-            lnu1 -= 2.0 * pnorm_std(-x * sqrt(dk) / 2.0) / dk;
-        }
-        while (fabs((lnu1 - lnu0) / lnu1) > tol) {
-            lnu0 = lnu1;
-            for (int i = 0; i < k; ++i) {
-                dk += 1.0;
-                lnu1 -= 2.0 * pnorm_std(-x * sqrt(dk) / 2.0) / dk;
-            }
-            k *= 2;
-        }
-    } else {
-        lnu1 = -0.583 * x;
-    }
-    return exp(lnu1);
-}
-
 __device__ __forceinline__ double it1tsq_dev(double x, double a) {
     double yy = x + a - 0.5;
     double r = (8.0 * yy) / (1.0 - 4.0 * yy * yy) + 2.0 * log((1.0 + 2.0 * yy) / (1.0 - 2.0 * yy));
@@ -1023,199 +1104,414 @@ __device__ __forceinline__ double t2_of(double bss, double tss, int n) {
     return bss / ((tss - bss) / ((double)n - 2.0));
 }
 
-enum { ST_NEED_TAILP = 4 };
-
-// thread per node: observed T^2 and the decisions that need no p-value
-__global__ void cbs_stat_kernel(Node* __restrict__ nodes, int nnodes, double alpha, int nperm, int nmin,
-                                int hybrid_method) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per node: observed T^2, the decisions that need no p-value, and the cheap two-sided bracket of
+// DNAcopy's tailp that settles almost every hybrid node without the series.
+// The Siegmund-Yakir closed form  nu_sy(x) = (2/x)(Phi(x/2)-1/2) / ((x/2)Phi(x/2)+phi(x/2))  lies
+// below the reference's truncated series value by at most 2.2 % for every x > 0.01 (it is exact to
+// 1e-15 for x > 12; tests/test_oracle_pins.py sweeps the bracket), so with p_sy = tailp computed
+// from nu_sy:  p_sy (1-1e-6) <= p_reference <= 1.05 p_sy.  A node whose bracket straddles alpha (or an
+// nrejc step alpha - m/nperm) keeps ST_NEED_TAILP, joins the need list and gets the exact series.
+// flags: bit 0 hybrid method, bit 1 diagnostics (every hybrid node gets its series), bit 2 no bracket
+__global__ void __launch_bounds__(128)
+cbs_stat_kernel(Node* __restrict__ nodes, int nnodes, double alpha, int nperm, int nmin, int flags, int ngrid,
+                int* __restrict__ need_list, Ctl* __restrict__ ctl) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * 4 + warp;
     if (idx >= nnodes) return;
     Node* nd = &nodes[idx];
     const int n = nd->hi - nd->lo;
     int state = ST_FINAL, nrejc = 0;
     double ostat = 0.0, ostat1 = 0.0;
+    const bool diag = (flags & 2) != 0;
     if (!nd->flat && nd->best_q >= 0.0) {
         const double t2 = t2_of(nd->best_q, nd->tss, n);
         ostat1 = sqrt(t2);
         ostat = t2 * 0.99999;
-        if (ostat1 > 0.1 || (hybrid_method & 2)) {
+        if (ostat1 > 0.1 || diag) {
             const int bi = nd->best_i, bj = nd->best_j;
             const int l = min(bj - bi, n - bj + bi);
-            const bool diag = (hybrid_method & 2) != 0;   // diagnostics: every hybrid node gets its tail probability
             if (ostat1 >= 7.0 && l >= 10 && !diag) state = ST_SPLIT;
-            else if ((hybrid_method & 1) && n > nmin) state = ST_NEED_TAILP;
+            else if ((flags & 1) && n > nmin) state = ST_NEED_TAILP;
             else { state = ST_PERM_EXACT; nrejc = (int)(alpha * (double)nperm); }
         }
     }
-    nd->state = state;
-    nd->nrejc = nrejc;
-    nd->ostat = ostat;
-    nd->ostat1 = ostat1;
-}
-
-// Cheap two-sided bracket of DNAcopy's tailp that settles almost every node without the series.
-// The Siegmund-Yakir closed form  nu_sy(x) = (2/x)(Phi(x/2)-1/2) / ((x/2)Phi(x/2)+phi(x/2))  lies
-// below the reference's truncated series value by at most 2.2 % for every x > 0.01 (it is exact to
-// 1e-15 for x > 12; tests/test_oracle_pins.py sweeps the bracket), so with p_sy = tailp computed
-// from nu_sy:  p_sy (1-1e-6) <= p_reference <= 1.05 p_sy.  One warp per node.  A node whose bracket
-// straddles alpha (or an nrejc step alpha - m/nperm) keeps ST_NEED_TAILP and gets the exact series.
-__global__ void __launch_bounds__(128)
-cbs_tailp_bounds_kernel(Node* __restrict__ nodes, int nnodes, double alpha, int nperm, int ngrid) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * 4 + warp;
-    if (idx >= nnodes) return;
-    Node* nd = &nodes[idx];
-    if (nd->state != ST_NEED_TAILP) return;
-    const int n = nd->hi - nd->lo;
-    const double b = nd->ostat1, delta = nd->delta;
-    const double dincr = (0.5 - delta) / (double)ngrid;
-    const double bsqrtm = b / sqrt((double)n);
-    double p = 0.0;
-    for (int g = lane; g < ngrid; g += 32) {
-        const double tl = 0.5 - dincr * (double)(g + 1), tt = 0.5 - dincr * ((double)g + 0.5);
-        const double x = bsqrtm / sqrt(tt * (1.0 - tt));
-        double nux;
-        if (x > 0.01) {
-            const double h = 0.5 * x;
-            const double Pc = 0.5 * erf(h * 0.70710678118654752440);  // Phi(h) - 1/2
-            const double ph = 0.3989422804014327 * exp(-0.5 * h * h);
-            nux = ((2.0 / x) * Pc) / (h * (0.5 + Pc) + ph);
-        } else {
-            nux = exp(-0.583 * x);
+    if (state == ST_NEED_TAILP && !(flags & 4) && !diag) {
+        const double b = ostat1, delta = nd->delta;
+        const double dincr = (0.5 - delta) / (double)ngrid;
+        const double bsqrtm = b / sqrt((double)n);
+        double p = 0.0;
+        for (int g = lane; g < ngrid; g += 32) {
+            const double tl = 0.5 - dincr * (double)(g + 1), tt = 0.5 - dincr * ((double)g + 0.5);
+            const double x = bsqrtm / sqrt(tt * (1.0 - tt));
+            double nux;
+            if (x > 0.01) {
+                const double h = 0.5 * x;
+                const double Pc = 0.5 * erf(h * 0.70710678118654752440);  // Phi(h) - 1/2
+                const double ph = 0.3989422804014327 * exp(-0.5 * h * h);
+                nux = ((2.0 / x) * Pc) / (h * (0.5 + Pc) + ph);
+            } else {
+                nux = exp(-0.583 * x);
+            }
+            p += (nux * nux) * it1tsq_dev(tl, dincr);
         }
-        p += (nux * nux) * it1tsq_dev(tl, dincr);
-    }
-    p = warp_sum(p);
-    if (lane == 0) {
+        p = warp_sum(p);
         p = 2.0 * (9.973557e-2 * (b * b * b) * exp(-(b * b) / 2.0) * p);
         const double plo = p * (1.0 - 1e-6), phi = p * 1.05;
         if (plo > alpha) {
-            nd->state = ST_FINAL;
+            state = ST_FINAL;
         } else if (phi <= alpha) {
             const int r_hi = (int)((alpha - plo) * (double)nperm), r_lo = (int)((alpha - phi) * (double)nperm);
-            if (r_hi == r_lo) { nd->state = ST_PERM_HYBRID; nd->nrejc = r_lo; }
+            if (r_hi == r_lo) { state = ST_PERM_HYBRID; nrejc = r_lo; }
         }
+    }
+    if (lane == 0) {
+        nd->state = state;
+        nd->nrejc = nrejc;
+        nd->ostat = ostat;
+        nd->ostat1 = ostat1;
+        if (state == ST_NEED_TAILP) need_list[atomicAdd(&ctl->n_need, 1)] = idx;
     }
 }
 
-// DNAcopy tailp: one CTA per (grid point, node).  nu(x)'s series is summed in the reference's
+// DNAcopy tailp: one CTA per (grid point, listed node).  nu(x)'s series is summed in the reference's
 // doubling blocks (2,2,4,8,...), each block split over the 128 threads and tree-reduced; the
 // relative-change stopping rule is evaluated between blocks exactly as in the serial code.
 __global__ void __launch_bounds__(128)
-cbs_tailp_terms_kernel(const Node* __restrict__ nodes, double* __restrict__ terms, int kmax, int ngrid, double tol) {
+cbs_tailp_terms_kernel(const Node* __restrict__ nodes, const int* __restrict__ need_list, const Ctl* __restrict__ ctl,
+                       double* __restrict__ terms, int ngrid, double tol) {
     __shared__ double s_part[4];
     __shared__ double s_sum;
-    const Node* nd = &nodes[blockIdx.y];
-    if (nd->state != ST_NEED_TAILP) return;
-    const int n = nd->hi - nd->lo;
+    const int n_need = ctl->n_need;
     const int g = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double b = nd->ostat1;
-    const double delta = nd->delta;
-    const double dincr = (0.5 - delta) / (double)ngrid;
-    const double bsqrtm = b / sqrt((double)n);
-    double tl = 0.5 - dincr, tt = 0.5 - 0.5 * dincr;
-    for (int s = 0; s < g; ++s) { tl -= dincr; tt -= dincr; }  // same roundings as the serial loop
-    const double x = bsqrtm / sqrt(tt * (1.0 - tt));
-    double lnu1;
-    if (x > 0.01) {
-        lnu1 = log(2.0) - 2.0 * log(x);
-        double lnu0 = lnu1;
-        long long done = 0;
-        int k = 2;
-        bool first = true;
-        for (;;) {
-            double part = 0.0;
-            for (long long i = done + 1 + tid; i <= done + k; i += 128) {
-                const double dk = (double)i;
-                part += 2.0 * pnorm_std(-x * sqrt(dk) / 2.0) / dk;
+    for (int li = blockIdx.y; li < n_need; li += gridDim.y) {
+        const int node = need_list[li];
+        const Node* nd = &nodes[node];
+        const int n = nd->hi - nd->lo;
+        const double b = nd->ostat1;
+        const double delta = nd->delta;
+        const double dincr = (0.5 - delta) / (double)ngrid;
+        const double bsqrtm = b / sqrt((double)n);
+        double tl = 0.5 - dincr, tt = 0.5 - 0.5 * dincr;
+        for (int s = 0; s < g; ++s) { tl -= dincr; tt -= dincr; }  // same roundings as the serial loop
+        const double x = bsqrtm / sqrt(tt * (1.0 - tt));
+        double lnu1;
+        if (x > 0.01) {
+            lnu1 = log(2.0) - 2.0 * log(x);
+            double lnu0 = lnu1;
+            long long done = 0;
+            int k = 2;
+            bool first = true;
+            for (;;) {
+                double part = 0.0;
+                for (long long i = done + 1 + tid; i <= done + k; i += 128) {
+                    const double dk = (double)i;
+                    part += 2.0 * pnorm_std(-x * sqrt(dk) / 2.0) / dk;
+                }
+                part = warp_sum(part);
+                if (lane == 0) s_part[warp] = part;
+                __syncthreads();
+                if (tid == 0) s_sum = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+                __syncthreads();
+                lnu1 -= s_sum;
+                done += k;
+                if (!first) k *= 2;
+                first = false;
+                if (!(fabs((lnu1 - lnu0) / lnu1) > tol)) break;
+                lnu0 = lnu1;
+                __syncthreads();
             }
-            part = warp_sum(part);
-            if (lane == 0) s_part[warp] = part;
-            __syncthreads();
-            if (tid == 0) s_sum = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
-            __syncthreads();
-            lnu1 -= s_sum;
-            done += k;
-            if (!first) k *= 2;
-            first = false;
-            if (!(fabs((lnu1 - lnu0) / lnu1) > tol)) break;
-            lnu0 = lnu1;
-            __syncthreads();
+        } else {
+            lnu1 = -0.583 * x;
         }
-    } else {
-        lnu1 = -0.583 * x;
-    }
-    if (tid == 0) {
-        const double nux = exp(lnu1);
-        terms[(size_t)blockIdx.y * ngrid + g] = (nux * nux) * it1tsq_dev(tl, dincr);
+        if (tid == 0) {
+            const double nux = exp(lnu1);
+            terms[(size_t)node * ngrid + g] = (nux * nux) * it1tsq_dev(tl, dincr);
+        }
+        __syncthreads();
     }
 }
 
-// thread per node: finish the tail probability and the hybrid decision
-__global__ void cbs_decide_kernel(Node* __restrict__ nodes, int nnodes, Decision* __restrict__ dec,
-                                  const double* __restrict__ terms, double alpha, int nperm, int ngrid) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nnodes) return;
-    Node* nd = &nodes[idx];
-    int state = nd->state, nrejc = nd->nrejc;
-    if (state == ST_NEED_TAILP) {
-        const double b = nd->ostat1;
-        double p = 0.0;
-        for (int g = 0; g < ngrid; ++g) p += terms[(size_t)idx * ngrid + g];
-        p = 9.973557e-2 * (b * b * b) * exp(-(b * b) / 2.0) * p;
-        p = 2.0 * p;
-        nd->tailp = p;
-        if (p > alpha) state = ST_FINAL;
-        else { state = ST_PERM_HYBRID; nrejc = (int)((alpha - p) * (double)nperm); }
-        nd->state = state;
-        nd->nrejc = nrejc;
+// ordered append of the threads' flagged items to a list (single CTA; call from all threads of the block)
+__device__ __forceinline__ void block_append(bool flag, int value, int* __restrict__ list, int* s_count,
+                                             int* s_warp, int nwarps) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int base = *s_count;
+    for (int k = 0; k < warp; ++k) base += s_warp[k];
+    if (flag) list[base + __popc(bal & ((1u << lane) - 1u))] = value;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < nwarps; ++k) tot += s_warp[k];
+        *s_count += tot;
     }
-    Decision d;
-    d.state = state;
-    d.nrejc = nrejc;
-    d.best_i = nd->best_i;
-    d.best_j = nd->best_j;
-    d.ostat = nd->ostat;
-    dec[idx] = d;
+    __syncthreads();
+}
+
+// single CTA: finish the tail probabilities, the hybrid decisions and the two permutation lists (node order)
+__global__ void __launch_bounds__(1024)
+cbs_decide_kernel(Node* __restrict__ nodes, int nnodes, const double* __restrict__ terms, double alpha, int nperm,
+                  int ngrid, int diag, int* __restrict__ hyb_list, int* __restrict__ exact_list, Ctl* __restrict__ ctl) {
+    __shared__ int s_warp[32];
+    __shared__ int s_nh, s_ne;
+    if (threadIdx.x == 0) { s_nh = 0; s_ne = 0; }
+    __syncthreads();
+    for (int base = 0; base < nnodes; base += 1024) {
+        const int idx = base + threadIdx.x;
+        int state = ST_FINAL;
+        if (idx < nnodes) {
+            Node* nd = &nodes[idx];
+            state = nd->state;
+            int nrejc = nd->nrejc;
+            if (state == ST_NEED_TAILP) {
+                const double b = nd->ostat1;
+                double p = 0.0;
+                for (int g = 0; g < ngrid; ++g) p += terms[(size_t)idx * ngrid + g];
+                p = 9.973557e-2 * (b * b * b) * exp(-(b * b) / 2.0) * p;
+                p = 2.0 * p;
+                nd->tailp = p;
+                if (p > alpha && !diag) state = ST_FINAL;
+                else { state = ST_PERM_HYBRID; nrejc = (int)((alpha - p) * (double)nperm); }
+            }
+            if (diag && (state == ST_PERM_HYBRID || state == ST_PERM_EXACT)) nrejc = nperm;   // never stop early
+            nd->state = state;
+            nd->nrejc = nrejc;
+            nd->nrej = 0;
+            nd->kk = nrejc * (nrejc + 1) / 2 + 1;
+        }
+        block_append(state == ST_PERM_HYBRID, idx, hyb_list, &s_nh, s_warp, 32);
+        block_append(state == ST_PERM_EXACT, idx, exact_list, &s_ne, s_warp, 32);
+    }
+    if (threadIdx.x == 0) {
+        ctl->n_hyb = s_nh;
+        ctl->n_exact = s_ne;
+        ctl->stats[3] += (unsigned long long)(s_nh + s_ne);
+    }
 }
 
 // ------------------------------------------------------------------------------------ permutations
-// Pruning limits for the hybrid permutation statistic of one node (DNAcopy keeps the same kind of table,
-// mncwt, for hwtmaxp).  A permutation only has to answer "does any short arc reach the observed
-// statistic?", i.e. is  acc^2 / den(s,k) >= q_thr  for some arc, with q_thr the smallest BSS whose T^2
-// reaches ostat.  The weights are not permuted, so den(s,k) = c (W - c), c = sum of the arc's k
-// normalised weights, is the same in every permutation: lim[k] = q_thr * min_s den(s,k) * (1 - 1e-12)
-// lets the permutation kernel drop an arc after one add, one multiply and one compare.
-// One CTA per node; cacc is accumulated exactly as the permutation kernel accumulates it.
-static const int HYB_LIM = HYB_KMAX + 1;
+// Both permutation tests run as ONE cooperative persistent kernel each: the host cannot know how many nodes
+// need them, so every size comes from the level control block and the kernels return at once when their
+// list is empty.  Inside: chunks of 64 -> 2048 permutations over the still-undecided nodes, DNAcopy's
+// sequential stopping boundary replayed by CTA 0 between chunks (grid.sync on both sides).
+struct PermArgs {
+    Node* nodes;
+    const int* list;               // nodes in this test (hyb_list / exact_list), n_list = ctl->n_hyb / n_exact
+    Ctl* ctl;
+    const double *x, *w, *rw, *cw;
+    double *y, *wn;                // exchangeable terms y = xc sqrt(w) and w / sqrt(sum w) of the listed nodes
+    unsigned long long* dmin_bits; // [node][HYB_LIM] smallest arc denominators (hybrid)
+    unsigned long long* pmax;      // 2 buffers of pm_entries permutation maxima (bit patterns)
+    long long pm_entries;
+    const int* sbdry;
+    int* act;                      // 2 x cap: active list (node indices), double-buffered
+    int* act_toff;                 // cap + 1: prefix of HYB_TP tiles over the active list (hybrid)
+    int cap;
+    u64 seed;
+    int al0, kmax, nperm, diag;
+};
 
-__global__ void __launch_bounds__(256)
-cbs_perm_bounds_kernel(const Node* __restrict__ nodes, const int* __restrict__ list, const double* __restrict__ wn,
-                       int al0, int kmax, unsigned long long* __restrict__ dmin_bits) {
-    // grid (tile of HYB_TP arc starts, list index): min over the tile's starts of den(s, k) for every k,
-    // merged into dmin_bits[node][k] with atomicMin on the bit pattern (den > 0, so the order is numeric)
-    __shared__ double s_w[HYB_TP + HYB_KMAX];
-    __shared__ double s_min[8][HYB_LIM];
-    const int node = list[blockIdx.y];
-    const Node nd = nodes[node];
+static const int PERM_THREADS = 256;
+
+// CTA 0 after a chunk: exceedance flags in permutation order -> nrej / boundary index -> decision;
+// survivors are compacted (order kept) into the other half of `act`; tile prefix for the hybrid kernel.
+__device__ void perm_replay(const PermArgs& A, const unsigned long long* pm, int n_act, int p0, int chunk, int cur,
+                            bool hybrid, int* s_cnt, int* s_warp) {
+    const int* act_cur = A.act + (size_t)cur * A.cap;
+    int* act_nxt = A.act + (size_t)(cur ^ 1) * A.cap;
+    if (threadIdx.x == 0) *s_cnt = 0;
+    __syncthreads();
+    const bool last_chunk = p0 + chunk >= A.nperm;
+    const int nthr = blockDim.x;
+    for (int base = 0; base < n_act; base += nthr) {
+        const int a = base + threadIdx.x;
+        bool keep = false;
+        int node = 0;
+        if (a < n_act) {
+            node = act_cur[a];
+            Node* nd = &A.nodes[node];
+            const int n = nd->hi - nd->lo, nrejc = nd->nrejc;
+            const double tss = nd->tss, ostat = nd->ostat;
+            int nrej = nd->nrej, kk = nd->kk, decided = 0;
+            for (int c = 0; c < chunk && !decided; ++c) {
+                const int np = p0 + c + 1;
+                const double pb = __longlong_as_double((long long)pm[(size_t)a * chunk + c]);
+                if (ostat <= t2_of(pb, tss, n)) { ++nrej; ++kk; }
+                if (A.diag) continue;
+                if (nrej > nrejc) decided = -1;
+                else if (np >= A.sbdry[kk - 1]) decided = 1;
+            }
+            if (decided == 0 && last_chunk) decided = 1;          // survived every permutation
+            nd->nrej = nrej;
+            nd->kk = kk;
+            if (decided) nd->state = decided > 0 ? ST_SPLIT : ST_FINAL;
+            keep = decided == 0;
+            const long long arcs = hybrid ? (long long)n * (A.kmax - A.al0 + 1) * chunk : (long long)n * n / 2 * chunk;
+            atomicAdd(&A.ctl->stats[5], (unsigned long long)arcs);
+        }
+        block_append(keep, node, act_nxt, s_cnt, s_warp, nthr / 32);
+    }
+    if (threadIdx.x == 0) {
+        const int m = *s_cnt;
+        A.ctl->stats[4] += (unsigned long long)n_act * chunk;
+        if (hybrid) {
+            int t = 0;
+            for (int a = 0; a < m; ++a) {
+                A.act_toff[a] = t;
+                const Node* nd = &A.nodes[act_nxt[a]];
+                t += (nd->hi - nd->lo + HYB_TP - 1) / HYB_TP;
+            }
+            A.act_toff[m] = t;
+        }
+        __threadfence();
+        A.ctl->n_act = m;
+    }
+}
+
+// rare path of the hybrid statistic: this arc could reach the observed statistic -> score it exactly
+__device__ __noinline__ void hyb_score(const double* __restrict__ wn, int lo, int n, double total, int pos0, int k,
+                                       double num, double& best, double& bestlo) {
+    double cacc = 0.0;
+    int pos = pos0;                                    // the weights are read from global memory here only
+    for (int j = 0; j < k; ++j) {
+        if (pos >= n) pos -= n;
+        cacc = __dadd_rn(cacc, wn[lo + pos]);
+        ++pos;
+    }
+    const double den = __dmul_rn(cacc, __dsub_rn(total, cacc));
+    if (num > __dmul_rn(bestlo, den)) {
+        const double q = __ddiv_rn(num, den);
+        if (q > best) { best = q; bestlo = q * (1.0 - 1e-12); }
+    }
+}
+
+// shared-memory layout of the permuted terms: 4 consecutive arc starts per thread read a sliding window, so the
+// tile is padded by one slot per 4 (thread stride 5 doubles: conflict-free 64-bit accesses)
+__device__ __forceinline__ int hyb_idx(int i) { return i + (i >> 2); }
+static const int HYB_SMEM_T = (HYB_TP + HYB_KMAX) + (HYB_TP + HYB_KMAX) / 4 + 8;
+
+// Hybrid permutation statistic of one (node, permutation, tile of HYB_TP arc starts): circular arcs of width
+// al0..kmax over the permuted terms.  Pruning limits per width (DNAcopy keeps the same kind of table, mncwt):
+// a permutation only has to answer "does any short arc reach the observed statistic?", i.e. is
+// acc^2 / den(s,k) >= q_thr for some arc; the weights are not permuted, so the smallest den(.,k) is a constant
+// of the node and an arc is dropped when |acc| < sqrt(q_thr min_s den(s,k)).  The hot loop therefore costs ONE
+// FP64 add per arc plus an integer compare of the high word of |acc| against a conservative limit; a group of
+// 4 starts that trips the filter is re-walked with the exact test of the running-sum square.
+template <int KMAX_T, int AL0_T>
+__device__ __forceinline__ void hyb_tile(const PermArgs& A, int node, int s0, int perm, double* s_t, double* s_lim,
+                                         u32* s_limhi, double* s_best, unsigned long long* pmax_slot) {
+    const Node nd = A.nodes[node];
     const int n = nd.hi - nd.lo, lo = nd.lo;
-    const int s0 = blockIdx.x * HYB_TP;
-    if (s0 >= n) return;
-    const double total = nd.total;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kmax = KMAX_T > 0 ? KMAX_T : A.kmax, al0 = AL0_T > 0 ? AL0_T : A.al0;
+    const int tid = threadIdx.x;
+    Prp prp;
+    prp.init(A.seed, (u32)(nd.lo - nd.base), (u32)(nd.hi - nd.base), 0u, (u32)perm, (u32)n);
     const int count = min(HYB_TP, n - s0);
     const int need = count + kmax - 1;
-    for (int k = threadIdx.x; k < need; k += 256) {
+    for (int k = tid; k < HYB_TP + HYB_KMAX; k += PERM_THREADS) {
+        double v = 0.0;
+        if (k < need) {
+            int pos = s0 + k;
+            if (pos >= n) pos -= n;
+            v = __dmul_rn(A.y[lo + prp((u32)pos)], A.rw[lo + pos]);
+        }
+        s_t[hyb_idx(k)] = v;
+    }
+    if (tid <= kmax) {
+        // smallest BSS whose T^2 reaches ostat: bss (n-2) / (tss - bss) >= ostat (t2_of is increasing there);
+        // no pruning when tss is so small that t2_of's guard (tss <= bss + 1e-4) could come into play
+        const double nm2 = (double)n - 2.0;
+        const double qthr = nd.ostat * nd.tss / (nm2 + nd.ostat) * (1.0 - 1e-9);
+        const bool safe = nd.tss * nm2 / (nm2 + nd.ostat) > 1e-3 && nd.ostat > 0.0 && tid >= al0;
+        const double dm = __longlong_as_double((long long)A.dmin_bits[(size_t)node * HYB_LIM + tid]);
+        const double lim = safe ? qthr * dm * (1.0 - 1e-12) : 0.0;
+        s_lim[tid] = lim;
+        // |acc| >= sqrt(lim) (1 - 1e-9) is implied by acc^2 >= lim; compare high words (monotone for doubles >= 0)
+        s_limhi[tid] = (u32)__double2hiint(sqrt(lim) * (1.0 - 1e-9));
+    }
+    __syncthreads();
+    const double total = nd.total;
+    double best = 0.0, bestlo = 0.0;
+    if (KMAX_T > 0) {
+        for (int grp = tid; 4 * grp < count; grp += PERM_THREADS) {
+            const double* v = s_t + 5 * grp;          // hyb_idx(4 grp + j) = 5 grp + j + (j >> 2)
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            double e0 = v[0], e1 = v[1], e2 = v[2], e3 = v[3];
+            bool hit = false;
+#pragma unroll
+            for (int k = 1; k <= KMAX_T; ++k) {
+                a0 = __dadd_rn(a0, e0); a1 = __dadd_rn(a1, e1); a2 = __dadd_rn(a2, e2); a3 = __dadd_rn(a3, e3);
+                if (k >= AL0_T) {
+                    const u32 L = s_limhi[k];
+                    hit |= ((u32)__double2hiint(a0) & 0x7fffffffu) >= L;
+                    hit |= ((u32)__double2hiint(a1) & 0x7fffffffu) >= L;
+                    hit |= ((u32)__double2hiint(a2) & 0x7fffffffu) >= L;
+                    hit |= ((u32)__double2hiint(a3) & 0x7fffffffu) >= L;
+                }
+                e0 = e1; e1 = e2; e2 = e3;
+                e3 = v[(k + 3) + ((k + 3) >> 2)];
+            }
+            if (hit) {
+                for (int m = 0; m < 4; ++m) {
+                    const int s = 4 * grp + m;
+                    if (s >= count) break;
+                    double acc = 0.0;
+                    for (int k = 1; k <= KMAX_T; ++k) {
+                        acc = __dadd_rn(acc, s_t[hyb_idx(s + k - 1)]);
+                        if (k >= AL0_T) {
+                            const double num = __dmul_rn(acc, acc);
+                            if (num >= s_lim[k]) hyb_score(A.wn, lo, n, total, s0 + s, k, num, best, bestlo);
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        for (int s = tid; s < count; s += PERM_THREADS) {
+            double acc = 0.0;
+            for (int k = 1; k <= kmax; ++k) {
+                acc = __dadd_rn(acc, s_t[hyb_idx(s + k - 1)]);
+                if (k >= al0) {
+                    const double num = __dmul_rn(acc, acc);
+                    if (num >= s_lim[k]) hyb_score(A.wn, lo, n, total, s0 + s, k, num, best, bestlo);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((tid & 31) == 0) s_best[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < PERM_THREADS / 32; ++k) best = fmax(best, s_best[k]);
+        if (best > 0.0) atomicMax(pmax_slot, (unsigned long long)__double_as_longlong(best));
+    }
+    __syncthreads();
+}
+
+// min over a tile's arc starts of den(s, k) for every width k, merged into dmin_bits[node][k] with atomicMin on
+// the bit pattern (den > 0, so the order is numeric); cacc is accumulated exactly as hyb_score accumulates it
+__device__ __forceinline__ void hyb_bounds_tile(const PermArgs& A, int node, int s0, double* s_w, double (*s_min)[HYB_LIM]) {
+    const Node nd = A.nodes[node];
+    const int n = nd.hi - nd.lo, lo = nd.lo;
+    const double total = nd.total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kmax = A.kmax, al0 = A.al0;
+    const int count = min(HYB_TP, n - s0);
+    const int need = count + kmax - 1;
+    for (int k = tid; k < need; k += PERM_THREADS) {
         int pos = s0 + k;
         if (pos >= n) pos -= n;
-        s_w[k] = wn[lo + pos];
+        s_w[k] = A.wn[lo + pos];
     }
     __syncthreads();
     double dmin[HYB_LIM];
 #pragma unroll 1
     for (int k = 0; k <= kmax; ++k) dmin[k] = INFINITY;
-    for (int s = threadIdx.x; s < count; s += 256) {
+    for (int s = tid; s < count; s += PERM_THREADS) {
         double cacc = 0.0;
 #pragma unroll 1
         for (int k = 1; k <= kmax; ++k) {
@@ -1231,164 +1527,204 @@ cbs_perm_bounds_kernel(const Node* __restrict__ nodes, const int* __restrict__ l
         if (lane == 0) s_min[warp][k] = v;
     }
     __syncthreads();
-    for (int k = al0 + threadIdx.x; k <= kmax; k += 256) {
+    for (int k = al0 + tid; k <= kmax; k += PERM_THREADS) {
         double v = s_min[0][k];
-        for (int w_ = 1; w_ < 8; ++w_) v = fmin(v, s_min[w_][k]);
-        if (v < INFINITY) atomicMin(&dmin_bits[(size_t)node * HYB_LIM + k], (unsigned long long)__double_as_longlong(v));
+        for (int w_ = 1; w_ < PERM_THREADS / 32; ++w_) v = fmin(v, s_min[w_][k]);
+        if (v < INFINITY) atomicMin(&A.dmin_bits[(size_t)node * HYB_LIM + k], (unsigned long long)__double_as_longlong(v));
     }
+    __syncthreads();
 }
 
-// hybrid: circular arcs of width al0..kmax over the permuted terms; grid (pos tile, perm, list idx)
-// KMAX_T / AL0_T > 0: widths fixed at compile time (DNAcopy's defaults kmax = 25, min.width = 2) so that the
-// arc loop unrolls into LDS + DADD + DMUL + DSETP per arc; 0 = run-time widths.
+// position of the active node that owns global tile t (act_toff is a prefix over the active list)
+__device__ __forceinline__ int find_slot(const int* __restrict__ toff, int n_act, int t) {
+    int lo_ = 0, hi_ = n_act;
+    while (hi_ - lo_ > 1) {
+        const int m = (lo_ + hi_) >> 1;
+        if (toff[m] <= t) lo_ = m; else hi_ = m;
+    }
+    return lo_;
+}
+
+__device__ __forceinline__ int chunk_for(int sched, int n_act, long long pm_entries, int left) {
+    long long c = sched;
+    const long long fit = pm_entries / (n_act > 0 ? n_act : 1);
+    if (c > fit) c = fit;
+    if (c < 1) c = 1;
+    if (c > left) c = left;
+    return (int)c;
+}
+
 template <int KMAX_T, int AL0_T>
-__global__ void __launch_bounds__(256, 3)
-cbs_perm_hybrid_kernel(const Node* __restrict__ nodes, const int* __restrict__ list, int p0,
-                       const double* __restrict__ y, const double* __restrict__ w_sqrt,
-                       const double* __restrict__ wn, const unsigned long long* __restrict__ dmin_bits, u64 seed,
-                       int al0, int kmax, unsigned long long* __restrict__ pmax, int chunk) {
-    __shared__ double s_t[HYB_TP + HYB_KMAX];
+__global__ void __launch_bounds__(PERM_THREADS, 2)
+cbs_perm_hybrid_kernel(PermArgs A) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ __align__(16) double s_t[HYB_SMEM_T];
     __shared__ double s_lim[HYB_LIM];
-    __shared__ double s_best[8];
-    const int node = list[blockIdx.z];
-    const Node nd = nodes[node];
-    const int n = nd.hi - nd.lo, lo = nd.lo;
-    const int s0 = blockIdx.x * HYB_TP;
-    if (s0 >= n) return;
-    const int perm = p0 + blockIdx.y;
-    Prp prp;
-    prp.init(seed, (u32)(nd.lo - nd.base), (u32)(nd.hi - nd.base), 0u, (u32)perm, (u32)n);
-    const int count = min(HYB_TP, n - s0);
-    const int need = count + kmax - 1;
-    for (int k = threadIdx.x; k < need; k += 256) {
-        int pos = s0 + k;
-        if (pos >= n) pos -= n;
-        s_t[k] = __dmul_rn(y[lo + prp((u32)pos)], w_sqrt[lo + pos]);
-    }
-    if (threadIdx.x <= kmax) {
-        // smallest BSS whose T^2 reaches ostat: bss (n-2) / (tss - bss) >= ostat (t2_of is increasing there);
-        // no pruning when tss is so small that t2_of's guard (tss <= bss + 1e-4) could come into play
-        const double nm2 = (double)n - 2.0;
-        const double qthr = nd.ostat * nd.tss / (nm2 + nd.ostat) * (1.0 - 1e-9);
-        const bool safe = nd.tss * nm2 / (nm2 + nd.ostat) > 1e-3 && nd.ostat > 0.0 && threadIdx.x >= al0;
-        const double dm = __longlong_as_double((long long)dmin_bits[(size_t)node * HYB_LIM + threadIdx.x]);
-        s_lim[threadIdx.x] = safe ? qthr * dm * (1.0 - 1e-12) : 0.0;
-    }
-    __syncthreads();
-    const double total = nd.total;
-    double best = 0.0, bestlo = 0.0;
-    // rare path: this arc could reach the observed statistic -> score it exactly
-    auto score = [&](int s, int k, double num) {
-        double cacc = 0.0;
-        int pos = s0 + s;                                  // the weights are read from global memory here only
-        for (int j = 0; j < k; ++j) {
-            if (pos >= n) pos -= n;
-            cacc = __dadd_rn(cacc, wn[lo + pos]);
-            ++pos;
+    __shared__ u32 s_limhi[HYB_LIM];
+    __shared__ double s_best[PERM_THREADS / 32];
+    __shared__ int s_cnt, s_warp[PERM_THREADS / 32];
+    const int n_list = A.ctl->n_hyb;
+    if (n_list == 0) return;                               // uniform over the grid
+    const int tid = threadIdx.x;
+    const long long gtid = (long long)blockIdx.x * PERM_THREADS + tid, gsize = (long long)gridDim.x * PERM_THREADS;
+    // ---- phase 0: exchangeable terms and normalised weights of the listed nodes; limits reset; active list
+    for (int li = 0; li < n_list; ++li) {
+        const int node = A.list[li];
+        const Node* nd = &A.nodes[node];
+        const int lo = nd->lo, hi = nd->hi;
+        const double avg = nd->avg, rsw = nd->rsw;
+        for (long long g = lo + gtid; g < hi; g += gsize) {
+            const double wv = A.w[g];
+            A.y[g] = __dmul_rn(__dsub_rn(A.x[g], avg), A.rw[g]);
+            A.wn[g] = __ddiv_rn(wv, rsw);
         }
-        const double den = __dmul_rn(cacc, __dsub_rn(total, cacc));
-        if (num > __dmul_rn(bestlo, den)) {
-            const double q = __ddiv_rn(num, den);
-            if (q > best) { best = q; bestlo = q * (1.0 - 1e-12); }
-        }
-    };
-    if (KMAX_T > 0) {
-        for (int s = threadIdx.x; s < count; s += 256) {
-            double acc = 0.0;
-#pragma unroll
-            for (int k = 1; k <= KMAX_T; ++k) {
-                acc = __dadd_rn(acc, s_t[s + k - 1]);
-                if (k >= AL0_T) {
-                    const double num = __dmul_rn(acc, acc);
-                    if (num >= s_lim[k]) score(s, k, num);
-                }
+        for (long long k = gtid; k < HYB_LIM; k += gsize) A.dmin_bits[(size_t)node * HYB_LIM + k] = 0x7f7f7f7f7f7f7f7full;
+    }
+    if (blockIdx.x == 0) {
+        for (int a = tid; a < n_list; a += PERM_THREADS) A.act[a] = A.list[a];
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int a = 0; a < n_list; ++a) {
+                A.act_toff[a] = t;
+                const Node* nd = &A.nodes[A.list[a]];
+                t += (nd->hi - nd->lo + HYB_TP - 1) / HYB_TP;
             }
-        }
-    } else {
-        for (int s = threadIdx.x; s < count; s += 256) {
-            double acc = 0.0;
-            for (int k = 1; k <= kmax; ++k) {
-                acc = __dadd_rn(acc, s_t[s + k - 1]);
-                if (k >= al0) {
-                    const double num = __dmul_rn(acc, acc);
-                    if (num >= s_lim[k]) score(s, k, num);
-                }
-            }
+            A.act_toff[n_list] = t;
+            A.ctl->n_act = n_list;
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < 8; ++k) best = fmax(best, s_best[k]);
-        if (best > 0.0)
-            atomicMax(&pmax[(size_t)blockIdx.z * chunk + blockIdx.y], (unsigned long long)__double_as_longlong(best));
+    {   // first chunk's maxima buffer
+        const long long z = (long long)n_list * chunk_for(64, n_list, A.pm_entries, A.nperm);
+        for (long long k = gtid; k < z; k += gsize) A.pmax[k] = 0ull;
+    }
+    grid.sync();
+    // ---- phase 1: pruning limits (smallest arc denominators per width)
+    {
+        const int ntile = A.act_toff[n_list];
+        double (*s_min)[HYB_LIM] = reinterpret_cast<double (*)[HYB_LIM]>(s_t + HYB_TP + HYB_KMAX);
+        for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
+            const int a = find_slot(A.act_toff, n_list, t);
+            hyb_bounds_tile(A, A.act[a], (t - A.act_toff[a]) * HYB_TP, s_t, s_min);
+        }
+    }
+    grid.sync();
+    // ---- chunks of permutations
+    int p0 = 0, sched = 64, cur = 0, buf = 0;
+    for (;;) {
+        const int n_act = *((volatile int*)&A.ctl->n_act);
+        if (n_act == 0 || p0 >= A.nperm) break;
+        const int chunk = chunk_for(sched, n_act, A.pm_entries, A.nperm - p0);
+        const int* act = A.act + (size_t)cur * A.cap;
+        unsigned long long* pm = A.pmax + (size_t)buf * A.pm_entries;
+        unsigned long long* pm_next = A.pmax + (size_t)(buf ^ 1) * A.pm_entries;
+        const int ntile = A.act_toff[n_act];
+        const long long items = (long long)ntile * chunk;
+        for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+            const int t = (int)(it / chunk), c = (int)(it % chunk);
+            const int a = find_slot(A.act_toff, n_act, t);
+            hyb_tile<KMAX_T, AL0_T>(A, act[a], (t - A.act_toff[a]) * HYB_TP, p0 + c, s_t, s_lim, s_limhi, s_best,
+                                    pm + (size_t)a * chunk + c);
+        }
+        {   // zero the other buffer for the next chunk (the active list only shrinks)
+            const int nsched = min(sched * 4, PERM_CHUNK_MAX);
+            const long long z = (long long)n_act * chunk_for(nsched, n_act, A.pm_entries, A.nperm);
+            for (long long k = gtid; k < z && k < A.pm_entries; k += gsize) pm_next[k] = 0ull;
+        }
+        __threadfence();
+        grid.sync();
+        if (blockIdx.x == 0) perm_replay(A, pm, n_act, p0, chunk, cur, true, &s_cnt, s_warp);
+        __threadfence();
+        grid.sync();
+        p0 += chunk;
+        sched = min(sched * 4, PERM_CHUNK_MAX);
+        cur ^= 1;
+        buf ^= 1;
     }
 }
 
 // exact: all arcs of the permuted node (n <= EXACT_NMAX); one warp per (node, perm)
-__global__ void __launch_bounds__(128)
-cbs_perm_exact_kernel(const Node* __restrict__ nodes, const int* __restrict__ list, int p0,
-                      const double* __restrict__ y, const double* __restrict__ w_sqrt,
-                      const double* __restrict__ cw, u64 seed, int al0, unsigned long long* __restrict__ pmax,
-                      int chunk) {
+__global__ void __launch_bounds__(128, 4)
+cbs_perm_exact_kernel(PermArgs A) {
+    cg::grid_group grid = cg::this_grid();
     __shared__ double s_S[4][EXACT_NMAX + 1];
-    __shared__ double s_cw[EXACT_NMAX + 1];
-    const Node nd = nodes[list[blockIdx.y]];
-    const int n = nd.hi - nd.lo, lo = nd.lo;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int k = threadIdx.x; k <= n; k += 128) s_cw[k] = pt(cw, lo, k);
-    const int pidx = blockIdx.x * 4 + warp;
-    const bool live = pidx < chunk;
-    double* Sp = s_S[warp];
-    if (live) {
-        Prp prp;
-        prp.init(seed, (u32)(nd.lo - nd.base), (u32)(nd.hi - nd.base), 0u, (u32)(p0 + pidx), (u32)n);
-        for (int k = lane; k < n; k += 32) Sp[k + 1] = __dmul_rn(y[lo + prp((u32)k)], w_sqrt[lo + k]);
-        __syncwarp();
-        if (lane == 0) {
-            double run = 0.0;
-            Sp[0] = 0.0;
-            for (int k = 1; k <= n; ++k) {
-                run = __dadd_rn(run, Sp[k]);
-                Sp[k] = run;
-            }
-        }
+    __shared__ double s_cw[4][EXACT_NMAX + 1];
+    __shared__ int s_cnt, s_warp[PERM_THREADS / 32];
+    const int n_list = A.ctl->n_exact;
+    if (n_list == 0) return;                               // uniform over the grid
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + tid, gsize = (long long)gridDim.x * blockDim.x;
+    for (int li = 0; li < n_list; ++li) {
+        const Node* nd = &A.nodes[A.list[li]];
+        const int lo = nd->lo, hi = nd->hi;
+        const double avg = nd->avg;
+        for (long long g = lo + gtid; g < hi; g += gsize) A.y[g] = __dmul_rn(__dsub_rn(A.x[g], avg), A.rw[g]);
     }
-    __syncthreads();
-    if (!live) return;
-    const double total = nd.total;
-    double best = 0.0, bestlo = 0.0;
-    for (int i = lane; i <= n - al0; i += 32) {
-        const double Si = Sp[i], ci = s_cw[i];
-        const int jhi = min(n, i + (n - al0));
-        for (int j = i + al0; j <= jhi; ++j) {
-            const double d = __dsub_rn(Sp[j], Si);
-            const double c = __dsub_rn(s_cw[j], ci);
-            const double den = __dmul_rn(c, __dsub_rn(total, c));
-            const double num = __dmul_rn(d, d);
-            if (num > __dmul_rn(bestlo, den)) {
-                const double q = __ddiv_rn(num, den);
-                if (q > best) { best = q; bestlo = q * (1.0 - 1e-12); }
-            }
-        }
+    if (blockIdx.x == 0) {
+        for (int a = tid; a < n_list; a += blockDim.x) A.act[a] = A.list[a];
+        if (tid == 0) A.ctl->n_act = n_list;
     }
+    __threadfence();
+    grid.sync();
+    int p0 = 0, sched = 64, cur = 0;
+    for (;;) {
+        const int n_act = *((volatile int*)&A.ctl->n_act);
+        if (n_act == 0 || p0 >= A.nperm) break;
+        const int chunk = chunk_for(sched, n_act, A.pm_entries, A.nperm - p0);
+        const int* act = A.act + (size_t)cur * A.cap;
+        const long long items = (long long)n_act * chunk;
+        const long long gw = (long long)blockIdx.x * 4 + warp, nw = (long long)gridDim.x * 4;
+        for (long long it = gw; it < items; it += nw) {
+            const int a = (int)(it / chunk), c = (int)(it % chunk);
+            const Node nd = A.nodes[act[a]];
+            const int n = nd.hi - nd.lo, lo = nd.lo;
+            double* Sp = s_S[warp];
+            double* Cp = s_cw[warp];
+            Prp prp;
+            prp.init(A.seed, (u32)(nd.lo - nd.base), (u32)(nd.hi - nd.base), 0u, (u32)(p0 + c), (u32)n);
+            for (int k = lane; k <= n; k += 32) Cp[k] = pt(A.cw, lo, k);
+            for (int k = lane; k < n; k += 32) Sp[k + 1] = __dmul_rn(A.y[lo + prp((u32)k)], A.rw[lo + k]);
+            __syncwarp();
+            if (lane == 0) {
+                double run = 0.0;
+                Sp[0] = 0.0;
+                for (int k = 1; k <= n; ++k) {
+                    run = __dadd_rn(run, Sp[k]);
+                    Sp[k] = run;
+                }
+            }
+            __syncwarp();
+            const double total = nd.total;
+            const int al0 = A.al0;
+            double best = 0.0, bestlo = 0.0;
+            for (int i = lane; i <= n - al0; i += 32) {
+                const double Si = Sp[i], ci = Cp[i];
+                const int jhi = min(n, i + (n - al0));
+                for (int j = i + al0; j <= jhi; ++j) {
+                    const double d = __dsub_rn(Sp[j], Si);
+                    const double cc = __dsub_rn(Cp[j], ci);
+                    const double den = __dmul_rn(cc, __dsub_rn(total, cc));
+                    const double num = __dmul_rn(d, d);
+                    if (num > __dmul_rn(bestlo, den)) {
+                        const double q = __ddiv_rn(num, den);
+                        if (q > best) { best = q; bestlo = q * (1.0 - 1e-12); }
+                    }
+                }
+            }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if (lane == 0) pmax[(size_t)blockIdx.y * chunk + pidx] = (unsigned long long)__double_as_longlong(best);
-}
-
-// exceedance flags: ostat <= T^2(pmax)
-__global__ void cbs_perm_flags_kernel(const Node* __restrict__ nodes, const int* __restrict__ list, int nlist,
-                                      const unsigned long long* __restrict__ pmax, int chunk,
-                                      unsigned char* __restrict__ flags) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nlist * chunk) return;
-    const Node* nd = &nodes[list[k / chunk]];
-    const double pb = __longlong_as_double((long long)pmax[k]);
-    const double pstat = t2_of(pb, nd->tss, nd->hi - nd->lo);
-    flags[k] = (nd->ostat <= pstat) ? 1 : 0;
+            for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (lane == 0) A.pmax[(size_t)a * chunk + c] = (unsigned long long)__double_as_longlong(best);
+            __syncwarp();
+        }
+        __threadfence();
+        grid.sync();
+        if (blockIdx.x == 0) perm_replay(A, A.pmax, n_act, p0, chunk, cur, false, &s_cnt, s_warp);
+        __threadfence();
+        grid.sync();
+        p0 += chunk;
+        sched = min(sched * 4, PERM_CHUNK_MAX);
+        cur ^= 1;
+    }
 }
 
 // ------------------------------------------------------------------------------------ flank tests
@@ -1396,113 +1732,315 @@ __global__ void cbs_perm_flags_kernel(const Node* __restrict__ nodes, const int*
 // then one thread per test combines the partials left to right -- deterministic, thresholds only
 static const int FLANK_SPLIT = 16;
 
+// single CTA: the split nodes whose maximal arc is interior get two tests each (node order)
+__global__ void __launch_bounds__(1024)
+cbs_flank_list_kernel(Node* __restrict__ nodes, int nnodes, FlankTest* __restrict__ tests, int* __restrict__ tmp,
+                      Ctl* __restrict__ ctl) {
+    __shared__ int s_warp[32];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int base = 0; base < nnodes; base += 1024) {
+        const int idx = base + threadIdx.x;
+        bool want = false;
+        if (idx < nnodes) {
+            const Node* nd = &nodes[idx];
+            const int n = nd->hi - nd->lo;
+            want = nd->state == ST_SPLIT && !(nd->best_j == n || nd->best_i == 0);
+        }
+        const int before = s_n;
+        block_append(want, idx, tmp, &s_n, s_warp, 32);
+        const int after = s_n;
+        // tmp[before..after) holds the nodes of this round in node order: rank r -> tests 2r, 2r+1
+        for (int r = before + threadIdx.x; r < after; r += 1024) {
+            Node* nd = &nodes[tmp[r]];
+            const int n = nd->hi - nd->lo, ai = nd->best_i, aj = nd->best_j;
+            FlankTest f;
+            memset(&f, 0, sizeof(f));
+            f.node = tmp[r]; f.off = 0; f.n1 = ai; f.n2 = aj - ai; f.tid = 1; f.pvalue = -1.0;
+            tests[2 * r] = f;
+            f.off = ai; f.n1 = aj - ai; f.n2 = n - aj; f.tid = 2;
+            tests[2 * r + 1] = f;
+            nd->flank = 2 * r;
+        }
+        if (idx < nnodes && !want) nodes[idx].flank = -1;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { ctl->n_flank = 2 * s_n; ctl->n_fperm = 0; }
+}
+
 __global__ void __launch_bounds__(256)
-cbs_flank_part_kernel(const Node* __restrict__ nodes, const FlankTest* __restrict__ tests,
-                      const double* __restrict__ xc, const double* __restrict__ w, double* __restrict__ part) {
+cbs_flank_part_kernel(const Node* __restrict__ nodes, const FlankTest* __restrict__ tests, const Ctl* __restrict__ ctl,
+                      const double* __restrict__ x, const double* __restrict__ w, double* __restrict__ part) {
     __shared__ double s_part[5][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x, sp = blockIdx.y;
-    const FlankTest ft = tests[idx];
-    const Node* nd = &nodes[ft.node];
-    const int g0 = nd->lo + ft.off;
-    const int n1 = ft.n1, n = ft.n1 + ft.n2;
-    const int chunk = (n + FLANK_SPLIT - 1) / FLANK_SPLIT;
-    const int k0 = sp * chunk, k1 = min(n, k0 + chunk);
-    double xs1 = 0, xs2 = 0, tss = 0, rn1 = 0, rn2 = 0;
-    for (int k = k0 + threadIdx.x; k < k1; k += 256) {
-        const double xv = xc[g0 + k], wv = w[g0 + k];
-        const double wx = wv * xv;
-        tss += wv * (xv * xv);
-        if (k < n1) { xs1 += wx; rn1 += wv; } else { xs2 += wx; rn2 += wv; }
-    }
-    xs1 = warp_sum(xs1); xs2 = warp_sum(xs2); tss = warp_sum(tss); rn1 = warp_sum(rn1); rn2 = warp_sum(rn2);
-    if (lane == 0) { s_part[0][warp] = xs1; s_part[1][warp] = xs2; s_part[2][warp] = tss; s_part[3][warp] = rn1; s_part[4][warp] = rn2; }
-    __syncthreads();
-    if (threadIdx.x < 5) {
-        double v = 0.0;
-        for (int k = 0; k < 8; ++k) v += s_part[threadIdx.x][k];
-        part[((size_t)idx * FLANK_SPLIT + sp) * 5 + threadIdx.x] = v;
+    const int items = ctl->n_flank * FLANK_SPLIT;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int idx = it / FLANK_SPLIT, sp = it % FLANK_SPLIT;
+        const FlankTest ft = tests[idx];
+        const Node* nd = &nodes[ft.node];
+        const double avg = nd->avg;
+        const int g0 = nd->lo + ft.off;
+        const int n1 = ft.n1, n = ft.n1 + ft.n2;
+        const int chunk = (n + FLANK_SPLIT - 1) / FLANK_SPLIT;
+        const int k0 = sp * chunk, k1 = min(n, k0 + chunk);
+        double xs1 = 0, xs2 = 0, tss = 0, rn1 = 0, rn2 = 0;
+        for (int k = k0 + threadIdx.x; k < k1; k += 256) {
+            const double xv = __dsub_rn(x[g0 + k], avg), wv = w[g0 + k];
+            const double wx = wv * xv;
+            tss += wv * (xv * xv);
+            if (k < n1) { xs1 += wx; rn1 += wv; } else { xs2 += wx; rn2 += wv; }
+        }
+        xs1 = warp_sum(xs1); xs2 = warp_sum(xs2); tss = warp_sum(tss); rn1 = warp_sum(rn1); rn2 = warp_sum(rn2);
+        if (lane == 0) { s_part[0][warp] = xs1; s_part[1][warp] = xs2; s_part[2][warp] = tss; s_part[3][warp] = rn1; s_part[4][warp] = rn2; }
+        __syncthreads();
+        if (threadIdx.x < 5) {
+            double v = 0.0;
+            for (int k = 0; k < 8; ++k) v += s_part[threadIdx.x][k];
+            part[((size_t)idx * FLANK_SPLIT + sp) * 5 + threadIdx.x] = v;
+        }
+        __syncthreads();
     }
 }
 
-__global__ void cbs_flank_prep_kernel(FlankTest* __restrict__ tests, int ntests, const double* __restrict__ part,
-                                      int force_perm) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= ntests) return;
-    FlankTest* o = &tests[idx];
-    const int n1 = o->n1, n2 = o->n2, n = n1 + n2;
-    if (n1 == 1 || n2 == 1) { o->pvalue = 1.0; o->need_perm = 0; return; }
-    double xs1 = 0, xs2 = 0, tss = 0, rn1 = 0, rn2 = 0;
-    for (int sp = 0; sp < FLANK_SPLIT; ++sp) {
-        const double* q = part + ((size_t)idx * FLANK_SPLIT + sp) * 5;
-        xs1 += q[0]; xs2 += q[1]; tss += q[2]; rn1 += q[3]; rn2 += q[4];
+__global__ void cbs_flank_prep_kernel(FlankTest* __restrict__ tests, Ctl* __restrict__ ctl, const double* __restrict__ part,
+                                      int* __restrict__ fperm_list, int force_perm) {
+    const int ntests = ctl->n_flank;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ntests; idx += gridDim.x * blockDim.x) {
+        FlankTest* o = &tests[idx];
+        const int n1 = o->n1, n2 = o->n2, n = n1 + n2;
+        if (n1 == 1 || n2 == 1) { o->pvalue = 1.0; o->need_perm = 0; continue; }
+        double xs1 = 0, xs2 = 0, tss = 0, rn1 = 0, rn2 = 0;
+        for (int sp = 0; sp < FLANK_SPLIT; ++sp) {
+            const double* q = part + ((size_t)idx * FLANK_SPLIT + sp) * 5;
+            xs1 += q[0]; xs2 += q[1]; tss += q[2]; rn1 += q[3]; rn2 += q[4];
+        }
+        const double rn = rn1 + rn2;
+        const double xbar = (xs1 + xs2) / rn;
+        tss = tss - rn * (xbar * xbar);
+        int m1, s0;
+        double rm1, odiff;
+        if (n1 <= n2) { m1 = n1; s0 = 0; rm1 = rn1; odiff = fabs(xs1 / rn1 - xbar); }
+        else { m1 = n2; s0 = n1; rm1 = rn2; odiff = fabs(xs2 / rn2 - xbar); }
+        double tstat = rn * rm1 * (odiff * odiff) / (rn - rm1);
+        tstat = tstat / ((tss - tstat) / ((double)n - 2.0));
+        o->m1 = m1; o->s0 = s0; o->rm1 = rm1; o->xbar = xbar; o->ostat = 0.99999 * odiff;
+        o->nrej = 0;
+        if (tstat > 25.0 && m1 >= 10 && !force_perm) { o->pvalue = 0.0; o->need_perm = 0; }
+        else {
+            o->pvalue = -1.0; o->need_perm = 1;
+            fperm_list[atomicAdd(&ctl->n_fperm, 1)] = idx;
+            atomicAdd(&ctl->stats[6], 1ull);
+        }
     }
-    const double rn = rn1 + rn2;
-    const double xbar = (xs1 + xs2) / rn;
-    tss = tss - rn * (xbar * xbar);
-    int m1, s0;
-    double rm1, odiff;
-    if (n1 <= n2) { m1 = n1; s0 = 0; rm1 = rn1; odiff = fabs(xs1 / rn1 - xbar); }
-    else { m1 = n2; s0 = n1; rm1 = rn2; odiff = fabs(xs2 / rn2 - xbar); }
-    double tstat = rn * rm1 * (odiff * odiff) / (rn - rm1);
-    tstat = tstat / ((tss - tstat) / ((double)n - 2.0));
-    o->m1 = m1; o->s0 = s0; o->rm1 = rm1; o->xbar = xbar; o->ostat = 0.99999 * odiff;
-    if (tstat > 25.0 && m1 >= 10 && !force_perm) { o->pvalue = 0.0; o->need_perm = 0; }
-    else { o->pvalue = -1.0; o->need_perm = 1; }
 }
 
-// one warp per (test, perm): pstat = |sum_{short side} y[pi(k)] rw[k] / rm1 - xbar|
+// persistent: one warp per (listed test, perm): pstat = |sum_{short side} y[pi(k)] rw[k] / rm1 - xbar|
 __global__ void __launch_bounds__(128)
-cbs_flank_perm_kernel(const Node* __restrict__ nodes, const FlankTest* __restrict__ tests,
-                      const int* __restrict__ list, int nperm, const double* __restrict__ xc,
-                      const double* __restrict__ w_sqrt, u64 seed, int* __restrict__ nrej) {
+cbs_flank_perm_kernel(const Node* __restrict__ nodes, FlankTest* __restrict__ tests, const int* __restrict__ fperm_list,
+                      const Ctl* __restrict__ ctl, int nperm, const double* __restrict__ x,
+                      const double* __restrict__ w_sqrt, u64 seed) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int perm = blockIdx.x * 4 + warp;
-    if (perm >= nperm) return;
-    const FlankTest ft = tests[list[blockIdx.y]];
-    const Node* nd = &nodes[ft.node];
-    const int g0 = nd->lo + ft.off;
-    const int n = ft.n1 + ft.n2;
-    Prp prp;
-    prp.init(seed, (u32)(nd->lo - nd->base), (u32)(nd->hi - nd->base), (u32)ft.tid, (u32)perm, (u32)n);
-    double xs = 0.0;
-    for (int k = lane; k < ft.m1; k += 32) {
-        const int src = g0 + (int)prp((u32)(ft.s0 + k));
-        xs += (xc[src] * w_sqrt[src]) * w_sqrt[g0 + ft.s0 + k];
-    }
-    xs = warp_sum(xs);
-    if (lane == 0) {
-        const double pstat = fabs(xs / ft.rm1 - ft.xbar);
-        if (ft.ostat <= pstat) atomicAdd(&nrej[blockIdx.y], 1);
+    const int nlist = ctl->n_fperm;
+    const int groups = (nperm + 3) / 4;
+    const long long items = (long long)nlist * groups;
+    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+        const int li = (int)(it / groups), perm = (int)(it % groups) * 4 + warp;
+        if (perm >= nperm) continue;
+        const int t = fperm_list[li];
+        const FlankTest ft = tests[t];
+        const Node* nd = &nodes[ft.node];
+        const double avg = nd->avg;
+        const int g0 = nd->lo + ft.off;
+        const int n = ft.n1 + ft.n2;
+        Prp prp;
+        prp.init(seed, (u32)(nd->lo - nd->base), (u32)(nd->hi - nd->base), (u32)ft.tid, (u32)perm, (u32)n);
+        double xs = 0.0;
+        for (int k = lane; k < ft.m1; k += 32) {
+            const int src = g0 + (int)prp((u32)(ft.s0 + k));
+            xs += (__dsub_rn(x[src], avg) * w_sqrt[src]) * w_sqrt[g0 + ft.s0 + k];
+        }
+        xs = warp_sum(xs);
+        if (lane == 0) {
+            const double pstat = fabs(xs / ft.rm1 - ft.xbar);
+            if (ft.ostat <= pstat) atomicAdd(&tests[t].nrej, 1);
+        }
     }
 }
 
-// ------------------------------------------------------------------------------------ misc kernels
+// ------------------------------------------------------------------------------------ frontier
+__device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int* total) {
+    // exclusive prefix of v over the CTA's threads (1024 threads); *total = sum
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int wv = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wv, o);
+            if (lane >= o) wv += t;
+        }
+        s_warp[lane] = wv;
+    }
+    __syncthreads();
+    const int base = warp ? s_warp[warp - 1] : 0;
+    *total = s_warp[31];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__host__ __device__ __forceinline__ long long node_qtiles(int n) {
+    const long long P = (long long)n + 1;
+    const long long NJ = (P + CBS_BLK - 1) / CBS_BLK, NI = (P + CBS_IBLK - 1) / CBS_IBLK;
+    long long K = (NJ + CBS_IW - 1) / CBS_IW;
+    if (K > NI) K = NI;
+    return K * NJ - CBS_IW * (K * (K - 1) / 2);
+}
+
+// single CTA: ternary-split bookkeeping (changepoints()): the pieces of every node, long ones -> next level's
+// node table (node order kept), short or unsplit ones -> final segment records of this level.  Idempotent: reads
+// the current level, writes the next one -- the host reruns it after growing a buffer that overflowed.
+__global__ void __launch_bounds__(1024)
+cbs_frontier_kernel(const Node* __restrict__ nodes, int nnodes, const FlankTest* __restrict__ tests, double alpha,
+                    int nperm, int min_width, Node* __restrict__ next, int cap_nodes, LevelOut* __restrict__ out,
+                    int* __restrict__ extra_lo, int* __restrict__ extra_hi, int cap_extra) {
+    __shared__ int s_warp[32];
+    __shared__ int s_child, s_seg, s_pt, s_bk, s_ib;
+    __shared__ long long s_qt, s_bins;
+    if (threadIdx.x == 0) { s_child = 0; s_seg = 0; s_pt = 0; s_bk = 0; s_ib = 0; s_qt = 0; s_bins = 0; }
+    __syncthreads();
+    for (int base = 0; base < nnodes; base += 1024) {
+        const int idx = base + threadIdx.x;
+        int cut[4] = {0, 0, 0, 0}, npieces = 0, nbase = 0;
+        if (idx < nnodes) {
+            const Node* nd = &nodes[idx];
+            const int n = nd->hi - nd->lo;
+            nbase = nd->base;
+            int ncpt = 0, icpt[2] = {0, 0};
+            if (nd->state == ST_SPLIT) {
+                const int ai = nd->best_i, aj = nd->best_j;
+                if (aj == n) { ncpt = 1; icpt[0] = ai; }
+                else if (ai == 0) { ncpt = 1; icpt[0] = aj; }
+                else {
+                    double pv[2];
+                    for (int t = 0; t < 2; ++t) {
+                        const FlankTest* ft = &tests[nd->flank + t];
+                        pv[t] = ft->need_perm ? (double)ft->nrej / (double)nperm : ft->pvalue;
+                    }
+                    if (pv[0] <= alpha) { ncpt = 1; icpt[0] = ai; }
+                    if (pv[1] <= alpha) { icpt[ncpt] = aj; ++ncpt; }
+                    if (ncpt == 0) { ncpt = 2; icpt[0] = ai; icpt[1] = aj; }
+                }
+            }
+            npieces = ncpt + 1;
+            cut[0] = nd->lo;
+            cut[1] = ncpt >= 1 ? nd->lo + icpt[0] : nd->hi;
+            cut[2] = ncpt == 2 ? nd->lo + icpt[1] : nd->hi;
+            cut[3] = nd->hi;
+            cut[npieces] = nd->hi;
+        }
+        int nchild = 0, nseg = 0, pt_ = 0, bk = 0, ibk = 0;
+        long long qt = 0, cb = 0;
+        for (int c = 0; c < npieces; ++c) {
+            const int len = cut[c + 1] - cut[c];
+            if (len >= 2 * min_width && npieces > 1) {
+                ++nchild;
+                pt_ += (len + 1 + PREP_TILE - 1) / PREP_TILE;
+                bk += (len + 1 + CBS_BLK - 1) / CBS_BLK;
+                ibk += (len + 1 + CBS_IBLK - 1) / CBS_IBLK;
+                qt += node_qtiles(len);
+                cb += len;
+            } else {
+                ++nseg;
+            }
+        }
+        int tot;
+        const int o_child = s_child + block_excl_scan(nchild, s_warp, &tot); const int t_child = tot;
+        const int o_seg = s_seg + block_excl_scan(nseg, s_warp, &tot); const int t_seg = tot;
+        const int o_pt = s_pt + block_excl_scan(pt_, s_warp, &tot); const int t_pt = tot;
+        const int o_bk = s_bk + block_excl_scan(bk, s_warp, &tot); const int t_bk = tot;
+        const int o_ib = s_ib + block_excl_scan(ibk, s_warp, &tot); const int t_ib = tot;
+        // long long reduction of the queue bound
+        for (int o = 16; o > 0; o >>= 1) { qt += __shfl_xor_sync(0xffffffffu, qt, o); cb += __shfl_xor_sync(0xffffffffu, cb, o); }
+        if ((threadIdx.x & 31) == 0 && cb) {
+            atomicAdd((unsigned long long*)&s_qt, (unsigned long long)qt);
+            atomicAdd((unsigned long long*)&s_bins, (unsigned long long)cb);
+        }
+        int ci = o_child, si = o_seg, pi = o_pt, bi = o_bk, ii = o_ib;
+        for (int c = 0; c < npieces; ++c) {
+            const int a0 = cut[c], a1 = cut[c + 1], len = a1 - a0;
+            if (len >= 2 * min_width && npieces > 1) {
+                if (ci < cap_nodes) {
+                    Node nn_;
+                    memset(&nn_, 0, sizeof(Node));
+                    nn_.lo = a0; nn_.hi = a1; nn_.base = nbase;
+                    nn_.best_q = -1.0; nn_.best_i = 0x7fffffff; nn_.best_j = 0x7fffffff;
+                    nn_.tailp = -1.0; nn_.flank = -1;
+                    nn_.ptile_off = pi; nn_.blk_off = bi; nn_.iblk_off = ii;
+                    next[ci] = nn_;
+                }
+                ++ci;
+                pi += (len + 1 + PREP_TILE - 1) / PREP_TILE;
+                bi += (len + 1 + CBS_BLK - 1) / CBS_BLK;
+                ii += (len + 1 + CBS_IBLK - 1) / CBS_IBLK;
+            } else {
+                if (si < SEG_WINDOW) { out->seg_lo[si] = a0; out->seg_hi[si] = a1; }
+                else if (si - SEG_WINDOW < cap_extra) { extra_lo[si - SEG_WINDOW] = a0; extra_hi[si - SEG_WINDOW] = a1; }
+                ++si;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_child += t_child; s_seg += t_seg; s_pt += t_pt; s_bk += t_bk; s_ib += t_ib; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        Ctl* c = &out->ctl;
+        c->nn_next = s_child; c->ptiles_next = s_pt; c->nblk_next = s_bk; c->niblk_next = s_ib;
+        c->qtiles_next = s_qt;
+        c->bins_next = s_bins;
+        c->nseg_new = s_seg;
+        c->overflow = (s_child > cap_nodes ? 1 : 0) | (s_seg > SEG_WINDOW + cap_extra ? 2 : 0);
+    }
+}
+
+// weighted.mean(log2, weight) per new segment (cbs.py:70-71); one CTA per segment, grid-stride
+__global__ void __launch_bounds__(256)
+seg_mean_kernel(const double* __restrict__ x, const double* __restrict__ w, LevelOut* __restrict__ out,
+                const int* __restrict__ extra_lo, const int* __restrict__ extra_hi, double* __restrict__ extra_mean) {
+    __shared__ double s_a[8], s_b[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nseg = out->ctl.overflow ? 0 : out->ctl.nseg_new;
+    for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+        const int lo = s < SEG_WINDOW ? out->seg_lo[s] : extra_lo[s - SEG_WINDOW];
+        const int hi = s < SEG_WINDOW ? out->seg_hi[s] : extra_hi[s - SEG_WINDOW];
+        double sw = 0.0, swx = 0.0;
+        for (int k = lo + threadIdx.x; k < hi; k += 256) {
+            sw += w[k];
+            swx += x[k] * w[k];
+        }
+        sw = warp_sum(sw);
+        swx = warp_sum(swx);
+        if (lane == 0) { s_a[warp] = sw; s_b[warp] = swx; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < 8; ++k) { sw += s_a[k]; swx += s_b[k]; }
+            const double m = swx / sw;
+            if (s < SEG_WINDOW) out->seg_mean[s] = m; else extra_mean[s - SEG_WINDOW] = m;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void sqrt_kernel(const double* __restrict__ w, double* __restrict__ out, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = sqrt(w[i]);
-}
-
-// weighted.mean(log2, weight) per segment (cbs.py:70-71); one CTA per segment
-__global__ void __launch_bounds__(1024)
-seg_mean_kernel(const double* __restrict__ x, const double* __restrict__ w, const long long* __restrict__ lo,
-                const long long* __restrict__ hi, int nseg, double* __restrict__ mean) {
-    __shared__ double s_a[32], s_b[32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x;
-    double sw = 0.0, swx = 0.0;
-    for (long long k = lo[s] + threadIdx.x; k < hi[s]; k += 1024) {
-        sw += w[k];
-        swx += x[k] * w[k];
-    }
-    sw = warp_sum(sw);
-    swx = warp_sum(swx);
-    if (lane == 0) { s_a[warp] = sw; s_b[warp] = swx; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < 32; ++k) { sw += s_a[k]; swx += s_b[k]; }
-        mean[s] = swx / sw;
-    }
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -1568,9 +2106,7 @@ void cbs_getbdry(double eta, int nperm, int max_ones, std::vector<int>& out) {
     }
 }
 
-// Pinned staging memory for the small per-level host<->device copies (node tables, decisions, flags):
-// copies from pageable std::vector storage go through the driver's own staging buffer and cost ~10 us
-// each, which adds up over ~10 copies per recursion level.  Chunks persist per thread across calls.
+// Pinned staging memory for the small host<->device copies (first node table, level records).
 struct PinnedArena {
     struct Chunk { char* p; size_t cap; };
     std::vector<Chunk> chunks;
@@ -1604,24 +2140,45 @@ static thread_local PinnedArena g_pinned;
         if (!(ptr)) { set_last_error("cbs_segment: pinned staging allocation failed"); return (int)cudaErrorMemoryAllocation; } \
     } while (0)
 
+// stream-ordered device buffer that grows (contents are not preserved)
+template <typename T>
+struct Grow {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaStream_t s = nullptr;
+    bool zero = false;            // memset new allocations to 0
+    ~Grow() { if (p) cudaFreeAsync(p, s); }
+    cudaError_t ensure(size_t need, cudaStream_t stream) {
+        s = stream;
+        if (need <= cap) return cudaSuccess;
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        cap = need + need / 2 + 16;
+        cudaError_t e = cudaMallocAsync((void**)&p, cap * sizeof(T), s);
+        if (e != cudaSuccess) { cap = 0; return e; }
+        if (zero) e = cudaMemsetAsync(p, 0, cap * sizeof(T), s);
+        return e;
+    }
+};
+
 struct HostNode {
     int lo, hi, base, arm;
 };
 
-// tasks (CTAs of the seed / bound kernels) and 1024x256 tiles of a node of n bins
-static void tiles_for(int n, int node, std::vector<int4>* table, long long* tasks, long long* tiles) {
-    const int P = n + 1;
-    const int NJ = (P + CBS_BLK - 1) / CBS_BLK, NI = (P + CBS_IBLK - 1) / CBS_IBLK;
-    long long t = 0, q = 0;
-    for (int ib = 0; ib < NI; ++ib) {
-        const int m = std::max(0, NJ - CBS_IW * ib);
-        const int chunks = (m + 255) / 256;
-        for (int c = 0; c < chunks; ++c) table->push_back(make_int4(node, ib, CBS_IW * ib + 256 * c, NJ));
-        t += chunks;
-        q += m;
+static bool tiles_overflow(long long ptiles, long long blks, long long iblks, long long qtiles) {
+    if (ptiles >= (1ll << 31) || blks >= (1ll << 31) || iblks >= (1ll << 31) || qtiles >= (1ll << 31)) {
+        set_last_error("cbs_segment: tile count overflow");
+        return true;
     }
-    *tasks = t;
-    *tiles = q;
+    return false;
+}
+
+static int coop_grid(const void* fn, int threads, int sm_count, int* cache) {
+    if (*cache > 0) return *cache;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    *cache = per_sm * sm_count;
+    return *cache;
 }
 
 int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, const CbsParams& P_in,
@@ -1635,17 +2192,18 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
     memset(&st, 0, sizeof(st));
     if (n_arms <= 0) { if (stats) *stats = st; return 0; }
     const long long N = h_off[n_arms];
-    if (N >= (1ll << 31)) { set_last_error("cbs_segment: too many bins (%lld)", N); return -2; }
+    if (N >= (1ll << 31) - 4) { set_last_error("cbs_segment: too many bins (%lld)", N); return -2; }
     if (P.kmax > HYB_KMAX || P.nmin > EXACT_NMAX || P.min_width < 2 || P.kmax < P.min_width || P.nperm < 1) {
         set_last_error("cbs_segment: unsupported parameters (kmax<=%d, nmin<=%d, min_width>=2)", HYB_KMAX, EXACT_NMAX);
         return -2;
     }
     if (P.nmin < 2 * P.kmax) { set_last_error("cbs_segment: need nmin >= 2*kmax"); return -2; }
-    int sm_count = 148;
-    {
+    static thread_local int sm_count = 0, grid_hyb25 = 0, grid_hyb0 = 0, grid_exact = 0;
+    if (!sm_count) {
         int dev = 0;
         CNVK_CHECK(cudaGetDevice(&dev));
         CNVK_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        CNVK_CHECK(cudaFuncSetAttribute(cbs_prep_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM));
     }
     const int max_ones = (int)std::floor((double)P.nperm * P.alpha) + 1;
     // the stopping boundary depends on (eta, nperm, max.ones) only and costs ~nperm * max.ones * 20 flops to
@@ -1658,492 +2216,318 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         sb_eta = P.eta; sb_nperm = P.nperm; sb_ones = max_ones;
     }
 
+    g_pinned.rewind();
     Scratch scratch(stream);
-    double *d_rw, *d_xc, *d_y, *d_S, *d_cw, *d_wn, *d_bmin, *d_bmax, *d_Sl, *d_cwl;
-    const size_t NB = (size_t)(N / CBS_BLK) + 2 * (size_t)n_arms + 2 * (size_t)N / 4 + 16;  // >= sum ceil((n+1)/256)
+    double *d_rw, *d_y, *d_S, *d_cw, *d_wn;
+    int* d_sbdry;
+    LevelOut* d_out;
     CNVK_CHECK(scratch.alloc(&d_rw, (size_t)N));
-    CNVK_CHECK(scratch.alloc(&d_xc, (size_t)N));
     CNVK_CHECK(scratch.alloc(&d_y, (size_t)N));
-    CNVK_CHECK(scratch.alloc(&d_S, (size_t)N));
-    CNVK_CHECK(scratch.alloc(&d_cw, (size_t)N));
     CNVK_CHECK(scratch.alloc(&d_wn, (size_t)N));
-    CNVK_CHECK(scratch.alloc(&d_Sl, (size_t)N));    // tile-local prefix sums (before the carries)
-    CNVK_CHECK(scratch.alloc(&d_cwl, (size_t)N));
-    CNVK_CHECK(scratch.alloc(&d_bmin, NB));
-    CNVK_CHECK(scratch.alloc(&d_bmax, NB));
-    int *d_bimin, *d_bimax;
-    double *d_bcmin, *d_bcmax;
-    CNVK_CHECK(scratch.alloc(&d_bimin, NB));
-    CNVK_CHECK(scratch.alloc(&d_bimax, NB));
-    CNVK_CHECK(scratch.alloc(&d_bcmin, NB));
-    CNVK_CHECK(scratch.alloc(&d_bcmax, NB));
+    CNVK_CHECK(scratch.alloc(&d_S, (size_t)N + 4));      // + slack: the band kernel's bulk copies are widened to 16 B
+    CNVK_CHECK(scratch.alloc(&d_cw, (size_t)N + 4));
+    CNVK_CHECK(scratch.alloc(&d_sbdry, sbdry.size()));
+    CNVK_CHECK(scratch.alloc(&d_out, 1));
+    {
+        int* p_sb = g_pinned.put(sbdry.data(), sbdry.size());
+        CNVK_PIN_CHECK(p_sb);
+        CNVK_CHECK(cudaMemcpyAsync(d_sbdry, p_sb, sbdry.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    }
+    CNVK_CHECK(cudaMemsetAsync(d_out, 0, sizeof(Ctl), stream));
     if (N > 0) {
         sqrt_kernel<<<div_up(N, 256), 256, 0, stream>>>(d_w, d_rw, N);
         CNVK_LAUNCH_CHECK();
     }
-    int* d_counter;  // [0] tiles queued, [1] tiles popped
-    unsigned long long* d_stats;
-    CNVK_CHECK(scratch.alloc(&d_counter, 2));
-    CNVK_CHECK(scratch.alloc(&d_stats, 3));  // [0] 256x256 sub-tiles scanned, [1] tested, [2] 32x32 band pairs scanned
-    CNVK_CHECK(cudaMemsetAsync(d_stats, 0, 3 * sizeof(unsigned long long), stream));
+    Ctl* d_ctl = &d_out->ctl;
+    unsigned long long* d_stats = d_ctl->stats;
 
-    std::vector<HostNode> frontier;
-    std::vector<std::vector<int>> ends(n_arms);
+    // ---- level 1: the arms (host-built; every later level comes from the frontier kernel)
+    std::vector<Node> h_nodes;
+    std::vector<CbsSeg> done;       // final segments as they arrive (any order; sorted at the end)
+    long long blk_off = 0, ptiles = 0, iblks = 0, qtiles = 0;
     for (int a = 0; a < n_arms; ++a) {
         const int lo = (int)h_off[a], hi = (int)h_off[a + 1];
         if (hi <= lo) continue;
-        if (hi - lo >= 2 * P.min_width) frontier.push_back({lo, hi, lo, a});
-        else ends[a].push_back(hi);
-    }
-
-    // growable device buffers for per-level arrays
-    size_t cap_nodes = 0, cap_queue = 0, cap_ptiles = 0;
-    TileRef* d_queue = nullptr;
-    TileSums* d_part1 = nullptr;
-    TileScan* d_part3 = nullptr;
-    int* d_ptile_off = nullptr;
-    std::vector<int> h_ptile_off;
-    std::vector<int4> h_task_tab;
-    int4* d_task_tab = nullptr;
-    SeedRes* d_seedres = nullptr;
-    int* d_task_off = nullptr;
-    size_t cap_tasks = 0, cap_task_off = 0;
-    struct TaskGuard { int4*& p; SeedRes*& r; int*& o; cudaStream_t s; ~TaskGuard() { if (p) cudaFreeAsync(p, s); if (r) cudaFreeAsync(r, s); if (o) cudaFreeAsync(o, s); } } tguard{d_task_tab, d_seedres, d_task_off, stream};
-    struct PartGuard { TileSums*& a; TileScan*& b; cudaStream_t s; ~PartGuard() { if (a) cudaFreeAsync(a, s); if (b) cudaFreeAsync(b, s); } } pguard{d_part1, d_part3, stream};
-    Node* d_nodes = nullptr;
-    Decision* d_dec = nullptr;
-    double* d_terms = nullptr;
-    struct QueueGuard { TileRef*& q; cudaStream_t s; ~QueueGuard() { if (q) cudaFreeAsync(q, s); } } qguard{d_queue, stream};
-    auto free_level = [&]() {
-        if (d_terms) cudaFreeAsync(d_terms, stream);
-        d_terms = nullptr;
-        if (d_nodes) cudaFreeAsync(d_nodes, stream);
-        if (d_dec) cudaFreeAsync(d_dec, stream);
-        if (d_ptile_off) cudaFreeAsync(d_ptile_off, stream);
-        d_nodes = nullptr; d_dec = nullptr; d_ptile_off = nullptr;
-    };
-    struct Guard { decltype(free_level)& f; ~Guard() { f(); } } guard{free_level};
-
-    std::vector<Node> h_nodes;
-    std::vector<Decision> h_dec;
-    std::vector<int> h_tile_off;
-
-    while (!frontier.empty()) {
-        st.levels++;
-        const int nn = (int)frontier.size();
-        st.nodes += nn;
-        if ((size_t)nn > cap_nodes) {
-            free_level();
-            cap_nodes = (size_t)nn * 2;
-            CNVK_CHECK(cudaMallocAsync((void**)&d_nodes, cap_nodes * sizeof(Node), stream));
-            CNVK_CHECK(cudaMallocAsync((void**)&d_dec, cap_nodes * sizeof(Decision), stream));
-            CNVK_CHECK(cudaMallocAsync((void**)&d_ptile_off, (cap_nodes + 1) * sizeof(int), stream));
-            CNVK_CHECK(cudaMallocAsync((void**)&d_terms, cap_nodes * 100 * sizeof(double), stream));
-        }
-        h_nodes.assign(nn, Node());
-        h_tile_off.assign(nn + 1, 0);
-        h_ptile_off.assign(nn + 1, 0);
-        h_task_tab.clear();
-        long long blk_off = 0, tiles = 0, qtiles = 0, ptiles = 0;
-        for (int k = 0; k < nn; ++k) {
-            Node& nd = h_nodes[k];
+        if (hi - lo >= 2 * P.min_width) {
+            Node nd;
             memset(&nd, 0, sizeof(Node));
-            nd.lo = frontier[k].lo; nd.hi = frontier[k].hi; nd.base = frontier[k].base;
-            nd.blk_off = (int)blk_off;
+            nd.lo = lo; nd.hi = hi; nd.base = lo;
             nd.best_q = -1.0; nd.best_i = 0x7fffffff; nd.best_j = 0x7fffffff;
-            nd.tailp = -1.0;
-            const int n = nd.hi - nd.lo;
-            st.prep_bins += n;
-            h_ptile_off[k] = (int)ptiles;
-            ptiles += (n + 1 + PREP_TILE - 1) / PREP_TILE;     // tiles of 2048 prefix points
+            nd.tailp = -1.0; nd.flank = -1;
+            nd.ptile_off = (int)ptiles; nd.blk_off = (int)blk_off; nd.iblk_off = (int)iblks;
+            const int n = hi - lo;
+            ptiles += (n + 1 + PREP_TILE - 1) / PREP_TILE;
             blk_off += (n + 1 + CBS_BLK - 1) / CBS_BLK;
-            h_tile_off[k] = (int)tiles;
-            long long nt_, nq_;
-            tiles_for(n, k, &h_task_tab, &nt_, &nq_);
-            tiles += nt_;
-            qtiles += nq_;
-            if (tiles >= (1ll << 31) || qtiles >= (1ll << 31)) { set_last_error("cbs_segment: tile count overflow"); return -2; }
+            iblks += (n + 1 + CBS_IBLK - 1) / CBS_IBLK;
+            qtiles += node_qtiles(n);
+            h_nodes.push_back(nd);
+        } else {
+            CbsSeg s;
+            s.arm = a; s.lo = lo; s.hi = hi; s.mean = 0.0;     // mean filled below (short arms: 1-3 bins)
+            done.push_back(s);
         }
-        h_tile_off[nn] = (int)tiles;
-        h_ptile_off[nn] = (int)ptiles;
-        if ((size_t)ptiles > cap_ptiles) {
-            if (d_part1) cudaFreeAsync(d_part1, stream);
-            if (d_part3) cudaFreeAsync(d_part3, stream);
-            d_part1 = nullptr; d_part3 = nullptr;
-            cap_ptiles = (size_t)ptiles * 2;
-            CNVK_CHECK(cudaMallocAsync((void**)&d_part1, cap_ptiles * sizeof(TileSums), stream));
-            CNVK_CHECK(cudaMallocAsync((void**)&d_part3, cap_ptiles * sizeof(TileScan), stream));
-        }
-        if ((size_t)blk_off > NB) { set_last_error("cbs_segment: block buffer too small"); return -3; }
-        g_pinned.rewind();   // every copy of the previous level has completed (the level ends with a sync)
-        if (h_task_tab.size() > cap_tasks) {
-            if (d_task_tab) cudaFreeAsync(d_task_tab, stream);
-            if (d_seedres) cudaFreeAsync(d_seedres, stream);
-            d_task_tab = nullptr; d_seedres = nullptr;
-            cap_tasks = h_task_tab.size() * 2;
-            CNVK_CHECK(cudaMallocAsync((void**)&d_task_tab, cap_tasks * sizeof(int4), stream));
-            CNVK_CHECK(cudaMallocAsync((void**)&d_seedres, cap_tasks * sizeof(SeedRes), stream));
-        }
-        if ((size_t)nn + 1 > cap_task_off) {
-            if (d_task_off) cudaFreeAsync(d_task_off, stream);
-            d_task_off = nullptr;
-            cap_task_off = ((size_t)nn + 1) * 2;
-            CNVK_CHECK(cudaMallocAsync((void**)&d_task_off, cap_task_off * sizeof(int), stream));
-        }
-        {
-            int* p_to = g_pinned.put(h_tile_off.data(), (size_t)nn + 1);
-            CNVK_PIN_CHECK(p_to);
-            CNVK_CHECK(cudaMemcpyAsync(d_task_off, p_to, ((size_t)nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-        }
-        if (!h_task_tab.empty()) {
-            int4* p_tab = g_pinned.put(h_task_tab.data(), h_task_tab.size());
-            CNVK_PIN_CHECK(p_tab);
-            CNVK_CHECK(cudaMemcpyAsync(d_task_tab, p_tab, h_task_tab.size() * sizeof(int4), cudaMemcpyHostToDevice, stream));
-        }
-        {
-            Node* p_nodes = g_pinned.put(h_nodes.data(), (size_t)nn);
-            int* p_pto = g_pinned.put(h_ptile_off.data(), (size_t)nn + 1);
-            CNVK_PIN_CHECK(p_nodes && p_pto);
-            CNVK_CHECK(cudaMemcpyAsync(d_nodes, p_nodes, nn * sizeof(Node), cudaMemcpyHostToDevice, stream));
-            CNVK_CHECK(cudaMemcpyAsync(d_ptile_off, p_pto, (nn + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-        }
-        CNVK_CHECK(cudaMemsetAsync(d_counter, 0, 2 * sizeof(int), stream));
-        if ((size_t)qtiles > cap_queue) {
-            if (d_queue) cudaFreeAsync(d_queue, stream);
-            d_queue = nullptr;
-            cap_queue = (size_t)qtiles;
-            CNVK_CHECK(cudaMallocAsync((void**)&d_queue, cap_queue * sizeof(TileRef), stream));
-        }
+    }
+    const size_t n_short = done.size();
+
+    Grow<Node> nodes_a, nodes_b;
+    Grow<int> ptile_node, blk_node, iblk_node, need_list, hyb_list, exact_list, act, act_toff, fperm_list, tmp_list;
+    Grow<int> bimin, bimax, extra_lo, extra_hi;
+    Grow<double> bmin, bmax, bcmin, bcmax, bwmin, terms, fpart, extra_mean;
+    Grow<TileSums> part1;
+    Grow<TileScan> part3;
+    part3.zero = true;
+    Grow<SeedRes> seedres;
+    Grow<TileRef> queue;
+    Grow<unsigned long long> dmin_bits, pmax;
+    Grow<FlankTest> tests;
+    CNVK_CHECK(extra_lo.ensure(4096, stream));
+    CNVK_CHECK(extra_hi.ensure(4096, stream));
+    CNVK_CHECK(extra_mean.ensure(4096, stream));
+
+    int nn = (int)h_nodes.size();
+    Grow<Node>* cur = &nodes_a;
+    Grow<Node>* nxt = &nodes_b;
+    if (nn > 0) {
+        CNVK_CHECK(cur->ensure((size_t)nn, stream));
+        Node* p_nodes = g_pinned.put(h_nodes.data(), (size_t)nn);
+        CNVK_PIN_CHECK(p_nodes);
+        CNVK_CHECK(cudaMemcpyAsync(cur->p, p_nodes, nn * sizeof(Node), cudaMemcpyHostToDevice, stream));
+    }
+    LevelOut* h_out = (LevelOut*)g_pinned.get(sizeof(LevelOut));
+    CNVK_PIN_CHECK(h_out);
+    const int hk = P.hybrid ? P.kmax : 0;
+    const int ngrid = 100;
+    int epoch = 0;
+    if (tiles_overflow(ptiles, blk_off, iblks, qtiles)) return -2;
+    long long level_bins = 0;
+    for (const Node& nd : h_nodes) level_bins += nd.hi - nd.lo;
+
+    while (nn > 0) {
+        st.levels++;
+        st.nodes += nn;
+        ++epoch;
+        st.prep_bins += level_bins;
+        // ---- buffers of this level (sizes known from the previous level's record)
+        CNVK_CHECK(ptile_node.ensure((size_t)ptiles, stream));
+        CNVK_CHECK(blk_node.ensure((size_t)blk_off, stream));
+        CNVK_CHECK(iblk_node.ensure((size_t)iblks, stream));
+        CNVK_CHECK(part1.ensure((size_t)ptiles, stream));
+        CNVK_CHECK(part3.ensure((size_t)ptiles, stream));
+        CNVK_CHECK(bmin.ensure((size_t)blk_off, stream));
+        CNVK_CHECK(bmax.ensure((size_t)blk_off, stream));
+        CNVK_CHECK(bimin.ensure((size_t)blk_off, stream));
+        CNVK_CHECK(bimax.ensure((size_t)blk_off, stream));
+        CNVK_CHECK(bcmin.ensure((size_t)blk_off, stream));
+        CNVK_CHECK(bcmax.ensure((size_t)blk_off, stream));
+        CNVK_CHECK(bwmin.ensure((size_t)blk_off, stream));
+        CNVK_CHECK(seedres.ensure((size_t)iblks, stream));
+        CNVK_CHECK(queue.ensure((size_t)std::max<long long>(qtiles, 1), stream));
+        CNVK_CHECK(terms.ensure((size_t)nn * ngrid, stream));
+        CNVK_CHECK(need_list.ensure((size_t)nn, stream));
+        CNVK_CHECK(hyb_list.ensure((size_t)nn, stream));
+        CNVK_CHECK(exact_list.ensure((size_t)nn, stream));
+        CNVK_CHECK(tmp_list.ensure((size_t)nn, stream));
+        CNVK_CHECK(act.ensure((size_t)2 * nn, stream));
+        CNVK_CHECK(act_toff.ensure((size_t)nn + 1, stream));
+        CNVK_CHECK(dmin_bits.ensure((size_t)nn * HYB_LIM, stream));
+        const long long pm_entries = std::min<long long>(std::max<long long>((long long)nn * PERM_CHUNK_MAX, 1 << 16), 1 << 22);
+        CNVK_CHECK(pmax.ensure((size_t)2 * pm_entries, stream));
+        CNVK_CHECK(tests.ensure((size_t)2 * nn, stream));
+        CNVK_CHECK(fpart.ensure((size_t)2 * nn * FLANK_SPLIT * 5, stream));
+        CNVK_CHECK(fperm_list.ensure((size_t)2 * nn, stream));
+        Node* d_nodes = cur->p;
+        // lists, queue and next-level fields of the control block (stats are kept)
+        CNVK_CHECK(cudaMemsetAsync(d_ctl, 0, offsetof(Ctl, stats), stream));
+
+        cbs_maps_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, nn, ptile_node.p, blk_node.p, iblk_node.p);
+        CNVK_LAUNCH_CHECK();
         {
             ProfScope ps(PC_CBS_PREP, stream);
-            const int hk = P.hybrid ? P.kmax : 0;
-            cbs_prep_sums_kernel<<<(int)ptiles, PREP_THREADS, 0, stream>>>(d_nodes, d_ptile_off, nn, d_x, d_w, d_part1);
+            cbs_prep_sums_kernel<<<(int)ptiles, PREP_THREADS, 0, stream>>>(d_nodes, ptile_node.p, d_x, d_w, part1.p);
             CNVK_LAUNCH_CHECK();
-            cbs_prep_scan_kernel<<<(int)ptiles, PREP_THREADS, PREP_SMEM, stream>>>(d_nodes, d_ptile_off, nn, d_x, d_w, d_part1, d_xc, d_y, d_wn, d_Sl, d_cwl, d_part3);
+            cbs_prep_scan_kernel<<<(int)ptiles, PREP_THREADS, PREP_SMEM, stream>>>(
+                d_nodes, ptile_node.p, d_x, d_w, part3.p, d_S, d_cw, bmin.p, bmax.p, bimin.p, bimax.p, bcmin.p, bcmax.p,
+                bwmin.p, P.min_width, hk, P.nmin, epoch);
             CNVK_LAUNCH_CHECK();
-            cbs_prep_finish_kernel<<<(int)ptiles, PREP_THREADS, 0, stream>>>(d_nodes, d_ptile_off, nn, d_Sl, d_cwl, d_part3, d_S, d_cw, d_bmin, d_bmax, d_bimin, d_bimax, d_bcmin, d_bcmax, hk, P.nmin);
-            CNVK_LAUNCH_CHECK();
-            cbs_prep_node_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, d_ptile_off, nn, d_part3, d_cw, d_bmin, d_bmax, d_bimin, d_bimax, d_bcmin, d_bcmax, P.min_width, hk, P.nmin);
+        }
+        if (P.prune & 1) {
+            ProfScope ps(PC_CBS_SEED, stream);
+            cbs_seed_kernel<<<(int)iblks, 256, 0, stream>>>(d_nodes, iblk_node.p, seedres.p, bmin.p, bmax.p, bimin.p, bimax.p,
+                                                            bcmin.p, bcmax.p, P.min_width);
             CNVK_LAUNCH_CHECK();
         }
         {
-            if (tiles > 0) {
-                const int grid = sm_count * 4;
-                if (P.prune & 1) {
-                    ProfScope ps(PC_CBS_SEED, stream);
-                    cbs_seed_kernel<<<(int)tiles, 256, 0, stream>>>(d_nodes, d_task_tab, d_seedres, d_bmin, d_bmax, d_bimin, d_bimax, d_bcmin, d_bcmax, P.min_width);
-                    CNVK_LAUNCH_CHECK();
-                    cbs_seed_reduce_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, nn, d_task_off, d_seedres);
-                    CNVK_LAUNCH_CHECK();
-                }
-                {
-                    ProfScope ps(PC_CBS_BAND, stream);
-                    if (P.prune & 1) cbs_band_kernel<true><<<(int)blk_off, 256, 0, stream>>>(d_nodes, nn, d_S, d_cw, P.min_width, d_stats);
-                    else cbs_band_kernel<false><<<(int)blk_off, 256, 0, stream>>>(d_nodes, nn, d_S, d_cw, P.min_width, d_stats);
-                    CNVK_LAUNCH_CHECK();
-                }
-                {
-                    ProfScope ps(PC_CBS_BOUND, stream);
-                    if (P.prune & 1) cbs_bound_kernel<true><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_task_tab, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
-                    else cbs_bound_kernel<false><<<(int)tiles, 256, 0, stream>>>(d_nodes, d_task_tab, d_cw, d_bmin, d_bmax, d_queue, d_counter, d_stats);
-                    CNVK_LAUNCH_CHECK();
-                }
-                {
-                    ProfScope ps(PC_CBS_SCAN, stream);
-                    if (P.prune & 1) cbs_scan_kernel<true><<<grid, 256, 0, stream>>>(d_nodes, d_queue, d_counter, d_counter + 1, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
-                    else cbs_scan_kernel<false><<<grid, 256, 0, stream>>>(d_nodes, d_queue, d_counter, d_counter + 1, d_S, d_cw, d_bmin, d_bmax, P.min_width, d_stats);
-                    CNVK_LAUNCH_CHECK();
-                }
-            }
+            ProfScope ps(PC_CBS_BAND, stream);
+            if (P.prune & 1) cbs_band_kernel<true><<<(int)blk_off, 256, 0, stream>>>(d_nodes, blk_node.p, d_S, d_cw, bmin.p, bmax.p, bwmin.p, P.min_width, d_stats);
+            else cbs_band_kernel<false><<<(int)blk_off, 256, 0, stream>>>(d_nodes, blk_node.p, d_S, d_cw, bmin.p, bmax.p, bwmin.p, P.min_width, d_stats);
+            CNVK_LAUNCH_CHECK();
+        }
+        {
+            ProfScope ps(PC_CBS_BOUND, stream);
+            if (P.prune & 1) cbs_bound_kernel<true><<<(int)iblks, 256, 0, stream>>>(d_nodes, iblk_node.p, d_cw, bmin.p, bmax.p, queue.p, &d_ctl->qcount, d_stats);
+            else cbs_bound_kernel<false><<<(int)iblks, 256, 0, stream>>>(d_nodes, iblk_node.p, d_cw, bmin.p, bmax.p, queue.p, &d_ctl->qcount, d_stats);
+            CNVK_LAUNCH_CHECK();
+        }
+        {
+            ProfScope ps(PC_CBS_SCAN, stream);
+            const int grid = (int)std::min<long long>((long long)sm_count * 4, std::max<long long>(qtiles, 1));
+            if (P.prune & 1) cbs_scan_kernel<true><<<grid, 256, 0, stream>>>(d_nodes, queue.p, &d_ctl->qcount, &d_ctl->qpop, d_S, d_cw, bmin.p, bmax.p, P.min_width, d_stats);
+            else cbs_scan_kernel<false><<<grid, 256, 0, stream>>>(d_nodes, queue.p, &d_ctl->qcount, &d_ctl->qpop, d_S, d_cw, bmin.p, bmax.p, P.min_width, d_stats);
+            CNVK_LAUNCH_CHECK();
         }
         {
             ProfScope ps(PC_CBS_DECIDE, stream);
-            const int ngrid = 100;
-            cbs_stat_kernel<<<div_up(nn, 128), 128, 0, stream>>>(d_nodes, nn, P.alpha, P.nperm, P.nmin, (P.hybrid ? 1 : 0) | (diag ? 2 : 0));
+            const int flags = (P.hybrid ? 1 : 0) | (diag ? 2 : 0) | ((P.prune & 2) ? 4 : 0);
+            cbs_stat_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, nn, P.alpha, P.nperm, P.nmin, flags, ngrid, need_list.p, d_ctl);
             CNVK_LAUNCH_CHECK();
-            if (P.hybrid && !(P.prune & 2)) {
-                cbs_tailp_bounds_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, nn, P.alpha, P.nperm, ngrid);
+            if (P.hybrid) {
+                cbs_tailp_terms_kernel<<<dim3(ngrid, std::min(nn, 64)), 128, 0, stream>>>(d_nodes, need_list.p, d_ctl, terms.p, ngrid, 1e-6);
                 CNVK_LAUNCH_CHECK();
             }
-            if (P.hybrid) {
-                for (int y0 = 0; y0 < nn; y0 += 32768) {
-                    const int ny = std::min(32768, nn - y0);
-                    cbs_tailp_terms_kernel<<<dim3(ngrid, ny), 128, 0, stream>>>(d_nodes + y0, d_terms + (size_t)y0 * ngrid, P.kmax, ngrid, 1e-6);
-                    CNVK_LAUNCH_CHECK();
-                }
-            }
-            cbs_decide_kernel<<<div_up(nn, 128), 128, 0, stream>>>(d_nodes, nn, d_dec, d_terms, P.alpha, P.nperm, ngrid);
+            cbs_decide_kernel<<<1, 1024, 0, stream>>>(d_nodes, nn, terms.p, P.alpha, P.nperm, ngrid, diag ? 1 : 0, hyb_list.p, exact_list.p, d_ctl);
             CNVK_LAUNCH_CHECK();
         }
-        h_dec.resize(nn);
-        {
-            Decision* p_dec = (Decision*)g_pinned.get((size_t)nn * sizeof(Decision));
-            CNVK_PIN_CHECK(p_dec);
-            CNVK_CHECK(cudaMemcpyAsync(p_dec, d_dec, nn * sizeof(Decision), cudaMemcpyDeviceToHost, stream));
-            CNVK_CHECK(cudaStreamSynchronize(stream));
-            memcpy(h_dec.data(), p_dec, (size_t)nn * sizeof(Decision));
+        // ---- permutation reference distributions (cooperative persistent kernels; no-ops when their list is empty)
+        PermArgs pa;
+        pa.nodes = d_nodes; pa.ctl = d_ctl; pa.x = d_x; pa.w = d_w; pa.rw = d_rw; pa.cw = d_cw; pa.y = d_y; pa.wn = d_wn;
+        pa.dmin_bits = dmin_bits.p; pa.pmax = pmax.p; pa.pm_entries = pm_entries; pa.sbdry = d_sbdry;
+        pa.act = act.p; pa.act_toff = act_toff.p; pa.cap = nn; pa.seed = P.seed; pa.al0 = P.min_width; pa.kmax = P.kmax;
+        pa.nperm = P.nperm; pa.diag = diag ? 1 : 0;
+        if (P.hybrid) {
+            ProfScope ps(PC_CBS_PERM_HYBRID, stream);
+            pa.list = hyb_list.p;
+            void* args[] = {&pa};
+            if (P.kmax == 25 && P.min_width == 2) {
+                const int g = coop_grid((const void*)cbs_perm_hybrid_kernel<25, 2>, PERM_THREADS, sm_count, &grid_hyb25);
+                CNVK_CHECK(cudaLaunchCooperativeKernel((const void*)cbs_perm_hybrid_kernel<25, 2>, dim3(g), dim3(PERM_THREADS), args, 0, stream));
+            } else {
+                const int g = coop_grid((const void*)cbs_perm_hybrid_kernel<0, 0>, PERM_THREADS, sm_count, &grid_hyb0);
+                CNVK_CHECK(cudaLaunchCooperativeKernel((const void*)cbs_perm_hybrid_kernel<0, 0>, dim3(g), dim3(PERM_THREADS), args, 0, stream));
+            }
+            CNVK_LAUNCH_CHECK();
         }
-        std::vector<int> diag_nrej;
+        {
+            ProfScope ps(PC_CBS_PERM_EXACT, stream);
+            pa.list = exact_list.p;
+            void* args[] = {&pa};
+            const int g = coop_grid((const void*)cbs_perm_exact_kernel, 128, sm_count, &grid_exact);
+            CNVK_CHECK(cudaLaunchCooperativeKernel((const void*)cbs_perm_exact_kernel, dim3(g), dim3(128), args, 0, stream));
+            CNVK_LAUNCH_CHECK();
+        }
+        // ---- ternary-split confirmation
+        {
+            ProfScope fscope(PC_CBS_FLANK, stream);
+            cbs_flank_list_kernel<<<1, 1024, 0, stream>>>(d_nodes, nn, tests.p, tmp_list.p, d_ctl);
+            CNVK_LAUNCH_CHECK();
+            cbs_flank_part_kernel<<<sm_count * 4, 256, 0, stream>>>(d_nodes, tests.p, d_ctl, d_x, d_w, fpart.p);
+            CNVK_LAUNCH_CHECK();
+            cbs_flank_prep_kernel<<<std::min(div_up(2 * nn, 128), sm_count), 128, 0, stream>>>(tests.p, d_ctl, fpart.p, fperm_list.p, diag ? 1 : 0);
+            CNVK_LAUNCH_CHECK();
+            cbs_flank_perm_kernel<<<sm_count * 8, 128, 0, stream>>>(d_nodes, tests.p, fperm_list.p, d_ctl, P.nperm, d_x, d_rw, P.seed);
+            CNVK_LAUNCH_CHECK();
+        }
         if (diag) {
             diag->nodes.resize(nn);
+            std::vector<FlankTest> h_tests((size_t)2 * nn);
             CNVK_CHECK(cudaMemcpyAsync(diag->nodes.data(), d_nodes, nn * sizeof(Node), cudaMemcpyDeviceToHost, stream));
+            CNVK_CHECK(cudaMemcpyAsync(h_tests.data(), tests.p, (size_t)2 * nn * sizeof(FlankTest), cudaMemcpyDeviceToHost, stream));
+            CNVK_CHECK(cudaMemcpyAsync(h_out, d_out, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
             CNVK_CHECK(cudaStreamSynchronize(stream));
-            diag_nrej.assign(nn, 0);
-            for (int k = 0; k < nn; ++k) {
-                const Node& nd = diag->nodes[k];
-                if (nd.flat || nd.best_q < 0.0) { h_dec[k].state = ST_FINAL; continue; }
-                h_dec[k].state = (P.hybrid && nd.hi - nd.lo > P.nmin) ? ST_PERM_HYBRID : ST_PERM_EXACT;
-                h_dec[k].nrejc = P.nperm;
-            }
-        }
-
-        // ---- permutation reference distributions
-        for (int mode = ST_PERM_HYBRID; mode <= ST_PERM_EXACT; ++mode) {
-            std::vector<int> list;
-            for (int k = 0; k < nn; ++k) if (h_dec[k].state == mode) list.push_back(k);
-            if (list.empty()) continue;
-            st.perm_nodes += (long long)list.size();
-            std::vector<int> nrej(list.size(), 0), kk(list.size()), done(list.size(), 0);
-            for (size_t q = 0; q < list.size(); ++q) {
-                const int nrejc = h_dec[list[q]].nrejc;
-                kk[q] = nrejc * (nrejc + 1) / 2 + 1;
-            }
-            int p0 = 0;
-            int chunk = 64;
-            std::vector<int> active(list.begin(), list.end());
-            std::vector<size_t> active_q(list.size());
-            for (size_t q = 0; q < list.size(); ++q) active_q[q] = q;
-            Scratch limscratch(stream);
-            unsigned long long* d_lim = nullptr;
-            if (mode == ST_PERM_HYBRID) {
-                // pruning limits of every node that enters the hybrid permutation test (once per node)
-                int* d_all;
-                CNVK_CHECK(limscratch.alloc(&d_lim, (size_t)nn * HYB_LIM));
-                CNVK_CHECK(limscratch.alloc(&d_all, list.size()));
-                CNVK_CHECK(cudaMemsetAsync(d_lim, 0x7f, (size_t)nn * HYB_LIM * sizeof(unsigned long long), stream));
-                int* p_all = g_pinned.put(list.data(), list.size());
-                CNVK_PIN_CHECK(p_all);
-                CNVK_CHECK(cudaMemcpyAsync(d_all, p_all, list.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-                ProfScope bscope(PC_CBS_PERM_HYBRID, stream);
-                int maxn = 0;
-                for (int k : list) maxn = std::max(maxn, frontier[k].hi - frontier[k].lo);
-                for (size_t z0 = 0; z0 < list.size(); z0 += 32768) {
-                    const int nz = (int)std::min<size_t>(32768, list.size() - z0);
-                    cbs_perm_bounds_kernel<<<dim3(div_up(maxn, HYB_TP), nz), 256, 0, stream>>>(d_nodes, d_all + z0, d_wn, P.min_width, P.kmax, d_lim);
-                    CNVK_LAUNCH_CHECK();
-                }
-            }
-            while (!active.empty() && p0 < P.nperm) {
-                chunk = std::min(chunk, P.nperm - p0);
-                const int na = (int)active.size();
-                Scratch ps(stream);
-                int* d_list;
-                unsigned long long* d_pmax;
-                unsigned char* d_flags;
-                CNVK_CHECK(ps.alloc(&d_list, (size_t)na));
-                CNVK_CHECK(ps.alloc(&d_pmax, (size_t)na * chunk));
-                CNVK_CHECK(ps.alloc(&d_flags, (size_t)na * chunk));
-                {
-                    int* p_list = g_pinned.put(active.data(), (size_t)na);
-                    CNVK_PIN_CHECK(p_list);
-                    CNVK_CHECK(cudaMemcpyAsync(d_list, p_list, na * sizeof(int), cudaMemcpyHostToDevice, stream));
-                }
-                CNVK_CHECK(cudaMemsetAsync(d_pmax, 0, (size_t)na * chunk * sizeof(unsigned long long), stream));
-                ProfScope pscope(mode == ST_PERM_HYBRID ? PC_CBS_PERM_HYBRID : PC_CBS_PERM_EXACT, stream);
-                if (mode == ST_PERM_HYBRID) {
-                    int maxn = 0;
-                    for (int k : active) maxn = std::max(maxn, frontier[k].hi - frontier[k].lo);
-                    // grid.z is limited to 65535 and grid.y too: split the node list if needed
-                    for (int z0 = 0; z0 < na; z0 += 32768) {
-                        const int nz = std::min(32768, na - z0);
-                        dim3 grid(div_up(maxn, HYB_TP), chunk, nz);
-                        if (P.kmax == 25 && P.min_width == 2)
-                            cbs_perm_hybrid_kernel<25, 2><<<grid, 256, 0, stream>>>(d_nodes, d_list + z0, p0, d_y, d_rw, d_wn, d_lim, P.seed, P.min_width, P.kmax, d_pmax + (size_t)z0 * chunk, chunk);
-                        else
-                            cbs_perm_hybrid_kernel<0, 0><<<grid, 256, 0, stream>>>(d_nodes, d_list + z0, p0, d_y, d_rw, d_wn, d_lim, P.seed, P.min_width, P.kmax, d_pmax + (size_t)z0 * chunk, chunk);
-                        CNVK_LAUNCH_CHECK();
-                    }
-                    for (int k : active) st.perm_arcs += (long long)(frontier[k].hi - frontier[k].lo) * (P.kmax - P.min_width + 1) * chunk;
-                } else {
-                    for (int z0 = 0; z0 < na; z0 += 32768) {
-                        const int nz = std::min(32768, na - z0);
-                        dim3 grid(div_up(chunk, 4), nz);
-                        cbs_perm_exact_kernel<<<grid, 128, 0, stream>>>(d_nodes, d_list + z0, p0, d_y, d_rw, d_cw, P.seed, P.min_width, d_pmax + (size_t)z0 * chunk, chunk);
-                        CNVK_LAUNCH_CHECK();
-                    }
-                    for (int k : active) { const long long n = frontier[k].hi - frontier[k].lo; st.perm_arcs += n * n / 2 * chunk; }
-                }
-                cbs_perm_flags_kernel<<<div_up((long long)na * chunk, 256), 256, 0, stream>>>(d_nodes, d_list, na, d_pmax, chunk, d_flags);
-                CNVK_LAUNCH_CHECK();
-                unsigned char* flags = (unsigned char*)g_pinned.get((size_t)na * chunk);
-                CNVK_PIN_CHECK(flags);
-                CNVK_CHECK(cudaMemcpyAsync(flags, d_flags, (size_t)na * chunk, cudaMemcpyDeviceToHost, stream));
-                CNVK_CHECK(cudaStreamSynchronize(stream));
-                st.perms_run += (long long)na * chunk;
-                // replay DNAcopy's sequential stopping rule on the flags
-                std::vector<int> next_active;
-                std::vector<size_t> next_q;
-                for (int a = 0; a < na; ++a) {
-                    const size_t q = active_q[a];
-                    const int nrejc = h_dec[list[q]].nrejc;
-                    int decided = 0;
-                    for (int c = 0; c < chunk && !decided; ++c) {
-                        const int np = p0 + c + 1;
-                        if (flags[(size_t)a * chunk + c]) { nrej[q]++; kk[q]++; }
-                        if (diag) continue;
-                        if (nrej[q] > nrejc) decided = -1;
-                        else if (np >= sbdry[kk[q] - 1]) decided = 1;
-                    }
-                    if (diag) diag_nrej[list[q]] = nrej[q];
-                    if (decided == 0 && p0 + chunk >= P.nperm) decided = 1;  // survived every permutation
-                    if (decided == 0) { next_active.push_back(active[a]); next_q.push_back(q); }
-                    else h_dec[list[q]].state = decided > 0 ? ST_SPLIT : ST_FINAL;
-                }
-                active.swap(next_active);
-                active_q.swap(next_q);
-                p0 += chunk;
-                chunk = std::min(chunk * 4, 2048);
-            }
-        }
-
-        // ---- ternary-split confirmation
-        std::vector<FlankTest> tests;
-        std::vector<int> test_owner;
-        for (int k = 0; k < nn; ++k) {
-            if (h_dec[k].state != ST_SPLIT) continue;
-            const int n = frontier[k].hi - frontier[k].lo, ai = h_dec[k].best_i, aj = h_dec[k].best_j;
-            if (aj == n || ai == 0) continue;
-            FlankTest f;
-            memset(&f, 0, sizeof(f));
-            f.node = k; f.off = 0; f.n1 = ai; f.n2 = aj - ai; f.tid = 1;
-            tests.push_back(f); test_owner.push_back(k);
-            f.off = ai; f.n1 = aj - ai; f.n2 = n - aj; f.tid = 2;
-            tests.push_back(f); test_owner.push_back(k);
-        }
-        std::vector<double> pvals(tests.size(), 0.0);
-        if (!tests.empty()) {
-            const int nt = (int)tests.size();
-            Scratch fs(stream);
-            FlankTest* d_tests;
-            CNVK_CHECK(fs.alloc(&d_tests, (size_t)nt));
-            FlankTest* p_tests = g_pinned.put(tests.data(), (size_t)nt);
-            CNVK_PIN_CHECK(p_tests);
-            CNVK_CHECK(cudaMemcpyAsync(d_tests, p_tests, nt * sizeof(FlankTest), cudaMemcpyHostToDevice, stream));
-            ProfScope fscope(PC_CBS_FLANK, stream);
-            double* d_part;
-            CNVK_CHECK(fs.alloc(&d_part, (size_t)nt * FLANK_SPLIT * 5));
-            for (int z0 = 0; z0 < nt; z0 += 32768) {   // grid.x is the test index
-                const int nz = std::min(32768, nt - z0);
-                cbs_flank_part_kernel<<<dim3(nz, FLANK_SPLIT), 256, 0, stream>>>(d_nodes, d_tests + z0, d_xc, d_w, d_part + (size_t)z0 * FLANK_SPLIT * 5);
-                CNVK_LAUNCH_CHECK();
-            }
-            cbs_flank_prep_kernel<<<div_up(nt, 128), 128, 0, stream>>>(d_tests, nt, d_part, diag ? 1 : 0);
-            CNVK_LAUNCH_CHECK();
-            CNVK_CHECK(cudaMemcpyAsync(p_tests, d_tests, nt * sizeof(FlankTest), cudaMemcpyDeviceToHost, stream));
-            CNVK_CHECK(cudaStreamSynchronize(stream));
-            memcpy(tests.data(), p_tests, (size_t)nt * sizeof(FlankTest));
-            std::vector<int> plist;
-            for (int t = 0; t < nt; ++t) if (tests[t].need_perm) plist.push_back(t);
-            if (!plist.empty()) {
-                const int np_ = (int)plist.size();
-                st.flank_perm_tests += np_;
-                int *d_plist, *d_nrej;
-                CNVK_CHECK(fs.alloc(&d_plist, (size_t)np_));
-                CNVK_CHECK(fs.alloc(&d_nrej, (size_t)np_));
-                CNVK_CHECK(cudaMemcpyAsync(d_plist, plist.data(), np_ * sizeof(int), cudaMemcpyHostToDevice, stream));
-                CNVK_CHECK(cudaMemsetAsync(d_nrej, 0, np_ * sizeof(int), stream));
-                for (int z0 = 0; z0 < np_; z0 += 32768) {
-                    const int nz = std::min(32768, np_ - z0);
-                    dim3 grid(div_up(P.nperm, 4), nz);
-                    cbs_flank_perm_kernel<<<grid, 128, 0, stream>>>(d_nodes, d_tests, d_plist + z0, P.nperm, d_xc, d_rw, P.seed, d_nrej + z0);
-                    CNVK_LAUNCH_CHECK();
-                }
-                std::vector<int> h_nrej(np_);
-                CNVK_CHECK(cudaMemcpyAsync(h_nrej.data(), d_nrej, np_ * sizeof(int), cudaMemcpyDeviceToHost, stream));
-                CNVK_CHECK(cudaStreamSynchronize(stream));
-                for (int q = 0; q < np_; ++q) tests[plist[q]].pvalue = (double)h_nrej[q] / (double)P.nperm;
-            }
-            for (int t = 0; t < nt; ++t) pvals[t] = tests[t].pvalue;
-        }
-
-        if (diag) {
-            diag->nrej = diag_nrej;
             diag->flank_p.assign((size_t)2 * nn, -1.0);
-            for (size_t t = 0; t < tests.size(); ++t) diag->flank_p[(size_t)2 * test_owner[t] + (tests[t].tid - 1)] = pvals[t];
+            for (int t = 0; t < h_out->ctl.n_flank; ++t) {
+                const FlankTest& f = h_tests[t];
+                diag->flank_p[(size_t)2 * f.node + (f.tid - 1)] = f.need_perm ? (double)f.nrej / (double)P.nperm : f.pvalue;
+            }
             if (stats) *stats = st;
             return 0;
         }
-        // ---- next frontier
-        std::vector<HostNode> next;
-        size_t tcur = 0;
-        for (int k = 0; k < nn; ++k) {
-            const HostNode& hn = frontier[k];
-            const int n = hn.hi - hn.lo;
-            int ncpt = 0, icpt[2] = {0, 0};
-            if (h_dec[k].state == ST_SPLIT) {
-                const int ai = h_dec[k].best_i, aj = h_dec[k].best_j;
-                if (aj == n) { ncpt = 1; icpt[0] = ai; }
-                else if (ai == 0) { ncpt = 1; icpt[0] = aj; }
-                else {
-                    if (pvals[tcur] <= P.alpha) { ncpt = 1; icpt[0] = ai; }
-                    if (pvals[tcur + 1] <= P.alpha) { icpt[ncpt] = aj; ++ncpt; }
-                    if (ncpt == 0) { ncpt = 2; icpt[0] = ai; icpt[1] = aj; }
-                    tcur += 2;
-                }
+        // ---- next frontier + the segments that became final, one record back to the host
+        int cap_nodes = 0;
+        for (;;) {
+            cap_nodes = std::max(cap_nodes, std::max(2 * nn + 64, (int)nxt->cap));
+            CNVK_CHECK(nxt->ensure((size_t)cap_nodes, stream));
+            cap_nodes = (int)std::min<size_t>(nxt->cap, 0x7fffffff);
+            cbs_frontier_kernel<<<1, 1024, 0, stream>>>(d_nodes, nn, tests.p, P.alpha, P.nperm, P.min_width, nxt->p, cap_nodes,
+                                                        d_out, extra_lo.p, extra_hi.p, (int)extra_lo.cap);
+            CNVK_LAUNCH_CHECK();
+            {
+                ProfScope ps(PC_CBS_MEANS, stream);
+                seg_mean_kernel<<<sm_count * 2, 256, 0, stream>>>(d_x, d_w, d_out, extra_lo.p, extra_hi.p, extra_mean.p);
+                CNVK_LAUNCH_CHECK();
             }
-            if (ncpt == 0) { ends[hn.arm].push_back(hn.hi); continue; }
-            int cuts[4] = {hn.lo, hn.lo + icpt[0], ncpt == 2 ? hn.lo + icpt[1] : hn.hi, hn.hi};
-            const int npieces = ncpt + 1;
-            for (int c = 0; c < npieces; ++c) {
-                const int a0 = cuts[c], a1 = (c == npieces - 1) ? hn.hi : cuts[c + 1];
-                if (a1 - a0 >= 2 * P.min_width) next.push_back({a0, a1, hn.base, hn.arm});
-                else ends[hn.arm].push_back(a1);
+            CNVK_CHECK(cudaMemcpyAsync(h_out, d_out, sizeof(LevelOut), cudaMemcpyDeviceToHost, stream));
+            CNVK_CHECK(cudaStreamSynchronize(stream));
+            if (!h_out->ctl.overflow) break;
+            if (h_out->ctl.overflow & 1) cap_nodes = h_out->ctl.nn_next + 64;
+            if (h_out->ctl.overflow & 2) {
+                const size_t need = (size_t)h_out->ctl.nseg_new;
+                CNVK_CHECK(extra_lo.ensure(need, stream));
+                CNVK_CHECK(extra_hi.ensure(need, stream));
+                CNVK_CHECK(extra_mean.ensure(need, stream));
             }
         }
-        frontier.swap(next);
+        const Ctl& c = h_out->ctl;
+        const int nseg_new = c.nseg_new;
+        const int in_window = std::min(nseg_new, SEG_WINDOW);
+        for (int s = 0; s < in_window; ++s) {
+            CbsSeg sg;
+            sg.arm = -1; sg.lo = h_out->seg_lo[s]; sg.hi = h_out->seg_hi[s]; sg.mean = h_out->seg_mean[s];
+            done.push_back(sg);
+        }
+        if (nseg_new > SEG_WINDOW) {
+            const int more = nseg_new - SEG_WINDOW;
+            std::vector<int> lo_(more), hi_(more);
+            std::vector<double> mean_(more);
+            CNVK_CHECK(cudaMemcpyAsync(lo_.data(), extra_lo.p, more * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CNVK_CHECK(cudaMemcpyAsync(hi_.data(), extra_hi.p, more * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CNVK_CHECK(cudaMemcpyAsync(mean_.data(), extra_mean.p, more * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CNVK_CHECK(cudaStreamSynchronize(stream));
+            for (int s = 0; s < more; ++s) {
+                CbsSeg sg;
+                sg.arm = -1; sg.lo = lo_[s]; sg.hi = hi_[s]; sg.mean = mean_[s];
+                done.push_back(sg);
+            }
+        }
+        st.obs_subtiles_scanned = (long long)c.stats[0];
+        st.obs_subtiles_total = (long long)c.stats[1];
+        st.obs_arcs = st.obs_subtiles_scanned * (long long)CBS_BLK * CBS_BLK + (long long)c.stats[2] * BAND_SUB * BAND_SUB;
+        st.perm_nodes = (long long)c.stats[3];
+        st.perms_run = (long long)c.stats[4];
+        st.perm_arcs = (long long)c.stats[5];
+        st.flank_perm_tests = (long long)c.stats[6];
+        h_nodes.clear();
+        nn = c.nn_next; ptiles = c.ptiles_next; blk_off = c.nblk_next; iblks = c.niblk_next; qtiles = c.qtiles_next;
+        level_bins = c.bins_next;
+        if (tiles_overflow(ptiles, blk_off, iblks, qtiles)) return -2;
+        std::swap(cur, nxt);
     }
 
-    // ---- segment table + weighted means
-    std::vector<long long> slo, shi;
-    for (int a = 0; a < n_arms; ++a) {
-        std::sort(ends[a].begin(), ends[a].end());
-        long long prev = h_off[a];
-        for (int e : ends[a]) {
-            CbsSeg s;
-            s.arm = a; s.lo = prev; s.hi = e; s.mean = 0.0;
-            segs.push_back(s);
-            slo.push_back(prev); shi.push_back(e);
-            prev = e;
+    // ---- segment table: arms in order, segments by start; short arms (never a node) get their mean here
+    if (n_short) {
+        std::vector<long long> lo_(n_short), hi_(n_short);
+        for (size_t s = 0; s < n_short; ++s) { lo_[s] = done[s].lo; hi_[s] = done[s].hi; }
+        std::vector<double> xs, ws;
+        // at most 3 bins each: read them back in one gather-free pass (they are rare: arms of < 2*min_width bins)
+        for (size_t s = 0; s < n_short; ++s) {
+            const int len = (int)(hi_[s] - lo_[s]);
+            std::vector<double> hx(len), hw(len);
+            CNVK_CHECK(cudaMemcpyAsync(hx.data(), d_x + lo_[s], len * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CNVK_CHECK(cudaMemcpyAsync(hw.data(), d_w + lo_[s], len * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CNVK_CHECK(cudaStreamSynchronize(stream));
+            double sw = 0.0, swx = 0.0;
+            for (int k = 0; k < len; ++k) { sw += hw[k]; swx += hx[k] * hw[k]; }
+            done[s].mean = swx / sw;
         }
     }
-    if (!segs.empty()) {
-        const int ns = (int)segs.size();
-        Scratch ms(stream);
-        long long *d_lo, *d_hi;
-        double* d_mean;
-        CNVK_CHECK(ms.alloc(&d_lo, (size_t)ns));
-        CNVK_CHECK(ms.alloc(&d_hi, (size_t)ns));
-        CNVK_CHECK(ms.alloc(&d_mean, (size_t)ns));
-        CNVK_CHECK(cudaMemcpyAsync(d_lo, slo.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, stream));
-        CNVK_CHECK(cudaMemcpyAsync(d_hi, shi.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, stream));
-        {
-            ProfScope ps(PC_CBS_MEANS, stream);
-            seg_mean_kernel<<<ns, 1024, 0, stream>>>(d_x, d_w, d_lo, d_hi, ns, d_mean);
-            CNVK_LAUNCH_CHECK();
-        }
-        std::vector<double> means(ns);
-        CNVK_CHECK(cudaMemcpyAsync(means.data(), d_mean, ns * sizeof(double), cudaMemcpyDeviceToHost, stream));
-        CNVK_CHECK(cudaStreamSynchronize(stream));
-        for (int s = 0; s < ns; ++s) segs[s].mean = means[s];
-    }
+    std::sort(done.begin(), done.end(), [](const CbsSeg& a, const CbsSeg& b) { return a.lo < b.lo; });
     {
-        unsigned long long h_stats[3];
-        CNVK_CHECK(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
-        CNVK_CHECK(cudaStreamSynchronize(stream));
-        st.obs_subtiles_scanned = (long long)h_stats[0];
-        st.obs_subtiles_total = (long long)h_stats[1];
-        st.obs_arcs = st.obs_subtiles_scanned * (long long)CBS_BLK * CBS_BLK + (long long)h_stats[2] * BAND_SUB * BAND_SUB;
+        int a = 0;
+        for (CbsSeg& s : done) {
+            while (a + 1 < n_arms && s.lo >= h_off[a + 1]) ++a;
+            s.arm = a;
+        }
     }
+    segs.swap(done);
     if (stats) *stats = st;
     return 0;
 }
@@ -2175,7 +2559,7 @@ int cbs_node_diag(const double* d_x, const double* d_w, const long long* h_off, 
         o[5] = diag.flank_p[(size_t)2 * k + 1];
         io[0] = live ? nd.best_i : 0;
         io[1] = live ? nd.best_j : 0;
-        io[2] = diag.nrej[k];
+        io[2] = live ? nd.nrej : 0;
         io[3] = hyb ? 1 : 0;
         io[4] = nd.flat ? 1 : 0;
     }

@@ -87,12 +87,34 @@ def chrom_sort_key(label: str):
     return ((2000 if len(rest) == 1 else 3000) + num, rest)
 
 
+def encode_column(col):
+    """(codes int64[n], unique values in first-appearance order) of a string column; missing values get
+    code -1.  pandas >= 3 keeps strings Arrow-backed: a dictionary encode in pyarrow costs a third of
+    `to_numpy()` alone (45 ms vs 145 ms at 3 M rows), so Series are encoded without materialising Python
+    strings; plain numpy object arrays take the pandas hash path."""
+    import pandas as pd
+
+    arr = getattr(col, "array", None)
+    pa_arr = getattr(arr, "_pa_array", None) if arr is not None else None
+    if pa_arr is not None:
+        try:
+            import pyarrow as pa
+
+            if isinstance(pa_arr, pa.ChunkedArray):
+                pa_arr = pa_arr.combine_chunks()
+            enc = pa_arr.dictionary_encode()
+            codes = enc.indices.fill_null(-1).to_numpy(zero_copy_only=False).astype(np.int64, copy=False)
+            return codes, np.asarray(enc.dictionary.to_pylist(), dtype=object)
+        except Exception:       # unexpected Arrow layout: fall through to the generic path
+            pass
+    codes, uniq = pd.factorize(col if arr is not None else np.asarray(col, dtype=object), sort=False)
+    return np.asarray(codes, dtype=np.int64), np.asarray(uniq, dtype=object)
+
+
 def _factorize(chrom):
     """(codes, unique names in first-appearance order) of a chromosome column -- one hash pass instead
     of a Python loop over the rows."""
-    import pandas as pd
-
-    codes, uniq = pd.factorize(chrom, sort=False)
+    codes, uniq = encode_column(chrom)
     return codes, list(uniq)
 
 
@@ -102,13 +124,13 @@ def chrom_runs(chromosomes: np.ndarray):
     Returns (names, offsets int64[k+1], chrom_id int32[n]).  Rows of one chromosome must be
     contiguous (true for any genomically sorted table); raises ValueError otherwise.
     """
-    chrom = np.asarray(chromosomes, dtype=object)
-    n = len(chrom)
+    n = len(chromosomes)
     if n == 0:
         return [], np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32)
-    change = np.flatnonzero(chrom[1:] != chrom[:-1]) + 1
+    codes, uniq = encode_column(chromosomes)
+    change = np.flatnonzero(codes[1:] != codes[:-1]) + 1
     starts = np.concatenate([[0], change])
-    names = [str(chrom[s]) for s in starts]
+    names = [str(uniq[codes[s]]) for s in starts]
     if len(set(names)) != len(names):
         raise ValueError("chromosome rows are not contiguous; sort the table first")
     offsets = np.concatenate([starts, [n]]).astype(np.int64)

@@ -14,7 +14,8 @@ import pandas as pd
 import torch
 
 from .. import _dev, _lib, params
-from ..cnary import arm_ranges
+from .. import genome
+from ..cnary import arm_cut, arm_ranges, arm_ranges_from_runs
 from . import cbs as _cbs
 from . import haar as _haar
 
@@ -61,14 +62,16 @@ def do_segmentation(
                  processes)
 
     data = cnarr.data.reset_index(drop=True)
-    arms = arm_ranges(data)  # GenomicArray.by_arm of the unfiltered table
+    start = data["start"].to_numpy(dtype=np.int64)
+    end = data["end"].to_numpy(dtype=np.int64)
+    # chromosome names stay dictionary-coded on the host: one Arrow encode instead of 3 M Python strings
+    chrom_names, chrom_off, chrom_id = genome.chrom_runs(data["chromosome"])
+    chrom_names = np.asarray(chrom_names, dtype=object)
+    arms = arm_ranges_from_runs(chrom_names, chrom_off, start, end)  # GenomicArray.by_arm of the unfiltered table
     log2 = data["log2"].to_numpy(dtype=np.float64)
     has_weight = "weight" in data.columns
     weight = data["weight"].to_numpy(dtype=np.float64) if has_weight else None
     depth = data["depth"].to_numpy(dtype=np.float64) if "depth" in data.columns else None
-    start = data["start"].to_numpy(dtype=np.int64)
-    end = data["end"].to_numpy(dtype=np.int64)
-    chrom = data["chromosome"].to_numpy()
     n = len(data)
     arm_off = np.array([a[1] for a in arms] + [arms[-1][2]], dtype=np.int64)
     arm_id = np.repeat(np.arange(len(arms)), np.diff(arm_off))
@@ -122,12 +125,12 @@ def do_segmentation(
     if method == "cbs":
         seg = _segment_cbs(f_log2, f_weight, f_arm, len(arms), threshold)
     else:
-        seg = _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, chrom[fidx], len(arms), threshold)
+        seg = _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, len(arms), threshold)
     s_unit, s_lo, s_hi, s_mean, unit_arm, sub_fidx = seg
     # rows of the per-arm segment tables (cbs.py:64-73 / haar.py:244-254)
     src = fidx if sub_fidx is None else fidx[sub_fidx]
     seg_arm = unit_arm[s_unit]
-    seg_chrom = chrom[src[s_lo]]
+    seg_chrom = chrom_names[chrom_id[src[s_lo]]]
     seg_start = start[src[s_lo]].copy()
     seg_end = end[src[s_hi - 1]].copy()
     probes = (s_hi - s_lo).astype(np.int64)
@@ -243,7 +246,7 @@ def _segment_cbs(f_log2, f_weight, f_arm, n_arms, threshold):
     return arm, lo, hi, mean, np.arange(n_arms), sub
 
 
-def _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, f_chrom, n_arms, threshold):
+def _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, n_arms, threshold):
     """`case "haar"` (:286-289): segment_haar re-splits every filtered arm with by_arm() again
     (haar.py:80-82), so the segmentation units are the arms of the *filtered* arm tables."""
     units_off = [0]
@@ -253,8 +256,8 @@ def _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, f_chrom, n_arms, thre
         lo, hi = int(off[a]), int(off[a + 1])
         if hi <= lo:
             continue
-        sub = pd.DataFrame({"chromosome": f_chrom[lo:hi], "start": f_start[lo:hi], "end": f_end[lo:hi]})
-        for _c, slo, shi in arm_ranges(sub):
+        cut = arm_cut(f_start, f_end, lo, hi)       # one chromosome: by_arm() of the filtered arm table
+        for shi in ((cut, hi - lo) if cut else (hi - lo,)):
             units_off.append(lo + shi)
             unit_arm.append(a)
     arm, lo, hi, mean = _haar.segment_arms(f_log2, f_weight, np.asarray(units_off, dtype=np.int64), float(threshold))
@@ -310,7 +313,7 @@ def _transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, seg_log2, probes, a
         _lib.call("cnvk_segment_bin_sums_dev", _dev.ptr(d_dep), _dev.ptr(d_w), _dev.ptr(d_lo), _dev.ptr(d_hi), nseg,
                   _dev.ptr(d_sw), _dev.ptr(d_sd), _dev.stream())
     seg_weight, seg_depth = d_sw.cpu().numpy(), d_sd.cpu().numpy()
-    genes = _join_genes(None if gene_codes is not None else data["gene"].to_numpy(), bin_lo, bin_hi, gene_codes,
+    genes = _join_genes(None if gene_codes is not None else data["gene"], bin_lo, bin_hi, gene_codes,
                         mask_end=end if nested else None, mask_start=seg_start if nested else None)
     return pd.DataFrame({
         "chromosome": seg_chrom, "start": seg_start, "end": seg_end, "gene": genes, "log2": seg_log2,
@@ -325,7 +328,8 @@ class GeneCodes:
 
     def __init__(self, bin_genes, ignore=None):
         ignore = set((params.IGNORE_GENE_NAMES if ignore is None else tuple(ignore)) + params.ANTITARGET_ALIASES)
-        codes, uniques = pd.factorize(pd.Series(bin_genes, dtype=object), sort=False)
+        codes, uniques = genome.encode_column(bin_genes if hasattr(bin_genes, "array") else
+                                              pd.Series(bin_genes, dtype=object))
         self.codes = codes
         self.parts = [tuple(p for p in u.split(",") if p not in ignore) if isinstance(u, str) else ()
                       for u in uniques]

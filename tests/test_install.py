@@ -97,11 +97,15 @@ def test_segmetrics_seam_merges_reference_columns_with_ours(golden):
     assert "ci_lo" not in no_ci.data.columns and "mean" in no_ci.data.columns
 
 
-def test_declined_inputs_fall_back_to_the_reference():
+def test_in_scope_inputs_never_fall_back_to_the_reference():
+    """north_star: "no CPU fallback".  Only the explicit option predicates forward a call to cnvlib; an in-scope
+    call that the GPU path cannot serve raises instead of silently rerunning on the CPU."""
     def ours(x):
         if x == "odd":
-            raise NotImplementedError("nested bins")
+            raise NotImplementedError("an input the GPU path declines")
         return "ours"
 
-    seam = I._route(ours, lambda x: "theirs", lambda a, k: False)
-    assert seam("plain") == "ours" and seam("odd") == "theirs"
+    seam = I._route(ours, lambda x: "theirs", lambda a, k: a[0] == "out-of-scope option")
+    assert seam("plain") == "ours" and seam("out-of-scope option") == "theirs"
+    with pytest.raises(NotImplementedError):
+        seam("odd")
