@@ -221,6 +221,38 @@ def exome_cpu_baseline(bins, ref, sample, cores, methods=("cbs", "haar")):
     return out
 
 
+def exome_reference_python(bins, ref, sample):
+    """The reference's OWN Python (cnvlib.fix.do_fix + cnvlib.segmentation.do_segmentation(method='haar'), one
+    process, unmodified code from baseline/_ref or /root/reference) on one C2 sample -- the CPU pipeline a user
+    runs today, minus R (absent, so CBS itself cannot be timed with the reference's code).  None if the reference
+    tree did not travel."""
+    try:
+        from oracle import refshim
+
+        if not refshim.available():
+            return None
+        R = refshim.load()
+    except Exception as exc:   # missing dependency of the reference on this box: report, do not fail the bench
+        return {"error": repr(exc)}
+    import logging
+
+    from cnvkit_b200 import synth
+
+    logging.disable(logging.WARNING)
+    T, A, Rf = synth.exome_tables(bins, ref, sample, sample_id="S0")
+    mk = lambda t: R.cnary.CopyNumArray(t.data.copy(), {"sample_id": "S0"})
+    t0 = time.perf_counter()
+    cnr = R.fix.do_fix(mk(T), mk(A), mk(Rf))
+    t1 = time.perf_counter()
+    cns = R.segmentation.do_segmentation(cnr, "haar")
+    t2 = time.perf_counter()
+    logging.disable(logging.NOTSET)
+    return {"kind": "reference", "cores": 1, "fix_s": t1 - t0, "haar_s": t2 - t1, "bins": int(len(cnr)),
+            "segments_haar": int(len(cns)), "samples_per_s_fix_haar": 1.0 / (t2 - t0),
+            "sample": "one C2 sample through cnvlib.fix.do_fix + cnvlib.segmentation.do_segmentation('haar'), the "
+                      f"unmodified reference from {R.root}, one process (R/DNAcopy absent: its CBS cannot run)"}
+
+
 def exome_leg(args, torch, dev):
     """C2: fix + CBS + Haar of single exome samples through cohort.Panel (host columns in, .cns tables
     out -- copies inside the timed region), plus per-kernel device time for the rolling-median path."""
@@ -284,6 +316,7 @@ def exome_leg(args, torch, dev):
                              if rm_ms else None, "note": "16 B/element algorithmic; on-chip selection bound, not HBM"}
     cores = len(os.sched_getaffinity(0))
     cpu = exome_cpu_baseline(bins, ref, samples[0], cores)
+    out["cpu_baseline_reference_python"] = exome_reference_python(bins, ref, samples[0])
     out["cpu_baseline"] = {"value": 1.0 / (cpu["fix_s"] + cpu["cbs_s"]), "unit": "samples/s", "cores": cores,
                            "kind": "port", "detail": cpu,
                            "sample": "one C2 sample, oracle/pipeline.py (fix: pandas rolling median as the reference; "

@@ -75,6 +75,11 @@ SIGNATURES = {
     "cnvk_haar_segment": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_double, c_int64, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
     "cnvk_cbs_getbdry": (c_int, [c_double, c_int32, c_int32, c_void_p]),
+    "cnvk_coverage_finalize_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
+    "cnvk_coverage_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]),
+    "cnvk_smooth_cna_dev": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_double, c_double, c_double, c_void_p,
+                                    c_void_p, c_void_p]),
+    "cnvk_smooth_cna": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_double, c_double, c_double, c_void_p, c_void_p]),
     "cnvk_cbs_node_diag": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "cnvk_fasta_gc_lo_dev": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "cnvk_fasta_gc_lo": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

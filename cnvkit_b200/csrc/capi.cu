@@ -457,6 +457,55 @@ int cnvk_cbs_segment(const double* log2, const double* weight, const int64_t* ar
     return hc.finish();
 }
 
+int cnvk_coverage_finalize_dev(const double* d_basecount, const int64_t* d_start, const int64_t* d_end, int64_t n,
+                               double null_log2, double* d_depth, double* d_log2, void* stream) {
+    RC(ensure_init());
+    return coverage_finalize(d_basecount, (const long long*)d_start, (const long long*)d_end, n, null_log2, d_depth,
+                             d_log2, (cudaStream_t)stream);
+}
+
+int cnvk_coverage_finalize(const double* basecount, const int64_t* start, const int64_t* end, int64_t n,
+                           double null_log2, double* depth, double* log2) {
+    HostCall hc;
+    RC(hc.begin());
+    double *db, *dd, *dl;
+    long long *ds, *de;
+    RC(hc.upload(basecount, (size_t)n, &db));
+    RC(hc.upload((const long long*)start, (size_t)n, &ds));
+    RC(hc.upload((const long long*)end, (size_t)n, &de));
+    CNVK_CHECK(hc.scratch->alloc(&dd, (size_t)n));
+    CNVK_CHECK(hc.scratch->alloc(&dl, (size_t)n));
+    RC(coverage_finalize(db, ds, de, n, null_log2, dd, dl, hc.stream));
+    RC(hc.download(depth, dd, (size_t)n));
+    RC(hc.download(log2, dl, (size_t)n));
+    return hc.finish();
+}
+
+int cnvk_smooth_cna_dev(const double* d_log2, const int64_t* arm_offsets, int32_t n_arms, int32_t smooth_region,
+                        double outlier_sd_scale, double smooth_sd_scale, double trim, double* d_out, double* d_sd,
+                        void* stream) {
+    RC(ensure_init());
+    std::vector<long long> off(arm_offsets, arm_offsets + n_arms + 1);
+    return smooth_cna(d_log2, off.data(), n_arms, smooth_region, outlier_sd_scale, smooth_sd_scale, trim, d_out, d_sd,
+                      (cudaStream_t)stream);
+}
+
+int cnvk_smooth_cna(const double* log2, const int64_t* arm_offsets, int32_t n_arms, int32_t smooth_region,
+                    double outlier_sd_scale, double smooth_sd_scale, double trim, double* out, double* sd) {
+    HostCall hc;
+    RC(hc.begin());
+    const size_t N = n_arms > 0 ? (size_t)arm_offsets[n_arms] : 0;
+    double *dx, *dout, *dsd;
+    RC(hc.upload(log2, N, &dx));
+    CNVK_CHECK(hc.scratch->alloc(&dout, N));
+    CNVK_CHECK(hc.scratch->alloc(&dsd, (size_t)std::max(n_arms, 1)));
+    std::vector<long long> off(arm_offsets, arm_offsets + n_arms + 1);
+    RC(smooth_cna(dx, off.data(), n_arms, smooth_region, outlier_sd_scale, smooth_sd_scale, trim, dout, dsd, hc.stream));
+    RC(hc.download(out, dout, N));
+    if (sd) RC(hc.download(sd, dsd, (size_t)n_arms));
+    return hc.finish();
+}
+
 int cnvk_cbs_node_diag(const double* log2, const double* weight, const int64_t* node_offsets, int32_t n_nodes,
                        const cnvk_cbs_params* p, double* out6, int32_t* iout5) {
     HostCall hc;

@@ -37,6 +37,7 @@
 //             segment records (+ weighted means) in the level's read-back record.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include <cooperative_groups.h>
@@ -55,7 +56,8 @@ static const int HYB_TP = 2048;           // arc starts per tile in the hybrid p
 static const int HYB_KMAX = 64;           // max supported kmax
 static const int EXACT_NMAX = 256;        // max supported nmin
 static const int HYB_LIM = HYB_KMAX + 1;
-static const int PERM_CHUNK_MAX = 2048;   // permutations per chunk (upper end of the 64 -> 2048 schedule)
+static const int PERM_CHUNK_FIRST = 16;   // first chunk: most tested nodes are noise and fail within a few permutations
+static const int PERM_CHUNK_MAX = 2048;   // permutations per chunk (16 -> 64 -> 256 -> 1024 -> 2048 -> 2048 ...)
 static const int SEG_WINDOW = 1024;       // final segments read back with the level record in one copy
 
 enum { ST_FINAL = 0, ST_SPLIT = 1, ST_PERM_HYBRID = 2, ST_PERM_EXACT = 3, ST_NEED_TAILP = 4 };
@@ -100,6 +102,8 @@ struct Ctl {
     long long bins_next;           // bins of the next level's nodes (prep work counter)
     unsigned long long stats[8];   // [0] sub-tiles scanned [1] tested [2] band pairs [3] perm nodes [4] perms run
                                    // [5] perm arcs [6] flank perm tests
+    long long tprof[8];            // SM cycles of CTA 0 inside the hybrid permutation kernel (CNVK_CBS_DEBUG):
+                                   // [0] materialise [1] limits [2] permutation chunks [3] replay [4] chunks run
 };
 
 struct LevelOut {                  // one device->host copy per level
@@ -240,12 +244,24 @@ cbs_prep_sums_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_nod
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double mn = INFINITY, mx = -INFINITY;
     DD a_w = {0.0, 0.0}, a_wx = {0.0, 0.0};
-    for (int r = tid; r < m; r += PREP_THREADS) {
-        const double v = x[lo + t0 + r], wv = w[lo + t0 + r];
-        mn = fmin(mn, v);
-        mx = fmax(mx, v);
-        dd_add(a_w, wv);
-        dd_add(a_wx, __dmul_rn(v, wv));
+    {
+        // all 16 loads of the thread in flight before the (dependent) compensated additions start
+        double xv[PREP_E], wv[PREP_E];
+#pragma unroll
+        for (int e = 0; e < PREP_E; ++e) {
+            const int r = tid + e * PREP_THREADS;
+            xv[e] = (r < m) ? x[lo + t0 + r] : 0.0;
+            wv[e] = (r < m) ? w[lo + t0 + r] : 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < PREP_E; ++e) {
+            if (tid + e * PREP_THREADS < m) {
+                mn = fmin(mn, xv[e]);
+                mx = fmax(mx, xv[e]);
+                dd_add(a_w, wv[e]);
+                dd_add(a_wx, __dmul_rn(xv[e], wv[e]));
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -389,17 +405,27 @@ cbs_prep_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_nod
     const double avg = nd->avg, rsw = nd->rsw;
 
     DD a_tss = {0.0, 0.0};
-    for (int r = tid; r < PREP_TILE; r += PREP_THREADS) {              // coalesced staging
-        double wv = 0.0, sv = 0.0;
-        if (r < m) {
-            const int g = lo + t0 + r;
-            wv = w[g];
-            const double cc = __dsub_rn(x[g], avg);
-            sv = __dmul_rn(cc, wv);
-            dd_add(a_tss, __dmul_rn(wv, __dmul_rn(cc, cc)));
+    {
+        // coalesced staging; the 16 loads of a thread are issued before the first dependent operation
+        double xv[PREP_E], wv[PREP_E];
+#pragma unroll
+        for (int e = 0; e < PREP_E; ++e) {
+            const int r = tid + e * PREP_THREADS;
+            xv[e] = (r < m) ? x[lo + t0 + r] : 0.0;
+            wv[e] = (r < m) ? w[lo + t0 + r] : 0.0;
         }
-        s_w[prep_pad(r)] = wv;
-        s_s[prep_pad(r)] = sv;
+#pragma unroll
+        for (int e = 0; e < PREP_E; ++e) {
+            const int r = tid + e * PREP_THREADS;
+            double sv = 0.0;
+            if (r < m) {
+                const double cc = __dsub_rn(xv[e], avg);
+                sv = __dmul_rn(cc, wv[e]);
+                dd_add(a_tss, __dmul_rn(wv[e], __dmul_rn(cc, cc)));
+            }
+            s_w[prep_pad(r)] = wv[e];
+            s_s[prep_pad(r)] = sv;
+        }
     }
     __syncthreads();
     double pw[PREP_E], ps[PREP_E];
@@ -446,46 +472,64 @@ cbs_prep_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_nod
     const bool want_delta = hk > 0 && n > nmin;
     const int jw = hk + 1;
     if (tid == 0) {
-        // publish this tile's totals, then take the carry C[k] = T[0] + ... + T[k-1] left to right
+        // publish this tile's totals for the tiles after it
         TileScan* o = &part3[blockIdx.x];
         o->Tw = Tw; o->Ts = Ts; o->tss_hi = tss.hi; o->tss_lo = tss.lo; o->dmin = INFINITY;
         __threadfence();
         *((volatile int*)&o->flag) = epoch;
+    }
+    if (warp == 0) {
+        // carry C[k] = T[0] + ... + T[k-1], added left to right (the fixed association); the loads of up to 32
+        // predecessors are in flight at once, only the additions are sequential
         double Cw = 0.0, Cs = 0.0;
-        for (int t = 0; t < k; ++t) {
-            volatile TileScan* p = ts_node + t;
-            while (p->flag != epoch) {}
-            __threadfence();
-            Cw = t ? __dadd_rn(Cw, p->Tw) : p->Tw;
-            Cs = t ? __dadd_rn(Cs, p->Ts) : p->Ts;
+        for (int t0_ = 0; t0_ < k; t0_ += 32) {
+            const int t = t0_ + lane;
+            double vw = 0.0, vs = 0.0;
+            if (t < k) {
+                volatile TileScan* p = ts_node + t;
+                while (p->flag != epoch) {}
+                __threadfence();
+                vw = p->Tw; vs = p->Ts;
+            }
+            const int cnt = min(32, k - t0_);
+            for (int j = 0; j < cnt; ++j) {
+                const double aw = __shfl_sync(0xffffffffu, vw, j), as = __shfl_sync(0xffffffffu, vs, j);
+                Cw = (t0_ + j) ? __dadd_rn(Cw, aw) : aw;
+                Cs = (t0_ + j) ? __dadd_rn(Cs, as) : as;
+            }
         }
-        s_carry[0] = Cw; s_carry[1] = Cs;
-        s_carry[2] = k ? __dadd_rn(Cw, Tw) : Tw;                       // C[k+1]
+        if (lane == 0) {
+            s_carry[0] = Cw; s_carry[1] = Cs;
+            s_carry[2] = k ? __dadd_rn(Cw, Tw) : Tw;                       // C[k+1]
+        }
     }
     // halo for getmncwt: cw at points t0+PREP_TILE+1 .. +jw are terms 0..jw-1 of the NEXT tile.  Their
     // tile-local prefix values follow from the same fixed association (warp 0 of that tile: X = 0, so
-    // local = E[j] + p[j,e]); thread 1 replays it from the raw weights -- no wait on a later tile.
-    if (want_delta && tid == 32) {
-        const int nthr = (jw + PREP_E - 1) / PREP_E;                     // "threads" of the next tile involved (<= 9)
-        double A[12], p8[12][PREP_E];
+    // local = E[j] + p[j,e]); one thread replays it from the raw weights -- no wait on a later tile.
+    if (want_delta && warp == 1) {
         const int g1 = lo + t0 + PREP_TILE;                              // first term of the next tile
         const int m1 = max(0, min(PREP_TILE, n - (t0 + PREP_TILE)));
-        for (int j = 0; j < nthr; ++j) {
-            double r = 0.0;
-            for (int e = 0; e < PREP_E; ++e) {
-                const int kk = PREP_E * j + e;
-                const double v = (kk < m1) ? w[g1 + kk] : 0.0;
-                r = e ? __dadd_rn(r, v) : v;
-                p8[j][e] = r;
+        for (int h = lane; h < PREP_HALO + 6; h += 32) s_halo[h] = (h < m1) ? w[g1 + h] : 0.0;   // raw weights
+        __syncwarp();
+        if (lane == 0) {
+            const int nthr = (jw + PREP_E - 1) / PREP_E;                 // "threads" of the next tile involved (<= 9)
+            double A[12], p8[12][PREP_E];
+            for (int j = 0; j < nthr; ++j) {
+                double r = 0.0;
+                for (int e = 0; e < PREP_E; ++e) {
+                    const double v = s_halo[PREP_E * j + e];
+                    r = e ? __dadd_rn(r, v) : v;
+                    p8[j][e] = r;
+                }
+                A[j] = r;
             }
-            A[j] = r;
-        }
-        for (int o = 1; o < 32; o <<= 1)
-            for (int l = nthr - 1; l >= o; --l) A[l] = __dadd_rn(A[l], A[l - o]);
-        for (int h = 0; h < jw; ++h) {
-            const int j = h / PREP_E, e = h % PREP_E;
-            const double E = j ? A[j - 1] : 0.0;
-            s_halo[h] = __dadd_rn(__dadd_rn(0.0, E), p8[j][e]);
+            for (int o = 1; o < 32; o <<= 1)
+                for (int l = nthr - 1; l >= o; --l) A[l] = __dadd_rn(A[l], A[l - o]);
+            for (int h = 0; h < jw; ++h) {
+                const int j = h / PREP_E, e = h % PREP_E;
+                const double E = j ? A[j - 1] : 0.0;
+                s_halo[h] = __dadd_rn(__dadd_rn(0.0, E), p8[j][e]);
+            }
         }
     }
     __syncthreads();
@@ -798,52 +842,70 @@ __device__ __forceinline__ bool tile_needed(const double* __restrict__ cw, const
 }
 
 // Narrow arcs: every (i, j) whose 256-point blocks are equal or adjacent.  At 256-point granularity
-// these pairs cannot be pruned by the tile bound (the lightest arc of the pair is a single bin), so one
-// CTA owns one start block:
-//   1. CTA-level bound from the block extrema of the two blocks and the lightest al0-window that starts
-//      in the start block (prep): when even that cannot reach the node's running best the CTA exits
-//      without touching S / cw -- the common case in nodes that hold a strong change-point;
-//   2. otherwise the 512-point strip of S and of cw is staged with one TMA bulk copy each
-//      (cp.async.bulk -> UBLKCP, completion on an mbarrier) and the bound test is repeated on 32x32
-//      sub-blocks, warp-uniformly (warp <-> 32 starts).
+// these pairs cannot be pruned by the tile bound (the lightest arc of the pair is a single bin).  One CTA owns
+// FOUR consecutive start blocks of a node (a 1024-point start block, like the seed / bound tasks), so the node
+// lookup, the staging and the commit are paid once per 1024 starts:
+//   1. per start block, a CTA-level bound from the block extrema of the block and its successor and the lightest
+//      al0-window that starts in the block (prep): blocks that cannot reach the node's running best are skipped,
+//      and when all four are, the CTA exits without touching S / cw -- the common case in nodes that hold a
+//      strong change-point;
+//   2. otherwise the 1280-point strip of S and of cw is staged with one TMA bulk copy each
+//      (cp.async.bulk -> UBLKCP, completion on an mbarrier) and, per live start block, the bound test is repeated
+//      on 32x32 sub-blocks, warp-uniformly (warp <-> 32 starts, lane <-> end sub-block).
 static const int BAND_SUB = 32;
-static const int BAND_PTS = 2 * CBS_BLK;
+static const int BAND_BLOCKS = CBS_IW;                          // start blocks per CTA
+static const int BAND_PTS = (BAND_BLOCKS + 1) * CBS_BLK;        // 1280 staged points
+static const int BAND_NSUB = BAND_PTS / BAND_SUB;               // 40 sub-blocks
 
 template <bool PRUNE>
 __global__ void __launch_bounds__(256)
-cbs_band_kernel(Node* __restrict__ nodes, const int* __restrict__ blk_node,
+cbs_band_kernel(Node* __restrict__ nodes, const int* __restrict__ iblk_node,
                 const double* __restrict__ S, const double* __restrict__ cw,
                 const double* __restrict__ blk_min, const double* __restrict__ blk_max,
                 const double* __restrict__ blk_wmin, int al0, unsigned long long* __restrict__ stats) {
     __shared__ __align__(16) double sS[BAND_PTS + 4], sC[BAND_PTS + 4];
     __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ double s_mn[BAND_PTS / BAND_SUB], s_mx[BAND_PTS / BAND_SUB];
+    __shared__ double s_mn[BAND_NSUB], s_mx[BAND_NSUB];
     __shared__ double s_q[8];
     __shared__ int s_i[8], s_j[8];
+    __shared__ double s_gq;
+    __shared__ unsigned s_live;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int a = blk_node[blockIdx.x];
+    const int a = iblk_node[blockIdx.x];
     Node* nd = &nodes[a];
     if (nd->flat) return;
     const int lo = nd->lo, n = nd->hi - nd->lo, boff = nd->blk_off;
-    const int bi = blockIdx.x - boff;
+    const int ib = blockIdx.x - nd->iblk_off;
     const int nb = (n + 1 + CBS_BLK - 1) / CBS_BLK;
-    const int ibase = bi * CBS_BLK;
+    const int ibase = ib * CBS_IBLK;                 // first point of the CTA
     const int npts = min(BAND_PTS, n + 1 - ibase);   // points ibase .. ibase+npts-1 (<= n)
     const double total = nd->total;
-    __shared__ double s_gq;
     if (tid == 0) s_gq = *((volatile double*)&nd->best_q);   // one read: the early exit below must be CTA-uniform
     __syncthreads();
     const double gq = s_gq;
-    if (PRUNE && gq >= 0.0) {
-        // CTA-level bound (uniform: every thread reads the same few words)
-        double mn = blk_min[boff + bi], mx = blk_max[boff + bi];
-        if (bi + 1 < nb) { mn = fmin(mn, blk_min[boff + bi + 1]); mx = fmax(mx, blk_max[boff + bi + 1]); }
-        const double dm = mx - mn;
-        const double cmin = blk_wmin[boff + bi];
-        const double cmax = pt(cw, lo, ibase + npts - 1) - pt(cw, lo, ibase);
-        const double fmin_ = fmin(cmin * (total - cmin), cmax * (total - cmax));
-        if (fmin_ > 0.0 && (dm * dm) / fmin_ * (1.0 + 1e-9) < gq) return;
+    // CTA-level bound per start block (lanes 0..3 of warp 0)
+    if (tid < 32) {
+        bool live = false;
+        const int bi = BAND_BLOCKS * ib + tid;
+        if (tid < BAND_BLOCKS && bi < nb) {
+            live = true;
+            if (PRUNE && gq >= 0.0) {
+                double mn = blk_min[boff + bi], mx = blk_max[boff + bi];
+                if (bi + 1 < nb) { mn = fmin(mn, blk_min[boff + bi + 1]); mx = fmax(mx, blk_max[boff + bi + 1]); }
+                const double dm = mx - mn;
+                const double cmin = blk_wmin[boff + bi];
+                const int p0 = bi * CBS_BLK, p1 = min(p0 + 2 * CBS_BLK - 1, n);
+                const double cmax = pt(cw, lo, p1) - pt(cw, lo, p0);
+                const double fmin_ = fmin(cmin * (total - cmin), cmax * (total - cmax));
+                if (fmin_ > 0.0 && (dm * dm) / fmin_ * (1.0 + 1e-9) < gq) live = false;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (tid == 0) s_live = m;
     }
+    __syncthreads();
+    const unsigned live_mask = s_live;
+    if (live_mask == 0) return;
     // stage points ibase .. ibase+npts-1: point p > 0 is array element lo+p-1, point 0 is the constant 0.
     // The copied range is widened to 16-byte alignment; slot(g) = g - a0 + 2 keeps a free slot for point 0.
     const int g0 = lo + max(ibase, 1) - 1, g1 = lo + ibase + npts - 1;      // elements [g0, g1)
@@ -885,40 +947,44 @@ cbs_band_kernel(Node* __restrict__ nodes, const int* __restrict__ blk_node,
     best.i = 0x7fffffff;
     best.j = 0x7fffffff;
     unsigned my_pairs = 0;
-    const int il = warp * BAND_SUB + lane;          // this lane's start point (local)
-    if (warp * BAND_SUB < npts && warp * BAND_SUB < CBS_BLK) {
+    const unsigned kw_span = (unsigned)(n - 2 * al0);   // al0 <= kw <= n - al0  <=>  kw - al0 <= n - 2 al0
+    for (int r = 0; r < BAND_BLOCKS; ++r) {
+        if (!(live_mask & (1u << r))) continue;
+        const int ssb = 8 * r + warp;                   // this warp's sub-block of starts (in the strip)
+        if (ssb * BAND_SUB >= npts) continue;
+        const int il = ssb * BAND_SUB + lane;           // this lane's start point (local)
         const int i = ibase + il;
         const bool iok = il < npts;
         // lanes without a start point carry NaN so that their comparisons are all false
         const double Si = iok ? pS[il] : __longlong_as_double(0x7ff8000000000000ll), ci = iok ? pC[il] : 0.0;
-        const unsigned kw_span = (unsigned)(n - 2 * al0);   // al0 <= kw <= n - al0  <=>  kw - al0 <= n - 2 al0
-        const int wend = min(warp * BAND_SUB + BAND_SUB - 1, npts - 1);
+        const int wend = min(ssb * BAND_SUB + BAND_SUB - 1, npts - 1);
         // weight of the lightest al0-wide window that starts in this warp's sub-block
         double wmin = (il + al0 < npts) ? pC[il + al0] - ci : INFINITY;
         if (PRUNE) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
         }
-        // lane <-> end sub-block: one bound test each, then walk the survivors (warp-uniform)
+        // lane <-> end sub-block 8r + lane (the block's own 8 sub-blocks and the 8 of the next block)
+        const int send = min(8 * r + 16, nsub);
         unsigned need = 0;
         {
-            const int sb = lane;
-            bool keep = sb >= warp && sb < nsub;
+            const int sb = 8 * r + lane;
+            bool keep = sb >= ssb && sb < send;
             if (PRUNE && keep && gq >= 0.0) {
                 const int j0 = sb * BAND_SUB, j1 = min(j0 + BAND_SUB - 1, npts - 1);
-                const double d1 = s_mx[sb] - s_mn[warp], d2 = s_mx[warp] - s_mn[sb];
+                const double d1 = s_mx[sb] - s_mn[ssb], d2 = s_mx[ssb] - s_mn[sb];
                 const double dm = fmax(fabs(d1), fabs(d2));
                 // lightest arc: for the own and the next sub-block every admissible arc holds an
                 // al0-wide window that starts in this warp's sub-block (the weights are >= 0)
-                const double cmin = (sb > warp + 1) ? pC[j0] - pC[wend] : wmin;
-                const double cmax = pC[j1] - pC[warp * BAND_SUB];
+                const double cmin = (sb > ssb + 1) ? pC[j0] - pC[wend] : wmin;
+                const double cmax = pC[j1] - pC[ssb * BAND_SUB];
                 const double fmin_ = fmin(cmin * (total - cmin), cmax * (total - cmax));
                 if (fmin_ > 0.0 && (dm * dm) / fmin_ * (1.0 + 1e-9) < gq) keep = false;
             }
             need = __ballot_sync(0xffffffffu, keep);
         }
         while (need) {
-            const int sb = __ffs(need) - 1;
+            const int sb = 8 * r + __ffs(need) - 1;
             need &= need - 1;
             const int j0 = sb * BAND_SUB, j1 = min(j0 + BAND_SUB - 1, npts - 1);
             ++my_pairs;
@@ -1000,9 +1066,11 @@ cbs_scan_kernel(Node* __restrict__ nodes, const TileRef* __restrict__ queue, con
                 int* __restrict__ pop_counter, const double* __restrict__ S, const double* __restrict__ cw,
                 const double* __restrict__ blk_min, const double* __restrict__ blk_max, int al0,
                 unsigned long long* __restrict__ stats) {
+    // work unit = ONE 256 x 256 sub-tile (start block r of a queued 1024 x 256 tile): 4 units per queue entry, so
+    // that the few hundred surviving tiles of a level spread evenly over the SMs' FP64 pipes
     __shared__ double2 sj[CBS_BLK];
     __shared__ int s_idx;
-    __shared__ unsigned s_mask;
+    __shared__ int s_keep;
     __shared__ double s_q[8];
     __shared__ int s_i[8], s_j[8];
     const int tid = threadIdx.x;
@@ -1012,55 +1080,42 @@ cbs_scan_kernel(Node* __restrict__ nodes, const TileRef* __restrict__ queue, con
         __syncthreads();
         if (tid == 0) s_idx = atomicAdd(pop_counter, 1);
         __syncthreads();
-        const int idx = s_idx;
-        if (idx >= nq) break;
-        const TileRef e = queue[idx];
+        const int unit = s_idx;
+        const int ent = unit >> 2, r = unit & 3;
+        if (ent >= nq) break;
+        const TileRef e = queue[ent];
+        if (!(e.mask & (1u << r))) continue;
         Node* nd = &nodes[e.node];
         const int lo = nd->lo, n = nd->hi - nd->lo, boff = nd->blk_off;
         const int P = n + 1;
-        const int ib = e.ib, jb = e.jb;
+        const int bi = CBS_IW * e.ib + r, jb = e.jb;
         const double total = nd->total;
-        const double gq = *((volatile double*)&nd->best_q);
-        unsigned mask = e.mask;
-        if (PRUNE) {
-            // the best may have risen since the bound kernel ran: re-test (warp 0, one lane per start block)
-            if (tid < 32) {
-                bool keep = false;
-                if (tid < CBS_IW && (mask & (1u << tid))) {
-                    const int bi = CBS_IW * ib + tid;
-                    keep = !(bi < jb && gq >= 0.0) || tile_needed(cw, blk_min, blk_max, lo, n, boff, bi, jb, total, gq);
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                if (tid == 0) s_mask = m;
-            }
-            __syncthreads();
-            mask = s_mask;
-            if (mask == 0) continue;
+        if (tid == 0) {
+            // the best may have risen since the bound kernel ran: re-test
+            const double gq0 = *((volatile double*)&nd->best_q);
+            s_keep = (!PRUNE || !(bi < jb && gq0 >= 0.0) || tile_needed(cw, blk_min, blk_max, lo, n, boff, bi, jb, total, gq0)) ? 1 : 0;
+            s_q[0] = gq0;
         }
+        __syncthreads();
+        if (!s_keep) continue;
+        const double gq = s_q[0];
         const int jbase = jb * CBS_BLK;
         const int jcount = min(CBS_BLK, P - jbase);
         const int jend = jbase + jcount - 1;
-        const int na = __popc(mask);
-        bool masked = false;
-#pragma unroll
-        for (int r = 0; r < CBS_IW; ++r) {
-            if (!(mask & (1u << r))) continue;
-            const int ibase = (CBS_IW * ib + r) * CBS_BLK;
-            const int iend = min(ibase + CBS_BLK - 1, n);
-            if (!(jbase - iend >= al0 && jend - ibase <= n - al0 && ibase + CBS_BLK - 1 <= n)) masked = true;
-        }
-        my_scanned += (tid == 0) ? na : 0;
+        const int ibase = bi * CBS_BLK;
+        const int iend = min(ibase + CBS_BLK - 1, n);
+        const bool masked = !(jbase - iend >= al0 && jend - ibase <= n - al0 && ibase + CBS_BLK - 1 <= n);
+        my_scanned += (tid == 0) ? 1 : 0;
+        __syncthreads();                                   // s_q[0] is reused by cta_commit
         if (tid < jcount) sj[tid] = make_double2(pt(S, lo, jbase + tid), pt(cw, lo, jbase + tid));
-        double Si[CBS_IW], ci[CBS_IW];
-        int ii[CBS_IW];
-#pragma unroll
-        for (int r = 0; r < CBS_IW; ++r) {
-            const int slot = (int)__fns(mask, 0, (r < na) ? r + 1 : 1);
-            const int i = (CBS_IW * ib + slot) * CBS_BLK + tid;
-            ii[r] = i;
+        double Si[1], ci[1];
+        int ii[1];
+        {
+            const int i = ibase + tid;
+            ii[0] = i;
             const bool ok = i <= n;
-            Si[r] = ok ? pt(S, lo, i) : 0.0;
-            ci[r] = ok ? pt(cw, lo, i) : 0.0;
+            Si[0] = ok ? pt(S, lo, i) : 0.0;
+            ci[0] = ok ? pt(cw, lo, i) : 0.0;
         }
         Cand best;
         best.q = gq;
@@ -1068,21 +1123,8 @@ cbs_scan_kernel(Node* __restrict__ nodes, const TileRef* __restrict__ queue, con
         best.i = 0x7fffffff;
         best.j = 0x7fffffff;
         __syncthreads();
-        if (masked) {
-            switch (na) {
-                case 1: scan_subtiles<1, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                case 2: scan_subtiles<2, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                case 3: scan_subtiles<3, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                default: scan_subtiles<4, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-            }
-        } else {
-            switch (na) {
-                case 1: scan_subtiles<1, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                case 2: scan_subtiles<2, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                case 3: scan_subtiles<3, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-                default: scan_subtiles<4, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0); break;
-            }
-        }
+        if (masked) scan_subtiles<1, true>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0);
+        else scan_subtiles<1, false>(best, sj, Si, ci, ii, jbase, jcount, total, n, al0);
         cta_commit(nd, best.q, best.i, best.j, s_q, s_i, s_j);
     }
     if (stats && tid == 0 && my_scanned) atomicAdd(&stats[0], my_scanned);
@@ -1254,7 +1296,8 @@ __device__ __forceinline__ void block_append(bool flag, int value, int* __restri
 // single CTA: finish the tail probabilities, the hybrid decisions and the two permutation lists (node order)
 __global__ void __launch_bounds__(1024)
 cbs_decide_kernel(Node* __restrict__ nodes, int nnodes, const double* __restrict__ terms, double alpha, int nperm,
-                  int ngrid, int diag, int* __restrict__ hyb_list, int* __restrict__ exact_list, Ctl* __restrict__ ctl) {
+                  int ngrid, int diag, int* __restrict__ hyb_list, int* __restrict__ exact_list, Ctl* __restrict__ ctl,
+                  unsigned long long* __restrict__ dmin_bits, int* __restrict__ act, int* __restrict__ act_toff) {
     __shared__ int s_warp[32];
     __shared__ int s_nh, s_ne;
     if (threadIdx.x == 0) { s_nh = 0; s_ne = 0; }
@@ -1285,7 +1328,20 @@ cbs_decide_kernel(Node* __restrict__ nodes, int nnodes, const double* __restrict
         block_append(state == ST_PERM_HYBRID, idx, hyb_list, &s_nh, s_warp, 32);
         block_append(state == ST_PERM_EXACT, idx, exact_list, &s_ne, s_warp, 32);
     }
+    __syncthreads();
+    // hybrid test set-up: limits table reset, first active list and its tile prefix
+    for (int k = threadIdx.x; k < s_nh * HYB_LIM; k += 1024)
+        dmin_bits[(size_t)hyb_list[k / HYB_LIM] * HYB_LIM + (k % HYB_LIM)] = 0x7f7f7f7f7f7f7f7full;
+    for (int a = threadIdx.x; a < s_nh; a += 1024) act[a] = hyb_list[a];
     if (threadIdx.x == 0) {
+        int t = 0;
+        for (int a = 0; a < s_nh; ++a) {
+            act_toff[a] = t;
+            const Node* nd = &nodes[hyb_list[a]];
+            t += (nd->hi - nd->lo + HYB_TP - 1) / HYB_TP;
+        }
+        act_toff[s_nh] = t;
+        ctl->n_act = s_nh;
         ctl->n_hyb = s_nh;
         ctl->n_exact = s_ne;
         ctl->stats[3] += (unsigned long long)(s_nh + s_ne);
@@ -1316,15 +1372,63 @@ struct PermArgs {
 
 static const int PERM_THREADS = 256;
 
-// CTA 0 after a chunk: exceedance flags in permutation order -> nrej / boundary index -> decision;
-// survivors are compacted (order kept) into the other half of `act`; tile prefix for the hybrid kernel.
-__device__ void perm_replay(const PermArgs& A, const unsigned long long* pm, int n_act, int p0, int chunk, int cur,
-                            bool hybrid, int* s_cnt, int* s_warp) {
+// After a chunk, every CTA: one WARP per still-active node turns the chunk's permutation maxima into exceedance
+// flags (32 at a time, coalesced) and replays DNAcopy's sequential rule over them -- at permutation np (in order):
+// an exceedance raises nrej and the boundary index kk; nrej > nrejc -> no split; np >= sbdry[kk] -> split.  Between
+// two exceedances kk does not change, so a run of clean permutations is decided by one comparison.
+__device__ void perm_decide(const PermArgs& A, const unsigned long long* pm, int n_act, int p0, int chunk, int cur,
+                            bool hybrid) {
+    const int* act_cur = A.act + (size_t)cur * A.cap;
+    const int lane = threadIdx.x & 31;
+    const int warps = blockDim.x >> 5;
+    const bool last_chunk = p0 + chunk >= A.nperm;
+    for (int a = blockIdx.x * warps + (threadIdx.x >> 5); a < n_act; a += gridDim.x * warps) {
+        const int node = act_cur[a];
+        Node* nd = &A.nodes[node];
+        const int n = nd->hi - nd->lo, nrejc = nd->nrejc;
+        const double tss = nd->tss, ostat = nd->ostat;
+        int nrej = nd->nrej, kk = nd->kk, decided = 0;
+        for (int g0 = 0; g0 < chunk && !decided; g0 += 32) {
+            const int c = g0 + lane;
+            bool flag = false;
+            if (c < chunk) {
+                const double pb = __longlong_as_double((long long)__ldcg(&pm[(size_t)a * chunk + c]));
+                flag = ostat <= t2_of(pb, tss, n);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, flag);
+            if (A.diag) { nrej += __popc(mask); kk += __popc(mask); continue; }
+            const int gend = min(g0 + 32, chunk);
+            int cur_c = g0;
+            while (!decided) {                                   // warp-uniform
+                const int e = mask ? g0 + __ffs(mask) - 1 : gend;
+                // clean permutations c in [cur_c, e): np = p0 + c + 1 reaches at most p0 + e
+                if (e > cur_c && A.sbdry[kk - 1] <= p0 + e) { decided = 1; break; }
+                if (e >= gend) break;
+                ++nrej; ++kk;                                    // exceedance at np = p0 + e + 1
+                if (nrej > nrejc) { decided = -1; break; }
+                if (p0 + e + 1 >= A.sbdry[kk - 1]) { decided = 1; break; }
+                mask &= mask - 1;
+                cur_c = e + 1;
+            }
+        }
+        if (decided == 0 && last_chunk) decided = 1;             // survived every permutation
+        if (lane == 0) {
+            nd->nrej = nrej;
+            nd->kk = kk;
+            if (decided) nd->state = decided > 0 ? ST_SPLIT : ST_FINAL;
+            const long long arcs = hybrid ? (long long)n * (A.kmax - A.al0 + 1) * chunk : (long long)n * n / 2 * chunk;
+            atomicAdd(&A.ctl->stats[5], (unsigned long long)arcs);
+        }
+    }
+}
+
+// CTA 0: the nodes still in their permutation test, compacted (order kept) into the other half of `act`;
+// tile prefix for the hybrid kernel
+__device__ void perm_compact(const PermArgs& A, int n_act, int chunk, int cur, bool hybrid, int* s_cnt, int* s_warp) {
     const int* act_cur = A.act + (size_t)cur * A.cap;
     int* act_nxt = A.act + (size_t)(cur ^ 1) * A.cap;
     if (threadIdx.x == 0) *s_cnt = 0;
     __syncthreads();
-    const bool last_chunk = p0 + chunk >= A.nperm;
     const int nthr = blockDim.x;
     for (int base = 0; base < n_act; base += nthr) {
         const int a = base + threadIdx.x;
@@ -1332,25 +1436,8 @@ __device__ void perm_replay(const PermArgs& A, const unsigned long long* pm, int
         int node = 0;
         if (a < n_act) {
             node = act_cur[a];
-            Node* nd = &A.nodes[node];
-            const int n = nd->hi - nd->lo, nrejc = nd->nrejc;
-            const double tss = nd->tss, ostat = nd->ostat;
-            int nrej = nd->nrej, kk = nd->kk, decided = 0;
-            for (int c = 0; c < chunk && !decided; ++c) {
-                const int np = p0 + c + 1;
-                const double pb = __longlong_as_double((long long)pm[(size_t)a * chunk + c]);
-                if (ostat <= t2_of(pb, tss, n)) { ++nrej; ++kk; }
-                if (A.diag) continue;
-                if (nrej > nrejc) decided = -1;
-                else if (np >= A.sbdry[kk - 1]) decided = 1;
-            }
-            if (decided == 0 && last_chunk) decided = 1;          // survived every permutation
-            nd->nrej = nrej;
-            nd->kk = kk;
-            if (decided) nd->state = decided > 0 ? ST_SPLIT : ST_FINAL;
-            keep = decided == 0;
-            const long long arcs = hybrid ? (long long)n * (A.kmax - A.al0 + 1) * chunk : (long long)n * n / 2 * chunk;
-            atomicAdd(&A.ctl->stats[5], (unsigned long long)arcs);
+            const int st_ = *((volatile int*)&A.nodes[node].state);
+            keep = st_ == ST_PERM_HYBRID || st_ == ST_PERM_EXACT;
         }
         block_append(keep, node, act_nxt, s_cnt, s_warp, nthr / 32);
     }
@@ -1400,40 +1487,83 @@ static const int HYB_SMEM_T = (HYB_TP + HYB_KMAX) + (HYB_TP + HYB_KMAX) / 4 + 8;
 // of the node and an arc is dropped when |acc| < sqrt(q_thr min_s den(s,k)).  The hot loop therefore costs ONE
 // FP64 add per arc plus an integer compare of the high word of |acc| against a conservative limit; a group of
 // 4 starts that trips the filter is re-walked with the exact test of the running-sum square.
-template <int KMAX_T, int AL0_T>
-__device__ __forceinline__ void hyb_tile(const PermArgs& A, int node, int s0, int perm, double* s_t, double* s_lim,
-                                         u32* s_limhi, double* s_best, unsigned long long* pmax_slot) {
-    const Node nd = A.nodes[node];
-    const int n = nd.hi - nd.lo, lo = nd.lo;
-    const int kmax = KMAX_T > 0 ? KMAX_T : A.kmax, al0 = AL0_T > 0 ? AL0_T : A.al0;
+// limits of one node (shared by every tile and permutation of that node): kept in shared memory while
+// consecutive work items of the CTA belong to the same node
+struct HybNodeCtx {
+    int node, lo, n, base;
+    double total;
+};
+
+__device__ __forceinline__ void hyb_node_ctx(const PermArgs& A, int node, HybNodeCtx* ctx, double* s_lim, u32* s_limhi) {
     const int tid = threadIdx.x;
-    Prp prp;
-    prp.init(A.seed, (u32)(nd.lo - nd.base), (u32)(nd.hi - nd.base), 0u, (u32)perm, (u32)n);
-    const int count = min(HYB_TP, n - s0);
-    const int need = count + kmax - 1;
-    for (int k = tid; k < HYB_TP + HYB_KMAX; k += PERM_THREADS) {
-        double v = 0.0;
-        if (k < need) {
-            int pos = s0 + k;
-            if (pos >= n) pos -= n;
-            v = __dmul_rn(A.y[lo + prp((u32)pos)], A.rw[lo + pos]);
-        }
-        s_t[hyb_idx(k)] = v;
-    }
+    const int kmax = A.kmax, al0 = A.al0;
+    if (ctx->node == node) return;                         // uniform: ctx lives in shared memory
+    __syncthreads();
+    const Node* nd = &A.nodes[node];
+    const int n = nd->hi - nd->lo;
     if (tid <= kmax) {
         // smallest BSS whose T^2 reaches ostat: bss (n-2) / (tss - bss) >= ostat (t2_of is increasing there);
         // no pruning when tss is so small that t2_of's guard (tss <= bss + 1e-4) could come into play
         const double nm2 = (double)n - 2.0;
-        const double qthr = nd.ostat * nd.tss / (nm2 + nd.ostat) * (1.0 - 1e-9);
-        const bool safe = nd.tss * nm2 / (nm2 + nd.ostat) > 1e-3 && nd.ostat > 0.0 && tid >= al0;
+        const double ostat = nd->ostat, tss = nd->tss;
+        const double qthr = ostat * tss / (nm2 + ostat) * (1.0 - 1e-9);
+        const bool safe = tss * nm2 / (nm2 + ostat) > 1e-3 && ostat > 0.0 && tid >= al0;
         const double dm = __longlong_as_double((long long)A.dmin_bits[(size_t)node * HYB_LIM + tid]);
         const double lim = safe ? qthr * dm * (1.0 - 1e-12) : 0.0;
         s_lim[tid] = lim;
         // |acc| >= sqrt(lim) (1 - 1e-9) is implied by acc^2 >= lim; compare high words (monotone for doubles >= 0)
         s_limhi[tid] = (u32)__double2hiint(sqrt(lim) * (1.0 - 1e-9));
     }
+    if (tid == 0) {
+        ctx->lo = nd->lo; ctx->n = n; ctx->base = nd->base; ctx->total = nd->total;
+        ctx->node = node;
+    }
     __syncthreads();
-    const double total = nd.total;
+}
+
+static const int HYB_STAGE_IT = (HYB_TP + HYB_KMAX + PERM_THREADS - 1) / PERM_THREADS;   // 9 elements per thread
+
+template <int KMAX_T, int AL0_T>
+__device__ __forceinline__ void hyb_tile(const PermArgs& A, const HybNodeCtx* ctx, int s0, int perm, double* s_t,
+                                         const double* s_lim, const u32* s_limhi, double* s_best,
+                                         unsigned long long* pmax_slot) {
+    const int n = ctx->n, lo = ctx->lo;
+    const int kmax = KMAX_T > 0 ? KMAX_T : A.kmax, al0 = AL0_T > 0 ? AL0_T : A.al0;
+    const int tid = threadIdx.x;
+    Prp prp;
+    prp.init(A.seed, (u32)(lo - ctx->base), (u32)(lo + n - ctx->base), 0u, (u32)perm, (u32)n);
+    const int count = min(HYB_TP, n - s0);
+    const int need = count + kmax - 1;
+    {
+        // permutation + gather prologue, unrolled so that the 9 Feistel evaluations and the 9 scattered loads of
+        // a thread are independent instruction streams (the cycle walk of the few out-of-range values comes after)
+        u32 pv[HYB_STAGE_IT];
+        int ps[HYB_STAGE_IT];
+#pragma unroll
+        for (int it = 0; it < HYB_STAGE_IT; ++it) {
+            const int k = tid + it * PERM_THREADS;
+            int pos = s0 + k;
+            if (pos >= n) pos -= n;
+            if (k >= need) pos = 0;
+            ps[it] = pos;
+            pv[it] = prp.once((u32)pos);
+        }
+#pragma unroll
+        for (int it = 0; it < HYB_STAGE_IT; ++it) pv[it] = prp.walk(pv[it]);
+        double yv[HYB_STAGE_IT], rv[HYB_STAGE_IT];
+#pragma unroll
+        for (int it = 0; it < HYB_STAGE_IT; ++it) {
+            yv[it] = A.y[lo + pv[it]];
+            rv[it] = A.rw[lo + ps[it]];
+        }
+#pragma unroll
+        for (int it = 0; it < HYB_STAGE_IT; ++it) {
+            const int k = tid + it * PERM_THREADS;
+            if (k < HYB_TP + HYB_KMAX) s_t[hyb_idx(k)] = (k < need) ? __dmul_rn(yv[it], rv[it]) : 0.0;
+        }
+    }
+    __syncthreads();
+    const double total = ctx->total;
     double best = 0.0, bestlo = 0.0;
     if (KMAX_T > 0) {
         for (int grp = tid; 4 * grp < count; grp += PERM_THREADS) {
@@ -1502,10 +1632,11 @@ __device__ __forceinline__ void hyb_bounds_tile(const PermArgs& A, int node, int
     const int kmax = A.kmax, al0 = A.al0;
     const int count = min(HYB_TP, n - s0);
     const int need = count + kmax - 1;
+    const double rsw = nd.rsw;
     for (int k = tid; k < need; k += PERM_THREADS) {
         int pos = s0 + k;
         if (pos >= n) pos -= n;
-        s_w[k] = A.wn[lo + pos];
+        s_w[k] = __ddiv_rn(A.w[lo + pos], rsw);       // = wn[lo + pos], which phase 0 is writing concurrently
     }
     __syncthreads();
     double dmin[HYB_LIM];
@@ -1555,7 +1686,7 @@ __device__ __forceinline__ int chunk_for(int sched, int n_act, long long pm_entr
 }
 
 template <int KMAX_T, int AL0_T>
-__global__ void __launch_bounds__(PERM_THREADS, 2)
+__global__ void __launch_bounds__(PERM_THREADS, 3)
 cbs_perm_hybrid_kernel(PermArgs A) {
     cg::grid_group grid = cg::this_grid();
     __shared__ __align__(16) double s_t[HYB_SMEM_T];
@@ -1563,11 +1694,16 @@ cbs_perm_hybrid_kernel(PermArgs A) {
     __shared__ u32 s_limhi[HYB_LIM];
     __shared__ double s_best[PERM_THREADS / 32];
     __shared__ int s_cnt, s_warp[PERM_THREADS / 32];
+    __shared__ HybNodeCtx s_ctx;
     const int n_list = A.ctl->n_hyb;
     if (n_list == 0) return;                               // uniform over the grid
     const int tid = threadIdx.x;
+    if (tid == 0) s_ctx.node = -1;
+    long long tk = clock64();
+    const bool timer = blockIdx.x == 0 && tid == 0;
     const long long gtid = (long long)blockIdx.x * PERM_THREADS + tid, gsize = (long long)gridDim.x * PERM_THREADS;
-    // ---- phase 0: exchangeable terms and normalised weights of the listed nodes; limits reset; active list
+    // ---- phase 0: exchangeable terms and normalised weights of the listed nodes; active list.  The limits table
+    // (dmin_bits) was reset by the decide kernel, so the limits pass below needs no barrier after this one.
     for (int li = 0; li < n_list; ++li) {
         const int node = A.list[li];
         const Node* nd = &A.nodes[node];
@@ -1578,39 +1714,30 @@ cbs_perm_hybrid_kernel(PermArgs A) {
             A.y[g] = __dmul_rn(__dsub_rn(A.x[g], avg), A.rw[g]);
             A.wn[g] = __ddiv_rn(wv, rsw);
         }
-        for (long long k = gtid; k < HYB_LIM; k += gsize) A.dmin_bits[(size_t)node * HYB_LIM + k] = 0x7f7f7f7f7f7f7f7full;
-    }
-    if (blockIdx.x == 0) {
-        for (int a = tid; a < n_list; a += PERM_THREADS) A.act[a] = A.list[a];
-        __syncthreads();
-        if (tid == 0) {
-            int t = 0;
-            for (int a = 0; a < n_list; ++a) {
-                A.act_toff[a] = t;
-                const Node* nd = &A.nodes[A.list[a]];
-                t += (nd->hi - nd->lo + HYB_TP - 1) / HYB_TP;
-            }
-            A.act_toff[n_list] = t;
-            A.ctl->n_act = n_list;
-        }
     }
     {   // first chunk's maxima buffer
-        const long long z = (long long)n_list * chunk_for(64, n_list, A.pm_entries, A.nperm);
+        const long long z = (long long)n_list * chunk_for(PERM_CHUNK_FIRST, n_list, A.pm_entries, A.nperm);
         for (long long k = gtid; k < z; k += gsize) A.pmax[k] = 0ull;
     }
-    grid.sync();
-    // ---- phase 1: pruning limits (smallest arc denominators per width)
+    // ---- phase 1: pruning limits (smallest arc denominators per width); tiles straight from the list
     {
-        const int ntile = A.act_toff[n_list];
         double (*s_min)[HYB_LIM] = reinterpret_cast<double (*)[HYB_LIM]>(s_t + HYB_TP + HYB_KMAX);
-        for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
-            const int a = find_slot(A.act_toff, n_list, t);
-            hyb_bounds_tile(A, A.act[a], (t - A.act_toff[a]) * HYB_TP, s_t, s_min);
+        int t_base = 0;
+        for (int li = 0; li < n_list; ++li) {
+            const int node = A.list[li];
+            const Node* nd = &A.nodes[node];
+            const int nt = (nd->hi - nd->lo + HYB_TP - 1) / HYB_TP;
+            // tile t of this node is global tile t_base + t; CTA b takes the global tiles congruent to b
+            for (int t = 0; t < nt; ++t)
+                if ((t_base + t) % (int)gridDim.x == (int)blockIdx.x) hyb_bounds_tile(A, node, t * HYB_TP, s_t, s_min);
+            t_base += nt;
         }
     }
+    if (timer) { const long long t = clock64(); A.ctl->tprof[0] += t - tk; tk = t; }
     grid.sync();
+    if (timer) { const long long t = clock64(); A.ctl->tprof[1] += t - tk; tk = t; }
     // ---- chunks of permutations
-    int p0 = 0, sched = 64, cur = 0, buf = 0;
+    int p0 = 0, sched = PERM_CHUNK_FIRST, cur = 0, buf = 0;
     for (;;) {
         const int n_act = *((volatile int*)&A.ctl->n_act);
         if (n_act == 0 || p0 >= A.nperm) break;
@@ -1623,7 +1750,8 @@ cbs_perm_hybrid_kernel(PermArgs A) {
         for (long long it = blockIdx.x; it < items; it += gridDim.x) {
             const int t = (int)(it / chunk), c = (int)(it % chunk);
             const int a = find_slot(A.act_toff, n_act, t);
-            hyb_tile<KMAX_T, AL0_T>(A, act[a], (t - A.act_toff[a]) * HYB_TP, p0 + c, s_t, s_lim, s_limhi, s_best,
+            hyb_node_ctx(A, act[a], &s_ctx, s_lim, s_limhi);
+            hyb_tile<KMAX_T, AL0_T>(A, &s_ctx, (t - A.act_toff[a]) * HYB_TP, p0 + c, s_t, s_lim, s_limhi, s_best,
                                     pm + (size_t)a * chunk + c);
         }
         {   // zero the other buffer for the next chunk (the active list only shrinks)
@@ -1633,9 +1761,14 @@ cbs_perm_hybrid_kernel(PermArgs A) {
         }
         __threadfence();
         grid.sync();
-        if (blockIdx.x == 0) perm_replay(A, pm, n_act, p0, chunk, cur, true, &s_cnt, s_warp);
+        if (timer) { const long long t = clock64(); A.ctl->tprof[2] += t - tk; tk = t; A.ctl->tprof[4] += 1; }
+        perm_decide(A, pm, n_act, p0, chunk, cur, true);
         __threadfence();
         grid.sync();
+        if (blockIdx.x == 0) perm_compact(A, n_act, chunk, cur, true, &s_cnt, s_warp);
+        __threadfence();
+        grid.sync();
+        if (timer) { const long long t = clock64(); A.ctl->tprof[3] += t - tk; tk = t; }
         p0 += chunk;
         sched = min(sched * 4, PERM_CHUNK_MAX);
         cur ^= 1;
@@ -1666,7 +1799,7 @@ cbs_perm_exact_kernel(PermArgs A) {
     }
     __threadfence();
     grid.sync();
-    int p0 = 0, sched = 64, cur = 0;
+    int p0 = 0, sched = PERM_CHUNK_FIRST, cur = 0;
     for (;;) {
         const int n_act = *((volatile int*)&A.ctl->n_act);
         if (n_act == 0 || p0 >= A.nperm) break;
@@ -1718,11 +1851,16 @@ cbs_perm_exact_kernel(PermArgs A) {
         }
         __threadfence();
         grid.sync();
-        if (blockIdx.x == 0) perm_replay(A, A.pmax, n_act, p0, chunk, cur, false, &s_cnt, s_warp);
+        perm_decide(A, A.pmax, n_act, p0, chunk, cur, false);
+        __threadfence();
+        grid.sync();
+        if (blockIdx.x == 0) perm_compact(A, n_act, chunk, cur, false, &s_cnt, s_warp);
         __threadfence();
         grid.sync();
         p0 += chunk;
-        sched = min(sched * 4, PERM_CHUNK_MAX);
+        // exact nodes are tiny (<= nmin bins): a node still undecided after 16 + 64 + 256 permutations almost always
+        // runs to the stopping boundary, and the remaining permutations are only a few waves of warps -- one chunk
+        sched = sched >= 256 ? A.nperm : sched * 4;
         cur ^= 1;
     }
 }
@@ -2011,17 +2149,17 @@ cbs_frontier_kernel(const Node* __restrict__ nodes, int nnodes, const FlankTest*
 }
 
 // weighted.mean(log2, weight) per new segment (cbs.py:70-71); one CTA per segment, grid-stride
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 seg_mean_kernel(const double* __restrict__ x, const double* __restrict__ w, LevelOut* __restrict__ out,
                 const int* __restrict__ extra_lo, const int* __restrict__ extra_hi, double* __restrict__ extra_mean) {
-    __shared__ double s_a[8], s_b[8];
+    __shared__ double s_a[32], s_b[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nseg = out->ctl.overflow ? 0 : out->ctl.nseg_new;
     for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
         const int lo = s < SEG_WINDOW ? out->seg_lo[s] : extra_lo[s - SEG_WINDOW];
         const int hi = s < SEG_WINDOW ? out->seg_hi[s] : extra_hi[s - SEG_WINDOW];
         double sw = 0.0, swx = 0.0;
-        for (int k = lo + threadIdx.x; k < hi; k += 256) {
+        for (int k = lo + threadIdx.x; k < hi; k += 1024) {
             sw += w[k];
             swx += x[k] * w[k];
         }
@@ -2030,7 +2168,7 @@ seg_mean_kernel(const double* __restrict__ x, const double* __restrict__ w, Leve
         if (lane == 0) { s_a[warp] = sw; s_b[warp] = swx; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int k = 1; k < 8; ++k) { sw += s_a[k]; swx += s_b[k]; }
+            for (int k = 1; k < 32; ++k) { sw += s_a[k]; swx += s_b[k]; }
             const double m = swx / sw;
             if (s < SEG_WINDOW) out->seg_mean[s] = m; else extra_mean[s - SEG_WINDOW] = m;
         }
@@ -2181,74 +2319,53 @@ static int coop_grid(const void* fn, int threads, int sm_count, int* cache) {
     return *cache;
 }
 
-int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, const CbsParams& P_in,
-                std::vector<CbsSeg>& segs, CbsStats* stats, cudaStream_t stream, CbsDiag* diag) {
-    // diagnostics (cnvk_cbs_node_diag): every interval is ONE node; one level only, the tail series is always
-    // summed, every node runs all nperm permutations (no stopping rule) and both flank tests with permutations
-    CbsParams P = P_in;
-    if (diag) P.prune |= 2;
-    segs.clear();
-    CbsStats st;
-    memset(&st, 0, sizeof(st));
-    if (n_arms <= 0) { if (stats) *stats = st; return 0; }
-    const long long N = h_off[n_arms];
-    if (N >= (1ll << 31) - 4) { set_last_error("cbs_segment: too many bins (%lld)", N); return -2; }
-    if (P.kmax > HYB_KMAX || P.nmin > EXACT_NMAX || P.min_width < 2 || P.kmax < P.min_width || P.nperm < 1) {
-        set_last_error("cbs_segment: unsupported parameters (kmax<=%d, nmin<=%d, min_width>=2)", HYB_KMAX, EXACT_NMAX);
-        return -2;
-    }
-    if (P.nmin < 2 * P.kmax) { set_last_error("cbs_segment: need nmin >= 2*kmax"); return -2; }
-    static thread_local int sm_count = 0, grid_hyb25 = 0, grid_hyb0 = 0, grid_exact = 0;
-    if (!sm_count) {
-        int dev = 0;
-        CNVK_CHECK(cudaGetDevice(&dev));
-        CNVK_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        CNVK_CHECK(cudaFuncSetAttribute(cbs_prep_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM));
-    }
-    const int max_ones = (int)std::floor((double)P.nperm * P.alpha) + 1;
-    // the stopping boundary depends on (eta, nperm, max.ones) only and costs ~nperm * max.ones * 20 flops to
-    // build: keep the last one per thread
-    static thread_local std::vector<int> sbdry;
-    static thread_local double sb_eta = -1.0;
-    static thread_local int sb_nperm = -1, sb_ones = -1;
-    if (sb_eta != P.eta || sb_nperm != P.nperm || sb_ones != max_ones) {
-        cbs_getbdry(P.eta, P.nperm, max_ones, sbdry);
-        sb_eta = P.eta; sb_nperm = P.nperm; sb_ones = max_ones;
-    }
+// Shared, read-only context of one cbs_segment call
+struct CbsShared {
+    const double *d_x, *d_w;
+    double *d_rw, *d_y, *d_wn, *d_S, *d_cw;
+    const int* d_sbdry;
+    CbsParams P;
+    int sm_count, hk, ngrid;
+    bool diag;
+};
 
-    g_pinned.rewind();
-    Scratch scratch(stream);
-    double *d_rw, *d_y, *d_S, *d_cw, *d_wn;
-    int* d_sbdry;
-    LevelOut* d_out;
-    CNVK_CHECK(scratch.alloc(&d_rw, (size_t)N));
-    CNVK_CHECK(scratch.alloc(&d_y, (size_t)N));
-    CNVK_CHECK(scratch.alloc(&d_wn, (size_t)N));
-    CNVK_CHECK(scratch.alloc(&d_S, (size_t)N + 4));      // + slack: the band kernel's bulk copies are widened to 16 B
-    CNVK_CHECK(scratch.alloc(&d_cw, (size_t)N + 4));
-    CNVK_CHECK(scratch.alloc(&d_sbdry, sbdry.size()));
-    CNVK_CHECK(scratch.alloc(&d_out, 1));
-    {
-        int* p_sb = g_pinned.put(sbdry.data(), sbdry.size());
-        CNVK_PIN_CHECK(p_sb);
-        CNVK_CHECK(cudaMemcpyAsync(d_sbdry, p_sb, sbdry.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-    }
-    CNVK_CHECK(cudaMemsetAsync(d_out, 0, sizeof(Ctl), stream));
-    if (N > 0) {
-        sqrt_kernel<<<div_up(N, 256), 256, 0, stream>>>(d_w, d_rw, N);
-        CNVK_LAUNCH_CHECK();
-    }
-    Ctl* d_ctl = &d_out->ctl;
-    unsigned long long* d_stats = d_ctl->stats;
+static thread_local int g_grid_hyb25 = 0, g_grid_hyb0 = 0, g_grid_exact = 0;
 
-    // ---- level 1: the arms (host-built; every later level comes from the frontier kernel)
+// One GROUP of arms walking down its recursion on its own stream.  A call normally runs ONE group; the state is kept
+// per group so that two independent chains can be interleaved on two streams (CNVK_CBS_GROUPS=2, see cbs_segment --
+// it does not pay while the chain contains cooperative kernels).  Groups touch disjoint bins of the shared columns.
+struct CbsRun {
+    const CbsShared* sh = nullptr;
+    cudaStream_t stream = nullptr;
+    LevelOut* d_out = nullptr;
+    LevelOut* h_out = nullptr;
+    Grow<Node> nodes_a, nodes_b;
+    Grow<Node>*cur = &nodes_a, *nxt = &nodes_b;
+    Grow<int> ptile_node, blk_node, iblk_node, need_list, hyb_list, exact_list, act, act_toff, fperm_list, tmp_list;
+    Grow<int> bimin, bimax, extra_lo, extra_hi;
+    Grow<double> bmin, bmax, bcmin, bcmax, bwmin, terms, fpart, extra_mean;
+    Grow<TileSums> part1;
+    Grow<TileScan> part3;
+    Grow<SeedRes> seedres;
+    Grow<TileRef> queue;
+    Grow<unsigned long long> dmin_bits, pmax;
+    Grow<FlankTest> tests;
     std::vector<Node> h_nodes;
-    std::vector<CbsSeg> done;       // final segments as they arrive (any order; sorted at the end)
-    long long blk_off = 0, ptiles = 0, iblks = 0, qtiles = 0;
-    for (int a = 0; a < n_arms; ++a) {
-        const int lo = (int)h_off[a], hi = (int)h_off[a + 1];
-        if (hi <= lo) continue;
-        if (hi - lo >= 2 * P.min_width) {
+    std::vector<CbsSeg> done;       // final segments as they arrive (any order)
+    int nn = 0, epoch = 0, cap_nodes = 0;
+    long long blk_off = 0, ptiles = 0, iblks = 0, qtiles = 0, level_bins = 0;
+    CbsStats st;
+    CbsDiag* diag_out = nullptr;
+
+    int setup(const CbsShared* shared, cudaStream_t s, const long long* h_off, const std::vector<int>& arms) {
+        sh = shared;
+        stream = s;
+        memset(&st, 0, sizeof(st));
+        part3.zero = true;
+        const CbsParams& P = sh->P;
+        for (int a : arms) {
+            const int lo = (int)h_off[a], hi = (int)h_off[a + 1];
+            if (hi - lo < 2 * P.min_width) continue;       // short arms are handled by the caller
             Node nd;
             memset(&nd, 0, sizeof(Node));
             nd.lo = lo; nd.hi = hi; nd.base = lo;
@@ -2260,49 +2377,52 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             blk_off += (n + 1 + CBS_BLK - 1) / CBS_BLK;
             iblks += (n + 1 + CBS_IBLK - 1) / CBS_IBLK;
             qtiles += node_qtiles(n);
+            level_bins += n;
             h_nodes.push_back(nd);
-        } else {
-            CbsSeg s;
-            s.arm = a; s.lo = lo; s.hi = hi; s.mean = 0.0;     // mean filled below (short arms: 1-3 bins)
-            done.push_back(s);
         }
-    }
-    const size_t n_short = done.size();
-
-    Grow<Node> nodes_a, nodes_b;
-    Grow<int> ptile_node, blk_node, iblk_node, need_list, hyb_list, exact_list, act, act_toff, fperm_list, tmp_list;
-    Grow<int> bimin, bimax, extra_lo, extra_hi;
-    Grow<double> bmin, bmax, bcmin, bcmax, bwmin, terms, fpart, extra_mean;
-    Grow<TileSums> part1;
-    Grow<TileScan> part3;
-    part3.zero = true;
-    Grow<SeedRes> seedres;
-    Grow<TileRef> queue;
-    Grow<unsigned long long> dmin_bits, pmax;
-    Grow<FlankTest> tests;
-    CNVK_CHECK(extra_lo.ensure(4096, stream));
-    CNVK_CHECK(extra_hi.ensure(4096, stream));
-    CNVK_CHECK(extra_mean.ensure(4096, stream));
-
-    int nn = (int)h_nodes.size();
-    Grow<Node>* cur = &nodes_a;
-    Grow<Node>* nxt = &nodes_b;
-    if (nn > 0) {
+        nn = (int)h_nodes.size();
+        if (nn == 0) return 0;
+        if (tiles_overflow(ptiles, blk_off, iblks, qtiles)) return -2;
+        CNVK_CHECK(cudaMallocAsync((void**)&d_out, sizeof(LevelOut), stream));
+        CNVK_CHECK(cudaMemsetAsync(d_out, 0, sizeof(Ctl), stream));
+        CNVK_CHECK(extra_lo.ensure(4096, stream));
+        CNVK_CHECK(extra_hi.ensure(4096, stream));
+        CNVK_CHECK(extra_mean.ensure(4096, stream));
         CNVK_CHECK(cur->ensure((size_t)nn, stream));
         Node* p_nodes = g_pinned.put(h_nodes.data(), (size_t)nn);
         CNVK_PIN_CHECK(p_nodes);
         CNVK_CHECK(cudaMemcpyAsync(cur->p, p_nodes, nn * sizeof(Node), cudaMemcpyHostToDevice, stream));
+        h_out = (LevelOut*)g_pinned.get(sizeof(LevelOut));
+        CNVK_PIN_CHECK(h_out);
+        return 0;
     }
-    LevelOut* h_out = (LevelOut*)g_pinned.get(sizeof(LevelOut));
-    CNVK_PIN_CHECK(h_out);
-    const int hk = P.hybrid ? P.kmax : 0;
-    const int ngrid = 100;
-    int epoch = 0;
-    if (tiles_overflow(ptiles, blk_off, iblks, qtiles)) return -2;
-    long long level_bins = 0;
-    for (const Node& nd : h_nodes) level_bins += nd.hi - nd.lo;
+    ~CbsRun() { if (d_out) cudaFreeAsync(d_out, stream); }
+    bool active() const { return nn > 0; }
 
-    while (nn > 0) {
+    int launch_frontier() {
+        const CbsParams& P = sh->P;
+        cap_nodes = std::max(cap_nodes, std::max(2 * nn + 64, (int)std::min<size_t>(nxt->cap, 0x7fffffff)));
+        CNVK_CHECK(nxt->ensure((size_t)cap_nodes, stream));
+        cap_nodes = (int)std::min<size_t>(nxt->cap, 0x7fffffff);
+        cbs_frontier_kernel<<<1, 1024, 0, stream>>>(cur->p, nn, tests.p, P.alpha, P.nperm, P.min_width, nxt->p, cap_nodes,
+                                                    d_out, extra_lo.p, extra_hi.p, (int)extra_lo.cap);
+        CNVK_LAUNCH_CHECK();
+        {
+            ProfScope ps(PC_CBS_MEANS, stream);
+            seg_mean_kernel<<<sh->sm_count, 1024, 0, stream>>>(sh->d_x, sh->d_w, d_out, extra_lo.p, extra_hi.p, extra_mean.p);
+            CNVK_LAUNCH_CHECK();
+        }
+        CNVK_CHECK(cudaMemcpyAsync(h_out, d_out, sizeof(LevelOut), cudaMemcpyDeviceToHost, stream));
+        return 0;
+    }
+
+    // every kernel of one recursion level + the read-back of its record, no synchronisation
+    int enqueue() {
+        const CbsParams& P = sh->P;
+        const int sm_count = sh->sm_count, hk = sh->hk, ngrid = sh->ngrid;
+        const bool diag = sh->diag;
+        const double *d_x = sh->d_x, *d_w = sh->d_w;
+        double *d_S = sh->d_S, *d_cw = sh->d_cw;
         st.levels++;
         st.nodes += nn;
         ++epoch;
@@ -2336,6 +2456,8 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         CNVK_CHECK(fpart.ensure((size_t)2 * nn * FLANK_SPLIT * 5, stream));
         CNVK_CHECK(fperm_list.ensure((size_t)2 * nn, stream));
         Node* d_nodes = cur->p;
+        Ctl* d_ctl = &d_out->ctl;
+        unsigned long long* d_stats = d_ctl->stats;
         // lists, queue and next-level fields of the control block (stats are kept)
         CNVK_CHECK(cudaMemsetAsync(d_ctl, 0, offsetof(Ctl, stats), stream));
 
@@ -2358,8 +2480,8 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         }
         {
             ProfScope ps(PC_CBS_BAND, stream);
-            if (P.prune & 1) cbs_band_kernel<true><<<(int)blk_off, 256, 0, stream>>>(d_nodes, blk_node.p, d_S, d_cw, bmin.p, bmax.p, bwmin.p, P.min_width, d_stats);
-            else cbs_band_kernel<false><<<(int)blk_off, 256, 0, stream>>>(d_nodes, blk_node.p, d_S, d_cw, bmin.p, bmax.p, bwmin.p, P.min_width, d_stats);
+            if (P.prune & 1) cbs_band_kernel<true><<<(int)iblks, 256, 0, stream>>>(d_nodes, iblk_node.p, d_S, d_cw, bmin.p, bmax.p, bwmin.p, P.min_width, d_stats);
+            else cbs_band_kernel<false><<<(int)iblks, 256, 0, stream>>>(d_nodes, iblk_node.p, d_S, d_cw, bmin.p, bmax.p, bwmin.p, P.min_width, d_stats);
             CNVK_LAUNCH_CHECK();
         }
         {
@@ -2370,7 +2492,7 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         }
         {
             ProfScope ps(PC_CBS_SCAN, stream);
-            const int grid = (int)std::min<long long>((long long)sm_count * 4, std::max<long long>(qtiles, 1));
+            const int grid = (int)std::min<long long>((long long)sm_count * 4, std::max<long long>(4 * qtiles, 1));
             if (P.prune & 1) cbs_scan_kernel<true><<<grid, 256, 0, stream>>>(d_nodes, queue.p, &d_ctl->qcount, &d_ctl->qpop, d_S, d_cw, bmin.p, bmax.p, P.min_width, d_stats);
             else cbs_scan_kernel<false><<<grid, 256, 0, stream>>>(d_nodes, queue.p, &d_ctl->qcount, &d_ctl->qpop, d_S, d_cw, bmin.p, bmax.p, P.min_width, d_stats);
             CNVK_LAUNCH_CHECK();
@@ -2384,13 +2506,13 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 cbs_tailp_terms_kernel<<<dim3(ngrid, std::min(nn, 64)), 128, 0, stream>>>(d_nodes, need_list.p, d_ctl, terms.p, ngrid, 1e-6);
                 CNVK_LAUNCH_CHECK();
             }
-            cbs_decide_kernel<<<1, 1024, 0, stream>>>(d_nodes, nn, terms.p, P.alpha, P.nperm, ngrid, diag ? 1 : 0, hyb_list.p, exact_list.p, d_ctl);
+            cbs_decide_kernel<<<1, 1024, 0, stream>>>(d_nodes, nn, terms.p, P.alpha, P.nperm, ngrid, diag ? 1 : 0, hyb_list.p, exact_list.p, d_ctl, dmin_bits.p, act.p, act_toff.p);
             CNVK_LAUNCH_CHECK();
         }
         // ---- permutation reference distributions (cooperative persistent kernels; no-ops when their list is empty)
         PermArgs pa;
-        pa.nodes = d_nodes; pa.ctl = d_ctl; pa.x = d_x; pa.w = d_w; pa.rw = d_rw; pa.cw = d_cw; pa.y = d_y; pa.wn = d_wn;
-        pa.dmin_bits = dmin_bits.p; pa.pmax = pmax.p; pa.pm_entries = pm_entries; pa.sbdry = d_sbdry;
+        pa.nodes = d_nodes; pa.ctl = d_ctl; pa.x = d_x; pa.w = d_w; pa.rw = sh->d_rw; pa.cw = d_cw; pa.y = sh->d_y; pa.wn = sh->d_wn;
+        pa.dmin_bits = dmin_bits.p; pa.pmax = pmax.p; pa.pm_entries = pm_entries; pa.sbdry = sh->d_sbdry;
         pa.act = act.p; pa.act_toff = act_toff.p; pa.cap = nn; pa.seed = P.seed; pa.al0 = P.min_width; pa.kmax = P.kmax;
         pa.nperm = P.nperm; pa.diag = diag ? 1 : 0;
         if (P.hybrid) {
@@ -2398,10 +2520,10 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             pa.list = hyb_list.p;
             void* args[] = {&pa};
             if (P.kmax == 25 && P.min_width == 2) {
-                const int g = coop_grid((const void*)cbs_perm_hybrid_kernel<25, 2>, PERM_THREADS, sm_count, &grid_hyb25);
+                const int g = coop_grid((const void*)cbs_perm_hybrid_kernel<25, 2>, PERM_THREADS, sm_count, &g_grid_hyb25);
                 CNVK_CHECK(cudaLaunchCooperativeKernel((const void*)cbs_perm_hybrid_kernel<25, 2>, dim3(g), dim3(PERM_THREADS), args, 0, stream));
             } else {
-                const int g = coop_grid((const void*)cbs_perm_hybrid_kernel<0, 0>, PERM_THREADS, sm_count, &grid_hyb0);
+                const int g = coop_grid((const void*)cbs_perm_hybrid_kernel<0, 0>, PERM_THREADS, sm_count, &g_grid_hyb0);
                 CNVK_CHECK(cudaLaunchCooperativeKernel((const void*)cbs_perm_hybrid_kernel<0, 0>, dim3(g), dim3(PERM_THREADS), args, 0, stream));
             }
             CNVK_LAUNCH_CHECK();
@@ -2410,7 +2532,8 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             ProfScope ps(PC_CBS_PERM_EXACT, stream);
             pa.list = exact_list.p;
             void* args[] = {&pa};
-            const int g = coop_grid((const void*)cbs_perm_exact_kernel, 128, sm_count, &grid_exact);
+            // two CTAs per SM: grid.sync cost grows with the CTA count and the work is only a few waves of warps
+            const int g = std::min(coop_grid((const void*)cbs_perm_exact_kernel, 128, sm_count, &g_grid_exact), 2 * sm_count);
             CNVK_CHECK(cudaLaunchCooperativeKernel((const void*)cbs_perm_exact_kernel, dim3(g), dim3(128), args, 0, stream));
             CNVK_LAUNCH_CHECK();
         }
@@ -2423,41 +2546,37 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
             CNVK_LAUNCH_CHECK();
             cbs_flank_prep_kernel<<<std::min(div_up(2 * nn, 128), sm_count), 128, 0, stream>>>(tests.p, d_ctl, fpart.p, fperm_list.p, diag ? 1 : 0);
             CNVK_LAUNCH_CHECK();
-            cbs_flank_perm_kernel<<<sm_count * 8, 128, 0, stream>>>(d_nodes, tests.p, fperm_list.p, d_ctl, P.nperm, d_x, d_rw, P.seed);
+            cbs_flank_perm_kernel<<<sm_count * 8, 128, 0, stream>>>(d_nodes, tests.p, fperm_list.p, d_ctl, P.nperm, d_x, sh->d_rw, P.seed);
             CNVK_LAUNCH_CHECK();
         }
-        if (diag) {
-            diag->nodes.resize(nn);
-            std::vector<FlankTest> h_tests((size_t)2 * nn);
-            CNVK_CHECK(cudaMemcpyAsync(diag->nodes.data(), d_nodes, nn * sizeof(Node), cudaMemcpyDeviceToHost, stream));
-            CNVK_CHECK(cudaMemcpyAsync(h_tests.data(), tests.p, (size_t)2 * nn * sizeof(FlankTest), cudaMemcpyDeviceToHost, stream));
-            CNVK_CHECK(cudaMemcpyAsync(h_out, d_out, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
-            CNVK_CHECK(cudaStreamSynchronize(stream));
-            diag->flank_p.assign((size_t)2 * nn, -1.0);
-            for (int t = 0; t < h_out->ctl.n_flank; ++t) {
-                const FlankTest& f = h_tests[t];
-                diag->flank_p[(size_t)2 * f.node + (f.tid - 1)] = f.need_perm ? (double)f.nrej / (double)P.nperm : f.pvalue;
-            }
-            if (stats) *stats = st;
-            return 0;
-        }
+        if (diag) return 0;
         // ---- next frontier + the segments that became final, one record back to the host
-        int cap_nodes = 0;
+        return launch_frontier();
+    }
+
+    int finish_diag() {
+        const CbsParams& P = sh->P;
+        diag_out->nodes.resize(nn);
+        std::vector<FlankTest> h_tests((size_t)2 * nn);
+        CNVK_CHECK(cudaMemcpyAsync(diag_out->nodes.data(), cur->p, nn * sizeof(Node), cudaMemcpyDeviceToHost, stream));
+        CNVK_CHECK(cudaMemcpyAsync(h_tests.data(), tests.p, (size_t)2 * nn * sizeof(FlankTest), cudaMemcpyDeviceToHost, stream));
+        CNVK_CHECK(cudaMemcpyAsync(h_out, d_out, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+        CNVK_CHECK(cudaStreamSynchronize(stream));
+        diag_out->flank_p.assign((size_t)2 * nn, -1.0);
+        for (int t = 0; t < h_out->ctl.n_flank; ++t) {
+            const FlankTest& f = h_tests[t];
+            diag_out->flank_p[(size_t)2 * f.node + (f.tid - 1)] = f.need_perm ? (double)f.nrej / (double)P.nperm : f.pvalue;
+        }
+        nn = 0;
+        return 0;
+    }
+
+    // wait for the level's record, collect the final segments, adopt the next level's sizes
+    int finish() {
         for (;;) {
-            cap_nodes = std::max(cap_nodes, std::max(2 * nn + 64, (int)nxt->cap));
-            CNVK_CHECK(nxt->ensure((size_t)cap_nodes, stream));
-            cap_nodes = (int)std::min<size_t>(nxt->cap, 0x7fffffff);
-            cbs_frontier_kernel<<<1, 1024, 0, stream>>>(d_nodes, nn, tests.p, P.alpha, P.nperm, P.min_width, nxt->p, cap_nodes,
-                                                        d_out, extra_lo.p, extra_hi.p, (int)extra_lo.cap);
-            CNVK_LAUNCH_CHECK();
-            {
-                ProfScope ps(PC_CBS_MEANS, stream);
-                seg_mean_kernel<<<sm_count * 2, 256, 0, stream>>>(d_x, d_w, d_out, extra_lo.p, extra_hi.p, extra_mean.p);
-                CNVK_LAUNCH_CHECK();
-            }
-            CNVK_CHECK(cudaMemcpyAsync(h_out, d_out, sizeof(LevelOut), cudaMemcpyDeviceToHost, stream));
             CNVK_CHECK(cudaStreamSynchronize(stream));
             if (!h_out->ctl.overflow) break;
+            // a buffer of the frontier kernel was too small: grow it and rerun that kernel (it is idempotent)
             if (h_out->ctl.overflow & 1) cap_nodes = h_out->ctl.nn_next + 64;
             if (h_out->ctl.overflow & 2) {
                 const size_t need = (size_t)h_out->ctl.nseg_new;
@@ -2465,6 +2584,8 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 CNVK_CHECK(extra_hi.ensure(need, stream));
                 CNVK_CHECK(extra_mean.ensure(need, stream));
             }
+            int rc = launch_frontier();
+            if (rc) return rc;
         }
         const Ctl& c = h_out->ctl;
         const int nseg_new = c.nseg_new;
@@ -2495,29 +2616,175 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
         st.perms_run = (long long)c.stats[4];
         st.perm_arcs = (long long)c.stats[5];
         st.flank_perm_tests = (long long)c.stats[6];
-        h_nodes.clear();
         nn = c.nn_next; ptiles = c.ptiles_next; blk_off = c.nblk_next; iblks = c.niblk_next; qtiles = c.qtiles_next;
         level_bins = c.bins_next;
         if (tiles_overflow(ptiles, blk_off, iblks, qtiles)) return -2;
         std::swap(cur, nxt);
+        return 0;
+    }
+};
+
+// internal side streams for the second group of a call (per host thread, created on first use)
+static thread_local cudaStream_t g_side_stream = nullptr;
+static thread_local cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+
+int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, const CbsParams& P_in,
+                std::vector<CbsSeg>& segs, CbsStats* stats, cudaStream_t stream, CbsDiag* diag) {
+    // diagnostics (cnvk_cbs_node_diag): every interval is ONE node; one level only, the tail series is always
+    // summed, every node runs all nperm permutations (no stopping rule) and both flank tests with permutations
+    CbsParams P = P_in;
+    if (diag) P.prune |= 2;
+    segs.clear();
+    CbsStats st;
+    memset(&st, 0, sizeof(st));
+    if (n_arms <= 0) { if (stats) *stats = st; return 0; }
+    const long long N = h_off[n_arms];
+    if (N >= (1ll << 31) - 4) { set_last_error("cbs_segment: too many bins (%lld)", N); return -2; }
+    if (P.kmax > HYB_KMAX || P.nmin > EXACT_NMAX || P.min_width < 2 || P.kmax < P.min_width || P.nperm < 1) {
+        set_last_error("cbs_segment: unsupported parameters (kmax<=%d, nmin<=%d, min_width>=2)", HYB_KMAX, EXACT_NMAX);
+        return -2;
+    }
+    if (P.nmin < 2 * P.kmax) { set_last_error("cbs_segment: need nmin >= 2*kmax"); return -2; }
+    static thread_local int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        CNVK_CHECK(cudaGetDevice(&dev));
+        CNVK_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        CNVK_CHECK(cudaFuncSetAttribute(cbs_prep_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM));
+    }
+    const int max_ones = (int)std::floor((double)P.nperm * P.alpha) + 1;
+    // the stopping boundary depends on (eta, nperm, max.ones) only and costs ~nperm * max.ones * 20 flops to
+    // build: keep the last one per thread
+    static thread_local std::vector<int> sbdry;
+    static thread_local double sb_eta = -1.0;
+    static thread_local int sb_nperm = -1, sb_ones = -1;
+    if (sb_eta != P.eta || sb_nperm != P.nperm || sb_ones != max_ones) {
+        cbs_getbdry(P.eta, P.nperm, max_ones, sbdry);
+        sb_eta = P.eta; sb_nperm = P.nperm; sb_ones = max_ones;
+    }
+
+    g_pinned.rewind();
+    Scratch scratch(stream);
+    CbsShared sh;
+    int* d_sbdry;
+    CNVK_CHECK(scratch.alloc(&sh.d_rw, (size_t)N));
+    CNVK_CHECK(scratch.alloc(&sh.d_y, (size_t)N));
+    CNVK_CHECK(scratch.alloc(&sh.d_wn, (size_t)N));
+    CNVK_CHECK(scratch.alloc(&sh.d_S, (size_t)N + 4));      // + slack: the band kernel's bulk copies are widened to 16 B
+    CNVK_CHECK(scratch.alloc(&sh.d_cw, (size_t)N + 4));
+    CNVK_CHECK(scratch.alloc(&d_sbdry, sbdry.size()));
+    {
+        int* p_sb = g_pinned.put(sbdry.data(), sbdry.size());
+        CNVK_PIN_CHECK(p_sb);
+        CNVK_CHECK(cudaMemcpyAsync(d_sbdry, p_sb, sbdry.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    }
+    if (N > 0) {
+        sqrt_kernel<<<div_up(N, 256), 256, 0, stream>>>(d_w, sh.d_rw, N);
+        CNVK_LAUNCH_CHECK();
+    }
+    sh.d_x = d_x; sh.d_w = d_w; sh.d_sbdry = d_sbdry; sh.P = P; sh.sm_count = sm_count;
+    sh.hk = P.hybrid ? P.kmax : 0; sh.ngrid = 100; sh.diag = diag != nullptr;
+
+    // ---- arms -> groups.  Short arms (< 2 min.width bins, never a node) are single segments.
+    std::vector<CbsSeg> done;
+    std::vector<int> long_arms;
+    for (int a = 0; a < n_arms; ++a) {
+        const long long lo = h_off[a], hi = h_off[a + 1];
+        if (hi <= lo) continue;
+        if (hi - lo >= 2 * P.min_width) long_arms.push_back(a);
+        else { CbsSeg s; s.arm = a; s.lo = lo; s.hi = hi; s.mean = 0.0; done.push_back(s); }
+    }
+    const size_t n_short = done.size();
+    long long long_bins = 0;
+    for (int a : long_arms) long_bins += h_off[a + 1] - h_off[a];
+    // Two groups on two streams are an experiment switch only (CNVK_CBS_GROUPS=2): measured on C3 they are SLOWER
+    // (2.33 vs 2.17 ms/step, profiles/r02g_*): every level holds two cooperative permutation kernels, which need
+    // the whole GPU and therefore act as barriers between the two chains.
+    const char* env_groups = getenv("CNVK_CBS_GROUPS");
+    const int n_groups = (env_groups && atoi(env_groups) == 2 && !diag && long_arms.size() >= 2 && long_bins >= 100000) ? 2 : 1;
+    std::vector<std::vector<int>> group_arms(n_groups);
+    if (n_groups == 1) {
+        group_arms[0] = long_arms;
+    } else {
+        // longest arms first, each to the lighter group (arm order inside a group stays ascending)
+        std::vector<int> order(long_arms);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h_off[a + 1] - h_off[a] > h_off[b + 1] - h_off[b]; });
+        long long load[2] = {0, 0};
+        for (int a : order) {
+            const int g = load[1] < load[0] ? 1 : 0;
+            group_arms[g].push_back(a);
+            load[g] += h_off[a + 1] - h_off[a];
+        }
+        for (auto& v : group_arms) std::sort(v.begin(), v.end());
+    }
+    // error paths return before the join below: the side stream must drain before the shared scratch is freed
+    // (destruction order: runs, then this guard, then `scratch`)
+    struct SideGuard { cudaStream_t s = nullptr; ~SideGuard() { if (s) cudaStreamSynchronize(s); } } side_guard;
+    CbsRun runs[2];
+    cudaStream_t streams[2] = {stream, stream};
+    if (n_groups == 2) {
+        if (!g_side_stream) {
+            CNVK_CHECK(cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking));
+            CNVK_CHECK(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+            CNVK_CHECK(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+        }
+        streams[1] = g_side_stream;
+        side_guard.s = g_side_stream;
+        // the side stream starts after everything already queued on the caller's stream (inputs, sqrt(w), boundary)
+        CNVK_CHECK(cudaEventRecord(g_ev_fork, stream));
+        CNVK_CHECK(cudaStreamWaitEvent(g_side_stream, g_ev_fork, 0));
+    }
+    for (int g = 0; g < n_groups; ++g) {
+        runs[g].diag_out = diag;
+        int rc = runs[g].setup(&sh, streams[g], h_off, group_arms[g]);
+        if (rc) return rc;
+    }
+    // ---- level loop: enqueue one level of every group, then collect the records
+    for (;;) {
+        bool any = false;
+        for (int g = 0; g < n_groups; ++g)
+            if (runs[g].active()) { int rc = runs[g].enqueue(); if (rc) return rc; any = true; }
+        if (!any) break;
+        for (int g = 0; g < n_groups; ++g)
+            if (runs[g].active()) { int rc = diag ? runs[g].finish_diag() : runs[g].finish(); if (rc) return rc; }
+    }
+    if (n_groups == 2) {
+        // later work on the caller's stream (and the scratch frees below) must follow the side stream's kernels
+        CNVK_CHECK(cudaEventRecord(g_ev_join, g_side_stream));
+        CNVK_CHECK(cudaStreamWaitEvent(stream, g_ev_join, 0));
+        side_guard.s = nullptr;
+    }
+    for (int g = 0; g < n_groups; ++g) {
+        const CbsStats& r = runs[g].st;
+        st.levels = std::max(st.levels, r.levels);
+        st.nodes += r.nodes; st.prep_bins += r.prep_bins;
+        st.obs_subtiles_scanned += r.obs_subtiles_scanned; st.obs_subtiles_total += r.obs_subtiles_total;
+        st.obs_arcs += r.obs_arcs; st.perm_nodes += r.perm_nodes; st.perms_run += r.perms_run;
+        st.perm_arcs += r.perm_arcs; st.flank_perm_tests += r.flank_perm_tests;
+        done.insert(done.end(), runs[g].done.begin(), runs[g].done.end());
+    }
+    if (diag) { if (stats) *stats = st; return 0; }
+    if (getenv("CNVK_CBS_DEBUG")) {
+        for (int g = 0; g < n_groups; ++g) {
+            if (!runs[g].h_out) continue;
+            const Ctl& c = runs[g].h_out->ctl;
+            fprintf(stderr, "[cbs] group %d/%d levels %lld nodes %lld | hybrid kernel CTA-0 cycles: materialise+limits %lld wait %lld "
+                            "chunks %lld replay %lld (chunks run %lld)\n", g, n_groups, runs[g].st.levels, runs[g].st.nodes,
+                    c.tprof[0], c.tprof[1], c.tprof[2], c.tprof[3], c.tprof[4]);
+        }
     }
 
     // ---- segment table: arms in order, segments by start; short arms (never a node) get their mean here
-    if (n_short) {
-        std::vector<long long> lo_(n_short), hi_(n_short);
-        for (size_t s = 0; s < n_short; ++s) { lo_[s] = done[s].lo; hi_[s] = done[s].hi; }
-        std::vector<double> xs, ws;
-        // at most 3 bins each: read them back in one gather-free pass (they are rare: arms of < 2*min_width bins)
-        for (size_t s = 0; s < n_short; ++s) {
-            const int len = (int)(hi_[s] - lo_[s]);
-            std::vector<double> hx(len), hw(len);
-            CNVK_CHECK(cudaMemcpyAsync(hx.data(), d_x + lo_[s], len * sizeof(double), cudaMemcpyDeviceToHost, stream));
-            CNVK_CHECK(cudaMemcpyAsync(hw.data(), d_w + lo_[s], len * sizeof(double), cudaMemcpyDeviceToHost, stream));
-            CNVK_CHECK(cudaStreamSynchronize(stream));
-            double sw = 0.0, swx = 0.0;
-            for (int k = 0; k < len; ++k) { sw += hw[k]; swx += hx[k] * hw[k]; }
-            done[s].mean = swx / sw;
-        }
+    for (size_t s = 0; s < n_short; ++s) {
+        // at most 3 bins each (arms of < 2*min_width bins are rare): read them back
+        const int len = (int)(done[s].hi - done[s].lo);
+        std::vector<double> hx(len), hw(len);
+        CNVK_CHECK(cudaMemcpyAsync(hx.data(), d_x + done[s].lo, len * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CNVK_CHECK(cudaMemcpyAsync(hw.data(), d_w + done[s].lo, len * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CNVK_CHECK(cudaStreamSynchronize(stream));
+        double sw = 0.0, swx = 0.0;
+        for (int k = 0; k < len; ++k) { sw += hw[k]; swx += hx[k] * hw[k]; }
+        done[s].mean = swx / sw;
     }
     std::sort(done.begin(), done.end(), [](const CbsSeg& a, const CbsSeg& b) { return a.lo < b.lo; });
     {

@@ -54,6 +54,31 @@ struct Prp {
         n = n_;
     }
 
+    // one application of the network (no cycle walking): the result may lie outside [0, n)
+    __host__ __device__ __forceinline__ u32 once(u32 v) const {
+        const int a = bits_a, b = bits_b;
+        const u32 ma = (1u << a) - 1u, mb = (1u << b) - 1u;
+        u32 L = v >> b, R = v & mb;
+        u32 t = (L ^ mix32(R ^ k[0])) & ma; L = R; R = t;
+        t = (L ^ mix32(R ^ k[1])) & mb; L = R; R = t;
+        t = (L ^ mix32(R ^ k[2])) & ma; L = R; R = t;
+        t = (L ^ mix32(R ^ k[3])) & mb; L = R; R = t;
+        if (rounds > 4) {
+            t = (L ^ mix32(R ^ k[4])) & ma; L = R; R = t;
+            t = (L ^ mix32(R ^ k[5])) & mb; L = R; R = t;
+            if (rounds > 6) {
+                t = (L ^ mix32(R ^ k[6])) & ma; L = R; R = t;
+                t = (L ^ mix32(R ^ k[7])) & mb; L = R; R = t;
+            }
+        }
+        return (L << b) | R;
+    }
+    // cycle walking of a value produced by once(): same result as operator() on the original input
+    __host__ __device__ __forceinline__ u32 walk(u32 v) const {
+        while (v >= n) v = once(v);
+        return v;
+    }
+
     __host__ __device__ __forceinline__ u32 operator()(u32 v) const {
         const int a = bits_a, b = bits_b;
         const u32 ma = (1u << a) - 1u, mb = (1u << b) - 1u;

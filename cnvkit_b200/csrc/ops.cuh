@@ -93,6 +93,12 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 std::vector<CbsSeg>& segs, CbsStats* stats, cudaStream_t stream, CbsDiag* diag = nullptr);
 int cbs_node_diag(const double* d_x, const double* d_w, const long long* h_off, int n_nodes, const CbsParams& P,
                   double* out6, int* iout5, cudaStream_t stream);
+// coverage.cu
+int coverage_finalize(const double* d_basecount, const long long* d_start, const long long* d_end, long long n,
+                      double null_log2, double* d_depth, double* d_log2, cudaStream_t stream);
+// smooth_cna.cu
+int smooth_cna(const double* d_x, const long long* h_off, int n_arms, int k, double outlier_scale, double smooth_scale,
+               double trim, double* d_out, double* d_sd_out, cudaStream_t stream);
 // haar.cu (segments reuse CbsSeg)
 int haar_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, double q,
                  std::vector<CbsSeg>& segs, cudaStream_t stream);

@@ -69,8 +69,7 @@ def _segment_needs_reference(args, kwargs):
     #                                                               cnvlib/segmentation/__init__.py:31-44
     method = _arg(args, kwargs, 1, "method", None)
     variants = _arg(args, kwargs, 4, "variants", None)
-    smooth = _arg(args, kwargs, 11, "smooth_cbs", False)
-    return method not in ("cbs", "haar") or (variants is not None and len(variants) > 0) or bool(smooth)
+    return method not in ("cbs", "haar") or (variants is not None and len(variants) > 0)
 
 
 def _segmetrics_seam(ours, theirs):

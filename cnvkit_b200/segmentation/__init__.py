@@ -50,8 +50,8 @@ def do_segmentation(
         raise NotImplementedError(f"method {method!r} is outside the GPU hot path (cbs and haar are implemented)")
     if variants is not None and len(variants):
         raise NotImplementedError("BAF-aware segmentation (variants=...) is outside the GPU hot path")
-    if smooth_cbs:
-        raise NotImplementedError("smooth_cbs (DNAcopy smooth.CNA) is not implemented on the GPU path")
+    if smooth_cbs and method != "cbs":
+        smooth_cbs = False          # the flag only reaches the R script of method 'cbs' (:318)
     if cnarr.sample_id is None:
         logging.warning(
             "Input has no sample_id set; the segmented output will be "
@@ -123,7 +123,7 @@ def do_segmentation(
     f_weight = weight[fidx] if has_weight else None
 
     if method == "cbs":
-        seg = _segment_cbs(f_log2, f_weight, f_arm, len(arms), threshold)
+        seg = _segment_cbs(f_log2, f_weight, f_arm, len(arms), threshold, smooth_cbs)
     else:
         seg = _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, len(arms), threshold)
     s_unit, s_lo, s_hi, s_mean, unit_arm, sub_fidx = seg
@@ -205,8 +205,8 @@ def _arm_offsets(arm_of_bin, n_arms):
     return np.concatenate([[0], np.cumsum(np.bincount(arm_of_bin, minlength=n_arms))]).astype(np.int64)
 
 
-def _segment_cbs(f_log2, f_weight, f_arm, n_arms, threshold):
-    """The `case "cbs"` block (:292-322): %.6g TSV -> R filters (cbs.py:22-35) -> segment()."""
+def _segment_cbs(f_log2, f_weight, f_arm, n_arms, threshold, smooth_cbs=False):
+    """The `case "cbs"` block (:292-322): %.6g TSV -> R filters (cbs.py:22-35) -> [smooth.CNA] -> segment()."""
     d_x = _dev.up(f_log2)
     d_xq = _dev.empty(len(f_log2), torch.float64)
     unhandled = np.zeros(1, dtype=np.uint64)
@@ -240,7 +240,19 @@ def _segment_cbs(f_log2, f_weight, f_arm, n_arms, threshold):
         sub = np.flatnonzero(ok)
         xq, wq, f_arm = xq[sub], wq[sub], f_arm[sub]
     off = _arm_offsets(f_arm, n_arms)
-    arm, lo, hi, mean, _stats = _cbs.segment_arms(xq, wq, off, alpha=float(threshold))
+    if smooth_cbs:
+        # cbs.py:51-58: segment() runs on the smoothed values, cbs.py:64-73 then takes every segment's
+        # weighted.mean from the ORIGINAL (quantised) log2
+        xs = _cbs.smooth_cna(xq, off)
+        arm, lo, hi, _mean_s, _stats = _cbs.segment_arms(xs, wq, off, alpha=float(threshold))
+        d_lo, d_hi = _dev.up(lo.astype(np.int64)), _dev.up(hi.astype(np.int64))
+        d_sw, d_sm = _dev.empty(len(lo), torch.float64), _dev.empty(len(lo), torch.float64)
+        d_xq, d_wq2 = _dev.up(xq), _dev.up(wq)
+        _lib.call("cnvk_segment_bin_sums_dev", _dev.ptr(d_xq), _dev.ptr(d_wq2), _dev.ptr(d_lo), _dev.ptr(d_hi), len(lo),
+                  _dev.ptr(d_sw), _dev.ptr(d_sm), _dev.stream())
+        mean = d_sm.cpu().numpy()
+    else:
+        arm, lo, hi, mean, _stats = _cbs.segment_arms(xq, wq, off, alpha=float(threshold))
     # R prints seg.mean with 15 significant digits (write.table) before the SEG parser reads it back
     mean = np.array([float("%.15g" % m) for m in mean]) if len(mean) else mean
     return arm, lo, hi, mean, np.arange(n_arms), sub

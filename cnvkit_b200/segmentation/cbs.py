@@ -63,6 +63,30 @@ def segment_arms(log2, weight, arm_offsets, alpha=1e-4, prune=True, device_ptrs=
     return seg_arm[:k].copy(), seg_lo[:k].copy(), seg_hi[:k].copy(), seg_mean[:k].copy(), stats.as_dict()
 
 
+# DNAcopy::smooth.CNA defaults (cbs.py:57 calls it without arguments)
+SMOOTH_DEFAULTS = dict(smooth_region=10, outlier_sd_scale=4.0, smooth_sd_scale=2.0, trim=0.025)
+
+
+def smooth_cna(log2, arm_offsets, device_ptrs=None, stream=0, **overrides):
+    """DNAcopy smooth.CNA of every arm (``--smooth-cbs``, cbs.py:51-58).  Host arrays in / out, or with
+    ``device_ptrs=(d_log2, d_out)`` on resident columns (returns None).  Arms of fewer than 2 bins are copied
+    unchanged (cbs.py:56: smoothing is skipped for them)."""
+    kw = dict(SMOOTH_DEFAULTS)
+    kw.update(overrides)
+    off = _lib.i64(arm_offsets)
+    n_arms = len(off) - 1
+    if device_ptrs is not None:
+        _lib.call("cnvk_smooth_cna_dev", int(device_ptrs[0]), _lib.ptr(off), n_arms, int(kw["smooth_region"]),
+                  float(kw["outlier_sd_scale"]), float(kw["smooth_sd_scale"]), float(kw["trim"]), int(device_ptrs[1]),
+                  0, int(stream))
+        return None
+    x = _lib.f64(log2)
+    out = np.empty_like(x)
+    _lib.call("cnvk_smooth_cna", _lib.ptr(x), _lib.ptr(off), n_arms, int(kw["smooth_region"]),
+              float(kw["outlier_sd_scale"]), float(kw["smooth_sd_scale"]), float(kw["trim"]), _lib.ptr(out), 0)
+    return out
+
+
 def node_diag(log2, weight, node_offsets, alpha=1e-4, **overrides):
     """Decision-chain diagnostics of every interval tested once as a node, nothing decided early
     (cnvk_cbs_node_diag): list of dicts with ``ostat1`` (sqrt T^2), ``ostat`` (0.99999 T^2), ``arc``, ``tailp`` /

@@ -224,6 +224,26 @@ int cnvk_cbs_segment(const double* log2, const double* weight, const int64_t* ar
                      int32_t n_arms, const cnvk_cbs_params* params, int64_t capacity, int32_t* seg_arm,
                      int64_t* seg_lo, int64_t* seg_hi, double* seg_mean, int64_t* n_segs,
                      cnvk_cbs_stats* stats);
+/* ---- coverage finalisation (the step before the path) ------------------------------ */
+/* cnvlib/coverage.py:637-643 (interval_coverages_pileup) and :403-409 (interval_coverages_bedgraph): depth =
+ * basecount / (end - start) for bins of positive width, else 0; log2 = log2(depth) where depth > 0, else null_log2
+ * (params.NULL_LOG2_COVERAGE = -20).  basecount is float64 (bedcov counts are far below 2^53). */
+int cnvk_coverage_finalize_dev(const double* d_basecount, const int64_t* d_start, const int64_t* d_end, int64_t n,
+                               double null_log2, double* d_depth, double* d_log2, void* stream);
+int cnvk_coverage_finalize(const double* basecount, const int64_t* start, const int64_t* end, int64_t n,
+                           double null_log2, double* depth, double* log2);
+
+/* DNAcopy::smooth.CNA -- the `--smooth-cbs` option: cnvlib/segmentation/cbs.py:51-58 runs `cna = smooth.CNA(cna)`
+ * (DNAcopy defaults: smooth_region 10, outlier_sd_scale 4, smooth_sd_scale 2, trim 0.025) on the arm's quantised
+ * log2 before segment(); segment means are still taken from the unsmoothed values (cbs.py:64-73).  Per arm:
+ * trimmed.SD from the smallest round((1 - 2 trim)(n - 1)) absolute first differences, then every bin that lies more
+ * than outlier_sd_scale trimmed.SD above (below) all other bins within smooth_region bins is moved to the window
+ * median +- smooth_sd_scale trimmed.SD.  arm_offsets is a HOST array; d_sd / sd (one trimmed.SD per arm) may be NULL. */
+int cnvk_smooth_cna_dev(const double* d_log2, const int64_t* arm_offsets, int32_t n_arms, int32_t smooth_region,
+                        double outlier_sd_scale, double smooth_sd_scale, double trim, double* d_out, double* d_sd,
+                        void* stream);
+int cnvk_smooth_cna(const double* log2, const int64_t* arm_offsets, int32_t n_arms, int32_t smooth_region,
+                    double outlier_sd_scale, double smooth_sd_scale, double trim, double* out, double* sd);
 /* Diagnostics of the CBS decision chain (DNAcopy wfindcpt; call site
  * cnvlib/segmentation/cbs.py:49-60): every interval [node_offsets[k], node_offsets[k+1]) is tested ONCE as a
  * node, nothing is decided early -- all nperm permutations run (no sequential stopping) and both ternary-split

@@ -80,8 +80,21 @@ def lib():
                                   c_uint32, c_void_p]
         L.cbso_node_diag.restype = c_int
         L.cbso_node_diag.argtypes = [c_void_p, c_void_p, c_int, c_int, POINTER(Params), c_int, c_void_p, c_void_p]
+        L.cbso_smooth_cna.restype = c_int
+        L.cbso_smooth_cna.argtypes = [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_double, c_void_p, c_void_p]
         _lib = L
     return _lib
+
+
+def smooth_cna(x, arm_offsets, smooth_region=10, outlier_sd_scale=4.0, smooth_sd_scale=2.0, trim=0.025):
+    """DNAcopy smooth.CNA of every arm (restated; see cbs_oracle.c).  Returns (smoothed, trimmed_sd_per_arm)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    off = np.ascontiguousarray(arm_offsets, dtype=np.int64)
+    out = np.empty_like(x)
+    sd = np.zeros(len(off) - 1, dtype=np.float64)
+    lib().cbso_smooth_cna(x.ctypes.data, off.ctypes.data, len(off) - 1, smooth_region, outlier_sd_scale, smooth_sd_scale,
+                          trim, out.ctypes.data, sd.ctypes.data)
+    return out, sd
 
 
 def tailp(b, delta, m, ngrid=100, tol=1e-6):

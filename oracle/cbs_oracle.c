@@ -837,3 +837,115 @@ double cbso_perm_pvalue_flank(const double* xc, const double* w, int n1, int n2,
     free(rw);
     return p;
 }
+
+/* ------------------------------------------------------------------ smooth.CNA (--smooth-cbs) */
+/* DNAcopy::smooth.CNA with its defaults, as the R script applies it to one arm before segment()
+ * (cnvlib/segmentation/cbs.py:51-58): smooth.region = 10, outlier.SD.scale = 4, smooth.SD.scale = 2,
+ * trim = 0.025.  PARITY UNPINNED like the rest of this file (restated from the package's R / Fortran:
+ * trimmed.variance, inflfact, smoothLR).
+ *   trimmed.SD = sqrt( inflfact(trim) * sum( sort(|diff(x)|)[1:n.keep]^2 ) / (2 n.keep) ),
+ *                n.keep = round((1 - 2 trim)(n - 1))            (R's round: half to even)
+ *   a point is an outlier when it lies more than 4 trimmed.SD above (below) EVERY other point within 10 bins
+ *   on either side (window clipped to the arm); it is then moved to median(window incl. itself) +- 2 trimmed.SD. */
+static double qnorm_as241(double p) {   /* Wichura's AS241 PPND16, the algorithm behind R's qnorm */
+    const double q = p - 0.5;
+    double r, val;
+    if (fabs(q) <= 0.425) {
+        r = 0.180625 - q * q;
+        val = q * (((((((r * 2509.0809287301226727 + 33430.575583588128105) * r + 67265.770927008700853) * r
+                       + 45921.953931549871457) * r + 13731.693765509461125) * r + 1971.5909503065514427) * r
+                     + 133.14166789178437745) * r + 3.387132872796366608)
+              / (((((((r * 5226.495278852545925 + 28729.085735721942674) * r + 39307.89580009271061) * r
+                     + 21213.794301586595867) * r + 5394.1960214247511077) * r + 687.1870074920579083) * r
+                   + 42.313330701600911252) * r + 1.0);
+        return val;
+    }
+    r = q < 0 ? p : 1.0 - p;
+    r = sqrt(-log(r));
+    if (r <= 5.0) {
+        r -= 1.6;
+        val = (((((((r * 7.7454501427834140764e-4 + 0.0227238449892691845833) * r + 0.24178072517745061177) * r
+                   + 1.27045825245236838258) * r + 3.64784832476320460504) * r + 5.7694972214606914055) * r
+                 + 4.6303378461565452959) * r + 1.42343711074968357734)
+              / (((((((r * 1.05075007164441684324e-9 + 5.475938084995344946e-4) * r + 0.0151986665636164571966) * r
+                     + 0.14810397642748007459) * r + 0.68976733498510000455) * r + 1.6763848301838038494) * r
+                   + 2.05319162663775882187) * r + 1.0);
+    } else {
+        r -= 5.0;
+        val = (((((((r * 2.01033439929228813265e-7 + 2.71155556874348757815e-5) * r + 0.0012426609473880784386) * r
+                   + 0.026532189526576123093) * r + 0.29656057182850489123) * r + 1.7848265399172913358) * r
+                 + 5.4637849111641143699) * r + 6.6579046435011037772)
+              / (((((((r * 2.04426310338993978564e-15 + 1.4215117583164458887e-7) * r + 1.8463183175100546818e-5) * r
+                     + 7.868691311456132591e-4) * r + 0.0148753612908506148525) * r + 0.13692988092273580531) * r
+                   + 0.59983224954205144545) * r + 1.0);
+    }
+    return q < 0.0 ? -val : val;
+}
+
+double cbso_inflfact(double trim) {
+    const double a = qnorm_as241(1.0 - trim);
+    const int m = 10001;
+    double s = 0.0;
+    for (int i = 0; i < m - 1; ++i) {
+        const double x0 = -a + (2.0 * a) * (double)i / (double)(m - 1), x1 = -a + (2.0 * a) * (double)(i + 1) / (double)(m - 1);
+        const double xm = (x0 + x1) / 2.0;
+        s += xm * xm * (exp(-0.5 * xm * xm) * 0.3989422804014327) / (1.0 - 2.0 * trim);
+    }
+    return 1.0 / (s * (2.0 * a / 10000.0));
+}
+
+static int cmp_double(const void* a, const void* b) {
+    const double x = *(const double*)a, y = *(const double*)b;
+    return (x > y) - (x < y);
+}
+
+/* one arm; out may not alias x.  Returns trimmed.SD. */
+double cbso_smooth_arm(const double* x, int n, int k, double outlier_scale, double smooth_scale, double trim, double* out) {
+    for (int i = 0; i < n; ++i) out[i] = x[i];
+    if (n < 2) return 0.0;
+    double* d = (double*)malloc(sizeof(double) * (size_t)(n - 1));
+    for (int i = 0; i + 1 < n; ++i) d[i] = fabs(x[i + 1] - x[i]);
+    qsort(d, (size_t)(n - 1), sizeof(double), cmp_double);
+    int nkeep = (int)nearbyint((1.0 - 2.0 * trim) * (double)(n - 1));   /* R round(): half to even */
+    if (nkeep < 1) nkeep = 1;
+    if (nkeep > n - 1) nkeep = n - 1;
+    dd_t acc = {0.0, 0.0};
+    for (int i = 0; i < nkeep; ++i) dd_add(&acc, d[i] * d[i]);          /* R-level sum(): correctly rounded */
+    free(d);
+    const double sd = sqrt(cbso_inflfact(trim) * ((acc.hi + acc.lo) / (2.0 * (double)nkeep)));
+    const double oSD = outlier_scale * sd, sSD = smooth_scale * sd;
+    double nb[64];
+    for (int i = 0; i < n; ++i) {
+        const int lo = i - k < 0 ? 0 : i - k, hi = i + k > n - 1 ? n - 1 : i + k;
+        double above = 100.0 * oSD, below = 100.0 * oSD;   /* x_i minus the largest neighbour / smallest minus x_i */
+        int first = 1;
+        double mx = 0.0, mn = 0.0;
+        for (int j = lo; j <= hi; ++j) {
+            if (j == i) continue;
+            if (first) { mx = mn = x[j]; first = 0; }
+            else { if (x[j] > mx) mx = x[j]; if (x[j] < mn) mn = x[j]; }
+        }
+        if (first) continue;
+        above = x[i] - mx;
+        below = mn - x[i];
+        if (!(above > oSD) && !(below > oSD)) continue;
+        int m = 0;
+        for (int j = lo; j <= hi; ++j) nb[m++] = x[j];
+        qsort(nb, (size_t)m, sizeof(double), cmp_double);
+        const double med = (m % 2) ? nb[m / 2] : (nb[m / 2 - 1] + nb[m / 2]) / 2.0;
+        out[i] = above > oSD ? med + sSD : med - sSD;
+    }
+    return sd;
+}
+
+/* every arm of a batch (same arm_offsets convention as cbso_segment); sd_out[a] = trimmed.SD of arm a */
+int cbso_smooth_cna(const double* x, const int64_t* arm_offsets, int n_arms, int k, double outlier_scale,
+                    double smooth_scale, double trim, double* out, double* sd_out) {
+    if (k > 31) return -1;
+    for (int a = 0; a < n_arms; ++a) {
+        const int64_t lo = arm_offsets[a], hi = arm_offsets[a + 1];
+        const double sd = cbso_smooth_arm(x + lo, (int)(hi - lo), k, outlier_scale, smooth_scale, trim, out + lo);
+        if (sd_out) sd_out[a] = sd;
+    }
+    return 0;
+}

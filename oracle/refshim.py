@@ -8,10 +8,10 @@ needs four third-party modules that are absent here and unused on the hot path
 live in ``oracle/refshim_stubs``.  ``cnvlib/__init__.py`` is bypassed with a
 namespace shim because it pulls matplotlib through ``commands.py``.
 
-/root/reference does not exist on the GPU box: nothing under ``tests/ -m gpu``,
-``bench.py`` or ``__graft_entry__.smoke()`` may call this module.  Its only
-consumers are ``oracle/make_golden.py`` and the authoring-container-only tests
-marked ``needs_reference``.
+/root/reference does not exist on the GPU box: nothing under ``tests/ -m gpu`` or
+``__graft_entry__.smoke()`` may call this module.  Its consumers are ``oracle/make_golden.py``, the
+authoring-container-only tests marked ``needs_reference`` and ``bench.py``'s ``cpu_baseline`` legs, which time
+the reference's own Python (the ``pip install --target baseline/_ref`` copy, git-ignored) beside the port.
 """
 from __future__ import annotations
 
@@ -19,7 +19,11 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CNVKIT_REFERENCE_ROOT", "/root/reference")
+# /root/reference in the authoring container; on the GPU box the pip-installed copy under baseline/_ref
+# (git-ignored, travels with the gpurun snapshot) -- bench.py's cpu_baseline legs time it there
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = [os.environ.get("CNVKIT_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if c and os.path.isdir(os.path.join(c, "cnvlib"))), "/root/reference")
 _STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refshim_stubs")
 
 
