@@ -75,6 +75,8 @@ SIGNATURES = {
     "cnvk_haar_segment": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_double, c_int64, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
     "cnvk_cbs_getbdry": (c_int, [c_double, c_int32, c_int32, c_void_p]),
+    "cnvk_cbs_input_filter_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cnvk_coverage_finalize_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
     "cnvk_coverage_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]),
     "cnvk_smooth_cna_dev": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_double, c_double, c_double, c_void_p,
@@ -97,6 +99,10 @@ SIGNATURES = {
     "cnvk_tsv_read_str": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
     "cnvk_tsv_read_str_dict": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "cnvk_tsv_hash_cols": (c_uint64, [c_void_p, c_void_p, c_int32]),
+    "cnvk_ordered_unique_ranges": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_int64]),
+    "cnvk_join_names_ranges": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_int64]),
     "cnvk_tsv_write": (c_int, [c_char_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
 }
 

@@ -124,11 +124,17 @@ class CopyNumArray:
     def sort(self):
         order = genome.genomic_order(self.data["chromosome"].to_numpy(), self.data["start"].to_numpy(),
                                      self.data["end"].to_numpy())
+        n = len(order)
+        if n and np.array_equal(order, np.arange(n)) and isinstance(self.data.index, pd.RangeIndex) \
+                and self.data.index.start == 0 and self.data.index.step == 1:
+            return                                   # already in genomic order with a clean index
         self.data = self.data.iloc[order].reset_index(drop=True)
 
     def sort_columns(self):
         extra = sorted(c for c in self.data.columns if c not in REQUIRED)
-        self.data = self.data.reindex(columns=list(REQUIRED) + extra)
+        want = list(REQUIRED) + extra
+        if list(self.data.columns) != want:
+            self.data = self.data.reindex(columns=want)
 
     def concat(self, others):
         table = pd.concat([o.data for o in others], ignore_index=True)

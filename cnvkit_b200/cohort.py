@@ -233,14 +233,43 @@ class Panel:
         xs, ws, offs = [], [], [0]
         unit_arm_all = []
         for d_log2, d_w, d_depth in samples:
+            d_mask = None
+            if method == "cbs":
+                # outlier mask, weight gate, %.6g quantisation, the R script's row filters and the compaction in one
+                # native call (one synchronisation; cnvk_cbs_input_filter_dev)
+                if skip_outliers:
+                    d_mask = _dev.empty(self.n, torch.uint8)
+                    _lib.call("cnvk_outlier_mask_dev", _dev.ptr(d_log2), _lib.ptr(self.arm_off), n_arms, 0.95,
+                              float(skip_outliers), _dev.ptr(d_mask), _dev.stream())
+                xq, wq = _dev.empty(self.n, torch.float64), _dev.empty(self.n, torch.float64)
+                d_src = _dev.empty(self.n, torch.int64)
+                units = np.zeros(n_arms + 1, dtype=np.int64)
+                flags = np.zeros(1, dtype=np.uint32)
+                _lib.call("cnvk_cbs_input_filter_dev", _dev.ptr(d_log2), _dev.ptr(d_w), _dev.ptr(d_mask),
+                          _dev.ptr(self.d_arm_id), _lib.ptr(self.arm_off), n_arms, self.n, _dev.ptr(xq), _dev.ptr(wq),
+                          _dev.ptr(d_src), _lib.ptr(units), _lib.ptr(flags), _dev.stream())
+                if flags[0] & 1:                  # non-finite ratios: the general path handles the per-arm drops
+                    per.append(None)
+                    continue
+                if not flags[0] & 2:
+                    nk = int(units[-1])
+                    per.append(dict(fidx=None, d_src=d_src[:nk], units=units, unit_arm=np.arange(n_arms), base=offs[-1],
+                                    unit0=len(unit_arm_all)))
+                    unit_arm_all.extend(range(n_arms))
+                    xs.append(xq[:nk])
+                    ws.append(wq[:nk])
+                    offs.extend((units[1:] + offs[-1]).tolist() if len(units) > 1 else [])
+                    continue
+                # a value outside the device quantiser's range (|v| < 1e-16 or > 1e21): the step-by-step path below
             if not bool(torch.isfinite(d_log2).all()):
                 per.append(None)
                 continue
             keep = torch.ones(self.n, dtype=torch.bool, device=d_log2.device)
             if skip_outliers:
-                d_mask = _dev.empty(self.n, torch.uint8)
-                _lib.call("cnvk_outlier_mask_dev", _dev.ptr(d_log2), _lib.ptr(self.arm_off), n_arms, 0.95,
-                          float(skip_outliers), _dev.ptr(d_mask), _dev.stream())
+                if d_mask is None:
+                    d_mask = _dev.empty(self.n, torch.uint8)
+                    _lib.call("cnvk_outlier_mask_dev", _dev.ptr(d_log2), _lib.ptr(self.arm_off), n_arms, 0.95,
+                              float(skip_outliers), _dev.ptr(d_mask), _dev.stream())
                 keep &= d_mask == 0
             keep &= d_w != 0                      # NaN weights compare True and survive, as in the reference
             d_fidx = torch.nonzero(keep).flatten()
@@ -263,8 +292,8 @@ class Panel:
             offs.extend((units[1:] + offs[-1]).tolist() if len(units) > 1 else [])
         results = [None] * len(samples)
         if xs:
-            X = torch.cat(xs).contiguous()
-            W = torch.cat(ws).contiguous()
+            X = (xs[0] if len(xs) == 1 else torch.cat(xs)).contiguous()
+            W = (ws[0] if len(ws) == 1 else torch.cat(ws)).contiguous()
             off = np.asarray(offs, dtype=np.int64)
             if method == "cbs":
                 u, lo, hi, mean, _st = _cbs.segment_arms(None, None, off, alpha=float(threshold),
@@ -350,18 +379,27 @@ class Panel:
 
     def _segments_table(self, sample, info, s_unit, s_lo, s_hi, s_mean, sample_id, ci=None):
         d_log2, d_w, d_depth = sample
-        src = info["fidx"]
         seg_arm = info["unit_arm"][s_unit]
-        seg_chrom = self.chrom[src[s_lo]]
-        seg_start = self.start[src[s_lo]].copy()
-        seg_end = self.end[src[s_hi - 1]].copy()
+        if info["fidx"] is None:
+            # source rows of the segment boundaries only: one small gather instead of the whole index column
+            want = torch.from_numpy(np.concatenate([s_lo, s_hi - 1]).astype(np.int64)).to(d_log2.device)
+            rows = info["d_src"].index_select(0, want).cpu().numpy()
+            r_lo, r_hi = rows[:len(s_lo)], rows[len(s_lo):]
+        else:
+            src = info["fidx"]
+            r_lo, r_hi = src[s_lo], src[s_hi - 1]
+        seg_chrom = self.chrom[r_lo]
+        seg_start = self.start[r_lo].copy()
+        seg_end = self.end[r_hi].copy()
         probes = (s_hi - s_lo).astype(np.int64)
         segtab = segmentation._transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, s_mean, probes, self.arms,
                                                self.bins, None, d_w, d_depth, self.start, self.end,
                                                gene_codes=self.gene_codes)
         out = self.meta_cls(segtab, {"sample_id": sample_id})
-        out.sort()
-        out.sort_columns()
+        # rows are produced arm by arm in the panel's genomic order and _transfer_fields lays the columns out in
+        # sort_columns() order, so the reference's sort() / sort_columns() (:189-190) are no-ops here
+        if list(segtab.columns[:5]) != ["chromosome", "start", "end", "gene", "log2"]:
+            out.sort_columns()
         if ci:
             # segmetrics.py:93: the bins each (stretched) segment overlaps, filtered bins included
             if self._bin_index is None:

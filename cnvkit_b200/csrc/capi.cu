@@ -457,6 +457,19 @@ int cnvk_cbs_segment(const double* log2, const double* weight, const int64_t* ar
     return hc.finish();
 }
 
+int cnvk_cbs_input_filter_dev(const double* d_log2, const double* d_weight, const uint8_t* d_outlier, const int64_t* d_arm_id,
+                              const int64_t* arm_offsets, int32_t n_arms, int64_t n, double* d_log2_out, double* d_weight_out,
+                              int64_t* d_src_rows, int64_t* unit_offsets, uint32_t* flags, void* stream) {
+    RC(ensure_init());
+    std::vector<long long> off(arm_offsets, arm_offsets + n_arms + 1), units((size_t)n_arms + 1, 0);
+    unsigned int f = 0;
+    RC(cbs_input_filter(d_log2, d_weight, d_outlier, (const long long*)d_arm_id, off.data(), n_arms, n, d_log2_out,
+                        d_weight_out, (long long*)d_src_rows, units.data(), &f, (cudaStream_t)stream));
+    for (int a = 0; a <= n_arms; ++a) unit_offsets[a] = units[a];
+    *flags = f;
+    return 0;
+}
+
 int cnvk_coverage_finalize_dev(const double* d_basecount, const int64_t* d_start, const int64_t* d_end, int64_t n,
                                double null_log2, double* d_depth, double* d_log2, void* stream) {
     RC(ensure_init());

@@ -93,6 +93,9 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
                 std::vector<CbsSeg>& segs, CbsStats* stats, cudaStream_t stream, CbsDiag* diag = nullptr);
 int cbs_node_diag(const double* d_x, const double* d_w, const long long* h_off, int n_nodes, const CbsParams& P,
                   double* out6, int* iout5, cudaStream_t stream);
+int cbs_input_filter(const double* d_log2, const double* d_weight, const unsigned char* d_outlier, const long long* d_arm_id,
+                     const long long* h_arm_off, int n_arms, long long n, double* d_x_out, double* d_w_out,
+                     long long* d_src_out, long long* h_units, unsigned int* h_flags, cudaStream_t stream);
 // coverage.cu
 int coverage_finalize(const double* d_basecount, const long long* d_start, const long long* d_end, long long n,
                       double null_log2, double* d_depth, double* d_log2, cudaStream_t stream);

@@ -9,6 +9,7 @@
 //   segment_bin_sums transfer_fields' numeric part (segmentation/__init__.py:489-501): per segment
 //                    nansum of bin weights and the weighted mean of bin depths.
 #include "ops.cuh"
+#include "prims.cuh"
 #include "prof.cuh"
 #include <vector>
 
@@ -171,12 +172,9 @@ __device__ __forceinline__ double round_exact_sum(double hi, double lo) {
     return (fmod(f, 2.0) == 0.0) ? f : f + 1.0;
 }
 
-__global__ void round_sig_kernel(const double* __restrict__ x, long long n, int digits, double* __restrict__ out,
-                                 unsigned long long* __restrict__ unhandled) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double v = x[i];
-    if (v == 0.0 || !(fabs(v) < INFINITY)) { out[i] = v; return; }   // 0, inf, NaN print as themselves
+// float("%.{digits}g" % v): returns false when the value is outside the handled range (|v| < 1e-16 or > 1e21)
+__device__ __forceinline__ bool round_sig_value(double v, int digits, double* out) {
+    if (v == 0.0 || !(fabs(v) < INFINITY)) { *out = v; return true; }   // 0, inf, NaN print as themselves
     const double a = fabs(v);
     int e = (int)floor(log10(a));
     double m = 0.0;
@@ -201,14 +199,24 @@ __global__ void round_sig_kernel(const double* __restrict__ x, long long n, int 
         else if (m < bot) { --e; }
         else ok = true;
     }
-    if (!ok) { out[i] = v; atomicAdd(unhandled, 1ull); return; }
+    if (!ok) { *out = v; return false; }
     // value of the decimal m * 10^(e-digits+1), correctly rounded (Clinger's fast path)
     const int p = e - digits + 1;
     double r;
     if (p >= 0 && p <= 22) r = m * pow10_exact(p);
     else if (p < 0 && p >= -22) r = m / pow10_exact(-p);
-    else { out[i] = v; atomicAdd(unhandled, 1ull); return; }
-    out[i] = copysign(r, v);
+    else { *out = v; return false; }
+    *out = copysign(r, v);
+    return true;
+}
+
+__global__ void round_sig_kernel(const double* __restrict__ x, long long n, int digits, double* __restrict__ out,
+                                 unsigned long long* __restrict__ unhandled) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r;
+    if (!round_sig_value(x[i], digits, &r)) atomicAdd(unhandled, 1ull);
+    out[i] = r;
 }
 
 int round_sig(const double* d_x, long long n, int digits, double* d_out, unsigned long long* h_unhandled,
@@ -227,6 +235,111 @@ int round_sig(const double* d_x, long long n, int digits, double* d_out, unsigne
         CNVK_CHECK(cudaMemcpyAsync(h_unhandled, d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         CNVK_CHECK(cudaStreamSynchronize(stream));
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------ CBS input filter
+// Everything between a .cnr table and DNAcopy's input, fused (cnvlib/segmentation/__init__.py:239-282 per-arm
+// filters + :299-301 "%.6g" TSV + the R row filters cbs.py:22-35):
+//   keep a bin unless it is an outlier (mask from cnvk_outlier_mask_dev) or its weight is 0 (NaN weights survive
+//   this gate, as in the reference); quantise log2 and weight to 6 significant digits; per ARM, if no bin has a
+//   non-NA weight every weight becomes 1.0, else bins with NA or <= 0 weight are dropped; bins with NA log2 are
+//   dropped; the survivors are compacted in order.  Outputs: quantised columns, the source row of every survivor,
+//   the survivors' arm offsets (n_arms + 1) and a flag word (bit 0: a log2 is not finite -- the caller takes the
+//   general path; bit 1: a value outside the range of the device quantiser).
+__global__ void __launch_bounds__(256)
+cbs_filter_mark_kernel(const double* __restrict__ log2v, const double* __restrict__ weight, const unsigned char* __restrict__ outlier,
+                       const long long* __restrict__ arm_id, long long n, double* __restrict__ xq, double* __restrict__ wq,
+                       unsigned char* __restrict__ keep1, int* __restrict__ arm_has_w, unsigned int* __restrict__ flags) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = log2v[i], w = weight ? weight[i] : 1.0;
+    unsigned f = 0;
+    if (!(fabs(x) < INFINITY)) f |= 1u;
+    const bool k1 = !(outlier && outlier[i]) && !(w == 0.0);
+    double rx, rw;
+    if (!round_sig_value(x, 6, &rx)) f |= 2u;
+    if (!round_sig_value(w, 6, &rw)) f |= 2u;
+    xq[i] = rx;
+    wq[i] = rw;
+    keep1[i] = k1 ? 1 : 0;
+    if (k1 && rw == rw) arm_has_w[arm_id[i]] = 1;          // benign race: every writer stores 1
+    if (f) atomicOr(flags, f);
+}
+
+__global__ void __launch_bounds__(256)
+cbs_filter_ok_kernel(const double* __restrict__ xq, const double* __restrict__ wq, const unsigned char* __restrict__ keep1,
+                     const long long* __restrict__ arm_id, const int* __restrict__ arm_has_w, long long n, int have_weight,
+                     u32* __restrict__ ok) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { ok[n] = 0; return; }
+    bool o = keep1[i] != 0;
+    if (o && have_weight && arm_has_w[arm_id[i]]) o = (wq[i] == wq[i]) && wq[i] > 0.0;   // cbs.py:22-24
+    if (o) o = xq[i] == xq[i];                                                          // cbs.py:30-33
+    ok[i] = o ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+cbs_filter_scatter_kernel(const double* __restrict__ xq, const double* __restrict__ wq, const u32* __restrict__ ok,
+                          const u32* __restrict__ pos, const long long* __restrict__ arm_id, const int* __restrict__ arm_has_w,
+                          long long n, int have_weight, double* __restrict__ x_out, double* __restrict__ w_out,
+                          long long* __restrict__ src_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !ok[i]) return;
+    const u32 p = pos[i];
+    x_out[p] = xq[i];
+    w_out[p] = (have_weight && arm_has_w[arm_id[i]]) ? wq[i] : 1.0;                       // cbs.py:25-28
+    src_out[p] = i;
+}
+
+__global__ void cbs_filter_units_kernel(const u32* __restrict__ pos, const long long* __restrict__ arm_off, int n_arms,
+                                        long long* __restrict__ units) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a <= n_arms) units[a] = (long long)pos[arm_off[a]];     // pos has n + 1 entries: pos[n] = number of survivors
+}
+
+int cbs_input_filter(const double* d_log2, const double* d_weight, const unsigned char* d_outlier, const long long* d_arm_id,
+                     const long long* h_arm_off, int n_arms, long long n, double* d_x_out, double* d_w_out,
+                     long long* d_src_out, long long* h_units, unsigned int* h_flags, cudaStream_t stream) {
+    *h_flags = 0;
+    for (int a = 0; a <= n_arms; ++a) h_units[a] = 0;
+    if (n <= 0 || n_arms <= 0) return 0;
+    if (n >= (1ll << 31)) { set_last_error("cbs_input_filter: too many bins"); return -2; }
+    ProfScope ps(PC_OTHER, stream);
+    Scratch scratch(stream);
+    double *xq, *wq;
+    unsigned char* keep1;
+    int* arm_has_w;
+    unsigned int* flags;
+    u32 *ok, *pos;
+    long long *d_off, *d_units;
+    CNVK_CHECK(scratch.alloc(&xq, (size_t)n));
+    CNVK_CHECK(scratch.alloc(&wq, (size_t)n));
+    CNVK_CHECK(scratch.alloc(&keep1, (size_t)n));
+    CNVK_CHECK(scratch.alloc(&arm_has_w, (size_t)n_arms + 2));
+    CNVK_CHECK(scratch.alloc(&flags, 1));
+    CNVK_CHECK(scratch.alloc(&ok, (size_t)n + 1));
+    CNVK_CHECK(scratch.alloc(&pos, (size_t)n + 1));
+    CNVK_CHECK(scratch.alloc(&d_off, (size_t)n_arms + 1));
+    CNVK_CHECK(scratch.alloc(&d_units, (size_t)n_arms + 1));
+    CNVK_CHECK(cudaMemsetAsync(arm_has_w, 0, ((size_t)n_arms + 2) * sizeof(int), stream));
+    CNVK_CHECK(cudaMemsetAsync(flags, 0, sizeof(unsigned int), stream));
+    CNVK_CHECK(cudaMemcpyAsync(d_off, h_arm_off, ((size_t)n_arms + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    const int have_weight = d_weight ? 1 : 0;
+    cbs_filter_mark_kernel<<<div_up(n, 256), 256, 0, stream>>>(d_log2, d_weight, d_outlier, d_arm_id, n, xq, wq, keep1, arm_has_w, flags);
+    CNVK_LAUNCH_CHECK();
+    cbs_filter_ok_kernel<<<div_up(n + 1, 256), 256, 0, stream>>>(xq, wq, keep1, d_arm_id, arm_has_w, n, have_weight, ok);
+    CNVK_LAUNCH_CHECK();
+    int rc = exclusive_scan_u32(ok, pos, n + 1, nullptr, stream);
+    if (rc) return rc;
+    cbs_filter_scatter_kernel<<<div_up(n, 256), 256, 0, stream>>>(xq, wq, ok, pos, d_arm_id, arm_has_w, n, have_weight, d_x_out, d_w_out, d_src_out);
+    CNVK_LAUNCH_CHECK();
+    cbs_filter_units_kernel<<<div_up(n_arms + 1, 128), 128, 0, stream>>>(pos, d_off, n_arms, d_units);
+    CNVK_LAUNCH_CHECK();
+    CNVK_CHECK(cudaMemcpyAsync(h_units, d_units, ((size_t)n_arms + 1) * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+    CNVK_CHECK(cudaMemcpyAsync(h_flags, flags, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    CNVK_CHECK(cudaStreamSynchronize(stream));
     return 0;
 }
 

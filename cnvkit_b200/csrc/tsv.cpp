@@ -433,4 +433,66 @@ int cnvk_tsv_write(const char* path, int32_t ncols, const char* const* names, co
     return 0;
 }
 
+// skgenome/combiners.py:58-94 join_strings over bin ranges, the host half of transfer_fields
+// (cnvlib/segmentation/__init__.py:467-501): for every row range [lo[s], hi[s]) the distinct gene codes in order
+// of first appearance, skipping codes < 0 (missing gene) and codes without a kept name (keep[code] == 0: the
+// ignored placeholder / antitarget names).  CSR output: out_off[nseg + 1], out_codes[<= capacity].  One pass over
+// the rows with a per-code "last segment seen" stamp -- O(rows), no hashing.  Optional nested-bin mask
+// (intersect.py _irange_nested): a row counts only if mask_end[row] > mask_start[s].
+int cnvk_ordered_unique_ranges(const int64_t* codes, const int64_t* lo, const int64_t* hi, int32_t nseg, int64_t ncodes,
+                               const uint8_t* keep, const int64_t* mask_end, const int64_t* mask_start, int64_t* out_off,
+                               int64_t* out_codes, int64_t capacity) {
+    std::vector<int32_t> stamp((size_t)std::max<int64_t>(ncodes, 1), -1);
+    int64_t pos = 0;
+    for (int32_t s = 0; s < nseg; ++s) {
+        out_off[s] = pos;
+        for (int64_t r = lo[s]; r < hi[s]; ++r) {
+            const int64_t c = codes[r];
+            if (c < 0 || c >= ncodes) continue;
+            if (keep && !keep[c]) continue;
+            if (mask_end && !(mask_end[r] > mask_start[s])) continue;
+            if (stamp[(size_t)c] == s) continue;
+            stamp[(size_t)c] = s;
+            if (pos >= capacity) return fail("cnvk_ordered_unique_ranges: %s", "output capacity exceeded");
+            out_codes[pos++] = c;
+        }
+    }
+    out_off[nseg] = pos;
+    return 0;
+}
+
+// The same pass, emitting the joined names: name_blob / name_off[ncodes + 1] hold one kept name per code (empty for
+// codes without one), the result is "a,b,c" per range ("-" when nothing remains) in out_blob / out_off[nseg + 1].
+// Only valid when every code carries at most one name and no name is shared between codes (the caller checks).
+int cnvk_join_names_ranges(const int64_t* codes, const int64_t* lo, const int64_t* hi, int32_t nseg, int64_t ncodes,
+                           const char* name_blob, const int64_t* name_off, const int64_t* mask_end,
+                           const int64_t* mask_start, char* out_blob, int64_t* out_off, int64_t capacity) {
+    std::vector<int32_t> stamp((size_t)std::max<int64_t>(ncodes, 1), -1);
+    int64_t pos = 0;
+    for (int32_t s = 0; s < nseg; ++s) {
+        out_off[s] = pos;
+        bool first = true;
+        for (int64_t r = lo[s]; r < hi[s]; ++r) {
+            const int64_t c = codes[r];
+            if (c < 0 || c >= ncodes) continue;
+            const int64_t len = name_off[c + 1] - name_off[c];
+            if (len == 0) continue;
+            if (mask_end && !(mask_end[r] > mask_start[s])) continue;
+            if (stamp[(size_t)c] == s) continue;
+            stamp[(size_t)c] = s;
+            if (pos + len + 1 > capacity) return fail("cnvk_join_names_ranges: %s", "output capacity exceeded");
+            if (!first) out_blob[pos++] = ',';
+            memcpy(out_blob + pos, name_blob + name_off[c], (size_t)len);
+            pos += len;
+            first = false;
+        }
+        if (first) {
+            if (pos + 1 > capacity) return fail("cnvk_join_names_ranges: %s", "output capacity exceeded");
+            out_blob[pos++] = '-';
+        }
+    }
+    out_off[nseg] = pos;
+    return 0;
+}
+
 }  // extern "C"

@@ -327,9 +327,10 @@ def _transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, seg_log2, probes, a
     seg_weight, seg_depth = d_sw.cpu().numpy(), d_sd.cpu().numpy()
     genes = _join_genes(None if gene_codes is not None else data["gene"], bin_lo, bin_hi, gene_codes,
                         mask_end=end if nested else None, mask_start=seg_start if nested else None)
+    # columns already in sort_columns() order (required five, then the extras alphabetically)
     return pd.DataFrame({
         "chromosome": seg_chrom, "start": seg_start, "end": seg_end, "gene": genes, "log2": seg_log2,
-        "probes": probes, "weight": seg_weight, "depth": seg_depth,
+        "depth": seg_depth, "probes": probes, "weight": seg_weight,
     })
 
 
@@ -343,12 +344,20 @@ class GeneCodes:
         codes, uniques = genome.encode_column(bin_genes if hasattr(bin_genes, "array") else
                                               pd.Series(bin_genes, dtype=object))
         self.codes = codes
+        self.codes64 = np.ascontiguousarray(codes, dtype=np.int64)
         self.parts = [tuple(p for p in u.split(",") if p not in ignore) if isinstance(u, str) else ()
                       for u in uniques]
         flat = [p for ps in self.parts for p in ps]
         self.simple = all(len(ps) <= 1 for ps in self.parts) and len(set(flat)) == len(flat)
         self.names = np.array([ps[0] if ps else "" for ps in self.parts] + [""], dtype=object)  # [-1] -> ""
         self.has_name = np.array([bool(ps) for ps in self.parts] + [False])
+        self.keep8 = np.ascontiguousarray(self.has_name[:-1].astype(np.uint8)) if len(self.parts) else np.zeros(1, np.uint8)
+        if self.simple:
+            enc = [(ps[0].encode("utf-8") if ps else b"") for ps in self.parts]
+            self.name_off = np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)
+            self.name_blob = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8).copy()
+            self.names_total = int(self.name_off[-1])
+            self.name_max = max([len(e) for e in enc], default=0)
 
 
 def factorize_genes(bin_genes):
@@ -358,28 +367,49 @@ def factorize_genes(bin_genes):
 
 def _join_genes(bin_genes, bin_lo, bin_hi, gene_codes=None, mask_end=None, mask_start=None):
     """skgenome/combiners.py:58-94 join_strings per segment: ordered-unique gene names of the
-    bins, split on ',', minus the ignored placeholder / antitarget names; '-' if none remain."""
+    bins, split on ',', minus the ignored placeholder / antitarget names; '-' if none remain.  The distinct codes
+    per range come from one native pass (cnvk_ordered_unique_ranges); names are joined here."""
     gc = gene_codes if gene_codes is not None else GeneCodes(bin_genes)
-    codes = gc.codes
-    out = []
-    for k, (lo, hi) in enumerate(zip(bin_lo, bin_hi)):
-        if hi <= lo:
-            out.append("-")
-            continue
-        rows = codes[lo:hi]
-        if mask_end is not None:                  # nested bins: only rows whose end lies beyond the segment start
-            rows = rows[np.asarray(mask_end[lo:hi]) > mask_start[k]]
-        u = pd.unique(rows)                       # hash-based, keeps first-appearance order
-        if gc.simple:
-            out.append(",".join(gc.names[u[gc.has_name[u]]].tolist()) or "-")
-            continue
-        seen = {}
-        for ci in u:
-            if ci >= 0:
-                for name in gc.parts[ci]:
+    nseg = len(bin_lo)
+    if nseg == 0:
+        return []
+    lo = np.ascontiguousarray(bin_lo, dtype=np.int64)
+    hi = np.ascontiguousarray(np.maximum(bin_hi, bin_lo), dtype=np.int64)
+    m_end = np.ascontiguousarray(mask_end, dtype=np.int64) if mask_end is not None else None
+    m_start = np.ascontiguousarray(mask_start, dtype=np.int64) if mask_end is not None else None
+    if gc.simple:
+        # names joined natively: one bytes blob for all segments
+        cap = int(nseg * (gc.names_total + len(gc.parts) + 2)) if nseg * len(gc.parts) < 4_000_000 else \
+            int(((hi - lo).sum() + nseg) * (gc.name_max + 1) + nseg + 1)
+        blob = np.empty(max(cap, 1), dtype=np.uint8)
+        off = np.empty(nseg + 1, dtype=np.int64)
+        _lib.call("cnvk_join_names_ranges", _lib.ptr(gc.codes64), _lib.ptr(lo), _lib.ptr(hi), nseg, len(gc.parts),
+                  _lib.ptr(gc.name_blob), _lib.ptr(gc.name_off), _lib.ptr(m_end) if m_end is not None else 0,
+                  _lib.ptr(m_start) if m_start is not None else 0, _lib.ptr(blob), _lib.ptr(off), len(blob))
+        raw = blob[:int(off[-1])].tobytes()
+        o = off.tolist()
+        return [raw[o[k]:o[k + 1]].decode("utf-8") for k in range(nseg)]
+    cap = int(min(int((hi - lo).sum()), nseg * max(len(gc.parts), 1))) + 1
+    off = np.empty(nseg + 1, dtype=np.int64)
+    out = np.empty(cap, dtype=np.int64)
+    _lib.call("cnvk_ordered_unique_ranges", _lib.ptr(gc.codes64), _lib.ptr(lo), _lib.ptr(hi), nseg, len(gc.parts),
+              _lib.ptr(gc.keep8), _lib.ptr(m_end) if m_end is not None else 0,
+              _lib.ptr(m_start) if m_start is not None else 0, _lib.ptr(off), _lib.ptr(out), cap)
+    res = []
+    names, parts = gc.names, gc.parts
+    for k in range(nseg):
+        u = out[off[k]:off[k + 1]]
+        if not len(u):
+            res.append("-")
+        elif gc.simple:
+            res.append(",".join(names[u].tolist()))
+        else:
+            seen = {}
+            for ci in u.tolist():
+                for name in parts[ci]:
                     seen.setdefault(name, None)
-        out.append(",".join(seen) or "-")
-    return out
+            res.append(",".join(seen) or "-")
+    return res
 
 
 def _seg_text(sample_id, chrom, start, end, probes, mean):

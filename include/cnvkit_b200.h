@@ -224,6 +224,18 @@ int cnvk_cbs_segment(const double* log2, const double* weight, const int64_t* ar
                      int32_t n_arms, const cnvk_cbs_params* params, int64_t capacity, int32_t* seg_arm,
                      int64_t* seg_lo, int64_t* seg_hi, double* seg_mean, int64_t* n_segs,
                      cnvk_cbs_stats* stats);
+/* Everything between a .cnr table and DNAcopy's input, fused for device-resident columns: the per-arm bin filters
+ * of cnvlib/segmentation/__init__.py:239-282 (outlier mask from cnvk_outlier_mask_dev or NULL, weight == 0), the
+ * "%.6g" TSV quantisation (:299-301) and the R script's row filters (cbs.py:22-35: per arm, no non-NA weight ->
+ * weight 1.0 for every bin, else NA / <= 0 weights dropped; NA log2 dropped), survivors compacted in order.
+ * d_arm_id[n] = arm of every bin, arm_offsets (HOST) the unfiltered arm offsets.  Outputs: d_log2_out / d_weight_out /
+ * d_src_rows (capacity n), unit_offsets[n_arms + 1] (HOST) = arm offsets of the survivors, *flags (HOST): bit 0 a
+ * log2 is not finite (caller must drop those bins first), bit 1 a value outside the device quantiser's range. */
+int cnvk_cbs_input_filter_dev(const double* d_log2, const double* d_weight, const uint8_t* d_outlier,
+                              const int64_t* d_arm_id, const int64_t* arm_offsets, int32_t n_arms, int64_t n,
+                              double* d_log2_out, double* d_weight_out, int64_t* d_src_rows, int64_t* unit_offsets,
+                              uint32_t* flags, void* stream);
+
 /* ---- coverage finalisation (the step before the path) ------------------------------ */
 /* cnvlib/coverage.py:637-643 (interval_coverages_pileup) and :403-409 (interval_coverages_bedgraph): depth =
  * basecount / (end - start) for bins of positive width, else 0; log2 = log2(depth) where depth > 0, else null_log2
@@ -347,6 +359,21 @@ typedef struct cnvk_tsv_dict {
 } cnvk_tsv_dict;
 int cnvk_tsv_write(const char* path, int32_t ncols, const char* const* names, const int32_t* kinds,
                    const void* const* ptrs, const void* const* ptrs2, int64_t nrows);
+
+/* skgenome/combiners.py:58-94 join_strings per bin range -- the string half of transfer_fields
+ * (cnvlib/segmentation/__init__.py:467-501), host only: for every row range [lo[s], hi[s]) of a dictionary-coded
+ * gene column the distinct codes in order of first appearance; codes < 0 (missing) and codes with keep[code] == 0
+ * (ignored placeholder / antitarget names) are skipped.  mask_end / mask_start (both NULL or both given) restrict a
+ * range to rows with mask_end[row] > mask_start[s] (nested bins).  CSR output out_off[nseg + 1], out_codes[capacity]. */
+int cnvk_ordered_unique_ranges(const int64_t* codes, const int64_t* lo, const int64_t* hi, int32_t nseg, int64_t ncodes,
+                               const uint8_t* keep, const int64_t* mask_end, const int64_t* mask_start, int64_t* out_off,
+                               int64_t* out_codes, int64_t capacity);
+/* The same pass with the names joined natively ("a,b,c" per range, "-" when nothing remains): name_blob /
+ * name_off[ncodes + 1] carry one kept name per code (empty = no name).  For gene columns in which every code holds at
+ * most one name and no name is shared between codes. */
+int cnvk_join_names_ranges(const int64_t* codes, const int64_t* lo, const int64_t* hi, int32_t nseg, int64_t ncodes,
+                           const char* name_blob, const int64_t* name_off, const int64_t* mask_end,
+                           const int64_t* mask_start, char* out_blob, int64_t* out_off, int64_t capacity);
 
 #ifdef __cplusplus
 }
