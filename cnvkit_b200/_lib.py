@@ -29,6 +29,7 @@ SIGNATURES = {
     "cnvk_launch_count": (c_ulonglong, []),
     "cnvk_device_info": (c_int, [c_int, POINTER(c_int), POINTER(c_uint64), POINTER(c_uint64)]),
     "cnvk_fp64_peak": (c_int, [c_int, c_int, c_void_p]),
+    "cnvk_nvtx_enable": (None, [c_int]),
     "cnvk_prof_enable": (None, [c_int]),
     "cnvk_prof_reset": (None, []),
     "cnvk_prof_count": (c_int, []),

@@ -1,9 +1,12 @@
 // extern "C" surface of libcnvkit_b200.so -- see include/cnvkit_b200.h for the contract.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/cnvkit_b200.h"
 #include <mutex>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "ops.cuh"
 #include "prof.cuh"
@@ -11,6 +14,7 @@
 namespace cnvk {
 std::atomic<unsigned long long> g_launch_count{0};
 int g_prof_enabled = 0;
+int g_nvtx_enabled = getenv("CNVK_NVTX") ? atoi(getenv("CNVK_NVTX")) : 0;
 struct ProfPending { int cls; cudaEvent_t a, b; };
 static std::vector<ProfPending> g_prof_pending;
 static std::mutex g_prof_mutex;   // host threads of a cohort run share the profiler
@@ -44,6 +48,8 @@ static const char* const kProfNames[PC_COUNT] = {
     "radix_sort", "wavelet_build", "window_query", "cbs_prep", "cbs_scan", "cbs_seed", "cbs_band",
     "cbs_bound", "cbs_means", "cbs_decide", "cbs_perm_hybrid",
     "cbs_perm_exact", "cbs_flank", "fix", "haar", "biweight", "other"};
+void prof_nvtx_push(int cls) { nvtxRangePushA((cls >= 0 && cls < PC_COUNT) ? kProfNames[cls] : "cnvk"); }
+void prof_nvtx_pop() { nvtxRangePop(); }
 static thread_local char g_err[1024] = "";
 void set_last_error(const char* fmt, ...) {
     va_list ap;
@@ -125,6 +131,7 @@ int cnvk_abi_version(void) { return 3; }
 unsigned long long cnvk_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
 
 void cnvk_prof_enable(int on) { g_prof_enabled = on; }
+void cnvk_nvtx_enable(int on) { g_nvtx_enabled = on; }
 void cnvk_prof_reset(void) {
     prof_collect();
     for (int k = 0; k < PC_COUNT; ++k) { g_prof_ms[k] = 0.0; g_prof_n[k] = 0; }

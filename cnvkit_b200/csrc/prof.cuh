@@ -27,18 +27,24 @@ enum ProfClass {
 };
 
 extern int g_prof_enabled;
+extern int g_nvtx_enabled;      // CNVK_NVTX=1: an NVTX range per kernel class (for nsys / ncu --nvtx timelines)
 void prof_begin(int cls, cudaStream_t stream, cudaEvent_t* start);
 void prof_end(int cls, cudaStream_t stream, cudaEvent_t start);
+void prof_nvtx_push(int cls);
+void prof_nvtx_pop();
 
 struct ProfScope {
     int cls;
     cudaStream_t stream;
     cudaEvent_t start;
-    ProfScope(int c, cudaStream_t s) : cls(c), stream(s), start(nullptr) {
+    bool nvtx;
+    ProfScope(int c, cudaStream_t s) : cls(c), stream(s), start(nullptr), nvtx(false) {
+        if (g_nvtx_enabled) { prof_nvtx_push(cls); nvtx = true; }
         if (g_prof_enabled) prof_begin(cls, stream, &start);
     }
     ~ProfScope() {
         if (start) prof_end(cls, stream, start);
+        if (nvtx) prof_nvtx_pop();
     }
 };
 

@@ -42,6 +42,9 @@ int cnvk_fp64_peak(int iters, int reps, double* tflops);
  * cnvk_prof_get synchronises on the recorded events and returns accumulated milliseconds and the
  * number of timed scopes per class; class names come from cnvk_prof_name(0..cnvk_prof_count()-1). */
 void cnvk_prof_enable(int on);
+/* NVTX range per kernel class around the launches (also switched on by the environment variable CNVK_NVTX=1), for
+ * `ncu --nvtx` / timeline tools. */
+void cnvk_nvtx_enable(int on);
 void cnvk_prof_reset(void);
 int cnvk_prof_count(void);
 const char* cnvk_prof_name(int cls);
