@@ -71,6 +71,10 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cnvk_cbs_segment": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cnvk_haar_segment_sigma": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_double, c_void_p, c_int64, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cnvk_haar_sigma": (c_int, [c_void_p, c_void_p, c_int32, c_void_p]),
+    "cnvk_haar_segment_means": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p]),
     "cnvk_haar_segment_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_double, c_int64, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p]),
     "cnvk_haar_segment": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_double, c_int64, c_void_p, c_void_p,

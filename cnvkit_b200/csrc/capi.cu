@@ -575,10 +575,10 @@ int cnvk_segment_bin_sums_masked_dev(const double* d_depth, const double* d_weig
 
 static int haar_common(const double* d_x, const double* d_w, const int64_t* arm_offsets, int32_t n_arms, double q,
                        int64_t capacity, int32_t* seg_arm, int64_t* seg_lo, int64_t* seg_hi, double* seg_mean,
-                       int64_t* n_segs, cudaStream_t stream) {
+                       int64_t* n_segs, cudaStream_t stream, const double* sigma_override = nullptr) {
     std::vector<long long> off(arm_offsets, arm_offsets + n_arms + 1);
     std::vector<CbsSeg> segs;
-    RC(haar_segment(d_x, d_w, off.data(), n_arms, q, segs, stream));
+    RC(haar_segment(d_x, d_w, off.data(), n_arms, q, segs, stream, sigma_override));
     if ((int64_t)segs.size() > capacity) {
         set_last_error("cnvk_haar_segment: %zu segments exceed capacity %lld", segs.size(), (long long)capacity);
         return -4;
@@ -608,6 +608,42 @@ int cnvk_haar_segment(const double* log2, const double* weight, const int64_t* a
     RC(hc.upload(log2, N, &dx));
     if (weight) RC(hc.upload(weight, N, &dw));
     RC(haar_common(dx, dw, arm_offsets, n_arms, fdr_q, capacity, seg_arm, seg_lo, seg_hi, seg_mean, n_segs, hc.stream));
+    return hc.finish();
+}
+
+int cnvk_haar_segment_sigma(const double* signal, const double* weight, const int64_t* arm_offsets, int32_t n_arms,
+                            double fdr_q, const double* sigma_override, int64_t capacity, int32_t* seg_arm,
+                            int64_t* seg_lo, int64_t* seg_hi, double* seg_mean, int64_t* n_segs) {
+    HostCall hc;
+    RC(hc.begin());
+    const size_t N = n_arms > 0 ? (size_t)arm_offsets[n_arms] : 0;
+    double *dx, *dw = nullptr;
+    RC(hc.upload(signal, N, &dx));
+    if (weight) RC(hc.upload(weight, N, &dw));
+    RC(haar_common(dx, dw, arm_offsets, n_arms, fdr_q, capacity, seg_arm, seg_lo, seg_hi, seg_mean, n_segs, hc.stream,
+                   sigma_override));
+    return hc.finish();
+}
+
+int cnvk_haar_sigma(const double* signal, const int64_t* arm_offsets, int32_t n_arms, double* sigma) {
+    HostCall hc;
+    RC(hc.begin());
+    const size_t N = n_arms > 0 ? (size_t)arm_offsets[n_arms] : 0;
+    double* dx;
+    RC(hc.upload(signal, N, &dx));
+    std::vector<long long> off(arm_offsets, arm_offsets + n_arms + 1);
+    RC(haar_sigma(dx, off.data(), n_arms, sigma, hc.stream));
+    return hc.finish();
+}
+
+int cnvk_haar_segment_means(const double* signal, const double* weight, int64_t n, const int64_t* seg_lo,
+                            const int64_t* seg_hi, int32_t n_segs, double* seg_mean) {
+    HostCall hc;
+    RC(hc.begin());
+    double *dx, *dw = nullptr;
+    RC(hc.upload(signal, (size_t)n, &dx));
+    if (weight) RC(hc.upload(weight, (size_t)n, &dw));
+    RC(haar_segment_means(dx, dw, (const long long*)seg_lo, (const long long*)seg_hi, n_segs, seg_mean, hc.stream));
     return hc.finish();
 }
 

@@ -348,8 +348,67 @@ __global__ void fill_u32_kernel(u32* p, long long n, u32 v) {
     if (i < n) p[i] = v;
 }
 
+__global__ void sigma_override_kernel(const double* __restrict__ ov, int n_arms, double* __restrict__ sigma) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < n_arms && ov[a] == ov[a]) sigma[a] = fmax(ov[a], 1e-10);      // haar.py:334-339 sigma_override, floored
+}
+
+// peakSigmaEst of haarSeg (haar.py:307-333) for every arm: 1.4826 * median |HaarConv(x, None, 1)|, floored
+int haar_sigma(const double* d_x, const long long* h_off, int n_arms, double* h_sigma, cudaStream_t stream) {
+    if (n_arms <= 0) return 0;
+    const long long N = h_off[n_arms];
+    for (int a = 0; a < n_arms; ++a) h_sigma[a] = 1e-10;
+    if (N <= 0) return 0;
+    ProfScope pscope(PC_HAAR, stream);
+    Scratch scratch(stream);
+    long long* d_off;
+    double *conv, *absv, *med, *sigma;
+    int* cnt;
+    CNVK_CHECK(scratch.alloc(&d_off, (size_t)n_arms + 1));
+    CNVK_CHECK(scratch.alloc(&conv, (size_t)N));
+    CNVK_CHECK(scratch.alloc(&absv, (size_t)N));
+    CNVK_CHECK(scratch.alloc(&med, (size_t)n_arms));
+    CNVK_CHECK(scratch.alloc(&sigma, (size_t)n_arms));
+    CNVK_CHECK(scratch.alloc(&cnt, (size_t)n_arms));
+    CNVK_CHECK(cudaMemcpyAsync(d_off, h_off, ((size_t)n_arms + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    haar_conv_kernel<<<dim3(n_arms, 1), 128, 0, stream>>>(d_x, nullptr, d_off, N, conv);     // chain 0 only
+    CNVK_LAUNCH_CHECK();
+    abs_kernel<<<div_up(N, 256), 256, 0, stream>>>(conv, N, absv);
+    CNVK_LAUNCH_CHECK();
+    int rc = segmented_median(absv, nullptr, d_off, n_arms, med, cnt, stream);
+    if (rc) return rc;
+    sigma_kernel<<<div_up(n_arms, 128), 128, 0, stream>>>(med, n_arms, sigma);
+    CNVK_LAUNCH_CHECK();
+    std::vector<double> tmp((size_t)n_arms);
+    CNVK_CHECK(cudaMemcpyAsync(tmp.data(), sigma, (size_t)n_arms * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CNVK_CHECK(cudaStreamSynchronize(stream));
+    for (int a = 0; a < n_arms; ++a)
+        if (h_off[a + 1] - h_off[a] >= 2) h_sigma[a] = tmp[(size_t)a];       // fewer than 2 values: the floor (haar.py:167-168)
+    return 0;
+}
+
+// SegmentByPeaks means (haar.py:405-451) for given segments
+int haar_segment_means(const double* d_x, const double* d_w, const long long* h_lo, const long long* h_hi, int nseg,
+                       double* h_mean, cudaStream_t stream) {
+    if (nseg <= 0) return 0;
+    ProfScope pscope(PC_HAAR, stream);
+    Scratch scratch(stream);
+    long long *d_lo, *d_hi;
+    double* d_mean;
+    CNVK_CHECK(scratch.alloc(&d_lo, (size_t)nseg));
+    CNVK_CHECK(scratch.alloc(&d_hi, (size_t)nseg));
+    CNVK_CHECK(scratch.alloc(&d_mean, (size_t)nseg));
+    CNVK_CHECK(cudaMemcpyAsync(d_lo, h_lo, (size_t)nseg * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    CNVK_CHECK(cudaMemcpyAsync(d_hi, h_hi, (size_t)nseg * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    haar_seg_mean_kernel<<<div_up(nseg, 4), 128, 0, stream>>>(d_x, d_w, d_lo, d_hi, nseg, d_mean);
+    CNVK_LAUNCH_CHECK();
+    CNVK_CHECK(cudaMemcpyAsync(h_mean, d_mean, (size_t)nseg * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CNVK_CHECK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
 int haar_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, double q,
-                 std::vector<CbsSeg>& segs, cudaStream_t stream) {
+                 std::vector<CbsSeg>& segs, cudaStream_t stream, const double* h_sigma_override) {
     segs.clear();
     if (n_arms <= 0) return 0;
     const long long N = h_off[n_arms];
@@ -380,6 +439,13 @@ int haar_segment(const double* d_x, const double* d_w, const long long* h_off, i
     if (rc) return rc;
     sigma_kernel<<<div_up(n_arms, 128), 128, 0, stream>>>(med, n_arms, sigma);
     CNVK_LAUNCH_CHECK();
+    if (h_sigma_override) {
+        double* d_ov;
+        CNVK_CHECK(scratch.alloc(&d_ov, (size_t)n_arms));
+        CNVK_CHECK(cudaMemcpyAsync(d_ov, h_sigma_override, (size_t)n_arms * sizeof(double), cudaMemcpyHostToDevice, stream));
+        sigma_override_kernel<<<div_up(n_arms, 128), 128, 0, stream>>>(d_ov, n_arms, sigma);
+        CNVK_LAUNCH_CHECK();
+    }
     // peaks
     const long long LN = (long long)HAAR_LEVELS * N;
     u32 *flags, *scan, *total;

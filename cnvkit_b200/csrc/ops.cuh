@@ -104,7 +104,10 @@ int smooth_cna(const double* d_x, const long long* h_off, int n_arms, int k, dou
                double trim, double* d_out, double* d_sd_out, cudaStream_t stream);
 // haar.cu (segments reuse CbsSeg)
 int haar_segment(const double* d_x, const double* d_w, const long long* h_off, int n_arms, double q,
-                 std::vector<CbsSeg>& segs, cudaStream_t stream);
+                 std::vector<CbsSeg>& segs, cudaStream_t stream, const double* h_sigma_override = nullptr);
+int haar_sigma(const double* d_x, const long long* h_off, int n_arms, double* h_sigma, cudaStream_t stream);
+int haar_segment_means(const double* d_x, const double* d_w, const long long* h_lo, const long long* h_hi, int nseg,
+                       double* h_mean, cudaStream_t stream);
 void cbs_getbdry(double eta, int nperm, int max_ones, std::vector<int>& out);
 
 }  // namespace cnvk

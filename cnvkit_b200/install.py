@@ -69,7 +69,8 @@ def _segment_needs_reference(args, kwargs):
     #                                                               cnvlib/segmentation/__init__.py:31-44
     method = _arg(args, kwargs, 1, "method", None)
     variants = _arg(args, kwargs, 4, "variants", None)
-    return method not in ("cbs", "haar") or (variants is not None and len(variants) > 0)
+    has_variants = variants is not None and len(variants) > 0
+    return method not in ("cbs", "haar") or (has_variants and method != "haar")   # haar takes the BAF union itself
 
 
 def _segmetrics_seam(ours, theirs):

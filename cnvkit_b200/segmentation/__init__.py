@@ -48,8 +48,12 @@ def do_segmentation(
         return (cnarr, "") if save_dataframe else cnarr
     if method not in _GPU_METHODS:
         raise NotImplementedError(f"method {method!r} is outside the GPU hot path (cbs and haar are implemented)")
-    if variants is not None and len(variants):
-        raise NotImplementedError("BAF-aware segmentation (variants=...) is outside the GPU hot path")
+    if variants is not None and not len(variants):
+        variants = None
+    if variants is not None and method != "haar":
+        raise NotImplementedError("variants=... with method 'cbs' (HMM re-segmentation of allele frequencies, "
+                                  "segmentation/__init__.py:340-358) is outside the GPU hot path; "
+                                  "method 'haar' takes the depth + BAF breakpoint union")
     if smooth_cbs and method != "cbs":
         smooth_cbs = False          # the flag only reaches the R script of method 'cbs' (:318)
     if cnarr.sample_id is None:
@@ -125,7 +129,8 @@ def do_segmentation(
     if method == "cbs":
         seg = _segment_cbs(f_log2, f_weight, f_arm, len(arms), threshold, smooth_cbs)
     else:
-        seg = _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, len(arms), threshold)
+        seg = _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, len(arms), threshold, variants,
+                            lambda rows: cnarr.as_dataframe(data.iloc[fidx[rows]].reset_index(drop=True)))
     s_unit, s_lo, s_hi, s_mean, unit_arm, sub_fidx = seg
     # rows of the per-arm segment tables (cbs.py:64-73 / haar.py:244-254)
     src = fidx if sub_fidx is None else fidx[sub_fidx]
@@ -137,6 +142,11 @@ def do_segmentation(
 
     segtab = _transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, s_mean, probes, arms, data, log2, weight,
                               depth, start, end)
+    if variants is not None:
+        # :359 -- per-segment BAF of the segments as the segmenter made them (before transfer_fields stretches them)
+        pre = cnarr.as_dataframe(pd.DataFrame({"chromosome": seg_chrom, "start": seg_start, "end": seg_end, "gene": "-",
+                                               "log2": s_mean, "probes": probes}))
+        segtab["baf"] = np.asarray(variants.baf_by_ranges(pre), dtype=np.float64)
     result = cnarr.as_dataframe(segtab)
     result.sort()
     result.sort_columns()
@@ -258,9 +268,12 @@ def _segment_cbs(f_log2, f_weight, f_arm, n_arms, threshold, smooth_cbs=False):
     return arm, lo, hi, mean, np.arange(n_arms), sub
 
 
-def _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, n_arms, threshold):
+def _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, n_arms, threshold, variants=None, subtable=None):
     """`case "haar"` (:286-289): segment_haar re-splits every filtered arm with by_arm() again
-    (haar.py:80-82), so the segmentation units are the arms of the *filtered* arm tables."""
+    (haar.py:80-82), so the segmentation units are the arms of the *filtered* arm tables.  With `variants`
+    (haar.py:188-225 one_chrom_baf) every unit is segmented twice -- log2, and the per-bin BAF signal with its own
+    noise estimate -- and the two breakpoint sets are merged (UnifyLevels, window 1); `subtable(rows)` returns the
+    unit's bins as the caller's array class for the VariantArray aggregation (host, the reference's own object)."""
     units_off = [0]
     unit_arm = []
     off = _arm_offsets(f_arm, n_arms)
@@ -272,8 +285,57 @@ def _segment_haar(f_log2, f_weight, f_arm, f_start, f_end, n_arms, threshold):
         for shi in ((cut, hi - lo) if cut else (hi - lo,)):
             units_off.append(lo + shi)
             unit_arm.append(a)
-    arm, lo, hi, mean = _haar.segment_arms(f_log2, f_weight, np.asarray(units_off, dtype=np.int64), float(threshold))
-    return arm, lo, hi, mean, np.asarray(unit_arm, dtype=np.int64), None
+    units_off = np.asarray(units_off, dtype=np.int64)
+    unit_arm = np.asarray(unit_arm, dtype=np.int64)
+    arm, lo, hi, mean = _haar.segment_arms(f_log2, f_weight, units_off, float(threshold))
+    if variants is None:
+        return arm, lo, hi, mean, unit_arm, None
+    # ---- BAF pass
+    nu = len(unit_arm)
+    n = len(f_log2)
+    baf_signal = np.full(n, 0.5)
+    baf_weight = np.zeros(n)
+    use_baf = np.zeros(nu, dtype=bool)
+    obs_vals, obs_off = [], [0]
+    has_counts = "alt_count" in variants and "depth" in variants
+    for u in range(nu):
+        ulo, uhi = int(units_off[u]), int(units_off[u + 1])
+        sub = subtable(np.arange(ulo, uhi))
+        if has_counts:       # haar.py:135-151 _baf_signal_and_sigma
+            minor, dp = (np.asarray(c, dtype=np.float64) for c in variants.baf_counts_by_ranges(sub))
+            observed = dp > 0
+            sig = np.where(observed, minor / np.maximum(dp, 1.0), 0.5)
+            wts = dp
+        elif "alt_freq" in variants:   # haar.py:173-185 _baf_signal_from_frequencies
+            vals = np.asarray(variants.baf_by_ranges(sub), dtype=np.float64)
+            observed = ~np.isnan(vals)
+            sig = np.where(observed, vals, 0.5)
+            wts = observed.astype(np.float64)
+        else:
+            obs_off.append(obs_off[-1])
+            continue
+        baf_signal[ulo:uhi] = sig
+        baf_weight[ulo:uhi] = wts
+        use_baf[u] = np.count_nonzero(wts) >= 2
+        obs_vals.append(sig[observed])
+        obs_off.append(obs_off[-1] + int(observed.sum()))
+    if use_baf.any():
+        sigma = _haar.level1_sigma(np.concatenate(obs_vals) if obs_vals else np.zeros(0), np.asarray(obs_off))
+        b_arm, b_lo, _b_hi, _b_mean = _haar.segment_arms(baf_signal, np.maximum(baf_weight, _haar.WEIGHT_FLOOR), units_off,
+                                                         float(threshold), sigma_override=sigma)
+        new_lo, new_hi, new_arm = [], [], []
+        for u in range(nu):
+            ulo, uhi = int(units_off[u]), int(units_off[u + 1])
+            bps = lo[arm == u][1:] - ulo                      # results['start'][1:] of the log2 pass
+            if use_baf[u]:
+                bps = _haar.unify_levels(bps, b_lo[b_arm == u][1:] - ulo, 1)
+            edges = np.concatenate([[0], bps, [uhi - ulo]]) + ulo
+            new_lo.append(edges[:-1])
+            new_hi.append(edges[1:])
+            new_arm.append(np.full(len(edges) - 1, u, dtype=np.int32))
+        arm, lo, hi = (np.concatenate(v) if v else np.zeros(0, dtype=np.int64) for v in (new_arm, new_lo, new_hi))
+        mean = _haar.segment_means(f_log2, f_weight, lo, hi)   # SegmentByPeaks(signal, breakpoints, weights)
+    return arm, lo.astype(np.int64), hi.astype(np.int64), mean, unit_arm, None
 
 
 def _transfer_fields(seg_arm, seg_chrom, seg_start, seg_end, seg_log2, probes, arms, data, log2, weight, depth,

@@ -326,6 +326,17 @@ int cnvk_haar_segment_dev(const double* d_log2, const double* d_weight, const in
 int cnvk_haar_segment(const double* log2, const double* weight, const int64_t* arm_offsets, int32_t n_arms,
                       double fdr_q, int64_t capacity, int32_t* seg_arm, int64_t* seg_lo, int64_t* seg_hi,
                       double* seg_mean, int64_t* n_segs);
+/* The depth + BAF breakpoint union of cnvlib/segmentation/haar.py:188-225 (one_chrom_baf) needs three more pieces:
+ * haarSeg with a caller-supplied noise estimate per arm (sigma_override of haar.py:334-339; NaN = use the signal's
+ * own estimate), that estimate for the compacted observed BAF values (haar.py:154-170 _observed_baf_sigma:
+ * 1.4826 * median |HaarConv(values, None, 1)|, floored at 1e-10; arms of fewer than 2 values get the floor), and
+ * SegmentByPeaks' (weighted) means for breakpoints merged on the host (haar.py:405-451).  Host buffers. */
+int cnvk_haar_segment_sigma(const double* signal, const double* weight, const int64_t* arm_offsets, int32_t n_arms,
+                            double fdr_q, const double* sigma_override, int64_t capacity, int32_t* seg_arm,
+                            int64_t* seg_lo, int64_t* seg_hi, double* seg_mean, int64_t* n_segs);
+int cnvk_haar_sigma(const double* signal, const int64_t* arm_offsets, int32_t n_arms, double* sigma);
+int cnvk_haar_segment_means(const double* signal, const double* weight, int64_t n, const int64_t* seg_lo,
+                            const int64_t* seg_hi, int32_t n_segs, double* seg_mean);
 
 /* ---- table I/O (host only) ------------------------------------------------------------------ */
 /* Reader for the tab-separated .cnn/.cnr/.cns tables: skgenome/tabio/tab.py:18-33 read_tab

@@ -539,6 +539,49 @@ def gen_sex(R):
     save("sex", **arrays)
 
 
+def synth_variants(cnr, seed=0xBAF):
+    """Heterozygous SNPs on the bins of `cnr` (about every second bin, depth ~ Poisson(60)); two chromosomes carry a
+    copy-neutral LOH stretch (allele fraction 0.2) that the depth signal does not show."""
+    import pandas as pd
+
+    rng = np.random.default_rng(seed)
+    d = cnr.data
+    pick = rng.random(len(d)) < 0.5
+    chrom = d["chromosome"].to_numpy()[pick]
+    pos = ((d["start"].to_numpy() + d["end"].to_numpy()) // 2)[pick]
+    depth = rng.poisson(60, pick.sum()).astype(np.int64) + 8
+    frac = np.full(pick.sum(), 0.5)
+    chroms = list(dict.fromkeys(chrom.tolist()))
+    for c in chroms[2:4]:
+        idx = np.flatnonzero(chrom == c)
+        frac[idx[len(idx) // 3: 2 * len(idx) // 3]] = 0.2
+    alt = rng.binomial(depth, frac)
+    return pd.DataFrame({"chromosome": chrom, "start": pos, "end": pos + 1, "ref": "A", "alt": "G", "zygosity": 0.5,
+                         "depth": depth, "alt_count": alt, "alt_freq": alt / depth})
+
+
+def gen_haar_baf(R):
+    """do_segmentation(cnr, 'haar', variants=...) of the UNMODIFIED reference (haar.py:188-225 depth + BAF breakpoint
+    union; segmentation/__init__.py:359 per-segment BAF) on test/formats/p2-20_1.cnr with synthetic het SNPs, once
+    with allele counts and once with allele frequencies only."""
+    from cnvlib.vary import VariantArray
+
+    cnr = R.read_cna(os.path.join(R.root, "test", "formats", "p2-20_1.cnr"))
+    vdf = synth_variants(cnr)
+    arrays = {f"var__{c}": (vdf[c].to_numpy().astype(str) if vdf[c].dtype == object or str(vdf[c].dtype) in ("str", "string")
+                            else vdf[c].to_numpy()) for c in vdf.columns}
+    arrays["var__columns"] = np.asarray(list(vdf.columns), dtype=str)
+    cns_counts = R.segmentation.do_segmentation(cnr, "haar", variants=VariantArray(vdf.copy()))
+    arrays.update(table_arrays(cns_counts, "cns_counts"))
+    vfreq = vdf.drop(columns=["alt_count", "depth"])
+    cns_freq = R.segmentation.do_segmentation(cnr, "haar", variants=VariantArray(vfreq.copy()))
+    arrays.update(table_arrays(cns_freq, "cns_freq"))
+    plain = R.segmentation.do_segmentation(cnr, "haar")
+    arrays["n_plain"] = np.asarray(len(plain))
+    print("haar_baf: segments plain", len(plain), "counts", len(cns_counts), "freq", len(cns_freq))
+    save("haar_baf", **arrays)
+
+
 def main():
     logging.basicConfig(level=logging.ERROR)
     os.makedirs(OUT, exist_ok=True)

@@ -34,6 +34,7 @@ def test_routing_predicates():
     assert I._segment_needs_reference((None, "hmm"), {})
     assert not I._segment_needs_reference((None, "cbs"), {"smooth_cbs": True})    # smooth.CNA runs on the GPU
     assert I._segment_needs_reference((None, "cbs"), {"variants": [1]})
+    assert not I._segment_needs_reference((None, "haar"), {"variants": [1]})          # depth + BAF union runs on the GPU
     assert not I._segment_needs_reference((None, "cbs"), {"threshold": 1e-4})
     assert not I._segment_needs_reference((None,), {"method": "haar"})
     assert I._fix_needs_reference((1, 2, 3), {"bias_smoother": "loess"})

@@ -42,3 +42,15 @@ def test_join_genes_matches_the_python_rule():
     end = np.array([1000, 200, 500, 700, 800, 1200])
     got = _join_genes(genes, np.array([0, 0]), np.array([3, 6]), None, mask_end=end, mask_start=np.array([0, 550]))
     assert got == ["A,B,C", "A,D,E,F"]
+
+
+def test_unify_levels_restatement():
+    """UnifyLevels (haar.py:615-663): addon breakpoints within `window` (inclusive) of a base breakpoint are dropped."""
+    from cnvkit_b200.segmentation.haar import unify_levels
+
+    base = np.array([10, 50, 90])
+    addon = np.array([5, 9, 11, 12, 49, 51, 70, 89, 91, 92])
+    assert unify_levels(base, addon, 1).tolist() == [5, 10, 12, 50, 70, 90, 92]
+    assert unify_levels(base, addon, 2).tolist() == [5, 10, 50, 70, 90]
+    assert unify_levels(np.array([], dtype=int), addon, 1).tolist() == addon.tolist()
+    assert unify_levels(base, np.array([], dtype=int), 1).tolist() == base.tolist()
