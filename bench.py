@@ -44,12 +44,14 @@ METRIC = "bins segmented/s (CBS, WGS 1 kb)"
 UNIT = "bins/s"
 ALPHA = 1e-4
 FLOP_PER_ARC = 7  # sub, sub, sub, mul, mul, mul, compare -- weighted BSS, division-free test
-PREP_BYTES_PER_BIN = 56  # read log2, weight (16 B); write xc, y, wn, S, cw (40 B)
-PREP_TRAFFIC = 217.0e6   # ncu dram bytes of the level-1 launches of the prep tile kernels (profiles/)
-PREP_NOTE = ("blocked FP64 prefix scan cut into 2048-point tiles (one CTA each); the tile kernels move 104 B/bin "
-             "(the sums pass re-reads the inputs, the tile-local prefixes make one round trip before the carries "
-             "are added); traffic = ncu dram bytes of the level-1 launches of the three tile kernels "
-             "(profiles/r01d_cbs_kernels_full_summary.md), the rest of the writes stays in L2")
+PREP_BYTES_PER_BIN = 48  # sums pass reads log2, weight (16 B); scan pass reads them again and writes S, cw (32 B)
+PREP_TRAFFIC = 109.9e6   # ncu dram bytes of the level-1 launches (sums 48.0 MB + scan 53.9 + 7.9 MB; profiles/r02f_summary.md)
+PREP_NOTE = ("two tile kernels per level: sums (min/max, double-double totals) and scan (centring, blocked FP64 prefix "
+             "scan, carries by chained look-back, block extrema); they move exactly the algorithmic 48 B/bin (xc, y, wn of "
+             "round 1 are no longer written: the exchangeable terms are materialised only for nodes that enter a "
+             "permutation test); traffic = ncu dram bytes of the level-1 launches (profiles/r02f_summary.md), most of "
+             "the S / cw writes are still in L2 when the capture ends; both kernels are latency-bound (3 CTAs/SM in the "
+             "scan kernel, long-scoreboard stalls), 1.1 TB/s at level 1")
 
 
 def parse_args():
@@ -314,6 +316,24 @@ def exome_leg(args, torch, dev):
     rm_ms = sum(out["kernel_ms_per_sample"].get(k, 0.0) for k in ("radix_sort", "wavelet_build", "window_query"))
     out["rolling_median"] = {"elements": rm_elems, "ms": rm_ms, "achieved_GBps": 16.0 * rm_elems / (rm_ms * 1e-3) / 1e9
                              if rm_ms else None, "note": "16 B/element algorithmic; on-chip selection bound, not HBM"}
+    # fix path: 80 B/bin fused elementwise + 24 B/bin per centre-by-window pass (4 passes per sample),
+    # over the two runs above (cbs + haar => the fix kernels ran twice)
+    fix_ms = out["kernel_ms_per_sample"].get("fix", 0.0) / 2.0
+    n_bins = n_t + n_a
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6540.8))
+    fix_bytes = 80.0 * n_bins + 24.0 * (2 * n_t + 2 * n_a)
+    out["fix_roofline"] = {"kernel": "fix.cu / select.cu / biweight.cu kernels of one sample (class `fix`)", "bound": "hbm",
+                           "achieved": fix_bytes / (fix_ms * 1e-3) / 1e9 if fix_ms else None, "peak": hbm, "unit": "GB/s",
+                           "frac": (fix_bytes / (fix_ms * 1e-3) / 1e9 / hbm) if fix_ms else None, "traffic": None,
+                           "algorithmic": f"80 B/bin x {n_bins} bins + 24 B/bin x 4 centre-by-window passes",
+                           "kernel_ms_per_sample": fix_ms,
+                           "note": "dozens of small launches per sample (medians by radix select, gathers, elementwise "
+                                   "passes over 150 k / 50 k bins): launch-latency-bound, not bandwidth-bound"}
     cores = len(os.sched_getaffinity(0))
     cpu = exome_cpu_baseline(bins, ref, samples[0], cores)
     out["cpu_baseline_reference_python"] = exome_reference_python(bins, ref, samples[0])
@@ -609,16 +629,17 @@ def run_b200(args):
         arc_tflops = (arcs * FLOP_PER_ARC) / (arc_ms * 1e-3) / 1e12 if arc_ms > 0 else 0.0
         roof_scan = {
             "kernel": "cbs_scan_kernel + cbs_band_kernel", "bound": "fp64", "achieved": arc_tflops, "peak": fp64_peak,
-            "unit": "TFLOP/s", "frac": arc_tflops / fp64_peak if fp64_peak else None, "traffic": 49.8e6,
+            "unit": "TFLOP/s", "frac": arc_tflops / fp64_peak if fp64_peak else None, "traffic": 22.4e6,
             "peak_source": "measured in this run: register-only DFMA stream (cnvk_fp64_peak); "
                            "MEASURED_PEAKS.json holds no FP64 figure",
             "algorithmic": f"{FLOP_PER_ARC} FP64 op/arc x {arcs} arcs evaluated per step "
                            f"({stats['obs_subtiles_scanned']} of {stats['obs_subtiles_total']} 256x256 sub-tiles "
                            f"survive the bound test; the rest are narrow-band arcs)",
             "kernel_ms_per_step": arc_ms,
-            "note": "non-fused FP64 ops: 1 flop per issued DP instruction, so frac <= 0.5 of the DFMA peak; "
-                    "with --no-prune (every arc evaluated) the same kernel reaches 0.46; traffic = ncu dram bytes of "
-                    "the level-1 launches (one read of S and cw) -- DRAM is idle, the pipe is the bound",
+            "note": "non-fused FP64 ops: 1 flop per issued DP instruction, so frac <= 0.5 of the DFMA peak; ncu "
+                    "(profiles/r02f_summary.md): FP64 pipe 38-44 % active in cbs_scan, 27-39 % in cbs_band, SM throughput "
+                    "58 % in the level-2 band launch; traffic = ncu dram bytes of the level-1 band + scan launches "
+                    "(20.7 + 1.7 MB: the CTA-level bound skips 57 % of the strips) -- DRAM is idle, the pipe is the bound",
         }
         prep_ms = per_step.get("cbs_prep", 0.0)
         prep_bytes = PREP_BYTES_PER_BIN * stats["prep_bins"]
@@ -631,7 +652,22 @@ def run_b200(args):
             "kernel_ms_per_step": prep_ms,
             "note": PREP_NOTE,
         }
-        roofline = dict(roof_prep if dominant == "cbs_prep" else roof_scan)
+        perm_ms = per_step.get("cbs_perm_hybrid", 0.0) + per_step.get("cbs_perm_exact", 0.0)
+        perm_tflops = (stats["perm_arcs"] * 3) / (perm_ms * 1e-3) / 1e12 if perm_ms > 0 else 0.0
+        roof_perm = {
+            "kernel": "cbs_perm_hybrid_kernel + cbs_perm_exact_kernel (cooperative, persistent)", "bound": "fp64",
+            "achieved": perm_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": perm_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+            "peak_source": roof_scan["peak_source"],
+            "algorithmic": f"3 FP64 op/arc (add, multiply, compare) x {stats['perm_arcs']} arcs of "
+                           f"{stats['perms_run']} permutations over {stats['perm_nodes']} nodes",
+            "kernel_ms_per_step": perm_ms,
+            "note": "the hot loop issues ONE FP64 add per arc (the multiply and compare are replaced by an integer "
+                    "compare of the high word against a conservative limit), so the FP64 pipe is not the bound: the "
+                    "permutation + gather prologue (~60-130 integer ops per permuted element) and, for this sample, the "
+                    "barriers of 5 chunks are; the `cliff` object holds the large-node figure (1.6 T arcs/s)",
+        }
+        roofline = dict({"cbs_prep": roof_prep, "cbs_perm_hybrid": roof_perm, "cbs_perm_exact": roof_perm}.get(dominant, roof_scan))
         roofline["dominant_class_by_time"] = dominant
         # CPU baseline on a bounded sample (rank 0, N = 1 only)
         cpu = None
@@ -675,7 +711,7 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "gpu_launches_per_step": int(launches) // max(args.steps, 1),
             "roofline": roofline,
-            "rooflines": [roof_prep, roof_scan],
+            "rooflines": [roof_prep, roof_scan, roof_perm],
             "cpu_baseline": cpu,
             "clocks": clocks,
             "kernel_ms_per_step": per_step,
