@@ -49,6 +49,43 @@
 namespace cnvk {
 namespace cg = cooperative_groups;
 
+// Programmatic dependent launch: the kernels of one level form a chain on one stream.  Each kernel first waits until its
+// predecessor has completed and flushed (griddepcontrol.wait; no global memory is touched before it) and only then lets
+// its successor be scheduled (launch_dependents), so the successor's launch latency and CTA ramp-up overlap this
+// kernel's body while at most one dependent grid is ever parked behind a running one.  (Triggering BEFORE the wait lets
+// a whole chain of grids stack up behind the first running kernel; with that order the bound -> scan pair lost queue
+// entries on the B200 -- profiles/r02q_pdl_bisect.md.)  Both instructions are no-ops for a kernel launched without the
+// attribute.  CNVK_PDL is a bit mask over the chain (0 = every kernel launched the plain way).
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+static long long g_pdl = -1;
+// CNVK_PDL: bit mask over the kernels of the chain (bit = position in launch order below), default all but the band
+// kernel -- its strips are staged by TMA bulk copies (async proxy) and griddepcontrol.wait orders the predecessor's
+// writes for the generic proxy only, so that kernel keeps a full stream dependency.
+enum { K_MAPS, K_SUMS, K_PSCAN, K_SEED, K_BAND, K_BOUND, K_SCAN, K_STAT, K_TERMS, K_DECIDE, K_FLIST, K_FPART, K_FPREP,
+       K_FPERM, K_FRONTIER, K_MEANS };
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(int id, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                       Args&&... args) {
+    if (g_pdl < 0) {
+        const char* e = getenv("CNVK_PDL");
+        g_pdl = e ? strtoll(e, nullptr, 0) : (0xffff & ~(1 << K_BAND));
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = ((g_pdl >> id) & 1) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static const int CBS_BLK = 256;           // points per bound block / j-block
 static const int CBS_IW = 4;              // arc starts per thread
 static const int CBS_IBLK = CBS_BLK * CBS_IW;
@@ -220,6 +257,7 @@ struct TileScan {      // per tile, written by the scan kernel
 __global__ void __launch_bounds__(128)
 cbs_maps_kernel(const Node* __restrict__ nodes, int nnodes, int* __restrict__ ptile_node, int* __restrict__ blk_node,
                 int* __restrict__ iblk_node) {
+    pdl_enter();
     const int a = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (a >= nnodes) return;
     const Node nd = nodes[a];
@@ -233,6 +271,7 @@ cbs_maps_kernel(const Node* __restrict__ nodes, int nnodes, int* __restrict__ pt
 __global__ void __launch_bounds__(PREP_THREADS)
 cbs_prep_sums_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_node, const double* __restrict__ x,
                      const double* __restrict__ w, TileSums* __restrict__ part) {
+    pdl_enter();
     __shared__ double s_a[32], s_b[32];
     __shared__ int s_last;
     const int a = ptile_node[blockIdx.x];
@@ -382,6 +421,7 @@ cbs_prep_scan_kernel(Node* __restrict__ nodes, const int* __restrict__ ptile_nod
                      double* __restrict__ cw, double* __restrict__ blk_min, double* __restrict__ blk_max,
                      int* __restrict__ blk_imin, int* __restrict__ blk_imax, double* __restrict__ blk_cmin,
                      double* __restrict__ blk_cmax, double* __restrict__ blk_wmin, int al0, int hk, int nmin, int epoch) {
+    pdl_enter();
     extern __shared__ __align__(16) double s_dyn[];
     __shared__ double s_a[32], s_b[32];
     __shared__ double s_wtot[2][PREP_THREADS / 32];
@@ -735,6 +775,7 @@ cbs_seed_kernel(Node* __restrict__ nodes, const int* __restrict__ iblk_node, See
                 const double* __restrict__ blk_min, const double* __restrict__ blk_max,
                 const int* __restrict__ blk_imin, const int* __restrict__ blk_imax,
                 const double* __restrict__ blk_cmin, const double* __restrict__ blk_cmax, int al0) {
+    pdl_enter();
     __shared__ double s_q[8];
     __shared__ int s_i[8], s_j[8];
     __shared__ int s_last;
@@ -863,6 +904,7 @@ cbs_band_kernel(Node* __restrict__ nodes, const int* __restrict__ iblk_node,
                 const double* __restrict__ S, const double* __restrict__ cw,
                 const double* __restrict__ blk_min, const double* __restrict__ blk_max,
                 const double* __restrict__ blk_wmin, int al0, unsigned long long* __restrict__ stats) {
+    pdl_enter();
     __shared__ __align__(16) double sS[BAND_PTS + 4], sC[BAND_PTS + 4];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ double s_mn[BAND_NSUB], s_mx[BAND_NSUB];
@@ -1011,6 +1053,7 @@ cbs_bound_kernel(const Node* __restrict__ nodes, const int* __restrict__ iblk_no
                  const double* __restrict__ cw, const double* __restrict__ blk_min,
                  const double* __restrict__ blk_max, TileRef* __restrict__ queue, int* __restrict__ qcount,
                  unsigned long long* __restrict__ stats) {
+    pdl_enter();
     __shared__ int s_warp_cnt[8];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1066,6 +1109,7 @@ cbs_scan_kernel(Node* __restrict__ nodes, const TileRef* __restrict__ queue, con
                 int* __restrict__ pop_counter, const double* __restrict__ S, const double* __restrict__ cw,
                 const double* __restrict__ blk_min, const double* __restrict__ blk_max, int al0,
                 unsigned long long* __restrict__ stats) {
+    pdl_enter();
     // work unit = ONE 256 x 256 sub-tile (start block r of a queued 1024 x 256 tile): 4 units per queue entry, so
     // that the few hundred surviving tiles of a level spread evenly over the SMs' FP64 pipes
     __shared__ double2 sj[CBS_BLK];
@@ -1157,6 +1201,7 @@ __device__ __forceinline__ double t2_of(double bss, double tss, int n) {
 __global__ void __launch_bounds__(128)
 cbs_stat_kernel(Node* __restrict__ nodes, int nnodes, double alpha, int nperm, int nmin, int flags, int ngrid,
                 int* __restrict__ need_list, Ctl* __restrict__ ctl) {
+    pdl_enter();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int idx = blockIdx.x * 4 + warp;
     if (idx >= nnodes) return;
@@ -1221,6 +1266,7 @@ cbs_stat_kernel(Node* __restrict__ nodes, int nnodes, double alpha, int nperm, i
 __global__ void __launch_bounds__(128)
 cbs_tailp_terms_kernel(const Node* __restrict__ nodes, const int* __restrict__ need_list, const Ctl* __restrict__ ctl,
                        double* __restrict__ terms, int ngrid, double tol) {
+    pdl_enter();
     __shared__ double s_part[4];
     __shared__ double s_sum;
     const int n_need = ctl->n_need;
@@ -1298,6 +1344,7 @@ __global__ void __launch_bounds__(1024)
 cbs_decide_kernel(Node* __restrict__ nodes, int nnodes, const double* __restrict__ terms, double alpha, int nperm,
                   int ngrid, int diag, int* __restrict__ hyb_list, int* __restrict__ exact_list, Ctl* __restrict__ ctl,
                   unsigned long long* __restrict__ dmin_bits, int* __restrict__ act, int* __restrict__ act_toff) {
+    pdl_enter();
     __shared__ int s_warp[32];
     __shared__ int s_nh, s_ne;
     if (threadIdx.x == 0) { s_nh = 0; s_ne = 0; }
@@ -1874,6 +1921,7 @@ static const int FLANK_SPLIT = 16;
 __global__ void __launch_bounds__(1024)
 cbs_flank_list_kernel(Node* __restrict__ nodes, int nnodes, FlankTest* __restrict__ tests, int* __restrict__ tmp,
                       Ctl* __restrict__ ctl) {
+    pdl_enter();
     __shared__ int s_warp[32];
     __shared__ int s_n;
     if (threadIdx.x == 0) s_n = 0;
@@ -1910,6 +1958,7 @@ cbs_flank_list_kernel(Node* __restrict__ nodes, int nnodes, FlankTest* __restric
 __global__ void __launch_bounds__(256)
 cbs_flank_part_kernel(const Node* __restrict__ nodes, const FlankTest* __restrict__ tests, const Ctl* __restrict__ ctl,
                       const double* __restrict__ x, const double* __restrict__ w, double* __restrict__ part) {
+    pdl_enter();
     __shared__ double s_part[5][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = ctl->n_flank * FLANK_SPLIT;
@@ -1943,6 +1992,7 @@ cbs_flank_part_kernel(const Node* __restrict__ nodes, const FlankTest* __restric
 
 __global__ void cbs_flank_prep_kernel(FlankTest* __restrict__ tests, Ctl* __restrict__ ctl, const double* __restrict__ part,
                                       int* __restrict__ fperm_list, int force_perm) {
+    pdl_enter();
     const int ntests = ctl->n_flank;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ntests; idx += gridDim.x * blockDim.x) {
         FlankTest* o = &tests[idx];
@@ -1978,6 +2028,7 @@ __global__ void __launch_bounds__(128)
 cbs_flank_perm_kernel(const Node* __restrict__ nodes, FlankTest* __restrict__ tests, const int* __restrict__ fperm_list,
                       const Ctl* __restrict__ ctl, int nperm, const double* __restrict__ x,
                       const double* __restrict__ w_sqrt, u64 seed) {
+    pdl_enter();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nlist = ctl->n_fperm;
     const int groups = (nperm + 3) / 4;
@@ -2049,6 +2100,7 @@ __global__ void __launch_bounds__(1024)
 cbs_frontier_kernel(const Node* __restrict__ nodes, int nnodes, const FlankTest* __restrict__ tests, double alpha,
                     int nperm, int min_width, Node* __restrict__ next, int cap_nodes, LevelOut* __restrict__ out,
                     int* __restrict__ extra_lo, int* __restrict__ extra_hi, int cap_extra) {
+    pdl_enter();
     __shared__ int s_warp[32];
     __shared__ int s_child, s_seg, s_pt, s_bk, s_ib;
     __shared__ long long s_qt, s_bins;
@@ -2152,6 +2204,7 @@ cbs_frontier_kernel(const Node* __restrict__ nodes, int nnodes, const FlankTest*
 __global__ void __launch_bounds__(1024)
 seg_mean_kernel(const double* __restrict__ x, const double* __restrict__ w, LevelOut* __restrict__ out,
                 const int* __restrict__ extra_lo, const int* __restrict__ extra_hi, double* __restrict__ extra_mean) {
+    pdl_enter();
     __shared__ double s_a[32], s_b[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nseg = out->ctl.overflow ? 0 : out->ctl.nseg_new;
@@ -2279,6 +2332,17 @@ static thread_local PinnedArena g_pinned;
     } while (0)
 
 // stream-ordered device buffer that grows (contents are not preserved)
+// CNVK_GROW_FILL=<byte>: fill every fresh scratch allocation with that byte (debug aid: a kernel that reads scratch it
+// has not written shows up as a changed table)
+static int grow_fill() {
+    static int v = -2;
+    if (v == -2) {
+        const char* e = getenv("CNVK_GROW_FILL");
+        v = e ? (int)(strtol(e, nullptr, 0) & 0xff) : -1;
+    }
+    return v;
+}
+
 template <typename T>
 struct Grow {
     T* p = nullptr;
@@ -2295,6 +2359,7 @@ struct Grow {
         cudaError_t e = cudaMallocAsync((void**)&p, cap * sizeof(T), s);
         if (e != cudaSuccess) { cap = 0; return e; }
         if (zero) e = cudaMemsetAsync(p, 0, cap * sizeof(T), s);
+        else if (grow_fill() >= 0) e = cudaMemsetAsync(p, grow_fill(), cap * sizeof(T), s);
         return e;
     }
 };
@@ -2404,12 +2469,12 @@ struct CbsRun {
         cap_nodes = std::max(cap_nodes, std::max(2 * nn + 64, (int)std::min<size_t>(nxt->cap, 0x7fffffff)));
         CNVK_CHECK(nxt->ensure((size_t)cap_nodes, stream));
         cap_nodes = (int)std::min<size_t>(nxt->cap, 0x7fffffff);
-        cbs_frontier_kernel<<<1, 1024, 0, stream>>>(cur->p, nn, tests.p, P.alpha, P.nperm, P.min_width, nxt->p, cap_nodes,
-                                                    d_out, extra_lo.p, extra_hi.p, (int)extra_lo.cap);
+        CNVK_CHECK(launch_chain(K_FRONTIER, cbs_frontier_kernel, 1, 1024, 0, stream, cur->p, nn, tests.p, P.alpha, P.nperm, P.min_width, nxt->p, cap_nodes,
+                                                    d_out, extra_lo.p, extra_hi.p, (int)extra_lo.cap));
         CNVK_LAUNCH_CHECK();
         {
             ProfScope ps(PC_CBS_MEANS, stream);
-            seg_mean_kernel<<<sh->sm_count, 1024, 0, stream>>>(sh->d_x, sh->d_w, d_out, extra_lo.p, extra_hi.p, extra_mean.p);
+            CNVK_CHECK(launch_chain(K_MEANS, seg_mean_kernel, sh->sm_count, 1024, 0, stream, sh->d_x, sh->d_w, d_out, extra_lo.p, extra_hi.p, extra_mean.p));
             CNVK_LAUNCH_CHECK();
         }
         CNVK_CHECK(cudaMemcpyAsync(h_out, d_out, sizeof(LevelOut), cudaMemcpyDeviceToHost, stream));
@@ -2461,52 +2526,52 @@ struct CbsRun {
         // lists, queue and next-level fields of the control block (stats are kept)
         CNVK_CHECK(cudaMemsetAsync(d_ctl, 0, offsetof(Ctl, stats), stream));
 
-        cbs_maps_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, nn, ptile_node.p, blk_node.p, iblk_node.p);
+        CNVK_CHECK(launch_chain(K_MAPS, cbs_maps_kernel, div_up(nn, 4), 128, 0, stream, d_nodes, nn, ptile_node.p, blk_node.p, iblk_node.p));
         CNVK_LAUNCH_CHECK();
         {
             ProfScope ps(PC_CBS_PREP, stream);
-            cbs_prep_sums_kernel<<<(int)ptiles, PREP_THREADS, 0, stream>>>(d_nodes, ptile_node.p, d_x, d_w, part1.p);
+            CNVK_CHECK(launch_chain(K_SUMS, cbs_prep_sums_kernel, (int)ptiles, PREP_THREADS, 0, stream, d_nodes, ptile_node.p, d_x, d_w, part1.p));
             CNVK_LAUNCH_CHECK();
-            cbs_prep_scan_kernel<<<(int)ptiles, PREP_THREADS, PREP_SMEM, stream>>>(
+            CNVK_CHECK(launch_chain(K_PSCAN, cbs_prep_scan_kernel, (int)ptiles, PREP_THREADS, PREP_SMEM, stream, 
                 d_nodes, ptile_node.p, d_x, d_w, part3.p, d_S, d_cw, bmin.p, bmax.p, bimin.p, bimax.p, bcmin.p, bcmax.p,
-                bwmin.p, P.min_width, hk, P.nmin, epoch);
+                bwmin.p, P.min_width, hk, P.nmin, epoch));
             CNVK_LAUNCH_CHECK();
         }
         if (P.prune & 1) {
             ProfScope ps(PC_CBS_SEED, stream);
-            cbs_seed_kernel<<<(int)iblks, 256, 0, stream>>>(d_nodes, iblk_node.p, seedres.p, bmin.p, bmax.p, bimin.p, bimax.p,
-                                                            bcmin.p, bcmax.p, P.min_width);
+            CNVK_CHECK(launch_chain(K_SEED, cbs_seed_kernel, (int)iblks, 256, 0, stream, d_nodes, iblk_node.p, seedres.p, bmin.p, bmax.p, bimin.p, bimax.p,
+                                                            bcmin.p, bcmax.p, P.min_width));
             CNVK_LAUNCH_CHECK();
         }
         {
             ProfScope ps(PC_CBS_BAND, stream);
-            if (P.prune & 1) cbs_band_kernel<true><<<(int)iblks, 256, 0, stream>>>(d_nodes, iblk_node.p, d_S, d_cw, bmin.p, bmax.p, bwmin.p, P.min_width, d_stats);
-            else cbs_band_kernel<false><<<(int)iblks, 256, 0, stream>>>(d_nodes, iblk_node.p, d_S, d_cw, bmin.p, bmax.p, bwmin.p, P.min_width, d_stats);
+            if (P.prune & 1) CNVK_CHECK(launch_chain(K_BAND, cbs_band_kernel<true>, (int)iblks, 256, 0, stream, d_nodes, iblk_node.p, d_S, d_cw, bmin.p, bmax.p, bwmin.p, P.min_width, d_stats));
+            else CNVK_CHECK(launch_chain(K_BAND, cbs_band_kernel<false>, (int)iblks, 256, 0, stream, d_nodes, iblk_node.p, d_S, d_cw, bmin.p, bmax.p, bwmin.p, P.min_width, d_stats));
             CNVK_LAUNCH_CHECK();
         }
         {
             ProfScope ps(PC_CBS_BOUND, stream);
-            if (P.prune & 1) cbs_bound_kernel<true><<<(int)iblks, 256, 0, stream>>>(d_nodes, iblk_node.p, d_cw, bmin.p, bmax.p, queue.p, &d_ctl->qcount, d_stats);
-            else cbs_bound_kernel<false><<<(int)iblks, 256, 0, stream>>>(d_nodes, iblk_node.p, d_cw, bmin.p, bmax.p, queue.p, &d_ctl->qcount, d_stats);
+            if (P.prune & 1) CNVK_CHECK(launch_chain(K_BOUND, cbs_bound_kernel<true>, (int)iblks, 256, 0, stream, d_nodes, iblk_node.p, d_cw, bmin.p, bmax.p, queue.p, &d_ctl->qcount, d_stats));
+            else CNVK_CHECK(launch_chain(K_BOUND, cbs_bound_kernel<false>, (int)iblks, 256, 0, stream, d_nodes, iblk_node.p, d_cw, bmin.p, bmax.p, queue.p, &d_ctl->qcount, d_stats));
             CNVK_LAUNCH_CHECK();
         }
         {
             ProfScope ps(PC_CBS_SCAN, stream);
             const int grid = (int)std::min<long long>((long long)sm_count * 4, std::max<long long>(4 * qtiles, 1));
-            if (P.prune & 1) cbs_scan_kernel<true><<<grid, 256, 0, stream>>>(d_nodes, queue.p, &d_ctl->qcount, &d_ctl->qpop, d_S, d_cw, bmin.p, bmax.p, P.min_width, d_stats);
-            else cbs_scan_kernel<false><<<grid, 256, 0, stream>>>(d_nodes, queue.p, &d_ctl->qcount, &d_ctl->qpop, d_S, d_cw, bmin.p, bmax.p, P.min_width, d_stats);
+            if (P.prune & 1) CNVK_CHECK(launch_chain(K_SCAN, cbs_scan_kernel<true>, grid, 256, 0, stream, d_nodes, queue.p, &d_ctl->qcount, &d_ctl->qpop, d_S, d_cw, bmin.p, bmax.p, P.min_width, d_stats));
+            else CNVK_CHECK(launch_chain(K_SCAN, cbs_scan_kernel<false>, grid, 256, 0, stream, d_nodes, queue.p, &d_ctl->qcount, &d_ctl->qpop, d_S, d_cw, bmin.p, bmax.p, P.min_width, d_stats));
             CNVK_LAUNCH_CHECK();
         }
         {
             ProfScope ps(PC_CBS_DECIDE, stream);
             const int flags = (P.hybrid ? 1 : 0) | (diag ? 2 : 0) | ((P.prune & 2) ? 4 : 0);
-            cbs_stat_kernel<<<div_up(nn, 4), 128, 0, stream>>>(d_nodes, nn, P.alpha, P.nperm, P.nmin, flags, ngrid, need_list.p, d_ctl);
+            CNVK_CHECK(launch_chain(K_STAT, cbs_stat_kernel, div_up(nn, 4), 128, 0, stream, d_nodes, nn, P.alpha, P.nperm, P.nmin, flags, ngrid, need_list.p, d_ctl));
             CNVK_LAUNCH_CHECK();
             if (P.hybrid) {
-                cbs_tailp_terms_kernel<<<dim3(ngrid, std::min(nn, 64)), 128, 0, stream>>>(d_nodes, need_list.p, d_ctl, terms.p, ngrid, 1e-6);
+                CNVK_CHECK(launch_chain(K_TERMS, cbs_tailp_terms_kernel, dim3(ngrid, std::min(nn, 64)), 128, 0, stream, d_nodes, need_list.p, d_ctl, terms.p, ngrid, 1e-6));
                 CNVK_LAUNCH_CHECK();
             }
-            cbs_decide_kernel<<<1, 1024, 0, stream>>>(d_nodes, nn, terms.p, P.alpha, P.nperm, ngrid, diag ? 1 : 0, hyb_list.p, exact_list.p, d_ctl, dmin_bits.p, act.p, act_toff.p);
+            CNVK_CHECK(launch_chain(K_DECIDE, cbs_decide_kernel, 1, 1024, 0, stream, d_nodes, nn, terms.p, P.alpha, P.nperm, ngrid, diag ? 1 : 0, hyb_list.p, exact_list.p, d_ctl, dmin_bits.p, act.p, act_toff.p));
             CNVK_LAUNCH_CHECK();
         }
         // ---- permutation reference distributions (cooperative persistent kernels; no-ops when their list is empty)
@@ -2540,13 +2605,13 @@ struct CbsRun {
         // ---- ternary-split confirmation
         {
             ProfScope fscope(PC_CBS_FLANK, stream);
-            cbs_flank_list_kernel<<<1, 1024, 0, stream>>>(d_nodes, nn, tests.p, tmp_list.p, d_ctl);
+            CNVK_CHECK(launch_chain(K_FLIST, cbs_flank_list_kernel, 1, 1024, 0, stream, d_nodes, nn, tests.p, tmp_list.p, d_ctl));
             CNVK_LAUNCH_CHECK();
-            cbs_flank_part_kernel<<<sm_count * 4, 256, 0, stream>>>(d_nodes, tests.p, d_ctl, d_x, d_w, fpart.p);
+            CNVK_CHECK(launch_chain(K_FPART, cbs_flank_part_kernel, sm_count * 4, 256, 0, stream, d_nodes, tests.p, d_ctl, d_x, d_w, fpart.p));
             CNVK_LAUNCH_CHECK();
-            cbs_flank_prep_kernel<<<std::min(div_up(2 * nn, 128), sm_count), 128, 0, stream>>>(tests.p, d_ctl, fpart.p, fperm_list.p, diag ? 1 : 0);
+            CNVK_CHECK(launch_chain(K_FPREP, cbs_flank_prep_kernel, std::min(div_up(2 * nn, 128), sm_count), 128, 0, stream, tests.p, d_ctl, fpart.p, fperm_list.p, diag ? 1 : 0));
             CNVK_LAUNCH_CHECK();
-            cbs_flank_perm_kernel<<<sm_count * 8, 128, 0, stream>>>(d_nodes, tests.p, fperm_list.p, d_ctl, P.nperm, d_x, sh->d_rw, P.seed);
+            CNVK_CHECK(launch_chain(K_FPERM, cbs_flank_perm_kernel, sm_count * 8, 128, 0, stream, d_nodes, tests.p, fperm_list.p, d_ctl, P.nperm, d_x, sh->d_rw, P.seed));
             CNVK_LAUNCH_CHECK();
         }
         if (diag) return 0;
