@@ -82,6 +82,10 @@ SIGNATURES = {
     "cnvk_cbs_getbdry": (c_int, [c_double, c_int32, c_int32, c_void_p]),
     "cnvk_cbs_input_filter_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cnvk_panel_prepare_dev": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_double, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p]),
+    "cnvk_panel_transfer_dev": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
     "cnvk_coverage_finalize_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
     "cnvk_coverage_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]),
     "cnvk_smooth_cna_dev": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_double, c_double, c_double, c_void_p,
@@ -158,6 +162,47 @@ class BootParams(ctypes.Structure):
         ("pcg_inc", c_uint64 * 2),
         ("noise_seed", c_uint64),
     ]
+
+
+class PanelGroup(ctypes.Structure):
+    """cnvk_panel_group (include/cnvkit_b200.h)."""
+
+    _fields_ = [
+        ("n0", c_int64),
+        ("n", c_int64),
+        ("d_keep_idx", c_void_p),
+        ("d_auto", c_void_p),
+        ("d_chrom_off", c_void_p),
+        ("nchrom", c_int32),
+        ("skip_low", c_int32),
+        ("d_order", c_void_p * 3),
+        ("wing", c_int64),
+    ]
+
+
+class PanelDesc(ctypes.Structure):
+    """cnvk_panel (include/cnvkit_b200.h)."""
+
+    _fields_ = [
+        ("grp", PanelGroup * 2),
+        ("n", c_int64),
+        ("d_order", c_void_p),
+        ("d_ref_log2", c_void_p),
+        ("d_ref_spread", c_void_p),
+        ("d_start", c_void_p),
+        ("d_end", c_void_p),
+        ("d_chrom_id", c_void_p),
+        ("d_is_anti", c_void_p),
+        ("d_auto", c_void_p),
+        ("d_chrom_off", c_void_p),
+        ("nchrom", c_int32),
+        ("n_arms", c_int32),
+        ("d_arm_id", c_void_p),
+        ("arm_off", c_void_p),
+    ]
+
+
+PANEL_NAN_INPUT, PANEL_LOW_COVERAGE, PANEL_NONFINITE, PANEL_QUANTISER_RANGE = 1, 2, 4, 8
 
 
 class CnvkError(RuntimeError):

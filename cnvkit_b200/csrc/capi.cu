@@ -542,6 +542,32 @@ int cnvk_cbs_node_diag(const double* log2, const double* weight, const int64_t* 
     return hc.finish();
 }
 
+int cnvk_panel_prepare_dev(const cnvk_panel* panel, int32_t n_samples, const double* const* d_in, double* const* d_out,
+                           int32_t want_cbs, double skip_outliers, double* const* d_cbs, int64_t* const* d_src,
+                           int64_t* unit_offsets, uint32_t* status, void* stream) {
+    RC(ensure_init());
+    if (!panel || !d_in || !d_out || !status || (want_cbs && (!d_cbs || !d_src || !unit_offsets)))
+    {
+        set_last_error("cnvk_panel_prepare_dev: null argument");
+        return -2;
+    }
+    return panel_prepare(panel, n_samples, d_in, d_out, want_cbs, skip_outliers, d_cbs, (long long* const*)d_src,
+                         (long long*)unit_offsets, status, (cudaStream_t)stream);
+}
+
+int cnvk_panel_transfer_dev(const cnvk_panel* panel, int32_t n_samples, int32_t n_seg, const int64_t* seg,
+                            const int64_t* const* d_src, const double* const* d_depth, const double* const* d_weight,
+                            int64_t* bounds, double* sums, void* stream) {
+    RC(ensure_init());
+    if (!panel || (n_seg > 0 && (!seg || !d_src || !d_depth || !d_weight || !bounds || !sums)))
+    {
+        set_last_error("cnvk_panel_transfer_dev: null argument");
+        return -2;
+    }
+    return panel_transfer(panel, n_samples, n_seg, (const long long*)seg, (const long long* const*)d_src, d_depth, d_weight,
+                          (long long*)bounds, sums, (cudaStream_t)stream);
+}
+
 int cnvk_outlier_mask_dev(const double* d_log2, const int64_t* arm_offsets, int32_t n_arms, double q, double factor,
                           uint8_t* d_mask, void* stream) {
     RC(ensure_init());

@@ -316,6 +316,32 @@ int fix_group_ordered(double* d_log2, const double* d_depth, const u8* d_auto_se
     return 0;
 }
 
+// The same without the host round trip of the "mostly empty" guard: the count of bins above the coverage floor goes to
+// *d_cnt (device) and the corrections run regardless; the caller reads the count later and, for the pathological sample
+// whose count is <= n / 2, discards the result (cnvk_panel_prepare_dev).
+int fix_group_ordered_enqueue(double* d_log2, const double* d_depth, const u8* d_auto_sel, long long n,
+                              const long long* d_chrom_off, int nchrom, const u32* const* d_orders, int n_orders,
+                              int skip_low, int do_center, long long wing, unsigned long long* d_cnt,
+                              cudaStream_t stream) {
+    if (n <= 0) return 0;
+    int rc;
+    if (do_center) {
+        rc = center_all(d_log2, d_depth, d_auto_sel, n, d_chrom_off, nchrom, skip_low, nullptr, stream);
+        if (rc) return rc;
+    }
+    {
+        ProfScope ps(PC_FIX, stream);
+        count_gt_kernel<<<std::min(div_up(n, 256), 1184), 256, 0, stream>>>(d_log2, n, NULL_LOG2_COVERAGE - MIN_REF_COVERAGE, d_cnt);
+        CNVK_LAUNCH_CHECK();
+    }
+    for (int k = 0; k < n_orders; ++k) {
+        if (!d_orders[k]) continue;
+        rc = center_by_order(d_log2, d_orders[k], n, wing, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 int fix_group(double* d_log2, const double* d_depth, const u8* d_auto_sel, long long n,
               const long long* d_chrom_off, int nchrom, const int* d_chrom_id, const long long* d_start,
               const long long* d_end, const double* d_gc, const double* d_rmask, const double* d_edge_in,

@@ -33,6 +33,10 @@ int center_by_order(double* d_log2, const u32* d_src_of, long long n, long long 
 int fix_group_ordered(double* d_log2, const double* d_depth, const unsigned char* d_auto_sel, long long n,
                       const long long* d_chrom_off, int nchrom, const u32* const* d_orders, int n_orders, int skip_low,
                       int do_center, long long wing, int* h_skipped, cudaStream_t stream);
+int fix_group_ordered_enqueue(double* d_log2, const double* d_depth, const unsigned char* d_auto_sel, long long n,
+                              const long long* d_chrom_off, int nchrom, const u32* const* d_orders, int n_orders,
+                              int skip_low, int do_center, long long wing, unsigned long long* d_cnt,
+                              cudaStream_t stream);
 int edge_bias(const long long* d_start, const long long* d_end, const int* d_chrom_id, long long n, long long margin,
               double* d_out, cudaStream_t stream);
 int fix_group(double* d_log2, const double* d_depth, const unsigned char* d_auto_sel, long long n,
@@ -49,11 +53,26 @@ int fix_finish(double* d_log2, const double* d_depth, const double* d_ref_log2, 
 // segutil.cu
 int outlier_mask(const double* d_x, const long long* h_off, int n_arms, double q, double factor,
                  unsigned char* d_mask, cudaStream_t stream);
+int cbs_input_filter_enqueue(const double* d_log2, const double* d_weight, const unsigned char* d_outlier,
+                             const long long* d_arm_id, const long long* d_arm_off, int n_arms, long long n,
+                             double* d_x_out, double* d_w_out, long long* d_src_out, long long* d_units_out,
+                             unsigned int* d_flags_out, cudaStream_t stream);
 int round_sig(const double* d_x, long long n, int digits, double* d_out, unsigned long long* h_unhandled,
               cudaStream_t stream);
 int segment_bin_sums(const double* d_depth, const double* d_weight, const long long* d_lo, const long long* d_hi,
                      const long long* d_bin_end, const long long* d_seg_start, int nseg, double* d_seg_weight,
                      double* d_seg_depth, cudaStream_t stream);
+
+// panel.cu (cnvk_panel is declared in include/cnvkit_b200.h)
+}  // namespace cnvk
+struct cnvk_panel;
+namespace cnvk {
+int panel_prepare(const cnvk_panel* P, int ns, const double* const* in, double* const* out, int want_cbs,
+                  double skip_outliers, double* const* cbs_out, long long* const* src_out, long long* h_units,
+                  unsigned int* h_status, cudaStream_t stream);
+int panel_transfer(const cnvk_panel* P, int ns, int nseg, const long long* h_seg, const long long* const* src_rows,
+                   const double* const* depth_cols, const double* const* weight_cols, long long* h_bounds,
+                   double* h_sums, cudaStream_t stream);
 
 // bootstrap.cu
 int bootstrap_ci(const double* d_values, const double* d_weights, const long long* h_lo, const long long* h_hi,

@@ -20,6 +20,7 @@ typedef unsigned char u8;
 static const int OL_WING = 25;      // _width2wing(50, x) for len(x) > 50
 static const int OL_PASSES = 7;     // total_width 51 // window_width 7
 static const int OL_TILE = 512;
+static const int OL_TOP = 8;        // upper-tail quantiles needing at most this many of the largest values take the register path
 static const int OL_HALO = 3 * OL_PASSES;   // 21 points each side feed the 7 passes
 
 // scipy.signal.savgol_coeffs(7, 3) as produced by this image's scipy/LAPACK, in the order
@@ -79,6 +80,27 @@ savgol_dists_kernel(const double* __restrict__ x, const long long* __restrict__ 
     }
 }
 
+// the M-th largest (*vlow) and the (M-1)-th largest (*vhigh) of v[0, W)
+template <int M>
+__device__ __forceinline__ void top_m(const double* v_, int W, double* vlow, double* vhigh) {
+    double top[M];
+#pragma unroll
+    for (int r = 0; r < M; ++r) top[r] = -INFINITY;
+    for (int j = 0; j < W; ++j) {
+        double v = v_[j];
+        if (v > top[M - 1]) {
+#pragma unroll
+            for (int r = 0; r < M; ++r) {
+                const double hi_ = fmax(top[r], v), lo_ = fmin(top[r], v);
+                top[r] = hi_;
+                v = lo_;
+            }
+        }
+    }
+    *vlow = top[M - 1];
+    *vhigh = (M >= 2) ? top[M >= 2 ? M - 2 : 0] : 0.0;
+}
+
 // mask[i] = dists[i] > quantile_q(window 2*wing+1 of mirror-padded dists) * factor
 __global__ void __launch_bounds__(256)
 quantile_mask_kernel(const double* __restrict__ dists, const long long* __restrict__ off,
@@ -98,17 +120,33 @@ quantile_mask_kernel(const double* __restrict__ dists, const long long* __restri
     const double idxf = q * (double)(W - 1);
     const int idx = (int)idxf;
     const double frac = idxf - (double)idx;
+    const int m = W - idx;                    // the order statistic `idx` is the m-th largest of the window
     for (int t = threadIdx.x; t < cnt; t += 256) {
         double vlow = 0.0, vhigh = 0.0;
-        for (int j = 0; j < W; ++j) {
-            const double v = s_v[t + j];
-            int rank = 0;
-            for (int k = 0; k < W; ++k) {
-                const double u = s_v[t + k];
-                rank += (u < v || (u == v && k < j)) ? 1 : 0;
+        if (m <= OL_TOP) {
+            // upper-tail quantile (0.95 of 51 values: the 4th and 3rd largest): keep the m largest in registers,
+            // W * m compare-exchanges instead of W * W rank comparisons
+            switch (m) {
+                case 1: top_m<1>(s_v + t, W, &vlow, &vhigh); break;
+                case 2: top_m<2>(s_v + t, W, &vlow, &vhigh); break;
+                case 3: top_m<3>(s_v + t, W, &vlow, &vhigh); break;
+                case 4: top_m<4>(s_v + t, W, &vlow, &vhigh); break;
+                case 5: top_m<5>(s_v + t, W, &vlow, &vhigh); break;
+                case 6: top_m<6>(s_v + t, W, &vlow, &vhigh); break;
+                case 7: top_m<7>(s_v + t, W, &vlow, &vhigh); break;
+                default: top_m<8>(s_v + t, W, &vlow, &vhigh); break;
             }
-            if (rank == idx) vlow = v;
-            if (rank == idx + 1) vhigh = v;
+        } else {
+            for (int j = 0; j < W; ++j) {
+                const double v = s_v[t + j];
+                int rank = 0;
+                for (int k = 0; k < W; ++k) {
+                    const double u = s_v[t + k];
+                    rank += (u < v || (u == v && k < j)) ? 1 : 0;
+                }
+                if (rank == idx) vlow = v;
+                if (rank == idx + 1) vhigh = v;
+            }
         }
         const double quant = (frac == 0.0) ? vlow : __dadd_rn(vlow, __dmul_rn(__dsub_rn(vhigh, vlow), frac));
         mask[lo + i0 + t] = (dists[lo + i0 + t] > __dmul_rn(quant, factor)) ? 1 : 0;
@@ -151,7 +189,8 @@ int outlier_mask(const double* d_x, const long long* h_off, int n_arms, double q
     CNVK_LAUNCH_CHECK();
     quantile_mask_kernel<<<tiles, 256, 0, stream>>>(d_dists, d_off, d_tile_off, d_ex, n_ex, q, factor, d_mask);
     CNVK_LAUNCH_CHECK();
-    CNVK_CHECK(cudaStreamSynchronize(stream));  // the host vectors above back the async copies
+    // no synchronisation: an asynchronous copy FROM pageable host memory returns once the source has been staged, so
+    // the host vectors above may go out of scope
     return 0;
 }
 
@@ -299,35 +338,28 @@ __global__ void cbs_filter_units_kernel(const u32* __restrict__ pos, const long 
     if (a <= n_arms) units[a] = (long long)pos[arm_off[a]];     // pos has n + 1 entries: pos[n] = number of survivors
 }
 
-int cbs_input_filter(const double* d_log2, const double* d_weight, const unsigned char* d_outlier, const long long* d_arm_id,
-                     const long long* h_arm_off, int n_arms, long long n, double* d_x_out, double* d_w_out,
-                     long long* d_src_out, long long* h_units, unsigned int* h_flags, cudaStream_t stream) {
-    *h_flags = 0;
-    for (int a = 0; a <= n_arms; ++a) h_units[a] = 0;
-    if (n <= 0 || n_arms <= 0) return 0;
+// device part: survivors, source rows, *d_units_out[n_arms + 1] and *d_flags_out stay on the device (no synchronisation)
+int cbs_input_filter_enqueue(const double* d_log2, const double* d_weight, const unsigned char* d_outlier,
+                             const long long* d_arm_id, const long long* d_arm_off, int n_arms, long long n,
+                             double* d_x_out, double* d_w_out, long long* d_src_out, long long* d_units_out,
+                             unsigned int* d_flags_out, cudaStream_t stream) {
     if (n >= (1ll << 31)) { set_last_error("cbs_input_filter: too many bins"); return -2; }
     ProfScope ps(PC_OTHER, stream);
     Scratch scratch(stream);
     double *xq, *wq;
     unsigned char* keep1;
     int* arm_has_w;
-    unsigned int* flags;
     u32 *ok, *pos;
-    long long *d_off, *d_units;
     CNVK_CHECK(scratch.alloc(&xq, (size_t)n));
     CNVK_CHECK(scratch.alloc(&wq, (size_t)n));
     CNVK_CHECK(scratch.alloc(&keep1, (size_t)n));
     CNVK_CHECK(scratch.alloc(&arm_has_w, (size_t)n_arms + 2));
-    CNVK_CHECK(scratch.alloc(&flags, 1));
     CNVK_CHECK(scratch.alloc(&ok, (size_t)n + 1));
     CNVK_CHECK(scratch.alloc(&pos, (size_t)n + 1));
-    CNVK_CHECK(scratch.alloc(&d_off, (size_t)n_arms + 1));
-    CNVK_CHECK(scratch.alloc(&d_units, (size_t)n_arms + 1));
     CNVK_CHECK(cudaMemsetAsync(arm_has_w, 0, ((size_t)n_arms + 2) * sizeof(int), stream));
-    CNVK_CHECK(cudaMemsetAsync(flags, 0, sizeof(unsigned int), stream));
-    CNVK_CHECK(cudaMemcpyAsync(d_off, h_arm_off, ((size_t)n_arms + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    CNVK_CHECK(cudaMemsetAsync(d_flags_out, 0, sizeof(unsigned int), stream));
     const int have_weight = d_weight ? 1 : 0;
-    cbs_filter_mark_kernel<<<div_up(n, 256), 256, 0, stream>>>(d_log2, d_weight, d_outlier, d_arm_id, n, xq, wq, keep1, arm_has_w, flags);
+    cbs_filter_mark_kernel<<<div_up(n, 256), 256, 0, stream>>>(d_log2, d_weight, d_outlier, d_arm_id, n, xq, wq, keep1, arm_has_w, d_flags_out);
     CNVK_LAUNCH_CHECK();
     cbs_filter_ok_kernel<<<div_up(n + 1, 256), 256, 0, stream>>>(xq, wq, keep1, d_arm_id, arm_has_w, n, have_weight, ok);
     CNVK_LAUNCH_CHECK();
@@ -335,8 +367,27 @@ int cbs_input_filter(const double* d_log2, const double* d_weight, const unsigne
     if (rc) return rc;
     cbs_filter_scatter_kernel<<<div_up(n, 256), 256, 0, stream>>>(xq, wq, ok, pos, d_arm_id, arm_has_w, n, have_weight, d_x_out, d_w_out, d_src_out);
     CNVK_LAUNCH_CHECK();
-    cbs_filter_units_kernel<<<div_up(n_arms + 1, 128), 128, 0, stream>>>(pos, d_off, n_arms, d_units);
+    cbs_filter_units_kernel<<<div_up(n_arms + 1, 128), 128, 0, stream>>>(pos, d_arm_off, n_arms, d_units_out);
     CNVK_LAUNCH_CHECK();
+    return 0;
+}
+
+int cbs_input_filter(const double* d_log2, const double* d_weight, const unsigned char* d_outlier, const long long* d_arm_id,
+                     const long long* h_arm_off, int n_arms, long long n, double* d_x_out, double* d_w_out,
+                     long long* d_src_out, long long* h_units, unsigned int* h_flags, cudaStream_t stream) {
+    *h_flags = 0;
+    for (int a = 0; a <= n_arms; ++a) h_units[a] = 0;
+    if (n <= 0 || n_arms <= 0) return 0;
+    Scratch scratch(stream);
+    unsigned int* flags;
+    long long *d_off, *d_units;
+    CNVK_CHECK(scratch.alloc(&flags, 1));
+    CNVK_CHECK(scratch.alloc(&d_off, (size_t)n_arms + 1));
+    CNVK_CHECK(scratch.alloc(&d_units, (size_t)n_arms + 1));
+    CNVK_CHECK(cudaMemcpyAsync(d_off, h_arm_off, ((size_t)n_arms + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    int rc = cbs_input_filter_enqueue(d_log2, d_weight, d_outlier, d_arm_id, d_off, n_arms, n, d_x_out, d_w_out, d_src_out,
+                                      d_units, flags, stream);
+    if (rc) return rc;
     CNVK_CHECK(cudaMemcpyAsync(h_units, d_units, ((size_t)n_arms + 1) * sizeof(long long), cudaMemcpyDeviceToHost, stream));
     CNVK_CHECK(cudaMemcpyAsync(h_flags, flags, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
     CNVK_CHECK(cudaStreamSynchronize(stream));
@@ -344,28 +395,42 @@ int cbs_input_filter(const double* d_log2, const double* d_weight, const unsigne
 }
 
 // ------------------------------------------------------------------ transfer_fields sums
-// one warp per segment over its bin range [lo, hi): weight = nansum(w); depth = sum(d*w)/sum(w)
-// over non-NaN weights, or 0 when the segment carries no weight
-__global__ void __launch_bounds__(128)
+// one CTA per segment over its bin range [lo, hi): weight = nansum(w); depth = sum(d*w)/sum(w)
+// over non-NaN weights, or 0 when the segment carries no weight.  (A segment is up to a whole chromosome arm: 256
+// threads with four independent loads in flight each, instead of one warp walking 10^4 bins.)
+__global__ void __launch_bounds__(256)
 segment_bin_sums_kernel(const double* __restrict__ depth, const double* __restrict__ weight,
                         const long long* __restrict__ lo, const long long* __restrict__ hi,
                         const long long* __restrict__ bin_end, const long long* __restrict__ seg_start, int nseg,
                         double* __restrict__ seg_weight, double* __restrict__ seg_depth) {
+    __shared__ double s_w[8], s_dw[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x * 4 + warp;
-    if (s >= nseg) return;
+    const int s = blockIdx.x;
     double sw = 0.0, sdw = 0.0;
     // nested bins (intersect.py _irange_nested, mode "outer"): rows [lo, hi) whose end lies beyond the
     // segment start; without the two optional columns every row of the range counts (_irange_simple)
     const long long s0 = bin_end ? seg_start[s] : 0;
-    for (long long k = lo[s] + lane; k < hi[s]; k += 32) {
-        if (bin_end && !(bin_end[k] > s0)) continue;
-        const double w = weight ? weight[k] : 1.0;
-        if (w == w) { sw += w; sdw += depth[k] * w; }
+    const long long k0 = lo[s], k1 = hi[s];
+    for (long long kb = k0 + threadIdx.x; kb < k1; kb += 4 * 256) {
+        double w[4], d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long k = kb + u * 256;
+            const bool ok = k < k1 && !(bin_end && !(bin_end[k] > s0));
+            w[u] = ok ? (weight ? weight[k] : 1.0) : __longlong_as_double(0x7ff8000000000000ll);
+            d[u] = ok ? depth[k] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (w[u] == w[u]) { sw += w[u]; sdw += d[u] * w[u]; }
     }
     sw = warp_sum(sw);
     sdw = warp_sum(sdw);
-    if (lane == 0) {
+    if (lane == 0) { s_w[warp] = sw; s_dw[warp] = sdw; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sw = 0.0; sdw = 0.0;
+        for (int k = 0; k < 8; ++k) { sw += s_w[k]; sdw += s_dw[k]; }
         seg_weight[s] = sw;
         seg_depth[s] = (sw > 0.0) ? sdw / sw : 0.0;
     }
@@ -376,7 +441,7 @@ int segment_bin_sums(const double* d_depth, const double* d_weight, const long l
                      double* d_seg_depth, cudaStream_t stream) {
     if (nseg <= 0) return 0;
     ProfScope ps(PC_OTHER, stream);
-    segment_bin_sums_kernel<<<div_up(nseg, 4), 128, 0, stream>>>(d_depth, d_weight, d_lo, d_hi, d_bin_end, d_seg_start, nseg, d_seg_weight, d_seg_depth);
+    segment_bin_sums_kernel<<<nseg, 256, 0, stream>>>(d_depth, d_weight, d_lo, d_hi, d_bin_end, d_seg_start, nseg, d_seg_weight, d_seg_depth);
     CNVK_LAUNCH_CHECK();
     return 0;
 }

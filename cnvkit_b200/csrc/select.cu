@@ -70,6 +70,63 @@ __device__ u64 cta_radix_select(const double* __restrict__ x, const unsigned cha
     return prefix;
 }
 
+// Register-resident variant for segments of at most SEL_K * 1024 elements (a chromosome of an exome panel, an arm of
+// a Haar level): every thread keeps its keys in registers, so the eight digit passes touch no memory but the 256-entry
+// shared histogram, and the loads of the single read pass are all in flight at once.  (The memory-walking select above
+// re-reads the segment once per digit with one dependent load per iteration: 60-90 us for a 13 k-bin chromosome
+// against ~10 us here.)
+static const int SEL_K = 16;
+
+__device__ u64 cta_radix_select_regs(const u64 (&key)[SEL_K], u32 alive, long long k, u32* s_hist, u64* s_state) {
+    u64 prefix = 0;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int d = threadIdx.x; d < 256; d += blockDim.x) s_hist[d] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < SEL_K; ++q) {
+            if (alive & (1u << q)) {
+                const u32 d = (u32)(key[q] >> shift) & 255u;
+                const u32 peers = __match_any_sync(__activemask(), d);
+                if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[d], (u32)__popc(peers));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            u32 c[8], tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { c[q] = s_hist[8 * lane + q]; tot += c[q]; }
+            u32 inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 t_ = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t_;
+            }
+            const u32 owners = __ballot_sync(0xffffffffu, (long long)inc > k);
+            const int owner = __ffs(owners) - 1;
+            if (lane == owner) {
+                long long kk = k - (long long)(inc - tot);
+                int q = 0;
+                for (; q < 7; ++q) {
+                    if (kk < (long long)c[q]) break;
+                    kk -= c[q];
+                }
+                s_state[0] = (u64)(8 * lane + q);
+                s_state[1] = (u64)kk;
+            }
+        }
+        __syncthreads();
+        const u32 dsel = (u32)s_state[0];
+        prefix |= (u64)dsel << shift;
+        k = (long long)s_state[1];
+#pragma unroll
+        for (int q = 0; q < SEL_K; ++q)
+            if ((alive & (1u << q)) && ((u32)(key[q] >> shift) & 255u) != dsel) alive &= ~(1u << q);
+        __syncthreads();
+    }
+    return prefix;
+}
+
 __global__ void __launch_bounds__(1024)
 segmented_median_kernel(const double* __restrict__ x, const unsigned char* __restrict__ use,
                         const long long* __restrict__ seg_off, double* __restrict__ med, int* __restrict__ cnt_out) {
@@ -81,13 +138,28 @@ segmented_median_kernel(const double* __restrict__ x, const unsigned char* __res
     const long long lo = seg_off[blockIdx.x], hi = seg_off[blockIdx.x + 1];
     if (threadIdx.x == 0) { s_cnt = 0; s_min_gt = ~0ull; s_cle = 0; }
     __syncthreads();
+    const bool in_regs = hi - lo <= (long long)SEL_K * 1024;
+    u64 key[SEL_K];
+    u32 alive = 0;
     long long c = 0;
-    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        if (use && !use[i]) continue;
-        const double v = x[i];
-        if (v == v) ++c;
+    if (in_regs) {
+#pragma unroll
+        for (int q = 0; q < SEL_K; ++q) {
+            const long long i = lo + (long long)q * 1024 + threadIdx.x;
+            const bool ok = i < hi && (!use || use[i]);
+            key[q] = ok ? f64_to_ordered(x[i]) : ~0ull;          // NaN maps to ~0 as well
+            if (key[q] != ~0ull) alive |= 1u << q;
+        }
+        c = __popc(alive);
+    } else {
+        for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            if (use && !use[i]) continue;
+            const double v = x[i];
+            if (v == v) ++c;
+        }
     }
-    if (c) atomicAdd((unsigned long long*)&s_cnt, (unsigned long long)c);
+    c = (long long)warp_sum_u32((u32)c);                         // a thread counts at most 2^31 / 1024 elements
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd((unsigned long long*)&s_cnt, (unsigned long long)c);
     __syncthreads();
     const long long cnt = s_cnt;
     if (cnt == 0) {
@@ -95,17 +167,26 @@ segmented_median_kernel(const double* __restrict__ x, const unsigned char* __res
         return;
     }
     const long long k1 = (cnt - 1) / 2;  // lower middle
-    const u64 key1 = cta_radix_select(x, use, lo, hi, k1, s_hist, s_state);
+    const u64 key1 = in_regs ? cta_radix_select_regs(key, alive, k1, s_hist, s_state)
+                             : cta_radix_select(x, use, lo, hi, k1, s_hist, s_state);
     double result = ordered_to_f64(key1);
     if ((cnt & 1) == 0) {
         // upper middle: key1 again if enough duplicates, else the smallest key above it
         u32 cle = 0;
         u64 mgt = ~0ull;
-        for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-            if (use && !use[i]) continue;
-            const u64 key = f64_to_ordered(x[i]);
-            if (key == ~0ull) continue;
-            if (key <= key1) ++cle; else if (key < mgt) mgt = key;
+        if (in_regs) {
+#pragma unroll
+            for (int q = 0; q < SEL_K; ++q) {
+                if (key[q] == ~0ull) continue;
+                if (key[q] <= key1) ++cle; else if (key[q] < mgt) mgt = key[q];
+            }
+        } else {
+            for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+                if (use && !use[i]) continue;
+                const u64 kk = f64_to_ordered(x[i]);
+                if (kk == ~0ull) continue;
+                if (kk <= key1) ++cle; else if (kk < mgt) mgt = kk;
+            }
         }
         if (cle) atomicAdd(&s_cle, cle);
         if (mgt != ~0ull) atomicMin((unsigned long long*)&s_min_gt, (unsigned long long)mgt);

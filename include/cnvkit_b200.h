@@ -239,6 +239,71 @@ int cnvk_cbs_input_filter_dev(const double* d_log2, const double* d_weight, cons
                               double* d_log2_out, double* d_weight_out, int64_t* d_src_rows, int64_t* unit_offsets,
                               uint32_t* flags, void* stream);
 
+/* ---- cohort fast path: a batch of samples on one shared bin set -------------------------------------------- */
+/* cnvlib/batch.py:524-566 (batch_run_sample) runs do_fix + do_segmentation for every sample against the SAME targets,
+ * antitargets and reference.  A cnvk_panel holds what depends on the bins only; all d_* members are device pointers
+ * owned by the caller, arm_off is a HOST array.  One bin set (targets or antitargets) after the reference masks of
+ * load_adjust_coverages (fix.py:226-262): */
+typedef struct cnvk_panel_group {
+    int64_t n0;                 /* rows of the sample's coverage table */
+    int64_t n;                  /* rows kept by the reference masks */
+    const int64_t* d_keep_idx;  /* [n] coverage-table row of every kept row */
+    const uint8_t* d_auto;      /* [n] autosome selector of center_all */
+    const int64_t* d_chrom_off; /* [nchrom + 1] chromosome offsets of the kept rows */
+    int32_t nchrom;
+    int32_t skip_low;           /* center_all(skip_low=...) of this group */
+    const uint32_t* d_order[3]; /* visiting orders of center_by_window for GC, edge, RepeatMasker (cnvk_trait_order_dev;
+                                   NULL = correction not applied) */
+    int64_t wing;               /* rolling-median half window of the corrections */
+} cnvk_panel_group;
+
+typedef struct cnvk_panel {
+    cnvk_panel_group grp[2];    /* targets, antitargets */
+    int64_t n;                  /* rows of the .cnr = grp[0].n + grp[1].n */
+    const int64_t* d_order;     /* [n] row of cat(targets, antitargets) found at every .cnr row (genomic order) */
+    const double* d_ref_log2;   /* [n] reference columns in .cnr row order */
+    const double* d_ref_spread;
+    const int64_t* d_start;     /* [n] */
+    const int64_t* d_end;
+    const int32_t* d_chrom_id;
+    const uint8_t* d_is_anti;
+    const uint8_t* d_auto;
+    const int64_t* d_chrom_off; /* [nchrom + 1] */
+    int32_t nchrom;
+    int32_t n_arms;
+    const int64_t* d_arm_id;    /* [n] arm of every .cnr row (GenomicArray.by_arm) */
+    const int64_t* arm_off;     /* HOST [n_arms + 1] */
+} cnvk_panel;
+
+/* status bits of cnvk_panel_prepare_dev: a flagged sample's outputs are to be discarded and the sample redone through
+ * the step-by-step entry points (which implement the reference's handling of these cases) */
+#define CNVK_PANEL_NAN_INPUT 1u       /* a NaN log2 in a coverage table: the kept set changes (fix.py:244) */
+#define CNVK_PANEL_LOW_COVERAGE 2u    /* "most bins have no or very low coverage": corrections skipped (fix.py:275) */
+#define CNVK_PANEL_NONFINITE 4u       /* a non-finite ratio reached the CBS input filter */
+#define CNVK_PANEL_QUANTISER_RANGE 8u /* a value outside the device %.6g quantiser's range */
+
+/* do_fix (fix.py:22-85) for n_samples samples, optionally followed by the CBS input preparation of
+ * segmentation/__init__.py:239-301 + cbs.py:22-35 (cnvk_outlier_mask_dev with factor skip_outliers when > 0, then
+ * cnvk_cbs_input_filter_dev), with ONE synchronisation for the whole batch.
+ * d_in[4 s + {0,1,2,3}]  : target log2, target depth, antitarget log2, antitarget depth of sample s (device, grp.n0 rows)
+ * d_out[3 s + {0,1,2}]   : .cnr log2, depth, weight of sample s (device, capacity n)
+ * d_cbs[2 s + {0,1}]     : quantised survivors log2 / weight (device, capacity n); d_src[s]: their .cnr rows
+ * unit_offsets (HOST)    : [n_samples][n_arms + 1] arm offsets of the survivors;  status (HOST): [n_samples] bits above
+ * d_cbs / d_src / unit_offsets may be NULL when want_cbs == 0. */
+int cnvk_panel_prepare_dev(const cnvk_panel* panel, int32_t n_samples, const double* const* d_in, double* const* d_out,
+                           int32_t want_cbs, double skip_outliers, double* const* d_cbs, int64_t* const* d_src,
+                           int64_t* unit_offsets, uint32_t* status, void* stream);
+
+/* Numeric part of transfer_fields (segmentation/__init__.py:401-506) for all segments of a batch.  seg (HOST) is
+ * [4][n_seg]: sample, arm, first and one-past-last survivor index (the CBS output, relative to the sample's survivors),
+ * sorted by (sample, arm, position).  Per segment: source rows of its first / last bin, start and end after the per-arm
+ * stretching (:431-437), the .cnr row range it spans (intersect.py:323-346, mode "outer"; bins must not nest) and
+ * weight = nansum(weight), depth = weighted mean depth over that range.
+ * bounds (HOST) [6][n_seg]: r_lo, r_hi, seg_start, seg_end, bin_lo, bin_hi;  sums (HOST) [2][n_seg]: weight, depth. */
+int cnvk_panel_transfer_dev(const cnvk_panel* panel, int32_t n_samples, int32_t n_seg, const int64_t* seg,
+                            const int64_t* const* d_src, const double* const* d_depth, const double* const* d_weight,
+                            int64_t* bounds, double* sums, void* stream);
+
 /* ---- coverage finalisation (the step before the path) ------------------------------ */
 /* cnvlib/coverage.py:637-643 (interval_coverages_pileup) and :403-409 (interval_coverages_bedgraph): depth =
  * basecount / (end - start) for bins of positive width, else 0; log2 = log2(depth) where depth > 0, else null_log2
