@@ -186,6 +186,12 @@ class Panel:
         self.d_arm_id = torch.from_numpy(self.arm_id).to(_dev.device())
         self.gene_codes = segmentation.factorize_genes(self.bins["gene"].to_numpy())
         self._bin_index = None           # segmetrics.BinIndex of the .cnr rows, built on first use
+        self._desc = None                # cnvk_panel descriptor of the native batch entry points, built on first use
+        # transfer_fields' simple row ranges need ascending bin ends within every arm (intersect.py:323-346)
+        step = np.diff(self.end)
+        inner = np.ones(len(step), dtype=bool)
+        inner[self.arm_off[1:-1] - 1] = False
+        self.nested_bins = bool(np.any(step[inner] < 0))
 
     # ------------------------------------------------------------------ fix
     def fix(self, target, antitarget):
@@ -401,14 +407,127 @@ class Panel:
         if list(segtab.columns[:5]) != ["chromosome", "start", "end", "gene", "log2"]:
             out.sort_columns()
         if ci:
-            # segmetrics.py:93: the bins each (stretched) segment overlaps, filtered bins included
-            if self._bin_index is None:
-                self._bin_index = segmetrics.BinIndex(self.bins)
-            b_lo, b_hi = self._bin_index.ranges(out.data)
-            c_lo, c_hi = segmetrics.bootstrap_ci(None, None, b_lo, b_hi, device_ptrs=(d_log2.data_ptr(), d_w.data_ptr()),
-                                                 stream=_dev.stream(), **ci)
-            out["ci_lo"] = c_lo.cpu().numpy()
-            out["ci_hi"] = c_hi.cpu().numpy()
+            out = self._add_ci(out, sample, ci)
+        return out
+
+    # ------------------------------------------------------------------ native batch path
+    def _descriptor(self):
+        """cnvk_panel (include/cnvkit_b200.h) over this panel's device-resident columns."""
+        if self._desc is None:
+            D = _lib.PanelDesc()
+            for k, g in enumerate((self.t, self.a)):
+                G = D.grp[k]
+                if not (g.n0 and g.n):
+                    G.n0 = G.n = 0
+                    continue
+                G.n0, G.n = g.n0, g.n
+                G.d_keep_idx, G.d_auto, G.d_chrom_off = g.d_keep_idx.data_ptr(), g.d_auto.data_ptr(), g.d_off.data_ptr()
+                G.nchrom, G.skip_low, G.wing = g.nchrom, int(bool(g.skip_low)), int(g.wing)
+                for j, o in enumerate(g.d_orders):
+                    G.d_order[j] = o.data_ptr() if o is not None else None
+            D.n = self.n
+            D.d_order = self.d_order.data_ptr()
+            D.d_ref_log2, D.d_ref_spread = self.d_rl.data_ptr(), self.d_rs.data_ptr()
+            D.d_start, D.d_end, D.d_chrom_id = self.d_start.data_ptr(), self.d_end.data_ptr(), self.d_cid.data_ptr()
+            D.d_is_anti, D.d_auto, D.d_chrom_off = self.d_anti.data_ptr(), self.d_auto.data_ptr(), self.d_off.data_ptr()
+            D.nchrom, D.n_arms = self.nchrom, len(self.arms)
+            D.d_arm_id = self.d_arm_id.data_ptr()
+            D.arm_off = self.arm_off.ctypes.data
+            self._desc = D
+        return self._desc
+
+    def _native_ok(self, method):
+        return (method == "cbs" and not self.nested_bins and self.n > 0 and self.d_cid.dtype == torch.int32
+                and all(o is None or o.dtype == torch.int32 for g in (self.t, self.a) if g.n0 and g.n for o in g.d_orders))
+
+    def _chunk_native(self, work, sids, threshold, keep_cnr, ci, skip_outliers=10):
+        """fix + CBS + transfer_fields for a batch of samples through the batch entry points: one synchronisation for
+        the fix / filter stage, the CBS level loop, one for the transfer stage; the per-sample Python work is the
+        gene join and the DataFrame.  Returns one (.cnr or None, .cns) per sample, None where the sample must take
+        the step-by-step path (NaN input, the low-coverage guard, values the device quantiser declines)."""
+        ns, n, n_arms = len(work), self.n, len(self.arms)
+        D = self._descriptor()
+        hold, in_ptrs = [], np.zeros(4 * ns, dtype=np.uint64)
+        for k, (tgt, anti) in enumerate(work):
+            cols = _cols(tgt) + _cols(anti)
+            if len(cols[0]) != self.t.n0 or len(cols[2]) != self.a.n0:
+                raise ValueError("sample tables do not match the panel's bin set")
+            for j, c in enumerate(cols):
+                t = c if torch.is_tensor(c) else _dev.up(c)
+                if t.dtype != torch.float64 or not t.is_contiguous():
+                    t = t.to(torch.float64).contiguous()
+                hold.append(t)
+                in_ptrs[4 * k + j] = t.data_ptr()
+        d_out = torch.empty((ns, 3, n), dtype=torch.float64, device=_dev.device())        # log2, depth, weight
+        d_cbs = torch.empty((ns, 2, n), dtype=torch.float64, device=_dev.device())        # quantised survivors
+        d_src = torch.empty((ns, n), dtype=torch.int64, device=_dev.device())
+        step = np.uint64(8 * n)
+        out_ptrs = np.uint64(d_out.data_ptr()) + step * np.arange(3 * ns, dtype=np.uint64)
+        cbs_ptrs = np.uint64(d_cbs.data_ptr()) + step * np.arange(2 * ns, dtype=np.uint64)
+        src_ptrs = np.uint64(d_src.data_ptr()) + step * np.arange(ns, dtype=np.uint64)
+        units = np.zeros((ns, n_arms + 1), dtype=np.int64)
+        status = np.zeros(ns, dtype=np.uint32)
+        _lib.call("cnvk_panel_prepare_dev", ctypes.addressof(D), ns, _lib.ptr(in_ptrs), _lib.ptr(out_ptrs), 1,
+                  float(skip_outliers or 0.0), _lib.ptr(cbs_ptrs), _lib.ptr(src_ptrs), _lib.ptr(units), _lib.ptr(status),
+                  _dev.stream())
+        del hold
+        good = [k for k in range(ns) if status[k] == 0]
+        results = [None] * ns
+        if not good:
+            return results
+        # ---- CBS over the survivors of every good sample (sample-major units)
+        nk = units[:, -1]
+        if len(good) == 1:
+            k = good[0]
+            X, W = d_cbs[k, 0, : nk[k]], d_cbs[k, 1, : nk[k]]
+        else:
+            X = torch.cat([d_cbs[k, 0, : nk[k]] for k in good])
+            W = torch.cat([d_cbs[k, 1, : nk[k]] for k in good])
+        bases = np.concatenate([[0], np.cumsum(nk[good])]).astype(np.int64)
+        off = np.concatenate([units[k, :-1] + bases[i] for i, k in enumerate(good)] + [bases[-1:]]).astype(np.int64)
+        u, lo, hi, mean, _st = _cbs.segment_arms(None, None, off, alpha=float(0.0001 if threshold is None else threshold),
+                                                 device_ptrs=(X.data_ptr(), W.data_ptr()), stream=_dev.stream())
+        nseg = len(u)
+        if nseg:
+            mean = np.array([float("%.15g" % m) for m in mean])
+        u = u.astype(np.int64)
+        smp = u // n_arms                     # position in `good`
+        seg = np.empty((4, nseg), dtype=np.int64)
+        seg[0] = np.asarray(good, dtype=np.int64)[smp]
+        seg[1] = u - smp * n_arms
+        seg[2] = lo - bases[smp]
+        seg[3] = hi - bases[smp]
+        bounds = np.empty((6, nseg), dtype=np.int64)
+        sums = np.empty((2, nseg), dtype=np.float64)
+        dep_ptrs = np.ascontiguousarray(out_ptrs[1::3])
+        w_ptrs = np.ascontiguousarray(out_ptrs[2::3])
+        _lib.call("cnvk_panel_transfer_dev", ctypes.addressof(D), ns, nseg, _lib.ptr(seg), _lib.ptr(src_ptrs),
+                  _lib.ptr(dep_ptrs), _lib.ptr(w_ptrs), _lib.ptr(bounds), _lib.ptr(sums), _dev.stream())
+        cut = np.searchsorted(smp, np.arange(len(good) + 1))
+        for i, k in enumerate(good):
+            a, b = int(cut[i]), int(cut[i + 1])
+            genes = segmentation._join_genes(None, bounds[4, a:b], bounds[5, a:b], self.gene_codes)
+            segtab = pd.DataFrame({
+                "chromosome": self.chrom[bounds[0, a:b]], "start": bounds[2, a:b], "end": bounds[3, a:b], "gene": genes,
+                "log2": mean[a:b], "depth": sums[1, a:b], "probes": seg[3, a:b] - seg[2, a:b], "weight": sums[0, a:b],
+            })
+            cns = self.meta_cls(segtab, {"sample_id": sids[k]})
+            trip = (d_out[k, 0], d_out[k, 2], d_out[k, 1])               # (log2, weight, depth) as Panel.fix returns
+            if ci:
+                cns = self._add_ci(cns, trip, ci)
+            results[k] = (self.cnr_table(*trip, sample_id=sids[k]) if keep_cnr else None, cns)
+        return results
+
+    def _add_ci(self, out, trip, ci):
+        """segmetrics.py:93: the bins each (stretched) segment overlaps, filtered bins included."""
+        d_log2, d_w, _d_depth = trip
+        if self._bin_index is None:
+            self._bin_index = segmetrics.BinIndex(self.bins)
+        b_lo, b_hi = self._bin_index.ranges(out.data)
+        c_lo, c_hi = segmetrics.bootstrap_ci(None, None, b_lo, b_hi, device_ptrs=(d_log2.data_ptr(), d_w.data_ptr()),
+                                             stream=_dev.stream(), **ci)
+        out["ci_lo"] = c_lo.cpu().numpy()
+        out["ci_hi"] = c_hi.cpu().numpy()
         return out
 
     # ------------------------------------------------------------------ driver
@@ -426,8 +545,19 @@ class Panel:
                for k in range(n)]
         chunks = [list(range(i, min(i + max(int(batch), 1), n))) for i in range(0, n, max(int(batch), 1))]
 
+        native = self._native_ok(method)
+
         def do_chunk(idx):
             out, pend, pend_k = {}, [], []
+            if native:
+                fits = [k for k in idx if not (hasattr(samples[k][0], "data") and (
+                    len(samples[k][0]) != self.t.n0 or len(samples[k][1]) != self.a.n0))]
+                if fits:
+                    res = self._chunk_native([samples[k] for k in fits], [ids[k] for k in fits], threshold, keep_cnr, ci)
+                    for k, r in zip(fits, res):
+                        if r is not None:
+                            out[k] = r
+                idx = [k for k in idx if k not in out]
             for k in idx:
                 tgt, anti = samples[k]
                 if hasattr(tgt, "data") and (len(tgt) != self.t.n0 or len(anti) != self.a.n0):

@@ -201,3 +201,29 @@ def test_cohort_confidence_intervals_equal_do_segmetrics(world, tmp_path):
         tab = tabio.read(cns_path)
         assert {"ci_lo", "ci_hi"} <= set(tab.data.columns)
         assert np.isfinite(tab["ci_lo"].to_numpy()).all() and (tab["ci_lo"].to_numpy() <= tab["ci_hi"].to_numpy()).all()
+
+
+def test_cohort_batch_path_flags_and_redoes_guarded_samples(world):
+    """The batch entry point evaluates the "mostly empty" guard of load_adjust_coverages (fix.py:275) speculatively;
+    a sample that trips it is redone by the step-by-step path, next to clean samples of the same batch."""
+    from cnvkit_b200 import _lib, cohort, fix, segmentation
+
+    bins, ref, tabs = world
+    T0, A0, R = tabs[0]
+    panel = cohort.Panel(T0, A0, R)
+    assert panel._native_ok("cbs")
+    T3, A3, _ = tabs[3]
+    t3 = T3.data.copy()
+    low = np.arange(len(t3)) % 5 != 0                      # 80 % of the targets far below the coverage floor
+    t3.loc[low, "log2"] = -24.0
+    t3.loc[low, "depth"] = 0.0
+    T3low = T3.as_dataframe(t3)
+    work = [(tabs[1][0], tabs[1][1]), (T3low, A3), (tabs[2][0], tabs[2][1])]
+    res = panel._chunk_native(work, ["a", "b", "c"], None, True, None)
+    assert res[0] is not None and res[2] is not None and res[1] is None
+    got = panel.run(work, method="cbs", batch=3, keep_cnr=True, sample_ids=["a", "b", "c"])
+    for (T, A), (cnr, cns) in zip(work, got):
+        want_cnr = fix.do_fix(T, A, R)
+        assert_same(cnr, want_cnr)
+        assert_same(cns, segmentation.do_segmentation(want_cnr, "cbs"))
+    assert _lib.PANEL_LOW_COVERAGE == 2
