@@ -562,6 +562,8 @@ def run_b200(args):
         step_ms = [a.elapsed_time(b) for a, b in pairs]
         gather_ms = g0.elapsed_time(g1)
         nrows = int(len(full)) // steps if full is not None else 0
+        timed.last_steps = {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)),
+                            "max": float(np.max(step_ms))}
         return (float(np.sum(step_ms)) + gather_ms) / steps, gather_ms, res, nrows
 
     # warm-up (>= 3): allocator pools, module load, clocks, NCCL's lazy communicator set-up
@@ -575,6 +577,7 @@ def run_b200(args):
     launches0 = _lib.launch_count()
     t0 = time.time()
     ms_res, gather_ms, res, nseg_total = timed(step_resident, args.steps)
+    step_spread = dict(timed.last_steps)
     t1 = time.time()
     launches = _lib.launch_count() - launches0
     # per-kernel attribution: the same K steps again with one CUDA-event pair around every kernel class
@@ -706,6 +709,7 @@ def run_b200(args):
             "scaling": "strong" if by_arms else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg, "segments": nseg_total, "prune": prune, "numa": numa,
             "gather_ms_per_batch": gather_ms,
+            "step_ms_spread": step_spread,   # of this rank's K timed steps (value uses their sum, as the contract says)
             "e2e": {"value": nbins_total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches),

@@ -440,11 +440,10 @@ class Panel:
         return (method == "cbs" and not self.nested_bins and self.n > 0 and self.d_cid.dtype == torch.int32
                 and all(o is None or o.dtype == torch.int32 for g in (self.t, self.a) if g.n0 and g.n for o in g.d_orders))
 
-    def _chunk_native(self, work, sids, threshold, keep_cnr, ci, skip_outliers=10):
-        """fix + CBS + transfer_fields for a batch of samples through the batch entry points: one synchronisation for
-        the fix / filter stage, the CBS level loop, one for the transfer stage; the per-sample Python work is the
-        gene join and the DataFrame.  Returns one (.cnr or None, .cns) per sample, None where the sample must take
-        the step-by-step path (NaN input, the low-coverage guard, values the device quantiser declines)."""
+    def _prepare_native(self, work, want_cbs, skip_outliers=10):
+        """cnvk_panel_prepare_dev for a batch: returns the device blocks (.cnr columns [ns, 3, n] = log2, depth,
+        weight; CBS inputs [ns, 2, n]; source rows [ns, n]), their pointer tables, the survivors' arm offsets and the
+        per-sample status bits."""
         ns, n, n_arms = len(work), self.n, len(self.arms)
         D = self._descriptor()
         hold, in_ptrs = [], np.zeros(4 * ns, dtype=np.uint64)
@@ -458,19 +457,32 @@ class Panel:
                     t = t.to(torch.float64).contiguous()
                 hold.append(t)
                 in_ptrs[4 * k + j] = t.data_ptr()
-        d_out = torch.empty((ns, 3, n), dtype=torch.float64, device=_dev.device())        # log2, depth, weight
-        d_cbs = torch.empty((ns, 2, n), dtype=torch.float64, device=_dev.device())        # quantised survivors
-        d_src = torch.empty((ns, n), dtype=torch.int64, device=_dev.device())
+        dev = _dev.device()
+        d_out = torch.empty((ns, 3, n), dtype=torch.float64, device=dev)
         step = np.uint64(8 * n)
         out_ptrs = np.uint64(d_out.data_ptr()) + step * np.arange(3 * ns, dtype=np.uint64)
-        cbs_ptrs = np.uint64(d_cbs.data_ptr()) + step * np.arange(2 * ns, dtype=np.uint64)
-        src_ptrs = np.uint64(d_src.data_ptr()) + step * np.arange(ns, dtype=np.uint64)
-        units = np.zeros((ns, n_arms + 1), dtype=np.int64)
         status = np.zeros(ns, dtype=np.uint32)
-        _lib.call("cnvk_panel_prepare_dev", ctypes.addressof(D), ns, _lib.ptr(in_ptrs), _lib.ptr(out_ptrs), 1,
-                  float(skip_outliers or 0.0), _lib.ptr(cbs_ptrs), _lib.ptr(src_ptrs), _lib.ptr(units), _lib.ptr(status),
-                  _dev.stream())
+        d_cbs = d_src = cbs_ptrs = src_ptrs = units = None
+        if want_cbs:
+            d_cbs = torch.empty((ns, 2, n), dtype=torch.float64, device=dev)
+            d_src = torch.empty((ns, n), dtype=torch.int64, device=dev)
+            cbs_ptrs = np.uint64(d_cbs.data_ptr()) + step * np.arange(2 * ns, dtype=np.uint64)
+            src_ptrs = np.uint64(d_src.data_ptr()) + step * np.arange(ns, dtype=np.uint64)
+            units = np.zeros((ns, n_arms + 1), dtype=np.int64)
+        _lib.call("cnvk_panel_prepare_dev", ctypes.addressof(D), ns, _lib.ptr(in_ptrs), _lib.ptr(out_ptrs),
+                  int(bool(want_cbs)), float(skip_outliers or 0.0), _lib.ptr(cbs_ptrs), _lib.ptr(src_ptrs), _lib.ptr(units),
+                  _lib.ptr(status), _dev.stream())
         del hold
+        return d_out, d_cbs, d_src, out_ptrs, src_ptrs, units, status
+
+    def _chunk_native(self, work, sids, threshold, keep_cnr, ci, skip_outliers=10):
+        """fix + CBS + transfer_fields for a batch of samples through the batch entry points: one synchronisation for
+        the fix / filter stage, the CBS level loop, one for the transfer stage; the per-sample Python work is the
+        gene join and the DataFrame.  Returns one (.cnr or None, .cns) per sample, None where the sample must take
+        the step-by-step path (NaN input, the low-coverage guard, values the device quantiser declines)."""
+        ns, n, n_arms = len(work), self.n, len(self.arms)
+        D = self._descriptor()
+        d_out, d_cbs, d_src, out_ptrs, src_ptrs, units, status = self._prepare_native(work, True, skip_outliers)
         good = [k for k in range(ns) if status[k] == 0]
         results = [None] * ns
         if not good:

@@ -77,6 +77,34 @@ static int ensure_init() {
     return 0;
 }
 
+// parked scratch slabs (common.cuh); the vector is leaked on purpose: thread-local destructors may run after statics
+static std::mutex* g_slab_mu = new std::mutex;
+static std::vector<cnvk::ScratchSlab>* g_slabs = new std::vector<cnvk::ScratchSlab>;
+namespace cnvk {
+bool scratch_stack_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CNVK_SCRATCH_STACK");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+void scratch_slab_park(const ScratchSlab& s) {
+    std::lock_guard<std::mutex> lock(*g_slab_mu);
+    g_slabs->push_back(s);
+}
+bool scratch_slab_adopt(int device, ScratchSlab* s) {
+    std::lock_guard<std::mutex> lock(*g_slab_mu);
+    int best = -1;
+    for (size_t i = 0; i < g_slabs->size(); ++i)
+        if ((*g_slabs)[i].device == device && (best < 0 || (*g_slabs)[i].cap > (*g_slabs)[best].cap)) best = (int)i;
+    if (best < 0) return false;
+    *s = (*g_slabs)[best];
+    g_slabs->erase(g_slabs->begin() + best);
+    return true;
+}
+}  // namespace cnvk
+
 #define RC0(expr)              \
     do {                       \
         int _rc = (expr);      \

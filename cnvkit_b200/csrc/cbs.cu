@@ -2343,23 +2343,25 @@ static int grow_fill() {
     return v;
 }
 
+// Buffers of a CbsRun, grown on demand.  They live in the Scratch scope of the enclosing cbs_segment call (a stack:
+// nothing is returned before the call ends), so growing abandons the old block instead of freeing it.
+static thread_local Scratch* g_cbs_scratch = nullptr;
+
 template <typename T>
 struct Grow {
     T* p = nullptr;
     size_t cap = 0;
-    cudaStream_t s = nullptr;
     bool zero = false;            // memset new allocations to 0
-    ~Grow() { if (p) cudaFreeAsync(p, s); }
     cudaError_t ensure(size_t need, cudaStream_t stream) {
-        s = stream;
         if (need <= cap) return cudaSuccess;
-        if (p) cudaFreeAsync(p, s);
-        p = nullptr;
-        cap = need + need / 2 + 16;
-        cudaError_t e = cudaMallocAsync((void**)&p, cap * sizeof(T), s);
-        if (e != cudaSuccess) { cap = 0; return e; }
-        if (zero) e = cudaMemsetAsync(p, 0, cap * sizeof(T), s);
-        else if (grow_fill() >= 0) e = cudaMemsetAsync(p, grow_fill(), cap * sizeof(T), s);
+        const size_t ncap = need + need / 2 + 16;
+        T* np = nullptr;
+        cudaError_t e = g_cbs_scratch->alloc(&np, ncap);
+        if (e != cudaSuccess) return e;
+        p = np;
+        cap = ncap;
+        if (zero) e = cudaMemsetAsync(p, 0, cap * sizeof(T), stream);
+        else if (grow_fill() >= 0) e = cudaMemsetAsync(p, grow_fill(), cap * sizeof(T), stream);
         return e;
     }
 };
@@ -2448,7 +2450,7 @@ struct CbsRun {
         nn = (int)h_nodes.size();
         if (nn == 0) return 0;
         if (tiles_overflow(ptiles, blk_off, iblks, qtiles)) return -2;
-        CNVK_CHECK(cudaMallocAsync((void**)&d_out, sizeof(LevelOut), stream));
+        CNVK_CHECK(g_cbs_scratch->alloc(&d_out, 1));
         CNVK_CHECK(cudaMemsetAsync(d_out, 0, sizeof(Ctl), stream));
         CNVK_CHECK(extra_lo.ensure(4096, stream));
         CNVK_CHECK(extra_hi.ensure(4096, stream));
@@ -2461,7 +2463,6 @@ struct CbsRun {
         CNVK_PIN_CHECK(h_out);
         return 0;
     }
-    ~CbsRun() { if (d_out) cudaFreeAsync(d_out, stream); }
     bool active() const { return nn > 0; }
 
     int launch_frontier() {
@@ -2730,6 +2731,10 @@ int cbs_segment(const double* d_x, const double* d_w, const long long* h_off, in
 
     g_pinned.rewind();
     Scratch scratch(stream);
+    struct ScratchBind {                 // Grow buffers of the runs below allocate from `scratch`
+        explicit ScratchBind(Scratch* s) { g_cbs_scratch = s; }
+        ~ScratchBind() { g_cbs_scratch = nullptr; }
+    } scratch_bind(&scratch);
     CbsShared sh;
     int* d_sbdry;
     CNVK_CHECK(scratch.alloc(&sh.d_rw, (size_t)N));
