@@ -67,6 +67,7 @@ def parse_args():
                     help="wgs: C3 (headline, default); cohort: C5 exome cohort fix + CBS sharded by sample")
     ap.add_argument("--samples", type=int, default=1024, help="cohort size for --workload cohort")
     ap.add_argument("--workers", type=int, default=4, help="host threads (one CUDA stream each) per rank, cohort workload")
+    ap.add_argument("--cohort-batch", type=int, default=8, help="samples per segmentation call, cohort workload")
     ap.add_argument("--no-exome-leg", action="store_true", help="skip the C2 exome leg of the default run")
     ap.add_argument("--no-cohort-leg", action="store_true", help="skip the C5 cohort leg of the default run")
     ap.add_argument("--no-extra-legs", action="store_true", help="skip the cliff / public-API / C1 legs (N = 1)")
@@ -870,7 +871,7 @@ def cohort_core(args, torch, dist, dev, world, rank, local_rank, samples, steps,
         work = [source[i % n_distinct] for i in which]
         if source is pinned:
             work = [tuple({k: v.numpy() for k, v in part.items()} for part in c) for c in work]
-        res = panel.run(work, method="cbs", batch=8, workers=args.workers, sample_ids=[f"S{i}" for i in which])
+        res = panel.run(work, method="cbs", batch=args.cohort_batch, workers=args.workers, sample_ids=[f"S{i}" for i in which])
         for i, (_c, cns) in zip(which, res):
             d = cns.data
             gatherer.append([np.full(len(d), i)] + [d[c].to_numpy() for c in ("start", "end", "log2", "probes", "weight", "depth")])
@@ -922,7 +923,7 @@ def cohort_core(args, torch, dist, dev, world, rank, local_rank, samples, steps,
         "steps": steps, "warmup": 2, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"C5 cohort of {samples} C2 exome tumours ({n_distinct} distinct synthetic samples "
-                               f"cycled), fix + CBS, 8 samples per segmentation call, {args.workers} host threads / streams per rank",
+                               f"cycled), fix + CBS, {args.cohort_batch} samples per segmentation call, {args.workers} host threads / streams per rank",
                    "samples": int(samples),
                    "sharding": f"samples over {world} rank(s) in blocks; one NCCL all-gather of the .cns rows per step",
                    "l2": "inputs of one step (>= 400 MB of columns per rank) exceed the 126 MB L2",

@@ -186,6 +186,8 @@ class Panel:
         self.d_arm_id = torch.from_numpy(self.arm_id).to(_dev.device())
         self.gene_codes = segmentation.factorize_genes(self.bins["gene"].to_numpy())
         self._bin_index = None           # segmetrics.BinIndex of the .cnr rows, built on first use
+        self._pool = None                # worker threads of run(workers > 1), kept across calls
+        self._pool_size = 0
         self._desc = None                # cnvk_panel descriptor of the native batch entry points, built on first use
         # transfer_fields' simple row ranges need ascending bin ends within every arm (intersect.py:323-346)
         step = np.diff(self.end)
@@ -597,41 +599,62 @@ class Panel:
             for idx in chunks:
                 results.update(do_chunk(idx))
         else:
-            import queue
-            import threading
+            # Worker threads (one CUDA stream each) live as long as the panel.  The library keeps per-thread state --
+            # a pinned staging arena, a device scratch slab, occupancy queries -- and torch's caching allocator pools
+            # blocks per stream; with fresh threads and streams in every call, the first chunk of each worker took
+            # 55-155 ms instead of ~40 (scripts/cohort_step_probe.py).
+            pool, tls = self._executor(min(int(workers), len(chunks)))
 
-            dev = _dev.device()
-            todo = queue.Queue()
-            for idx in chunks:
-                todo.put(idx)
-            errors = []
-
-            def worker():
-                torch.cuda.set_device(dev)
-                stream = torch.cuda.Stream(device=dev)
+            def task(idx):
+                stream = tls.stream
                 with torch.cuda.stream(stream):
-                    while True:
-                        try:
-                            idx = todo.get_nowait()
-                        except queue.Empty:
-                            break
-                        try:
-                            part = do_chunk(idx)
-                            stream.synchronize()
-                            results.update(part)
-                        except Exception as exc:  # surface in the caller
-                            errors.append(exc)
-                            break
+                    part = do_chunk(idx)
+                    stream.synchronize()
+                return part
 
             torch.cuda.current_stream().synchronize()
-            threads = [threading.Thread(target=worker) for _ in range(min(int(workers), len(chunks)))]
-            for t in threads:
-                t.start()
-            for t in threads:
-                t.join()
-            if errors:
-                raise errors[0]
+            futures = [pool.submit(task, idx) for idx in chunks]
+            first_error = None
+            for f in futures:
+                try:
+                    results.update(f.result())
+                except Exception as exc:  # surface in the caller, after every worker has stopped
+                    first_error = first_error or exc
+            if first_error is not None:
+                raise first_error
         return [results[k] for k in range(n)]
+
+    def _executor(self, nthreads):
+        """Thread pool of run(workers > 1): `nthreads` persistent workers, each bound to the device with its own stream."""
+        from concurrent.futures import ThreadPoolExecutor
+        import threading
+
+        if self._pool is None or self._pool_size < nthreads:
+            if self._pool is not None:
+                self._pool.shutdown(wait=True)
+            dev = _dev.device()
+            tls = threading.local()
+
+            def init():
+                torch.cuda.set_device(dev)
+                tls.stream = torch.cuda.Stream(device=dev)
+
+            self._pool = ThreadPoolExecutor(max_workers=nthreads, initializer=init, thread_name_prefix="cnvk-panel")
+            self._pool_tls, self._pool_size = tls, nthreads
+        return self._pool, self._pool_tls
+
+    def close(self):
+        """Stop the worker threads of run(workers > 1)."""
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+
+    def __del__(self):
+        try:
+            if self._pool is not None:
+                self._pool.shutdown(wait=False)
+        except Exception:
+            pass
 
     def _as_tables(self, tgt, anti, sid):
         def one(proto, s):

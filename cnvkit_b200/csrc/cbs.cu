@@ -2383,6 +2383,10 @@ static int coop_grid(const void* fn, int threads, int sm_count, int* cache) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     *cache = per_sm * sm_count;
+    // experiment switch: cap the cooperative grids (a cooperative launch needs all its CTAs resident at once, so a
+    // full-GPU grid drains every other stream first)
+    const char* cap = getenv("CNVK_CBS_COOP_CAP");
+    if (cap && atoi(cap) > 0) *cache = std::min(*cache, atoi(cap));
     return *cache;
 }
 

@@ -137,8 +137,8 @@ struct Scratch {
         ScratchArena& A = g_scratch_arena;
         A.top = mark;
         A.vtop = vmark;
-        if (--A.depth == 0 && A.ev) {
-            if (cudaEventRecord(A.ev, stream) == cudaSuccess) A.ev_pending = true;
+        if (--A.depth == 0) {
+            if (A.ev && cudaEventRecord(A.ev, stream) == cudaSuccess) A.ev_pending = true;
             A.stream = nullptr;
         }
     }

@@ -1,5 +1,7 @@
 // Internal C++ entry points of the kernels (one per .cu file), called by capi.cu.
 #pragma once
+#include <vector>
+
 #include "prims.cuh"
 
 namespace cnvk {
@@ -57,6 +59,9 @@ int cbs_input_filter_enqueue(const double* d_log2, const double* d_weight, const
                              const long long* d_arm_id, const long long* d_arm_off, int n_arms, long long n,
                              double* d_x_out, double* d_w_out, long long* d_src_out, long long* d_units_out,
                              unsigned int* d_flags_out, cudaStream_t stream);
+int outlier_tables(const long long* h_off, int n_arms, std::vector<int>* ex_arm, std::vector<int>* tile_off);
+int outlier_mask_enqueue(const double* d_x, long long N, const long long* d_off, const int* d_tile_off, const int* d_ex,
+                         int n_ex, int tiles, double q, double factor, unsigned char* d_mask, cudaStream_t stream);
 int round_sig(const double* d_x, long long n, int digits, double* d_out, unsigned long long* h_unhandled,
               cudaStream_t stream);
 int segment_bin_sums(const double* d_depth, const double* d_weight, const long long* d_lo, const long long* d_hi,

@@ -14,6 +14,8 @@
 //   cnvk_panel_transfer_dev: segmentation/__init__.py:401-506 transfer_fields per arm -- arm-end stretching, the bin
 //                            range of every segment (intersect.py:323-346 _irange_simple, mode "outer") and the
 //                            weight / depth sums, for all segments of all samples of the batch in two launches
+#include <vector>
+
 #include "ops.cuh"
 #include "prof.cuh"
 
@@ -54,76 +56,162 @@ __global__ void merge_order_kernel(const double* __restrict__ tl, const double* 
     }
 }
 
+// ---- one sample: everything from the four coverage columns to the CBS inputs, enqueued on `stream` without a
+// synchronisation and without touching host memory (the caller synchronises once per batch)
+struct PanelTables {            // device copies of the panel's small host tables
+    long long* d_arm_off = nullptr;
+    int *d_tile_off = nullptr, *d_ex = nullptr;
+    int n_ex = 0, tiles = 0;
+};
+struct SampleIO {
+    const double* in[4];        // target log2 / depth, antitarget log2 / depth (coverage-table rows)
+    double *o_l, *o_d, *o_w;    // .cnr columns
+    double *xq, *wq;            // CBS inputs (survivors)
+    long long* src;             // .cnr rows of the survivors
+    unsigned long long* stat;   // [3]: NaN seen, bins above the coverage floor per group
+    unsigned int* fflags;       // [1]
+    long long* units;           // [n_arms + 1]
+    double* g[2][2];            // per-group work columns (grp.n each)
+    unsigned char* mask;        // outlier mask (n), nullptr = no outlier test
+};
+
+static int prepare_one(const cnvk_panel* P, const PanelTables& T, const SampleIO& io, int want_cbs, double skip_outliers,
+                       cudaStream_t stream) {
+    const long long n = P->n;
+    const int n_arms = P->n_arms;
+    CNVK_CHECK(cudaMemsetAsync(io.stat, 0, 3 * sizeof(unsigned long long), stream));
+    CNVK_CHECK(cudaMemsetAsync(io.fflags, 0, sizeof(unsigned int), stream));
+    if (want_cbs) CNVK_CHECK(cudaMemsetAsync(io.units, 0, ((size_t)n_arms + 1) * sizeof(long long), stream));
+    for (int k = 0; k < 2; ++k) {
+        const cnvk_panel_group& G = P->grp[k];
+        if (G.n0 <= 0 || G.n <= 0) continue;
+        const double* in_l = io.in[2 * k];
+        const double* in_d = io.in[2 * k + 1];
+        {
+            ProfScope ps(PC_FIX, stream);
+            nan_any_kernel<<<(int)std::min<long long>(div_up(G.n0, 256), 592), 256, 0, stream>>>(in_l, G.n0, io.stat);
+            CNVK_LAUNCH_CHECK();
+            gather_rows2_kernel<<<div_up(G.n, 256), 256, 0, stream>>>(in_l, in_d, (const long long*)G.d_keep_idx, G.n, io.g[k][0], io.g[k][1]);
+            CNVK_LAUNCH_CHECK();
+        }
+        const u32* orders[3] = {G.d_order[0], G.d_order[1], G.d_order[2]};
+        int rc = fix_group_ordered_enqueue(io.g[k][0], io.g[k][1], G.d_auto, G.n, (const long long*)G.d_chrom_off, G.nchrom,
+                                           orders, 3, G.skip_low, 1, G.wing, io.stat + 1 + k, stream);
+        if (rc) return rc;
+    }
+    if (n <= 0) return 0;
+    {
+        ProfScope ps(PC_FIX, stream);
+        merge_order_kernel<<<div_up(n, 256), 256, 0, stream>>>(io.g[0][0], io.g[0][1], io.g[1][0], io.g[1][1], P->grp[0].n,
+                                                               (const long long*)P->d_order, n, io.o_l, io.o_d);
+        CNVK_LAUNCH_CHECK();
+    }
+    int rc = fix_finish(io.o_l, io.o_d, P->d_ref_log2, P->d_ref_spread, (const long long*)P->d_start,
+                        (const long long*)P->d_end, P->d_chrom_id, P->d_is_anti, P->d_auto, n,
+                        (const long long*)P->d_chrom_off, P->nchrom, io.o_w, nullptr, stream);
+    if (rc) return rc;
+    if (!want_cbs) return 0;
+    if (io.mask) {
+        rc = outlier_mask_enqueue(io.o_l, n, T.d_arm_off, T.d_tile_off, T.d_ex, T.n_ex, T.tiles, 0.95, skip_outliers,
+                                  io.mask, stream);
+        if (rc) return rc;
+    }
+    return cbs_input_filter_enqueue(io.o_l, io.o_w, io.mask, (const long long*)P->d_arm_id, T.d_arm_off, n_arms, n, io.xq,
+                                    io.wq, io.src, io.units, io.fflags, stream);
+}
+
+// ---- per-thread plan: device copies of the panel's small host tables and the work columns of one sample, kept while
+// the same panel is served.  (Replaying the chain of a sample as a captured CUDA graph was tried -- one launch per
+// sample instead of ~110 -- and did not move the cohort throughput (811 vs 796 samples/s with 4 host threads,
+// profiles/r02aj_panel_graph.log): the cohort is not bound by the launch rate.  Removed again.)
+struct PanelPlan {
+    cnvk_panel key;
+    bool have_key = false;
+    int want_cbs = -1;
+    double skip_outliers = -1.0;
+    std::vector<long long> arm_off;
+    PanelTables T;
+    SampleIO io;
+    void* bufs[16];
+    int nbufs = 0;
+    void release() {
+        for (int i = 0; i < nbufs; ++i) cudaFree(bufs[i]);
+        nbufs = 0;
+        have_key = false;
+    }
+    ~PanelPlan() {}             // thread exit: buffers are left to the process (CUDA may already be shutting down)
+    template <typename T_>
+    cudaError_t buf(T_** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T_));
+        if (e != cudaSuccess) return e;
+        bufs[nbufs++] = p;
+        *out = (T_*)p;
+        return cudaSuccess;
+    }
+};
+static thread_local PanelPlan g_plan;
+
+static int plan_build(PanelPlan& L, const cnvk_panel* P, int want_cbs, double skip_outliers) {
+    L.release();
+    L.key = *P;
+    L.arm_off.assign(P->arm_off, P->arm_off + P->n_arms + 1);
+    L.have_key = true;
+    L.want_cbs = want_cbs;
+    L.skip_outliers = skip_outliers;
+    const long long n = std::max<long long>(P->n, 1);
+    const int n_arms = P->n_arms;
+    std::vector<int> ex_arm, tile_off;
+    L.T.tiles = outlier_tables(L.arm_off.data(), n_arms, &ex_arm, &tile_off);
+    L.T.n_ex = (int)ex_arm.size();
+    CNVK_CHECK(L.buf(&L.T.d_arm_off, (size_t)n_arms + 1));
+    CNVK_CHECK(L.buf(&L.T.d_tile_off, tile_off.size()));
+    CNVK_CHECK(L.buf(&L.T.d_ex, ex_arm.size() + 1));
+    CNVK_CHECK(cudaMemcpy(L.T.d_arm_off, L.arm_off.data(), ((size_t)n_arms + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    CNVK_CHECK(cudaMemcpy(L.T.d_tile_off, tile_off.data(), tile_off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (L.T.n_ex) CNVK_CHECK(cudaMemcpy(L.T.d_ex, ex_arm.data(), ex_arm.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SampleIO& io = L.io;
+    for (int k = 0; k < 2; ++k) {
+        CNVK_CHECK(L.buf(&io.g[k][0], (size_t)std::max<long long>(P->grp[k].n, 1)));
+        CNVK_CHECK(L.buf(&io.g[k][1], (size_t)std::max<long long>(P->grp[k].n, 1)));
+    }
+    io.mask = nullptr;
+    if (want_cbs && skip_outliers > 0.0) CNVK_CHECK(L.buf(&io.mask, (size_t)n));
+    return 0;
+}
+
 int panel_prepare(const cnvk_panel* P, int ns, const double* const* in, double* const* out, int want_cbs,
                   double skip_outliers, double* const* cbs_out, long long* const* src_out, long long* h_units,
                   unsigned int* h_status, cudaStream_t stream) {
     if (ns <= 0) return 0;
     const long long n = P->n;
     const int n_arms = P->n_arms;
+    PanelPlan& L = g_plan;
+    const bool same = L.have_key && memcmp(&L.key, P, sizeof(cnvk_panel)) == 0 && L.want_cbs == want_cbs &&
+                      L.skip_outliers == skip_outliers && (int)L.arm_off.size() == n_arms + 1 &&
+                      memcmp(L.arm_off.data(), P->arm_off, ((size_t)n_arms + 1) * sizeof(long long)) == 0;
+    if (!same) {
+        int rc = plan_build(L, P, want_cbs, skip_outliers);
+        if (rc) { L.release(); return rc; }
+    }
     Scratch scratch(stream);
     // per sample: [0] NaN seen, [1] / [2] bins above the coverage floor per group; then the filter flags
     unsigned long long* d_stat;
     unsigned int* d_fflags;
-    long long *d_units, *d_arm_off;
+    long long* d_units;
     CNVK_CHECK(scratch.alloc(&d_stat, (size_t)ns * 3));
     CNVK_CHECK(scratch.alloc(&d_fflags, (size_t)ns));
     CNVK_CHECK(scratch.alloc(&d_units, (size_t)ns * (n_arms + 1)));
-    CNVK_CHECK(scratch.alloc(&d_arm_off, (size_t)n_arms + 1));
-    CNVK_CHECK(cudaMemsetAsync(d_stat, 0, (size_t)ns * 3 * sizeof(unsigned long long), stream));
-    CNVK_CHECK(cudaMemsetAsync(d_fflags, 0, (size_t)ns * sizeof(unsigned int), stream));
-    CNVK_CHECK(cudaMemsetAsync(d_units, 0, (size_t)ns * (n_arms + 1) * sizeof(long long), stream));
-    CNVK_CHECK(cudaMemcpyAsync(d_arm_off, P->arm_off, ((size_t)n_arms + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream));
-    std::vector<long long> h_arm_off(P->arm_off, P->arm_off + n_arms + 1);
-    const long long nt = P->grp[0].n, na = P->grp[1].n;
-    double* g[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    for (int k = 0; k < 2; ++k) {
-        const long long m = P->grp[k].n;
-        CNVK_CHECK(scratch.alloc(&g[k][0], (size_t)std::max<long long>(m, 1)));
-        CNVK_CHECK(scratch.alloc(&g[k][1], (size_t)std::max<long long>(m, 1)));
-    }
-    unsigned char* d_mask = nullptr;
-    if (want_cbs && skip_outliers > 0.0) CNVK_CHECK(scratch.alloc(&d_mask, (size_t)std::max<long long>(n, 1)));
     for (int s = 0; s < ns; ++s) {
-        for (int k = 0; k < 2; ++k) {
-            const cnvk_panel_group& G = P->grp[k];
-            if (G.n0 <= 0 || G.n <= 0) continue;
-            const double* in_l = in[4 * s + 2 * k];
-            const double* in_d = in[4 * s + 2 * k + 1];
-            {
-                ProfScope ps(PC_FIX, stream);
-                nan_any_kernel<<<(int)std::min<long long>(div_up(G.n0, 256), 592), 256, 0, stream>>>(in_l, G.n0, d_stat + 3 * s);
-                CNVK_LAUNCH_CHECK();
-                gather_rows2_kernel<<<div_up(G.n, 256), 256, 0, stream>>>(in_l, in_d, (const long long*)G.d_keep_idx, G.n, g[k][0], g[k][1]);
-                CNVK_LAUNCH_CHECK();
-            }
-            const u32* orders[3] = {G.d_order[0], G.d_order[1], G.d_order[2]};
-            int rc = fix_group_ordered_enqueue(g[k][0], g[k][1], G.d_auto, G.n, (const long long*)G.d_chrom_off, G.nchrom,
-                                               orders, 3, G.skip_low, 1, G.wing, d_stat + 3 * s + 1 + k, stream);
-            if (rc) return rc;
-        }
-        double *o_l = out[3 * s], *o_d = out[3 * s + 1], *o_w = out[3 * s + 2];
-        if (n > 0) {
-            {
-                ProfScope ps(PC_FIX, stream);
-                merge_order_kernel<<<div_up(n, 256), 256, 0, stream>>>(g[0][0], g[0][1], g[1][0], g[1][1], nt,
-                                                                       (const long long*)P->d_order, n, o_l, o_d);
-                CNVK_LAUNCH_CHECK();
-            }
-            int rc = fix_finish(o_l, o_d, P->d_ref_log2, P->d_ref_spread, (const long long*)P->d_start,
-                                (const long long*)P->d_end, P->d_chrom_id, P->d_is_anti, P->d_auto, n,
-                                (const long long*)P->d_chrom_off, P->nchrom, o_w, nullptr, stream);
-            if (rc) return rc;
-            if (want_cbs) {
-                if (d_mask) {
-                    rc = outlier_mask(o_l, h_arm_off.data(), n_arms, 0.95, skip_outliers, d_mask, stream);
-                    if (rc) return rc;
-                }
-                rc = cbs_input_filter_enqueue(o_l, o_w, d_mask, (const long long*)P->d_arm_id, d_arm_off, n_arms, n,
-                                              cbs_out[2 * s], cbs_out[2 * s + 1], src_out[s],
-                                              d_units + (size_t)s * (n_arms + 1), d_fflags + s, stream);
-                if (rc) return rc;
-            }
-        }
+        SampleIO io = L.io;
+        for (int j = 0; j < 4; ++j) io.in[j] = in[4 * s + j];
+        io.o_l = out[3 * s]; io.o_d = out[3 * s + 1]; io.o_w = out[3 * s + 2];
+        if (want_cbs) { io.xq = cbs_out[2 * s]; io.wq = cbs_out[2 * s + 1]; io.src = src_out[s]; }
+        io.stat = d_stat + 3 * s;
+        io.fflags = d_fflags + s;
+        io.units = d_units + (size_t)s * (n_arms + 1);
+        int rc = prepare_one(P, L.T, io, want_cbs, skip_outliers, stream);
+        if (rc) return rc;
     }
     std::vector<unsigned long long> h_stat((size_t)ns * 3);
     std::vector<unsigned int> h_ff((size_t)ns);
@@ -132,7 +220,6 @@ int panel_prepare(const cnvk_panel* P, int ns, const double* const* in, double* 
     if (want_cbs)
         CNVK_CHECK(cudaMemcpyAsync(h_units, d_units, (size_t)ns * (n_arms + 1) * sizeof(long long), cudaMemcpyDeviceToHost, stream));
     CNVK_CHECK(cudaStreamSynchronize(stream));
-    (void)na;
     for (int s = 0; s < ns; ++s) {
         unsigned int st = 0;
         if (h_stat[3 * s]) st |= CNVK_PANEL_NAN_INPUT;

@@ -153,45 +153,60 @@ quantile_mask_kernel(const double* __restrict__ dists, const long long* __restri
     }
 }
 
+// tables of the arms that are examined (more than 50 bins, smoothing.py:458-459): tile -> arm lookup
+int outlier_tables(const long long* h_off, int n_arms, std::vector<int>* ex_arm, std::vector<int>* tile_off) {
+    int tiles = 0;
+    ex_arm->clear();
+    tile_off->clear();
+    for (int a = 0; a < n_arms; ++a) {
+        const long long n = h_off[a + 1] - h_off[a];
+        if (n > 50) {
+            ex_arm->push_back(a);
+            tile_off->push_back(tiles);
+            tiles += div_up(n, OL_TILE);
+        }
+    }
+    tile_off->push_back(tiles);
+    return tiles;
+}
+
+// device part with the tables already resident (no host memory involved: can be captured into a CUDA graph)
+int outlier_mask_enqueue(const double* d_x, long long N, const long long* d_off, const int* d_tile_off, const int* d_ex,
+                         int n_ex, int tiles, double q, double factor, u8* d_mask, cudaStream_t stream) {
+    if (N <= 0) return 0;
+    ProfScope ps(PC_OTHER, stream);
+    CNVK_CHECK(cudaMemsetAsync(d_mask, 0, (size_t)N, stream));
+    if (n_ex == 0) return 0;
+    Scratch scratch(stream);
+    double* d_dists;
+    CNVK_CHECK(scratch.alloc(&d_dists, (size_t)N));
+    savgol_dists_kernel<<<tiles, 256, 0, stream>>>(d_x, d_off, d_tile_off, d_ex, n_ex, d_dists);
+    CNVK_LAUNCH_CHECK();
+    quantile_mask_kernel<<<tiles, 256, 0, stream>>>(d_dists, d_off, d_tile_off, d_ex, n_ex, q, factor, d_mask);
+    CNVK_LAUNCH_CHECK();
+    return 0;
+}
+
 int outlier_mask(const double* d_x, const long long* h_off, int n_arms, double q, double factor, u8* d_mask,
                  cudaStream_t stream) {
     if (n_arms <= 0) return 0;
     const long long N = h_off[n_arms];
     if (N <= 0) return 0;
-    ProfScope ps(PC_OTHER, stream);
-    CNVK_CHECK(cudaMemsetAsync(d_mask, 0, (size_t)N, stream));
-    // only arms with more than 50 bins are examined (smoothing.py:458-459)
     std::vector<int> ex_arm, tile_off;
-    int tiles = 0;
-    for (int a = 0; a < n_arms; ++a) {
-        const long long n = h_off[a + 1] - h_off[a];
-        if (n > 50) {
-            ex_arm.push_back(a);
-            tile_off.push_back(tiles);
-            tiles += div_up(n, OL_TILE);
-        }
-    }
-    tile_off.push_back(tiles);
+    const int tiles = outlier_tables(h_off, n_arms, &ex_arm, &tile_off);
     const int n_ex = (int)ex_arm.size();
-    if (n_ex == 0) return 0;
     Scratch scratch(stream);
     long long* d_off;
     int *d_tile_off, *d_ex;
-    double* d_dists;
     CNVK_CHECK(scratch.alloc(&d_off, (size_t)n_arms + 1));
     CNVK_CHECK(scratch.alloc(&d_tile_off, tile_off.size()));
-    CNVK_CHECK(scratch.alloc(&d_ex, ex_arm.size()));
-    CNVK_CHECK(scratch.alloc(&d_dists, (size_t)N));
+    CNVK_CHECK(scratch.alloc(&d_ex, ex_arm.size() + 1));
+    // an asynchronous copy FROM pageable host memory returns once the source has been staged, so the host vectors
+    // may go out of scope without a synchronisation
     CNVK_CHECK(cudaMemcpyAsync(d_off, h_off, ((size_t)n_arms + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream));
     CNVK_CHECK(cudaMemcpyAsync(d_tile_off, tile_off.data(), tile_off.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-    CNVK_CHECK(cudaMemcpyAsync(d_ex, ex_arm.data(), ex_arm.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-    savgol_dists_kernel<<<tiles, 256, 0, stream>>>(d_x, d_off, d_tile_off, d_ex, n_ex, d_dists);
-    CNVK_LAUNCH_CHECK();
-    quantile_mask_kernel<<<tiles, 256, 0, stream>>>(d_dists, d_off, d_tile_off, d_ex, n_ex, q, factor, d_mask);
-    CNVK_LAUNCH_CHECK();
-    // no synchronisation: an asynchronous copy FROM pageable host memory returns once the source has been staged, so
-    // the host vectors above may go out of scope
-    return 0;
+    if (n_ex) CNVK_CHECK(cudaMemcpyAsync(d_ex, ex_arm.data(), ex_arm.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    return outlier_mask_enqueue(d_x, N, d_off, d_tile_off, d_ex, n_ex, tiles, q, factor, d_mask, stream);
 }
 
 // ------------------------------------------------------------------ "%.{digits}g" quantisation
