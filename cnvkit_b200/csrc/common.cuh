@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <stdint.h>
 #include <stdio.h>
@@ -110,7 +111,8 @@ struct Scratch {
                 if (A.base) cudaFreeAsync(A.base, s);
                 A.base = nullptr;
                 A.cap = 0;
-                const size_t ncap = A.want + A.want / 4 + (1u << 20);
+                // generous: growing means new physical memory from the driver (~10 ms for a few hundred MB)
+                const size_t ncap = std::max(A.want + A.want / 2, 2 * A.cap) + (1u << 20);
                 void* p = nullptr;
                 if (cudaMallocAsync(&p, ncap, s) == cudaSuccess) {
                     A.base = (char*)p;
