@@ -375,30 +375,8 @@ def load_sample_block(filenames, fa_fname, is_haploid_x, diploid_parx_genome, se
             fast_hash = None
     rows_logr = [d_flat.clone()]
     rows_depth = []
-    for i, fname in enumerate(filenames):
-        sample_id = fbase(fname)
-        if i == 0:
-            log2 = d1["log2"].to_numpy(dtype=np.float64)
-            depth = d1["depth"].to_numpy(dtype=np.float64) if "depth" in cnarr1 else None
-        elif fast_hash is not None:
-            logging.info("Loading %s", fname)
-            try:
-                raw, h = tabio.read_columns(fname, columns=num_cols)
-            except KeyError:
-                raw, h = None, None
-            if raw is None or h != fast_hash or len(raw["log2"]) != n or np.isnan(raw["log2"]).any():
-                raise RuntimeError(f"{fname} bins do not match those in {filenames[0]}")
-            log2, depth = raw["log2"], raw.get("depth")
-        else:
-            logging.info("Loading %s", fname)
-            cn = _read(fname)
-            if not np.array_equal(key_cols, cn.data.loc[:, ("chromosome", "start", "end", "gene")].values):
-                raise RuntimeError(f"{fname} bins do not match those in {filenames[0]}")
-            log2 = cn.data["log2"].to_numpy(dtype=np.float64)
-            depth = cn.data["depth"].to_numpy(dtype=np.float64) if "depth" in cn else None
-        d_log2 = _dev.up(log2)
-        d_depth = _dev.up(depth) if depth is not None else None
-        rows_depth.append(d_depth if d_depth is not None else torch.exp2(d_log2))
+
+    def _correct(d_log2, d_depth, sample_id):
         known = sexes.get(sample_id)
         if known is None:
             logging.warning("Cannot determine sex for sample %s; treating chrX as diploid (female)",
@@ -412,6 +390,40 @@ def load_sample_block(filenames, fa_fname, is_haploid_x, diploid_parx_genome, se
         if skipped.value:
             logging.warning("WARNING: most bins have no or very low coverage; check that the right BED file was used")
         rows_logr.append(d_log2)
+
+    for i, fname in enumerate(filenames):
+        sample_id = fbase(fname)
+        if i == 0:
+            log2 = d1["log2"].to_numpy(dtype=np.float64)
+            depth = d1["depth"].to_numpy(dtype=np.float64) if "depth" in cnarr1 else None
+        else:
+            logging.info("Loading %s", fname)
+            raw = None
+            if fast_hash is not None:
+                try:
+                    raw, h = tabio.read_columns(fname, columns=num_cols)
+                except (KeyError, _lib.CnvkError):
+                    raw, h = None, None
+                if raw is not None and (h != fast_hash or len(raw["log2"]) != n or np.isnan(raw["log2"]).any()):
+                    raw = None
+            if raw is not None:
+                log2, depth = raw["log2"], raw.get("depth")
+                d_log2 = _dev.up(log2)
+                d_depth = _dev.up(depth) if depth is not None else None
+                rows_depth.append(d_depth if d_depth is not None else torch.exp2(d_log2))
+                _correct(d_log2, d_depth, sample_id)
+                continue
+            # the byte-level hash differs (formatting, row order, a missing column, rows without log2): compare the
+            # PARSED keys as the reference does (reference.py:594-598) before declaring a mismatch
+            cn = _read(fname)
+            if not np.array_equal(key_cols, cn.data.loc[:, ("chromosome", "start", "end", "gene")].values):
+                raise RuntimeError(f"{fname} bins do not match those in {filenames[0]}")
+            log2 = cn.data["log2"].to_numpy(dtype=np.float64)
+            depth = cn.data["depth"].to_numpy(dtype=np.float64) if "depth" in cn else None
+        d_log2 = _dev.up(log2)
+        d_depth = _dev.up(depth) if depth is not None else None
+        rows_depth.append(d_depth if d_depth is not None else torch.exp2(d_log2))
+        _correct(d_log2, d_depth, sample_id)
     ref_df = pd.DataFrame.from_dict(ref_columns)
     return ref_df, torch.stack(rows_logr).contiguous(), torch.stack(rows_depth).contiguous()
 

@@ -84,6 +84,23 @@ def test_do_reference_errors(Rf, golden, tmp_path):
     assert len(ref) == len(golden_table(g, "normal_p2-5_5_target"))
 
 
+def test_do_reference_accepts_files_that_differ_in_formatting_only(Rf, golden, tmp_path):
+    """The fast path compares a hash of the raw coordinate / gene bytes; a file whose rows are in another order (or
+    lacks the depth column) parses to the same bins, and the reference -- which compares parsed keys,
+    reference.py:594-598 -- accepts it.  So must we: same table as from the files as written."""
+    import pandas as pd
+
+    g, tfn, afn = write_normals(golden, str(tmp_path))
+    sexes = {str(k): bool(v) for k, v in zip(g["ref_sex_ids"], g["ref_sex_is_female"])}
+    want = Rf.do_reference(tfn, afn, is_haploid_x_reference=True, sexes=sexes)
+    # second target file: rows reversed; third antitarget file (if any): rows reversed as well
+    for path in (tfn[1], afn[-1]):
+        df = pd.read_csv(path, sep="\t", dtype={"chromosome": str})
+        df.iloc[::-1].to_csv(path, sep="\t", index=False, float_format="%.6g")
+    got = Rf.do_reference(tfn, afn, is_haploid_x_reference=True, sexes=sexes)
+    pd.testing.assert_frame_equal(got.data, want.data, check_exact=True)
+
+
 def test_full_pipeline_reference_fix_segment(Rf, golden, tmp_path):
     """test_regression.py end to end on the GPU path: reference -> fix -> segment(haar)."""
     from cnvkit_b200 import fix, segmentation
