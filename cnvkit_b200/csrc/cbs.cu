@@ -135,7 +135,7 @@ struct Ctl {
     // lists of this level
     int n_need, n_hyb, n_exact, n_flank, n_fperm, n_act;
     int qcount, qpop;              // tile queue of the arc scan
-    int pad0;
+    int chunk_done;                // CTAs that finished their share of the current permutation chunk (perm_chunk_end)
     long long bins_next;           // bins of the next level's nodes (prep work counter)
     unsigned long long stats[8];   // [0] sub-tiles scanned [1] tested [2] band pairs [3] perm nodes [4] perms run
                                    // [5] perm arcs [6] flank perm tests
@@ -1424,12 +1424,12 @@ static const int PERM_THREADS = 256;
 // an exceedance raises nrej and the boundary index kk; nrej > nrejc -> no split; np >= sbdry[kk] -> split.  Between
 // two exceedances kk does not change, so a run of clean permutations is decided by one comparison.
 __device__ void perm_decide(const PermArgs& A, const unsigned long long* pm, int n_act, int p0, int chunk, int cur,
-                            bool hybrid) {
+                            bool hybrid, int cta, int nctas) {
     const int* act_cur = A.act + (size_t)cur * A.cap;
     const int lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
     const bool last_chunk = p0 + chunk >= A.nperm;
-    for (int a = blockIdx.x * warps + (threadIdx.x >> 5); a < n_act; a += gridDim.x * warps) {
+    for (int a = cta * warps + (threadIdx.x >> 5); a < n_act; a += nctas * warps) {
         const int node = act_cur[a];
         Node* nd = &A.nodes[node];
         const int n = nd->hi - nd->lo, nrejc = nd->nrejc;
@@ -1503,6 +1503,40 @@ __device__ void perm_compact(const PermArgs& A, int n_act, int chunk, int cur, b
         __threadfence();
         A.ctl->n_act = m;
     }
+}
+
+// End of a permutation chunk.  With few active nodes (one warp each fits in a CTA -- the usual case: a level holds a
+// handful of nodes that need permutations) the LAST CTA to finish its share of the chunk replays the stopping rule
+// and compacts the list alone, and the grid meets once; a grid-wide barrier costs about as much as these nodes'
+// replay, and the three-phase form below (replay spread over all CTAs, compaction by CTA 0) pays three of them.
+__device__ __forceinline__ void perm_chunk_end(cg::grid_group& grid, const PermArgs& A, const unsigned long long* pm,
+                                               int n_act, int p0, int chunk, int cur, bool hybrid, int* s_cnt,
+                                               int* s_warp, int* s_last) {
+    const int warps = blockDim.x >> 5;
+    __threadfence();
+    if (n_act <= warps) {                                  // uniform over the grid
+        __syncthreads();
+        if (threadIdx.x == 0) *s_last = (atomicAdd(&A.ctl->chunk_done, 1) == (int)gridDim.x - 1) ? 1 : 0;
+        __syncthreads();
+        if (*s_last) {
+            __threadfence();
+            perm_decide(A, pm, n_act, p0, chunk, cur, hybrid, 0, 1);
+            __threadfence();
+            __syncthreads();
+            perm_compact(A, n_act, chunk, cur, hybrid, s_cnt, s_warp);
+            if (threadIdx.x == 0) A.ctl->chunk_done = 0;
+            __threadfence();
+        }
+        grid.sync();
+        return;
+    }
+    grid.sync();
+    perm_decide(A, pm, n_act, p0, chunk, cur, hybrid, blockIdx.x, gridDim.x);
+    __threadfence();
+    grid.sync();
+    if (blockIdx.x == 0) perm_compact(A, n_act, chunk, cur, hybrid, s_cnt, s_warp);
+    __threadfence();
+    grid.sync();
 }
 
 // rare path of the hybrid statistic: this arc could reach the observed statistic -> score it exactly
@@ -1740,7 +1774,7 @@ cbs_perm_hybrid_kernel(PermArgs A) {
     __shared__ double s_lim[HYB_LIM];
     __shared__ u32 s_limhi[HYB_LIM];
     __shared__ double s_best[PERM_THREADS / 32];
-    __shared__ int s_cnt, s_warp[PERM_THREADS / 32];
+    __shared__ int s_cnt, s_last, s_warp[PERM_THREADS / 32];
     __shared__ HybNodeCtx s_ctx;
     const int n_list = A.ctl->n_hyb;
     if (n_list == 0) return;                               // uniform over the grid
@@ -1806,15 +1840,8 @@ cbs_perm_hybrid_kernel(PermArgs A) {
             const long long z = (long long)n_act * chunk_for(nsched, n_act, A.pm_entries, A.nperm);
             for (long long k = gtid; k < z && k < A.pm_entries; k += gsize) pm_next[k] = 0ull;
         }
-        __threadfence();
-        grid.sync();
         if (timer) { const long long t = clock64(); A.ctl->tprof[2] += t - tk; tk = t; A.ctl->tprof[4] += 1; }
-        perm_decide(A, pm, n_act, p0, chunk, cur, true);
-        __threadfence();
-        grid.sync();
-        if (blockIdx.x == 0) perm_compact(A, n_act, chunk, cur, true, &s_cnt, s_warp);
-        __threadfence();
-        grid.sync();
+        perm_chunk_end(grid, A, pm, n_act, p0, chunk, cur, true, &s_cnt, s_warp, &s_last);
         if (timer) { const long long t = clock64(); A.ctl->tprof[3] += t - tk; tk = t; }
         p0 += chunk;
         sched = min(sched * 4, PERM_CHUNK_MAX);
@@ -1829,7 +1856,7 @@ cbs_perm_exact_kernel(PermArgs A) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double s_S[4][EXACT_NMAX + 1];
     __shared__ double s_cw[4][EXACT_NMAX + 1];
-    __shared__ int s_cnt, s_warp[PERM_THREADS / 32];
+    __shared__ int s_cnt, s_last, s_warp[PERM_THREADS / 32];
     const int n_list = A.ctl->n_exact;
     if (n_list == 0) return;                               // uniform over the grid
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1896,14 +1923,7 @@ cbs_perm_exact_kernel(PermArgs A) {
             if (lane == 0) A.pmax[(size_t)a * chunk + c] = (unsigned long long)__double_as_longlong(best);
             __syncwarp();
         }
-        __threadfence();
-        grid.sync();
-        perm_decide(A, A.pmax, n_act, p0, chunk, cur, false);
-        __threadfence();
-        grid.sync();
-        if (blockIdx.x == 0) perm_compact(A, n_act, chunk, cur, false, &s_cnt, s_warp);
-        __threadfence();
-        grid.sync();
+        perm_chunk_end(grid, A, A.pmax, n_act, p0, chunk, cur, false, &s_cnt, s_warp, &s_last);
         p0 += chunk;
         // exact nodes are tiny (<= nmin bins): a node still undecided after 16 + 64 + 256 permutations almost always
         // runs to the stopping boundary, and the remaining permutations are only a few waves of warps -- one chunk
