@@ -692,8 +692,31 @@ template <int NA, bool MASKED>
 __device__ __forceinline__ void scan_subtiles(Cand& best, const double2* __restrict__ sj, const double* Si,
                                               const double* ci, const int* ii, int jbase, int jcount, double total,
                                               int n, int al0) {
+    int jj = 0;
+    if (NA == 1 && !MASKED) {
+        // four end points at a time against a snapshot of the running threshold (see cbs_band_kernel)
+        for (; jj + 3 < jcount; jj += 4) {
+            const double qlo = best.qlo;
+            double num[4], den[4];
+            bool hit = false;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double2 pj = sj[jj + u];
+                const double d = __dsub_rn(pj.x, Si[0]);
+                const double c = __dsub_rn(pj.y, ci[0]);
+                den[u] = __dmul_rn(c, __dsub_rn(total, c));
+                num[u] = __dmul_rn(d, d);
+                hit |= num[u] > __dmul_rn(qlo, den[u]);
+            }
+            if (hit) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (num[u] > __dmul_rn(best.qlo, den[u])) cand_update(best, num[u], den[u], ii[0], jbase + jj + u);
+            }
+        }
+    }
 #pragma unroll 2
-    for (int jj = 0; jj < jcount; ++jj) {
+    for (; jj < jcount; ++jj) {
         const double2 pj = sj[jj];
         const int j = jbase + jj;
 #pragma unroll
@@ -1030,15 +1053,50 @@ cbs_band_kernel(Node* __restrict__ nodes, const int* __restrict__ iblk_node,
             need &= need - 1;
             const int j0 = sb * BAND_SUB, j1 = min(j0 + BAND_SUB - 1, npts - 1);
             ++my_pairs;
-            for (int jl = j0; jl <= j1; ++jl) {
-                const double Sj = pS[jl], cj = pC[jl];
-                const int kw = jl - il;
-                const double d = __dsub_rn(Sj, Si);
-                const double c = __dsub_rn(cj, ci);
-                const double den = __dmul_rn(c, __dsub_rn(total, c));
-                const double num = __dmul_rn(d, d);
-                if ((unsigned)(kw - al0) <= kw_span && num > __dmul_rn(best.qlo, den))
-                    cand_update_inl(best, num, den, i, ibase + jl);
+            // every arc of this pair of sub-blocks has an admissible width (al0 <= kw <= n - al0) unless the pair
+            // touches the diagonal or the node's far end: warp-uniform, so most pairs run without the width test
+            const bool all_ok = j0 - (ssb * BAND_SUB + BAND_SUB - 1) >= al0 && j1 - ssb * BAND_SUB <= n - al0;
+            if (all_ok) {
+                // four arcs at a time against a snapshot of the running threshold: the threshold only rises, so the
+                // snapshot passes a superset and the exact test below decides -- but the four dependent chains
+                // (d, c -> den, num -> threshold * den -> compare) no longer wait for each other through best.qlo
+                int jl = j0;
+                for (; jl + 3 <= j1; jl += 4) {
+                    const double qlo = best.qlo;
+                    double num[4], den[4];
+                    bool hit = false;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double d = __dsub_rn(pS[jl + u], Si);
+                        const double c = __dsub_rn(pC[jl + u], ci);
+                        den[u] = __dmul_rn(c, __dsub_rn(total, c));
+                        num[u] = __dmul_rn(d, d);
+                        hit |= num[u] > __dmul_rn(qlo, den[u]);
+                    }
+                    if (hit) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (num[u] > __dmul_rn(best.qlo, den[u])) cand_update_inl(best, num[u], den[u], i, ibase + jl + u);
+                    }
+                }
+                for (; jl <= j1; ++jl) {
+                    const double d = __dsub_rn(pS[jl], Si);
+                    const double c = __dsub_rn(pC[jl], ci);
+                    const double den = __dmul_rn(c, __dsub_rn(total, c));
+                    const double num = __dmul_rn(d, d);
+                    if (num > __dmul_rn(best.qlo, den)) cand_update_inl(best, num, den, i, ibase + jl);
+                }
+            } else {
+                for (int jl = j0; jl <= j1; ++jl) {
+                    const double Sj = pS[jl], cj = pC[jl];
+                    const int kw = jl - il;
+                    const double d = __dsub_rn(Sj, Si);
+                    const double c = __dsub_rn(cj, ci);
+                    const double den = __dmul_rn(c, __dsub_rn(total, c));
+                    const double num = __dmul_rn(d, d);
+                    if ((unsigned)(kw - al0) <= kw_span && num > __dmul_rn(best.qlo, den))
+                        cand_update_inl(best, num, den, i, ibase + jl);
+                }
             }
         }
     }
