@@ -82,6 +82,7 @@ SIGNATURES = {
     "cnvk_cbs_getbdry": (c_int, [c_double, c_int32, c_int32, c_void_p]),
     "cnvk_cbs_input_filter_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cnvk_panel_sizeof": (c_int64, []),
     "cnvk_panel_prepare_dev": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_double, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p]),
     "cnvk_panel_transfer_dev": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -418,6 +418,8 @@ class Panel:
     def _descriptor(self):
         """cnvk_panel (include/cnvkit_b200.h) over this panel's device-resident columns."""
         if self._desc is None:
+            if int(_lib.load().cnvk_panel_sizeof()) != ctypes.sizeof(_lib.PanelDesc):
+                raise _lib.CnvkError("cnvk_panel layout differs between _lib.PanelDesc and the built library")
             D = _lib.PanelDesc()
             for k, g in enumerate((self.t, self.a)):
                 G = D.grp[k]

@@ -570,6 +570,8 @@ int cnvk_cbs_node_diag(const double* log2, const double* weight, const int64_t* 
     return hc.finish();
 }
 
+int64_t cnvk_panel_sizeof(void) { return (int64_t)sizeof(cnvk_panel); }
+
 int cnvk_panel_prepare_dev(const cnvk_panel* panel, int32_t n_samples, const double* const* d_in, double* const* d_out,
                            int32_t want_cbs, double skip_outliers, double* const* d_cbs, int64_t* const* d_src,
                            int64_t* unit_offsets, uint32_t* status, void* stream) {

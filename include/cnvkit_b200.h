@@ -282,6 +282,9 @@ typedef struct cnvk_panel {
 #define CNVK_PANEL_NONFINITE 4u       /* a non-finite ratio reached the CBS input filter */
 #define CNVK_PANEL_QUANTISER_RANGE 8u /* a value outside the device %.6g quantiser's range */
 
+/* sizeof(cnvk_panel) as this library was compiled: a binding checks its own struct definition against it */
+int64_t cnvk_panel_sizeof(void);
+
 /* do_fix (fix.py:22-85) for n_samples samples, optionally followed by the CBS input preparation of
  * segmentation/__init__.py:239-301 + cbs.py:22-35 (cnvk_outlier_mask_dev with factor skip_outliers when > 0, then
  * cnvk_cbs_input_filter_dev), with ONE synchronisation for the whole batch.

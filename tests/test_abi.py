@@ -42,3 +42,15 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(ImportError):
         _lib.load()
+
+
+def test_panel_descriptor_layout_matches_the_library():
+    """The ctypes mirror of cnvk_panel (device pointers handed to the batch entry points) must have the layout the
+    library was compiled with; the size is the canary for a reordered or resized member."""
+    import ctypes
+
+    from cnvkit_b200 import _lib
+
+    assert int(_lib.load().cnvk_panel_sizeof()) == ctypes.sizeof(_lib.PanelDesc)
+    assert ctypes.sizeof(_lib.PanelGroup) * 2 == _lib.PanelDesc.n.offset
+    assert _lib.PanelDesc.arm_off.offset + 8 == ctypes.sizeof(_lib.PanelDesc)
