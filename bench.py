@@ -874,9 +874,15 @@ def cohort_core(args, torch, dist, dev, world, rank, local_rank, samples, steps,
         if source is pinned:
             work = [tuple({k: v.numpy() for k, v in part.items()} for part in c) for c in work]
         res = panel.run(work, method="cbs", batch=args.cohort_batch, workers=args.workers, sample_ids=[f"S{i}" for i in which])
+        names = ("start", "end", "log2", "probes", "weight", "depth")
+        ids, parts = [], [[] for _ in names]
         for i, (_c, cns) in zip(which, res):
             d = cns.data
-            gatherer.append([np.full(len(d), i)] + [d[c].to_numpy() for c in ("start", "end", "log2", "probes", "weight", "depth")])
+            ids.append(np.full(len(d), i))
+            for j, c in enumerate(names):
+                parts[j].append(d[c].to_numpy())
+        if ids:     # one staged block per step instead of one per sample
+            gatherer.append([np.concatenate(ids)] + [np.concatenate(p) for p in parts])
         full = gatherer.flush(dst=0)
         return len(full) if full is not None else 0
 
