@@ -1563,16 +1563,19 @@ __device__ void perm_compact(const PermArgs& A, int n_act, int chunk, int cur, b
     }
 }
 
-// End of a permutation chunk.  With few active nodes (one warp each fits in a CTA -- the usual case: a level holds a
-// handful of nodes that need permutations) the LAST CTA to finish its share of the chunk replays the stopping rule
-// and compacts the list alone, and the grid meets once; a grid-wide barrier costs about as much as these nodes'
-// replay, and the three-phase form below (replay spread over all CTAs, compaction by CTA 0) pays three of them.
+// End of a permutation chunk.  When the replay is short (few active nodes, or the small first chunks) the LAST CTA to
+// finish its share of the chunk replays the stopping rule and compacts the list alone, and the grid meets once; a
+// grid-wide barrier costs about as much as such a replay, and the three-phase form below (replay spread over all
+// CTAs, compaction by CTA 0) pays three of them.  The exact-test kernel spent most of its 60-80 us per level in
+// barriers (2 % issue utilisation, profiles/r02fin_perm_band_full_raw.csv).
 __device__ __forceinline__ void perm_chunk_end(cg::grid_group& grid, const PermArgs& A, const unsigned long long* pm,
                                                int n_act, int p0, int chunk, int cur, bool hybrid, int* s_cnt,
                                                int* s_warp, int* s_last) {
     const int warps = blockDim.x >> 5;
     __threadfence();
-    if (n_act <= warps) {                                  // uniform over the grid
+    // the replay walks ceil(chunk / 32) groups of flags per node, ~1 us each (a dependent L2 load); two grid barriers
+    // cost ~10 us, so one CTA takes the replay as long as its warps have at most a dozen groups each
+    if ((long long)n_act * ((chunk + 31) >> 5) <= 12LL * warps) {   // uniform over the grid
         __syncthreads();
         if (threadIdx.x == 0) *s_last = (atomicAdd(&A.ctl->chunk_done, 1) == (int)gridDim.x - 1) ? 1 : 0;
         __syncthreads();
@@ -1950,13 +1953,26 @@ cbs_perm_exact_kernel(PermArgs A) {
             for (int k = lane; k <= n; k += 32) Cp[k] = pt(A.cw, lo, k);
             for (int k = lane; k < n; k += 32) Sp[k + 1] = __dmul_rn(A.y[lo + prp((u32)k)], A.rw[lo + k]);
             __syncwarp();
-            if (lane == 0) {
+            {
+                // prefix sums in a fixed blocked association (the oracle restates it: oracle/cbs_oracle.c
+                // node_perm_stat_buf): lane l sums its run of ceil(n/32) terms left to right, the run totals are
+                // accumulated left to right, prefix = offset + local prefix.  (One lane walking all n terms was a
+                // third of this kernel's time: 2 % issue utilisation in profiles/r02fin_perm_band_full_raw.csv.)
+                const int cper = (n + 31) >> 5;
+                const int k0 = lane * cper, k1 = min(k0 + cper, n);
                 double run = 0.0;
-                Sp[0] = 0.0;
-                for (int k = 1; k <= n; ++k) {
-                    run = __dadd_rn(run, Sp[k]);
-                    Sp[k] = run;
+                for (int k = k0; k < k1; ++k) {
+                    run = __dadd_rn(run, Sp[k + 1]);
+                    Sp[k + 1] = run;
                 }
+                double off = 0.0;
+#pragma unroll
+                for (int l = 0; l < 31; ++l) {
+                    const double tl = __shfl_sync(0xffffffffu, run, l);
+                    if (lane > l) off = __dadd_rn(off, tl);
+                }
+                for (int k = k0; k < k1; ++k) Sp[k + 1] = __dadd_rn(off, Sp[k + 1]);
+                if (lane == 0) Sp[0] = 0.0;
             }
             __syncwarp();
             const double total = nd.total;

@@ -596,8 +596,27 @@ static double node_perm_stat_buf(const node_t* N, double* t, const double* wn, c
         pbss = perm_stat_hybrid(N, wn, t, al0, P->kmax, st ? &st->perm_arcs : NULL);
     } else {
         double* Sp = (double*)malloc(sizeof(double) * (n + 1));
-        Sp[0] = 0.0;
-        for (int i = 0; i < n; ++i) Sp[i + 1] = Sp[i] + t[i];
+        /* Prefix sums of the permuted terms in a FIXED blocked association (32 runs of ceil(n/32) terms: each run is
+         * summed left to right from zero, the run totals are accumulated left to right, prefix = offset + local
+         * prefix) -- the association a warp uses (one run per lane, csrc/cbs.cu cbs_perm_exact_kernel), so that
+         * both sides produce the same bits.  A strictly sequential sum differs in the last place only. */
+        {
+            const int c = (n + 31) / 32;
+            double tot[32];
+            Sp[0] = 0.0;
+            for (int l = 0; l < 32; ++l) {
+                const int k0 = l * c, k1 = (k0 + c < n) ? k0 + c : n;
+                double run = 0.0;
+                for (int k = k0; k < k1; ++k) { run = run + t[k]; Sp[k + 1] = run; }
+                tot[l] = run;
+            }
+            double off = 0.0;
+            for (int l = 0; l < 32; ++l) {
+                const int k0 = l * c, k1 = (k0 + c < n) ? k0 + c : n;
+                for (int k = k0; k < k1; ++k) Sp[k + 1] = off + Sp[k + 1];
+                off = off + tot[l];
+            }
+        }
         int pi, pj;
         pbss = max_arc_full(N, Sp, al0, &pi, &pj, st ? &st->perm_arcs : NULL);
         free(Sp);
