@@ -1917,6 +1917,7 @@ cbs_perm_exact_kernel(PermArgs A) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double s_S[4][EXACT_NMAX + 1];
     __shared__ double s_cw[4][EXACT_NMAX + 1];
+    __shared__ double s_rw[4][EXACT_NMAX];
     __shared__ int s_cnt, s_last, s_warp[PERM_THREADS / 32];
     const int n_list = A.ctl->n_exact;
     if (n_list == 0) return;                               // uniform over the grid
@@ -1942,16 +1943,43 @@ cbs_perm_exact_kernel(PermArgs A) {
         const int* act = A.act + (size_t)cur * A.cap;
         const long long items = (long long)n_act * chunk;
         const long long gw = (long long)blockIdx.x * 4 + warp, nw = (long long)gridDim.x * 4;
+        int cached = -1;                                   // node whose cw / sqrt(w) this warp holds in shared memory
         for (long long it = gw; it < items; it += nw) {
             const int a = (int)(it / chunk), c = (int)(it % chunk);
             const Node nd = A.nodes[act[a]];
             const int n = nd.hi - nd.lo, lo = nd.lo;
             double* Sp = s_S[warp];
             double* Cp = s_cw[warp];
+            double* Rp = s_rw[warp];
             Prp prp;
             prp.init(A.seed, (u32)(nd.lo - nd.base), (u32)(nd.hi - nd.base), 0u, (u32)(p0 + c), (u32)n);
-            for (int k = lane; k <= n; k += 32) Cp[k] = pt(A.cw, lo, k);
-            for (int k = lane; k < n; k += 32) Sp[k + 1] = __dmul_rn(A.y[lo + prp((u32)k)], A.rw[lo + k]);
+            // consecutive items of a warp are permutations of the same node: its prefix weights and sqrt(w) stay
+            if (cached != act[a]) {
+                __syncwarp();
+                for (int k = lane; k <= n; k += 32) Cp[k] = pt(A.cw, lo, k);
+                for (int k = lane; k < n; k += 32) Rp[k] = A.rw[lo + k];
+                cached = act[a];
+            }
+            {
+                // an item is latency, not work (2 % issue utilisation with one dependent bijection + gather per
+                // iteration): all indices first, then all gathers in flight together
+                const int QN = EXACT_NMAX / 32;
+                u32 idx[QN];
+                double yv[QN];
+#pragma unroll
+                for (int q = 0; q < QN; ++q) {
+                    const int k = lane + 32 * q;
+                    idx[q] = (k < n) ? prp((u32)k) : 0u;
+                }
+#pragma unroll
+                for (int q = 0; q < QN; ++q) yv[q] = (lane + 32 * q < n) ? A.y[lo + idx[q]] : 0.0;
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < QN; ++q) {
+                    const int k = lane + 32 * q;
+                    if (k < n) Sp[k + 1] = __dmul_rn(yv[q], Rp[k]);
+                }
+            }
             __syncwarp();
             {
                 // prefix sums in a fixed blocked association (the oracle restates it: oracle/cbs_oracle.c
@@ -2696,8 +2724,9 @@ struct CbsRun {
             ProfScope ps(PC_CBS_PERM_EXACT, stream);
             pa.list = exact_list.p;
             void* args[] = {&pa};
-            // two CTAs per SM: grid.sync cost grows with the CTA count and the work is only a few waves of warps
-            const int g = std::min(coop_grid((const void*)cbs_perm_exact_kernel, 128, sm_count, &g_grid_exact), 2 * sm_count);
+            // as many CTAs as fit: an item (one permutation of one small node) is ~5 us of latency, and the last chunk
+            // of a node that goes the whole distance is ~10^4 items -- the number of resident warps sets the time
+            const int g = coop_grid((const void*)cbs_perm_exact_kernel, 128, sm_count, &g_grid_exact);
             CNVK_CHECK(cudaLaunchCooperativeKernel((const void*)cbs_perm_exact_kernel, dim3(g), dim3(128), args, 0, stream));
             CNVK_LAUNCH_CHECK();
         }
