@@ -2009,7 +2009,33 @@ cbs_perm_exact_kernel(PermArgs A) {
             for (int i = lane; i <= n - al0; i += 32) {
                 const double Si = Sp[i], ci = Cp[i];
                 const int jhi = min(n, i + (n - al0));
-                for (int j = i + al0; j <= jhi; ++j) {
+                int j = i + al0;
+                // four arcs per iteration against a snapshot of the running threshold (it only rises, so the snapshot
+                // passes a superset and the exact test below decides): the four FP64 chains overlap instead of
+                // waiting for each other through `bestlo` -- an item is ~600 dependent chains otherwise
+                for (; j + 3 <= jhi; j += 4) {
+                    const double lo_snap = bestlo;
+                    double num[4], den[4];
+                    bool hit = false;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double d = __dsub_rn(Sp[j + u], Si);
+                        const double cc = __dsub_rn(Cp[j + u], ci);
+                        den[u] = __dmul_rn(cc, __dsub_rn(total, cc));
+                        num[u] = __dmul_rn(d, d);
+                        hit |= num[u] > __dmul_rn(lo_snap, den[u]);
+                    }
+                    if (hit) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (num[u] > __dmul_rn(bestlo, den[u])) {
+                                const double q = __ddiv_rn(num[u], den[u]);
+                                if (q > best) { best = q; bestlo = q * (1.0 - 1e-12); }
+                            }
+                        }
+                    }
+                }
+                for (; j <= jhi; ++j) {
                     const double d = __dsub_rn(Sp[j], Si);
                     const double cc = __dsub_rn(Cp[j], ci);
                     const double den = __dmul_rn(cc, __dsub_rn(total, cc));
