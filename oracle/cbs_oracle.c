@@ -33,6 +33,10 @@
  *      maximum is the same, ties resolve to the smallest (i, j).
  *  (4) hwtmaxp (hybrid permutation statistic) is restated as windowed sums over circular
  *      arcs of width min.width..kmax, accumulated element by element from the arc start.
+ *  (5) wtmaxp (exact permutation statistic, nodes of <= nmin probes): the partial sums of the permuted
+ *      terms use one fixed blocked association (32 runs of ceil(n/32) terms, run totals accumulated left
+ *      to right; node_perm_stat_buf) instead of the Fortran left-to-right loop -- last-place differences,
+ *      chosen so that a warp can produce the same bits with one run per lane.
  *
  * Build: make -C oracle   (gcc -O2 -ffp-contract=off -fopenmp -shared)
  */
