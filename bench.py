@@ -570,13 +570,16 @@ def run_b200(args):
     # warm-up (>= 3): allocator pools, module load, clocks, NCCL's lazy communicator set-up
     # (the host-buffer step first: it needs the larger scratch slab, and a slab that grows inside the timed loop costs
     # one 10 ms step -- `step_ms_spread` would show it)
-    timed(step_host, 1)
-    timed(step_resident, max(args.warmup, 3))
-
+    # The clock sampler (an nvidia-smi poller on rank 0) starts BEFORE the warm-up, so that the warm-up steps run
+    # straight into the timed ones: with its 0.3 s start-up pause between them the GPU idled and the first timed step
+    # was 8-10 % slower than the median (`step_ms_spread.argmax` was always 0).
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    timed(step_host, 1)
+    timed(step_resident, max(args.warmup, 3))
+
     launches0 = _lib.launch_count()
     t0 = time.time()
     ms_res, gather_ms, res, nseg_total = timed(step_resident, args.steps)
