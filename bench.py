@@ -666,7 +666,7 @@ def run_b200(args):
         roof_perm = {
             "kernel": "cbs_perm_hybrid_kernel + cbs_perm_exact_kernel (cooperative, persistent)", "bound": "fp64",
             "achieved": perm_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": perm_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+            "frac": perm_tflops / fp64_peak if fp64_peak else None, "traffic": 192768.0,
             "peak_source": roof_scan["peak_source"],
             "algorithmic": f"3 FP64 op/arc (add, multiply, compare) x {stats['perm_arcs']} arcs of "
                            f"{stats['perms_run']} permutations over {stats['perm_nodes']} nodes",
@@ -674,7 +674,9 @@ def run_b200(args):
             "note": "the hot loop issues ONE FP64 add per arc (the multiply and compare are replaced by an integer "
                     "compare of the high word against a conservative limit), so the FP64 pipe is not the bound: the "
                     "permutation + gather prologue (~60-130 integer ops per permuted element) and, for this sample, the "
-                    "barriers of 5 chunks are; the `cliff` object holds the large-node figure (1.6 T arcs/s)",
+                    "barriers of 5 chunks are; the `cliff` object holds the large-node figure (1.6 T arcs/s); traffic = "
+                    "ncu dram bytes of the level-3 hybrid launch (profiles/r02fin_perm_band_full_raw.csv: 0.19 MB read, "
+                    "7 KB written -- the node's columns live in L2): issue active 33 %, ALU pipe 40 %, FP64 pipe 4 %",
         }
         roofline = dict({"cbs_prep": roof_prep, "cbs_perm_hybrid": roof_perm, "cbs_perm_exact": roof_perm}.get(dominant, roof_scan))
         roofline["dominant_class_by_time"] = dominant
