@@ -54,3 +54,13 @@ def test_panel_descriptor_layout_matches_the_library():
     assert int(_lib.load().cnvk_panel_sizeof()) == ctypes.sizeof(_lib.PanelDesc)
     assert ctypes.sizeof(_lib.PanelGroup) * 2 == _lib.PanelDesc.n.offset
     assert _lib.PanelDesc.arm_off.offset + 8 == ctypes.sizeof(_lib.PanelDesc)
+
+
+def test_cohort_chunk_plan_covers_every_sample_once():
+    from cnvkit_b200.cohort import _chunk_plan
+
+    for n, batch, workers in [(0, 8, 4), (1, 8, 1), (7, 8, 2), (8, 8, 4), (9, 8, 4), (1024, 8, 4), (5, 16, 1)]:
+        chunks = _chunk_plan(n, batch, workers)
+        flat = [k for c in chunks for k in c]
+        assert flat == list(range(n))
+        assert all(1 <= len(c) <= batch for c in chunks)
